@@ -1,0 +1,180 @@
+/*
+ * libsnpmatch_b200 — C ABI of the B200-native genotype-matching hot path.
+ *
+ * The reference (Gregor-Mendel-Institute/SNPmatch 5.0.1, pure Python) has no FFI layer; the
+ * operator boundary on this path is a set of NumPy-in / NumPy-out functions.  Every entry point
+ * below names the reference function it replaces (file:line relative to the reference tree).
+ * The Python host (snpmatch_b200/core/*.py) binds these with ctypes over NumPy buffers;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SNPM_E_* code; the message of the last
+ *     failure on the calling thread is snpm_last_error();
+ *   - all pointers are caller-owned, contiguous, host memory unless the name ends in _dev;
+ *   - a snpm_db is bound to ONE CUDA device and ONE stream; calls on a handle are stream-ordered
+ *     and synchronous on return (except the *_async / batch_run calls, which say so);
+ *     handles are not thread-safe;
+ *   - there is NO CPU fallback: without a CUDA device snpm_db_create fails with SNPM_E_CUDA.
+ *
+ * Genotype codes (makedb.py:59, parsers.py:32-34): 0 hom-ref, 1 hom-alt, 2 het, -1 missing.
+ * Packed form: code & 3 (3 = missing) as two bit planes; per row and per group of 32 accessions
+ * one 64-bit word, low half = bit 0 of the 32 codes, high half = bit 1 (accession g*32+j is bit j).
+ * Row stride = snpm_db_row_words() words (padded to a multiple of 2 words = 16 bytes); padding
+ * accessions are missing.
+ */
+#ifndef SNPMATCH_B200_H
+#define SNPMATCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNPM_VERSION 100           /* 0.1.0 */
+
+#define SNPM_OK            0
+#define SNPM_E_ARG        -1       /* bad argument (shape, null pointer, unsorted keys) */
+#define SNPM_E_CUDA       -2       /* CUDA runtime error / no device */
+#define SNPM_E_NOMEM      -3
+#define SNPM_E_STATE      -4       /* call order (e.g. fetch before run) */
+#define SNPM_E_ASSERT     -5       /* the reference would have tripped an assert (y > n, snpmatch.py:43) */
+
+#define SNPM_CHUNK_ROWS 1000       /* Genotyper chunk_size, snpmatch.py:173 */
+
+typedef struct snpm_db snpm_db;          /* HBM-resident packed panel (A0) */
+typedef struct snpm_batch snpm_batch;    /* one or more samples resident on the device + their results */
+
+/* ---- diagnostics ------------------------------------------------------------------------- */
+int          snpm_version(void);
+const char  *snpm_last_error(void);
+int          snpm_device_count(void);
+/* name_buf receives the device name; sm = major*10+minor; mem_bytes total global memory */
+int          snpm_device_info(int device, char *name_buf, int name_len, int *sm, int64_t *mem_bytes, int *n_sm);
+
+/* ---- A0: database container ---------------------------------------------------------------
+ * Replaces pygwas/genotype.py:534-673 (HDF5Genotype.snps/positions/chr_regions) and
+ * snp_genotype.py:26-41 (Genotype.__init__) as the thing the kernels read.
+ * positions int32[n_rows] sorted ascending inside each chromosome; chr_regions int64[n_chr,2]
+ * row ranges [start,end) in database order.  row0_global: index of this shard's first row in the
+ * whole panel (0 on a single GPU) — returned db indices are global. */
+int snpm_db_create(int device, int64_t n_rows, int32_t n_acc,
+                   const int32_t *positions, const int64_t *chr_regions, int32_t n_chr,
+                   int64_t row0_global, snpm_db **out);
+int snpm_db_destroy(snpm_db *db);
+/* streaming loaders: rows [row0, row0+n) of the shard, int8 [n, n_acc] C-order or packed words */
+int snpm_db_load_int8(snpm_db *db, int64_t row0, int64_t n, const int8_t *snps);
+int snpm_db_load_packed(snpm_db *db, int64_t row0, int64_t n, const uint64_t *packed);
+/* deterministic synthetic panel generated in HBM: code = f(seed, global row, accession), the same
+ * integer hash as snpmatch_b200/synth.py:panel_codes_cols */
+int snpm_db_fill_synthetic(snpm_db *db, uint64_t seed);
+/* read back (tests / HDF5Genotype.snps[rows,:] equivalent, snpmatch.py:222): local row indices */
+int snpm_db_read_rows_int8(snpm_db *db, const int64_t *rows, int64_t k, int8_t *out);
+int snpm_db_read_packed(snpm_db *db, int64_t row0, int64_t n, uint64_t *out);
+int64_t snpm_db_n_rows(const snpm_db *db);
+int32_t snpm_db_n_acc(const snpm_db *db);
+int32_t snpm_db_row_words(const snpm_db *db);
+int64_t snpm_db_packed_bytes(const snpm_db *db);
+/* run the handle's work on a caller-provided CUDA stream (cudaStream_t as void*); NULL = own stream */
+int snpm_db_set_stream(snpm_db *db, void *cuda_stream);
+
+/* ---- A1: (chrom,pos) join -----------------------------------------------------------------
+ * Replaces Genotype.get_common_positions (snp_genotype.py:46-68) for a sample against the
+ * resident database.  s_chrom_id[i] = index of the marker's chromosome in the database's
+ * chromosome list (after the 'chr'-stripping of parsers.py:161), -1 when absent; markers must be
+ * grouped by chromosome in database order with positions strictly ascending inside a chromosome
+ * (the reference's implicit precondition) — SNPM_E_ARG otherwise.
+ * Outputs db_idx/s_idx int64[>= n], paired, ascending in db order; *m = number of pairs.
+ * algo: 0 auto, 1 per-marker binary search, 2 merge-path. */
+int snpm_intersect(snpm_db *db, const int32_t *s_chrom_id, const int32_t *s_pos, int64_t n,
+                   int algo, int64_t *db_idx, int64_t *s_idx, int64_t *m);
+
+/* ---- A2: matchGTsAccs ---------------------------------------------------------------------
+ * Drop-in for matchGTsAccs(sampleWei, t1001snps, skip_hets_db) (snpmatch.py:74-89): k rows of
+ * int8 codes [k, n_acc] (host) and weights f64 [k,3] -> score f64[n_acc], ninfo int64[n_acc],
+ * summed in the reference's floating-point order (sequential over rows per class, then
+ * ((0+ref)+het)+alt).  Independent of any snpm_db (device = the device to run on). */
+int snpm_match_gts_accs(int device, const double *wei, const int8_t *snps, int64_t k, int32_t n_acc,
+                        int skip_hets_db, double *score, int64_t *ninfo);
+
+/* ---- A4: likelihood epilogue --------------------------------------------------------------
+ * GenotyperOutput.calculate_likelihoods (snpmatch.py:106-117) + likeliTest (:40-55) +
+ * get_fraction (:25-28): L, LR = L/nanmin(L) (nan when the minimum is <= 0 or nan); prob = y/n
+ * (nan when n <= 0).  amin_is_calc != 0 -> nanmin, else use amin.  SNPM_E_ASSERT if any y > n. */
+int snpm_calculate_likelihoods(int device, const double *scores, const double *ninfo, int64_t n_acc,
+                               int amin_is_calc, double amin, double *prob, double *L, double *LR);
+
+/* ---- A1+A2+A3+A4: Genotyper.genotyper for one or many samples ------------------------------
+ * Replaces Genotyper.genotyper (snpmatch.py:207-233) + GenotyperOutput (:94-120).
+ * A batch holds S samples: offsets int64[S+1] into the concatenated marker arrays
+ * (s_chrom_id int32, s_pos int32, wei f64 [n,3]).  Each sample is scored on its own, exactly as
+ * S separate `snpmatch inbred` runs would (README.md:9: one process per sample). */
+int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets,
+                      const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei,
+                      snpm_batch **out);
+/* replace the samples of an existing batch, reusing its device buffers (copies are queued on the
+ * db's stream; the host arrays must stay alive until the next wait/fetch) */
+int snpm_batch_upload(snpm_batch *b, int64_t n_samples, const int64_t *offsets,
+                      const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei);
+int snpm_batch_destroy(snpm_batch *b);
+/* optional Genotyper.genotyper(filter_pos_ix=...) (snpmatch.py:211-216): keep only pairs whose
+ * GLOBAL database row is in the sorted list (applies to every sample of the batch); n = 0 clears */
+int snpm_batch_set_row_filter(snpm_batch *b, const int64_t *sorted_rows, int64_t n);
+/* join + chunked scoring + per-sample totals; device work is queued on the db's stream and the
+ * call returns without waiting (inputs already resident).  mode: 0 = reference-order kernel. */
+int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode);
+/* likelihood epilogue on the (possibly all-reduced) totals; queued, not waited for */
+int snpm_batch_epilogue(snpm_batch *b);
+/* wait for the queued work; ms_device = GPU time of the last run+epilogue measured with CUDA
+ * events on the db's stream (may be NULL) */
+int snpm_batch_wait(snpm_batch *b, float *ms_device);
+/* device address of the f64 reduce buffer [S, 2*n_acc+2]: per sample score[n_acc],
+ * ninfo[n_acc] (as f64, exact), m, y>n violation count — the payload of the cross-GPU sum (8e) */
+int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles);
+/* copy results to the host (any pointer may be NULL).  score f64[S,A] (untruncated),
+ * matches int64[S,A] (= int(score), snpmatch.py:96), ninfo int64[S,A], m int64[S],
+ * prob/L/LR f64[S,A]. */
+int snpm_batch_fetch(snpm_batch *b, double *score, int64_t *matches, int64_t *ninfo, int64_t *m,
+                     double *prob, double *L, double *LR);
+/* matched pairs of sample s (global db rows, marker index inside the sample) — commonSNPs,
+ * snpmatch.py:186-187.  capacity in elements; *m receives the pair count. */
+int snpm_batch_fetch_pairs(snpm_batch *b, int64_t s, int64_t *db_idx, int64_t *s_idx, int64_t capacity, int64_t *m);
+/* per-stage device times of the last run (ms): [0] join, [1] scoring kernel, [2] combine,
+ * [3] epilogue, [4] whole run; plus the number of kernel launches in ms[5] */
+int snpm_batch_timings(snpm_batch *b, float *ms, int n);
+
+/* one-call host-buffer form of the above for a single sample (upload, run, epilogue, fetch) */
+int snpm_score(snpm_db *db, const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei, int64_t n,
+               int skip_db_hets, const int64_t *filter_rows, int64_t n_filter,
+               double *score, int64_t *matches, int64_t *ninfo, int64_t *m,
+               double *prob, double *L, double *LR);
+
+/* ---- A5+A6: CrossIdentifier.window_genotyper ----------------------------------------------
+ * Replaces csmatch.py:64-104 + get_window_data (:44-61) + genomes.get_bins_* (genomes.py:73-127)
+ * for sample 0 of the batch.  Per database chromosome c: win_count[c] windows of bin_len bp
+ * (0 when the chromosome is not in the genome JSON), first global window number win_off[c]
+ * (0-based, in genome-JSON order).  n_windows = total.  kmax int32[kmax_len]: identity table,
+ * identical <=> floor(n - x - 1) + 1 <= kmax[n] (built by the host with scipy.stats.binom.sf,
+ * snpmatch.py:57-72).  Device work is queued; fetch waits. */
+int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len,
+                           const int32_t *win_count, const int32_t *win_off, int32_t n_windows,
+                           const int32_t *kmax, int64_t kmax_len, double lr_thres);
+/* win_score f64[W,A], win_ninfo int32[W,A], win_L f64[W,A], win_LR f64[W,A],
+ * win_identical uint8[W,A], win_num_amb int32[W], win_nrows int32[W] (matched markers per window),
+ * matched_s_idx int64[capacity] in window order (matchedTarInd, csmatch.py:90) with *n_matched;
+ * totals come from snpm_batch_fetch. */
+int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninfo, double *win_L, double *win_LR,
+                             uint8_t *win_identical, int32_t *win_num_amb, int32_t *win_nrows,
+                             int64_t *matched_s_idx, int64_t capacity, int64_t *n_matched);
+
+/* ---- A7: simulated F1 pass ----------------------------------------------------------------
+ * Replaces the loop body of CrossIdentifier.match_insilico_f1s (csmatch.py:115-126) for sample 0
+ * of the batch over its whole-genome join: all n_top*(n_top-1)/2 pairs (i<j in list order) of the
+ * given accession columns.  pair_score f64[P], pair_ninfo int64[P]. */
+int snpm_batch_f1_pairs(snpm_batch *b, const int32_t *acc_idx, int32_t n_top,
+                        double *pair_score, int64_t *pair_ninfo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNPMATCH_B200_H */

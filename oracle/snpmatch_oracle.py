@@ -368,16 +368,17 @@ def f1_pair_scores(db_snps, common, s_wei, top_accs):
 # --------------------------------------------------------------------------
 # data-format helper shared by the tests (not reference behaviour)
 # --------------------------------------------------------------------------
-def pack_2bit_planes(db_snps):
+def pack_2bit_words(db_snps):
     """Reference packing used by tests to check the device packer: code = int8 & 3
-    (0 ref, 1 alt, 2 het, 3 missing); per row, granules of 128 accessions, each granule =
-    16 bytes of low bits then 16 bytes of high bits (little-endian bit order); padding
-    accessions are missing (3).  See DESIGN.md 'HBM layout'."""
+    (0 ref, 1 alt, 2 het, 3 missing); per row one uint64 per 32 accessions, low half = bit 0 of
+    the codes, high half = bit 1 (accession g*32+j is bit j); the row is padded to an even number
+    of words and padding accessions are missing (3).  See include/snpmatch_b200.h."""
     db = np.asarray(db_snps, dtype=np.int8)
     n, a = db.shape
-    g = (a + 127) // 128
-    codes = np.full((n, g * 128), 3, dtype=np.uint8)
+    words = (a + 31) // 32
+    stride = (words + 1) & ~1
+    codes = np.full((n, stride * 32), 3, dtype=np.uint8)
     codes[:, :a] = (db & 3).astype(np.uint8)
-    lo = np.packbits((codes & 1).reshape(n, g, 128), axis=2, bitorder="little")
-    hi = np.packbits((codes >> 1).reshape(n, g, 128), axis=2, bitorder="little")
-    return np.ascontiguousarray(np.concatenate([lo, hi], axis=2).reshape(n, g * 32))
+    lo = np.packbits((codes & 1).reshape(n, stride, 32), axis=2, bitorder="little").view("<u4").reshape(n, stride)
+    hi = np.packbits((codes >> 1).reshape(n, stride, 32), axis=2, bitorder="little").view("<u4").reshape(n, stride)
+    return np.ascontiguousarray(lo.astype(np.uint64) | (hi.astype(np.uint64) << np.uint64(32)))

@@ -1,0 +1,114 @@
+"""
+snpmatch_b200 — B200-native genotype-matching hot path behind SNPmatch's `inbred` / `cross` interface.
+
+The command line mirrors the reference's `snpmatch/__init__.py` for the two sub-commands on the
+matching path (`inbred`, `cross`: flags of __init__.py:44-63) plus `parser` (:88-92); the other
+sub-commands of the reference are outside this package's scope.
+"""
+import argparse
+import logging
+import os
+import os.path
+import sys
+
+__version__ = '0.1.0'
+__reference_version__ = '5.0.1'
+
+
+def setLog(logDebug):
+    log = logging.getLogger()
+    level = logging.DEBUG if logDebug else logging.ERROR
+    handler = logging.StreamHandler()
+    handler.setLevel(level)
+    handler.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+    log.setLevel(level)
+    log.addHandler(handler)
+
+
+def die(msg):
+    sys.stderr.write('Error: ' + msg + '\n')
+    sys.exit(1)
+
+
+def check_file(inFile):
+    if not inFile:
+        die("file: %s not specified" % inFile)
+    if not os.path.isfile(inFile):
+        die("input file does not exist: " + inFile)
+
+
+def snpmatch_inbred(args):
+    check_file(args['inFile'])
+    from .core import snpmatch
+    snpmatch.potatoGenotyper(args)
+
+
+def snpmatch_cross(args):
+    check_file(args['inFile'])
+    from .core import csmatch
+    csmatch.potatoCrossIdentifier(args)
+
+
+def snpmatch_parser(args):
+    check_file(args['inFile'])
+    if not args['outFile'] and os.path.isfile(args['inFile'] + ".snpmatch.npz"):
+        os.remove(args['inFile'] + ".snpmatch.npz")
+    from .core import parsers
+    parsers.potatoParser(inFile=args['inFile'], logDebug=args['logDebug'], outFile=args['outFile'])
+
+
+def get_options(description, version_message):
+    p = argparse.ArgumentParser(description=description)
+    p.add_argument('-V', '--version', action='version', version=version_message)
+    sub = p.add_subparsers(title='subcommands', description='Choose a command to run', help='Following commands are supported')
+    db_help = "Path to the SNP database: the reference's row-chunked hdf5 file (needs h5py) or a packed .npz written by Genotype.save_packed"
+    inbred = sub.add_parser('inbred', help="SNPmatch on the inbred samples")
+    inbred.add_argument("-i", "--input_file", dest="inFile", help="VCF/BED file for the variants in the sample")
+    inbred.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
+    inbred.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility; one resident copy serves both)")
+    inbred.add_argument("--refine", action="store_true", dest="refine", default=False, help="Refine scores for indistinguishable lines")
+    inbred.add_argument("--skip_db_hets", action="store_true", dest="skip_db_hets", default=False, help="Replace heterozygous calls in DB with nan during the analysis.")
+    inbred.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    inbred.add_argument("-o", "--output", dest="outFile", default="identify_inbred", help="Output file with the probability scores")
+    inbred.set_defaults(func=snpmatch_inbred)
+
+    cross = sub.add_parser('cross', help="SNPmatch on the crosses (F2s and F3s) of A. thaliana")
+    cross.add_argument("-i", "--input_file", dest="inFile", help="VCF/BED file for the variants in the sample")
+    cross.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
+    cross.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility)")
+    cross.add_argument("-b", "--binLength", dest="binLen", help="Length of bins to calculate the likelihoods", default=300000, type=int)
+    cross.add_argument("--genome", dest="genome", default="athaliana_tair10", help="Path to Reference JSON file, if you are working with non-thaliana tair10 assembly")
+    cross.add_argument("--skip_db_hets", action="store_true", dest="skip_db_hets", default=False, help="Replace heterozygous calls in DB with nan during the analysis.")
+    cross.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    cross.add_argument("-o", "--output", dest="outFile", default="identify_cross", help="Output files with the probability scores and scores along windows")
+    cross.set_defaults(func=snpmatch_cross)
+
+    parser = sub.add_parser('parser', help="parse the input file")
+    parser.add_argument("-i", "--input_file", dest="inFile", help="VCF/BED file for the variants in the sample")
+    parser.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    parser.add_argument("-o", "--output", dest="outFile", help="output + .npz file is generater required for SNPmatch")
+    parser.set_defaults(func=snpmatch_parser)
+    return p
+
+
+def main(argv=None):
+    """Exit codes as in the reference (__init__.py:155-183): 0 ok, 2 on an exception."""
+    version_message = '%%(prog)s v%s (B200 matching path of SNPmatch %s)' % (__version__, __reference_version__)
+    parser = get_options("SNPmatch genotype matching on NVIDIA B200", version_message)
+    args = vars(parser.parse_args(argv))
+    setLog(args.get('logDebug', False))
+    if 'func' not in args:
+        parser.print_help()
+        return 0
+    try:
+        args['func'](args)
+        return 0
+    except KeyboardInterrupt:
+        return 0
+    except Exception as e:
+        logging.exception(e)
+        return 2
+
+
+if __name__ == '__main__':
+    sys.exit(main())

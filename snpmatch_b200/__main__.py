@@ -1,0 +1,3 @@
+import sys
+from . import main
+sys.exit(main())

@@ -1,0 +1,818 @@
+// C ABI of libsnpmatch_b200 (include/snpmatch_b200.h): handle lifecycle, uploads, kernel launches.
+#include "common.cuh"
+#include "pack.cuh"
+#include "join.cuh"
+#include "score.cuh"
+#include "windows.cuh"
+#include "f1.cuh"
+
+namespace snpm {
+thread_local std::string g_last_error;
+
+static int grid_for(int64_t items, int threads, int n_sm, int per_sm = 16) {
+    int64_t g = ceil_div64(items, threads);
+    const int64_t cap = int64_t(n_sm) * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return int(g);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+};
+
+static int launch_score(cudaStream_t st, const ScoreArgs &a, int grid_x, bool skip_hets) {
+    int nw, yb;
+    size_t smem;
+    score_launch_shape(a.stride, &nw, &yb, &smem);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[skip_hets ? 1 : 0]) {
+        if (skip_hets) SNPM_CUDA(cudaFuncSetAttribute(k_score_segments<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        else SNPM_CUDA(cudaFuncSetAttribute(k_score_segments<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[skip_hets ? 1 : 0] = true;
+    }
+    if (grid_x <= 0) return SNPM_OK;
+    dim3 grid(grid_x, yb), block(32, nw);
+    if (skip_hets) k_score_segments<true><<<grid, block, smem, st>>>(a);
+    else k_score_segments<false><<<grid, block, smem, st>>>(a);
+    SNPM_KERNEL_CHECK();
+    return SNPM_OK;
+}
+}  // namespace snpm
+
+using namespace snpm;
+
+extern "C" {
+
+int snpm_version(void) { return SNPM_VERSION; }
+const char *snpm_last_error(void) { return g_last_error.c_str(); }
+
+int snpm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int snpm_device_info(int device, char *name_buf, int name_len, int *sm, int64_t *mem_bytes, int *n_sm) {
+    cudaDeviceProp p;
+    SNPM_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name_buf && name_len > 0) { strncpy(name_buf, p.name, size_t(name_len) - 1); name_buf[name_len - 1] = 0; }
+    if (sm) *sm = p.major * 10 + p.minor;
+    if (mem_bytes) *mem_bytes = int64_t(p.totalGlobalMem);
+    if (n_sm) *n_sm = p.multiProcessorCount;
+    return SNPM_OK;
+}
+
+// ---- A0 ------------------------------------------------------------------------------------------
+int snpm_db_create(int device, int64_t n_rows, int32_t n_acc, const int32_t *positions, const int64_t *chr_regions,
+                   int32_t n_chr, int64_t row0_global, snpm_db **out) {
+    if (!out) return fail(SNPM_E_ARG, "snpm_db_create: out is NULL");
+    *out = nullptr;
+    if (n_rows < 0 || n_rows >= (int64_t(1) << 31) || n_acc <= 0 || n_chr < 0 || (n_rows > 0 && !positions) || (n_chr > 0 && !chr_regions))
+        return fail(SNPM_E_ARG, "snpm_db_create: bad shape (n_rows=%lld n_acc=%d n_chr=%d)", (long long)n_rows, n_acc, n_chr);
+    for (int c = 0; c < n_chr; ++c) {
+        const int64_t s = chr_regions[2 * c], e = chr_regions[2 * c + 1];
+        if (s < 0 || e < s || e > n_rows) return fail(SNPM_E_ARG, "snpm_db_create: chr_regions[%d] = [%lld,%lld) outside the shard", c, (long long)s, (long long)e);
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(SNPM_E_CUDA, "snpm_db_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(SNPM_E_ARG, "snpm_db_create: device %d of %d", device, n_dev);
+    SNPM_CUDA(cudaSetDevice(device));
+    snpm_db *db = new snpm_db();
+    db->device = device;
+    db->n_rows = n_rows;
+    db->n_acc = n_acc;
+    db->n_words = (n_acc + 31) / 32;
+    db->stride = (db->n_words + 1) & ~1;
+    db->row0_global = row0_global;
+    db->n_chr = n_chr;
+    db->h_chr_regions.assign(chr_regions, chr_regions + 2 * size_t(n_chr));
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) == cudaSuccess) db->n_sm = p.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete db; return fail(SNPM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    db->own_stream = true;
+    const size_t pbytes = std::max<size_t>(size_t(n_rows) * db->stride * 8, 256);
+    e = cudaMalloc(&db->d_packed, pbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_pos, std::max<size_t>(size_t(n_rows) * 4, 256));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_chr_regions, std::max<size_t>(size_t(n_chr) * 16, 256));
+    if (e != cudaSuccess) { snpm_db_destroy(db); return fail(SNPM_E_NOMEM, "snpm_db_create: cudaMalloc of the packed panel (%zu bytes): %s", pbytes, cudaGetErrorString(e)); }
+    // every call is missing until loaded
+    e = cudaMemsetAsync(db->d_packed, 0xFF, pbytes, db->stream);
+    if (e == cudaSuccess && n_rows) e = cudaMemcpyAsync(db->d_pos, positions, size_t(n_rows) * 4, cudaMemcpyHostToDevice, db->stream);
+    if (e == cudaSuccess && n_chr) e = cudaMemcpyAsync(db->d_chr_regions, chr_regions, size_t(n_chr) * 16, cudaMemcpyHostToDevice, db->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+    if (e != cudaSuccess) { snpm_db_destroy(db); return fail(SNPM_E_CUDA, "snpm_db_create: upload: %s", cudaGetErrorString(e)); }
+    *out = db;
+    return SNPM_OK;
+}
+
+int snpm_db_destroy(snpm_db *db) {
+    if (!db) return SNPM_OK;
+    cudaSetDevice(db->device);
+    if (db->stream) cudaStreamSynchronize(db->stream);
+    if (db->d_packed) cudaFree(db->d_packed);
+    if (db->d_pos) cudaFree(db->d_pos);
+    if (db->d_chr_regions) cudaFree(db->d_chr_regions);
+    db->scratch.release();
+    if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+    return SNPM_OK;
+}
+
+int snpm_db_set_stream(snpm_db *db, void *cuda_stream) {
+    if (!db) return fail(SNPM_E_ARG, "snpm_db_set_stream: db is NULL");
+    SNPM_CUDA(cudaSetDevice(db->device));
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    if (db->own_stream) { cudaStreamDestroy(db->stream); db->own_stream = false; }
+    if (cuda_stream) db->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    else { SNPM_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking)); db->own_stream = true; }
+    return SNPM_OK;
+}
+
+int snpm_db_load_int8(snpm_db *db, int64_t row0, int64_t n, const int8_t *snps) {
+    if (!db || row0 < 0 || n < 0 || row0 + n > db->n_rows || (n > 0 && !snps)) return fail(SNPM_E_ARG, "snpm_db_load_int8: bad row range");
+    if (n == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    const int64_t max_rows = std::max<int64_t>(1, (int64_t(256) << 20) / db->n_acc);    // 256 MB staging
+    SNPM_TRY(db->scratch.ensure(size_t(std::min(n, max_rows)) * db->n_acc));
+    for (int64_t r = 0; r < n; r += max_rows) {
+        const int64_t k = std::min(max_rows, n - r);
+        SNPM_CUDA(cudaMemcpyAsync(db->scratch.p, snps + r * db->n_acc, size_t(k) * db->n_acc, cudaMemcpyHostToDevice, db->stream));
+        k_pack_int8<<<grid_for(k * db->stride * 32, 256, db->n_sm), 256, 0, db->stream>>>(
+            db->scratch.as<int8_t>(), k, db->n_acc, db->stride, db->d_packed + (row0 + r) * db->stride);
+        SNPM_KERNEL_CHECK();
+        SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    }
+    return SNPM_OK;
+}
+
+int snpm_db_load_packed(snpm_db *db, int64_t row0, int64_t n, const uint64_t *packed) {
+    if (!db || row0 < 0 || n < 0 || row0 + n > db->n_rows || (n > 0 && !packed)) return fail(SNPM_E_ARG, "snpm_db_load_packed: bad row range");
+    if (n == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    SNPM_CUDA(cudaMemcpyAsync(db->d_packed + row0 * db->stride, packed, size_t(n) * db->stride * 8, cudaMemcpyHostToDevice, db->stream));
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    return SNPM_OK;
+}
+
+int snpm_db_fill_synthetic(snpm_db *db, uint64_t seed) {
+    if (!db) return fail(SNPM_E_ARG, "snpm_db_fill_synthetic: db is NULL");
+    SNPM_CUDA(cudaSetDevice(db->device));
+    if (db->n_rows == 0) return SNPM_OK;
+    k_fill_synthetic<<<grid_for(db->n_rows * db->stride, 256, db->n_sm, 32), 256, 0, db->stream>>>(
+        db->d_packed, db->n_rows, db->n_acc, db->stride, seed, db->row0_global);
+    SNPM_KERNEL_CHECK();
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    return SNPM_OK;
+}
+
+int snpm_db_read_rows_int8(snpm_db *db, const int64_t *rows, int64_t k, int8_t *out) {
+    if (!db || k < 0 || (k > 0 && (!rows || !out))) return fail(SNPM_E_ARG, "snpm_db_read_rows_int8: bad arguments");
+    if (k == 0) return SNPM_OK;
+    for (int64_t i = 0; i < k; ++i)
+        if (rows[i] < 0 || rows[i] >= db->n_rows) return fail(SNPM_E_ARG, "snpm_db_read_rows_int8: row %lld out of range", (long long)rows[i]);
+    SNPM_CUDA(cudaSetDevice(db->device));
+    DevBuf d_rows, d_out;
+    SNPM_TRY(d_rows.ensure(size_t(k) * 8));
+    int rc = d_out.ensure(size_t(k) * db->n_acc);
+    if (rc) { d_rows.release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d_rows.p, rows, size_t(k) * 8, cudaMemcpyHostToDevice, db->stream);
+    if (e == cudaSuccess) {
+        k_unpack_rows<<<grid_for(k * db->n_acc, 256, db->n_sm), 256, 0, db->stream>>>(db->d_packed, db->stride, db->n_acc, d_rows.as<int64_t>(), k, d_out.as<int8_t>());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, size_t(k) * db->n_acc, cudaMemcpyDeviceToHost, db->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+    d_rows.release();
+    d_out.release();
+    if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_db_read_rows_int8: %s", cudaGetErrorString(e));
+    return SNPM_OK;
+}
+
+int snpm_db_read_packed(snpm_db *db, int64_t row0, int64_t n, uint64_t *out) {
+    if (!db || row0 < 0 || n < 0 || row0 + n > db->n_rows || (n > 0 && !out)) return fail(SNPM_E_ARG, "snpm_db_read_packed: bad row range");
+    if (n == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    SNPM_CUDA(cudaMemcpyAsync(out, db->d_packed + row0 * db->stride, size_t(n) * db->stride * 8, cudaMemcpyDeviceToHost, db->stream));
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    return SNPM_OK;
+}
+
+int64_t snpm_db_n_rows(const snpm_db *db) { return db ? db->n_rows : -1; }
+int32_t snpm_db_n_acc(const snpm_db *db) { return db ? db->n_acc : -1; }
+int32_t snpm_db_row_words(const snpm_db *db) { return db ? db->stride : -1; }
+int64_t snpm_db_packed_bytes(const snpm_db *db) { return db ? db->n_rows * int64_t(db->stride) * 8 : -1; }
+
+// ---- batches --------------------------------------------------------------------------------------
+static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const int32_t *chrom, const int32_t *pos, const double *wei) {
+    snpm_db *db = b->db;
+    if (S < 1 || !offsets) return fail(SNPM_E_ARG, "batch: need at least one sample and its offsets");
+    if (offsets[0] != 0) return fail(SNPM_E_ARG, "batch: offsets[0] must be 0");
+    for (int64_t s = 0; s < S; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "batch: offsets must be non-decreasing");
+    const int64_t n = offsets[S];
+    if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "batch: %lld markers exceed the 2^31 limit", (long long)n);
+    if (n > 0 && (!chrom || !pos || !wei)) return fail(SNPM_E_ARG, "batch: NULL marker arrays");
+    b->S = S;
+    b->n = n;
+    b->h_off.assign(offsets, offsets + S + 1);
+    int64_t nseg = 0;
+    for (int64_t s = 0; s < S; ++s) nseg += ceil_div64(std::min<int64_t>(offsets[s + 1] - offsets[s], db->n_rows), SNPM_CHUNK_ROWS);
+    b->nseg_cap = nseg;
+    SNPM_TRY(b->d_off.ensure(size_t(S + 1) * 8));
+    SNPM_TRY(b->d_chrom.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pos.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_wei.ensure(size_t(n) * 24));
+    cudaStream_t st = db->stream;
+    SNPM_CUDA(cudaMemcpyAsync(b->d_off.p, offsets, size_t(S + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n) {
+        SNPM_CUDA(cudaMemcpyAsync(b->d_chrom.p, chrom, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_wei.p, wei, size_t(n) * 24, cudaMemcpyHostToDevice, st));
+    }
+    b->ran = b->ran_windows = b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos,
+                      const double *wei, snpm_batch **out) {
+    if (!db || !out) return fail(SNPM_E_ARG, "snpm_batch_create: NULL handle");
+    *out = nullptr;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    snpm_batch *b = new snpm_batch();
+    b->db = db;
+    for (int i = 0; i < SNPM_N_EVENTS; ++i) {
+        if (cudaEventCreate(&b->ev[i]) != cudaSuccess) { snpm_batch_destroy(b); return fail(SNPM_E_CUDA, "cudaEventCreate failed"); }
+    }
+    if (cudaMallocHost(reinterpret_cast<void **>(&b->h_status), 8 * sizeof(int)) != cudaSuccess) {
+        snpm_batch_destroy(b);
+        return fail(SNPM_E_NOMEM, "cudaMallocHost failed");
+    }
+    int rc = batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, wei);
+    if (rc == SNPM_OK && cudaStreamSynchronize(db->stream) != cudaSuccess) rc = fail(SNPM_E_CUDA, "snpm_batch_create: upload failed");
+    if (rc != SNPM_OK) { snpm_batch_destroy(b); return rc; }
+    *out = b;
+    return SNPM_OK;
+}
+
+int snpm_batch_upload(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos,
+                      const double *wei) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload: NULL batch");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    return batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, wei);
+}
+
+int snpm_batch_destroy(snpm_batch *b) {
+    if (!b) return SNPM_OK;
+    cudaSetDevice(b->db->device);
+    cudaStreamSynchronize(b->db->stream);
+    DevBuf *bufs[] = {&b->d_off, &b->d_chrom, &b->d_pos, &b->d_wei, &b->d_filter, &b->d_match_row, &b->d_tile_cnt, &b->d_tile_off,
+                      &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
+                      &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
+                      &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
+                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out};
+    for (DevBuf *d : bufs) d->release();
+    for (int i = 0; i < SNPM_N_EVENTS; ++i)
+        if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    if (b->h_status) cudaFreeHost(b->h_status);
+    delete b;
+    return SNPM_OK;
+}
+
+int snpm_batch_set_row_filter(snpm_batch *b, const int64_t *sorted_rows, int64_t n) {
+    if (!b || n < 0 || (n > 0 && !sorted_rows)) return fail(SNPM_E_ARG, "snpm_batch_set_row_filter: bad arguments");
+    for (int64_t i = 1; i < n; ++i)
+        if (sorted_rows[i] <= sorted_rows[i - 1]) return fail(SNPM_E_ARG, "snpm_batch_set_row_filter: rows must be strictly ascending");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    b->n_filter = n;
+    if (n) {
+        SNPM_TRY(b->d_filter.ensure(size_t(n) * 8));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_filter.p, sorted_rows, size_t(n) * 8, cudaMemcpyHostToDevice, b->db->stream));
+        SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
+    }
+    return SNPM_OK;
+}
+
+// join + compaction + per-sample ranges (queued on the stream)
+static int batch_join(snpm_batch *b, int algo) {
+    snpm_db *db = b->db;
+    cudaStream_t st = db->stream;
+    const int64_t n = b->n, S = b->S;
+    const int64_t n_tiles = ceil_div64(n, JOIN_TILE);
+    SNPM_TRY(b->d_match_row.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_tile_cnt.ensure(size_t(n_tiles) * 4));
+    SNPM_TRY(b->d_tile_off.ensure(size_t(n_tiles) * 4));
+    SNPM_TRY(b->d_prefix.ensure(size_t(n + 1) * 4));
+    SNPM_TRY(b->d_pair_db.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pair_s.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pair_w.ensure(size_t(n) * 32));
+    SNPM_TRY(b->d_mstart.ensure(size_t(S + 1) * 4));
+    SNPM_TRY(b->d_seg_off.ensure(size_t(S + 1) * 4));
+    SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
+    SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
+    if (algo == 0) algo = (n / S) * 32 >= db->n_rows ? 2 : 1;
+    const int64_t *filter = b->n_filter ? b->d_filter.as<int64_t>() : nullptr;
+    if (n_tiles > 0) {
+        if (algo == 2)
+            k_join_mergepath<<<int(n_tiles), 256, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
+                                                         db->d_pos, db->d_chr_regions, db->n_chr, filter, b->n_filter, db->row0_global,
+                                                         b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>());
+        else
+            k_join_search<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
+                                                            db->d_pos, db->d_chr_regions, db->n_chr, filter, b->n_filter, db->row0_global,
+                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>());
+        SNPM_KERNEL_CHECK();
+        k_scan_tiles<<<1, 1024, 0, st>>>(b->d_tile_cnt.as<int32_t>(), n_tiles, b->d_tile_off.as<int32_t>(), b->d_prefix.as<int32_t>() + n);
+        SNPM_KERNEL_CHECK();
+        k_scatter_pairs<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_wei.as<double>(),
+                                                          b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(),
+                                                          b->d_pair_w.as<double>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 3;
+    } else {
+        SNPM_CUDA(cudaMemsetAsync(b->d_prefix.p, 0, 4, st));
+    }
+    k_sample_ranges<<<1, 1024, 0, st>>>(b->d_prefix.as<int32_t>(), b->d_off.as<int64_t>(), S, SNPM_CHUNK_ROWS, b->d_mstart.as<int32_t>(),
+                                        b->d_seg_off.as<int32_t>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    return SNPM_OK;
+}
+
+static int batch_alloc_outputs(snpm_batch *b, int64_t nseg) {
+    snpm_db *db = b->db;
+    const int64_t a_pad = int64_t(db->stride) * 32;
+    const int64_t SA = b->S * int64_t(db->n_acc);
+    SNPM_TRY(b->d_part_score.ensure(size_t(std::max<int64_t>(nseg, 1)) * a_pad * 8));
+    SNPM_TRY(b->d_part_ninfo.ensure(size_t(std::max<int64_t>(nseg, 1)) * a_pad * 4));
+    SNPM_TRY(b->d_red.ensure(size_t(b->S) * (2 * size_t(db->n_acc) + 2) * 8));
+    SNPM_TRY(b->d_matches.ensure(size_t(SA) * 8));
+    SNPM_TRY(b->d_ninfo64.ensure(size_t(SA) * 8));
+    SNPM_TRY(b->d_prob.ensure(size_t(SA) * 8));
+    SNPM_TRY(b->d_L.ensure(size_t(SA) * 8));
+    SNPM_TRY(b->d_LR.ensure(size_t(SA) * 8));
+    return SNPM_OK;
+}
+
+static void rec(snpm_batch *b, int which) {
+    cudaEventRecord(b->ev[which], b->db->stream);
+    b->ev_rec[which] = true;
+}
+
+int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_run: NULL batch");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const int kernel_mode = mode & 0xff, algo = (mode >> 8) & 0xff;
+    if (kernel_mode != 0) return fail(SNPM_E_ARG, "snpm_batch_run: unknown kernel mode %d", kernel_mode);
+    if (algo > 2) return fail(SNPM_E_ARG, "snpm_batch_run: unknown join algorithm %d", algo);
+    b->launches = 0;
+    for (int i = 0; i < SNPM_N_EVENTS; ++i) b->ev_rec[i] = false;
+    SNPM_TRY(batch_alloc_outputs(b, b->nseg_cap));
+    rec(b, SNPM_EV_START);
+    SNPM_TRY(batch_join(b, algo));
+    rec(b, SNPM_EV_JOIN);
+    ScoreArgs a = {};
+    a.packed = db->d_packed;
+    a.stride = db->stride;
+    a.pair_db = b->d_pair_db.as<int32_t>();
+    a.pair_w = b->d_pair_w.as<double>();
+    a.seg_off = b->d_seg_off.as<int32_t>();
+    a.mstart = b->d_mstart.as<int32_t>();
+    a.S = int32_t(b->S);
+    a.chunk = SNPM_CHUNK_ROWS;
+    a.table = 0;
+    a.part_score = b->d_part_score.as<double>();
+    a.part_ninfo = b->d_part_ninfo.as<int32_t>();
+    a.a_pad = db->stride * 32;
+    SNPM_TRY(launch_score(st, a, int(b->nseg_cap), skip_db_hets != 0));
+    if (b->nseg_cap > 0) b->launches += 1;
+    rec(b, SNPM_EV_SCORE);
+    dim3 cgrid((db->n_acc + 255) / 256, unsigned(b->S));
+    k_combine<<<cgrid, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, a.seg_off, a.mstart, 0, nullptr, nullptr, b->d_red.as<double>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    rec(b, SNPM_EV_COMBINE);
+    b->ran = true;
+    b->ran_windows = false;
+    b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+int snpm_batch_epilogue(snpm_batch *b) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_epilogue: NULL batch");
+    if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_epilogue: run the batch first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    rec(b, SNPM_EV_EPI_START);
+    k_epilogue<<<unsigned(b->S), 1024, 0, db->stream>>>(b->d_red.as<double>(), db->n_acc, 1, 0, 0.0, b->d_matches.as<int64_t>(),
+                                                        b->d_ninfo64.as<int64_t>(), b->d_prob.as<double>(), b->d_L.as<double>(),
+                                                        b->d_LR.as<double>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    rec(b, SNPM_EV_EPI_END);
+    b->epilogue_done = true;
+    return SNPM_OK;
+}
+
+int snpm_batch_wait(snpm_batch *b, float *ms_device) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_wait: NULL batch");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    if (b->d_status.p) SNPM_CUDA(cudaMemcpyAsync(b->h_status, b->d_status.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, db->stream));
+    else memset(b->h_status, 0, 8 * sizeof(int));
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    if (ms_device) {
+        *ms_device = 0.f;
+        if (b->ev_rec[SNPM_EV_START] && b->ev_rec[SNPM_EV_COMBINE]) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, b->ev[SNPM_EV_START], b->ev[SNPM_EV_COMBINE]);
+            *ms_device += t;
+        }
+        if (b->ev_rec[SNPM_EV_EPI_START] && b->ev_rec[SNPM_EV_EPI_END]) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, b->ev[SNPM_EV_EPI_START], b->ev[SNPM_EV_EPI_END]);
+            *ms_device += t;
+        }
+    }
+    if (b->h_status[0] > 0)
+        return fail(SNPM_E_ARG, "sample markers are not sorted by (database chromosome order, position) or repeat a position (%d places)", b->h_status[0]);
+    if (b->h_status[1] > 0)
+        return fail(SNPM_E_ASSERT, "provided y is greater than n (%d window cells; likeliTest, snpmatch.py:43)", b->h_status[1]);
+    if (b->h_status[2] > 0)
+        return fail(SNPM_E_ARG, "identity table too short for %d window cells", b->h_status[2]);
+    return SNPM_OK;
+}
+
+int snpm_batch_timings(snpm_batch *b, float *ms, int n) {
+    if (!b || !ms || n < 6) return fail(SNPM_E_ARG, "snpm_batch_timings: need room for 6 floats");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    auto el = [&](int a, int c) {
+        float t = 0.f;
+        if (b->ev_rec[a] && b->ev_rec[c]) cudaEventElapsedTime(&t, b->ev[a], b->ev[c]);
+        return t;
+    };
+    ms[0] = el(SNPM_EV_START, SNPM_EV_JOIN);
+    ms[1] = el(SNPM_EV_JOIN, SNPM_EV_SCORE);
+    ms[2] = el(SNPM_EV_SCORE, SNPM_EV_COMBINE);
+    ms[3] = el(SNPM_EV_EPI_START, SNPM_EV_EPI_END);
+    ms[4] = el(SNPM_EV_START, SNPM_EV_COMBINE) + ms[3];
+    ms[5] = float(b->launches);
+    return SNPM_OK;
+}
+
+int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles) {
+    if (!b || !dev_ptr) return fail(SNPM_E_ARG, "snpm_batch_reduce_buffer: NULL argument");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    SNPM_TRY(b->d_red.ensure(size_t(b->S) * (2 * size_t(b->db->n_acc) + 2) * 8));
+    *dev_ptr = b->d_red.p;
+    if (n_doubles) *n_doubles = b->S * (2 * int64_t(b->db->n_acc) + 2);
+    return SNPM_OK;
+}
+
+int snpm_batch_fetch(snpm_batch *b, double *score, int64_t *matches, int64_t *ninfo, int64_t *m, double *prob, double *L, double *LR) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_fetch: NULL batch");
+    if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_fetch: run the batch first");
+    if ((matches || ninfo || prob || L || LR) && !b->epilogue_done) return fail(SNPM_E_STATE, "snpm_batch_fetch: run the epilogue first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const size_t A = size_t(db->n_acc), S = size_t(b->S), pitch = (2 * A + 2) * 8;
+    const double *red = b->d_red.as<double>();
+    std::vector<double> tail(2 * S);
+    if (score) SNPM_CUDA(cudaMemcpy2DAsync(score, A * 8, red, pitch, A * 8, S, cudaMemcpyDeviceToHost, st));
+    SNPM_CUDA(cudaMemcpy2DAsync(tail.data(), 16, red + 2 * A, pitch, 16, S, cudaMemcpyDeviceToHost, st));
+    if (matches) SNPM_CUDA(cudaMemcpyAsync(matches, b->d_matches.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (ninfo) SNPM_CUDA(cudaMemcpyAsync(ninfo, b->d_ninfo64.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, b->d_prob.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (L) SNPM_CUDA(cudaMemcpyAsync(L, b->d_L.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, b->d_LR.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    SNPM_TRY(snpm_batch_wait(b, nullptr));
+    long long viol = 0;
+    for (size_t s = 0; s < S; ++s) {
+        if (m) m[s] = int64_t(tail[2 * s]);
+        viol += (long long)tail[2 * s + 1];
+    }
+    if (viol > 0 && b->epilogue_done) return fail(SNPM_E_ASSERT, "provided y is greater than n (%lld accessions; likeliTest, snpmatch.py:43)", viol);
+    return SNPM_OK;
+}
+
+int snpm_batch_fetch_pairs(snpm_batch *b, int64_t s, int64_t *db_idx, int64_t *s_idx, int64_t capacity, int64_t *m) {
+    if (!b || s < 0 || s >= b->S || !m) return fail(SNPM_E_ARG, "snpm_batch_fetch_pairs: bad arguments");
+    if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_fetch_pairs: run the batch first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    int32_t range[2];
+    SNPM_CUDA(cudaMemcpyAsync(range, b->d_mstart.as<int32_t>() + s, 8, cudaMemcpyDeviceToHost, db->stream));
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    const int64_t cnt = range[1] - range[0];
+    *m = cnt;
+    if (cnt == 0 || (!db_idx && !s_idx)) return SNPM_OK;
+    if (cnt > capacity) return fail(SNPM_E_ARG, "snpm_batch_fetch_pairs: capacity %lld < %lld pairs", (long long)capacity, (long long)cnt);
+    std::vector<int32_t> tmp(size_t(cnt) * 2);
+    SNPM_CUDA(cudaMemcpyAsync(tmp.data(), b->d_pair_db.as<int32_t>() + range[0], size_t(cnt) * 4, cudaMemcpyDeviceToHost, db->stream));
+    SNPM_CUDA(cudaMemcpyAsync(tmp.data() + cnt, b->d_pair_s.as<int32_t>() + range[0], size_t(cnt) * 4, cudaMemcpyDeviceToHost, db->stream));
+    SNPM_CUDA(cudaStreamSynchronize(db->stream));
+    const int64_t base = b->h_off[size_t(s)];
+    for (int64_t i = 0; i < cnt; ++i) {
+        if (db_idx) db_idx[i] = int64_t(tmp[size_t(i)]) + db->row0_global;
+        if (s_idx) s_idx[i] = int64_t(tmp[size_t(cnt + i)]) - base;
+    }
+    return SNPM_OK;
+}
+
+int snpm_score(snpm_db *db, const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei, int64_t n, int skip_db_hets,
+               const int64_t *filter_rows, int64_t n_filter, double *score, int64_t *matches, int64_t *ninfo, int64_t *m,
+               double *prob, double *L, double *LR) {
+    if (!db) return fail(SNPM_E_ARG, "snpm_score: db is NULL");
+    const int64_t off[2] = {0, n};
+    snpm_batch *b = nullptr;
+    SNPM_TRY(snpm_batch_create(db, 1, off, s_chrom_id, s_pos, wei, &b));
+    int rc = snpm_batch_set_row_filter(b, filter_rows, n_filter);
+    if (rc == SNPM_OK) rc = snpm_batch_run(b, skip_db_hets, 0);
+    if (rc == SNPM_OK) rc = snpm_batch_epilogue(b);
+    if (rc == SNPM_OK) rc = snpm_batch_fetch(b, score, matches, ninfo, m, prob, L, LR);
+    snpm_batch_destroy(b);
+    return rc;
+}
+
+int snpm_intersect(snpm_db *db, const int32_t *s_chrom_id, const int32_t *s_pos, int64_t n, int algo, int64_t *db_idx, int64_t *s_idx,
+                   int64_t *m) {
+    if (!db || !m || algo < 0 || algo > 2) return fail(SNPM_E_ARG, "snpm_intersect: bad arguments");
+    const int64_t off[2] = {0, n};
+    std::vector<double> wei(size_t(n) * 3, 0.0);
+    snpm_batch *b = nullptr;
+    SNPM_TRY(snpm_batch_create(db, 1, off, s_chrom_id, s_pos, wei.data(), &b));
+    b->launches = 0;
+    int rc = batch_join(b, algo);
+    if (rc == SNPM_OK) { b->ran = true; rc = snpm_batch_wait(b, nullptr); }
+    if (rc == SNPM_OK) rc = snpm_batch_fetch_pairs(b, 0, db_idx, s_idx, n, m);
+    snpm_batch_destroy(b);
+    return rc;
+}
+
+// ---- A2 / A4 stand-alone operators ------------------------------------------------------------------
+int snpm_match_gts_accs(int device, const double *wei, const int8_t *snps, int64_t k, int32_t n_acc, int skip_hets_db, double *score,
+                        int64_t *ninfo) {
+    if (k < 0 || n_acc <= 0 || !score || !ninfo || (k > 0 && (!wei || !snps))) return fail(SNPM_E_ARG, "snpm_match_gts_accs: bad arguments");
+    if (k >= (int64_t(1) << 31)) return fail(SNPM_E_ARG, "snpm_match_gts_accs: too many rows");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(SNPM_E_CUDA, "snpm_match_gts_accs: no CUDA device (there is no CPU fallback)");
+    SNPM_CUDA(cudaSetDevice(device));
+    const int32_t stride = (((n_acc + 31) / 32) + 1) & ~1;
+    const int64_t a_pad = int64_t(stride) * 32;
+    std::vector<int32_t> iota(size_t(k) + 2);
+    std::vector<double> w4(size_t(k) * 4);
+    for (int64_t r = 0; r < k; ++r) {
+        iota[size_t(r)] = int32_t(r);
+        w4[size_t(4 * r)] = wei[3 * r];
+        w4[size_t(4 * r + 1)] = wei[3 * r + 1];
+        w4[size_t(4 * r + 2)] = wei[3 * r + 2];
+        w4[size_t(4 * r + 3)] = 0.0;
+    }
+    const int32_t seg[2] = {0, int32_t(k)};
+    DevBuf d_snps, d_packed, d_rows, d_w, d_seg, d_ps, d_pn;
+    int rc = SNPM_OK;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        d_snps.release(); d_packed.release(); d_rows.release(); d_w.release(); d_seg.release(); d_ps.release(); d_pn.release();
+        if (st) cudaStreamDestroy(st);
+    };
+#define MG_TRY(x) do { rc = (x); if (rc != SNPM_OK) { cleanup(); return rc; } } while (0)
+#define MG_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(SNPM_E_CUDA, "snpm_match_gts_accs: %s -> %s", #x, cudaGetErrorString(e_)); } } while (0)
+    MG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    MG_TRY(d_snps.ensure(size_t(k) * n_acc));
+    MG_TRY(d_packed.ensure(size_t(k) * stride * 8));
+    MG_TRY(d_rows.ensure(size_t(k) * 4));
+    MG_TRY(d_w.ensure(size_t(k) * 32));
+    MG_TRY(d_seg.ensure(8));
+    MG_TRY(d_ps.ensure(size_t(a_pad) * 8));
+    MG_TRY(d_pn.ensure(size_t(a_pad) * 4));
+    if (k > 0) {
+        MG_CUDA(cudaMemcpyAsync(d_snps.p, snps, size_t(k) * n_acc, cudaMemcpyHostToDevice, st));
+        MG_CUDA(cudaMemcpyAsync(d_rows.p, iota.data(), size_t(k) * 4, cudaMemcpyHostToDevice, st));
+        MG_CUDA(cudaMemcpyAsync(d_w.p, w4.data(), size_t(k) * 32, cudaMemcpyHostToDevice, st));
+        k_pack_int8<<<grid_for(k * stride * 32, 256, 148), 256, 0, st>>>(d_snps.as<int8_t>(), k, n_acc, stride, d_packed.as<uint64_t>());
+        MG_CUDA(cudaGetLastError());
+    }
+    MG_CUDA(cudaMemcpyAsync(d_seg.p, seg, 8, cudaMemcpyHostToDevice, st));
+    ScoreArgs a = {};
+    a.packed = d_packed.as<uint64_t>();
+    a.stride = stride;
+    a.pair_db = d_rows.as<int32_t>();
+    a.pair_w = d_w.as<double>();
+    a.table = 1;
+    a.nseg = 1;
+    a.seg_begin = d_seg.as<int32_t>();
+    a.seg_end = d_seg.as<int32_t>() + 1;
+    a.part_score = d_ps.as<double>();
+    a.part_ninfo = d_pn.as<int32_t>();
+    a.a_pad = int32_t(a_pad);
+    MG_TRY(launch_score(st, a, 1, skip_hets_db != 0));
+    std::vector<int32_t> ni(static_cast<size_t>(n_acc), 0);
+    MG_CUDA(cudaMemcpyAsync(score, d_ps.p, size_t(n_acc) * 8, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaMemcpyAsync(ni.data(), d_pn.p, size_t(n_acc) * 4, cudaMemcpyDeviceToHost, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    for (int32_t i = 0; i < n_acc; ++i) ninfo[i] = ni[size_t(i)];
+    cleanup();
+#undef MG_TRY
+#undef MG_CUDA
+    return SNPM_OK;
+}
+
+int snpm_calculate_likelihoods(int device, const double *scores, const double *ninfo, int64_t n_acc, int amin_is_calc, double amin,
+                               double *prob, double *L, double *LR) {
+    if (n_acc <= 0 || n_acc >= (int64_t(1) << 30) || !scores || !ninfo) return fail(SNPM_E_ARG, "snpm_calculate_likelihoods: bad arguments");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(SNPM_E_CUDA, "snpm_calculate_likelihoods: no CUDA device (there is no CPU fallback)");
+    SNPM_CUDA(cudaSetDevice(device));
+    const size_t A = size_t(n_acc);
+    std::vector<double> red(2 * A + 2, 0.0);
+    memcpy(red.data(), scores, A * 8);
+    memcpy(red.data() + A, ninfo, A * 8);
+    DevBuf d_red, d_out;
+    int rc = d_red.ensure((2 * A + 2) * 8);
+    if (rc == SNPM_OK) rc = d_out.ensure(3 * A * 8);
+    cudaError_t e = cudaSuccess;
+    if (rc == SNPM_OK) {
+        e = cudaMemcpy(d_red.p, red.data(), (2 * A + 2) * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            double *o = d_out.as<double>();
+            k_epilogue<<<1, 1024>>>(d_red.as<double>(), int32_t(n_acc), 0, amin_is_calc ? 0 : 1, amin, nullptr, nullptr, o, o + A, o + 2 * A);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        double viol = 0.0;
+        if (e == cudaSuccess) e = cudaMemcpy(&viol, d_red.as<double>() + 2 * A + 1, 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && prob) e = cudaMemcpy(prob, d_out.p, A * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && L) e = cudaMemcpy(L, d_out.as<double>() + A, A * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && LR) e = cudaMemcpy(LR, d_out.as<double>() + 2 * A, A * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && viol > 0.0) rc = fail(SNPM_E_ASSERT, "provided y is greater than n (%lld accessions; likeliTest, snpmatch.py:43)", (long long)viol);
+    }
+    d_red.release();
+    d_out.release();
+    if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_calculate_likelihoods: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+// ---- A5 + A6 ----------------------------------------------------------------------------------------
+int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, const int32_t *win_count, const int32_t *win_off,
+                           int32_t n_windows, const int32_t *kmax, int64_t kmax_len, double lr_thres) {
+    if (!b || bin_len <= 0 || n_windows < 0 || !win_count || !win_off || !kmax || kmax_len < 1)
+        return fail(SNPM_E_ARG, "snpm_batch_run_windows: bad arguments");
+    if (b->S != 1) return fail(SNPM_E_ARG, "snpm_batch_run_windows: windows are scored for a single-sample batch");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const int32_t W = n_windows;
+    b->launches = 0;
+    for (int i = 0; i < SNPM_N_EVENTS; ++i) b->ev_rec[i] = false;
+    SNPM_TRY(batch_alloc_outputs(b, std::max<int64_t>(W, 1)));
+    const size_t WA = size_t(std::max(W, 1)) * db->n_acc;
+    SNPM_TRY(b->d_win_count.ensure(size_t(std::max(db->n_chr, 1)) * 4));
+    SNPM_TRY(b->d_win_off.ensure(size_t(std::max(db->n_chr, 1)) * 4));
+    SNPM_TRY(b->d_win_begin.ensure(size_t(std::max(W, 1)) * 4));
+    SNPM_TRY(b->d_win_end.ensure(size_t(std::max(W, 1)) * 4));
+    SNPM_TRY(b->d_kmax.ensure(size_t(kmax_len) * 4));
+    SNPM_TRY(b->d_win_L.ensure(WA * 8));
+    SNPM_TRY(b->d_win_LR.ensure(WA * 8));
+    SNPM_TRY(b->d_win_ident.ensure(WA));
+    SNPM_TRY(b->d_win_amb.ensure(size_t(std::max(W, 1)) * 4));
+    if (db->n_chr) {
+        SNPM_CUDA(cudaMemcpyAsync(b->d_win_count.p, win_count, size_t(db->n_chr) * 4, cudaMemcpyHostToDevice, st));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_win_off.p, win_off, size_t(db->n_chr) * 4, cudaMemcpyHostToDevice, st));
+    }
+    SNPM_CUDA(cudaMemcpyAsync(b->d_kmax.p, kmax, size_t(kmax_len) * 4, cudaMemcpyHostToDevice, st));
+    rec(b, SNPM_EV_START);
+    SNPM_TRY(batch_join(b, 0));
+    SNPM_CUDA(cudaMemsetAsync(b->d_win_begin.p, 0, size_t(std::max(W, 1)) * 4, st));
+    SNPM_CUDA(cudaMemsetAsync(b->d_win_end.p, 0, size_t(std::max(W, 1)) * 4, st));
+    if (b->n > 0 && W > 0) {
+        k_window_bounds<<<int(ceil_div64(b->n, 256)), 256, 0, st>>>(b->d_pair_s.as<int32_t>(), b->d_prefix.as<int32_t>() + b->n,
+                                                                 b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), b->d_win_count.as<int32_t>(),
+                                                                 b->d_win_off.as<int32_t>(), bin_len, b->d_win_begin.as<int32_t>(),
+                                                                 b->d_win_end.as<int32_t>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 1;
+    }
+    rec(b, SNPM_EV_JOIN);
+    ScoreArgs a = {};
+    a.packed = db->d_packed;
+    a.stride = db->stride;
+    a.pair_db = b->d_pair_db.as<int32_t>();
+    a.pair_w = b->d_pair_w.as<double>();
+    a.table = 1;
+    a.nseg = W;
+    a.seg_begin = b->d_win_begin.as<int32_t>();
+    a.seg_end = b->d_win_end.as<int32_t>();
+    a.part_score = b->d_part_score.as<double>();
+    a.part_ninfo = b->d_part_ninfo.as<int32_t>();
+    a.a_pad = db->stride * 32;
+    SNPM_TRY(launch_score(st, a, W, skip_db_hets != 0));
+    if (W > 0) b->launches += 1;
+    rec(b, SNPM_EV_SCORE);
+    dim3 cgrid((db->n_acc + 255) / 256, 1);
+    k_combine<<<cgrid, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, nullptr, nullptr, W, a.seg_begin, a.seg_end, b->d_red.as<double>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    if (W > 0) {
+        k_window_epilogue<<<W, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, a.seg_begin, a.seg_end, b->d_kmax.as<int32_t>(), kmax_len,
+                                             lr_thres, b->d_win_L.as<double>(), b->d_win_LR.as<double>(), b->d_win_ident.as<uint8_t>(),
+                                             b->d_win_amb.as<int32_t>(), b->d_status.as<int>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 1;
+    }
+    rec(b, SNPM_EV_COMBINE);
+    b->n_windows = W;
+    b->bin_len = bin_len;
+    b->lr_thres = lr_thres;
+    b->ran = true;
+    b->ran_windows = true;
+    b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninfo, double *win_L, double *win_LR, uint8_t *win_identical,
+                             int32_t *win_num_amb, int32_t *win_nrows, int64_t *matched_s_idx, int64_t capacity, int64_t *n_matched) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_fetch_windows: NULL batch");
+    if (!b->ran_windows) return fail(SNPM_E_STATE, "snpm_batch_fetch_windows: run the windows first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const size_t W = size_t(b->n_windows), A = size_t(db->n_acc), a_pad = size_t(db->stride) * 32;
+    std::vector<int32_t> wb(W + 1), we(W + 1), ps;
+    if (W) {
+        if (win_score) SNPM_CUDA(cudaMemcpy2DAsync(win_score, A * 8, b->d_part_score.p, a_pad * 8, A * 8, W, cudaMemcpyDeviceToHost, st));
+        if (win_ninfo) SNPM_CUDA(cudaMemcpy2DAsync(win_ninfo, A * 4, b->d_part_ninfo.p, a_pad * 4, A * 4, W, cudaMemcpyDeviceToHost, st));
+        if (win_L) SNPM_CUDA(cudaMemcpyAsync(win_L, b->d_win_L.p, W * A * 8, cudaMemcpyDeviceToHost, st));
+        if (win_LR) SNPM_CUDA(cudaMemcpyAsync(win_LR, b->d_win_LR.p, W * A * 8, cudaMemcpyDeviceToHost, st));
+        if (win_identical) SNPM_CUDA(cudaMemcpyAsync(win_identical, b->d_win_ident.p, W * A, cudaMemcpyDeviceToHost, st));
+        if (win_num_amb) SNPM_CUDA(cudaMemcpyAsync(win_num_amb, b->d_win_amb.p, W * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpyAsync(wb.data(), b->d_win_begin.p, W * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpyAsync(we.data(), b->d_win_end.p, W * 4, cudaMemcpyDeviceToHost, st));
+    }
+    int32_t m_all = 0;
+    SNPM_CUDA(cudaMemcpyAsync(&m_all, b->d_prefix.as<int32_t>() + b->n, 4, cudaMemcpyDeviceToHost, st));
+    SNPM_TRY(snpm_batch_wait(b, nullptr));
+    int64_t total = 0;
+    for (size_t w = 0; w < W; ++w) {
+        if (win_nrows) win_nrows[w] = we[w] - wb[w];
+        total += we[w] - wb[w];
+    }
+    if (n_matched) *n_matched = total;
+    if (matched_s_idx && total > 0) {
+        if (total > capacity) return fail(SNPM_E_ARG, "snpm_batch_fetch_windows: capacity %lld < %lld", (long long)capacity, (long long)total);
+        ps.resize(size_t(m_all));
+        SNPM_CUDA(cudaMemcpyAsync(ps.data(), b->d_pair_s.p, size_t(m_all) * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaStreamSynchronize(st));
+        int64_t o = 0;
+        for (size_t w = 0; w < W; ++w)
+            for (int32_t r = wb[w]; r < we[w]; ++r) matched_s_idx[o++] = ps[size_t(r)];
+    }
+    return SNPM_OK;
+}
+
+// ---- A7 ---------------------------------------------------------------------------------------------
+int snpm_batch_f1_pairs(snpm_batch *b, const int32_t *acc_idx, int32_t n_top, double *pair_score, int64_t *pair_ninfo) {
+    if (!b || !acc_idx || n_top < 2 || n_top > 4096 || !pair_score || !pair_ninfo) return fail(SNPM_E_ARG, "snpm_batch_f1_pairs: bad arguments");
+    if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_f1_pairs: run the batch first");
+    if (b->S != 1) return fail(SNPM_E_ARG, "snpm_batch_f1_pairs: single-sample batch expected");
+    snpm_db *db = b->db;
+    for (int i = 0; i < n_top; ++i)
+        if (acc_idx[i] < 0 || acc_idx[i] >= db->n_acc) return fail(SNPM_E_ARG, "snpm_batch_f1_pairs: accession index %d out of range", acc_idx[i]);
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const int n_pairs = n_top * (n_top - 1) / 2;
+    const int n_blocks = int(std::max<int64_t>(1, ceil_div64(b->n, F1_ROWS_PER_BLOCK)));
+    SNPM_TRY(b->d_f1_acc.ensure(size_t(n_top) * 4));
+    SNPM_TRY(b->d_f1_part.ensure(size_t(n_pairs) * n_blocks * 32));
+    SNPM_TRY(b->d_f1_out.ensure(size_t(n_pairs) * 16));
+    SNPM_CUDA(cudaMemcpyAsync(b->d_f1_acc.p, acc_idx, size_t(n_top) * 4, cudaMemcpyHostToDevice, st));
+    dim3 grid(n_blocks, n_pairs);
+    k_f1_partial<<<grid, F1_THREADS, 0, st>>>(db->d_packed, db->stride, b->d_pair_db.as<int32_t>(), b->d_pair_w.as<double>(),
+                                              b->d_prefix.as<int32_t>() + b->n, b->d_f1_acc.as<int32_t>(), n_top, b->d_f1_part.as<double>());
+    SNPM_KERNEL_CHECK();
+    k_f1_final<<<(n_pairs + 127) / 128, 128, 0, st>>>(b->d_f1_part.as<double>(), n_blocks, n_pairs, b->d_f1_out.as<double>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 2;
+    std::vector<double> out(size_t(n_pairs) * 2);
+    SNPM_CUDA(cudaMemcpyAsync(out.data(), b->d_f1_out.p, size_t(n_pairs) * 16, cudaMemcpyDeviceToHost, st));
+    SNPM_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < n_pairs; ++p) {
+        pair_score[p] = out[size_t(2 * p)];
+        pair_ninfo[p] = int64_t(out[size_t(2 * p + 1)]);
+    }
+    return SNPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+// Shared host/device helpers of libsnpmatch_b200 (error convention, device buffers, handle structs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/snpmatch_b200.h"
+
+namespace snpm {
+
+extern thread_local std::string g_last_error;
+
+inline int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define SNPM_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return snpm::fail(SNPM_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                              cudaGetErrorString(e__));                                          \
+    } while (0)
+
+#define SNPM_TRY(call)                 \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != SNPM_OK) return rc__; \
+    } while (0)
+
+#define SNPM_KERNEL_CHECK() SNPM_CUDA(cudaGetLastError())
+
+// Grow-only device allocation.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return SNPM_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes < 256 ? 256 : bytes;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(SNPM_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return SNPM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace snpm
+
+// ---------------------------------------------------------------------------------------------
+// Handles
+// ---------------------------------------------------------------------------------------------
+struct snpm_db {
+    int device = 0;
+    int64_t n_rows = 0;       // rows of this shard
+    int32_t n_acc = 0;
+    int32_t n_words = 0;      // ceil(n_acc / 32)
+    int32_t stride = 0;       // words per row (even -> 16-byte multiple)
+    int64_t row0_global = 0;
+    int32_t n_chr = 0;
+    int n_sm = 148;
+    uint64_t *d_packed = nullptr;
+    int32_t *d_pos = nullptr;
+    int64_t *d_chr_regions = nullptr;   // [n_chr,2], local rows
+    std::vector<int64_t> h_chr_regions;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    snpm::DevBuf scratch;               // upload staging for int8 rows
+};
+
+enum { SNPM_EV_START = 0, SNPM_EV_JOIN, SNPM_EV_SCORE, SNPM_EV_COMBINE, SNPM_EV_EPI_START, SNPM_EV_EPI_END, SNPM_N_EVENTS };
+
+struct snpm_batch {
+    snpm_db *db = nullptr;
+    int64_t S = 0;            // samples
+    int64_t n = 0;            // markers over all samples
+    int64_t nseg_cap = 0;     // upper bound of 1000-row chunks over all samples
+    std::vector<int64_t> h_off;
+    // inputs (device)
+    snpm::DevBuf d_off, d_chrom, d_pos, d_wei, d_filter;
+    int64_t n_filter = 0;
+    // join products
+    snpm::DevBuf d_match_row, d_tile_cnt, d_tile_off, d_prefix, d_pair_db, d_pair_s, d_pair_w;
+    snpm::DevBuf d_mstart, d_seg_off;
+    // scoring products
+    snpm::DevBuf d_part_score, d_part_ninfo, d_red, d_matches, d_ninfo64, d_prob, d_L, d_LR, d_status;
+    // windows
+    int32_t n_windows = 0;
+    int64_t bin_len = 0;
+    double lr_thres = 3.841;
+    snpm::DevBuf d_win_count, d_win_off, d_win_begin, d_win_end, d_kmax, d_win_L, d_win_LR, d_win_ident, d_win_amb;
+    // f1
+    snpm::DevBuf d_f1_acc, d_f1_part, d_f1_out;
+    // state
+    bool ran = false, ran_windows = false, epilogue_done = false;
+    int launches = 0;
+    cudaEvent_t ev[SNPM_N_EVENTS] = {};
+    bool ev_rec[SNPM_N_EVENTS] = {};
+    int *h_status = nullptr;  // pinned, 8 ints
+};

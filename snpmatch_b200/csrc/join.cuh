@@ -1,0 +1,278 @@
+// A1 — (chrom, pos) join of sample markers against the resident panel.
+// Replaces Genotype.get_common_positions (snp_genotype.py:46-68).
+//
+// Two device algorithms produce the same per-marker result `match_row[i]` (local panel row or -1):
+//   * k_join_search   — one binary search per marker inside its chromosome's row range
+//                       (n*log2(N) probes; the right tool for low-coverage samples, n << N);
+//   * k_join_mergepath — merge-path partition of the two sorted key streams, each CTA merging one
+//                       diagonal band from shared memory (reads every panel position once; the
+//                       right tool for dense samples and batches).
+// An order-preserving compaction (tile counts -> scan -> scatter) then emits the index pairs in
+// panel order, the matched weights in matched order, and the inclusive prefix used to cut the
+// pairs into samples.
+#pragma once
+#include "common.cuh"
+
+namespace snpm {
+
+constexpr int JOIN_TILE = 1024;
+
+__device__ __forceinline__ int64_t lower_bound_i32(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int32_t key) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool contains_i64(const int64_t *__restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && __ldg(a + lo) == key;
+}
+
+// status[0] += number of adjacent marker pairs that break the (chromosome, position) order inside a sample
+__device__ __forceinline__ void check_order(const int32_t *__restrict__ chrom, const int32_t *__restrict__ pos,
+                                            const int64_t *__restrict__ off, int64_t S, int64_t i, int *status) {
+    if (i == 0) return;
+    const int32_t c1 = chrom[i], c0 = chrom[i - 1];
+    if (c1 < 0 || c0 < 0) return;
+    const bool bad = (c1 < c0) || (c1 == c0 && pos[i] <= pos[i - 1]);
+    if (!bad) return;
+    // a new sample may restart the order: is i one of the offsets?
+    int64_t lo = 0, hi = S + 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (off[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    if (lo <= S && off[lo] == i) return;
+    atomicAdd(status, 1);
+}
+
+__global__ void __launch_bounds__(JOIN_TILE) k_join_search(
+        const int32_t *__restrict__ chrom, const int32_t *__restrict__ pos, int64_t n,
+        const int64_t *__restrict__ off, int64_t S,
+        const int32_t *__restrict__ db_pos, const int64_t *__restrict__ chr_regions, int32_t n_chr,
+        const int64_t *__restrict__ filter, int64_t n_filter, int64_t row0_global,
+        int32_t *__restrict__ match_row, int32_t *__restrict__ tile_cnt, int *status) {
+    const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
+    int32_t row = -1;
+    if (i < n) {
+        check_order(chrom, pos, off, S, i, status);
+        const int32_t c = chrom[i];
+        if (c >= 0 && c < n_chr) {
+            const int64_t rs = chr_regions[2 * c], re = chr_regions[2 * c + 1];
+            const int32_t p = pos[i];
+            const int64_t j = lower_bound_i32(db_pos, rs, re, p);
+            if (j < re && __ldg(db_pos + j) == p) {
+                row = int32_t(j);
+                if (n_filter > 0 && !contains_i64(filter, n_filter, j + row0_global)) row = -1;
+            }
+        }
+        match_row[i] = row;
+    }
+    const int cnt = __syncthreads_count(row >= 0);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = cnt;
+}
+
+// ---- merge-path variant -------------------------------------------------------------------------
+// Keys: panel side (chromosome c, position) for rows of chromosome c; sample side the same from
+// (s_chrom_id, s_pos); both streams ascending in (c, pos) (markers with chromosome -1 are skipped by
+// giving them the key of their predecessor's successor... they are handled by the caller: see below).
+// One launch per (sample, chromosome) would fragment the work; instead a CTA owns MP_TILE consecutive
+// sample markers of ONE chromosome range and the panel slice [lower_bound(first key), upper_bound(last
+// key)) that can match them, and merges the two from shared memory.  Panel positions are streamed
+// coalesced exactly once over a dense sample; sparse samples make the panel slices long, which is why
+// the host picks the search kernel for them.
+constexpr int MP_TILE = 1024;          // sample markers per CTA
+constexpr int MP_DB_CHUNK = 4096;      // panel positions staged per step
+
+__global__ void __launch_bounds__(256) k_join_mergepath(
+        const int32_t *__restrict__ chrom, const int32_t *__restrict__ pos, int64_t n,
+        const int64_t *__restrict__ off, int64_t S,
+        const int32_t *__restrict__ db_pos, const int64_t *__restrict__ chr_regions, int32_t n_chr,
+        const int64_t *__restrict__ filter, int64_t n_filter, int64_t row0_global,
+        int32_t *__restrict__ match_row, int32_t *__restrict__ tile_cnt, int *status) {
+    __shared__ int32_t s_pos[MP_TILE];
+    __shared__ int32_t s_chr[MP_TILE];
+    __shared__ int32_t s_db[MP_DB_CHUNK];
+    __shared__ int32_t s_cnt;
+    const int64_t base = int64_t(blockIdx.x) * MP_TILE;
+    const int tile_n = int((n - base) < int64_t(MP_TILE) ? (n - base) : int64_t(MP_TILE));
+    if (threadIdx.x == 0) s_cnt = 0;
+    for (int t = threadIdx.x; t < tile_n; t += blockDim.x) {
+        check_order(chrom, pos, off, S, base + t, status);
+        s_pos[t] = pos[base + t];
+        s_chr[t] = chrom[base + t];
+    }
+    __syncthreads();
+    int local_cnt = 0;
+    // walk the tile chromosome run by chromosome run (a tile usually holds one run)
+    int run_start = 0;
+    while (run_start < tile_n) {
+        const int32_t c = s_chr[run_start];
+        int run_end = run_start + 1;
+        // every thread computes the same run bounds; also stop where the order restarts (next sample)
+        while (run_end < tile_n && s_chr[run_end] == c && s_pos[run_end] > s_pos[run_end - 1]) ++run_end;
+        if (c < 0 || c >= n_chr) {
+            for (int t = run_start + threadIdx.x; t < run_end; t += blockDim.x) match_row[base + t] = -1;
+            run_start = run_end;
+            continue;
+        }
+        const int64_t rs = chr_regions[2 * c], re = chr_regions[2 * c + 1];
+        const int32_t p_first = s_pos[run_start], p_last = s_pos[run_end - 1];
+        // panel slice that can match this run
+        const int64_t d0 = lower_bound_i32(db_pos, rs, re, p_first);
+        const int64_t d1 = lower_bound_i32(db_pos, d0, re, p_last + 1);
+        // thread t owns marker(s) run_start+t...; result accumulates over panel chunks
+        for (int t = run_start + threadIdx.x; t < run_end; t += blockDim.x) match_row[base + t] = -1;
+        for (int64_t dc = d0; dc < d1; dc += MP_DB_CHUNK) {
+            const int chunk_n = int((d1 - dc) < int64_t(MP_DB_CHUNK) ? (d1 - dc) : int64_t(MP_DB_CHUNK));
+            __syncthreads();
+            for (int t = threadIdx.x; t < chunk_n; t += blockDim.x) s_db[t] = __ldg(db_pos + dc + t);
+            __syncthreads();
+            const int32_t lo_key = s_db[0], hi_key = s_db[chunk_n - 1];
+            // merge-path split: each thread takes an equal share of the (markers-in-range + chunk) diagonal
+            // range of markers that can fall into this chunk
+            int m0 = run_start, m1 = run_end;
+            {   // lower_bound of lo_key / upper_bound of hi_key among the run's markers
+                int lo = run_start, hi = run_end;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_pos[mid] < lo_key) lo = mid + 1; else hi = mid; }
+                m0 = lo;
+                hi = run_end;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_pos[mid] <= hi_key) lo = mid + 1; else hi = mid; }
+                m1 = lo;
+            }
+            const int na = m1 - m0, nb = chunk_n;
+            const int total = na + nb;
+            const int per = (total + blockDim.x - 1) / blockDim.x;
+            const int diag0 = min(total, int(threadIdx.x) * per);
+            const int diag1 = min(total, diag0 + per);
+            // find (i, j) with i + j = diag0 on the merge path of A = s_pos[m0..m1), B = s_db[0..nb)
+            int lo = max(0, diag0 - nb), hi = min(diag0, na);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_pos[m0 + mid] < s_db[diag0 - 1 - mid]) lo = mid + 1; else hi = mid;
+            }
+            int i = lo, j = diag0 - lo;
+            // ties: the panel element goes first (consistent with the strict '<' of the split above), so a
+            // marker is matched when the panel element consumed just before it carries the same position
+            for (int d = diag0; d < diag1; ++d) {
+                const bool take_b = (j < nb) && (i >= na || s_db[j] <= s_pos[m0 + i]);
+                if (take_b) {
+                    ++j;
+                } else {
+                    if (j > 0 && s_db[j - 1] == s_pos[m0 + i]) {
+                        int32_t row = int32_t(dc + j - 1);
+                        if (n_filter > 0 && !contains_i64(filter, n_filter, int64_t(row) + row0_global)) row = -1;
+                        match_row[base + m0 + i] = row;
+                        if (row >= 0) ++local_cnt;
+                    }
+                    ++i;
+                }
+            }
+        }
+        __syncthreads();
+        run_start = run_end;
+    }
+    atomicAdd(&s_cnt, local_cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_cnt;
+}
+
+// ---- compaction ---------------------------------------------------------------------------------
+// exclusive scan of `v` over the block (blockDim.x multiple of 32, <= 1024); returns the prefix and
+// the block total through *total
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *s_warp /*[33]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nwarp ? s_warp[lane] : 0;
+        int xs = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, xs, d);
+            if (lane >= d) xs += y;
+        }
+        if (lane < nwarp) s_warp[lane] = xs - w;
+        if (lane == 31) s_warp[32] = xs;
+    }
+    __syncthreads();
+    const int res = s_warp[warp] + x - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+// single CTA: tile_off = exclusive scan of tile_cnt; prefix[n] = total
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int32_t *__restrict__ tile_cnt, int64_t n_tiles,
+                                                     int32_t *__restrict__ tile_off, int32_t *__restrict__ prefix_last) {
+    __shared__ int s_warp[33];
+    int carry = 0;
+    for (int64_t base = 0; base < n_tiles; base += blockDim.x) {
+        const int64_t t = base + threadIdx.x;
+        const int v = t < n_tiles ? tile_cnt[t] : 0;
+        int total;
+        const int ex = block_excl_scan(v, &total, s_warp);
+        if (t < n_tiles) tile_off[t] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *prefix_last = carry;
+}
+
+// scatter pairs in order; prefix[i] = number of matched markers before i; pair_w = matched weights
+__global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs(
+        const int32_t *__restrict__ match_row, int64_t n, const int32_t *__restrict__ tile_off,
+        const double *__restrict__ wei, int32_t *__restrict__ prefix, int32_t *__restrict__ pair_db,
+        int32_t *__restrict__ pair_s, double *__restrict__ pair_w) {
+    __shared__ int s_warp[33];
+    const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
+    const int32_t row = i < n ? match_row[i] : -1;
+    const int flag = row >= 0;
+    int total;
+    const int ex = block_excl_scan(flag, &total, s_warp);
+    if (i < n) {
+        const int32_t p = tile_off[blockIdx.x] + ex;
+        prefix[i] = p;
+        if (flag) {
+            pair_db[p] = row;
+            pair_s[p] = int32_t(i);
+            pair_w[3 * int64_t(p) + 0] = wei[3 * i + 0];
+            pair_w[3 * int64_t(p) + 1] = wei[3 * i + 1];
+            pair_w[3 * int64_t(p) + 2] = wei[3 * i + 2];
+        }
+    }
+}
+
+// single CTA: matched range of every sample and its number of 1000-row chunks
+//   mstart[s] = prefix[off[s]] (mstart[S] = total);  seg_off = exclusive scan of ceil(m_s / chunk)
+__global__ void __launch_bounds__(1024) k_sample_ranges(const int32_t *__restrict__ prefix, const int64_t *__restrict__ off,
+                                                        int64_t S, int32_t chunk, int32_t *__restrict__ mstart,
+                                                        int32_t *__restrict__ seg_off) {
+    __shared__ int s_warp[33];
+    for (int64_t s = threadIdx.x; s <= S; s += blockDim.x) mstart[s] = prefix[off[s]];
+    __syncthreads();
+    int carry = 0;
+    for (int64_t base = 0; base < S; base += blockDim.x) {
+        const int64_t s = base + threadIdx.x;
+        int v = 0;
+        if (s < S) v = (mstart[s + 1] - mstart[s] + chunk - 1) / chunk;
+        int total;
+        const int ex = block_excl_scan(v, &total, s_warp);
+        if (s < S) seg_off[s] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) seg_off[S] = carry;
+}
+
+}  // namespace snpm

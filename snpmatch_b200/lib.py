@@ -1,0 +1,336 @@
+"""
+ctypes binding of libsnpmatch_b200.so (include/snpmatch_b200.h).
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is no
+CPU fallback: if the library is missing, or no CUDA device is present when a database is created,
+the call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnpmatch_b200.so")
+
+SNPM_OK = 0
+SNPM_E_ARG = -1
+SNPM_E_CUDA = -2
+SNPM_E_NOMEM = -3
+SNPM_E_STATE = -4
+SNPM_E_ASSERT = -5
+
+CHUNK_ROWS = 1000
+
+JOIN_AUTO, JOIN_SEARCH, JOIN_MERGEPATH = 0, 1, 2
+
+
+class SnpmError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libsnpmatch_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+_p = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f64 = C.c_double
+
+# name -> (restype, argtypes); every symbol include/snpmatch_b200.h declares
+SIGNATURES = {
+    "snpm_version": (C.c_int, []),
+    "snpm_last_error": (C.c_char_p, []),
+    "snpm_device_count": (C.c_int, []),
+    "snpm_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, _p, _p, _p]),
+    "snpm_db_create": (C.c_int, [C.c_int, _i64, _i32, _p, _p, _i32, _i64, _p]),
+    "snpm_db_destroy": (C.c_int, [_p]),
+    "snpm_db_load_int8": (C.c_int, [_p, _i64, _i64, _p]),
+    "snpm_db_load_packed": (C.c_int, [_p, _i64, _i64, _p]),
+    "snpm_db_fill_synthetic": (C.c_int, [_p, C.c_uint64]),
+    "snpm_db_read_rows_int8": (C.c_int, [_p, _p, _i64, _p]),
+    "snpm_db_read_packed": (C.c_int, [_p, _i64, _i64, _p]),
+    "snpm_db_n_rows": (_i64, [_p]),
+    "snpm_db_n_acc": (_i32, [_p]),
+    "snpm_db_row_words": (_i32, [_p]),
+    "snpm_db_packed_bytes": (_i64, [_p]),
+    "snpm_db_set_stream": (C.c_int, [_p, _p]),
+    "snpm_intersect": (C.c_int, [_p, _p, _p, _i64, C.c_int, _p, _p, _p]),
+    "snpm_match_gts_accs": (C.c_int, [C.c_int, _p, _p, _i64, _i32, C.c_int, _p, _p]),
+    "snpm_calculate_likelihoods": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _f64, _p, _p, _p]),
+    "snpm_batch_create": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p]),
+    "snpm_batch_upload": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "snpm_batch_destroy": (C.c_int, [_p]),
+    "snpm_batch_set_row_filter": (C.c_int, [_p, _p, _i64]),
+    "snpm_batch_run": (C.c_int, [_p, C.c_int, C.c_int]),
+    "snpm_batch_epilogue": (C.c_int, [_p]),
+    "snpm_batch_wait": (C.c_int, [_p, _p]),
+    "snpm_batch_reduce_buffer": (C.c_int, [_p, _p, _p]),
+    "snpm_batch_fetch": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p]),
+    "snpm_batch_fetch_pairs": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),
+    "snpm_batch_timings": (C.c_int, [_p, _p, C.c_int]),
+    "snpm_score": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "snpm_batch_run_windows": (C.c_int, [_p, C.c_int, _i64, _p, _p, _i32, _p, _i64, _f64]),
+    "snpm_batch_fetch_windows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "snpm_batch_f1_pairs": (C.c_int, [_p, _p, _i32, _p, _p]),
+}
+
+
+def load():
+    """Load the shared library (once); raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a); snpmatch_b200 has no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != SNPM_OK:
+        msg = load().snpm_last_error()
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        if rc == SNPM_E_ASSERT:
+            raise AssertionError(msg)
+        raise SnpmError(rc, msg)
+
+
+def ptr(a):
+    """Pointer to a C-contiguous NumPy buffer (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def as_c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def device_count():
+    return load().snpm_device_count()
+
+
+def device_info(device=0):
+    name = C.create_string_buffer(256)
+    sm, mem, n_sm = C.c_int(0), C.c_int64(0), C.c_int(0)
+    check(load().snpm_device_info(device, name, 256, C.byref(sm), C.byref(mem), C.byref(n_sm)))
+    return {"name": name.value.decode(), "sm": sm.value, "mem_bytes": mem.value, "n_sm": n_sm.value}
+
+
+class Database(object):
+    """HBM-resident 2-bit packed panel (A0).  One per GPU (or per SNP-row shard)."""
+
+    def __init__(self, positions, chr_regions, n_acc, device=0, row0_global=0):
+        lib = load()
+        self.positions = as_c(positions, np.int32)
+        self.chr_regions = as_c(chr_regions, np.int64).reshape(-1, 2)
+        self.n_rows = int(len(self.positions))
+        self.n_acc = int(n_acc)
+        self.device = int(device)
+        self.row0_global = int(row0_global)
+        h = C.c_void_p()
+        check(lib.snpm_db_create(self.device, self.n_rows, self.n_acc, ptr(self.positions), ptr(self.chr_regions),
+                                 len(self.chr_regions), self.row0_global, C.byref(h)))
+        self._h = h
+        self.row_words = lib.snpm_db_row_words(h)
+        self.packed_bytes = lib.snpm_db_packed_bytes(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().snpm_db_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_int8(self, snps, row0=0):
+        snps = as_c(snps, np.int8)
+        assert snps.ndim == 2 and snps.shape[1] == self.n_acc
+        check(load().snpm_db_load_int8(self._h, row0, snps.shape[0], ptr(snps)))
+
+    def load_packed(self, packed, row0=0):
+        packed = as_c(packed, np.uint64)
+        assert packed.ndim == 2 and packed.shape[1] == self.row_words
+        check(load().snpm_db_load_packed(self._h, row0, packed.shape[0], ptr(packed)))
+
+    def fill_synthetic(self, seed):
+        check(load().snpm_db_fill_synthetic(self._h, int(seed)))
+
+    def read_rows(self, rows):
+        rows = as_c(rows, np.int64).ravel()
+        out = np.empty((len(rows), self.n_acc), dtype=np.int8)
+        check(load().snpm_db_read_rows_int8(self._h, ptr(rows), len(rows), ptr(out)))
+        return out
+
+    def read_packed(self, row0, n):
+        out = np.empty((n, self.row_words), dtype=np.uint64)
+        check(load().snpm_db_read_packed(self._h, row0, n, ptr(out)))
+        return out
+
+    def set_stream(self, cuda_stream):
+        check(load().snpm_db_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def intersect(self, s_chrom_id, s_pos, algo=JOIN_AUTO):
+        s_chrom_id = as_c(s_chrom_id, np.int32)
+        s_pos = as_c(s_pos, np.int32)
+        n = len(s_pos)
+        db_idx = np.empty(max(n, 1), dtype=np.int64)
+        s_idx = np.empty(max(n, 1), dtype=np.int64)
+        m = C.c_int64(0)
+        check(load().snpm_intersect(self._h, ptr(s_chrom_id), ptr(s_pos), n, algo, ptr(db_idx), ptr(s_idx), C.byref(m)))
+        return db_idx[:m.value].copy(), s_idx[:m.value].copy()
+
+
+class Batch(object):
+    """One or more samples resident on the device next to a Database, plus their results."""
+
+    def __init__(self, db, offsets, s_chrom_id, s_pos, wei):
+        self.db = db
+        self._h = None
+        args = self._prep(offsets, s_chrom_id, s_pos, wei)
+        h = C.c_void_p()
+        check(load().snpm_batch_create(db._h, self.n_samples, *[ptr(a) for a in args], C.byref(h)))
+        self._h = h
+
+    def _prep(self, offsets, s_chrom_id, s_pos, wei):
+        offsets = as_c(offsets, np.int64)
+        s_chrom_id = as_c(s_chrom_id, np.int32)
+        s_pos = as_c(s_pos, np.int32)
+        wei = as_c(wei, np.float64).reshape(-1, 3)
+        assert len(s_chrom_id) == len(s_pos) == len(wei) == int(offsets[-1])
+        self.n_samples = len(offsets) - 1
+        self.offsets = offsets
+        self._keep = (offsets, s_chrom_id, s_pos, wei)
+        return self._keep
+
+    def upload(self, offsets, s_chrom_id, s_pos, wei):
+        """Replace the batch's samples, reusing its device buffers (queued on the stream)."""
+        args = self._prep(offsets, s_chrom_id, s_pos, wei)
+        check(load().snpm_batch_upload(self._h, self.n_samples, *[ptr(a) for a in args]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().snpm_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_row_filter(self, rows):
+        rows = as_c(np.unique(np.asarray(rows, dtype=np.int64)), np.int64) if rows is not None else np.zeros(0, np.int64)
+        check(load().snpm_batch_set_row_filter(self._h, ptr(rows) if len(rows) else None, len(rows)))
+
+    def run(self, skip_db_hets=False, kernel_mode=0, join_algo=JOIN_AUTO):
+        check(load().snpm_batch_run(self._h, int(bool(skip_db_hets)), int(kernel_mode) | (int(join_algo) << 8)))
+
+    def epilogue(self):
+        check(load().snpm_batch_epilogue(self._h))
+
+    def wait(self):
+        ms = C.c_float(0)
+        check(load().snpm_batch_wait(self._h, C.byref(ms)))
+        return ms.value
+
+    def timings(self):
+        ms = np.zeros(6, dtype=np.float32)
+        check(load().snpm_batch_timings(self._h, ptr(ms), 6))
+        return {"join_ms": float(ms[0]), "score_ms": float(ms[1]), "combine_ms": float(ms[2]), "epilogue_ms": float(ms[3]),
+                "total_ms": float(ms[4]), "launches": int(ms[5])}
+
+    def reduce_buffer(self):
+        """(device pointer, number of f64) of the per-sample totals — the payload of the cross-GPU sum."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        check(load().snpm_batch_reduce_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def fetch(self, epilogue=True, out=None):
+        S, A = self.n_samples, self.db.n_acc
+        r = out if out is not None else {}
+        if "score" not in r:
+            r["score"] = np.empty((S, A), dtype=np.float64)
+            r["m"] = np.empty(S, dtype=np.int64)
+            if epilogue:
+                r["matches"] = np.empty((S, A), dtype=np.int64)
+                r["ninfo"] = np.empty((S, A), dtype=np.int64)
+                r["prob"] = np.empty((S, A), dtype=np.float64)
+                r["L"] = np.empty((S, A), dtype=np.float64)
+                r["LR"] = np.empty((S, A), dtype=np.float64)
+        check(load().snpm_batch_fetch(self._h, ptr(r["score"]), ptr(r.get("matches")), ptr(r.get("ninfo")), ptr(r["m"]),
+                                      ptr(r.get("prob")), ptr(r.get("L")), ptr(r.get("LR"))))
+        return r
+
+    def fetch_pairs(self, s=0):
+        n = int(self.offsets[s + 1] - self.offsets[s])
+        db_idx = np.empty(max(n, 1), dtype=np.int64)
+        s_idx = np.empty(max(n, 1), dtype=np.int64)
+        m = C.c_int64(0)
+        check(load().snpm_batch_fetch_pairs(self._h, s, ptr(db_idx), ptr(s_idx), n, C.byref(m)))
+        return db_idx[:m.value].copy(), s_idx[:m.value].copy()
+
+    def run_windows(self, skip_db_hets, bin_len, win_count, win_off, n_windows, kmax, lr_thres=3.841):
+        win_count = as_c(win_count, np.int32)
+        win_off = as_c(win_off, np.int32)
+        kmax = as_c(kmax, np.int32)
+        self.n_windows = int(n_windows)
+        check(load().snpm_batch_run_windows(self._h, int(bool(skip_db_hets)), int(bin_len), ptr(win_count), ptr(win_off),
+                                            self.n_windows, ptr(kmax), len(kmax), float(lr_thres)))
+
+    def fetch_windows(self):
+        W, A = self.n_windows, self.db.n_acc
+        n = int(self.offsets[1])
+        r = {"score": np.empty((W, A), np.float64), "ninfo": np.empty((W, A), np.int32), "L": np.empty((W, A), np.float64),
+             "LR": np.empty((W, A), np.float64), "identical": np.empty((W, A), np.uint8), "num_amb": np.empty(W, np.int32),
+             "nrows": np.empty(W, np.int32)}
+        tar = np.empty(max(n, 1), dtype=np.int64)
+        m = C.c_int64(0)
+        check(load().snpm_batch_fetch_windows(self._h, ptr(r["score"]), ptr(r["ninfo"]), ptr(r["L"]), ptr(r["LR"]),
+                                              ptr(r["identical"]), ptr(r["num_amb"]), ptr(r["nrows"]), ptr(tar), n, C.byref(m)))
+        r["matched_s_idx"] = tar[:m.value].copy()
+        return r
+
+    def f1_pairs(self, acc_idx):
+        acc_idx = as_c(acc_idx, np.int32)
+        k = len(acc_idx)
+        n_pairs = k * (k - 1) // 2
+        score = np.empty(n_pairs, dtype=np.float64)
+        ninfo = np.empty(n_pairs, dtype=np.int64)
+        check(load().snpm_batch_f1_pairs(self._h, ptr(acc_idx), k, ptr(score), ptr(ninfo)))
+        return score, ninfo
+
+
+def match_gts_accs(wei, snps, skip_hets_db=False, device=0):
+    wei = as_c(wei, np.float64)
+    snps = as_c(snps, np.int8)
+    k, n_acc = snps.shape
+    score = np.empty(n_acc, dtype=np.float64)
+    ninfo = np.empty(n_acc, dtype=np.int64)
+    check(load().snpm_match_gts_accs(device, ptr(wei), ptr(snps), k, n_acc, int(bool(skip_hets_db)), ptr(score), ptr(ninfo)))
+    return score, ninfo
+
+
+def calculate_likelihoods(scores, ninfo, amin="calc", device=0):
+    scores = as_c(scores, np.float64).ravel()
+    ninfo = as_c(ninfo, np.float64).ravel()
+    n = len(scores)
+    prob = np.empty(n, dtype=np.float64)
+    lik = np.empty(n, dtype=np.float64)
+    lr = np.empty(n, dtype=np.float64)
+    calc = amin == "calc"
+    check(load().snpm_calculate_likelihoods(device, ptr(scores), ptr(ninfo), n, int(calc), 0.0 if calc else float(amin),
+                                            ptr(prob), ptr(lik), ptr(lr)))
+    return prob, lik, lr

@@ -1,0 +1,408 @@
+"""Parity of the CUDA path (through the C ABI / the Python mirror of the reference interface) against
+the CPU oracle and the golden vectors generated from the unmodified reference.
+
+Bars: integers, indices and — because the kernels sum in the reference's order — the fp64 scores are
+bit-exact; likelihoods / ratios / probabilities agree to rtol 1e-9 (north star asks 1e-6)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import snpmatch_oracle as orc
+from snpmatch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from snpmatch_b200 import lib as L
+    assert L.device_count() > 0, "GPU tests need a CUDA device"
+    return L
+
+
+@pytest.fixture(scope="module")
+def small_geno(lib, small_panel):
+    from snpmatch_b200.core import snp_genotype
+    p = small_panel
+    g = snp_genotype.Genotype.from_arrays(p["snps"], p["positions"], p["chrs"], p["chr_regions"], p["accessions"])
+    yield g
+    g.close()
+
+
+# ---- A0 -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_acc", [1, 31, 32, 33, 64, 70, 300, 1135])
+def test_pack_roundtrip_and_layout(lib, n_acc):
+    rng = np.random.default_rng(n_acc)
+    n = 257
+    snps = rng.choice(np.array([-1, 0, 1, 2], dtype=np.int8), size=(n, n_acc), p=[0.1, 0.5, 0.3, 0.1])
+    pos = np.arange(1, n + 1, dtype=np.int32)
+    db = lib.Database(pos, np.array([[0, n]]), n_acc)
+    db.load_int8(snps)
+    assert np.array_equal(db.read_packed(0, n), orc.pack_2bit_words(snps))
+    rows = rng.integers(0, n, size=100)
+    assert np.array_equal(db.read_rows(rows), snps[rows])
+    # packed load path
+    db2 = lib.Database(pos, np.array([[0, n]]), n_acc)
+    db2.load_packed(orc.pack_2bit_words(snps))
+    assert np.array_equal(db2.read_rows(np.arange(n)), snps)
+    db.close(); db2.close()
+
+
+def test_synthetic_fill_matches_host_hash(lib):
+    n_rows, n_acc = 5000, 333
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    rows = np.array([0, 1, 2, 77, 1234, 4998, 4999])
+    assert np.array_equal(db.read_rows(rows), synth.panel_codes(synth.SEED_PANEL, rows, n_acc))
+    db.close()
+    # a shard generates the same global rows
+    db = lib.Database(pos[1000:3000], np.clip(regions, 1000, 3000) - 1000, n_acc, row0_global=1000)
+    db.fill_synthetic(synth.SEED_PANEL)
+    assert np.array_equal(db.read_rows(np.array([0, 5, 1999])), synth.panel_codes(synth.SEED_PANEL, np.array([1000, 1005, 2999]), n_acc))
+    db.close()
+
+
+# ---- A2 -------------------------------------------------------------------------------------------
+def test_match_gts_accs_golden_bit_exact(lib):
+    from snpmatch_b200.core import snpmatch
+    g = load_golden("match_gts_accs.npz")
+    for i in range(int(g["n_cases"])):
+        score, ninfo = snpmatch.matchGTsAccs(g["c%d_wei" % i], g["c%d_snps" % i].copy(), bool(g["c%d_skip" % i]))
+        assert np.array_equal(ninfo, g["c%d_ninfo" % i]), "ninfo, case %d" % i
+        assert np.array_equal(score, g["c%d_score" % i]), "fp64 score not bit-exact, case %d" % i
+
+
+@pytest.mark.parametrize("k,n_acc", [(0, 5), (1, 1), (63, 40), (64, 129), (65, 1135), (1000, 1135), (2500, 777), (130, 2000)])
+def test_match_gts_accs_vs_oracle(lib, k, n_acc):
+    rng = np.random.default_rng(k * 7 + n_acc)
+    snps = rng.choice(np.array([-1, 0, 1, 2], dtype=np.int8), size=(k, n_acc), p=[0.1, 0.55, 0.3, 0.05])
+    code = rng.choice([0, 1, 2], size=k, p=[0.7, 0.25, 0.05]).astype(np.int8)
+    wei = synth._pl_weights(rng, code, 1 + rng.poisson(3, size=k))[1] if k else np.zeros((0, 3))
+    for skip in (False, True):
+        score, ninfo = lib.match_gts_accs(wei, snps, skip)
+        ref_s, ref_n = orc.match_gts_accs(wei, snps, skip)
+        assert np.array_equal(ninfo, ref_n)
+        assert np.array_equal(score, ref_s)
+
+
+def test_match_gts_accs_edge_weights(lib):
+    # many exact 1.0 weights plus tiny ones: the truncation edge of SURVEY section 7 hard part 1
+    k, n_acc = 3000, 64
+    rng = np.random.default_rng(1)
+    snps = rng.choice(np.array([0, 1], dtype=np.int8), size=(k, n_acc))
+    wei = np.zeros((k, 3))
+    wei[:, 0] = 1.0
+    wei[:, 2] = np.exp(-rng.integers(200, 900, size=k) / 10.0)
+    snps[:, 5] = 0
+    score, ninfo = lib.match_gts_accs(wei, snps)
+    ref_s, ref_n = orc.match_gts_accs(wei, snps)
+    assert np.array_equal(score, ref_s) and np.array_equal(ninfo, ref_n)
+    assert score[5] == 3000.0 and int(score[5]) == 3000
+
+
+# ---- A4 -------------------------------------------------------------------------------------------
+def test_likelihood_known_answers(lib):
+    from snpmatch_b200.core import snpmatch
+    assert abs(snpmatch.likeliTest(10, 3) - 122.8361221819443) <= 1e-12 * 122.8361221819443   # tests/test_inbred.py:22
+    assert np.isnan(snpmatch.likeliTest(10, 0))                                               # tests/test_inbred.py:24
+    assert np.isnan(snpmatch.likeliTest(0, 0))
+    assert snpmatch.likeliTest(7, 7) == 1.0
+    with pytest.raises(AssertionError):
+        snpmatch.likeliTest(3, 4)
+
+
+def test_epilogue_golden_sets(lib):
+    from snpmatch_b200.core import snpmatch
+    g = load_golden("epilogue.npz")
+    for i in range(int(g["n_sets"])):
+        L, LR = snpmatch.GenotyperOutput.calculate_likelihoods(g["e%d_y" % i], g["e%d_n" % i])
+        np.testing.assert_allclose(L, g["e%d_L" % i], rtol=RTOL, equal_nan=True)
+        np.testing.assert_allclose(LR, g["e%d_LR" % i], rtol=RTOL, equal_nan=True)
+    prob, L, LR = lib.calculate_likelihoods(np.array([3.0, 5.0]), np.array([10.0, 10.0]), amin=2.0)
+    np.testing.assert_allclose(LR, L / 2.0, rtol=1e-15)
+    np.testing.assert_allclose(prob, [0.3, 0.5], rtol=0)
+
+
+# ---- A1 -------------------------------------------------------------------------------------------
+def test_join_golden_cases(lib):
+    from snpmatch_b200.core import snp_genotype
+    g = load_golden("join.npz")
+    for i in range(int(g["n_cases"])):
+        i1, i2 = snp_genotype.Genotype.get_common_positions(g["j%d_c1" % i], g["j%d_p1" % i], g["j%d_c2" % i], g["j%d_p2" % i])
+        assert np.array_equal(i1, g["j%d_i1" % i]), "db side, case %d" % i
+        assert np.array_equal(i2, g["j%d_i2" % i]), "sample side, case %d" % i
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("n_db,n_s", [(6000, 0), (6000, 1), (6000, 2900), (200000, 5000), (200000, 150000)])
+def test_join_search_and_mergepath_agree_with_oracle(lib, algo, n_db, n_s):
+    rng = np.random.default_rng(n_db + n_s + algo)
+    pos, regions = synth.panel_positions(n_db)
+    db = lib.Database(pos, regions, 3)
+    rows = np.sort(rng.choice(n_db, size=min(n_s, n_db) * 9 // 10, replace=False))
+    chrom = np.searchsorted(regions[:, 1], rows, side="right")
+    extra = n_s - len(rows)
+    e_chr = rng.integers(0, 6, size=extra)                    # chromosome 5 does not exist in the panel
+    e_pos = rng.integers(1, 18_000_000, size=extra)
+    s_chr = np.concatenate([chrom, e_chr])
+    s_pos = np.concatenate([pos[rows].astype(np.int64), e_pos])
+    key = np.unique(s_chr.astype(np.int64) * (1 << 32) + s_pos)
+    s_chr, s_pos = (key >> 32).astype(np.int32), (key & 0xFFFFFFFF).astype(np.int32)
+    cid = np.where(s_chr < 5, s_chr, -1).astype(np.int32)
+    db_idx, s_idx = db.intersect(cid, s_pos, algo)
+    names = np.array(["1", "2", "3", "4", "5"])
+    labels = orc.db_chromosome_labels(names, regions)
+    o1, o2 = orc.get_common_positions(labels, pos, np.array(["Chr%d" % (c + 1) for c in s_chr]), s_pos)
+    assert np.array_equal(db_idx, o1) and np.array_equal(s_idx, o2)
+    db.close()
+
+
+def test_join_rejects_unsorted_markers(lib):
+    pos, regions = synth.panel_positions(6000)
+    db = lib.Database(pos, regions, 3)
+    with pytest.raises(lib.SnpmError):
+        db.intersect(np.zeros(3, np.int32), np.array([50, 40, 60], np.int32))
+    db.close()
+
+
+# ---- A3 + A4: inbred ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,wei_key,skip", [("pl", "wei", False), ("pl_skip", "wei", True), ("hard", "wei_hard", False)])
+def test_inbred_workflow_files_and_arrays(lib, small_geno, sample_inbred, golden_outputs, tmp_path, tag, wei_key, skip):
+    from snpmatch_b200.core import parsers, snpmatch
+    g = load_golden("inbred_%s.npz" % tag)
+    s = sample_inbred
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s[wei_key], s["dp"])
+    out = str(tmp_path / ("inbred_" + tag))
+    gt = snpmatch.Genotyper(inp, small_geno, out, run_genotyper=True, skip_db_hets=skip)
+    r = gt.result
+    assert np.array_equal(gt.commonSNPs[0], g["common_db"]) and np.array_equal(gt.commonSNPs[1], g["common_s"])
+    assert r.num_snps == int(g["num_snps"]) and r.overlap == float(g["overlap"])
+    assert np.array_equal(r.scores, g["scores"]) and np.array_equal(r.ninfo, g["ninfo"])
+    np.testing.assert_allclose(r.probabilies, g["probs"], rtol=0, atol=0, equal_nan=True)
+    np.testing.assert_allclose(r.likelis, g["likelis"], rtol=RTOL, equal_nan=True)
+    np.testing.assert_allclose(r.lrts, g["lrts"], rtol=RTOL, equal_nan=True)
+    want = golden_outputs["inbred_" + tag]
+    _compare_tables(open(out + ".scores.txt").read(), want["scores.txt"], int_cols=(1, 2, 6), float_cols=(3, 4, 5, 7))
+    _json_close(json.loads(open(out + ".matches.json").read()), json.loads(want["matches.json"]))
+
+
+def _json_close(a, b, rtol=RTOL):
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and sorted(a) == sorted(b), (sorted(a), sorted(b))
+        for k in a:
+            _json_close(a[k], b[k], rtol)
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            _json_close(x, y, rtol)
+    elif isinstance(a, float) or isinstance(b, float):
+        if a is None or b is None:
+            assert a is b
+        elif np.isnan(a) or np.isnan(b):
+            assert np.isnan(a) and np.isnan(b)
+        else:
+            assert abs(a - b) <= rtol * abs(b), (a, b)
+    else:
+        assert a == b, (a, b)
+    return True
+
+
+def _compare_tables(got, want, int_cols, float_cols, header=False):
+    g_lines, w_lines = got.strip("\n").split("\n"), want.strip("\n").split("\n")
+    assert len(g_lines) == len(w_lines)
+    if header:
+        assert g_lines[0] == w_lines[0]
+        g_lines, w_lines = g_lines[1:], w_lines[1:]
+    for gl, wl in zip(g_lines, w_lines):
+        gf, wf = gl.split("\t"), wl.split("\t")
+        assert len(gf) == len(wf) and gf[0] == wf[0]
+        for c in int_cols:
+            assert gf[c] == wf[c], (gl, wl)
+        for c in float_cols:
+            if wf[c] in ("", "nan"):
+                assert gf[c] == wf[c], (gl, wl)
+            else:
+                assert abs(float(gf[c]) - float(wf[c])) <= RTOL * abs(float(wf[c])), (gl, wl)
+
+
+# ---- A5 + A6 + A7: cross ------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,sample_name,wei_key,skip", [("pl", "cross", "wei", False), ("hard_skip", "cross", "wei_hard", True),
+                                                          ("inbredlike", "inbred", "wei", False)])
+def test_cross_workflow_files_and_arrays(lib, small_geno, sample_inbred, sample_cross, golden_outputs, tmp_path, tag, sample_name,
+                                         wei_key, skip):
+    from snpmatch_b200.core import csmatch, parsers
+    g = load_golden("cross_%s.npz" % tag)
+    s = sample_cross if sample_name == "cross" else sample_inbred
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s[wei_key], s["dp"])
+    out = str(tmp_path / ("cross_" + tag))
+    ci = csmatch.CrossIdentifier(inp, small_geno, "athaliana_tair10", 300000, out, run_identifier=True, skip_db_hets=skip)
+    r = ci.result
+    n_acc = 40
+    assert r.num_snps == int(g["num_snps"]) and r.overlap == float(g["overlap"])
+    assert np.array_equal(r.matchedTarInd, g["matchedTarInd"])
+    assert np.array_equal(r.winds_chrs, g["winds_chrs"])
+    assert np.array_equal(r.accs, g["accs"])
+    assert np.array_equal(r.ninfo, g["ninfo"])
+    assert np.array_equal(r.scores[:n_acc], g["scores"][:n_acc])                       # truncated window totals: exact
+    np.testing.assert_allclose(r.scores[n_acc:], g["scores"][n_acc:], rtol=RTOL)        # simulated F1 rows: float sums
+    np.testing.assert_allclose(r.likelis, g["likelis"], rtol=RTOL, equal_nan=True)
+    np.testing.assert_allclose(r.lrts, g["lrts"], rtol=RTOL, equal_nan=True)
+    want = golden_outputs["cross_" + tag]
+    _compare_tables(open(out + ".windowscore.txt").read(), want["windowscore.txt"], int_cols=(1, 2, 6, 7), float_cols=(3, 4, 5), header=True)
+    _compare_tables(open(out + ".scores.txt").read(), want["scores.txt"], int_cols=(2, 6), float_cols=(1, 3, 4, 5, 7))
+    _json_close(json.loads(open(out + ".scores.txt.matches.json").read()), json.loads(want["scores.txt.matches.json"]))
+    assert os.path.exists(out + ".matches.json") == ("matches.json" in want)
+    if "matches.json" in want:
+        _json_close(json.loads(open(out + ".matches.json").read()), json.loads(want["matches.json"]))
+
+
+def test_window_scores_bit_exact_vs_oracle(lib, small_geno, small_panel, sample_cross):
+    from snpmatch_b200.core import genomes, snpmatch
+    p, s = small_panel, sample_cross
+    w = orc.window_genotyper(p["snps"], p["chrs"], p["chr_regions"], p["positions"], s["chrs"], s["pos"], s["wei"],
+                             synth.TAIR10_CHRS, synth.TAIR10_CHRLEN, 300000, False)
+    gen = genomes.Genome("athaliana_tair10")
+    cnt, off, n_w, _ = gen.window_layout(p["chrs"], 300000)
+    order, cid, pos = small_geno.prepare_markers(s["chrs"], s["pos"], style="genome")
+    b = lib.Batch(small_geno.db, [0, len(pos)], cid, pos, s["wei"][order])
+    b.run_windows(False, 300000, cnt, off, n_w, snpmatch.identity_kmax_table(500, 0.02))
+    b.epilogue()
+    tot = b.fetch()
+    win = b.fetch_windows()
+    assert n_w == w.n_windows == 399
+    assert np.array_equal(tot["score"][0], w.tot_score) and np.array_equal(tot["ninfo"][0], w.tot_ninfo)
+    assert int(tot["m"][0]) == w.num_snps
+    seen = np.zeros(n_w, bool)
+    for widx, sc, ni in w.windows:
+        assert np.array_equal(win["score"][widx - 1], sc), "window %d" % widx
+        assert np.array_equal(win["ninfo"][widx - 1], ni)
+        lik, lr, ident, num_amb, keep = orc.window_epilogue(sc, ni, 0.02)
+        np.testing.assert_allclose(win["L"][widx - 1], lik, rtol=RTOL, equal_nan=True)
+        np.testing.assert_allclose(win["LR"][widx - 1], lr, rtol=RTOL, equal_nan=True)
+        assert np.array_equal(win["identical"][widx - 1], ident)
+        assert int(win["num_amb"][widx - 1]) == num_amb
+        seen[widx - 1] = True
+    assert np.array_equal(win["nrows"] > 0, seen)
+    b.close()
+
+
+def test_vcf701_repo_config(lib, golden_outputs, tmp_path):
+    """BASELINE configs[0] stand-in: the reference's sample VCF (parsed weights committed as a fixture)
+    against a synthetic database over its positions; inbred and cross outputs vs the reference's."""
+    from snpmatch_b200.core import csmatch, parsers, snp_genotype, snpmatch
+    p = load_golden("vcf701_panel.npz")
+    s = load_golden("vcf701_sample.npz")
+    g = snp_genotype.Genotype.from_arrays(p["snps"], p["positions"], p["chrs"], p["chr_regions"], p["accessions"])
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei"], s["dp"])
+    out = str(tmp_path / "vcf701")
+    snpmatch.Genotyper(inp, g, out)
+    want = golden_outputs["vcf701_inbred"]
+    _compare_tables(open(out + ".scores.txt").read(), want["scores.txt"], int_cols=(1, 2, 6), float_cols=(3, 4, 5, 7))
+    _json_close(json.loads(open(out + ".matches.json").read()), json.loads(want["matches.json"]))
+    csmatch.CrossIdentifier(inp, g, "athaliana_tair10", 300000, out + "_cross")
+    want = golden_outputs["vcf701_cross"]
+    _compare_tables(open(out + "_cross.windowscore.txt").read(), want["windowscore.txt"], int_cols=(1, 2, 6, 7), float_cols=(3, 4, 5), header=True)
+    _compare_tables(open(out + "_cross.scores.txt").read(), want["scores.txt"], int_cols=(2, 6), float_cols=(1, 3, 4, 5, 7))
+    assert not os.path.exists(out + "_cross.matches.json")
+    g.close()
+
+
+# ---- batches ------------------------------------------------------------------------------------------
+def test_batch_of_samples_equals_single_runs(lib):
+    n_rows, n_acc = 60000, 1135
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=3 + 11 * i, n_db=nd, n_extra=ne, seed=900 + i)
+               for i, (nd, ne) in enumerate([(2500, 200), (0, 50), (999, 0), (1000, 1), (1001, 7), (4321, 300)])]
+    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])])
+    b = lib.Batch(db, offs, np.concatenate([s["chr_ix"] for s in samples]), np.concatenate([s["pos"] for s in samples]),
+                  np.concatenate([s["wei"] for s in samples]))
+    b.run()
+    b.epilogue()
+    r = b.fetch()
+    for i, s in enumerate(samples):
+        rows = np.sort(s["rows"]) if "rows" in s else None
+        db_idx, s_idx = b.fetch_pairs(i)
+        codes = synth.panel_codes(synth.SEED_PANEL, db_idx, n_acc)
+        score = np.zeros(n_acc)
+        ninfo = np.zeros(n_acc, dtype=np.int64)
+        for j in range(0, len(db_idx), 1000):
+            t_s, t_n = orc.match_gts_accs(s["wei"][s_idx[j:j + 1000]], codes[j:j + 1000])
+            score = score + t_s
+            ninfo = ninfo + t_n
+        assert int(r["m"][i]) == len(db_idx)
+        assert np.array_equal(pos[db_idx].astype(np.int64), s["pos"][s_idx])
+        assert np.array_equal(r["score"][i], score) and np.array_equal(r["ninfo"][i], ninfo)
+        assert np.array_equal(r["matches"][i], score.astype(np.int64))
+        lik, lr = orc.calculate_likelihoods(score.astype(np.int64), ninfo)
+        np.testing.assert_allclose(r["L"][i], lik, rtol=RTOL, equal_nan=True)
+        np.testing.assert_allclose(r["LR"][i], lr, rtol=RTOL, equal_nan=True)
+        if len(db_idx) > 500:
+            assert int(np.nanargmin(r["L"][i])) == 3 + 11 * i
+    # re-upload into the same batch object
+    s = samples[0]
+    b.upload([0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei_hard"])
+    b.run(skip_db_hets=True)
+    b.epilogue()
+    r1 = b.fetch()
+    one = lib.Batch(db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei_hard"])
+    one.run(skip_db_hets=True)
+    one.epilogue()
+    r2 = one.fetch()
+    for k in ("score", "matches", "ninfo", "m"):
+        assert np.array_equal(r1[k], r2[k])
+    t = one.timings()
+    assert t["launches"] >= 6 and t["total_ms"] > 0
+    one.close(); b.close(); db.close()
+
+
+def test_row_filter_refine_path(lib, small_geno, small_panel, sample_inbred):
+    p, s = small_panel, sample_inbred
+    keep_rows = np.arange(0, 6000, 3)
+    ref = orc.genotyper(p["snps"], p["chrs"], p["chr_regions"], p["positions"], s["chrs"], s["pos"], s["wei"], filter_pos_ix=keep_rows)
+    order, cid, pos = small_geno.prepare_markers(s["chrs"], s["pos"])
+    b = lib.Batch(small_geno.db, [0, len(pos)], cid, pos, s["wei"][order])
+    b.set_row_filter(keep_rows)
+    b.run()
+    b.epilogue()
+    r = b.fetch()
+    assert int(r["m"][0]) == ref.num_snps
+    assert np.array_equal(r["score"][0], ref.score_f64) and np.array_equal(r["ninfo"][0], ref.ninfo)
+    b.close()
+
+
+def test_dense_sample_properties(lib):
+    """Full-size shape check by properties: a sample that carries EVERY database row of one accession
+    must match that accession perfectly; ninfo equals the accession's called rows."""
+    n_rows, n_acc = 300000, 1135
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    rows = np.arange(n_rows)
+    code = synth.panel_codes_cols(synth.SEED_PANEL, rows, [42])[:, 0]
+    chrom = np.searchsorted(regions[:, 1], rows, side="right").astype(np.int32)
+    wei = synth.hard_weights(np.where(code < 0, 0, code))
+    for algo in (1, 2):
+        b = lib.Batch(db, [0, n_rows], chrom, pos, wei)
+        b.run(join_algo=algo)
+        b.epilogue()
+        r = b.fetch()
+        called = int((code >= 0).sum())
+        assert int(r["m"][0]) == n_rows
+        assert int(r["ninfo"][0, 42]) == called and int(r["matches"][0, 42]) == called
+        assert r["L"][0, 42] == 1.0 and int(np.nanargmin(r["L"][0])) == 42
+        assert r["ninfo"][0].max() <= n_rows and (r["matches"][0] <= r["ninfo"][0]).all()
+        b.close()
+    db.close()

@@ -1,0 +1,144 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every declared symbol; host logic
+(identity table, window geometry, marker preparation, parsers) against the oracle / golden facts."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import snpmatch_oracle as orc
+from snpmatch_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from snpmatch_b200 import lib
+    return lib
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = built_lib
+    header = open(os.path.join(ROOT, "include", "snpmatch_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(snpm_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    handle = lib.load()
+    for name in sorted(declared):
+        assert hasattr(handle, name), "libsnpmatch_b200.so does not export %s" % name
+    assert declared == set(lib.SIGNATURES), "lib.py binds %s" % sorted(declared ^ set(lib.SIGNATURES))
+    assert handle.snpm_version() == 100
+
+
+def test_no_device_is_a_loud_failure(built_lib):
+    lib = built_lib
+    if lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(lib.SnpmError):
+        lib.Database(np.arange(1, 11, dtype=np.int32), np.array([[0, 10]]), 4)
+    with pytest.raises(lib.SnpmError):
+        lib.match_gts_accs(np.ones((2, 3)), np.zeros((2, 4), dtype=np.int8))
+
+
+def test_identity_table_matches_bruteforce():
+    from snpmatch_b200.core import snpmatch
+    for e in (0.02, 0.0005, 0.1):
+        fast = snpmatch.identity_kmax_table(1500, e)
+        slow = orc.identity_kmax_table(1500, e)
+        assert np.array_equal(fast[:1501], slow)
+    g = load_golden("epilogue.npz")
+    assert np.array_equal(snpmatch.np_test_identity(g["id_x"], g["id_n"], error_rate=0.02), g["id_e02"])
+    assert np.array_equal(snpmatch.np_test_identity(g["id_xf"], g["id_n"], error_rate=0.02), g["id_e02_f"])
+    assert np.array_equal(snpmatch.np_test_identity(g["id_x"], g["id_n"]), g["id_default"])
+
+
+def test_window_geometry():
+    from snpmatch_b200.core import genomes
+    gen = genomes.Genome("athaliana_tair10")
+    assert gen.chrs_ids.tolist() == ["1", "2", "3", "4", "5"]
+    cnt, off, n, winds = gen.window_layout(np.array(["Chr1", "chr2", "3", "4", "5"]), 300000)
+    assert n == 399 and cnt.tolist() == [102, 66, 79, 62, 90] and off.tolist() == [0, 102, 168, 247, 309]
+    assert len(winds) == 399 and winds[0] == "1" and winds[-1] == "5"
+    # a database that lists the chromosomes in another order, plus one the genome lacks (count 0)
+    gen2 = genomes.Genome("athaliana_tair10")
+    gen2.chrs_ids = np.array(["1", "2", "3", "4", "5", "c"])
+    gen2.chrlen = np.append(gen2.chrlen, 1000)
+    cnt, off, n, _ = gen2.window_layout(np.array(["5", "1", "C"]), 300000)
+    assert cnt.tolist() == [90, 102, 1] and off.tolist() == [309, 0, 399] and n == 400
+    # iterator API against a brute-force binning
+    rng = np.random.default_rng(5)
+    pos = np.sort(rng.choice(2_000_000, size=500, replace=False)) + 1
+    bins = list(genomes.get_bins_echr(1_900_000, pos, 300000, 7))
+    assert len(bins) == orc.num_windows(1_900_000, 300000) == 7
+    for k, (bed, idx) in enumerate(bins):
+        assert bed == [1 + k * 300000, (k + 1) * 300000]
+        want = [i + 7 for i, p in enumerate(pos) if bed[0] <= p <= bed[1]]
+        assert idx == want
+    assert np.array_equal(orc.window_of(pos, 1_900_000, 300000) >= 0, pos <= 7 * 300000)
+
+
+def test_prepare_markers_orders_like_the_reference_join():
+    from snpmatch_b200.core import snp_genotype
+    g = object.__new__(snp_genotype.Genotype)
+    g.chrs = np.array(["Chr1", "Chr3", "chrC"])
+    g._db_chr_norm = snp_genotype.normalize_chr_names(g.chrs)
+    chrs = np.array(["1", "1", "1", "2", "2", "ChrM", "ChrM", "C", "C"])
+    pos = np.array([9, 12, 13, 1, 2, 5, 6, 8, 9])
+    order, cid, p = g.prepare_markers(chrs, pos)
+    assert cid.tolist() == [0, 0, 0, 2, 2, -1, -1, -1, -1]
+    assert order.tolist() == [0, 1, 2, 7, 8, 3, 4, 5, 6] and p.tolist() == [9, 12, 13, 8, 9, 1, 2, 5, 6]
+    # unsorted chromosome -> sorted for the join; duplicates keep the first
+    order, cid, p = g.prepare_markers(np.array(["1", "1", "1", "1"]), np.array([30, 10, 20, 10]))
+    assert p[cid >= 0].tolist() == [10, 20, 30] and sorted(order.tolist()) == [0, 1, 2, 3]
+    assert order[:3].tolist() == [1, 2, 0]
+
+
+def test_synthetic_panel_is_block_addressable():
+    a = synth.panel_codes(synth.SEED_PANEL, np.arange(100, 140), 70)
+    b = synth.panel_codes_cols(synth.SEED_PANEL, np.arange(110, 120), np.arange(5, 50))
+    assert np.array_equal(a[10:20, 5:50], b)
+    pos, regions = synth.panel_positions(50000)
+    for s, e in regions:
+        assert np.all(np.diff(pos[s:e]) > 0)
+    assert regions[-1, 1] == 50000
+
+
+def test_pack_reference_layout():
+    rng = np.random.default_rng(3)
+    snps = rng.choice(np.array([-1, 0, 1, 2], dtype=np.int8), size=(5, 70))
+    packed = orc.pack_2bit_words(snps)
+    assert packed.shape == (5, 4) and packed.dtype == np.uint64     # 3 words padded to 4
+    for r in range(5):
+        for a in range(70):
+            w = int(packed[r, a // 32])
+            code = ((w >> (a % 32)) & 1) | ((((w >> 32) >> (a % 32)) & 1) << 1)
+            assert code == (int(snps[r, a]) & 3)
+    assert int(packed[0, 3]) == 2**64 - 1 and (int(packed[0, 2]) >> 6) & 1 == 1    # padding = missing
+
+
+REF_SAMPLES = "/root/reference/sample_files"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="reference sample files are only in the build container")
+def test_parsers_on_the_reference_sample_files(tmp_path, golden_outputs):
+    import shutil
+    from snpmatch_b200.core import parsers
+    vcf = tmp_path / "701_501.filter.vcf"
+    bed = tmp_path / "701_502.filter.bed"
+    shutil.copy(os.path.join(REF_SAMPLES, "701_501.filter.vcf"), vcf)      # the parser writes next to its input
+    shutil.copy(os.path.join(REF_SAMPLES, "701_502.filter.bed"), bed)
+    v = parsers.ParseInputs(str(vcf))
+    facts = golden_outputs["facts"]
+    assert len(v.chrs) == 7545 == facts["vcf_kept"]                          # tests/test_inbred.py:9-12
+    assert v.chrs[0] == "Chr1" and v.gt[0] == "0/0" and int(v.pos[0]) == 13226
+    np.testing.assert_allclose(v.wei.sum(axis=0), [6582.58869952, 3247.44885746, 903.85454402], rtol=1e-9)
+    np.testing.assert_allclose(v.wei[0], [1.0, 0.40656966, 1.66585811e-04], rtol=1e-7)
+    g = load_golden("vcf701_sample.npz")
+    assert np.array_equal(v.pos, g["pos"]) and np.array_equal(v.wei, g["wei"]) and np.array_equal(v.gt, g["gt"])
+    b = parsers.ParseInputs(str(bed))
+    assert len(b.chrs) == 10000 and b.chrs[0] == "1" and b.gt[0] == "0/0" and int(b.pos[1]) == 51103   # tests/test_inbred.py:14-18
+    assert os.path.isfile(str(bed) + ".snpmatch.npz") and os.path.isfile(str(bed) + ".snpmatch.stats.json")
+    again = parsers.ParseInputs(str(bed))                                    # npz cache path
+    assert np.array_equal(again.pos, b.pos) and np.array_equal(again.wei, b.wei)
