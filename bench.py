@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""
+bench.py — SNP x accession comparisons/s of the genotype-matching hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[1] — the synthetic 1001-Genomes-shaped panel
+(1135 accessions x 10.7 M SNPs, generated in HBM) scored against low-coverage samples with PL
+weights (~50 k markers each, ~45 k of them in the panel).  One step = one pass of the hot path
+(join + chunked scoring + combine + likelihood epilogue) over one batch of `--samples` independent
+samples, each scored on its own exactly as separate `snpmatch inbred` runs would.
+
+  value      comparisons/s with the batch already resident in HBM (device-timed, CUDA events on the
+             stream the kernels run on, max over ranks);
+  e2e        the same through the host-buffer API: per step the H2D copy of the samples from pinned
+             memory and the D2H read of scores / counts / likelihoods are inside the timed region;
+  roofline   the scoring kernel (k_score_segments): algorithmic bytes per launch / its CUDA-event time;
+  cpu_baseline  the CPU oracle (a NumPy restatement of the reference path) on one sample, one core.
+
+N > 1 (torchrun): the panel is sharded by SNP-row ranges, samples are replicated, per-GPU partial
+scores/counts are summed with one NCCL all-reduce, then the epilogue runs on the reduced totals.
+The batch grows with N (samples = N x --samples) so that per-GPU work is fixed: "scaling": "weak".
+
+`--impl reference` times the reference's own CPU path (oracle port; one process per sample on all
+host cores, the way the reference is deployed) for the same metric and config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ROWS = 10_700_000
+N_ACC = 1135
+N_DB_MARKERS = 45_000
+N_EXTRA_MARKERS = 5_000
+METRIC = "snp_accession_comparisons_per_sec"
+UNIT = "comparisons/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=64, help="samples per step and per GPU")
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--accessions", type=int, default=N_ACC)
+    ap.add_argument("--markers", type=int, default=N_DB_MARKERS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus, n_samples):
+    return {
+        "workload": "configs[1]: inbred scoring of %d low-coverage PL samples (~%d markers each, %d in the panel) against the "
+                    "synthetic 1001G-shaped panel %d accessions x %d SNPs" % (
+                        n_samples, args.markers + N_EXTRA_MARKERS, args.markers, args.accessions, args.rows),
+        "panel_rows": args.rows, "accessions": args.accessions, "samples_per_step": n_samples,
+        "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)",
+        "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + NCCL all-reduce of per-accession partials" % n_gpus,
+        "cache": "inputs larger than L2: each step gathers %.0f MB of distinct panel rows" % (
+            n_samples * args.markers * ((args.accessions + 63) // 64 * 16) / 1e6),
+    }
+
+
+def make_samples(positions, regions, n_acc, n_samples, n_markers, first_seed=5000):
+    from snpmatch_b200 import synth
+    out = []
+    for i in range(n_samples):
+        out.append(synth.make_sample_fast(positions, regions, n_acc, true_acc=(7 + 13 * i) % n_acc, n_db=n_markers,
+                                          n_extra=N_EXTRA_MARKERS, seed=first_seed + i))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, one sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_prepare_sample(sample, n_acc, max_markers=0):
+    """Materialise (outside the timed region) the panel rows the sample touches, as the in-RAM int8 matrix the
+    reference would read from HDF5."""
+    from snpmatch_b200 import synth
+    rows = sample["rows"][sample["rows"] >= 0]
+    if max_markers and len(rows) > max_markers:
+        rows = rows[:max_markers]
+    codes = synth.panel_codes(synth.SEED_PANEL, rows, n_acc)
+    return rows, codes
+
+
+def cpu_run_sample(positions, regions, sample, rows, codes):
+    """Timed region of the CPU arm: Genotyper.genotyper of the reference (snpmatch.py:207-233) as restated by
+    the oracle — the (chrom,pos) join over the database's per-row chromosome labels, then 1000-row chunks of
+    matchGTsAccs — plus the likelihood epilogue.  Returns (comparisons, seconds)."""
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import synth
+    n_acc = codes.shape[1]
+    names = np.array(synth.TAIR10_CHRS)
+    s_chrs = np.char.add("Chr", names[sample["chr_ix"]])
+    s_pos = sample["pos"].astype(np.int64)
+    lookup = np.full(len(positions), -1, dtype=np.int64)
+    lookup[rows] = np.arange(len(rows))
+    t0 = time.perf_counter()
+    labels = orc.db_chromosome_labels(names, regions)                 # pygwas/genotype.py:156-161
+    common = orc.get_common_positions(labels, positions, s_chrs, s_pos)
+    keep = lookup[common[0]] >= 0                                     # bounded sample: only the materialised rows
+    c0, c1 = common[0][keep], common[1][keep]
+    score = np.zeros(n_acc)
+    ninfo = np.zeros(n_acc, dtype=np.int64)
+    for j in range(0, len(c0), 1000):
+        t_s, t_n = orc.match_gts_accs(sample["wei"][c1[j:j + 1000]], codes[lookup[c0[j:j + 1000]]])
+        score = score + t_s
+        ninfo = ninfo + t_n
+    with np.errstate(all="ignore"):
+        orc.calculate_likelihoods(score.astype(np.int64), ninfo)
+    dt = time.perf_counter() - t0
+    return len(c0) * n_acc, dt, score, ninfo
+
+
+_W = {}
+
+
+def _worker(i):
+    s = _W["samples"][i]
+    comps, dt, _, _ = cpu_run_sample(_W["positions"], _W["regions"], s, *_W["prepared"][i])
+    return comps, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: one process per sample on all host cores (README.md:9 deployment model)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from snpmatch_b200 import synth
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = max(1, min(cores, 32))
+    positions, regions = synth.panel_positions(args.rows)
+    samples = make_samples(positions, regions, args.accessions, procs, args.markers)
+    cap = args.cpu_markers or 0
+    _W.update(positions=positions, regions=regions, samples=samples,
+              prepared=[cpu_prepare_sample(s, args.accessions, cap) for s in samples])
+    ctx = mp.get_context("fork")
+    times = []
+    comps = 0
+    with ctx.Pool(procs) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_worker, range(procs))
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+                comps = sum(r[0] for r in res)
+    total = sum(times)
+    value = comps * len(times) / total if total > 0 else 0.0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1, procs),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": "%d samples per step, one process each (join over the %d database labels + %d-marker "
+                                   "chunked matchGTsAccs + likelihoods); NumPy oracle port of snpmatch.py:207-233, database "
+                                   "rows held in RAM as int8" % (procs, args.rows, cap or args.markers)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class _DevArray(object):
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def run_b200_arm(args):
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    from snpmatch_b200 import lib, synth
+    from snpmatch_b200.core import snp_genotype
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert lib.device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(device=dev)
+
+    n_rows, n_acc = args.rows, args.accessions
+    S = args.samples * world
+    positions, regions = synth.panel_positions(n_rows)
+    r0, r1 = rank * n_rows // world, (rank + 1) * n_rows // world
+    g = snp_genotype.Genotype.synthetic(n_rows, n_acc, row_range=(r0, r1), device=local_rank)
+    db = g.db
+    db.set_stream(stream.cuda_stream)
+    samples = make_samples(positions, regions, n_acc, S, args.markers)
+    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])]).astype(np.int64)
+    n_tot = int(offs[-1])
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    arrs = []
+    for a in (offs, np.concatenate([s["chr_ix"] for s in samples]).astype(np.int32),
+              np.concatenate([s["pos"] for s in samples]).astype(np.int32),
+              np.concatenate([s["wei"] for s in samples]).astype(np.float64)):
+        t, v = pinned(a)
+        keep.append(t)
+        arrs.append(v)
+    h_off, h_chr, h_pos, h_wei = arrs
+    out_t = {k: torch.empty((S, n_acc), dtype=torch.float64 if k in ("score", "prob", "L", "LR") else torch.int64).pin_memory()
+             for k in ("score", "matches", "ninfo", "prob", "L", "LR")}
+    out_t["m"] = torch.empty(S, dtype=torch.int64).pin_memory()
+    out = {k: v.numpy() for k, v in out_t.items()}
+
+    batch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
+    red = None
+
+    def device_step():
+        nonlocal red
+        batch.run()
+        if world > 1:
+            if red is None:
+                p, n = batch.reduce_buffer()
+                red = torch.as_tensor(_DevArray(p, n), device=dev)
+            dist.all_reduce(red)
+        batch.epilogue()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    score_ms, total_launches = [], 0
+    with torch.cuda.stream(stream):
+        # ---- resident arm -------------------------------------------------------------------------
+        for _ in range(args.warmup):
+            device_step()
+        batch.wait()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            device_step()
+        ev1.record(stream)
+        batch.wait()
+        barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+        # per-kernel times of the scoring kernel: one more timed pass that reads the library's own events each step
+        for _ in range(args.steps):
+            device_step()
+            t = batch.timings()
+            score_ms.append(t["score_ms"])
+            total_launches = t["launches"]
+        barrier()
+        # ---- end-to-end arm: host buffers in, host buffers out -------------------------------------
+        def e2e_step():
+            batch.upload(h_off, h_chr, h_pos, h_wei)
+            device_step()
+            if rank == 0:
+                batch.fetch(out=out)
+            else:
+                batch.wait()
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if rank == 0 else None
+
+    m_per_sample = out["m"].astype(np.int64) if rank == 0 else None
+    tms = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(tms[0]), float(tms[1])
+
+    if rank == 0:
+        m_total = int(m_per_sample.sum())
+        comps = m_total * n_acc
+        value = comps * args.steps / (dev_ms * 1e-3)
+        e2e_value = comps * args.steps / (e2e_ms * 1e-3)
+        # roofline of the scoring kernel on this rank: its share of the matched rows
+        m_rank = m_total if world == 1 else None
+        local_rows = None
+        if world > 1:
+            local_rows = sum(int(((s["rows"] >= r0) & (s["rows"] < r1)).sum()) for s in samples)
+        rows_here = m_total if world == 1 else local_rows
+        algo_bytes = rows_here * ((n_acc + 3) // 4 + 24) + 16 * n_acc * S
+        k_ms = float(np.mean(score_ms))
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, S),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(world * (h_off.nbytes + h_chr.nbytes + h_pos.nbytes + h_wei.nbytes)),
+                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values()))},
+            "gpu_launches": int(total_launches * args.steps),
+            "roofline": {"bound": "hbm", "kernel": "k_score_segments", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "clocks": clocks,
+            "matched_markers_per_step": m_total,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            s0 = samples[0]
+            rows, codes = cpu_prepare_sample(s0, n_acc, args.cpu_markers)
+            c, dt, cpu_score, cpu_ninfo = cpu_run_sample(positions, regions, s0, rows, codes)
+            line["cpu_baseline"] = {"value": c / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+                                    "sample": "sample 0 of the batch (%d matched markers x %d accessions): join over the %d "
+                                              "database labels + chunked matchGTsAccs + likelihoods, NumPy oracle port of "
+                                              "snpmatch.py:207-233, database rows held in RAM as int8" % (len(rows), n_acc, n_rows)}
+            if not args.cpu_markers:
+                line["cpu_baseline"]["parity"] = bool(np.array_equal(cpu_score, out["score"][0]) and
+                                                      np.array_equal(cpu_ninfo, out["ninfo"][0]))
+        print(json.dumps(line))
+    batch.close()
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

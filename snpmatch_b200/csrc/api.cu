@@ -37,7 +37,7 @@ static int launch_score(cudaStream_t st, const ScoreArgs &a, int grid_x, bool sk
         attr_set[skip_hets ? 1 : 0] = true;
     }
     if (grid_x <= 0) return SNPM_OK;
-    dim3 grid(grid_x, yb), block(32, nw);
+    dim3 grid(grid_x, yb), block(32, nw + 1);      // + the producer warp
     if (skip_hets) k_score_segments<true><<<grid, block, smem, st>>>(a);
     else k_score_segments<false><<<grid, block, smem, st>>>(a);
     SNPM_KERNEL_CHECK();

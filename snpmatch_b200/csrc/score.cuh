@@ -6,20 +6,27 @@
 // per accession and class a plain left-to-right sum over the segment's rows, classes combined as
 // ((0 + ref) + het) + alt, so fp64 scores are bit-identical to NumPy's.
 //
-// Mapping: lane = accession inside a 32-accession word, a warp owns SC_WPW consecutive words, a CTA
-// owns a contiguous word slice of every row of ONE segment.  Row slices (gathered rows of the 2-bit
-// panel) and the segment's weights travel HBM -> shared memory as 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx) through an SC_STAGES-deep ring, issued by warp 0 while all
-// warps reduce the previous tile from shared memory with broadcast 128-bit loads.
+// Data movement: a CTA owns a contiguous word slice of every row of ONE segment.  A dedicated producer
+// warp gathers the segment's rows of the 2-bit panel (one 1-D TMA bulk copy per row, cp.async.bulk +
+// mbarrier complete_tx) and the matched weights (one bulk copy per tile) into an SC_STAGES-deep shared
+// memory ring; consumer warps release a stage through an "empty" mbarrier, so no block-wide barrier sits
+// in the loop.
+//
+// Arithmetic: a consumer warp owns SC_WPW words (32 accessions each); lane = accession.  Rows are taken
+// 32 at a time: lane l loads row l's word, a 5-stage shuffle butterfly transposes the two bit planes so
+// that every lane holds the 32 row-bits of ITS accession, class masks cost one LOP3 per 32 rows, ninfo is
+// a popcount, and the unrolled row loop tests immediate bit positions — which ptxas turns into R2P (seven
+// predicates per instruction) feeding predicated DADDs.  The FP64 pipe (two DADDs per comparison: ref and
+// alt; het only for rows that have one) is what bounds the kernel, not HBM.
 #pragma once
 #include "common.cuh"
 
 namespace snpm {
 
-constexpr int SC_TILE_ROWS = 64;
+constexpr int SC_TILE_ROWS = 64;   // multiple of 32
 constexpr int SC_STAGES = 3;
-constexpr int SC_WPW = 4;          // words (of 32 accessions) per warp
-constexpr int SC_MAX_WARPS = 12;
+constexpr int SC_WPW = 4;          // words (of 32 accessions) per consumer warp
+constexpr int SC_MAX_WARPS = 12;   // consumer warps per CTA (+1 producer warp)
 
 // ---- PTX helpers (sm_100a) ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -30,6 +37,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -69,26 +79,29 @@ struct ScoreArgs {
     int32_t a_pad;              // stride * 32
 };
 
-__device__ __forceinline__ void score_word(uint64_t word, uint32_t lanebit, int lane, double w_ref, double w_het, double w_alt,
-                                           double &s_ref, double &s_het, double &s_alt, int32_t &ninfo, bool skip_hets) {
-    const uint32_t lo = uint32_t(word), hi = uint32_t(word >> 32);
-    const uint32_t refm = ~(lo | hi), altm = lo & ~hi, hetm = hi & ~lo;
-    if (refm & lanebit) s_ref += w_ref;
-    if (altm & lanebit) s_alt += w_alt;
-    if (!skip_hets) {
-        if (hetm != 0u) {                       // warp-uniform: hets are rare (makedb.py:59 code 2)
-            if (hetm & lanebit) s_het += w_het;
-        }
-        ninfo += int32_t((~(lo & hi)) >> lane & 1u);
-    } else {
-        ninfo += int32_t((refm | altm) >> lane & 1u);   // snpmatch.py:78-79: het -> missing
+// shared-memory pitch of one staged row slice: a multiple of 16 bytes (TMA) whose 16-byte count is odd, so
+// that the 64-bit row-per-lane loads of the transpose are at worst 2-way bank conflicted
+__host__ __device__ __forceinline__ uint32_t score_row_pitch(int slice_words) {
+    const uint32_t b = uint32_t(slice_words) * 8u;
+    return ((b >> 4) & 1u) ? b : b + 16u;
+}
+
+// 32x32 bit transpose across the warp: on return bit r of lane l = bit l of the value lane r passed in
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const uint32_t (&sel)[5], const uint32_t (&rot)[5]) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        uint32_t y = __shfl_xor_sync(0xffffffffu, x, 16 >> s);
+        y = __funnelshift_l(y, y, rot[s]);
+        x = (x & ~sel[s]) | (y & sel[s]);
     }
+    return x;
 }
 
 template <bool SKIP_HETS>
-__global__ void __launch_bounds__(32 * SC_MAX_WARPS) k_score_segments(const ScoreArgs a) {
+__global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(const ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x, warp = threadIdx.y, nwarps = blockDim.y;
+    const int lane = threadIdx.x, warp = threadIdx.y, ncons = blockDim.y - 1;
+    const bool producer = warp == ncons;
     const int seg = blockIdx.x;
 
     int32_t begin, end;
@@ -107,14 +120,16 @@ __global__ void __launch_bounds__(32 * SC_MAX_WARPS) k_score_segments(const Scor
         end = min(a.mstart[lo + 1], begin + a.chunk);
     }
 
-    const int w_start = blockIdx.y * (SC_WPW * nwarps);
-    const int slice_words = min(SC_WPW * nwarps, a.stride - w_start);
+    const int w_start = blockIdx.y * (SC_WPW * ncons);
+    const int slice_words = min(SC_WPW * ncons, a.stride - w_start);
     const uint32_t slice_bytes = uint32_t(slice_words) * 8u;
+    const uint32_t pitch = score_row_pitch(SC_WPW * ncons);
     const int vw = max(0, min(SC_WPW, slice_words - warp * SC_WPW));   // valid words of this warp: 0, 2 or 4
 
-    // shared memory: [STAGES] mbarriers | STAGES x (row tile | weight tile)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    const uint32_t tile_bytes = uint32_t(SC_TILE_ROWS) * uint32_t(SC_WPW * nwarps) * 8u;
+    // shared memory: full[STAGES], empty[STAGES] mbarriers | STAGES x (row tile | weight tile)
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + SC_STAGES;
+    const uint32_t tile_bytes = uint32_t(SC_TILE_ROWS) * pitch;
     const uint32_t wtile_bytes = SC_TILE_ROWS * 32u;
     unsigned char *stage0 = smem + 128;
     const uint32_t stage_bytes = tile_bytes + wtile_bytes;
@@ -124,59 +139,118 @@ __global__ void __launch_bounds__(32 * SC_MAX_WARPS) k_score_segments(const Scor
 
     if (n_tiles > 0) {
         if (warp == 0 && lane == 0) {
-            for (int s = 0; s < SC_STAGES; ++s) mbar_init(smem_u32(bars + s), 1u);
+            for (int s = 0; s < SC_STAGES; ++s) {
+                mbar_init(smem_u32(full + s), 1u);
+                mbar_init(smem_u32(empty + s), uint32_t(ncons));
+            }
             mbar_fence_init();
         }
         __syncthreads();
     }
 
-    auto issue_tile = [&](int t) {          // warp 0, all lanes
-        const int st = t % SC_STAGES;
-        const int r0 = begin + t * SC_TILE_ROWS;
-        const int rows = min(SC_TILE_ROWS, end - r0);
-        const uint32_t bar = smem_u32(bars + st);
-        unsigned char *dst = stage0 + size_t(st) * stage_bytes;
-        if (lane == 0) mbar_arrive_expect_tx(bar, uint32_t(rows) * (slice_bytes + 32u));
-        __syncwarp();
-        for (int r = lane; r < rows; r += 32) {
-            const int64_t row = a.pair_db[r0 + r];
-            tma_bulk_g2s(smem_u32(dst + size_t(r) * slice_bytes), a.packed + row * a.stride + w_start, slice_bytes, bar);
+    if (producer) {
+        // ---- producer warp: gather rows + weights of tile t into stage t % STAGES ----------------------
+        for (int t = 0; t < n_tiles; ++t) {
+            const int st = t % SC_STAGES;
+            if (t >= SC_STAGES) mbar_wait(smem_u32(empty + st), uint32_t(t / SC_STAGES - 1) & 1u);
+            const int r0 = begin + t * SC_TILE_ROWS;
+            const int rows = min(SC_TILE_ROWS, end - r0);
+            const uint32_t bar = smem_u32(full + st);
+            unsigned char *dst = stage0 + size_t(st) * stage_bytes;
+            if (lane == 0) mbar_arrive_expect_tx(bar, uint32_t(rows) * (slice_bytes + 32u));
+            __syncwarp();
+            for (int r = lane; r < rows; r += 32) {
+                const int64_t row = a.pair_db[r0 + r];
+                tma_bulk_g2s(smem_u32(dst + size_t(r) * pitch), a.packed + row * a.stride + w_start, slice_bytes, bar);
+            }
+            if (lane == 0) tma_bulk_g2s(smem_u32(dst + tile_bytes), a.pair_w + 4 * int64_t(r0), uint32_t(rows) * 32u, bar);
         }
-        if (lane == 0) tma_bulk_g2s(smem_u32(dst + tile_bytes), a.pair_w + 4 * int64_t(r0), uint32_t(rows) * 32u, bar);
-    };
+        return;
+    }
 
+    // ---- consumer warps --------------------------------------------------------------------------------
     double s_ref[SC_WPW], s_het[SC_WPW], s_alt[SC_WPW];
     int32_t ninfo[SC_WPW];
 #pragma unroll
     for (int j = 0; j < SC_WPW; ++j) { s_ref[j] = 0.0; s_het[j] = 0.0; s_alt[j] = 0.0; ninfo[j] = 0; }
-    const uint32_t lanebit = 1u << lane;
-
-    if (warp == 0) {
-        for (int t = 0; t < min(n_tiles, SC_STAGES - 1); ++t) issue_tile(t);
+    // per-stage constants of the transpose butterfly (j = 16, 8, 4, 2, 1)
+    uint32_t t_sel[5], t_rot[5];
+    {
+        const uint32_t m[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int j = 16 >> s;
+            t_sel[s] = (lane & j) ? m[s] : ~m[s];
+            t_rot[s] = (lane & j) ? uint32_t(32 - j) : uint32_t(j);
+        }
     }
+
     for (int t = 0; t < n_tiles; ++t) {
-        if (warp == 0 && t + SC_STAGES - 1 < n_tiles) issue_tile(t + SC_STAGES - 1);
         const int st = t % SC_STAGES;
-        mbar_wait(smem_u32(bars + st), uint32_t(t / SC_STAGES) & 1u);
+        mbar_wait(smem_u32(full + st), uint32_t(t / SC_STAGES) & 1u);
         const int rows = min(SC_TILE_ROWS, n_rows - t * SC_TILE_ROWS);
         const unsigned char *tile = stage0 + size_t(st) * stage_bytes;
         const unsigned char *wt = tile + tile_bytes;
-        if (vw > 0) {
-            const unsigned char *mine = tile + warp * (SC_WPW * 8);
-#pragma unroll 2
-            for (int r = 0; r < rows; ++r) {
-                const ulonglong2 q0 = *reinterpret_cast<const ulonglong2 *>(mine + size_t(r) * slice_bytes);
-                ulonglong2 q1 = make_ulonglong2(~0ull, ~0ull);
-                if (vw == SC_WPW) q1 = *reinterpret_cast<const ulonglong2 *>(mine + size_t(r) * slice_bytes + 16);
-                const double2 w01 = *reinterpret_cast<const double2 *>(wt + r * 32);
-                const double w2 = *reinterpret_cast<const double *>(wt + r * 32 + 16);
-                score_word(q0.x, lanebit, lane, w01.x, w01.y, w2, s_ref[0], s_het[0], s_alt[0], ninfo[0], SKIP_HETS);
-                score_word(q0.y, lanebit, lane, w01.x, w01.y, w2, s_ref[1], s_het[1], s_alt[1], ninfo[1], SKIP_HETS);
-                score_word(q1.x, lanebit, lane, w01.x, w01.y, w2, s_ref[2], s_het[2], s_alt[2], ninfo[2], SKIP_HETS);
-                score_word(q1.y, lanebit, lane, w01.x, w01.y, w2, s_ref[3], s_het[3], s_alt[3], ninfo[3], SKIP_HETS);
+        {
+            for (int g0 = 0; g0 < rows; g0 += 32) {
+                // lane l holds row g0+l: load its SC_WPW words, transpose both bit planes
+                const bool have = g0 + lane < rows;
+                const unsigned char *mine = tile + size_t(g0 + lane) * pitch + warp * (SC_WPW * 8);
+                uint32_t ref[SC_WPW], alt[SC_WPW], het[SC_WPW], het_rows[SC_WPW];
+#pragma unroll
+                for (int j = 0; j < SC_WPW; ++j) {
+                    uint64_t v = ~0ull;
+                    if (have && j < vw) v = *reinterpret_cast<const uint64_t *>(mine + j * 8);
+                    uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+                    het_rows[j] = SKIP_HETS ? 0u : __ballot_sync(0xffffffffu, (hi & ~lo) != 0u);   // rows of this word with a het
+                    lo = warp_transpose32(lo, t_sel, t_rot);
+                    hi = warp_transpose32(hi, t_sel, t_rot);
+                    ref[j] = ~(lo | hi);
+                    alt[j] = lo & ~hi;
+                    het[j] = hi & ~lo;
+                    asm volatile("" : "+r"(ref[j]), "+r"(alt[j]));      // keep the class masks in registers (R2P source)
+                    ninfo[j] += __popc(SKIP_HETS ? (ref[j] | alt[j]) : ~(lo & hi));   // snpmatch.py:78-79,88
+                }
+                const unsigned char *wg = wt + g0 * 32;
+                // Rows in blocks of 8; inside a block one accumulator at a time runs through its 8 rows, so that the
+                // eight bit tests hit one register byte (R2P -> 7 predicates) and the adds stay predicated DADDs.  The
+                // add is a volatile asm so that neither nvvm nor ptxas turns it into add + select.
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    double w_ref[8], w_alt[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        w_ref[r] = *reinterpret_cast<const double *>(wg + (r0 + r) * 32);
+                        w_alt[r] = *reinterpret_cast<const double *>(wg + (r0 + r) * 32 + 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < SC_WPW; ++j) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (ref[j] & (1u << (r0 + r))) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_ref[j]) : "d"(w_ref[r]));
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (alt[j] & (1u << (r0 + r))) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_alt[j]) : "d"(w_alt[r]));
+                    }
+                }
+                if (!SKIP_HETS) {
+                    // hets are rare (makedb.py:59 code 2; ~0.2 % of calls): visit only the rows of a word that hold
+                    // one, in ascending row order (het_rows is warp-uniform, so the loop does not diverge)
+#pragma unroll
+                    for (int j = 0; j < SC_WPW; ++j) {
+                        uint32_t m = het_rows[j];
+                        while (m) {
+                            const int r = __ffs(m) - 1;
+                            m &= m - 1;
+                            const double w_het = *reinterpret_cast<const double *>(wg + r * 32 + 8);
+                            if ((het[j] >> r) & 1u) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_het[j]) : "d"(w_het));
+                        }
+                    }
+                }
             }
         }
-        __syncthreads();                      // every warp is done with stage st before it is refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + st));     // this warp is done with stage st
     }
 
 #pragma unroll
@@ -191,11 +265,11 @@ __global__ void __launch_bounds__(32 * SC_MAX_WARPS) k_score_segments(const Scor
 }
 
 static inline void score_launch_shape(int32_t stride, int *nwarps, int *yblocks, size_t *smem_bytes) {
-    int nw = (stride + SC_WPW - 1) / SC_WPW;
+    int nw = (stride + SC_WPW - 1) / SC_WPW;       // consumer warps
     if (nw > SC_MAX_WARPS) nw = 8;
     *nwarps = nw;
     *yblocks = (stride + SC_WPW * nw - 1) / (SC_WPW * nw);
-    *smem_bytes = 128 + size_t(SC_STAGES) * (size_t(SC_TILE_ROWS) * SC_WPW * nw * 8 + SC_TILE_ROWS * 32);
+    *smem_bytes = 128 + size_t(SC_STAGES) * (size_t(SC_TILE_ROWS) * score_row_pitch(SC_WPW * nw) + SC_TILE_ROWS * 32);
 }
 
 // ---- combine: sequential sum of the segment partials of one sample, in segment order ----------------

@@ -198,3 +198,44 @@ def small_panel(n_rows=6000, n_acc=40, seed=SEED_PANEL, chrlen=TAIR10_CHRLEN, ch
     snps = panel_codes(seed, np.arange(n_rows), n_acc)
     return dict(snps=snps, positions=pos, chr_regions=regions, chrs=np.array(chr_names, dtype="str"),
                 accessions=accession_ids(n_acc))
+
+
+def make_sample_fast(positions, chr_regions, n_acc, true_acc, n_db=45000, n_extra=5000, seed=SEED_SAMPLE,
+                     panel_seed=SEED_PANEL, err=0.01, het=0.02, chrlen=TAIR10_CHRLEN):
+    """Vectorised variant of make_sample for large panels (no per-marker Python loop, no name strings):
+    returns dict(chr_ix int32, pos int32, wei f64[n,3], code int8, rows int64) sorted by (chromosome, position).
+    Extra markers sit at positions absent from the panel."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    n_rows = len(positions)
+    rows = np.unique(rng.integers(0, n_rows, size=int(n_db * 1.05) + 16))
+    if len(rows) > n_db:
+        rows = np.sort(rng.choice(rows, size=n_db, replace=False))
+    code = panel_codes_cols(panel_seed, rows, [true_acc])[:, 0]
+    code = np.where(code < 0, 0, code)
+    flip = rng.random(len(rows)) < err
+    code = np.where(flip & (code != 2), 1 - code, code)
+    code = np.where(rng.random(len(rows)) < het, 2, code).astype(np.int8)
+    row_chr = np.searchsorted(chr_regions[:, 1], rows, side="right")
+    ex_chr = rng.integers(0, len(chr_regions), size=n_extra)
+    ex_pos = (rng.random(n_extra) * (np.asarray(chrlen)[ex_chr] - 2)).astype(np.int64) + 1
+    key_db = row_chr.astype(np.int64) * (1 << 32) + positions[rows].astype(np.int64)
+    key_ex = np.unique(ex_chr.astype(np.int64) * (1 << 32) + ex_pos)
+    # drop extras that collide with a panel position
+    ec, ep = key_ex >> 32, key_ex & 0xFFFFFFFF
+    hit = np.zeros(len(key_ex), bool)
+    for c, (s, e) in enumerate(chr_regions):
+        sel = np.flatnonzero(ec == c)
+        seg = positions[s:e]
+        if len(seg) and len(sel):
+            j = np.minimum(np.searchsorted(seg, ep[sel]), len(seg) - 1)
+            hit[sel] = seg[j] == ep[sel]
+    key_ex = key_ex[~hit]
+    key = np.concatenate([key_db, key_ex])
+    s_code = np.concatenate([code, rng.integers(0, 2, size=len(key_ex)).astype(np.int8)])
+    s_rows = np.concatenate([rows, np.full(len(key_ex), -1, dtype=np.int64)])
+    o = np.argsort(key, kind="stable")
+    key, s_code, s_rows = key[o], s_code[o], s_rows[o]
+    dp = 1 + rng.poisson(3, size=len(key))
+    _, wei = _pl_weights(rng, s_code, dp)
+    return dict(chr_ix=(key >> 32).astype(np.int32), pos=(key & 0xFFFFFFFF).astype(np.int32), wei=wei, code=s_code,
+                rows=s_rows, dp=dp.astype(np.float64))
