@@ -225,16 +225,11 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-class _DevArray(object):
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
 def run_b200_arm(args):
     import torch
     import __graft_entry__ as ge
     ge.build()
-    from snpmatch_b200 import lib, synth
+    from snpmatch_b200 import lib, sharding, synth
     from snpmatch_b200.core import snp_genotype
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,7 +247,7 @@ def run_b200_arm(args):
     n_rows, n_acc = args.rows, args.accessions
     S = args.samples * world
     positions, regions = synth.panel_positions(n_rows)
-    r0, r1 = rank * n_rows // world, (rank + 1) * n_rows // world
+    r0, r1 = sharding.shard_rows(n_rows, world, rank)
     g = snp_genotype.Genotype.synthetic(n_rows, n_acc, row_range=(r0, r1), device=local_rank)
     db = g.db
     db.set_stream(stream.cuda_stream)
@@ -279,16 +274,11 @@ def run_b200_arm(args):
     out = {k: v.numpy() for k, v in out_t.items()}
 
     batch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
-    red = None
 
     def device_step():
-        nonlocal red
         batch.run()
         if world > 1:
-            if red is None:
-                p, n = batch.reduce_buffer()
-                red = torch.as_tensor(_DevArray(p, n), device=dev)
-            dist.all_reduce(red)
+            sharding.allreduce_batch(batch, dist, dev)      # one NCCL all-reduce of [S, 2A+2] f64
         batch.epilogue()
 
     def barrier():

@@ -127,11 +127,11 @@ class Genotype(object):
     def synthetic(cls, n_rows, n_acc, seed=None, device=0, row_range=None):
         """The deterministic panel of synth.py generated in HBM.  row_range=(r0, r1) keeps only
         that SNP-row shard on this device (multi-GPU); indices returned by the join stay global."""
-        from .. import synth
+        from .. import sharding, synth
         seed = synth.SEED_PANEL if seed is None else seed
         positions, regions = synth.panel_positions(n_rows, seed=seed)
         r0, r1 = (0, n_rows) if row_range is None else row_range
-        local_regions = np.clip(regions, r0, r1) - r0
+        local_regions = sharding.local_regions(regions, r0, r1)
         self = object.__new__(cls)
         db = lib.Database(positions[r0:r1], local_regions, n_acc, device=device, row0_global=r0)
         db.fill_synthetic(seed)

@@ -1,0 +1,79 @@
+"""
+SNP-row sharding of the panel over the GPUs of one box.
+
+The database is cut into contiguous row ranges, one per rank (boundaries ignore chromosomes:
+low-coverage markers are spread evenly over the genome, so matched rows balance).  Samples are
+replicated.  Every rank joins and scores against its own rows; the per-sample partial totals
+(score f64, ninfo, matched pairs) travel in ONE buffer and are summed with one all-reduce, after
+which every rank runs the likelihood epilogue on identical totals.
+
+This module is the host logic of that scheme and is independent of CUDA, so that it can be tested
+with the gloo backend on CPU; `bench.py` and `allreduce_batch` below use it with NCCL on the
+device buffer of a `lib.Batch`.
+"""
+import numpy as np
+
+
+def shard_rows(n_rows, world, rank):
+    """Contiguous row range [r0, r1) of `rank`."""
+    return rank * n_rows // world, (rank + 1) * n_rows // world
+
+
+def local_regions(chr_regions, r0, r1):
+    """Chromosome row ranges clipped to a shard and shifted to shard-local row numbers; chromosomes
+    outside the shard become empty ranges (the join then finds nothing there)."""
+    reg = np.asarray(chr_regions, dtype=np.int64).reshape(-1, 2)
+    return np.clip(reg, r0, r1) - r0
+
+
+def reduce_row_len(n_acc):
+    """f64 per sample in the reduce buffer: score[n_acc] | ninfo[n_acc] | matched pairs | y>n count."""
+    return 2 * n_acc + 2
+
+
+def pack_reduce_rows(score, ninfo, m):
+    """Host-side picture of the device reduce buffer (csrc/score.cuh k_combine): integers are stored as
+    f64, exact below 2**53, so that one sum collective carries everything."""
+    score = np.atleast_2d(np.asarray(score, dtype=np.float64))
+    ninfo = np.atleast_2d(np.asarray(ninfo))
+    S, A = score.shape
+    out = np.zeros((S, reduce_row_len(A)), dtype=np.float64)
+    out[:, :A] = score
+    out[:, A:2 * A] = ninfo
+    out[:, 2 * A] = np.asarray(m).reshape(S)
+    return out
+
+
+def unpack_reduce_rows(buf, n_acc):
+    buf = np.asarray(buf, dtype=np.float64).reshape(-1, reduce_row_len(n_acc))
+    return buf[:, :n_acc], buf[:, n_acc:2 * n_acc].astype(np.int64), buf[:, 2 * n_acc].astype(np.int64)
+
+
+def truncation_guard(score, rel_eps=1e-12):
+    """Accessions whose int(score) could depend on the summation order: a sharded run adds the chunk
+    partials in another order than the single-GPU reference, which moves the fp64 sum by a few ulp;
+    only sums within that distance of an integer can truncate differently (hard part 1).
+    Returns a boolean mask (True = ambiguous, must be re-scored in reference order)."""
+    s = np.asarray(score, dtype=np.float64)
+    frac = s - np.floor(s)
+    tol = np.maximum(np.abs(s), 1.0) * rel_eps
+    near_int = (frac < tol) | (1.0 - frac < tol)
+    exact_int = s == np.floor(s)
+    # sums of 0/1 weights are exact integers in every order: not ambiguous
+    return near_int & ~exact_int
+
+
+def allreduce_batch(batch, dist, device):
+    """Sum the per-sample partial totals of a lib.Batch over all ranks, in place on the device buffer
+    (NCCL; the buffer is wrapped zero-copy through __cuda_array_interface__)."""
+    import torch
+
+    class _Dev(object):
+        pass
+
+    ptr, n = batch.reduce_buffer()
+    holder = _Dev()
+    holder.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    t = torch.as_tensor(holder, device=device)
+    dist.all_reduce(t)
+    return t

@@ -1,0 +1,93 @@
+"""world_size-2 test of the multi-GPU host logic on CPU (gloo): SNP-row shards, local chromosome
+ranges, one all-reduce of the packed per-sample totals, epilogue on the reduced totals.  The per-shard
+compute stand-in is the CPU oracle (the CUDA kernels need a GPU; their sharded run is in bench.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    golden = os.path.join(ROOT, "tests", "golden")
+    p = dict(np.load(os.path.join(golden, "small_panel.npz")))
+    s = dict(np.load(os.path.join(golden, "sample_inbred.npz")))
+    n_rows, n_acc = p["snps"].shape
+    r0, r1 = sharding.shard_rows(n_rows, world, rank)
+    regions = sharding.local_regions(p["chr_regions"], r0, r1)
+    res = orc.genotyper(p["snps"][r0:r1], p["chrs"], regions, p["positions"][r0:r1], s["chrs"], s["pos"], s["wei"])
+    buf = sharding.pack_reduce_rows(res.score_f64, res.ninfo, res.num_snps)
+    t = torch.from_numpy(buf)
+    dist.all_reduce(t)
+    score, ninfo, m = sharding.unpack_reduce_rows(t.numpy(), n_acc)
+    # global pair indices of this shard
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), score=score[0], ninfo=ninfo[0], m=m,
+             db_idx=res.common[0] + r0, s_idx=res.common[1], regions=regions)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_row_sharded_allreduce_matches_single_run(tmp_path, world):
+    import torch.multiprocessing as mp
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import sharding
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = load_golden("inbred_pl.npz")
+    outs = [np.load(str(tmp_path / ("rank%d.npz" % r))) for r in range(world)]
+    # every rank holds the same reduced totals
+    for o in outs[1:]:
+        assert np.array_equal(o["score"], outs[0]["score"]) and np.array_equal(o["ninfo"], outs[0]["ninfo"])
+    o = outs[0]
+    assert int(o["m"][0]) == int(g["num_snps"])
+    assert np.array_equal(o["ninfo"], g["ninfo"])                       # integers: exact in any order
+    single = orc.genotyper(*[load_golden("small_panel.npz")[k] for k in ("snps", "chrs", "chr_regions", "positions")],
+                           *[load_golden("sample_inbred.npz")[k] for k in ("chrs", "pos", "wei")])
+    np.testing.assert_allclose(o["score"], single.score_f64, rtol=1e-13)  # fp64: another summation order
+    guard = sharding.truncation_guard(o["score"])
+    assert np.array_equal(o["score"].astype(np.int64)[~guard], g["scores"][~guard])
+    assert guard.sum() <= 1
+    # likelihoods on the reduced totals agree with the single run
+    lik, lr = orc.calculate_likelihoods(o["score"].astype(np.int64), o["ninfo"])
+    np.testing.assert_allclose(lik, g["likelis"], rtol=1e-12, equal_nan=True)
+    # the shards' pairs concatenate to the whole join
+    db_idx = np.concatenate([x["db_idx"] for x in outs])
+    s_idx = np.concatenate([x["s_idx"] for x in outs])
+    assert np.array_equal(db_idx, g["common_db"]) and np.array_equal(s_idx, g["common_s"])
+
+
+def test_shard_geometry():
+    from snpmatch_b200 import sharding
+    reg = np.array([[0, 100], [100, 250], [250, 400]])
+    cuts = [sharding.shard_rows(400, 3, r) for r in range(3)]
+    assert cuts == [(0, 133), (133, 266), (266, 400)]
+    assert sharding.local_regions(reg, 133, 266).tolist() == [[0, 0], [0, 117], [117, 133]]
+    assert sharding.local_regions(reg, 0, 133).tolist() == [[0, 100], [100, 133], [133, 133]]
+    total = sum(int((sharding.local_regions(reg, a, b)[:, 1] - sharding.local_regions(reg, a, b)[:, 0]).sum()) for a, b in cuts)
+    assert total == 400
+    buf = sharding.pack_reduce_rows(np.array([[1.5, 2.5]]), np.array([[3, 4]]), [7])
+    assert buf.shape == (1, 6) and buf[0].tolist() == [1.5, 2.5, 3.0, 4.0, 7.0, 0.0]
+    sc, ni, m = sharding.unpack_reduce_rows(buf * 2, 2)
+    assert sc.tolist() == [[3.0, 5.0]] and ni.tolist() == [[6, 8]] and m.tolist() == [14]
+    g = sharding.truncation_guard(np.array([4719.0, 4718.999999999999, 12.5, 3.0000000000000004, 0.0]))
+    assert g.tolist() == [False, True, False, True, False]
