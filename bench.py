@@ -252,7 +252,14 @@ def run_b200_arm(args):
     db = g.db
     db.set_stream(stream.cuda_stream)
     samples = make_samples(positions, regions, n_acc, S, args.markers)
-    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])]).astype(np.int64)
+    # a rank only needs the markers that can fall into its row range (constant per-GPU join work and H2D bytes)
+    parts = samples
+    if world > 1:
+        parts = []
+        for s in samples:
+            i0, i1 = sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, positions, r0, r1)
+            parts.append({k: s[k][i0:i1] for k in ("chr_ix", "pos", "wei")})
+    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in parts])]).astype(np.int64)
     n_tot = int(offs[-1])
 
     def pinned(a):
@@ -261,9 +268,9 @@ def run_b200_arm(args):
 
     keep = []
     arrs = []
-    for a in (offs, np.concatenate([s["chr_ix"] for s in samples]).astype(np.int32),
-              np.concatenate([s["pos"] for s in samples]).astype(np.int32),
-              np.concatenate([s["wei"] for s in samples]).astype(np.float64)):
+    for a in (offs, np.concatenate([s["chr_ix"] for s in parts]).astype(np.int32),
+              np.concatenate([s["pos"] for s in parts]).astype(np.int32),
+              np.concatenate([s["wei"] for s in parts]).astype(np.float64)):
         t, v = pinned(a)
         keep.append(t)
         arrs.append(v)

@@ -26,6 +26,29 @@ def local_regions(chr_regions, r0, r1):
     return np.clip(reg, r0, r1) - r0
 
 
+def shard_marker_range(chr_ix, pos, chr_regions, positions, r0, r1):
+    """Slice [i0, i1) of a sample's markers (sorted by (database chromosome index, position)) that can match
+    rows [r0, r1) of the panel: only that slice has to be uploaded to the rank holding the shard, which keeps
+    per-GPU join work and H2D traffic constant as ranks are added.  Markers of unknown chromosomes (index < 0)
+    never match and are left out."""
+    chr_ix = np.asarray(chr_ix)
+    pos = np.asarray(pos)
+    if r1 <= r0 or len(pos) == 0:
+        return 0, 0
+    reg = np.asarray(chr_regions, dtype=np.int64).reshape(-1, 2)
+    c_lo = int(np.searchsorted(reg[:, 1], r0, side="right"))
+    c_hi = int(np.searchsorted(reg[:, 1], r1 - 1, side="right"))
+    key = chr_ix.astype(np.int64) * (1 << 32) + pos.astype(np.int64)
+    known = chr_ix >= 0
+    assert np.all(np.diff(key[known]) > 0), "markers must be sorted by (chromosome index, position)"
+    lo = c_lo * (1 << 32) + int(positions[r0])
+    hi = c_hi * (1 << 32) + int(positions[r1 - 1])
+    first_unknown = int(np.argmax(~known)) if (~known).any() else len(key)
+    assert known[:first_unknown].all() and not known[first_unknown:].any(), "unknown chromosomes must come last"
+    k = key[:first_unknown]
+    return int(np.searchsorted(k, lo, side="left")), int(np.searchsorted(k, hi, side="right"))
+
+
 def reduce_row_len(n_acc):
     """f64 per sample in the reduce buffer: score[n_acc] | ninfo[n_acc] | matched pairs | y>n count."""
     return 2 * n_acc + 2

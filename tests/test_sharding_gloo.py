@@ -91,3 +91,22 @@ def test_shard_geometry():
     assert sc.tolist() == [[3.0, 5.0]] and ni.tolist() == [[6, 8]] and m.tolist() == [14]
     g = sharding.truncation_guard(np.array([4719.0, 4718.999999999999, 12.5, 3.0000000000000004, 0.0]))
     assert g.tolist() == [False, True, False, True, False]
+
+
+def test_marker_slices_cover_the_join_exactly():
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import sharding, synth
+    pos, regions = synth.panel_positions(50000)
+    s = synth.make_sample_fast(pos, regions, 50, 3, n_db=4000, n_extra=500, seed=11)
+    rows = s["rows"]
+    for world in (1, 2, 3, 8):
+        seen = np.zeros(len(rows), dtype=int)
+        for rank in range(world):
+            r0, r1 = sharding.shard_rows(50000, world, rank)
+            i0, i1 = sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, pos, r0, r1)
+            in_shard = (rows >= r0) & (rows < r1)
+            assert in_shard[:i0].sum() == 0 and in_shard[i1:].sum() == 0      # nothing matchable is left out
+            seen[i0:i1] += 1
+        assert np.all(seen[rows >= 0] >= 1)
+        assert seen.sum() <= len(rows) + 2 * world                             # slices overlap by boundary markers at most
+    assert sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, pos, 10, 10) == (0, 0)
