@@ -26,22 +26,30 @@ struct DeviceGuard {
     }
 };
 
+template <bool SKIP, int NW, int MINB>
+static int launch_score_t(cudaStream_t st, const ScoreArgs &a, dim3 grid, dim3 block, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SNPM_CUDA(cudaFuncSetAttribute(k_score_segments<SKIP, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    k_score_segments<SKIP, NW, MINB><<<grid, block, smem, st>>>(a);
+    SNPM_KERNEL_CHECK();
+    return SNPM_OK;
+}
+
 static int launch_score(cudaStream_t st, const ScoreArgs &a, int grid_x, bool skip_hets) {
     int nw, yb;
     size_t smem;
     score_launch_shape(a.stride, &nw, &yb, &smem);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[skip_hets ? 1 : 0]) {
-        if (skip_hets) SNPM_CUDA(cudaFuncSetAttribute(k_score_segments<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        else SNPM_CUDA(cudaFuncSetAttribute(k_score_segments<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[skip_hets ? 1 : 0] = true;
-    }
     if (grid_x <= 0) return SNPM_OK;
     dim3 grid(grid_x, yb), block(32, nw + 1);      // + the producer warp
-    if (skip_hets) k_score_segments<true><<<grid, block, smem, st>>>(a);
-    else k_score_segments<false><<<grid, block, smem, st>>>(a);
-    SNPM_KERNEL_CHECK();
-    return SNPM_OK;
+    // launch bounds match the two shapes that occur in practice: 9 consumer warps (a 1135-accession row in one CTA)
+    // and 8 (32-word slices of wide panels); anything else takes the generic instantiation
+    if (nw + 1 == 10) return skip_hets ? launch_score_t<true, 10, 2>(st, a, grid, block, smem) : launch_score_t<false, 10, 2>(st, a, grid, block, smem);
+    if (nw + 1 == 9) return skip_hets ? launch_score_t<true, 9, 2>(st, a, grid, block, smem) : launch_score_t<false, 9, 2>(st, a, grid, block, smem);
+    return skip_hets ? launch_score_t<true, SC_MAX_WARPS + 1, 1>(st, a, grid, block, smem)
+                     : launch_score_t<false, SC_MAX_WARPS + 1, 1>(st, a, grid, block, smem);
 }
 }  // namespace snpm
 
@@ -576,8 +584,8 @@ int snpm_match_gts_accs(int device, const double *wei, const int8_t *snps, int64
     for (int64_t r = 0; r < k; ++r) {
         iota[size_t(r)] = int32_t(r);
         w4[size_t(4 * r)] = wei[3 * r];
-        w4[size_t(4 * r + 1)] = wei[3 * r + 1];
-        w4[size_t(4 * r + 2)] = wei[3 * r + 2];
+        w4[size_t(4 * r + 1)] = wei[3 * r + 2];      // (w_ref, w_alt, w_het, 0)
+        w4[size_t(4 * r + 2)] = wei[3 * r + 1];
         w4[size_t(4 * r + 3)] = 0.0;
     }
     const int32_t seg[2] = {0, int32_t(k)};

@@ -38,9 +38,10 @@ __global__ void __launch_bounds__(F1_THREADS) k_f1_partial(const uint64_t *__res
         const uint64_t *rowp = packed + int64_t(pair_db[r]) * stride;
         const uint32_t g1 = code_at(rowp, a1), g2 = code_at(rowp, a2);
         const double *w = pair_w + 4 * r;
-        if (g1 == 1u && g2 == 1u) { alt += w[2]; ++cnt; }
+        // pair_w rows are (w_ref, w_alt, w_het, 0)
+        if (g1 == 1u && g2 == 1u) { alt += w[1]; ++cnt; }
         else if (g1 == 0u && g2 == 0u) { ref += w[0]; ++cnt; }
-        else if (g1 != 3u && g2 != 3u && g1 != g2) { het += w[1]; ++cnt; }
+        else if (g1 != 3u && g2 != 3u && g1 != g2) { het += w[2]; ++cnt; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {

@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs(
         if (flag) {
             pair_db[p] = row;
             pair_s[p] = int32_t(i);
-            double4 w4;                        // 32-byte rows: (w_ref, w_het, w_alt, 0) — TMA-copyable tiles
+            double4 w4;                        // 32-byte rows: (w_ref, w_alt, w_het, 0) — TMA-copyable tiles
             w4.x = wei[3 * i + 0];
-            w4.y = wei[3 * i + 1];
-            w4.z = wei[3 * i + 2];
+            w4.y = wei[3 * i + 2];
+            w4.z = wei[3 * i + 1];
             w4.w = 0.0;
             reinterpret_cast<double4 *>(pair_w)[p] = w4;
         }

@@ -41,6 +41,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// named barriers 1..SC_STAGES signal "stage free": consumer warps arrive (non-blocking), the producer warp syncs and
+// therefore sleeps in hardware instead of spinning on an mbarrier and stealing issue slots from the consumers
+__device__ __forceinline__ void named_bar_arrive(int id, int n_threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -59,11 +67,23 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void *src_
                  : "memory");
 }
 
+// 16-byte Ampere-style async copy global -> shared (LDGSTS) and its mbarrier hook
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#ifndef SC_GATHER_LDGSTS
+#define SC_GATHER_LDGSTS 1      // 1: rows gathered with 16-byte cp.async by the producer warp; 0: one TMA bulk copy per row
+#endif
+
 struct ScoreArgs {
     const uint64_t *packed;     // [n_rows, stride]
     int32_t stride;
     const int32_t *pair_db;     // matched local rows
-    const double *pair_w;       // [m, 4] = (w_ref, w_het, w_alt, 0) per matched pair, 32-byte rows
+    const double *pair_w;       // [m, 4] = (w_ref, w_alt, w_het, 0) per matched pair, 32-byte rows
     // chunk mode (table == 0): segment j belongs to sample s with seg_off[s] <= j < seg_off[s+1]
     const int32_t *seg_off;     // [S+1]
     const int32_t *mstart;      // [S+1]
@@ -97,8 +117,8 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const uint32_t 
     return x;
 }
 
-template <bool SKIP_HETS>
-__global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(const ScoreArgs a) {
+template <bool SKIP_HETS, int NWARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(32 * NWARPS, MIN_BLOCKS) k_score_segments(const ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x, warp = threadIdx.y, ncons = blockDim.y - 1;
     const bool producer = warp == ncons;
@@ -128,7 +148,6 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
 
     // shared memory: full[STAGES], empty[STAGES] mbarriers | STAGES x (row tile | weight tile)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *empty = full + SC_STAGES;
     const uint32_t tile_bytes = uint32_t(SC_TILE_ROWS) * pitch;
     const uint32_t wtile_bytes = SC_TILE_ROWS * 32u;
     unsigned char *stage0 = smem + 128;
@@ -140,8 +159,7 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
     if (n_tiles > 0) {
         if (warp == 0 && lane == 0) {
             for (int s = 0; s < SC_STAGES; ++s) {
-                mbar_init(smem_u32(full + s), 1u);
-                mbar_init(smem_u32(empty + s), uint32_t(ncons));
+                mbar_init(smem_u32(full + s), SC_GATHER_LDGSTS ? 33u : 1u);
             }
             mbar_fence_init();
         }
@@ -152,11 +170,31 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
         // ---- producer warp: gather rows + weights of tile t into stage t % STAGES ----------------------
         for (int t = 0; t < n_tiles; ++t) {
             const int st = t % SC_STAGES;
-            if (t >= SC_STAGES) mbar_wait(smem_u32(empty + st), uint32_t(t / SC_STAGES - 1) & 1u);
+            if (t >= SC_STAGES) named_bar_sync(1 + st, 32 * (ncons + 1));
             const int r0 = begin + t * SC_TILE_ROWS;
             const int rows = min(SC_TILE_ROWS, end - r0);
             const uint32_t bar = smem_u32(full + st);
             unsigned char *dst = stage0 + size_t(st) * stage_bytes;
+#if SC_GATHER_LDGSTS
+            // row indices of the tile: lane l keeps rows l and l+32, handed out by shuffle below
+            const int64_t idx0 = lane < rows ? int64_t(a.pair_db[r0 + lane]) : 0;
+            const int64_t idx1 = lane + 32 < rows ? int64_t(a.pair_db[r0 + 32 + lane]) : 0;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, uint32_t(rows) * 32u);
+                tma_bulk_g2s(smem_u32(dst + tile_bytes), a.pair_w + 4 * int64_t(r0), uint32_t(rows) * 32u, bar);
+            }
+            const uint32_t cpr = slice_bytes >> 4;                         // 16-byte chunks per row slice
+            const uint32_t total = uint32_t(rows) * cpr;
+            const uint32_t magic = cpr > 1u ? 0xFFFFFFFFu / cpr + 1u : 0u; // floor(i / cpr) = umulhi(i, magic) for i < 2^16, cpr > 1
+            const uint64_t *src0 = a.packed + w_start;
+            for (uint32_t i = lane; i < ((total + 31u) & ~31u); i += 32) {
+                const uint32_t r = cpr > 1u ? __umulhi(i, magic) : i, c = i - r * cpr;
+                const int64_t lo_i = __shfl_sync(0xffffffffu, idx0, r & 31), hi_i = __shfl_sync(0xffffffffu, idx1, r & 31);
+                const int64_t row = r < 32 ? lo_i : hi_i;
+                if (i < total) cp_async16(smem_u32(dst + size_t(r) * pitch + c * 16u), src0 + row * a.stride + c * 2u);
+            }
+            cp_async_mbar_arrive_noinc(bar);
+#else
             if (lane == 0) mbar_arrive_expect_tx(bar, uint32_t(rows) * (slice_bytes + 32u));
             __syncwarp();
             for (int r = lane; r < rows; r += 32) {
@@ -164,6 +202,7 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
                 tma_bulk_g2s(smem_u32(dst + size_t(r) * pitch), a.packed + row * a.stride + w_start, slice_bytes, bar);
             }
             if (lane == 0) tma_bulk_g2s(smem_u32(dst + tile_bytes), a.pair_w + 4 * int64_t(r0), uint32_t(rows) * 32u, bar);
+#endif
         }
         return;
     }
@@ -185,6 +224,15 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
         }
     }
 
+    // PRMT selectors of the two byte-exchange stages: [send, merge even, merge odd] for accession bit 4, then bit 3
+    uint32_t b_sel[6];
+    b_sel[0] = (lane & 16) ? 0x5410u : 0x7632u;
+    b_sel[1] = (lane & 16) ? 0x3254u : 0x5410u;
+    b_sel[2] = (lane & 16) ? 0x3276u : 0x7610u;
+    b_sel[3] = (lane & 8) ? 0x6420u : 0x7531u;
+    b_sel[4] = (lane & 8) ? 0x3514u : 0x5240u;
+    b_sel[5] = (lane & 8) ? 0x3716u : 0x7260u;
+
     for (int t = 0; t < n_tiles; ++t) {
         const int st = t % SC_STAGES;
         mbar_wait(smem_u32(full + st), uint32_t(t / SC_STAGES) & 1u);
@@ -196,42 +244,79 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
                 // lane l holds row g0+l: load its SC_WPW words, transpose both bit planes
                 const bool have = g0 + lane < rows;
                 const unsigned char *mine = tile + size_t(g0 + lane) * pitch + warp * (SC_WPW * 8);
-                uint32_t ref[SC_WPW], alt[SC_WPW], het[SC_WPW], het_rows[SC_WPW];
+                // class planes of row g0+lane: x[j] = hom-ref plane of word j, x[4+j] = hom-alt plane (bit = accession);
+                // the het plane stays row-major and is consulted only for rows that hold a het
+                uint32_t x[2 * SC_WPW], het[SC_WPW], het_rows[SC_WPW];
 #pragma unroll
                 for (int j = 0; j < SC_WPW; ++j) {
                     uint64_t v = ~0ull;
                     if (have && j < vw) v = *reinterpret_cast<const uint64_t *>(mine + j * 8);
-                    uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
-                    het_rows[j] = SKIP_HETS ? 0u : __ballot_sync(0xffffffffu, (hi & ~lo) != 0u);   // rows of this word with a het
-                    lo = warp_transpose32(lo, t_sel, t_rot);
-                    hi = warp_transpose32(hi, t_sel, t_rot);
-                    ref[j] = ~(lo | hi);
-                    alt[j] = lo & ~hi;
+                    const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
                     het[j] = hi & ~lo;
-                    asm volatile("" : "+r"(ref[j]), "+r"(alt[j]));      // keep the class masks in registers (R2P source)
-                    ninfo[j] += __popc(SKIP_HETS ? (ref[j] | alt[j]) : ~(lo & hi));   // snpmatch.py:78-79,88
+                    het_rows[j] = SKIP_HETS ? 0u : __ballot_sync(0xffffffffu, het[j] != 0u);
+                    x[j] = ~(lo | hi);
+                    x[SC_WPW + j] = lo & ~hi;
+                    // informative sites of this lane's accession: transpose the called plane, count its rows
+                    // (hets are counted where they are added; snpmatch.py:78-79,88)
+                    ninfo[j] += __popc(warp_transpose32(x[j] | x[SC_WPW + j], t_sel, t_rot));
+                }
+                // (1) inside the lane: 8x8 bit transpose of the eight planes per byte column, after which byte b of
+                //     x[i] holds the eight class flags (ref word 0-3, alt word 0-3) of accession 8b+i in this row
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int jj = 4 >> s;
+                    const uint32_t m = s == 0 ? 0x0F0F0F0Fu : (s == 1 ? 0x33333333u : 0x55555555u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k & jj) continue;
+                        const uint32_t t = ((x[k] >> jj) ^ x[k + jj]) & m;
+                        x[k + jj] ^= t;
+                        x[k] ^= t << jj;
+                    }
+                }
+                // (2) across the warp: 32x32 transpose of those bytes (lane <-> accession, slot <-> row); afterwards
+                //     byte b of x[i] in lane a holds the flags of (row 8b+i, accession a)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // accession bit 4: byte positions {2,3} <-> {0,1}
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(x[2 * k], x[2 * k + 1], b_sel[0]), 16);
+                    x[2 * k] = __byte_perm(x[2 * k], recv, b_sel[1]);
+                    x[2 * k + 1] = __byte_perm(x[2 * k + 1], recv, b_sel[2]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {          // accession bit 3: byte positions {1,3} <-> {0,2}
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(x[2 * k], x[2 * k + 1], b_sel[3]), 8);
+                    x[2 * k] = __byte_perm(x[2 * k], recv, b_sel[4]);
+                    x[2 * k + 1] = __byte_perm(x[2 * k + 1], recv, b_sel[5]);
+                }
+#pragma unroll
+                for (int q = 2; q >= 0; --q) {         // accession bits 2..0: whole registers
+                    const bool up = (lane >> q) & 1;
+#pragma unroll
+                    for (int i0 = 0; i0 < 8; ++i0) {
+                        if (i0 & (1 << q)) continue;
+                        const int i1 = i0 | (1 << q);
+                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? x[i0] : x[i1], 1 << q);
+                        x[i0] = up ? recv : x[i0];
+                        x[i1] = up ? x[i1] : recv;
+                    }
                 }
                 const unsigned char *wg = wt + g0 * 32;
-                // Rows in blocks of 8; inside a block one accumulator at a time runs through its 8 rows, so that the
-                // eight bit tests hit one register byte (R2P -> 7 predicates) and the adds stay predicated DADDs.  The
-                // add is a volatile asm so that neither nvvm nor ptxas turns it into add + select.
+                // Row loop: the eight flags of a row sit in one register byte, so ptxas extracts them with one R2P (7
+                // predicates) + one LOP3 and they feed eight INDEPENDENT predicated DADDs (four words x ref/alt).  Each
+                // accumulator still sees its rows in ascending order.  The add is a volatile asm so that neither nvvm
+                // nor ptxas rewrites it as add + select.
 #pragma unroll
-                for (int r0 = 0; r0 < 32; r0 += 8) {
-                    double w_ref[8], w_alt[8];
+                for (int r = 0; r < 32; ++r) {
+                    const uint32_t z = x[r & 7];
+                    const int sh = (r >> 3) * 8;
+                    const double2 w_ra = *reinterpret_cast<const double2 *>(wg + r * 32);     // (w_ref, w_alt)
+                    const double w_ref = w_ra.x, w_alt = w_ra.y;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        w_ref[r] = *reinterpret_cast<const double *>(wg + (r0 + r) * 32);
-                        w_alt[r] = *reinterpret_cast<const double *>(wg + (r0 + r) * 32 + 16);
-                    }
+                    for (int j = 0; j < SC_WPW; ++j)
+                        if (z & (1u << (sh + j))) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_ref[j]) : "d"(w_ref));
 #pragma unroll
-                    for (int j = 0; j < SC_WPW; ++j) {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            if (ref[j] & (1u << (r0 + r))) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_ref[j]) : "d"(w_ref[r]));
-#pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            if (alt[j] & (1u << (r0 + r))) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_alt[j]) : "d"(w_alt[r]));
-                    }
+                    for (int j = 0; j < SC_WPW; ++j)
+                        if (z & (1u << (sh + SC_WPW + j))) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_alt[j]) : "d"(w_alt));
                 }
                 if (!SKIP_HETS) {
                     // hets are rare (makedb.py:59 code 2; ~0.2 % of calls): visit only the rows of a word that hold
@@ -242,15 +327,18 @@ __global__ void __launch_bounds__(32 * (SC_MAX_WARPS + 1)) k_score_segments(cons
                         while (m) {
                             const int r = __ffs(m) - 1;
                             m &= m - 1;
-                            const double w_het = *reinterpret_cast<const double *>(wg + r * 32 + 8);
-                            if ((het[j] >> r) & 1u) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_het[j]) : "d"(w_het));
+                            const double w_het = *reinterpret_cast<const double *>(wg + r * 32 + 16);
+                            const uint32_t hw = __shfl_sync(0xffffffffu, het[j], r);       // het plane of row r
+                            if ((hw >> lane) & 1u) {
+                                asm volatile("add.f64 %0, %0, %1;" : "+d"(s_het[j]) : "d"(w_het));
+                                ninfo[j] += 1;
+                            }
                         }
                     }
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(empty + st));     // this warp is done with stage st
+        if (t + SC_STAGES < n_tiles) named_bar_arrive(1 + st, 32 * (ncons + 1));   // this warp is done with stage st
     }
 
 #pragma unroll
