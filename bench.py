@@ -319,19 +319,29 @@ def run_b200_arm(args):
             total_launches = t["launches"]
         barrier()
         # ---- end-to-end arm: host buffers in, host buffers out -------------------------------------
-        def e2e_step():
-            batch.upload(h_off, h_chr, h_pos, h_wei)
-            device_step()
+        # Two batch objects alternate: while one is scored, the next step's samples are copied from pinned host
+        # memory on the other's copy stream.  Every step uploads its inputs and reads its results back.
+        batch2 = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
+        pair = [batch, batch2]
+
+        def e2e_step(k):
+            cur, nxt = pair[k % 2], pair[(k + 1) % 2]
+            nxt.upload(h_off, h_chr, h_pos, h_wei)          # H2D of step k+1, overlaps the kernels of step k
+            cur.run()
+            if world > 1:
+                sharding.allreduce_batch(cur, dist, dev)
+            cur.epilogue()
             if rank == 0:
-                batch.fetch(out=out)
+                cur.fetch(out=out)                          # D2H of step k (waits for it)
             else:
-                batch.wait()
-        for _ in range(args.warmup):
-            e2e_step()
+                cur.wait()
+        pair[0].upload(h_off, h_chr, h_pos, h_wei)
+        for k in range(args.warmup):
+            e2e_step(k)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        for k in range(args.warmup, args.warmup + args.steps):
+            e2e_step(k)
         barrier()
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop() if rank == 0 else None
@@ -391,6 +401,7 @@ def run_b200_arm(args):
                                                       np.array_equal(cpu_ninfo, out["ninfo"][0]))
         print(json.dumps(line))
     batch.close()
+    batch2.close()
     g.close()
     if world > 1:
         dist.destroy_process_group()

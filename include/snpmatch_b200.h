@@ -112,8 +112,10 @@ int snpm_calculate_likelihoods(int device, const double *scores, const double *n
 int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets,
                       const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei,
                       snpm_batch **out);
-/* replace the samples of an existing batch, reusing its device buffers (copies are queued on the
- * db's stream; the host arrays must stay alive until the next wait/fetch) */
+/* replace the samples of an existing batch, reusing its device buffers.  The copies are queued on the
+ * batch's own copy stream (after the kernels that still read the previous samples), so the upload of
+ * one batch overlaps the scoring of another; snpm_batch_run waits for them on the device.  The host
+ * arrays must stay alive until the next wait/fetch of this batch. */
 int snpm_batch_upload(snpm_batch *b, int64_t n_samples, const int64_t *offsets,
                       const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei);
 int snpm_batch_destroy(snpm_batch *b);

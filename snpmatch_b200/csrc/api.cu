@@ -238,13 +238,16 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
     SNPM_TRY(b->d_chrom.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_pos.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_wei.ensure(size_t(n) * 24));
-    cudaStream_t st = db->stream;
+    // copies go to the batch's copy stream, after the last kernels that read the previous inputs
+    cudaStream_t st = b->copy_stream;
+    SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_inputs_free, 0));
     SNPM_CUDA(cudaMemcpyAsync(b->d_off.p, offsets, size_t(S + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n) {
         SNPM_CUDA(cudaMemcpyAsync(b->d_chrom.p, chrom, size_t(n) * 4, cudaMemcpyHostToDevice, st));
         SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
         SNPM_CUDA(cudaMemcpyAsync(b->d_wei.p, wei, size_t(n) * 24, cudaMemcpyHostToDevice, st));
     }
+    SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
     b->ran = b->ran_windows = b->epilogue_done = false;
     return SNPM_OK;
 }
@@ -259,12 +262,18 @@ int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets, co
     for (int i = 0; i < SNPM_N_EVENTS; ++i) {
         if (cudaEventCreate(&b->ev[i]) != cudaSuccess) { snpm_batch_destroy(b); return fail(SNPM_E_CUDA, "cudaEventCreate failed"); }
     }
+    if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_inputs_free, cudaEventDisableTiming) != cudaSuccess) {
+        snpm_batch_destroy(b);
+        return fail(SNPM_E_CUDA, "snpm_batch_create: copy stream / events");
+    }
     if (cudaMallocHost(reinterpret_cast<void **>(&b->h_status), 8 * sizeof(int)) != cudaSuccess) {
         snpm_batch_destroy(b);
         return fail(SNPM_E_NOMEM, "cudaMallocHost failed");
     }
     int rc = batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, wei);
-    if (rc == SNPM_OK && cudaStreamSynchronize(db->stream) != cudaSuccess) rc = fail(SNPM_E_CUDA, "snpm_batch_create: upload failed");
+    if (rc == SNPM_OK && cudaStreamSynchronize(b->copy_stream) != cudaSuccess) rc = fail(SNPM_E_CUDA, "snpm_batch_create: upload failed");
     if (rc != SNPM_OK) { snpm_batch_destroy(b); return rc; }
     *out = b;
     return SNPM_OK;
@@ -281,6 +290,9 @@ int snpm_batch_destroy(snpm_batch *b) {
     if (!b) return SNPM_OK;
     cudaSetDevice(b->db->device);
     cudaStreamSynchronize(b->db->stream);
+    if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
+    if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
+    if (b->ev_inputs_free) cudaEventDestroy(b->ev_inputs_free);
     DevBuf *bufs[] = {&b->d_off, &b->d_chrom, &b->d_pos, &b->d_wei, &b->d_filter, &b->d_match_row, &b->d_tile_cnt, &b->d_tile_off,
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
@@ -324,6 +336,7 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_mstart.ensure(size_t(S + 1) * 4));
     SNPM_TRY(b->d_seg_off.ensure(size_t(S + 1) * 4));
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
+    SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_uploaded, 0));       // the samples are on the device
     SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
     if (algo == 0) algo = (n / S) * 32 >= db->n_rows ? 2 : 1;
     const int64_t *filter = b->n_filter ? b->d_filter.as<int64_t>() : nullptr;
@@ -409,6 +422,7 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     SNPM_KERNEL_CHECK();
     b->launches += 1;
     rec(b, SNPM_EV_COMBINE);
+    SNPM_CUDA(cudaEventRecord(b->ev_inputs_free, st));
     b->ran = true;
     b->ran_windows = false;
     b->epilogue_done = false;
@@ -741,6 +755,7 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
         b->launches += 1;
     }
     rec(b, SNPM_EV_COMBINE);
+    SNPM_CUDA(cudaEventRecord(b->ev_inputs_free, st));
     b->n_windows = W;
     b->bin_len = bin_len;
     b->lr_thres = lr_thres;

@@ -118,6 +118,9 @@ struct snpm_batch {
     // state
     bool ran = false, ran_windows = false, epilogue_done = false;
     int launches = 0;
+    // uploads run on the batch's own copy stream so that the H2D of one batch overlaps the kernels of another
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_uploaded = nullptr, ev_inputs_free = nullptr;
     cudaEvent_t ev[SNPM_N_EVENTS] = {};
     bool ev_rec[SNPM_N_EVENTS] = {};
     int *h_status = nullptr;  // pinned, 8 ints
