@@ -254,11 +254,13 @@ def run_b200_arm(args):
     samples = make_samples(positions, regions, n_acc, S, args.markers)
     # a rank only needs the markers that can fall into its row range (constant per-GPU join work and H2D bytes)
     parts = samples
+    slices = [(0, len(s["pos"])) for s in samples]
     if world > 1:
-        parts = []
+        parts, slices = [], []
         for s in samples:
             i0, i1 = sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, positions, r0, r1)
             parts.append({k: s[k][i0:i1] for k in ("chr_ix", "pos", "wei")})
+            slices.append((i0, i1))
     offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in parts])]).astype(np.int64)
     n_tot = int(offs[-1])
 
@@ -318,6 +320,35 @@ def run_b200_arm(args):
             score_ms.append(t["score_ms"])
             total_launches = t["launches"]
         barrier()
+        # ---- called-genotype variant of the same samples (0/1 weights, as BED / GT-only VCF inputs give): popcount kernel
+        hard = lib.Batch(db, h_off, h_chr, h_pos, np.concatenate([synth.hard_weights(s["code"][:len(p["pos"])] if world == 1 else
+                                                                                     s["code"][sl[0]:sl[1]])
+                                                                  for s, p, sl in zip(samples, parts, slices)]))
+        hard_ms, hard_kernel_ms = 0.0, []
+
+        def hard_step():
+            hard.run(kernel_mode=lib.KERNEL_POPCOUNT)
+            if world > 1:
+                sharding.allreduce_batch(hard, dist, dev)
+            hard.epilogue()
+        for _ in range(args.warmup):
+            hard_step()
+        hard.wait()
+        barrier()
+        hv0, hv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hv0.record(stream)
+        for _ in range(args.steps):
+            hard_step()
+        hv1.record(stream)
+        hard.wait()
+        barrier()
+        hard_ms = hv0.elapsed_time(hv1)
+        for _ in range(args.steps):
+            hard_step()
+            hard_kernel_ms.append(hard.timings()["score_ms"])
+        hard_res = hard.fetch()
+        hard.close()
+        barrier()
         # ---- end-to-end arm: host buffers in, host buffers out -------------------------------------
         # Two batch objects alternate: while one is scored, the next step's samples are copied from pinned host
         # memory on the other's copy stream.  Every step uploads its inputs and reads its results back.
@@ -347,10 +378,10 @@ def run_b200_arm(args):
         clocks = sampler.stop() if rank == 0 else None
 
     m_per_sample = out["m"].astype(np.int64) if rank == 0 else None
-    tms = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(tms[0]), float(tms[1])
+    dev_ms, e2e_ms, hard_ms = float(tms[0]), float(tms[1]), float(tms[2])
 
     if rank == 0:
         m_total = int(m_per_sample.sum())
@@ -388,6 +419,15 @@ def run_b200_arm(args):
             "clocks": clocks,
             "matched_markers_per_step": m_total,
         }
+        # the same samples as called genotypes (0/1 weights): popcount kernel, bound by the HBM row gather
+        hk_ms = float(np.mean(hard_kernel_ms))
+        h_bytes = rows_here * ((n_acc + 3) // 4 + 5) + 12 * ((n_acc + 63) // 64 * 64) * int(np.ceil(args.markers / 1000.0)) * S
+        h_ach = h_bytes / (hk_ms * 1e-3) / 1e9 if hk_ms > 0 else 0.0
+        line["called_genotypes"] = {
+            "workload": "same batch with one-hot weights (BED / GT-only VCF inputs), popcount kernel k_score_hard",
+            "value": int(hard_res["m"].sum()) * n_acc * args.steps / (hard_ms * 1e-3), "unit": UNIT, "ms_per_step": hard_ms / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_score_hard", "achieved": h_ach, "peak": peak, "unit": "GB/s",
+                         "frac": h_ach / peak if peak else None, "algorithmic_bytes_per_launch": int(h_bytes), "kernel_ms": hk_ms}}
         if not args.no_cpu_baseline and world == 1:
             s0 = samples[0]
             rows, codes = cpu_prepare_sample(s0, n_acc, args.cpu_markers)

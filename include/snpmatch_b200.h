@@ -123,7 +123,11 @@ int snpm_batch_destroy(snpm_batch *b);
  * GLOBAL database row is in the sorted list (applies to every sample of the batch); n = 0 clears */
 int snpm_batch_set_row_filter(snpm_batch *b, const int64_t *sorted_rows, int64_t n);
 /* join + chunked scoring + per-sample totals; device work is queued on the db's stream and the
- * call returns without waiting (inputs already resident).  mode: 0 = reference-order kernel. */
+ * call returns without waiting (inputs already resident).
+ * mode bits 0-7: scoring kernel — 0 = fp64 kernel in the reference's summation order (any weights);
+ *                1 = popcount kernel for called genotypes (every weight row one-hot, as ParseInputs.get_wei_from_GT
+ *                    produces, parsers.py:132-139; exact in any order; SNPM_E_ARG at wait/fetch otherwise).
+ * mode bits 8-15: join algorithm (0 auto, 1 binary search, 2 merge-path). */
 int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode);
 /* likelihood epilogue on the (possibly all-reduced) totals; queued, not waited for */
 int snpm_batch_epilogue(snpm_batch *b);

@@ -237,7 +237,9 @@ class Genotyper(object):
             if filter_pos_ix is not None:
                 assert type(filter_pos_ix) is np.ndarray, "provide np array for indices to be considered"
                 batch.set_row_filter(filter_pos_ix)
-            batch.run(self._skip_db_hets)
+            # called genotypes (BED, VCF without PL) take the popcount kernel; likelihood-weighted samples the fp64 one
+            mode = lib.KERNEL_POPCOUNT if lib.weights_are_one_hot(wei) else lib.KERNEL_FP64
+            batch.run(self._skip_db_hets, kernel_mode=mode)
             batch.epilogue()
             r = batch.fetch()
             db_idx, s_idx = batch.fetch_pairs(0)

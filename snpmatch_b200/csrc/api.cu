@@ -5,6 +5,7 @@
 #include "score.cuh"
 #include "windows.cuh"
 #include "f1.cuh"
+#include "hardcall.cuh"
 
 namespace snpm {
 thread_local std::string g_last_error;
@@ -297,7 +298,7 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
                       &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
-                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out};
+                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
@@ -393,7 +394,7 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
     const int kernel_mode = mode & 0xff, algo = (mode >> 8) & 0xff;
-    if (kernel_mode != 0) return fail(SNPM_E_ARG, "snpm_batch_run: unknown kernel mode %d", kernel_mode);
+    if (kernel_mode != 0 && kernel_mode != 1) return fail(SNPM_E_ARG, "snpm_batch_run: unknown kernel mode %d", kernel_mode);
     if (algo > 2) return fail(SNPM_E_ARG, "snpm_batch_run: unknown join algorithm %d", algo);
     b->launches = 0;
     for (int i = 0; i < SNPM_N_EVENTS; ++i) b->ev_rec[i] = false;
@@ -414,8 +415,32 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     a.part_score = b->d_part_score.as<double>();
     a.part_ninfo = b->d_part_ninfo.as<int32_t>();
     a.a_pad = db->stride * 32;
-    SNPM_TRY(launch_score(st, a, int(b->nseg_cap), skip_db_hets != 0));
-    if (b->nseg_cap > 0) b->launches += 1;
+    if (kernel_mode == 1 && b->nseg_cap > 0) {
+        // called genotypes (one-hot weights): popcount kernel, exact in every summation order
+        SNPM_TRY(b->d_pair_code.ensure(size_t(std::max<int64_t>(b->n, 1))));
+        k_pair_codes<<<int(ceil_div64(b->n, 256)), 256, 0, st>>>(a.pair_w, b->d_prefix.as<int32_t>() + b->n, b->d_pair_code.as<uint8_t>());
+        SNPM_KERNEL_CHECK();
+        HardArgs h = {};
+        h.packed = a.packed; h.stride = a.stride; h.pair_db = a.pair_db; h.pair_code = b->d_pair_code.as<uint8_t>();
+        h.seg_off = a.seg_off; h.mstart = a.mstart; h.S = a.S; h.chunk = a.chunk;
+        h.part_score = a.part_score; h.part_ninfo = a.part_ninfo; h.a_pad = a.a_pad; h.status = b->d_status.as<int>();
+        const int wx = std::min<int>(db->stride, HC_THREADS), spc = std::min(HC_THREADS / wx, HC_MAX_SEGS);
+        dim3 hgrid(unsigned(ceil_div64(b->nseg_cap, spc)), unsigned((db->stride + HC_THREADS - 1) / HC_THREADS));
+        const size_t hsmem = size_t(spc) * SNPM_CHUNK_ROWS * 5;
+        static bool hc_attr = false;
+        if (!hc_attr) {
+            SNPM_CUDA(cudaFuncSetAttribute(k_score_hard<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            SNPM_CUDA(cudaFuncSetAttribute(k_score_hard<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            hc_attr = true;
+        }
+        if (skip_db_hets) k_score_hard<true><<<hgrid, HC_THREADS, hsmem, st>>>(h);
+        else k_score_hard<false><<<hgrid, HC_THREADS, hsmem, st>>>(h);
+        SNPM_KERNEL_CHECK();
+        b->launches += 2;
+    } else {
+        SNPM_TRY(launch_score(st, a, int(b->nseg_cap), skip_db_hets != 0));
+        if (b->nseg_cap > 0) b->launches += 1;
+    }
     rec(b, SNPM_EV_SCORE);
     dim3 cgrid((db->n_acc + 255) / 256, unsigned(b->S));
     k_combine<<<cgrid, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, a.seg_off, a.mstart, 0, nullptr, nullptr, b->d_red.as<double>());
@@ -471,6 +496,8 @@ int snpm_batch_wait(snpm_batch *b, float *ms_device) {
         return fail(SNPM_E_ASSERT, "provided y is greater than n (%d window cells; likeliTest, snpmatch.py:43)", b->h_status[1]);
     if (b->h_status[2] > 0)
         return fail(SNPM_E_ARG, "identity table too short for %d window cells", b->h_status[2]);
+    if (b->h_status[3] > 0)
+        return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
     return SNPM_OK;
 }
 

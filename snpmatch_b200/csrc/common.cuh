@@ -115,6 +115,7 @@ struct snpm_batch {
     snpm::DevBuf d_win_count, d_win_off, d_win_begin, d_win_end, d_kmax, d_win_L, d_win_LR, d_win_ident, d_win_amb;
     // f1
     snpm::DevBuf d_f1_acc, d_f1_part, d_f1_out;
+    snpm::DevBuf d_pair_code;
     // state
     bool ran = false, ran_windows = false, epilogue_done = false;
     int launches = 0;

@@ -24,7 +24,7 @@
 namespace snpm {
 
 constexpr int SC_TILE_ROWS = 64;   // multiple of 32
-constexpr int SC_STAGES = 3;
+constexpr int SC_STAGES = 4;
 constexpr int SC_WPW = 4;          // words (of 32 accessions) per consumer warp
 constexpr int SC_MAX_WARPS = 12;   // consumer warps per CTA (+1 producer warp)
 
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(32 * NWARPS, MIN_BLOCKS) k_score_segments(cons
             const uint32_t total = uint32_t(rows) * cpr;
             const uint32_t magic = cpr > 1u ? 0xFFFFFFFFu / cpr + 1u : 0u; // floor(i / cpr) = umulhi(i, magic) for i < 2^16, cpr > 1
             const uint64_t *src0 = a.packed + w_start;
+#pragma unroll 6
             for (uint32_t i = lane; i < ((total + 31u) & ~31u); i += 32) {
                 const uint32_t r = cpr > 1u ? __umulhi(i, magic) : i, c = i - r * cpr;
                 const int64_t lo_i = __shfl_sync(0xffffffffu, idx0, r & 31), hi_i = __shfl_sync(0xffffffffu, idx1, r & 31);
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(32 * NWARPS, MIN_BLOCKS) k_score_segments(cons
     int32_t ninfo[SC_WPW];
 #pragma unroll
     for (int j = 0; j < SC_WPW; ++j) { s_ref[j] = 0.0; s_het[j] = 0.0; s_alt[j] = 0.0; ninfo[j] = 0; }
+    const uint32_t lanebit = 1u << lane;
     // per-stage constants of the transpose butterfly (j = 16, 8, 4, 2, 1)
     uint32_t t_sel[5], t_rot[5];
     {
@@ -256,9 +258,9 @@ __global__ void __launch_bounds__(32 * NWARPS, MIN_BLOCKS) k_score_segments(cons
                     het_rows[j] = SKIP_HETS ? 0u : __ballot_sync(0xffffffffu, het[j] != 0u);
                     x[j] = ~(lo | hi);
                     x[SC_WPW + j] = lo & ~hi;
-                    // informative sites of this lane's accession: transpose the called plane, count its rows
-                    // (hets are counted where they are added; snpmatch.py:78-79,88)
-                    ninfo[j] += __popc(warp_transpose32(x[j] | x[SC_WPW + j], t_sel, t_rot));
+                    // informative sites of this lane's accession (snpmatch.py:78-79,88): transpose the plane of called
+                    // genotypes (hets count unless they are skipped) and count its rows
+                    ninfo[j] += __popc(warp_transpose32(SKIP_HETS ? (x[j] | x[SC_WPW + j]) : ~(lo & hi), t_sel, t_rot));
                 }
                 // (1) inside the lane: 8x8 bit transpose of the eight planes per byte column, after which byte b of
                 //     x[i] holds the eight class flags (ref word 0-3, alt word 0-3) of accession 8b+i in this row
@@ -329,10 +331,7 @@ __global__ void __launch_bounds__(32 * NWARPS, MIN_BLOCKS) k_score_segments(cons
                             m &= m - 1;
                             const double w_het = *reinterpret_cast<const double *>(wg + r * 32 + 16);
                             const uint32_t hw = __shfl_sync(0xffffffffu, het[j], r);       // het plane of row r
-                            if ((hw >> lane) & 1u) {
-                                asm volatile("add.f64 %0, %0, %1;" : "+d"(s_het[j]) : "d"(w_het));
-                                ninfo[j] += 1;
-                            }
+                            if (hw & lanebit) asm volatile("add.f64 %0, %0, %1;" : "+d"(s_het[j]) : "d"(w_het));
                         }
                     }
                 }

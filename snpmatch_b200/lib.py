@@ -23,6 +23,16 @@ SNPM_E_ASSERT = -5
 CHUNK_ROWS = 1000
 
 JOIN_AUTO, JOIN_SEARCH, JOIN_MERGEPATH = 0, 1, 2
+KERNEL_FP64, KERNEL_POPCOUNT = 0, 1
+
+
+def weights_are_one_hot(wei):
+    """True when every weight row is one of (1,0,0), (0,1,0), (0,0,1): called genotypes, as
+    ParseInputs.get_wei_from_GT produces (parsers.py:132-139) — the popcount kernel applies."""
+    w = np.asarray(wei)
+    if w.ndim != 2 or w.shape[1] != 3 or len(w) == 0:
+        return False
+    return bool(np.all((w == 0.0) | (w == 1.0)) and np.all(w.sum(axis=1) == 1.0))
 
 
 class SnpmError(RuntimeError):

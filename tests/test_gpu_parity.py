@@ -368,6 +368,45 @@ def test_batch_of_samples_equals_single_runs(lib):
     one.close(); b.close(); db.close()
 
 
+@pytest.mark.parametrize("skip", [False, True])
+def test_popcount_kernel_equals_fp64_kernel_for_called_genotypes(lib, skip):
+    n_rows, n_acc = 80000, 1135
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=5 + 7 * i, n_db=nd, n_extra=ne, seed=700 + i, het=0.05)
+               for i, (nd, ne) in enumerate([(3333, 100), (1, 0), (1000, 10), (2049, 5), (0, 3)])]
+    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])])
+    wei = np.concatenate([s["wei_hard"] for s in samples])
+    assert lib.weights_are_one_hot(wei) and not lib.weights_are_one_hot(samples[0]["wei"])
+    b = lib.Batch(db, offs, np.concatenate([s["chr_ix"] for s in samples]), np.concatenate([s["pos"] for s in samples]), wei)
+    res = {}
+    for mode in (lib.KERNEL_FP64, lib.KERNEL_POPCOUNT):
+        b.run(skip_db_hets=skip, kernel_mode=mode)
+        b.epilogue()
+        res[mode] = {k: v.copy() for k, v in b.fetch().items()}
+    for k in ("score", "matches", "ninfo", "m", "prob", "L", "LR"):
+        assert np.array_equal(res[0][k], res[1][k], equal_nan=True), k
+    # and against the oracle for one sample
+    s = samples[0]
+    db_idx, s_idx = b.fetch_pairs(0)
+    ref_s, ref_n = np.zeros(n_acc), np.zeros(n_acc, dtype=np.int64)
+    codes = synth.panel_codes(synth.SEED_PANEL, db_idx, n_acc)
+    for j in range(0, len(db_idx), 1000):
+        t_s, t_n = orc.match_gts_accs(s["wei_hard"][s_idx[j:j + 1000]], codes[j:j + 1000], skip)
+        ref_s, ref_n = ref_s + t_s, ref_n + t_n
+    assert np.array_equal(res[1]["score"][0], ref_s) and np.array_equal(res[1]["ninfo"][0], ref_n)
+    b.close()
+    # likelihood weights are refused by the popcount kernel
+    s = samples[0]
+    b = lib.Batch(db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei"])
+    b.run(kernel_mode=lib.KERNEL_POPCOUNT)
+    with pytest.raises(lib.SnpmError):
+        b.wait()
+    b.close()
+    db.close()
+
+
 def test_row_filter_refine_path(lib, small_geno, small_panel, sample_inbred):
     p, s = small_panel, sample_inbred
     keep_rows = np.arange(0, 6000, 3)
