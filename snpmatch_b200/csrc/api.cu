@@ -425,7 +425,9 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
         h.seg_off = a.seg_off; h.mstart = a.mstart; h.S = a.S; h.chunk = a.chunk;
         h.part_score = a.part_score; h.part_ninfo = a.part_ninfo; h.a_pad = a.a_pad; h.status = b->d_status.as<int>();
         const int wx = std::min<int>(db->stride, HC_THREADS), spc = std::min(HC_THREADS / wx, HC_MAX_SEGS);
-        dim3 hgrid(unsigned(ceil_div64(b->nseg_cap, spc)), unsigned((db->stride + HC_THREADS - 1) / HC_THREADS));
+        h.wx = wx;
+        h.spc = spc;
+        dim3 hgrid(unsigned(ceil_div64(b->nseg_cap, spc)), unsigned((db->stride + wx - 1) / wx));
         const size_t hsmem = size_t(spc) * SNPM_CHUNK_ROWS * 5;
         static bool hc_attr = false;
         if (!hc_attr) {

@@ -41,7 +41,18 @@ inline int fail(int code, const char *fmt, ...) {
         if (rc__ != SNPM_OK) return rc__; \
     } while (0)
 
-#define SNPM_KERNEL_CHECK() SNPM_CUDA(cudaGetLastError())
+// launch check; with SNPM_SYNC_DEBUG=1 in the environment every launch is also waited for, so that a device fault is
+// reported at the kernel that caused it
+static inline bool snpm_sync_debug() {
+    static int v = -1;
+    if (v < 0) v = getenv("SNPM_SYNC_DEBUG") ? 1 : 0;
+    return v == 1;
+}
+#define SNPM_KERNEL_CHECK()                                              \
+    do {                                                                 \
+        SNPM_CUDA(cudaGetLastError());                                   \
+        if (snpm_sync_debug()) SNPM_CUDA(cudaDeviceSynchronize());       \
+    } while (0)
 
 // Grow-only device allocation.
 struct DevBuf {

@@ -29,6 +29,8 @@ struct HardArgs {
     int32_t *part_ninfo;          // [nseg, a_pad]
     int32_t a_pad;
     int *status;                  // status[3] += rows whose weights were not one-hot
+    int32_t wx;                   // words per CTA slice = min(stride, HC_THREADS)
+    int32_t spc;                  // segments per CTA = min(HC_THREADS / wx, HC_MAX_SEGS)
 };
 
 // full adder on bit planes: (h, l) = a + b + c
@@ -74,11 +76,12 @@ struct VCounter {                 // bit-sliced counter of 32 lanes
 // HC_THREADS / wx segments side by side (wx = words of its slice): thread -> (segment q, word w), no cross-thread reduction.
 template <bool SKIP_HETS>
 __global__ void __launch_bounds__(HC_THREADS) k_score_hard(const HardArgs a) {
-    const int wx = min(a.stride - int(blockIdx.y) * HC_THREADS, HC_THREADS);
-    const int spc = min(HC_THREADS / wx, HC_MAX_SEGS);
+    const int wx = a.wx, spc = a.spc;
     const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
     const int seg = blockIdx.x * spc + q;
+    const int word = blockIdx.y * wx + w;
     const bool active = q < spc && seg < a.seg_off[a.S];
+    const bool has_word = word < a.stride;
     int begin = 0, end = 0;
     if (active) {
         int lo_s = 0, hi_s = a.S;
@@ -89,8 +92,7 @@ __global__ void __launch_bounds__(HC_THREADS) k_score_hard(const HardArgs a) {
         begin = a.mstart[lo_s] + (seg - a.seg_off[lo_s]) * a.chunk;
         end = min(a.mstart[lo_s + 1], begin + a.chunk);
     }
-    const int word = blockIdx.y * HC_THREADS + w;
-    const uint64_t *col = a.packed + word;
+    const uint64_t *col = a.packed + (has_word ? word : 0);
 
     // stage the segment's row numbers and sample calls in shared memory (coalesced, once): the gathers below then have
     // no dependent index load in front of them
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(HC_THREADS) k_score_hard(const HardArgs a) {
         }
     }
     if (bad) atomicAdd(a.status + 3, bad);
-    if (!active) return;
+    if (!active || !has_word) return;
     double *ps = a.part_score + int64_t(seg) * a.a_pad + int64_t(word) * 32;
     int32_t *pn = a.part_ninfo + int64_t(seg) * a.a_pad + int64_t(word) * 32;
 #pragma unroll 4

@@ -445,3 +445,68 @@ def test_dense_sample_properties(lib):
         assert r["ninfo"][0].max() <= n_rows and (r["matches"][0] <= r["ninfo"][0]).all()
         b.close()
     db.close()
+
+
+def test_wide_panel_20k_accessions(lib):
+    """BASELINE configs[4] shape at reduced row count: 20 000 accessions (626-word rows, 20 word slices per segment);
+    fp64 and popcount kernels against the oracle on the rows they touch."""
+    n_rows, n_acc = 40000, 20000
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    s = synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=12345, n_db=2100, n_extra=100, seed=42)
+    b = lib.Batch(db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei"])
+    b.run()
+    b.epilogue()
+    r = b.fetch()
+    db_idx, s_idx = b.fetch_pairs(0)
+    codes = synth.panel_codes(synth.SEED_PANEL, db_idx, n_acc)
+    score, ninfo = np.zeros(n_acc), np.zeros(n_acc, dtype=np.int64)
+    for j in range(0, len(db_idx), 1000):
+        t_s, t_n = orc.match_gts_accs(s["wei"][s_idx[j:j + 1000]], codes[j:j + 1000])
+        score, ninfo = score + t_s, ninfo + t_n
+    assert np.array_equal(r["score"][0], score) and np.array_equal(r["ninfo"][0], ninfo)
+    assert int(np.nanargmin(r["L"][0])) == 12345
+    b.upload([0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei_hard"])
+    b.run(kernel_mode=lib.KERNEL_POPCOUNT)
+    b.epilogue()
+    r = b.fetch()
+    score, ninfo = np.zeros(n_acc), np.zeros(n_acc, dtype=np.int64)
+    for j in range(0, len(db_idx), 1000):
+        t_s, t_n = orc.match_gts_accs(s["wei_hard"][s_idx[j:j + 1000]], codes[j:j + 1000])
+        score, ninfo = score + t_s, ninfo + t_n
+    assert np.array_equal(r["score"][0], score) and np.array_equal(r["ninfo"][0], ninfo)
+    b.close()
+    db.close()
+
+
+def test_cross_full_panel_properties(lib):
+    """BASELINE configs[2] shape by properties: windows of a sample drawn from ONE accession; every non-empty
+    window's best likelihood belongs to that accession, window counts add up to the totals, F1 pairs with the true
+    accession as a parent carry its called sites."""
+    from snpmatch_b200.core import genomes, snpmatch
+    n_rows, n_acc = 400000, 1135
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    s = synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=77, n_db=20000, n_extra=500, seed=43, err=0.0, het=0.0)
+    gen = genomes.Genome("athaliana_tair10")
+    cnt, off, n_w, _ = gen.window_layout(np.array(synth.TAIR10_CHRS), 300000)
+    b = lib.Batch(db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei_hard"])
+    b.run_windows(False, 300000, cnt, off, n_w, snpmatch.identity_kmax_table(2000, 0.02))
+    b.epilogue()
+    tot = b.fetch()
+    w = b.fetch_windows()
+    assert n_w == 399 and int(w["nrows"].sum()) == int(tot["m"][0]) == len(w["matched_s_idx"])
+    assert np.array_equal(w["ninfo"].astype(np.int64).sum(axis=0), tot["ninfo"][0])
+    assert np.array_equal(w["score"].sum(axis=0), tot["score"][0])            # 0/1 weights: exact in any order
+    live = np.flatnonzero(w["nrows"] > 0)
+    assert len(live) > 380
+    assert np.all(w["score"][live, 77] == w["ninfo"][live, 77])               # perfect match in every window
+    assert np.all(w["L"][live, 77] == 1.0) and np.all(w["identical"][live, 77] == 1)
+    assert int(np.nanargmin(tot["L"][0])) == 77
+    top = np.argsort(-tot["prob"][0])[:10]
+    f_score, f_ninfo = b.f1_pairs(top)
+    assert len(f_score) == 45 and np.all(f_ninfo <= int(tot["m"][0])) and np.all(f_score <= f_ninfo)
+    b.close()
+    db.close()
