@@ -103,7 +103,7 @@ class CrossIdentifier(object):
             n_max = int(np.unique(wkey, return_counts=True)[1].max())
         kmax = snpmatch.identity_kmax_table(n_max, self.error_rate)
         self._close_batch()
-        batch = lib.Batch(g.db, [0, len(pos)], cid, pos, wei)
+        batch = g.db.scratch_batch([0, len(pos)], cid, pos, wei)
         self._batch = batch
         self._order = order
         self._join_style_same = np.array_equal(

@@ -232,7 +232,7 @@ class Genotyper(object):
         g = self.g
         order, cid, pos = g.prepare_markers(self.inputs.chrs, self.inputs.pos)
         wei = np.ascontiguousarray(np.asarray(self.inputs.wei, dtype=np.float64)[order])
-        batch = lib.Batch(g.db, [0, len(pos)], cid, pos, wei)
+        batch = g.db.scratch_batch([0, len(pos)], cid, pos, wei)
         try:
             if filter_pos_ix is not None:
                 assert type(filter_pos_ix) is np.ndarray, "provide np array for indices to be considered"

@@ -129,6 +129,7 @@ int snpm_db_destroy(snpm_db *db) {
     if (db->d_packed) cudaFree(db->d_packed);
     if (db->d_pos) cudaFree(db->d_pos);
     if (db->d_chr_regions) cudaFree(db->d_chr_regions);
+    if (db->scratch_batch_) { snpm_batch_destroy(db->scratch_batch_); db->scratch_batch_ = nullptr; }
     db->scratch.release();
     if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
     delete db;
@@ -253,11 +254,7 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
     return SNPM_OK;
 }
 
-int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos,
-                      const double *wei, snpm_batch **out) {
-    if (!db || !out) return fail(SNPM_E_ARG, "snpm_batch_create: NULL handle");
-    *out = nullptr;
-    SNPM_CUDA(cudaSetDevice(db->device));
+static int batch_new(snpm_db *db, snpm_batch **out) {
     snpm_batch *b = new snpm_batch();
     b->db = db;
     for (int i = 0; i < SNPM_N_EVENTS; ++i) {
@@ -273,6 +270,17 @@ int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets, co
         snpm_batch_destroy(b);
         return fail(SNPM_E_NOMEM, "cudaMallocHost failed");
     }
+    *out = b;
+    return SNPM_OK;
+}
+
+int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos,
+                      const double *wei, snpm_batch **out) {
+    if (!db || !out) return fail(SNPM_E_ARG, "snpm_batch_create: NULL handle");
+    *out = nullptr;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    snpm_batch *b = nullptr;
+    SNPM_TRY(batch_new(db, &b));
     int rc = batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, wei);
     if (rc == SNPM_OK && cudaStreamSynchronize(b->copy_stream) != cudaSuccess) rc = fail(SNPM_E_CUDA, "snpm_batch_create: upload failed");
     if (rc != SNPM_OK) { snpm_batch_destroy(b); return rc; }
@@ -339,7 +347,10 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
     SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_uploaded, 0));       // the samples are on the device
     SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
-    if (algo == 0) algo = (n / S) * 32 >= db->n_rows ? 2 : 1;
+    // auto = per-marker binary search: measured on B200 it beats the merge-path kernel even for a sample that carries
+    // every panel row (0.47 ms vs 4.3 ms at 10.7 M markers; profiles/r1_configs.jsonl) — the top of the search tree is
+    // cache resident.  Merge-path stays selectable (algo 2).
+    if (algo == 0) algo = 1;
     const int64_t *filter = b->n_filter ? b->d_filter.as<int64_t>() : nullptr;
     if (n_tiles > 0) {
         if (algo == 2)
@@ -444,8 +455,9 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
         if (b->nseg_cap > 0) b->launches += 1;
     }
     rec(b, SNPM_EV_SCORE);
-    dim3 cgrid((db->n_acc + 255) / 256, unsigned(b->S));
-    k_combine<<<cgrid, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, a.seg_off, a.mstart, 0, nullptr, nullptr, b->d_red.as<double>());
+    // one warp per CTA: the per-accession chain is sequential, so spread the accessions over as many SMs as possible
+    dim3 cgrid((db->n_acc + 31) / 32, unsigned(b->S));
+    k_combine<<<cgrid, 32, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, a.seg_off, a.mstart, 0, nullptr, nullptr, b->d_red.as<double>());
     SNPM_KERNEL_CHECK();
     b->launches += 1;
     rec(b, SNPM_EV_COMBINE);
@@ -586,14 +598,17 @@ int snpm_score(snpm_db *db, const int32_t *s_chrom_id, const int32_t *s_pos, con
                const int64_t *filter_rows, int64_t n_filter, double *score, int64_t *matches, int64_t *ninfo, int64_t *m,
                double *prob, double *L, double *LR) {
     if (!db) return fail(SNPM_E_ARG, "snpm_score: db is NULL");
+    SNPM_CUDA(cudaSetDevice(db->device));
     const int64_t off[2] = {0, n};
-    snpm_batch *b = nullptr;
-    SNPM_TRY(snpm_batch_create(db, 1, off, s_chrom_id, s_pos, wei, &b));
-    int rc = snpm_batch_set_row_filter(b, filter_rows, n_filter);
+    // one batch object lives with the handle: repeated calls reuse its device buffers, stream and events
+    if (!db->scratch_batch_) SNPM_TRY(batch_new(db, &db->scratch_batch_));
+    snpm_batch *b = db->scratch_batch_;
+    int rc = batch_upload(b, 1, off, s_chrom_id, s_pos, wei);
+    if (rc == SNPM_OK) rc = snpm_batch_set_row_filter(b, filter_rows, n_filter);
     if (rc == SNPM_OK) rc = snpm_batch_run(b, skip_db_hets, 0);
     if (rc == SNPM_OK) rc = snpm_batch_epilogue(b);
     if (rc == SNPM_OK) rc = snpm_batch_fetch(b, score, matches, ninfo, m, prob, L, LR);
-    snpm_batch_destroy(b);
+    if (rc != SNPM_OK) { cudaStreamSynchronize(b->copy_stream); cudaStreamSynchronize(db->stream); }   // the host arrays may go away
     return rc;
 }
 
@@ -772,8 +787,8 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
     SNPM_TRY(launch_score(st, a, W, skip_db_hets != 0));
     if (W > 0) b->launches += 1;
     rec(b, SNPM_EV_SCORE);
-    dim3 cgrid((db->n_acc + 255) / 256, 1);
-    k_combine<<<cgrid, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, nullptr, nullptr, W, a.seg_begin, a.seg_end, b->d_red.as<double>());
+    dim3 cgrid((db->n_acc + 31) / 32, 1);
+    k_combine<<<cgrid, 32, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, nullptr, nullptr, W, a.seg_begin, a.seg_end, b->d_red.as<double>());
     SNPM_KERNEL_CHECK();
     b->launches += 1;
     if (W > 0) {

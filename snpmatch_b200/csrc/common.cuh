@@ -101,6 +101,7 @@ struct snpm_db {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     snpm::DevBuf scratch;               // upload staging for int8 rows
+    struct snpm_batch *scratch_batch_ = nullptr;   // reused by snpm_score
 };
 
 enum { SNPM_EV_START = 0, SNPM_EV_JOIN, SNPM_EV_SCORE, SNPM_EV_COMBINE, SNPM_EV_EPI_START, SNPM_EV_EPI_END, SNPM_N_EVENTS };

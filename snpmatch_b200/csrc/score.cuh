@@ -375,7 +375,24 @@ __global__ void __launch_bounds__(256) k_combine(const double *__restrict__ part
     if (acc < n_acc) {
         double tot = 0.0;
         long long ni = 0;
-        for (int j = j0; j < j1; ++j) {
+        // the adds are sequential (reference order); the loads are not: fetch 16 segments ahead, then add in order
+        constexpr int CB = 16;
+        int j = j0;
+        for (; j + CB <= j1; j += CB) {
+            double v[CB];
+            int32_t c[CB];
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                v[k] = __ldg(part_score + int64_t(j + k) * a_pad + acc);
+                c[k] = __ldg(part_ninfo + int64_t(j + k) * a_pad + acc);
+            }
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                tot = tot + v[k];
+                ni += c[k];
+            }
+        }
+        for (; j < j1; ++j) {
             tot = tot + part_score[int64_t(j) * a_pad + acc];
             ni += part_ninfo[int64_t(j) * a_pad + acc];
         }

@@ -155,6 +155,11 @@ class Database(object):
         self.packed_bytes = lib.snpm_db_packed_bytes(h)
 
     def close(self):
+        b = getattr(self, "_scratch", None)
+        if b is not None:
+            b._scratch = False
+            b.close()
+            self._scratch = None
         if getattr(self, "_h", None):
             load().snpm_db_destroy(self._h)
             self._h = None
@@ -191,6 +196,19 @@ class Database(object):
 
     def set_stream(self, cuda_stream):
         check(load().snpm_db_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def scratch_batch(self, offsets, s_chrom_id, s_pos, wei):
+        """A Batch that lives with the database: the first call creates it, later calls re-upload into the same device
+        buffers (creating a batch costs a few ms of cudaMalloc / stream / event setup).  Do not close it."""
+        b = getattr(self, "_scratch", None)
+        if b is None or b._h is None:
+            b = Batch(self, offsets, s_chrom_id, s_pos, wei)
+            b._scratch = True
+            self._scratch = b
+        else:
+            b.set_row_filter(None)
+            b.upload(offsets, s_chrom_id, s_pos, wei)
+        return b
 
     def intersect(self, s_chrom_id, s_pos, algo=JOIN_AUTO):
         s_chrom_id = as_c(s_chrom_id, np.int32)
@@ -231,6 +249,8 @@ class Batch(object):
         check(load().snpm_batch_upload(self._h, self.n_samples, *[ptr(a) for a in args]))
 
     def close(self):
+        if getattr(self, "_scratch", False):
+            return                                  # owned by the Database
         if getattr(self, "_h", None):
             load().snpm_batch_destroy(self._h)
             self._h = None
