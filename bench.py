@@ -354,34 +354,51 @@ def run_b200_arm(args):
         # memory on the other's copy stream.  Every step uploads its inputs and reads its results back.
         batch2 = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
         pair = [batch, batch2]
+        # weights dictionary-coded once at parse time (uint16 index into the table of distinct f64 values: every integer
+        # PL of a VCF gives one exp(-PL/10)); 6 instead of 24 bytes per marker cross PCIe, the device expands them exactly
+        coded = lib.index_weights(h_wei)
+        if coded is not None:
+            idx_t, h_idx = pinned(coded[0])
+            tab_t, h_tab = pinned(coded[1])
+            keep.extend([idx_t, tab_t])
 
-        def e2e_step(k):
-            cur, nxt = pair[k % 2], pair[(k + 1) % 2]
-            nxt.upload(h_off, h_chr, h_pos, h_wei)          # H2D of step k+1, overlaps the kernels of step k
-            cur.run()
-            if world > 1:
-                sharding.allreduce_batch(cur, dist, dev)
-            cur.epilogue()
-            if rank == 0:
-                cur.fetch(out=out)                          # D2H of step k (waits for it)
-            else:
-                cur.wait()
-        pair[0].upload(h_off, h_chr, h_pos, h_wei)
-        for k in range(args.warmup):
-            e2e_step(k)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.warmup, args.warmup + args.steps):
-            e2e_step(k)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        def e2e_run(indexed):
+            def up(bt):
+                if indexed:
+                    bt.upload_indexed(h_off, h_chr, h_pos, h_idx, h_tab)
+                else:
+                    bt.upload(h_off, h_chr, h_pos, h_wei)
+
+            def e2e_step(k):
+                cur, nxt = pair[k % 2], pair[(k + 1) % 2]
+                up(nxt)                                          # H2D of step k+1, overlaps the kernels of step k
+                cur.run()
+                if world > 1:
+                    sharding.allreduce_batch(cur, dist, dev)
+                cur.epilogue()
+                if rank == 0:
+                    cur.fetch(out=out)                           # D2H of step k (waits for it)
+                else:
+                    cur.wait()
+            up(pair[0])
+            for k in range(args.warmup):
+                e2e_step(k)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.warmup, args.warmup + args.steps):
+                e2e_step(k)
+            barrier()
+            return time.perf_counter() - t0
+        e2e_raw_s = e2e_run(False)
+        e2e_s = e2e_run(True) if coded is not None else e2e_raw_s
+        h2d_bytes = h_off.nbytes + h_chr.nbytes + h_pos.nbytes + (h_idx.nbytes + h_tab.nbytes if coded is not None else h_wei.nbytes)
         clocks = sampler.stop() if rank == 0 else None
 
     m_per_sample = out["m"].astype(np.int64) if rank == 0 else None
-    tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms], dtype=torch.float64, device=dev)
+    tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms, e2e_raw_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, hard_ms = float(tms[0]), float(tms[1]), float(tms[2])
+    dev_ms, e2e_ms, hard_ms, e2e_raw_ms = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
 
     if rank == 0:
         m_total = int(m_per_sample.sum())
@@ -409,8 +426,13 @@ def run_b200_arm(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, S),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(world * (h_off.nbytes + h_chr.nbytes + h_pos.nbytes + h_wei.nbytes)),
-                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values()))},
+                    "h2d_bytes_per_step": int(world * h2d_bytes),
+                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())),
+                    "inputs": "pinned host arrays chrom int32, pos int32, weights as uint16 indices into the table of their distinct "
+                              "f64 values (coded once at parse time; expanded bit-exactly on the device); two batches alternate so "
+                              "that the H2D of step k+1 overlaps the kernels of step k",
+                    "f64_weight_upload": {"value": comps * args.steps / (e2e_raw_ms * 1e-3), "ms_per_step": e2e_raw_ms / args.steps,
+                                          "h2d_bytes_per_step": int(world * (h_off.nbytes + h_chr.nbytes + h_pos.nbytes + h_wei.nbytes))}},
             "gpu_launches": int(total_launches * args.steps),
             "roofline": {"bound": "hbm", "kernel": "k_score_segments", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,

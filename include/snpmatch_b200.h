@@ -118,6 +118,12 @@ int snpm_batch_create(snpm_db *db, int64_t n_samples, const int64_t *offsets,
  * arrays must stay alive until the next wait/fetch of this batch. */
 int snpm_batch_upload(snpm_batch *b, int64_t n_samples, const int64_t *offsets,
                       const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei);
+/* same as snpm_batch_upload with the weights dictionary-coded: wei_idx uint16 [n,3] indexes `table` (f64, n_table <= 65536
+ * entries, the exact host values, e.g. exp(-PL/10) for every integer PL of the file, or {0.0, 1.0} for called genotypes);
+ * the device expands them to the f64 [n,3] weights bit for bit.  6 instead of 24 bytes per marker cross the PCIe bus. */
+int snpm_batch_upload_indexed(snpm_batch *b, int64_t n_samples, const int64_t *offsets,
+                              const int32_t *s_chrom_id, const int32_t *s_pos, const uint16_t *wei_idx,
+                              const double *table, int32_t n_table);
 int snpm_batch_destroy(snpm_batch *b);
 /* optional Genotyper.genotyper(filter_pos_ix=...) (snpmatch.py:211-216): keep only pairs whose
  * GLOBAL database row is in the sorted list (applies to every sample of the batch); n = 0 clears */

@@ -221,7 +221,8 @@ int32_t snpm_db_row_words(const snpm_db *db) { return db ? db->stride : -1; }
 int64_t snpm_db_packed_bytes(const snpm_db *db) { return db ? db->n_rows * int64_t(db->stride) * 8 : -1; }
 
 // ---- batches --------------------------------------------------------------------------------------
-static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const int32_t *chrom, const int32_t *pos, const double *wei) {
+static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const int32_t *chrom, const int32_t *pos, const double *wei,
+                        const uint16_t *wei_idx = nullptr, const double *table = nullptr, int32_t n_table = 0) {
     snpm_db *db = b->db;
     if (S < 1 || !offsets) return fail(SNPM_E_ARG, "batch: need at least one sample and its offsets");
     if (offsets[0] != 0) return fail(SNPM_E_ARG, "batch: offsets[0] must be 0");
@@ -229,7 +230,8 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
         if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "batch: offsets must be non-decreasing");
     const int64_t n = offsets[S];
     if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "batch: %lld markers exceed the 2^31 limit", (long long)n);
-    if (n > 0 && (!chrom || !pos || !wei)) return fail(SNPM_E_ARG, "batch: NULL marker arrays");
+    if (n > 0 && (!chrom || !pos || (!wei && !wei_idx))) return fail(SNPM_E_ARG, "batch: NULL marker arrays");
+    if (wei_idx && (!table || n_table < 1 || n_table > 65536)) return fail(SNPM_E_ARG, "batch: weight table must hold 1..65536 entries");
     b->S = S;
     b->n = n;
     b->h_off.assign(offsets, offsets + S + 1);
@@ -247,7 +249,17 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
     if (n) {
         SNPM_CUDA(cudaMemcpyAsync(b->d_chrom.p, chrom, size_t(n) * 4, cudaMemcpyHostToDevice, st));
         SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
-        SNPM_CUDA(cudaMemcpyAsync(b->d_wei.p, wei, size_t(n) * 24, cudaMemcpyHostToDevice, st));
+        if (wei_idx) {
+            SNPM_TRY(b->d_wei_idx.ensure(size_t(n) * 6));
+            SNPM_TRY(b->d_wei_table.ensure(size_t(n_table) * 8));
+            SNPM_CUDA(cudaMemcpyAsync(b->d_wei_idx.p, wei_idx, size_t(n) * 6, cudaMemcpyHostToDevice, st));
+            SNPM_CUDA(cudaMemcpyAsync(b->d_wei_table.p, table, size_t(n_table) * 8, cudaMemcpyHostToDevice, st));
+            k_expand_weights<<<int(ceil_div64(n * 3, 256)), 256, 0, st>>>(b->d_wei_idx.as<uint16_t>(), b->d_wei_table.as<double>(), n * 3,
+                                                                         b->d_wei.as<double>());
+            SNPM_KERNEL_CHECK();
+        } else {
+            SNPM_CUDA(cudaMemcpyAsync(b->d_wei.p, wei, size_t(n) * 24, cudaMemcpyHostToDevice, st));
+        }
     }
     SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
     b->ran = b->ran_windows = b->epilogue_done = false;
@@ -295,6 +307,14 @@ int snpm_batch_upload(snpm_batch *b, int64_t n_samples, const int64_t *offsets, 
     return batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, wei);
 }
 
+int snpm_batch_upload_indexed(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos,
+                              const uint16_t *wei_idx, const double *table, int32_t n_table) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload_indexed: NULL batch");
+    if (!wei_idx && offsets && n_samples >= 1 && offsets[n_samples] > 0) return fail(SNPM_E_ARG, "snpm_batch_upload_indexed: NULL weight indices");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    return batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, nullptr, wei_idx, table, n_table);
+}
+
 int snpm_batch_destroy(snpm_batch *b) {
     if (!b) return SNPM_OK;
     cudaSetDevice(b->db->device);
@@ -306,7 +326,7 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
                       &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
-                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code};
+                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);

@@ -128,6 +128,7 @@ struct snpm_batch {
     // f1
     snpm::DevBuf d_f1_acc, d_f1_part, d_f1_out;
     snpm::DevBuf d_pair_code;
+    snpm::DevBuf d_wei_idx, d_wei_table;
     // state
     bool ran = false, ran_windows = false, epilogue_done = false;
     int launches = 0;

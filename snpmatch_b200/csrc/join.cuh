@@ -257,6 +257,13 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs(
     }
 }
 
+// dictionary-coded weights -> f64 weights (snpm_batch_upload_indexed)
+__global__ void __launch_bounds__(256) k_expand_weights(const uint16_t *__restrict__ idx, const double *__restrict__ table,
+                                                        int64_t n3, double *__restrict__ wei) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n3) wei[i] = __ldg(table + idx[i]);
+}
+
 // single CTA: matched range of every sample and its number of 1000-row chunks
 //   mstart[s] = prefix[off[s]] (mstart[S] = total);  seg_off = exclusive scan of ceil(m_s / chunk)
 __global__ void __launch_bounds__(1024) k_sample_ranges(const int32_t *__restrict__ prefix, const int64_t *__restrict__ off,

@@ -35,6 +35,17 @@ def weights_are_one_hot(wei):
     return bool(np.all((w == 0.0) | (w == 1.0)) and np.all(w.sum(axis=1) == 1.0))
 
 
+def index_weights(wei):
+    """Dictionary-code a weight matrix: (idx uint16 [n,3], table f64) with table[idx] == wei bit for bit, or None when it
+    holds more than 65536 distinct values.  Weights derived from integer PLs (exp(-PL/10), parsers.py:147-151) and one-hot
+    weights of called genotypes always qualify.  Done once per sample at parse time; it shrinks the per-run H2D copy 4x."""
+    w = np.ascontiguousarray(wei, dtype=np.float64)
+    table, inv = np.unique(w.view(np.uint64).ravel(), return_inverse=True)      # bit patterns: keeps -0.0 / nan payloads apart
+    if len(table) > 65536:
+        return None
+    return inv.astype(np.uint16).reshape(w.shape), table.view(np.float64)
+
+
 class SnpmError(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, "libsnpmatch_b200 error %d: %s" % (code, msg))
@@ -71,6 +82,7 @@ SIGNATURES = {
     "snpm_calculate_likelihoods": (C.c_int, [C.c_int, _p, _p, _i64, C.c_int, _f64, _p, _p, _p]),
     "snpm_batch_create": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p]),
     "snpm_batch_upload": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "snpm_batch_upload_indexed": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
     "snpm_batch_destroy": (C.c_int, [_p]),
     "snpm_batch_set_row_filter": (C.c_int, [_p, _p, _i64]),
     "snpm_batch_run": (C.c_int, [_p, C.c_int, C.c_int]),
@@ -247,6 +259,20 @@ class Batch(object):
         """Replace the batch's samples, reusing its device buffers (queued on the stream)."""
         args = self._prep(offsets, s_chrom_id, s_pos, wei)
         check(load().snpm_batch_upload(self._h, self.n_samples, *[ptr(a) for a in args]))
+
+    def upload_indexed(self, offsets, s_chrom_id, s_pos, wei_idx, table):
+        """upload() with dictionary-coded weights: wei_idx uint16 [n,3] into `table` (f64).  See index_weights()."""
+        offsets = as_c(offsets, np.int64)
+        s_chrom_id = as_c(s_chrom_id, np.int32)
+        s_pos = as_c(s_pos, np.int32)
+        wei_idx = as_c(wei_idx, np.uint16).reshape(-1, 3)
+        table = as_c(table, np.float64)
+        assert len(s_chrom_id) == len(s_pos) == len(wei_idx) == int(offsets[-1]) and 1 <= len(table) <= 65536
+        self.n_samples = len(offsets) - 1
+        self.offsets = offsets
+        self._keep = (offsets, s_chrom_id, s_pos, wei_idx, table)
+        check(load().snpm_batch_upload_indexed(self._h, self.n_samples, ptr(offsets), ptr(s_chrom_id), ptr(s_pos), ptr(wei_idx),
+                                               ptr(table), len(table)))
 
     def close(self):
         if getattr(self, "_scratch", False):

@@ -351,6 +351,15 @@ def test_batch_of_samples_equals_single_runs(lib):
         np.testing.assert_allclose(r["LR"][i], lr, rtol=RTOL, equal_nan=True)
         if len(db_idx) > 500:
             assert int(np.nanargmin(r["L"][i])) == 3 + 11 * i
+    # dictionary-coded weights expand to the same bits
+    idx, table = lib.index_weights(np.concatenate([s["wei"] for s in samples]))
+    assert len(table) < 2000
+    b.upload_indexed(offs, np.concatenate([s["chr_ix"] for s in samples]), np.concatenate([s["pos"] for s in samples]), idx, table)
+    b.run()
+    b.epilogue()
+    r_idx = b.fetch()
+    for k in ("score", "matches", "ninfo", "m", "L", "LR", "prob"):
+        assert np.array_equal(r_idx[k], r[k], equal_nan=True), k
     # re-upload into the same batch object
     s = samples[0]
     b.upload([0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei_hard"])
