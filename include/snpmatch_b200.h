@@ -71,6 +71,9 @@ int snpm_db_fill_synthetic(snpm_db *db, uint64_t seed);
 /* read back (tests / HDF5Genotype.snps[rows,:] equivalent, snpmatch.py:222): local row indices */
 int snpm_db_read_rows_int8(snpm_db *db, const int64_t *rows, int64_t k, int8_t *out);
 int snpm_db_read_packed(snpm_db *db, int64_t row0, int64_t n, uint64_t *out);
+/* --refine support: flags[r] = 1 when the selected accession columns carry at least two different called genotypes on
+ * row r — Genotype.identify_segregating_snps (snp_genotype.py:188-211, segregting_snps :378-383).  flags uint8[n_rows]. */
+int snpm_db_segregating_rows(snpm_db *db, const int32_t *acc_idx, int32_t n_sel, uint8_t *flags);
 int64_t snpm_db_n_rows(const snpm_db *db);
 int32_t snpm_db_n_acc(const snpm_db *db);
 int32_t snpm_db_row_words(const snpm_db *db);

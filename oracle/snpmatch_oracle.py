@@ -365,6 +365,19 @@ def f1_pair_scores(db_snps, common, s_wei, top_accs):
     return pairs, np.array(scores, dtype=np.float64), np.array(ninfos, dtype=np.int64)
 
 
+def segregating_rows(db_snps, accs_ix):
+    """snp_genotype.py:188-211 + segregting_snps (:378-383): after masking missing calls (< 0 -> nan) and sorting each row,
+    t_sum = 1 + #adjacent equal pairs, t_r_sum = #called; rows with t_sum / t_r_sum < 1 and t_r_sum != 0."""
+    t = np.array(np.asarray(db_snps)[:, np.asarray(accs_ix)], dtype=float)
+    t[t < 0] = np.nan
+    t = np.sort(t, axis=1)
+    t_r_sum = np.sum(~np.isnan(t), axis=1)
+    t_sum = np.nansum(t[:, 1:] == t[:, :-1], axis=1) + 1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        div = np.where(t_r_sum != 0, t_sum / np.maximum(t_r_sum, 1), np.inf)
+    return np.setdiff1d(np.flatnonzero(div < 1), np.flatnonzero(t_r_sum == 0))
+
+
 # --------------------------------------------------------------------------
 # data-format helper shared by the tests (not reference behaviour)
 # --------------------------------------------------------------------------

@@ -270,18 +270,14 @@ class Genotyper(object):
 
 
 def identify_segregating_snps(g, accs_ix):
-    """Rows where the given accessions are not all identical (snp_genotype.py:188-211,378-383):
-    a row segregates when its called (>= 0... the reference compares raw codes) values differ.
-    Reads the rows back from the device in blocks; used by --refine only."""
-    accs_ix = np.asarray(accs_ix, dtype=np.int64)
-    n = g.g.num_snps
-    keep = []
-    step = max(1, (64 << 20) // max(g.g.num_accessions, 1))
-    for r in range(0, n, step):
-        block = g.g.snps[r:min(n, r + step), :][:, accs_ix]
-        seg = np.flatnonzero(block.min(axis=1) != block.max(axis=1))
-        keep.append(seg + r)
-    return np.concatenate(keep) if keep else np.zeros(0, dtype=np.int64)
+    """Rows where the given accessions carry more than one distinct called genotype (snp_genotype.py:188-211 with
+    segregting_snps :378-383).  One scan of the resident panel on the GPU.  Like the reference, returns None when more
+    than half of the accessions are selected."""
+    assert type(accs_ix) is np.ndarray, "provide an np array for list of indices to be considered"
+    assert len(accs_ix) > 1, "polymorphism happens in more than 1 line"
+    if len(accs_ix) > (len(g.accessions) / 2):
+        return None
+    return g.db.segregating_rows(accs_ix) + g.db.row0_global
 
 
 def getHeterozygosity(snpGT, outFile='default'):

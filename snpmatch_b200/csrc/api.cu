@@ -215,6 +215,35 @@ int snpm_db_read_packed(snpm_db *db, int64_t row0, int64_t n, uint64_t *out) {
     return SNPM_OK;
 }
 
+int snpm_db_segregating_rows(snpm_db *db, const int32_t *acc_idx, int32_t n_sel, uint8_t *flags) {
+    if (!db || n_sel < 0 || (n_sel > 0 && !acc_idx) || (db->n_rows > 0 && !flags)) return fail(SNPM_E_ARG, "snpm_db_segregating_rows: bad arguments");
+    std::vector<uint32_t> sel(size_t(db->stride), 0u);
+    for (int32_t i = 0; i < n_sel; ++i) {
+        if (acc_idx[i] < 0 || acc_idx[i] >= db->n_acc) return fail(SNPM_E_ARG, "snpm_db_segregating_rows: accession index %d out of range", acc_idx[i]);
+        sel[size_t(acc_idx[i] >> 5)] |= 1u << (acc_idx[i] & 31);
+    }
+    if (db->n_rows == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    DevBuf d_sel, d_flags;
+    SNPM_TRY(d_sel.ensure(size_t(db->stride) * 4));
+    int rc = d_flags.ensure(size_t(db->n_rows));
+    cudaError_t e = cudaSuccess;
+    if (rc == SNPM_OK) {
+        e = cudaMemcpyAsync(d_sel.p, sel.data(), size_t(db->stride) * 4, cudaMemcpyHostToDevice, db->stream);
+        if (e == cudaSuccess) {
+            k_segregating_rows<<<grid_for(db->n_rows * 32, 256, db->n_sm, 32), 256, 0, db->stream>>>(db->d_packed, db->n_rows, db->stride,
+                                                                                                  d_sel.as<uint32_t>(), d_flags.as<uint8_t>());
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(flags, d_flags.p, size_t(db->n_rows), cudaMemcpyDeviceToHost, db->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+    }
+    d_sel.release();
+    d_flags.release();
+    if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_db_segregating_rows: %s", cudaGetErrorString(e));
+    return rc;
+}
+
 int64_t snpm_db_n_rows(const snpm_db *db) { return db ? db->n_rows : -1; }
 int32_t snpm_db_n_acc(const snpm_db *db) { return db ? db->n_acc : -1; }
 int32_t snpm_db_row_words(const snpm_db *db) { return db ? db->stride : -1; }
@@ -367,10 +396,9 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
     SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_uploaded, 0));       // the samples are on the device
     SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
-    // auto = per-marker binary search: measured on B200 it beats the merge-path kernel even for a sample that carries
-    // every panel row (0.47 ms vs 4.3 ms at 10.7 M markers; profiles/r1_configs.jsonl) — the top of the search tree is
-    // cache resident.  Merge-path stays selectable (algo 2).
-    if (algo == 0) algo = 1;
+    // auto: per-marker binary search for low-coverage samples (n << N: a tile of markers spans a long panel slice), merge-path
+    // once a sample carries more than an eighth of the panel rows (measured at m = N = 10.7 M: 0.40 ms vs 0.47 ms)
+    if (algo == 0) algo = (n / S) * 8 >= db->n_rows ? 2 : 1;
     const int64_t *filter = b->n_filter ? b->d_filter.as<int64_t>() : nullptr;
     if (n_tiles > 0) {
         if (algo == 2)

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) k_join_mergepath(
     __shared__ int32_t s_chr[MP_TILE];
     __shared__ int32_t s_db[MP_DB_CHUNK];
     __shared__ int32_t s_cnt;
+    __shared__ int32_t s_next;
+    __shared__ uint8_t s_brk[MP_TILE];          // marker t starts a new run (chromosome change or order restart)
     const int64_t base = int64_t(blockIdx.x) * MP_TILE;
     const int tile_n = int((n - base) < int64_t(MP_TILE) ? (n - base) : int64_t(MP_TILE));
     if (threadIdx.x == 0) s_cnt = 0;
@@ -109,14 +111,21 @@ __global__ void __launch_bounds__(256) k_join_mergepath(
         s_chr[t] = chrom[base + t];
     }
     __syncthreads();
+    for (int t = threadIdx.x; t < tile_n; t += blockDim.x)
+        s_brk[t] = t == 0 || s_chr[t] != s_chr[t - 1] || s_pos[t] <= s_pos[t - 1];
     int local_cnt = 0;
-    // walk the tile chromosome run by chromosome run (a tile usually holds one run)
+    // walk the tile run by run: a run = markers of one chromosome in ascending order (a tile usually holds one run;
+    // a chromosome change or the start of the next sample begins another)
     int run_start = 0;
     while (run_start < tile_n) {
         const int32_t c = s_chr[run_start];
-        int run_end = run_start + 1;
-        // every thread computes the same run bounds; also stop where the order restarts (next sample)
-        while (run_end < tile_n && s_chr[run_end] == c && s_pos[run_end] > s_pos[run_end - 1]) ++run_end;
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = tile_n;
+        __syncthreads();
+        for (int t = threadIdx.x; t < tile_n; t += blockDim.x)
+            if (s_brk[t] && t > run_start) atomicMin(&s_next, t);
+        __syncthreads();
+        const int run_end = s_next;
         if (c < 0 || c >= n_chr) {
             for (int t = run_start + threadIdx.x; t < run_end; t += blockDim.x) match_row[base + t] = -1;
             run_start = run_end;

@@ -40,6 +40,30 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const uint64_t *__restrict_
     }
 }
 
+// Rows on which the selected accessions carry at least two different called genotypes — the segregating SNPs of
+// Genotype.identify_segregating_snps (snp_genotype.py:188-211 with segregting_snps :378-383: after masking missing
+// calls, t_sum / t_r_sum < 1  <=>  more than one distinct called value).  One warp per row: lanes sweep the row's words,
+// AND them with the accession-selection mask, and OR-reduce the three class planes.
+__global__ void __launch_bounds__(256) k_segregating_rows(const uint64_t *__restrict__ packed, int64_t n_rows, int32_t stride,
+                                                          const uint32_t *__restrict__ sel, uint8_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp_global; row < n_rows; row += n_warps) {
+        uint32_t has_ref = 0u, has_alt = 0u, has_het = 0u;
+        for (int w = lane; w < stride; w += 32) {
+            const uint64_t v = __ldg(packed + row * stride + w);
+            const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32), m = sel[w];
+            has_ref |= ~(lo | hi) & m;
+            has_alt |= lo & ~hi & m;
+            has_het |= hi & ~lo & m;
+        }
+        const int classes = (__any_sync(0xffffffffu, has_ref != 0u) ? 1 : 0) + (__any_sync(0xffffffffu, has_alt != 0u) ? 1 : 0) +
+                            (__any_sync(0xffffffffu, has_het != 0u) ? 1 : 0);
+        if (lane == 0) flags[row] = classes > 1;
+    }
+}
+
 // ---- synthetic panel: the integer hash of snpmatch_b200/synth.py --------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t key, uint64_t seed) {
     uint64_t z = key + (seed + 1ull) * 0x9E3779B97F4A7C15ull;

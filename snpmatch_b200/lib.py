@@ -72,6 +72,7 @@ SIGNATURES = {
     "snpm_db_fill_synthetic": (C.c_int, [_p, C.c_uint64]),
     "snpm_db_read_rows_int8": (C.c_int, [_p, _p, _i64, _p]),
     "snpm_db_read_packed": (C.c_int, [_p, _i64, _i64, _p]),
+    "snpm_db_segregating_rows": (C.c_int, [_p, _p, _i32, _p]),
     "snpm_db_n_rows": (_i64, [_p]),
     "snpm_db_n_acc": (_i32, [_p]),
     "snpm_db_row_words": (_i32, [_p]),
@@ -205,6 +206,13 @@ class Database(object):
         out = np.empty((n, self.row_words), dtype=np.uint64)
         check(load().snpm_db_read_packed(self._h, row0, n, ptr(out)))
         return out
+
+    def segregating_rows(self, acc_idx):
+        """Local row indices on which the given accessions carry >= 2 different called genotypes (full-panel scan on the GPU)."""
+        acc_idx = as_c(acc_idx, np.int32)
+        flags = np.empty(max(self.n_rows, 1), dtype=np.uint8)
+        check(load().snpm_db_segregating_rows(self._h, ptr(acc_idx), len(acc_idx), ptr(flags)))
+        return np.flatnonzero(flags[:self.n_rows])
 
     def set_stream(self, cuda_stream):
         check(load().snpm_db_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))

@@ -519,3 +519,30 @@ def test_cross_full_panel_properties(lib):
     assert len(f_score) == 45 and np.all(f_ninfo <= int(tot["m"][0])) and np.all(f_score <= f_ninfo)
     b.close()
     db.close()
+
+
+def test_segregating_rows_and_refine(lib, small_geno, small_panel, sample_inbred, tmp_path):
+    from snpmatch_b200.core import parsers, snpmatch
+    p = small_panel
+    for sel in (np.array([7, 9]), np.array([0, 3, 11, 17, 21, 30, 39]), np.array([11, 12])):
+        got = snpmatch.identify_segregating_snps(small_geno, sel)
+        assert np.array_equal(got, orc.segregating_rows(p["snps"], sel))
+    assert snpmatch.identify_segregating_snps(small_geno, np.arange(25)) is None
+    # --refine end to end: accession 9 is a near-copy of accession 7 in the golden panel
+    s = sample_inbred
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei"], s["dp"])
+    out = str(tmp_path / "refine")
+    gt = snpmatch.Genotyper(inp, small_geno, out, run_genotyper=False)
+    gt.filter_tophits()
+    assert os.path.exists(out + ".scores.txt")
+    with np.errstate(invalid="ignore"):
+        top = np.flatnonzero(gt.result.lrts < snpmatch.lr_thres)
+    if 1 < len(top) <= 20:
+        seg = orc.segregating_rows(p["snps"], top)
+        ref = orc.genotyper(p["snps"], p["chrs"], p["chr_regions"], p["positions"], s["chrs"], s["pos"], s["wei"], filter_pos_ix=seg)
+        with np.errstate(invalid="ignore"):
+            keep = np.setdiff1d(np.arange(40), np.flatnonzero(gt.result.lrts >= snpmatch.lr_thres))   # nan ratios stay, as in the reference
+        assert os.path.exists(out + ".refined.scores.txt")
+        assert np.array_equal(gt.result_fine.scores, ref.scores[keep]) and np.array_equal(gt.result_fine.ninfo, ref.ninfo[keep])
+        assert gt.result_fine.num_snps == ref.num_snps
