@@ -6,6 +6,7 @@
 #include "windows.cuh"
 #include "f1.cuh"
 #include "hardcall.cuh"
+#include "gemm_onehot.cuh"
 
 namespace snpm {
 thread_local std::string g_last_error;
@@ -777,6 +778,78 @@ int snpm_calculate_likelihoods(int device, const double *scores, const double *n
     d_out.release();
     if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_calculate_likelihoods: %s", cudaGetErrorString(e));
     return rc;
+}
+
+// ---- A9 ------------------------------------------------------------------------------------------------
+int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, const uint8_t *codes, int64_t S, int skip_db_hets,
+                            int64_t *score, int64_t *ninfo, double *prob, double *L, double *LR, float *ms_gemm) {
+    if (!db || K < 0 || S < 1 || S > (1 << 22) || (K > 0 && (!panel_rows || !codes)) || !score || !ninfo)
+        return fail(SNPM_E_ARG, "snpm_score_shared_panel: bad arguments");
+    if (K >= (int64_t(1) << 29)) return fail(SNPM_E_ARG, "snpm_score_shared_panel: int32 accumulators hold at most 2^29 markers");
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const int64_t Kpad = std::max<int64_t>(OG_ROWS, ceil_div64(K, OG_ROWS) * OG_ROWS);
+    const int32_t A = db->n_acc, ld_out = int32_t(ceil_div64(A, OG_BN) * OG_BN);
+    std::vector<int32_t> rows(size_t(Kpad), -1);
+    for (int64_t k = 0; k < K; ++k) {
+        const int64_t r = panel_rows[k] - db->row0_global;
+        if (r < 0 || r >= db->n_rows) return fail(SNPM_E_ARG, "snpm_score_shared_panel: panel row %lld is not on this device", (long long)panel_rows[k]);
+        rows[size_t(k)] = int32_t(r);
+    }
+    DevBuf d_rows, d_codes, d_os, d_on, d_red, d_m, d_n64, d_p, d_l, d_lr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = SNPM_OK;
+    auto cleanup = [&]() {
+        for (DevBuf *d : {&d_rows, &d_codes, &d_os, &d_on, &d_red, &d_m, &d_n64, &d_p, &d_l, &d_lr}) d->release();
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define SP_TRY(x) do { rc = (x); if (rc != SNPM_OK) { cleanup(); return rc; } } while (0)
+#define SP_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(SNPM_E_CUDA, "snpm_score_shared_panel: %s -> %s", #x, cudaGetErrorString(e_)); } } while (0)
+    SP_TRY(d_rows.ensure(size_t(Kpad) * 4));
+    SP_TRY(d_codes.ensure(size_t(S) * Kpad));
+    SP_TRY(d_os.ensure(size_t(S) * ld_out * 4));
+    SP_TRY(d_on.ensure(size_t(S) * ld_out * 4));
+    SP_TRY(d_red.ensure(size_t(S) * (2 * size_t(A) + 2) * 8));
+    SP_TRY(d_m.ensure(size_t(S) * A * 8));
+    SP_TRY(d_n64.ensure(size_t(S) * A * 8));
+    SP_TRY(d_p.ensure(size_t(S) * A * 8));
+    SP_TRY(d_l.ensure(size_t(S) * A * 8));
+    SP_TRY(d_lr.ensure(size_t(S) * A * 8));
+    SP_CUDA(cudaEventCreate(&e0));
+    SP_CUDA(cudaEventCreate(&e1));
+    SP_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), size_t(Kpad) * 4, cudaMemcpyHostToDevice, st));
+    SP_CUDA(cudaMemsetAsync(d_codes.p, 3, size_t(S) * Kpad, st));                 // padding markers are absent
+    if (K > 0) SP_CUDA(cudaMemcpy2DAsync(d_codes.p, size_t(Kpad), codes, size_t(K), size_t(K), size_t(S), cudaMemcpyHostToDevice, st));
+    OneHotGemmArgs g = {};
+    g.packed = db->d_packed; g.stride = db->stride; g.rows = d_rows.as<int32_t>(); g.codes = d_codes.as<uint8_t>();
+    g.S = int32_t(S); g.Kpad = int32_t(Kpad); g.n_acc = A; g.skip_hets = skip_db_hets ? 1 : 0;
+    g.out_score = d_os.as<int32_t>(); g.out_ninfo = d_on.as<int32_t>(); g.ld_out = ld_out;
+    const size_t smem = size_t(OG_STAGES) * 2 * OG_TILE_BYTES + 1024;
+    static bool og_attr = false;
+    if (!og_attr) { SP_CUDA(cudaFuncSetAttribute(k_onehot_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); og_attr = true; }
+    dim3 grid(unsigned(ceil_div64(S, 64)), unsigned(ld_out / OG_BN));
+    SP_CUDA(cudaEventRecord(e0, st));
+    k_onehot_gemm<<<grid, OG_THREADS, smem, st>>>(g);
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(cudaEventRecord(e1, st));
+    dim3 tgrid((A + 255) / 256, unsigned(S));
+    k_onehot_totals<<<tgrid, 256, 0, st>>>(g.out_score, g.out_ninfo, ld_out, A, int32_t(K), d_red.as<double>());
+    SP_CUDA(cudaGetLastError());
+    k_epilogue<<<unsigned(S), 1024, 0, st>>>(d_red.as<double>(), A, 1, 0, 0.0, d_m.as<int64_t>(), d_n64.as<int64_t>(), d_p.as<double>(),
+                                             d_l.as<double>(), d_lr.as<double>());
+    SP_CUDA(cudaGetLastError());
+    SP_CUDA(cudaMemcpyAsync(score, d_m.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    SP_CUDA(cudaMemcpyAsync(ninfo, d_n64.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    if (prob) SP_CUDA(cudaMemcpyAsync(prob, d_p.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    if (L) SP_CUDA(cudaMemcpyAsync(L, d_l.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    if (LR) SP_CUDA(cudaMemcpyAsync(LR, d_lr.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    SP_CUDA(cudaStreamSynchronize(st));
+    if (ms_gemm) { *ms_gemm = 0.f; cudaEventElapsedTime(ms_gemm, e0, e1); }
+    cleanup();
+#undef SP_TRY
+#undef SP_CUDA
+    return SNPM_OK;
 }
 
 // ---- A5 + A6 ----------------------------------------------------------------------------------------

@@ -97,6 +97,7 @@ SIGNATURES = {
     "snpm_batch_run_windows": (C.c_int, [_p, C.c_int, _i64, _p, _p, _i32, _p, _i64, _f64]),
     "snpm_batch_fetch_windows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "snpm_batch_f1_pairs": (C.c_int, [_p, _p, _i32, _p, _p]),
+    "snpm_score_shared_panel": (C.c_int, [_p, _p, _i64, _p, _i64, C.c_int, _p, _p, _p, _p, _p, _p]),
 }
 
 
@@ -213,6 +214,23 @@ class Database(object):
         flags = np.empty(max(self.n_rows, 1), dtype=np.uint8)
         check(load().snpm_db_segregating_rows(self._h, ptr(acc_idx), len(acc_idx), ptr(flags)))
         return np.flatnonzero(flags[:self.n_rows])
+
+    def score_shared_panel(self, panel_rows, codes, skip_db_hets=False, likelihoods=True):
+        """Batched tensor-core scoring (A9): codes uint8 [S,K] (0 ref, 1 alt, 2 het, 3 absent) of S called-genotype samples on
+        the K shared markers `panel_rows` (global rows).  Returns dict(matches, ninfo[, prob, L, LR], gemm_ms)."""
+        panel_rows = as_c(panel_rows, np.int64)
+        codes = as_c(codes, np.uint8)
+        S, K = codes.shape
+        assert K == len(panel_rows)
+        r = {"matches": np.empty((S, self.n_acc), np.int64), "ninfo": np.empty((S, self.n_acc), np.int64)}
+        if likelihoods:
+            for k in ("prob", "L", "LR"):
+                r[k] = np.empty((S, self.n_acc), np.float64)
+        ms = C.c_float(0)
+        check(load().snpm_score_shared_panel(self._h, ptr(panel_rows), K, ptr(codes), S, int(bool(skip_db_hets)), ptr(r["matches"]),
+                                             ptr(r["ninfo"]), ptr(r.get("prob")), ptr(r.get("L")), ptr(r.get("LR")), C.byref(ms)))
+        r["gemm_ms"] = ms.value
+        return r
 
     def set_stream(self, cuda_stream):
         check(load().snpm_db_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))

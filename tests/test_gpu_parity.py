@@ -546,3 +546,28 @@ def test_segregating_rows_and_refine(lib, small_geno, small_panel, sample_inbred
         assert os.path.exists(out + ".refined.scores.txt")
         assert np.array_equal(gt.result_fine.scores, ref.scores[keep]) and np.array_equal(gt.result_fine.ninfo, ref.ninfo[keep])
         assert gt.result_fine.num_snps == ref.num_snps
+
+
+@pytest.mark.parametrize("n_acc,S,K,skip", [(40, 70, 300, False), (1135, 130, 1000, False), (300, 64, 33, True), (129, 5, 1, False)])
+def test_shared_panel_tensor_core_batch(lib, n_acc, S, K, skip):
+    """A9: one-hot int8 GEMM on tcgen05 vs the oracle's matchGTsAccs per sample (integers, exact)."""
+    n_rows = 20000
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    rng = np.random.default_rng(S * 1000 + K)
+    rows = np.sort(rng.choice(n_rows, size=K, replace=False))
+    codes = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(S, K), p=[0.55, 0.3, 0.05, 0.1])
+    r = db.score_shared_panel(rows, codes, skip_db_hets=skip)
+    panel = synth.panel_codes(synth.SEED_PANEL, rows, n_acc)
+    for s in range(S):
+        have = np.flatnonzero(codes[s] < 3)
+        wei = synth.hard_weights(codes[s][have].astype(np.int8))
+        sc, ni = orc.match_gts_accs(wei, panel[have], skip)
+        assert np.array_equal(r["matches"][s], sc.astype(np.int64)), "sample %d" % s
+        assert np.array_equal(r["ninfo"][s], ni), "sample %d" % s
+        lik, lr = orc.calculate_likelihoods(sc.astype(np.int64), ni)
+        np.testing.assert_allclose(r["L"][s], lik, rtol=RTOL, equal_nan=True)
+        np.testing.assert_allclose(r["LR"][s], lr, rtol=RTOL, equal_nan=True)
+    assert r["gemm_ms"] > 0
+    db.close()
