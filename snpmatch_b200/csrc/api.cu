@@ -796,18 +796,22 @@ int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, c
         if (r < 0 || r >= db->n_rows) return fail(SNPM_E_ARG, "snpm_score_shared_panel: panel row %lld is not on this device", (long long)panel_rows[k]);
         rows[size_t(k)] = int32_t(r);
     }
-    DevBuf d_rows, d_codes, d_os, d_on, d_red, d_m, d_n64, d_p, d_l, d_lr;
+    DevBuf d_rows, d_codes, d_os, d_on, d_red, d_m, d_n64, d_p, d_l, d_lr, d_at, d_bt;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = SNPM_OK;
     auto cleanup = [&]() {
-        for (DevBuf *d : {&d_rows, &d_codes, &d_os, &d_on, &d_red, &d_m, &d_n64, &d_p, &d_l, &d_lr}) d->release();
+        for (DevBuf *d : {&d_rows, &d_codes, &d_os, &d_on, &d_red, &d_m, &d_n64, &d_p, &d_l, &d_lr, &d_at, &d_bt}) d->release();
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
 #define SP_TRY(x) do { rc = (x); if (rc != SNPM_OK) { cleanup(); return rc; } } while (0)
 #define SP_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(SNPM_E_CUDA, "snpm_score_shared_panel: %s -> %s", #x, cudaGetErrorString(e_)); } } while (0)
+    const int n_kb = int(Kpad / OG_ROWS);
+    const int m_blocks = int(ceil_div64(S, 64)), n_blocks = ld_out / OG_BN;
     SP_TRY(d_rows.ensure(size_t(Kpad) * 4));
     SP_TRY(d_codes.ensure(size_t(S) * Kpad));
+    SP_TRY(d_at.ensure(size_t(m_blocks) * n_kb * OG_A_TILE));
+    SP_TRY(d_bt.ensure(size_t(n_blocks) * n_kb * OG_B_TILE));
     SP_TRY(d_os.ensure(size_t(S) * ld_out * 4));
     SP_TRY(d_on.ensure(size_t(S) * ld_out * 4));
     SP_TRY(d_red.ensure(size_t(S) * (2 * size_t(A) + 2) * 8));
@@ -821,14 +825,19 @@ int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, c
     SP_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), size_t(Kpad) * 4, cudaMemcpyHostToDevice, st));
     SP_CUDA(cudaMemsetAsync(d_codes.p, 3, size_t(S) * Kpad, st));                 // padding markers are absent
     if (K > 0) SP_CUDA(cudaMemcpy2DAsync(d_codes.p, size_t(Kpad), codes, size_t(K), size_t(K), size_t(S), cudaMemcpyHostToDevice, st));
+    // one-hot operands, tile by tile in their shared-memory image
+    k_onehot_expand_samples<<<dim3(n_kb, m_blocks), 128, 0, st>>>(d_codes.as<uint8_t>(), int32_t(S), int32_t(Kpad), d_at.as<unsigned char>());
+    SP_CUDA(cudaGetLastError());
+    k_onehot_expand_panel<<<dim3(n_kb, n_blocks), 256, 0, st>>>(db->d_packed, db->stride, d_rows.as<int32_t>(), int32_t(Kpad), skip_db_hets ? 1 : 0,
+                                                                d_bt.as<unsigned char>());
+    SP_CUDA(cudaGetLastError());
     OneHotGemmArgs g = {};
-    g.packed = db->d_packed; g.stride = db->stride; g.rows = d_rows.as<int32_t>(); g.codes = d_codes.as<uint8_t>();
-    g.S = int32_t(S); g.Kpad = int32_t(Kpad); g.n_acc = A; g.skip_hets = skip_db_hets ? 1 : 0;
+    g.a_tiled = d_at.as<unsigned char>(); g.b_tiled = d_bt.as<unsigned char>(); g.n_kb = n_kb; g.S = int32_t(S);
     g.out_score = d_os.as<int32_t>(); g.out_ninfo = d_on.as<int32_t>(); g.ld_out = ld_out;
-    const size_t smem = size_t(OG_STAGES) * 2 * OG_TILE_BYTES + 1024;
+    const size_t smem = size_t(OG_STAGES) * (OG_A_TILE + OG_B_TILE) + 1024;
     static bool og_attr = false;
     if (!og_attr) { SP_CUDA(cudaFuncSetAttribute(k_onehot_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); og_attr = true; }
-    dim3 grid(unsigned(ceil_div64(S, 64)), unsigned(ld_out / OG_BN));
+    dim3 grid((unsigned)m_blocks, (unsigned)n_blocks);
     SP_CUDA(cudaEventRecord(e0, st));
     k_onehot_gemm<<<grid, OG_THREADS, smem, st>>>(g);
     SP_CUDA(cudaGetLastError());

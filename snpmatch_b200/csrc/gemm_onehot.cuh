@@ -8,10 +8,12 @@
 // Both are one GEMM  C[2*64 rows, 128 accessions] += A_op[128, 4K] * B_op[128, 4K]^T  per CTA tile: every panel row k
 // contributes four int8 K-slots (slot c = one-hot of the code, slot 3 unused); the first 64 rows of a tile are the score
 // operands of 64 samples (one-hot of the sample's call), the last 64 their ninfo operands (1 in every class slot when the
-// sample has the marker).  Neither operand ever exists in HBM: four loader warps expand the 2-bit panel words and the
-// samples' code bytes straight into shared memory in the canonical no-swizzle K-major UMMA layout (core matrix = 8 rows x
-// 16 bytes, contiguous), fence them into the async proxy, and one elected thread of the MMA warp issues four
-// tcgen05.mma (M=128, N=128, K=32) per 32-row block.  int32 accumulation is exact.
+// sample has the marker).  Two expansion kernels write the one-hot operands once, tile by tile, in the exact shared-memory
+// image of the canonical no-swizzle K-major UMMA layout; the GEMM kernel is then a pure pipeline: a producer thread fills a
+// 4-stage ring with two 1-D TMA bulk copies per k-block, one elected thread issues four tcgen05.mma (M=128, N=256, K=32) per
+// block into a 128 x 256 int32 accumulator in TMEM, four epilogue warps read it back with tcgen05.ld.  int32 accumulation is
+// exact.  (A first version expanded the operands inside the GEMM kernel; the expansion ALU work and its dependent panel
+// loads ran 100x slower than the tensor pipe — profiles/r1_configs.jsonl keeps that measurement.)
 #pragma once
 #include "common.cuh"
 #include "score.cuh"
@@ -19,27 +21,87 @@
 namespace snpm {
 
 constexpr int OG_STAGES = 4;
-constexpr int OG_BM = 128, OG_BN = 128;
+constexpr int OG_BM = 128, OG_BN = 256;
 constexpr int OG_ROWS = 32;                     // panel rows per k-block = 128 K-bytes = 4 MMAs of K=32
-constexpr int OG_TILE_BYTES = 128 * 128;        // one operand tile
-constexpr int OG_THREADS = 160;                 // warps 0-3: loaders + epilogue, warp 4: TMEM owner + MMA issuer
+constexpr int OG_A_TILE = OG_BM * 128;          // bytes of one A tile (128 operand rows x 128 K-bytes)
+constexpr int OG_B_TILE = OG_BN * 128;
+constexpr int OG_THREADS = 192;                 // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, warps 2-5: epilogue
+
+// Operand tiles live in HBM already in the shared-memory image the tensor core reads: the canonical no-swizzle K-major UMMA
+// layout — core matrix = 8 operand rows x 16 K-bytes, contiguous (128 B); the core matrices of one 16-byte K chunk follow each
+// other (stride 128 B = SBO), the 8 K chunks of a k-block are R*16 bytes apart (LBO; R = rows of the tile).  A tile therefore
+// reaches shared memory with ONE 1-D TMA bulk copy, no tensor map and no swizzle.
+__host__ __device__ __forceinline__ uint32_t og_tile_offset(int row, int chunk, int tile_rows) {
+    return uint32_t(chunk) * uint32_t(tile_rows) * 16u + uint32_t(row >> 3) * 128u + uint32_t(row & 7) * 16u;
+}
+
+// A operand: tile (m_blk, kb) = 64 samples x 32 markers; rows 0-63 one-hot of the sample's call (score), rows 64-127 ones in
+// every class slot when the sample has the marker (ninfo).  K slot = 4 * marker + class; slot 3 stays zero.
+__global__ void __launch_bounds__(128) k_onehot_expand_samples(const uint8_t *__restrict__ codes, int32_t S, int32_t Kpad,
+                                                               unsigned char *__restrict__ a_tiled) {
+    const int n_kb = Kpad / OG_ROWS;
+    const int kb = blockIdx.x, m_blk = blockIdx.y, t = threadIdx.x;
+    const int sample = m_blk * 64 + (t & 63);
+    const bool ninfo_row = t >= 64;
+    unsigned char *tile = a_tiled + (size_t(m_blk) * n_kb + kb) * OG_A_TILE;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t cw = sample < S ? *reinterpret_cast<const uint32_t *>(codes + size_t(sample) * Kpad + kb * OG_ROWS + 4 * c) : 0x03030303u;
+        uint4 v;
+        uint32_t *pv = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t code = (cw >> (8 * q)) & 0xFFu;
+            pv[q] = code < 3u ? (ninfo_row ? 0x00010101u : (1u << (8 * code))) : 0u;
+        }
+        *reinterpret_cast<uint4 *>(tile + og_tile_offset(t, c, OG_BM)) = v;
+    }
+}
+
+// B operand: tile (n_blk, kb) = 256 accessions x 32 panel rows, one-hot of the database call (missing, masked hets and padding
+// rows/accessions are all-zero)
+__global__ void __launch_bounds__(256) k_onehot_expand_panel(const uint64_t *__restrict__ packed, int32_t stride, const int32_t *__restrict__ rows,
+                                                             int32_t Kpad, int32_t skip_hets, unsigned char *__restrict__ b_tiled) {
+    const int n_kb = Kpad / OG_ROWS;
+    const int kb = blockIdx.x, n_blk = blockIdx.y, t = threadIdx.x;
+    const int acc = n_blk * OG_BN + t;
+    const bool acc_ok = acc < stride * 32;
+    const uint64_t *pcol = packed + (acc_ok ? (acc >> 5) : 0);
+    const int bit = acc & 31;
+    unsigned char *tile = b_tiled + (size_t(n_blk) * n_kb + kb) * OG_B_TILE;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 v;
+        uint32_t *pv = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int32_t r = rows[kb * OG_ROWS + 4 * c + q];
+            uint32_t w = 0u;
+            if (r >= 0 && acc_ok) {
+                const uint64_t x = __ldg(pcol + int64_t(r) * stride);
+                const uint32_t code = (uint32_t(x) >> bit & 1u) | ((uint32_t(x >> 32) >> bit & 1u) << 1);
+                if (code < 3u && !(skip_hets && code == 2u)) w = 1u << (8 * code);
+            }
+            pv[q] = w;
+        }
+        *reinterpret_cast<uint4 *>(tile + og_tile_offset(t, c, OG_BN)) = v;
+    }
+}
 
 struct OneHotGemmArgs {
-    const uint64_t *packed;      // panel
-    int32_t stride;
-    const int32_t *rows;         // [Kpad] local panel rows of the shared markers, -1 = padding
-    const uint8_t *codes;        // [S, Kpad] sample calls: 0 ref, 1 alt, 2 het, 3 absent
-    int32_t S, Kpad, n_acc;
-    int32_t skip_hets;
-    int32_t *out_score;          // [S, ld_out]
-    int32_t *out_ninfo;          // [S, ld_out]
-    int32_t ld_out;              // accessions rounded up to a multiple of OG_BN
+    const unsigned char *a_tiled;   // [m_blocks][n_kb][OG_A_TILE]
+    const unsigned char *b_tiled;   // [n_blocks][n_kb][OG_B_TILE]
+    int32_t n_kb;
+    int32_t S;
+    int32_t *out_score;             // [S, ld_out]
+    int32_t *out_ninfo;             // [S, ld_out]
+    int32_t ld_out;                 // accessions rounded up to a multiple of OG_BN
 };
 
-__device__ __forceinline__ uint64_t og_smem_desc(uint32_t saddr) {
-    // K-major, no swizzle: 16-byte rows of a core matrix are contiguous, 8-row groups are 128 B apart (SBO), the two
-    // 16-byte K chunks of one MMA are 2048 B apart (LBO).  Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1
-    return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(2048u >> 4) << 16) | (uint64_t(128u >> 4) << 32) | (uint64_t(1) << 46);
+__device__ __forceinline__ uint64_t og_smem_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    // K-major, no swizzle.  Bits: [0,14) address>>4, [16,30) LBO>>4 (between the two 16-byte K chunks of an MMA), [32,46) SBO>>4
+    // (between 8-row groups = 128 B), [46,48) descriptor version 1 (Blackwell), layout type 0.
+    return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(128u >> 4) << 32) | (uint64_t(1) << 46);
 }
 
 __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmArgs a) {
@@ -48,18 +110,19 @@ __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmA
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x, n_blk = blockIdx.y;
-    const int n_kb = a.Kpad / OG_ROWS;
+    const int n_kb = a.n_kb;
+    constexpr uint32_t STAGE_BYTES = OG_A_TILE + OG_B_TILE;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < OG_STAGES; ++s) {
-            mbar_init(smem_u32(&full[s]), 4u);          // one arrive per loader warp
+            mbar_init(smem_u32(&full[s]), 1u);          // producer's arrive.expect_tx + the bytes of two bulk copies
             mbar_init(smem_u32(&empty[s]), 1u);         // tcgen05.commit
         }
         mbar_init(smem_u32(&acc_ready), 1u);
         mbar_fence_init();
     }
-    if (warp == 4) {                                    // TMEM: 128 columns of 32-bit accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    if (warp == 1) {                                    // TMEM: 256 columns of 32-bit accumulators (128 lanes x 256 int32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -67,66 +130,60 @@ __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmA
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = tmem_base_slot;
 
-    if (warp < 4) {
-        // ---- loaders: expand both operand tiles of k-block kb into stage kb % STAGES ------------------------------
-        const int t = threadIdx.x;                       // 0..127 = operand row (m or n)
-        const int sample = m_blk * 64 + (t & 63);
-        const bool ninfo_row = t >= 64;
-        const uint8_t *crow = a.codes + int64_t(min(sample, a.S - 1)) * a.Kpad;
-        const bool sample_ok = sample < a.S;
-        const int acc = n_blk * OG_BN + t;
-        const bool acc_ok = acc < a.stride * 32;          // columns beyond the padded row produce zeros
-        const uint64_t *pcol = a.packed + (acc_ok ? (acc >> 5) : 0);
-        const int bit = acc & 31;
-        const uint32_t row_off = uint32_t(t >> 3) * 128u + uint32_t(t & 7) * 16u;   // inside a K-chunk slab of 16 row groups
+    if (warp == 0) {
+        // ---- producer: two 1-D TMA bulk copies per k-block (the tiles are stored in their shared-memory image) ----------
+        if (lane == 0) {
+            const unsigned char *ga = a.a_tiled + size_t(m_blk) * n_kb * OG_A_TILE;
+            const unsigned char *gb = a.b_tiled + size_t(n_blk) * n_kb * OG_B_TILE;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int st = kb % OG_STAGES;
+                mbar_wait(smem_u32(&empty[st]), (uint32_t(kb / OG_STAGES) & 1u) ^ 1u);
+                const uint32_t bar = smem_u32(&full[st]);
+                unsigned char *sa = og_smem + size_t(st) * STAGE_BYTES;
+                mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                tma_bulk_g2s(smem_u32(sa), ga + size_t(kb) * OG_A_TILE, OG_A_TILE, bar);
+                tma_bulk_g2s(smem_u32(sa + OG_A_TILE), gb + size_t(kb) * OG_B_TILE, OG_B_TILE, bar);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: one elected thread ---------------------------------------------------------------------------------
+        // instruction descriptor (kind::i8): D = S32 (bits 4-5 = 2), A/B = unsigned 8-bit, both K-major, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (2u << 4) | (uint32_t(OG_BN >> 3) << 17) | (uint32_t(OG_BM >> 4) << 24);
         for (int kb = 0; kb < n_kb; ++kb) {
             const int st = kb % OG_STAGES;
-            mbar_wait(smem_u32(&empty[st]), (uint32_t(kb / OG_STAGES) & 1u) ^ 1u);
-            unsigned char *sa = og_smem + size_t(st) * 2 * OG_TILE_BYTES;
-            unsigned char *sb = sa + OG_TILE_BYTES;
+            mbar_wait(smem_u32(&full[st]), uint32_t(kb / OG_STAGES) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(og_smem + size_t(st) * STAGE_BYTES), sb = sa + OG_A_TILE;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {                // 16-byte K chunk c = panel rows 4c..4c+3 of the block
-                const int k0 = kb * OG_ROWS + 4 * c;
-                // A: the sample's four calls
-                uint32_t cw = sample_ok ? *reinterpret_cast<const uint32_t *>(crow + k0) : 0x03030303u;
-                uint4 va;
-                uint32_t *pa = reinterpret_cast<uint32_t *>(&va);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t code = (cw >> (8 * q)) & 0xFFu;
-                    pa[q] = code < 3u ? (ninfo_row ? 0x00010101u : (1u << (8 * code))) : 0u;
+                for (int kk = 0; kk < 4; ++kk) {         // K = 32 bytes = K chunks 2kk, 2kk+1
+                    const uint64_t da = og_smem_desc(sa + kk * 2 * (OG_BM * 16), OG_BM * 16);
+                    const uint64_t db = og_smem_desc(sb + kk * 2 * (OG_BN * 16), OG_BN * 16);
+                    const uint32_t accumulate = (kb | kk) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem_acc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
                 }
-                *reinterpret_cast<uint4 *>(sa + c * 2048 + row_off) = va;
-                // B: the panel's four calls for this accession
-                uint4 vb;
-                uint32_t *pb = reinterpret_cast<uint32_t *>(&vb);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int32_t r = a.rows[k0 + q];
-                    uint32_t w = 0u;
-                    if (r >= 0 && acc_ok) {
-                        const uint64_t v = __ldg(pcol + int64_t(r) * a.stride);
-                        const uint32_t code = (uint32_t(v) >> bit & 1u) | ((uint32_t(v >> 32) >> bit & 1u) << 1);
-                        if (code < 3u && !(a.skip_hets && code == 2u)) w = 1u << (8 * code);
-                    }
-                    pb[q] = w;
-                }
-                *reinterpret_cast<uint4 *>(sb + c * 2048 + row_off) = vb;
+                // the stage is free once these MMAs have read it; the accumulator is complete after the last block
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
+                if (kb == n_kb - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_ready)) : "memory");
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&full[st]));
         }
-        // ---- epilogue: TMEM -> registers -> global; warp w reads TMEM lanes 32w..32w+31 = tile rows ------------------
+    } else {
+        // ---- epilogue: TMEM -> registers -> global; a warp may touch TMEM lanes 32*(warp%4) .. +31 = tile rows ----------------
         mbar_wait(smem_u32(&acc_ready), 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = warp * 32 + lane;                // tile row: < 64 score of sample, >= 64 ninfo
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;                  // tile row: < 64 score of a sample, >= 64 its ninfo
         const int s_out = m_blk * 64 + (row & 63);
         int32_t *dst = (row < 64 ? a.out_score : a.out_ninfo) + int64_t(s_out) * a.ld_out + n_blk * OG_BN;
 #pragma unroll 1
         for (int col = 0; col < OG_BN; col += 32) {
             uint32_t r[32];
-            const uint32_t taddr = tmem_acc + (uint32_t(warp * 32) << 16) + uint32_t(col);
+            const uint32_t taddr = tmem_acc + (uint32_t(lg * 32) << 16) + uint32_t(col);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -143,36 +200,10 @@ __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmA
                     *reinterpret_cast<int4 *>(dst + col + j) = make_int4(int(r[j]), int(r[j + 1]), int(r[j + 2]), int(r[j + 3]));
             }
         }
-    } else {
-        // ---- MMA issuer: one elected thread -----------------------------------------------------------------------------
-        // instruction descriptor (kind::i8): D = S32 (bits 4-5 = 2), A/B = unsigned 8-bit, both K-major, N>>3 at bit 17, M>>4 at bit 24
-        const uint32_t idesc = (2u << 4) | (uint32_t(OG_BN >> 3) << 17) | (uint32_t(OG_BM >> 4) << 24);
-        for (int kb = 0; kb < n_kb; ++kb) {
-            const int st = kb % OG_STAGES;
-            mbar_wait(smem_u32(&full[st]), uint32_t(kb / OG_STAGES) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(og_smem + size_t(st) * 2 * OG_TILE_BYTES), sb = sa + OG_TILE_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {         // K = 32 bytes = K-chunks 2kk, 2kk+1
-                    const uint64_t da = og_smem_desc(sa + kk * 4096), db = og_smem_desc(sb + kk * 4096);
-                    const uint32_t accumulate = (kb | kk) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem_acc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-                }
-                // the stage is free once these MMAs have read it; the accumulator is complete after the last block
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
-                if (kb == n_kb - 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_ready)) : "memory");
-            }
-            __syncwarp();
-        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_acc) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_acc) : "memory");
 }
 
 // int32 GEMM outputs -> the f64 reduce rows the likelihood epilogue reads (score | ninfo | markers | 0)
