@@ -133,6 +133,10 @@ def _worker(i):
     return comps, dt
 
 
+def _prepare(i):
+    return cpu_prepare_sample(_W["samples"][i], _W["n_acc"], _W["cap"])
+
+
 def run_reference_arm(args):
     """--impl reference: one process per sample on all host cores (README.md:9 deployment model)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -145,9 +149,11 @@ def run_reference_arm(args):
     positions, regions = synth.panel_positions(args.rows)
     samples = make_samples(positions, regions, args.accessions, procs, args.markers)
     cap = args.cpu_markers or 0
-    _W.update(positions=positions, regions=regions, samples=samples,
-              prepared=[cpu_prepare_sample(s, args.accessions, cap) for s in samples])
     ctx = mp.get_context("fork")
+    _W.update(positions=positions, regions=regions, samples=samples, n_acc=args.accessions, cap=cap)
+    with ctx.Pool(procs) as pool:                       # untimed: materialise the panel rows every sample touches
+        prepared = pool.map(_prepare, range(procs))
+    _W.update(prepared=prepared)                        # the timed pool below is forked after this, so workers inherit it
     times = []
     comps = 0
     with ctx.Pool(procs) as pool:

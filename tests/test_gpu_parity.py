@@ -571,3 +571,55 @@ def test_shared_panel_tensor_core_batch(lib, n_acc, S, K, skip):
         np.testing.assert_allclose(r["LR"][s], lr, rtol=RTOL, equal_nan=True)
     assert r["gemm_ms"] > 0
     db.close()
+
+
+def test_genotype_batch_equals_per_sample_genotyper(lib, small_geno, small_panel, tmp_path):
+    """Batched tensor-core mode through the Python mirror vs Genotyper run sample by sample (called genotypes)."""
+    from snpmatch_b200.core import batch, parsers, snpmatch
+    p = small_panel
+    inputs = []
+    for i in range(9):
+        s = synth.make_sample(p["positions"], p["chr_regions"], p["chrs"], 40, true_acc=3 + 4 * i, n_db=800 + 50 * i, n_extra=40, seed=300 + i)
+        inp = parsers.ParseInputs("")
+        inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei_hard"], s["dp"])
+        inputs.append(inp)
+    for skip in (False, True):
+        results, info = batch.genotype_batch(small_geno, inputs, skip_db_hets=skip)
+        assert info["panel_markers"] > 800 and info["gemm_ms"] > 0
+        for i, inp in enumerate(inputs):
+            one = snpmatch.Genotyper(inp, small_geno, str(tmp_path / ("b%d" % i)), run_genotyper=False, skip_db_hets=skip).genotyper()
+            got = results[i]
+            assert np.array_equal(got.scores, one.scores) and np.array_equal(got.ninfo, one.ninfo)
+            assert got.num_snps == one.num_snps and got.overlap == one.overlap
+            got.get_likelihoods(); one.get_likelihoods()
+            np.testing.assert_allclose(got.likelis, one.likelis, rtol=RTOL, equal_nan=True)
+            np.testing.assert_allclose(got.lrts, one.lrts, rtol=RTOL, equal_nan=True)
+            if not skip and 3 + 4 * i not in (9, 11):      # 11 is all-missing and 9 a near-copy of 7 in the golden panel
+                assert int(np.nanargmin(got.likelis)) == 3 + 4 * i
+
+
+def test_command_line_inbred_and_cross(lib, small_geno, sample_inbred, golden_outputs, tmp_path):
+    """The `snpmatch inbred` / `cross` command line on a packed database file and a BED sample."""
+    import snpmatch_b200
+    db_path = str(tmp_path / "panel.npz")
+    small_geno.save_packed(db_path)
+    s = sample_inbred
+    bed = tmp_path / "sample.bed"
+    with open(bed, "w") as fh:
+        for c, pos, gt in zip(s["chrs"], s["pos"], s["gt"]):
+            fh.write("%s\t%d\t%s\n" % (c, pos, gt))
+    out = str(tmp_path / "cli")
+    assert snpmatch_b200.main(["inbred", "-i", str(bed), "-d", db_path, "-o", out]) == 0
+    want = golden_outputs["inbred_hard"]["scores.txt"].strip("\n").split("\n")
+    got = open(out + ".scores.txt").read().strip("\n").split("\n")
+    assert len(got) == len(want)
+    for g_line, w_line in zip(got, want):
+        gf, wf = g_line.split("\t"), w_line.split("\t")
+        assert gf[:3] == wf[:3] and gf[6] == wf[6]                 # accession, matches, ninfo, num_snps
+        assert gf[7] == ""                                          # BED carries no depth: nan instead of the reference's crash (A.8 Q5)
+    js = json.loads(open(out + ".matches.json").read())
+    assert js["interpretation"]["case"] == json.loads(golden_outputs["inbred_hard"]["matches.json"])["interpretation"]["case"]
+    assert snpmatch_b200.main(["cross", "-i", str(bed), "-d", db_path, "-o", out + "_x", "-b", "300000"]) == 0
+    assert os.path.exists(out + "_x.windowscore.txt") and os.path.exists(out + "_x.scores.txt")
+    with pytest.raises(SystemExit):                                 # die(): missing input file -> exit 1, as the reference
+        snpmatch_b200.main(["inbred", "-i", str(tmp_path / "missing.bed"), "-d", db_path])
