@@ -467,6 +467,22 @@ def run_b200_arm(args):
             if not args.cpu_markers:
                 line["cpu_baseline"]["parity"] = bool(np.array_equal(cpu_score, out["score"][0]) and
                                                       np.array_equal(cpu_ninfo, out["ninfo"][0]))
+        if world == 1:
+            # batched shared-panel mode (BASELINE configs[3]): 4096 called-genotype samples on 20 000 shared markers as a
+            # one-hot int8 GEMM on tcgen05; device time of the GEMM kernel (operand expansion and H2D of the codes excluded)
+            rng = np.random.default_rng(9)
+            S9, K9 = 4096, 20000
+            rows9 = np.sort(rng.choice(n_rows, size=K9, replace=False))
+            codes9 = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(S9, K9), p=[0.6, 0.28, 0.02, 0.1])
+            g9 = min(db.score_shared_panel(rows9, codes9, likelihoods=False)["gemm_ms"] for _ in range(3))
+            ops9 = 2.0 * (2 * S9) * (((n_acc + 255) // 256) * 256) * (4 * K9)
+            peak9 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+            line["batched_shared_panel"] = {
+                "workload": "configs[3]: %d called-genotype samples x %d shared markers vs %d accessions, one-hot int8 GEMM on tcgen05" % (S9, K9, n_acc),
+                "value": S9 * K9 * n_acc / (g9 * 1e-3), "unit": UNIT, "gemm_ms": g9,
+                "roofline": {"bound": "tensor", "kernel": "k_onehot_gemm", "achieved": ops9 / (g9 * 1e-3) / 1e12, "peak": peak9, "unit": "TOP/s (int8)",
+                             "frac": ops9 / (g9 * 1e-3) / 1e12 / peak9,
+                             "peak_source": "2 x measured dense bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 dense is nominally 2x bf16: 4500 vs 2250)"}}
         print(json.dumps(line))
     batch.close()
     batch2.close()

@@ -832,12 +832,12 @@ int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, c
                                                                 d_bt.as<unsigned char>());
     SP_CUDA(cudaGetLastError());
     OneHotGemmArgs g = {};
-    g.a_tiled = d_at.as<unsigned char>(); g.b_tiled = d_bt.as<unsigned char>(); g.n_kb = n_kb; g.S = int32_t(S);
+    g.a_tiled = d_at.as<unsigned char>(); g.b_tiled = d_bt.as<unsigned char>(); g.n_kb = n_kb; g.m_blocks = m_blocks; g.n_blocks = n_blocks; g.S = int32_t(S);
     g.out_score = d_os.as<int32_t>(); g.out_ninfo = d_on.as<int32_t>(); g.ld_out = ld_out;
     const size_t smem = size_t(OG_STAGES) * (OG_A_TILE + OG_B_TILE) + 1024;
     static bool og_attr = false;
     if (!og_attr) { SP_CUDA(cudaFuncSetAttribute(k_onehot_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); og_attr = true; }
-    dim3 grid((unsigned)m_blocks, (unsigned)n_blocks);
+    dim3 grid((unsigned)std::min(m_blocks * n_blocks, db->n_sm));      // persistent: one CTA per SM walks the tiles
     SP_CUDA(cudaEventRecord(e0, st));
     k_onehot_gemm<<<grid, OG_THREADS, smem, st>>>(g);
     SP_CUDA(cudaGetLastError());

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_onehot_expand_panel(const uint64_t *__r
 struct OneHotGemmArgs {
     const unsigned char *a_tiled;   // [m_blocks][n_kb][OG_A_TILE]
     const unsigned char *b_tiled;   // [n_blocks][n_kb][OG_B_TILE]
-    int32_t n_kb;
+    int32_t n_kb, m_blocks, n_blocks;
     int32_t S;
     int32_t *out_score;             // [S, ld_out]
     int32_t *out_ninfo;             // [S, ld_out]
@@ -104,13 +104,16 @@ __device__ __forceinline__ uint64_t og_smem_desc(uint32_t saddr, uint32_t lbo_by
     return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(128u >> 4) << 32) | (uint64_t(1) << 46);
 }
 
+// Persistent: grid = min(tiles, SMs); a CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so CTAs running at the same
+// time share the B operand in L2).  Two 256-column accumulators in TMEM alternate, so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
 __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmArgs a) {
     extern __shared__ __align__(1024) unsigned char og_smem[];
-    __shared__ uint64_t full[OG_STAGES], empty[OG_STAGES], acc_ready;
+    __shared__ uint64_t full[OG_STAGES], empty[OG_STAGES], acc_ready[2], acc_free[2];
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y;
     const int n_kb = a.n_kb;
+    const int n_tiles = a.m_blocks * a.n_blocks;
     constexpr uint32_t STAGE_BYTES = OG_A_TILE + OG_B_TILE;
 
     if (threadIdx.x == 0) {
@@ -118,92 +121,115 @@ __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmA
             mbar_init(smem_u32(&full[s]), 1u);          // producer's arrive.expect_tx + the bytes of two bulk copies
             mbar_init(smem_u32(&empty[s]), 1u);         // tcgen05.commit
         }
-        mbar_init(smem_u32(&acc_ready), 1u);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&acc_ready[s]), 1u);     // tcgen05.commit after a tile's last MMA
+            mbar_init(smem_u32(&acc_free[s]), 4u);      // one arrive per epilogue warp
+        }
         mbar_fence_init();
     }
-    if (warp == 1) {                                    // TMEM: 256 columns of 32-bit accumulators (128 lanes x 256 int32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+    if (warp == 1) {                                    // all of TMEM: two 128-lane x 256-column int32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = tmem_base_slot;
+    const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
         // ---- producer: two 1-D TMA bulk copies per k-block (the tiles are stored in their shared-memory image) ----------
         if (lane == 0) {
-            const unsigned char *ga = a.a_tiled + size_t(m_blk) * n_kb * OG_A_TILE;
-            const unsigned char *gb = a.b_tiled + size_t(n_blk) * n_kb * OG_B_TILE;
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int st = kb % OG_STAGES;
-                mbar_wait(smem_u32(&empty[st]), (uint32_t(kb / OG_STAGES) & 1u) ^ 1u);
-                const uint32_t bar = smem_u32(&full[st]);
-                unsigned char *sa = og_smem + size_t(st) * STAGE_BYTES;
-                mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                tma_bulk_g2s(smem_u32(sa), ga + size_t(kb) * OG_A_TILE, OG_A_TILE, bar);
-                tma_bulk_g2s(smem_u32(sa + OG_A_TILE), gb + size_t(kb) * OG_B_TILE, OG_B_TILE, bar);
+            uint32_t it = 0;                             // k-blocks issued so far, over all tiles
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_blk = tile % a.m_blocks, n_blk = tile / a.m_blocks;
+                const unsigned char *ga = a.a_tiled + size_t(m_blk) * n_kb * OG_A_TILE;
+                const unsigned char *gb = a.b_tiled + size_t(n_blk) * n_kb * OG_B_TILE;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const uint32_t st = it % OG_STAGES;
+                    mbar_wait(smem_u32(&empty[st]), ((it / OG_STAGES) & 1u) ^ 1u);
+                    const uint32_t bar = smem_u32(&full[st]);
+                    unsigned char *sa = og_smem + size_t(st) * STAGE_BYTES;
+                    mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                    tma_bulk_g2s(smem_u32(sa), ga + size_t(kb) * OG_A_TILE, OG_A_TILE, bar);
+                    tma_bulk_g2s(smem_u32(sa + OG_A_TILE), gb + size_t(kb) * OG_B_TILE, OG_B_TILE, bar);
+                }
             }
         }
     } else if (warp == 1) {
         // ---- MMA issuer: one elected thread ---------------------------------------------------------------------------------
         // instruction descriptor (kind::i8): D = S32 (bits 4-5 = 2), A/B = unsigned 8-bit, both K-major, N>>3 at bit 17, M>>4 at bit 24
         const uint32_t idesc = (2u << 4) | (uint32_t(OG_BN >> 3) << 17) | (uint32_t(OG_BM >> 4) << 24);
-        for (int kb = 0; kb < n_kb; ++kb) {
-            const int st = kb % OG_STAGES;
-            mbar_wait(smem_u32(&full[st]), uint32_t(kb / OG_STAGES) & 1u);
+        uint32_t it = 0, ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1u;
+            mbar_wait(smem_u32(&acc_free[buf]), ((ti >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(og_smem + size_t(st) * STAGE_BYTES), sb = sa + OG_A_TILE;
+            const uint32_t tmem_acc = tmem_base + buf * uint32_t(OG_BN);
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t st = it % OG_STAGES;
+                mbar_wait(smem_u32(&full[st]), (it / OG_STAGES) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(og_smem + size_t(st) * STAGE_BYTES), sb = sa + OG_A_TILE;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {         // K = 32 bytes = K chunks 2kk, 2kk+1
-                    const uint64_t da = og_smem_desc(sa + kk * 2 * (OG_BM * 16), OG_BM * 16);
-                    const uint64_t db = og_smem_desc(sb + kk * 2 * (OG_BN * 16), OG_BN * 16);
-                    const uint32_t accumulate = (kb | kk) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem_acc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+                    for (int kk = 0; kk < 4; ++kk) {     // K = 32 bytes = K chunks 2kk, 2kk+1
+                        const uint64_t da = og_smem_desc(sa + kk * 2 * (OG_BM * 16), OG_BM * 16);
+                        const uint64_t db = og_smem_desc(sb + kk * 2 * (OG_BN * 16), OG_BN * 16);
+                        const uint32_t accumulate = (kb | kk) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem_acc), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+                    }
+                    // the stage is free once these MMAs have read it; the accumulator is complete after the last block
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
+                    if (kb == n_kb - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_ready[buf])) : "memory");
                 }
-                // the stage is free once these MMAs have read it; the accumulator is complete after the last block
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
-                if (kb == n_kb - 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_ready)) : "memory");
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ---- epilogue: TMEM -> registers -> global; a warp may touch TMEM lanes 32*(warp%4) .. +31 = tile rows ----------------
-        mbar_wait(smem_u32(&acc_ready), 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;
         const int row = lg * 32 + lane;                  // tile row: < 64 score of a sample, >= 64 its ninfo
-        const int s_out = m_blk * 64 + (row & 63);
-        int32_t *dst = (row < 64 ? a.out_score : a.out_ninfo) + int64_t(s_out) * a.ld_out + n_blk * OG_BN;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const int m_blk = tile % a.m_blocks, n_blk = tile / a.m_blocks;
+            const uint32_t buf = ti & 1u;
+            mbar_wait(smem_u32(&acc_ready[buf]), (ti >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int s_out = m_blk * 64 + (row & 63);
+            int32_t *dst = (row < 64 ? a.out_score : a.out_ninfo) + int64_t(s_out) * a.ld_out + n_blk * OG_BN;
 #pragma unroll 1
-        for (int col = 0; col < OG_BN; col += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_acc + (uint32_t(lg * 32) << 16) + uint32_t(col);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (s_out < a.S) {
+            for (int col = 0; col < OG_BN; col += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + buf * uint32_t(OG_BN) + (uint32_t(lg * 32) << 16) + uint32_t(col);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (s_out < a.S) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<int4 *>(dst + col + j) = make_int4(int(r[j]), int(r[j + 1]), int(r[j + 2]), int(r[j + 3]));
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<int4 *>(dst + col + j) = make_int4(int(r[j]), int(r[j + 1]), int(r[j + 2]), int(r[j + 3]));
+                }
             }
+            // this warp has read its lanes of the accumulator: hand the buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_free[buf]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_acc) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // int32 GEMM outputs -> the f64 reduce rows the likelihood epilogue reads (score | ninfo | markers | 0)
