@@ -475,7 +475,7 @@ def run_b200_arm(args):
             rows9 = np.sort(rng.choice(n_rows, size=K9, replace=False))
             codes9 = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(S9, K9), p=[0.6, 0.28, 0.02, 0.1])
             g9 = min(db.score_shared_panel(rows9, codes9, likelihoods=False)["gemm_ms"] for _ in range(3))
-            ops9 = 2.0 * (2 * S9) * (((n_acc + 255) // 256) * 256) * (4 * K9)
+            ops9 = 2.0 * (2 * S9) * n_acc * (3 * K9)          # algorithmic int8 ops (the kernel pads A to 1280 and K-slots to 4 per row)
             peak9 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
             line["batched_shared_panel"] = {
                 "workload": "configs[3]: %d called-genotype samples x %d shared markers vs %d accessions, one-hot int8 GEMM on tcgen05" % (S9, K9, n_acc),
