@@ -39,6 +39,7 @@ extern "C" {
 #define SNPM_E_NOMEM      -3
 #define SNPM_E_STATE      -4       /* call order (e.g. fetch before run) */
 #define SNPM_E_ASSERT     -5       /* the reference would have tripped an assert (y > n, snpmatch.py:43) */
+#define SNPM_E_RANGE      -6       /* a compact encoding does not fit (too many distinct weight triples, chromosome id > 254) */
 
 #define SNPM_CHUNK_ROWS 1000       /* Genotyper chunk_size, snpmatch.py:173 */
 
@@ -127,6 +128,29 @@ int snpm_batch_upload(snpm_batch *b, int64_t n_samples, const int64_t *offsets,
 int snpm_batch_upload_indexed(snpm_batch *b, int64_t n_samples, const int64_t *offsets,
                               const int32_t *s_chrom_id, const int32_t *s_pos, const uint16_t *wei_idx,
                               const double *table, int32_t n_table);
+/* ---- grouped order: the throughput path of likelihood-weighted scoring (k_score_grouped) -----------------------------
+ * matchGTsAccs (snpmatch.py:74-89) adds one of three weights per matched row; exp(-PL/10) takes few distinct values
+ * (parsers.py:147-151), so rows that share a weight triple can be COUNTED per accession and weighted once.
+ *
+ * snpm_group_markers (host code, no device needed; run once per sample set at parse time, like ParseInputs' npz cache,
+ * parsers.py:96-98): assigns every marker the id of its weight triple (table f64 [*n_table, 3] in wei's column order,
+ * at most min(table_cap, 65536) triples per call -> SNPM_E_RANGE beyond), and writes each sample's markers ordered by
+ * (id, original order): chromosome ids as one byte (255 = not in the panel), positions, ids, and (optional) out_order =
+ * index of the marker in the input arrays.  Weights must be finite and >= 0 (SNPM_E_ARG otherwise: use the position-order
+ * path for such inputs). */
+int snpm_group_markers(int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos,
+                       const double *wei, uint8_t *out_chrom, int32_t *out_pos, uint16_t *out_gid, int64_t *out_order,
+                       double *table, int32_t table_cap, int32_t *n_table);
+/* replace the samples of a batch by grouped ones (7 bytes per marker cross the PCIe bus); asynchronous like
+ * snpm_batch_upload.  Such a batch is scored with snpm_batch_run(mode 2) only; windows and the F1 pass need position order. */
+int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8,
+                              const int32_t *s_pos, const uint16_t *gid, const double *table, int32_t n_table);
+/* after snpm_batch_epilogue on a grouped batch: counts[s] = accessions of sample s whose fractional score part lies
+ * within the rounding-error bound of an integer, i.e. whose int(score) depends on the reference's own summation order
+ * (probability ~1e-7 per accession).  Re-score those samples with mode 0.  All zeros for position-order batches. */
+int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts);
+/* rows per segment of the grouped kernel (16..1008, a multiple of 8, default 1000); takes effect at the next grouped upload */
+int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows);
 int snpm_batch_destroy(snpm_batch *b);
 /* optional Genotyper.genotyper(filter_pos_ix=...) (snpmatch.py:211-216): keep only pairs whose
  * GLOBAL database row is in the sorted list (applies to every sample of the batch); n = 0 clears */
@@ -135,7 +159,9 @@ int snpm_batch_set_row_filter(snpm_batch *b, const int64_t *sorted_rows, int64_t
  * call returns without waiting (inputs already resident).
  * mode bits 0-7: scoring kernel — 0 = fp64 kernel in the reference's summation order (any weights);
  *                1 = popcount kernel for called genotypes (every weight row one-hot, as ParseInputs.get_wei_from_GT
- *                    produces, parsers.py:132-139; exact in any order; SNPM_E_ARG at wait/fetch otherwise).
+ *                    produces, parsers.py:132-139; exact in any order; SNPM_E_ARG at wait/fetch otherwise);
+ *                2 = grouped counting kernel (batches uploaded with snpm_batch_upload_grouped, any finite weights >= 0):
+ *                    integers bit-exact, fp64 scores within a few ulp of the reference; see snpm_batch_guard_counts.
  * mode bits 8-15: join algorithm (0 auto, 1 binary search, 2 merge-path). */
 int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode);
 /* likelihood epilogue on the (possibly all-reduced) totals; queued, not waited for */
@@ -144,7 +170,9 @@ int snpm_batch_epilogue(snpm_batch *b);
  * events on the db's stream (may be NULL) */
 int snpm_batch_wait(snpm_batch *b, float *ms_device);
 /* device address of the f64 reduce buffer [S, 2*n_acc+2]: per sample score[n_acc],
- * ninfo[n_acc] (as f64, exact), m, y>n violation count — the payload of the cross-GPU sum (8e) */
+ * ninfo[n_acc] (as f64, exact), m, y>n violation count — the payload of the cross-GPU sum (8e).
+ * Grouped batches: [S, 3*n_acc+2] = fractional part F | ninfo | m | violations | integer part I; the epilogue
+ * turns F into the score after the reduce. */
 int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles);
 /* copy results to the host (any pointer may be NULL).  score f64[S,A] (untruncated),
  * matches int64[S,A] (= int(score), snpmatch.py:96), ninfo int64[S,A], m int64[S],

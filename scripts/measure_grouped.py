@@ -1,0 +1,87 @@
+"""Development measurement of the grouped kernel on the headline workload (64 PL samples x 50 k markers vs 1135 x 10.7 M):
+device times of the scoring kernels (library CUDA events) and integer parity against the order-exact kernel.
+    python scripts/measure_grouped.py [--samples 64] [--chunks 1000,500] [--accessions 1135]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--rows", type=int, default=10_700_000)
+    ap.add_argument("--accessions", type=int, default=1135)
+    ap.add_argument("--markers", type=int, default=45000)
+    ap.add_argument("--chunks", default="1000")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--no-exact", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as ge
+    ge.build()
+    from snpmatch_b200 import lib, synth
+    from snpmatch_b200.core import snp_genotype
+    import bench
+    positions, regions = synth.panel_positions(args.rows)
+    g = snp_genotype.Genotype.synthetic(args.rows, args.accessions, device=0)
+    db = g.db
+    bench.N_EXTRA_MARKERS = 5000
+    samples = bench.make_samples(positions, regions, args.accessions, args.samples, args.markers)
+    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])]).astype(np.int64)
+    chrom = np.concatenate([s["chr_ix"] for s in samples]).astype(np.int32)
+    pos = np.concatenate([s["pos"] for s in samples]).astype(np.int32)
+    wei = np.concatenate([s["wei"] for s in samples])
+    b = lib.Batch(db, offs, chrom, pos, wei)
+    out = {"samples": args.samples, "accessions": args.accessions}
+    exact = None
+    if not args.no_exact:
+        ts = []
+        for _ in range(args.reps):
+            b.run()
+            b.epilogue()
+            b.wait()
+            ts.append(b.timings())
+        exact = {k: v.copy() for k, v in b.fetch().items()}
+        out["exact"] = {k: float(np.median([t[k] for t in ts])) for k in ts[0]}
+    import time
+    t0 = time.perf_counter()
+    gs = lib.group_markers(offs, chrom, pos, wei)
+    out["group_markers_host_s"] = time.perf_counter() - t0
+    out["distinct_triples"] = int(len(gs.table))
+    m_total = None
+    for chunk in [int(c) for c in args.chunks.split(",")]:
+        b.set_group_chunk(chunk)
+        b.upload_grouped(gs)
+        ts = []
+        for _ in range(args.reps):
+            b.run(kernel_mode=lib.KERNEL_GROUPED)
+            b.epilogue()
+            b.wait()
+            ts.append(b.timings())
+        r = b.fetch()
+        guard = b.guard_counts()
+        t = {k: float(np.median([x[k] for x in ts])) for k in ts[0]}
+        m_total = int(r["m"].sum())
+        alg = m_total * ((args.accessions + 3) // 4 + 24) + 16 * args.accessions * args.samples
+        t["score_GBps"] = alg / (t["score_ms"] * 1e-3) / 1e9
+        t["comparisons_per_s_total"] = m_total * args.accessions / (t["total_ms"] * 1e-3)
+        t["guard_flagged_samples"] = int((guard > 0).sum())
+        if exact is not None:
+            ok = guard == 0
+            t["matches_equal"] = bool(np.array_equal(r["matches"][ok], exact["matches"][ok]))
+            t["ninfo_equal"] = bool(np.array_equal(r["ninfo"], exact["ninfo"]))
+            t["score_max_rel"] = float(np.max(np.abs(r["score"] - exact["score"]) / np.maximum(exact["score"], 1.0)))
+            t["LR_max_rel"] = float(np.nanmax(np.abs(r["LR"][ok] - exact["LR"][ok]) / np.abs(exact["LR"][ok])))
+        out["grouped_chunk_%d" % chunk] = t
+    print(json.dumps(out, indent=1))
+    b.close()
+    g.close()
+
+
+if __name__ == "__main__":
+    main()

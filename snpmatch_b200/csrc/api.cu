@@ -7,6 +7,8 @@
 #include "f1.cuh"
 #include "hardcall.cuh"
 #include "gemm_onehot.cuh"
+#include "grouped.cuh"
+#include <unordered_map>
 
 namespace snpm {
 thread_local std::string g_last_error;
@@ -264,6 +266,7 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
     if (wei_idx && (!table || n_table < 1 || n_table > 65536)) return fail(SNPM_E_ARG, "batch: weight table must hold 1..65536 entries");
     b->S = S;
     b->n = n;
+    b->grouped = false;
     b->h_off.assign(offsets, offsets + S + 1);
     int64_t nseg = 0;
     for (int64_t s = 0; s < S; ++s) nseg += ceil_div64(std::min<int64_t>(offsets[s + 1] - offsets[s], db->n_rows), SNPM_CHUNK_ROWS);
@@ -345,6 +348,189 @@ int snpm_batch_upload_indexed(snpm_batch *b, int64_t n_samples, const int64_t *o
     return batch_upload(b, n_samples, offsets, s_chrom_id, s_pos, nullptr, wei_idx, table, n_table);
 }
 
+
+// ---- grouped order (k_score_grouped) ---------------------------------------------------------------
+// Host-side preparation, done once per sample set at parse time: order every sample's markers by their weight triple.
+int snpm_group_markers(int64_t n_samples, const int64_t *offsets, const int32_t *s_chrom_id, const int32_t *s_pos, const double *wei,
+                       uint8_t *out_chrom, int32_t *out_pos, uint16_t *out_gid, int64_t *out_order, double *table, int32_t table_cap,
+                       int32_t *n_table) {
+    if (n_samples < 1 || !offsets || !n_table || !table || table_cap < 1) return fail(SNPM_E_ARG, "snpm_group_markers: bad arguments");
+    const int64_t n = offsets[n_samples];
+    if (n > 0 && (!s_chrom_id || !s_pos || !wei || !out_chrom || !out_pos || !out_gid)) return fail(SNPM_E_ARG, "snpm_group_markers: NULL marker arrays");
+    struct Key {
+        uint64_t a, b, c;
+        bool operator==(const Key &o) const { return a == o.a && b == o.b && c == o.c; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key &k) const {
+            uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
+            h ^= (k.b + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+            h ^= (k.c + 0x165667B19E3779F9ull) * 0xFF51AFD7ED558CCDull + (h << 6) + (h >> 2);
+            return size_t(h ^ (h >> 29));
+        }
+    };
+    std::unordered_map<Key, int32_t, KeyHash> ids;
+    ids.reserve(4096);
+    const int32_t cap = std::min<int32_t>(table_cap, 65536);
+    std::vector<int32_t> gid(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) {
+        const double w0 = wei[3 * i], w1 = wei[3 * i + 1], w2 = wei[3 * i + 2];
+        if (!(w0 >= 0.0 && w1 >= 0.0 && w2 >= 0.0) || std::isinf(w0) || std::isinf(w1) || std::isinf(w2))
+            return fail(SNPM_E_ARG, "snpm_group_markers: weights must be finite and non-negative (marker %lld)", (long long)i);
+        Key k;
+        memcpy(&k.a, &w0, 8);
+        memcpy(&k.b, &w1, 8);
+        memcpy(&k.c, &w2, 8);
+        if (w0 == 0.0) k.a = 0;        // -0.0 and 0.0 weigh the same
+        if (w1 == 0.0) k.b = 0;
+        if (w2 == 0.0) k.c = 0;
+        auto it = ids.find(k);
+        if (it == ids.end()) {
+            const int32_t id = int32_t(ids.size());
+            if (id >= cap) return fail(SNPM_E_RANGE, "snpm_group_markers: more than %d distinct weight triples", cap);
+            table[3 * size_t(id)] = w0;
+            table[3 * size_t(id) + 1] = w1;
+            table[3 * size_t(id) + 2] = w2;
+            it = ids.emplace(k, id).first;
+        }
+        gid[size_t(i)] = it->second;
+        const int32_t c = s_chrom_id[i];
+        if (c >= 255) return fail(SNPM_E_RANGE, "snpm_group_markers: chromosome id %d does not fit one byte", c);
+    }
+    const int32_t T = int32_t(ids.size());
+    *n_table = T;
+    // Order the triples so that along a sample's markers every class weight changes as rarely as possible (the kernel reads a
+    // class counter out only when THAT class's weight changes): first by the called class (the one whose weight is 1.0, else
+    // the largest), then by the remaining class with fewer distinct values, then by the other one.
+    {
+        std::vector<int32_t> called(static_cast<size_t>(T));
+        std::vector<std::vector<double>> seen(9);
+        for (int32_t t = 0; t < T; ++t) {
+            const double *w = table + 3 * size_t(t);
+            int c = 0;
+            if (w[0] == 1.0) c = 0; else if (w[2] == 1.0) c = 2; else if (w[1] == 1.0) c = 1;
+            else { c = 0; if (w[2] > w[c]) c = 2; if (w[1] > w[c]) c = 1; }
+            called[size_t(t)] = c;
+            for (int k = 0; k < 3; ++k) seen[size_t(3 * c + k)].push_back(w[k]);
+        }
+        int slow[3], fast[3];
+        for (int c = 0; c < 3; ++c) {
+            size_t distinct[3] = {0, 0, 0};
+            for (int k = 0; k < 3; ++k) {
+                auto &v = seen[size_t(3 * c + k)];
+                std::sort(v.begin(), v.end());
+                distinct[k] = size_t(std::unique(v.begin(), v.end()) - v.begin());
+            }
+            const int o1 = (c + 1) % 3, o2 = (c + 2) % 3;
+            if (distinct[o1] <= distinct[o2]) { slow[c] = o1; fast[c] = o2; } else { slow[c] = o2; fast[c] = o1; }
+        }
+        std::vector<int32_t> perm(static_cast<size_t>(T)), rank(static_cast<size_t>(T));
+        for (int32_t t = 0; t < T; ++t) perm[size_t(t)] = t;
+        std::sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) {
+            const int cx = called[size_t(x)], cy = called[size_t(y)];
+            if (cx != cy) return cx < cy;
+            const double *wx_ = table + 3 * size_t(x), *wy_ = table + 3 * size_t(y);
+            if (wx_[cx] != wy_[cx]) return wx_[cx] > wy_[cx];
+            if (wx_[slow[cx]] != wy_[slow[cx]]) return wx_[slow[cx]] > wy_[slow[cx]];
+            if (wx_[fast[cx]] != wy_[fast[cx]]) return wx_[fast[cx]] > wy_[fast[cx]];
+            return x < y;
+        });
+        std::vector<double> sorted(static_cast<size_t>(T) * 3);
+        for (int32_t r = 0; r < T; ++r) {
+            rank[size_t(perm[size_t(r)])] = r;
+            memcpy(&sorted[3 * size_t(r)], table + 3 * size_t(perm[size_t(r)]), 24);
+        }
+        memcpy(table, sorted.data(), size_t(T) * 24);
+        for (int64_t i = 0; i < n; ++i) gid[size_t(i)] = rank[size_t(gid[size_t(i)])];
+    }
+    std::vector<int64_t> cnt(static_cast<size_t>(T) + 1);
+    for (int64_t s = 0; s < n_samples; ++s) {
+        const int64_t b0 = offsets[s], b1 = offsets[s + 1];
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int64_t i = b0; i < b1; ++i) ++cnt[size_t(gid[size_t(i)]) + 1];
+        for (int32_t t = 0; t < T; ++t) cnt[size_t(t) + 1] += cnt[size_t(t)];
+        for (int64_t i = b0; i < b1; ++i) {                       // stable: position order is kept inside a group
+            const int32_t g = gid[size_t(i)];
+            const int64_t o = b0 + cnt[size_t(g)]++;
+            out_chrom[o] = s_chrom_id[i] < 0 ? uint8_t(255) : uint8_t(s_chrom_id[i]);
+            out_pos[o] = s_pos[i];
+            out_gid[o] = uint16_t(g);
+            if (out_order) out_order[o] = i;
+        }
+    }
+    return SNPM_OK;
+}
+
+int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8, const int32_t *s_pos,
+                              const uint16_t *gid, const double *table, int32_t n_table) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL batch");
+    snpm_db *db = b->db;
+    if (n_samples < 1 || !offsets || offsets[0] != 0) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: need samples and offsets starting at 0");
+    for (int64_t s = 0; s < n_samples; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: offsets must be non-decreasing");
+    const int64_t n = offsets[n_samples];
+    if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: %lld markers exceed the 2^31 limit", (long long)n);
+    if (n > 0 && (!chrom_u8 || !s_pos || !gid)) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL marker arrays");
+    if (!table || n_table < 1 || n_table > 65536) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: weight table must hold 1..65536 triples");
+    std::vector<double> t4(size_t(n_table) * 4);
+    for (int32_t t = 0; t < n_table; ++t) {
+        const double w0 = table[3 * size_t(t)], w1 = table[3 * size_t(t) + 1], w2 = table[3 * size_t(t) + 2];
+        if (!(w0 >= 0.0 && w1 >= 0.0 && w2 >= 0.0) || std::isinf(w0) || std::isinf(w1) || std::isinf(w2))
+            return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: weights must be finite and non-negative (triple %d)", t);
+        t4[4 * size_t(t)] = w0;            // (w_ref, w_alt, w_het, 0): the order of pair_w
+        t4[4 * size_t(t) + 1] = w2;
+        t4[4 * size_t(t) + 2] = w1;
+        t4[4 * size_t(t) + 3] = 0.0;
+    }
+    SNPM_CUDA(cudaSetDevice(db->device));
+    b->S = n_samples;
+    b->n = n;
+    b->grouped = true;
+    b->n_gtable = n_table;
+    b->h_off.assign(offsets, offsets + n_samples + 1);
+    int64_t nseg = 0;
+    for (int64_t s = 0; s < n_samples; ++s) nseg += ceil_div64(std::min<int64_t>(offsets[s + 1] - offsets[s], db->n_rows), b->gchunk);
+    b->nseg_cap = nseg;
+    SNPM_TRY(b->d_off.ensure(size_t(n_samples + 1) * 8));
+    SNPM_TRY(b->d_chrom8.ensure(size_t(n)));
+    SNPM_TRY(b->d_chrom.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pos.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_gid.ensure(size_t(n) * 2));
+    SNPM_TRY(b->d_gtable.ensure(size_t(n_table) * 32));
+    cudaStream_t st = b->copy_stream;
+    SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_inputs_free, 0));
+    SNPM_CUDA(cudaMemcpyAsync(b->d_off.p, offsets, size_t(n_samples + 1) * 8, cudaMemcpyHostToDevice, st));
+    // the table is staged in a buffer the batch owns so that the caller's (and this function's) copy may go away
+    b->h_gtable.assign(t4.begin(), t4.end());
+    SNPM_CUDA(cudaMemcpyAsync(b->d_gtable.p, b->h_gtable.data(), size_t(n_table) * 32, cudaMemcpyHostToDevice, st));
+    if (n) {
+        SNPM_CUDA(cudaMemcpyAsync(b->d_chrom8.p, chrom_u8, size_t(n), cudaMemcpyHostToDevice, st));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, s_pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_gid.p, gid, size_t(n) * 2, cudaMemcpyHostToDevice, st));
+        k_expand_chrom<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_chrom8.as<uint8_t>(), n, b->d_chrom.as<int32_t>());
+        SNPM_KERNEL_CHECK();
+    }
+    SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
+    b->ran = b->ran_windows = b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts) {
+    if (!b || !counts) return fail(SNPM_E_ARG, "snpm_batch_guard_counts: NULL argument");
+    if (!b->grouped) { for (int64_t s = 0; s < b->S; ++s) counts[s] = 0; return SNPM_OK; }
+    if (!b->epilogue_done) return fail(SNPM_E_STATE, "snpm_batch_guard_counts: run the epilogue first");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    SNPM_CUDA(cudaMemcpyAsync(counts, b->d_guard.p, size_t(b->S) * 4, cudaMemcpyDeviceToHost, b->db->stream));
+    SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
+    return SNPM_OK;
+}
+
+int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows) {
+    if (!b || rows < 16 || rows > GR_MAX_CHUNK || rows % 8) return fail(SNPM_E_ARG, "snpm_batch_set_group_chunk: 16..%d rows, a multiple of 8", GR_MAX_CHUNK);
+    b->gchunk = rows;
+    return SNPM_OK;
+}
+
 int snpm_batch_destroy(snpm_batch *b) {
     if (!b) return SNPM_OK;
     cudaSetDevice(b->db->device);
@@ -356,7 +542,8 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
                       &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
-                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table};
+                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
+                      &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
@@ -391,7 +578,8 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_prefix.ensure(size_t(n + 1) * 4));
     SNPM_TRY(b->d_pair_db.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_pair_s.ensure(size_t(n) * 4));
-    SNPM_TRY(b->d_pair_w.ensure(size_t(n) * 32));
+    if (b->grouped) SNPM_TRY(b->d_pair_gid.ensure(size_t(n) * 2 + 16));
+    else SNPM_TRY(b->d_pair_w.ensure(size_t(n) * 32));
     SNPM_TRY(b->d_mstart.ensure(size_t(S + 1) * 4));
     SNPM_TRY(b->d_seg_off.ensure(size_t(S + 1) * 4));
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
@@ -400,6 +588,7 @@ static int batch_join(snpm_batch *b, int algo) {
     // auto: per-marker binary search for low-coverage samples (n << N: a tile of markers spans a long panel slice), merge-path
     // once a sample carries more than an eighth of the panel rows (measured at m = N = 10.7 M: 0.40 ms vs 0.47 ms)
     if (algo == 0) algo = (n / S) * 8 >= db->n_rows ? 2 : 1;
+    if (b->grouped) algo = 1;                                    // markers are not in position order
     const int64_t *filter = b->n_filter ? b->d_filter.as<int64_t>() : nullptr;
     if (n_tiles > 0) {
         if (algo == 2)
@@ -409,19 +598,24 @@ static int batch_join(snpm_batch *b, int algo) {
         else
             k_join_search<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
                                                             db->d_pos, db->d_chr_regions, db->n_chr, filter, b->n_filter, db->row0_global,
-                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>());
+                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>(), b->grouped ? 0 : 1);
         SNPM_KERNEL_CHECK();
         k_scan_tiles<<<1, 1024, 0, st>>>(b->d_tile_cnt.as<int32_t>(), n_tiles, b->d_tile_off.as<int32_t>(), b->d_prefix.as<int32_t>() + n);
         SNPM_KERNEL_CHECK();
-        k_scatter_pairs<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_wei.as<double>(),
-                                                          b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(),
-                                                          b->d_pair_w.as<double>());
+        if (b->grouped)
+            k_scatter_pairs_grouped<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(),
+                                                                      b->d_gid.as<uint16_t>(), b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(),
+                                                                      b->d_pair_s.as<int32_t>(), b->d_pair_gid.as<uint16_t>());
+        else
+            k_scatter_pairs<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_wei.as<double>(),
+                                                              b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(),
+                                                              b->d_pair_w.as<double>());
         SNPM_KERNEL_CHECK();
         b->launches += 3;
     } else {
         SNPM_CUDA(cudaMemsetAsync(b->d_prefix.p, 0, 4, st));
     }
-    k_sample_ranges<<<1, 1024, 0, st>>>(b->d_prefix.as<int32_t>(), b->d_off.as<int64_t>(), S, SNPM_CHUNK_ROWS, b->d_mstart.as<int32_t>(),
+    k_sample_ranges<<<1, 1024, 0, st>>>(b->d_prefix.as<int32_t>(), b->d_off.as<int64_t>(), S, b->grouped ? b->gchunk : SNPM_CHUNK_ROWS, b->d_mstart.as<int32_t>(),
                                         b->d_seg_off.as<int32_t>());
     SNPM_KERNEL_CHECK();
     b->launches += 1;
@@ -434,7 +628,8 @@ static int batch_alloc_outputs(snpm_batch *b, int64_t nseg) {
     const int64_t SA = b->S * int64_t(db->n_acc);
     SNPM_TRY(b->d_part_score.ensure(size_t(std::max<int64_t>(nseg, 1)) * a_pad * 8));
     SNPM_TRY(b->d_part_ninfo.ensure(size_t(std::max<int64_t>(nseg, 1)) * a_pad * 4));
-    SNPM_TRY(b->d_red.ensure(size_t(b->S) * (2 * size_t(db->n_acc) + 2) * 8));
+    SNPM_TRY(b->d_red.ensure(size_t(b->S) * size_t(b->red_pitch()) * 8));
+    if (b->grouped) SNPM_TRY(b->d_part_int.ensure(size_t(std::max<int64_t>(nseg, 1)) * a_pad * 4));
     SNPM_TRY(b->d_matches.ensure(size_t(SA) * 8));
     SNPM_TRY(b->d_ninfo64.ensure(size_t(SA) * 8));
     SNPM_TRY(b->d_prob.ensure(size_t(SA) * 8));
@@ -454,7 +649,9 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
     const int kernel_mode = mode & 0xff, algo = (mode >> 8) & 0xff;
-    if (kernel_mode != 0 && kernel_mode != 1) return fail(SNPM_E_ARG, "snpm_batch_run: unknown kernel mode %d", kernel_mode);
+    if (kernel_mode < 0 || kernel_mode > 2) return fail(SNPM_E_ARG, "snpm_batch_run: unknown kernel mode %d", kernel_mode);
+    if ((kernel_mode == 2) != b->grouped)
+        return fail(SNPM_E_STATE, "snpm_batch_run: kernel mode 2 scores batches uploaded with snpm_batch_upload_grouped, and only those");
     if (algo > 2) return fail(SNPM_E_ARG, "snpm_batch_run: unknown join algorithm %d", algo);
     b->launches = 0;
     for (int i = 0; i < SNPM_N_EVENTS; ++i) b->ev_rec[i] = false;
@@ -475,6 +672,48 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     a.part_score = b->d_part_score.as<double>();
     a.part_ninfo = b->d_part_ninfo.as<int32_t>();
     a.a_pad = db->stride * 32;
+    if (kernel_mode == 2) {
+        if (b->nseg_cap > 0) {
+            GroupArgs g = {};
+            g.packed = db->d_packed; g.stride = db->stride; g.pair_db = a.pair_db; g.pair_gid = b->d_pair_gid.as<uint16_t>();
+            g.table = b->d_gtable.as<double>(); g.seg_off = a.seg_off; g.mstart = a.mstart; g.S = a.S; g.chunk = b->gchunk;
+            g.part_score = a.part_score; g.part_int = b->d_part_int.as<int32_t>(); g.part_ninfo = a.part_ninfo; g.a_pad = a.a_pad;
+            const int nsl = (db->stride + GR_MAX_WX - 1) / GR_MAX_WX;
+            g.wx = (db->stride + nsl - 1) / nsl;
+            g.spc = std::min(GR_THREADS / g.wx, GR_MAX_TEAMS);
+            const size_t gsmem = size_t(g.spc) * grouped_team_smem(g.wx, g.chunk);
+            static bool gr_attr = false;
+            if (!gr_attr) {
+                SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped<true, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped<false, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                gr_attr = true;
+            }
+            dim3 ggrid(unsigned(ceil_div64(b->nseg_cap, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
+            if (g.wx == GR_MAX_WX) {              // the 1135-accession row: addresses known at compile time
+                if (skip_db_hets) k_score_grouped<true, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
+                else k_score_grouped<false, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
+            } else {
+                if (skip_db_hets) k_score_grouped<true, 0><<<ggrid, GR_THREADS, gsmem, st>>>(g);
+                else k_score_grouped<false, 0><<<ggrid, GR_THREADS, gsmem, st>>>(g);
+            }
+            SNPM_KERNEL_CHECK();
+            b->launches += 1;
+        }
+        rec(b, SNPM_EV_SCORE);
+        dim3 cgrid((db->n_acc + 127) / 128, unsigned(b->S));
+        k_combine_grouped<<<cgrid, 128, 0, st>>>(a.part_score, b->d_part_int.as<int32_t>(), a.part_ninfo, a.a_pad, db->n_acc, a.seg_off, a.mstart,
+                                                 b->d_red.as<double>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 1;
+        rec(b, SNPM_EV_COMBINE);
+        SNPM_CUDA(cudaEventRecord(b->ev_inputs_free, st));
+        b->ran = true;
+        b->ran_windows = false;
+        b->epilogue_done = false;
+        return SNPM_OK;
+    }
     if (kernel_mode == 1 && b->nseg_cap > 0) {
         // called genotypes (one-hot weights): popcount kernel, exact in every summation order
         SNPM_TRY(b->d_pair_code.ensure(size_t(std::max<int64_t>(b->n, 1))));
@@ -523,7 +762,16 @@ int snpm_batch_epilogue(snpm_batch *b) {
     snpm_db *db = b->db;
     SNPM_CUDA(cudaSetDevice(db->device));
     rec(b, SNPM_EV_EPI_START);
-    k_epilogue<<<unsigned(b->S), 1024, 0, db->stream>>>(b->d_red.as<double>(), db->n_acc, 1, 0, 0.0, b->d_matches.as<int64_t>(),
+    if (b->grouped) {
+        // totals (after any cross-GPU reduce) -> score with the reference's truncation, guard counts per sample
+        SNPM_TRY(b->d_guard.ensure(size_t(b->S) * 4));
+        SNPM_CUDA(cudaMemsetAsync(b->d_guard.p, 0, size_t(b->S) * 4, db->stream));
+        dim3 fgrid((db->n_acc + 255) / 256, unsigned(b->S));
+        k_grouped_finalize<<<fgrid, 256, 0, db->stream>>>(b->d_red.as<double>(), db->n_acc, b->d_guard.as<int32_t>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 1;
+    }
+    k_epilogue<<<unsigned(b->S), 1024, 0, db->stream>>>(b->d_red.as<double>(), b->red_pitch(), db->n_acc, 1, 0, 0.0, b->d_matches.as<int64_t>(),
                                                         b->d_ninfo64.as<int64_t>(), b->d_prob.as<double>(), b->d_L.as<double>(),
                                                         b->d_LR.as<double>());
     SNPM_KERNEL_CHECK();
@@ -586,9 +834,9 @@ int snpm_batch_timings(snpm_batch *b, float *ms, int n) {
 int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles) {
     if (!b || !dev_ptr) return fail(SNPM_E_ARG, "snpm_batch_reduce_buffer: NULL argument");
     SNPM_CUDA(cudaSetDevice(b->db->device));
-    SNPM_TRY(b->d_red.ensure(size_t(b->S) * (2 * size_t(b->db->n_acc) + 2) * 8));
+    SNPM_TRY(b->d_red.ensure(size_t(b->S) * size_t(b->red_pitch()) * 8));
     *dev_ptr = b->d_red.p;
-    if (n_doubles) *n_doubles = b->S * (2 * int64_t(b->db->n_acc) + 2);
+    if (n_doubles) *n_doubles = b->S * b->red_pitch();
     return SNPM_OK;
 }
 
@@ -599,7 +847,8 @@ int snpm_batch_fetch(snpm_batch *b, double *score, int64_t *matches, int64_t *ni
     snpm_db *db = b->db;
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
-    const size_t A = size_t(db->n_acc), S = size_t(b->S), pitch = (2 * A + 2) * 8;
+    const size_t A = size_t(db->n_acc), S = size_t(b->S), pitch = size_t(b->red_pitch()) * 8;
+    if (b->grouped && score && !b->epilogue_done) return fail(SNPM_E_STATE, "snpm_batch_fetch: grouped batches finalise their scores in the epilogue; run it first");
     const double *red = b->d_red.as<double>();
     std::vector<double> tail(2 * S);
     if (score) SNPM_CUDA(cudaMemcpy2DAsync(score, A * 8, red, pitch, A * 8, S, cudaMemcpyDeviceToHost, st));
@@ -763,7 +1012,7 @@ int snpm_calculate_likelihoods(int device, const double *scores, const double *n
         e = cudaMemcpy(d_red.p, red.data(), (2 * A + 2) * 8, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) {
             double *o = d_out.as<double>();
-            k_epilogue<<<1, 1024>>>(d_red.as<double>(), int32_t(n_acc), 0, amin_is_calc ? 0 : 1, amin, nullptr, nullptr, o, o + A, o + 2 * A);
+            k_epilogue<<<1, 1024>>>(d_red.as<double>(), 2 * int64_t(n_acc) + 2, int32_t(n_acc), 0, amin_is_calc ? 0 : 1, amin, nullptr, nullptr, o, o + A, o + 2 * A);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -845,7 +1094,7 @@ int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, c
     dim3 tgrid((A + 255) / 256, unsigned(S));
     k_onehot_totals<<<tgrid, 256, 0, st>>>(g.out_score, g.out_ninfo, ld_out, A, int32_t(K), d_red.as<double>());
     SP_CUDA(cudaGetLastError());
-    k_epilogue<<<unsigned(S), 1024, 0, st>>>(d_red.as<double>(), A, 1, 0, 0.0, d_m.as<int64_t>(), d_n64.as<int64_t>(), d_p.as<double>(),
+    k_epilogue<<<unsigned(S), 1024, 0, st>>>(d_red.as<double>(), 2 * int64_t(A) + 2, A, 1, 0, 0.0, d_m.as<int64_t>(), d_n64.as<int64_t>(), d_p.as<double>(),
                                              d_l.as<double>(), d_lr.as<double>());
     SP_CUDA(cudaGetLastError());
     SP_CUDA(cudaMemcpyAsync(score, d_m.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
@@ -867,6 +1116,7 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
     if (!b || bin_len <= 0 || n_windows < 0 || !win_count || !win_off || !kmax || kmax_len < 1)
         return fail(SNPM_E_ARG, "snpm_batch_run_windows: bad arguments");
     if (b->S != 1) return fail(SNPM_E_ARG, "snpm_batch_run_windows: windows are scored for a single-sample batch");
+    if (b->grouped) return fail(SNPM_E_STATE, "snpm_batch_run_windows: windows need the batch in position order (snpm_batch_upload)");
     snpm_db *db = b->db;
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
@@ -984,6 +1234,7 @@ int snpm_batch_f1_pairs(snpm_batch *b, const int32_t *acc_idx, int32_t n_top, do
     if (!b || !acc_idx || n_top < 2 || n_top > 4096 || !pair_score || !pair_ninfo) return fail(SNPM_E_ARG, "snpm_batch_f1_pairs: bad arguments");
     if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_f1_pairs: run the batch first");
     if (b->S != 1) return fail(SNPM_E_ARG, "snpm_batch_f1_pairs: single-sample batch expected");
+    if (b->grouped) return fail(SNPM_E_STATE, "snpm_batch_f1_pairs: needs the batch in position order (snpm_batch_upload)");
     snpm_db *db = b->db;
     for (int i = 0; i < n_top; ++i)
         if (acc_idx[i] < 0 || acc_idx[i] >= db->n_acc) return fail(SNPM_E_ARG, "snpm_batch_f1_pairs: accession index %d out of range", acc_idx[i]);

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 
 #include "../../include/snpmatch_b200.h"
 
@@ -129,6 +130,13 @@ struct snpm_batch {
     snpm::DevBuf d_f1_acc, d_f1_part, d_f1_out;
     snpm::DevBuf d_pair_code;
     snpm::DevBuf d_wei_idx, d_wei_table;
+    // grouped mode (snpm_batch_upload_grouped): markers ordered by weight triple, scored by k_score_grouped
+    bool grouped = false;
+    int32_t n_gtable = 0;
+    int32_t gchunk = 1000;
+    snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard;
+    std::vector<double> h_gtable;
+    int64_t red_pitch() const { return (grouped ? 3 : 2) * int64_t(db->n_acc) + 2; }   // doubles per sample row of d_red
     // state
     bool ran = false, ran_windows = false, epilogue_done = false;
     int launches = 0;

@@ -1,0 +1,490 @@
+// A2/A3 in "grouped" order — the throughput path of likelihood-weighted scoring (matchGTsAccs, snpmatch.py:74-89, inside the
+// chunk loop of Genotyper.genotyper, snpmatch.py:207-233).
+//
+// The reference adds, per accession, one fp64 weight per matched row: two DADDs per SNP x accession comparison once the
+// summation order is fixed, which caps an order-exact kernel at 38 % of the HBM roofline (k_score_segments, score.cuh).
+// This kernel does integer work per comparison instead.  exp(-PL/10) takes few distinct values, so the markers of a
+// sample are ordered (by the host, once, at parse time: snpm_group_markers) by their weight triple (w_ref, w_het, w_alt).
+// Inside a group every row carries the same three weights, hence
+//     score[a] = sum over groups g of  w_ref(g)*#{rows of g: d=ref} + w_alt(g)*#{d=alt} + w_het(g)*#{d=het}
+// and the per-row work is counting: a thread owns one 32-accession word column, forms the three class planes of a row
+// with one LOP3 each and adds them into bit-sliced vertical counters (Harley-Seal carry-save tree, 16 rows per step,
+// ~2.6 LOP3 per row and counter).  At a group boundary the counters are read out (8x8 bit transposes -> one byte per
+// accession) and folded into the thread's 32 fp64 accumulators with ONE fma per accession and class; classes whose weight
+// is exactly 1.0 (the called genotype of a normalised PL triple, and every one-hot weight) never touch fp64: their counts
+// go into an integer counter by a bit-sliced add.  The result is split as  score = I + F,  I an exact integer and F a sum
+// of non-negative fractional terms, which is what makes the truncated `matches = int(score)` of the reference
+// (snpmatch.py:96) reproducible without its summation order: the reference's sum is >= I and < I + F + eps, so
+// matches = I + floor(F) unless F lies within the rounding-error bound of an integer k >= 1 — those (sample, accession)
+// cells are flagged (k_grouped_finalize) and the sample is re-scored by the order-exact kernel.  fp64 scores agree with the
+// reference to a few ulp (tests: rtol 1e-12), integers bit for bit.
+//
+// Data movement: every thread fetches its own 8-byte column of the rows with cp.async (LDGSTS) into a private slot of a
+// 64-row shared-memory ring, 4 blocks of 16 rows in flight, so no barrier or mbarrier sits in the loop and ~150 KB of
+// gathers are outstanding per SM.  Measured gather ceiling for this access pattern (scripts/microbench_gather.cu):
+// 4.7-4.9 TB/s for rows in panel order, 4.3 TB/s for the weight-grouped order.
+#pragma once
+#include "common.cuh"
+#include "hardcall.cuh"
+
+namespace snpm {
+
+constexpr int GR_THREADS = 256;                       // 7 teams of 36 threads: one CTA per SM, ~240 registers per thread, no spills
+constexpr int GR_MAX_WX = 36;                         // words per team (one 1135-accession row)
+constexpr int GR_MAX_TEAMS = 7;
+constexpr int GR_BLOCK = 16;                          // rows per step
+constexpr int GR_RING = 64;                           // rows of the per-team ring
+constexpr int GR_INFLIGHT = GR_RING / GR_BLOCK;
+constexpr int GR_LP = 10;                             // planes of a counter (chunk <= 1023 rows)
+constexpr int GR_MAX_CHUNK = 1008;
+
+struct GroupArgs {
+    const uint64_t *packed;
+    int32_t stride;
+    const int32_t *pair_db;       // [m] matched local rows, grouped order
+    const uint16_t *pair_gid;     // [m] weight-triple id of every matched pair
+    const double *table;          // [T, 4] = (w_ref, w_alt, w_het, 0)
+    const int32_t *seg_off;       // [S+1]
+    const int32_t *mstart;        // [S+1]
+    int32_t S;
+    int32_t chunk;
+    double *part_score;           // [nseg, a_pad]  fractional part F of the segment
+    int32_t *part_int;            // [nseg, a_pad]  integer part I (matches of weight-1.0 classes)
+    int32_t *part_ninfo;          // [nseg, a_pad]
+    int32_t a_pad;
+    int32_t wx;                   // words per team slice
+    int32_t spc;                  // teams (segments) per CTA
+};
+
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// bit-sliced counter of 32 lanes, P planes
+template <int P>
+struct BitCounter {
+    uint32_t p[P];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < P; ++k) p[k] = 0u;
+    }
+    __device__ __forceinline__ uint32_t any() const {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int k = 0; k < P; ++k) o |= p[k];
+        return o;
+    }
+    // add sixteen 1-bit planes: 15 carry-save adders arranged as a tree (depth 8 instead of 15, for instruction-level
+    // parallelism), then the sixteens ripple upwards
+    __device__ __forceinline__ void add16(const uint32_t (&m)[16]) {
+        uint32_t c0, c1, c2, c3, c4, c5, c6, c7, s0, s1, s2, s3, s4, t0, t1;
+        SNPM_CSA(c0, s0, m[0], m[1], m[2]);
+        SNPM_CSA(c1, s1, m[3], m[4], m[5]);
+        SNPM_CSA(c2, s2, m[6], m[7], m[8]);
+        SNPM_CSA(c3, s3, m[9], m[10], m[11]);
+        SNPM_CSA(c4, s4, m[12], m[13], m[14]);
+        SNPM_CSA(c5, t0, s0, s1, s2);
+        SNPM_CSA(c6, t1, s3, s4, m[15]);
+        SNPM_CSA(c7, p[0], t0, t1, p[0]);
+        uint32_t d0, d1, d2, d3, u0, u1, u2;
+        SNPM_CSA(d0, u0, c0, c1, c2);
+        SNPM_CSA(d1, u1, c3, c4, c5);
+        SNPM_CSA(d2, u2, c6, c7, p[1]);
+        SNPM_CSA(d3, p[1], u0, u1, u2);
+        uint32_t e0, e1, v0, s;
+        SNPM_CSA(e0, v0, d0, d1, d2);
+        SNPM_CSA(e1, p[2], v0, d3, p[2]);
+        SNPM_CSA(s, p[3], e0, e1, p[3]);
+#pragma unroll
+        for (int k = 4; k < P; ++k) {
+            const uint32_t c = p[k] & s;
+            p[k] ^= s;
+            s = c;
+        }
+    }
+    // add a shorter counter (bit-sliced ripple-carry adder)
+    template <int Q>
+    __device__ __forceinline__ void add_counter(const BitCounter<Q> &o) {
+        uint32_t carry = 0u;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            if (k < Q) {
+                uint32_t h, l;
+                SNPM_CSA(h, l, p[k], o.p[k], carry);
+                p[k] = l;
+                carry = h;
+            } else {
+                const uint32_t c = p[k] & carry;
+                p[k] ^= carry;
+                carry = c;
+            }
+        }
+    }
+};
+
+// 8x8 bit transposes of the four byte columns of eight planes: afterwards byte j of r[i] holds, for lane 8j+i, the eight
+// plane bits as one number (bit k = plane k)
+__device__ __forceinline__ void transpose_planes8(uint32_t (&r)[8]) {
+#define SNPM_SWAP(a, b, s, m)                            \
+    do {                                                 \
+        const uint32_t t__ = (((a) >> (s)) ^ (b)) & (m); \
+        (b) ^= t__;                                      \
+        (a) ^= t__ << (s);                               \
+    } while (0)
+    SNPM_SWAP(r[0], r[1], 1, 0x55555555u);
+    SNPM_SWAP(r[2], r[3], 1, 0x55555555u);
+    SNPM_SWAP(r[4], r[5], 1, 0x55555555u);
+    SNPM_SWAP(r[6], r[7], 1, 0x55555555u);
+    SNPM_SWAP(r[0], r[2], 2, 0x33333333u);
+    SNPM_SWAP(r[1], r[3], 2, 0x33333333u);
+    SNPM_SWAP(r[4], r[6], 2, 0x33333333u);
+    SNPM_SWAP(r[5], r[7], 2, 0x33333333u);
+    SNPM_SWAP(r[0], r[4], 4, 0x0F0F0F0Fu);
+    SNPM_SWAP(r[1], r[5], 4, 0x0F0F0F0Fu);
+    SNPM_SWAP(r[2], r[6], 4, 0x0F0F0F0Fu);
+    SNPM_SWAP(r[3], r[7], 4, 0x0F0F0F0Fu);
+#undef SNPM_SWAP
+}
+
+// F[lane] += w * count[lane] for the 32 lanes of a class counter
+__device__ __forceinline__ void fold_counts(const BitCounter<GR_LP> &c, double w, double (&F)[32]) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = c.p[k];
+    transpose_planes8(t);
+    if ((c.p[8] | c.p[9]) == 0u) {                // fewer than 256 rows since the last read-out: the common case
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cnt = int((t[i] >> (8 * j)) & 0xffu);
+                F[8 * j + i] = fma(w, double(cnt), F[8 * j + i]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 8 * j + i;
+                const int cnt = int((t[i] >> (8 * j)) & 0xffu) | int(((c.p[8] >> b) & 1u) << 8) | int(((c.p[9] >> b) & 1u) << 9);
+                F[b] = fma(w, double(cnt), F[b]);
+            }
+        }
+    }
+}
+
+// values of a 10-plane counter for the 32 lanes
+__device__ __forceinline__ void counter_values(const BitCounter<GR_LP> &c, int32_t (&v)[32]) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = c.p[k];
+    transpose_planes8(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 8 * j + i;
+            v[b] = int32_t((t[i] >> (8 * j)) & 0xffu) | int32_t(((c.p[8] >> b) & 1u) << 8) | int32_t(((c.p[9] >> b) & 1u) << 9);
+        }
+    }
+}
+
+// shared memory of one team: ring | row numbers | triple ids | per-block weight-change masks
+__host__ __device__ __forceinline__ size_t grouped_team_smem(int wx, int chunk) {
+    const size_t n_blocks = size_t(chunk + GR_BLOCK - 1) / GR_BLOCK;
+    return size_t(GR_RING) * wx * 8 + size_t(chunk) * 4 + ((size_t(chunk) * 2 + 15) & ~size_t(15)) + ((n_blocks * 8 + 15) & ~size_t(15));
+}
+
+// grid.x = ceil(segments / teams per CTA), grid.y = word slices.  thread -> (team q, word w); a team scores one segment.
+// WX > 0: words per team known at compile time (ring addresses fold into the instructions); WX == 0: a.wx.
+template <bool SKIP_HETS, int WX>
+__global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs a) {
+    extern __shared__ __align__(16) unsigned char gr_smem[];
+    const int wx = WX ? WX : a.wx;
+    const int spc = a.spc;
+    const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
+    const int seg = blockIdx.x * spc + q;
+    const int word = blockIdx.y * wx + w;
+    const bool team_ok = q < spc && seg < a.seg_off[a.S];
+    int begin = 0, end = 0;
+    if (team_ok) {
+        int lo_s = 0, hi_s = a.S;
+        while (lo_s < hi_s) {
+            const int mid = (lo_s + hi_s + 1) >> 1;
+            if (a.seg_off[mid] <= seg) lo_s = mid; else hi_s = mid - 1;
+        }
+        begin = a.mstart[lo_s] + (seg - a.seg_off[lo_s]) * a.chunk;
+        end = min(a.mstart[lo_s + 1], begin + a.chunk);
+    }
+    const int n_rows = end - begin;
+    const int n_blocks = (n_rows + GR_BLOCK - 1) / GR_BLOCK;
+    unsigned char *team = gr_smem + size_t(q < spc ? q : 0) * grouped_team_smem(wx, a.chunk);
+    uint64_t *ring = reinterpret_cast<uint64_t *>(team);
+    int32_t *s_row = reinterpret_cast<int32_t *>(team + size_t(GR_RING) * wx * 8);
+    uint16_t *s_gid = reinterpret_cast<uint16_t *>(team + size_t(GR_RING) * wx * 8 + size_t(a.chunk) * 4);
+    // s_chg[b] = three 16-bit masks (ref | alt << 16 | het << 32): bit k set <=> the weight of that class at row 16b+k differs
+    // from the row before it (never set for the first row of the segment)
+    unsigned long long *s_chg = reinterpret_cast<unsigned long long *>(team + size_t(GR_RING) * wx * 8 + size_t(a.chunk) * 4 +
+                                                                       ((size_t(a.chunk) * 2 + 15) & ~size_t(15)));
+    if (team_ok) {
+        for (int b = w; b < n_blocks; b += wx) s_chg[b] = 0ull;
+#pragma unroll 4
+        for (int r = w; r < n_rows; r += wx) {
+            s_row[r] = __ldg(a.pair_db + begin + r);
+            s_gid[r] = __ldg(a.pair_gid + begin + r);
+        }
+    }
+    __syncthreads();
+    if (team_ok) {
+        for (int r = w + 1; r < n_rows; r += wx) {
+            const int g1 = s_gid[r], g0 = s_gid[r - 1];
+            if (g1 != g0) {
+                const double4 t1 = reinterpret_cast<const double4 *>(a.table)[g1];
+                const double4 t0 = reinterpret_cast<const double4 *>(a.table)[g0];
+                unsigned long long f = 0ull;
+                if (t1.x != t0.x) f |= 1ull << (r & 15);
+                if (t1.y != t0.y) f |= 1ull << (16 + (r & 15));
+                if (t1.z != t0.z) f |= 1ull << (32 + (r & 15));
+                if (f) atomicOr(s_chg + (r >> 4), f);
+            }
+        }
+    }
+    __syncthreads();                              // the last CTA-wide barrier: threads may leave from here on
+    if (!team_ok || word >= a.stride) return;
+
+    const uint64_t *col = a.packed + word;
+    const uint32_t my_ring = smem_u32(ring + w);
+    const uint32_t ring_pitch = uint32_t(wx) * 8u;
+    const int64_t stride = a.stride;
+    const int n_full = n_rows / GR_BLOCK;         // blocks without a ragged end
+    // queue the gathers of block b (this thread's 8-byte column of 16 rows); full blocks carry no predicates
+    auto issue = [&](int b) {
+        const int r0 = b * GR_BLOCK;
+        const uint32_t slot0 = my_ring + uint32_t(r0 & (GR_RING - 1)) * ring_pitch;
+        if (b < n_full) {
+#pragma unroll
+            for (int k4 = 0; k4 < GR_BLOCK; k4 += 4) {
+                const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
+                cp_async8(slot0 + uint32_t(k4 + 0) * ring_pitch, col + int64_t(rr.x) * stride);
+                cp_async8(slot0 + uint32_t(k4 + 1) * ring_pitch, col + int64_t(rr.y) * stride);
+                cp_async8(slot0 + uint32_t(k4 + 2) * ring_pitch, col + int64_t(rr.z) * stride);
+                cp_async8(slot0 + uint32_t(k4 + 3) * ring_pitch, col + int64_t(rr.w) * stride);
+            }
+        } else if (b < n_blocks) {
+            for (int k = 0; r0 + k < n_rows; ++k) cp_async8(slot0 + uint32_t(k) * ring_pitch, col + int64_t(s_row[r0 + k]) * stride);
+        }
+        cp_async_commit();                        // always: the wait below counts groups
+    };
+#pragma unroll
+    for (int b = 0; b < GR_INFLIGHT; ++b) issue(b);
+
+    double F[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) F[b] = 0.0;
+    BitCounter<GR_LP> c_int, c_ninfo, c_ref, c_alt, c_het;
+    c_int.clear();
+    c_ninfo.clear();
+    c_ref.clear();
+    c_alt.clear();
+    c_het.clear();
+    double w_ref, w_alt, w_het;
+    {
+        const double4 t = *reinterpret_cast<const double4 *>(a.table + 4 * size_t(s_gid[0]));
+        w_ref = t.x;
+        w_alt = t.y;
+        w_het = t.z;
+    }
+    // read a class counter out: its counts are informative sites, and matches weighted by `wt`
+    auto flush_class = [&](BitCounter<GR_LP> &c, double wt) {
+        if (c.any()) {
+            c_ninfo.add_counter(c);
+            if (wt == 1.0) c_int.add_counter(c);
+            else if (wt != 0.0) fold_counts(c, wt, F);
+            c.clear();
+        }
+    };
+    // one class: add the block's planes; where the class weight changes inside the block (bit k of `mask`: row k starts a
+    // new weight), add the rows piece by piece and read the counter out in between
+    auto add_class = [&](BitCounter<GR_LP> &c, double &wt, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, int r0) {
+        if (mask == 0u) {
+            c.add16(pl);
+            return;
+        }
+        int k0 = 0;
+        while (true) {
+            const int k1 = mask ? __ffs(mask) - 1 : GR_BLOCK;
+            if (k1 > k0) {
+                const uint32_t rm = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
+                uint32_t m[GR_BLOCK];
+#pragma unroll
+                for (int k = 0; k < GR_BLOCK; ++k) m[k] = pl[k] & uint32_t(int32_t(rm << (31 - k)) >> 31);
+                c.add16(m);
+            }
+            if (k1 >= GR_BLOCK) break;
+            flush_class(c, wt);
+            wt = a.table[4 * size_t(s_gid[r0 + k1]) + which];
+            mask &= mask - 1u;
+            k0 = k1;
+        }
+    };
+    auto score_block = [&](const uint32_t (&lo)[GR_BLOCK], const uint32_t (&hi)[GR_BLOCK], int b) {
+        const unsigned long long chg = s_chg[b];
+        uint32_t pl[GR_BLOCK];
+#pragma unroll
+        for (int k = 0; k < GR_BLOCK; ++k) pl[k] = ~(lo[k] | hi[k]);
+        add_class(c_ref, w_ref, pl, uint32_t(chg) & 0xffffu, 0, b * GR_BLOCK);
+#pragma unroll
+        for (int k = 0; k < GR_BLOCK; ++k) pl[k] = lo[k] & ~hi[k];
+        add_class(c_alt, w_alt, pl, uint32_t(chg >> 16) & 0xffffu, 1, b * GR_BLOCK);
+        if (!SKIP_HETS) {                         // snpmatch.py:78-79: masked hets match nothing and are not informative
+#pragma unroll
+            for (int k = 0; k < GR_BLOCK; ++k) pl[k] = hi[k] & ~lo[k];
+            add_class(c_het, w_het, pl, uint32_t(chg >> 32) & 0xffffu, 2, b * GR_BLOCK);
+        }
+    };
+
+    for (int b = 0; b < n_full; ++b) {
+        cp_async_wait<GR_INFLIGHT - 1>();         // block b has landed (this thread's own copies)
+        const uint64_t *slot = ring + size_t((b * GR_BLOCK) & (GR_RING - 1)) * wx + w;
+        uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
+#pragma unroll
+        for (int k = 0; k < GR_BLOCK; ++k) {
+            const uint64_t v = slot[size_t(k) * wx];
+            lo[k] = uint32_t(v);
+            hi[k] = uint32_t(v >> 32);
+        }
+        score_block(lo, hi, b);
+        issue(b + GR_INFLIGHT);                   // refill the slots of this block
+    }
+    if (n_full < n_blocks) {                      // ragged last block: rows past the end read as missing everywhere
+        cp_async_wait<0>();
+        const int r0 = n_full * GR_BLOCK;
+        const uint64_t *slot = ring + size_t(r0 & (GR_RING - 1)) * wx + w;
+        uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
+#pragma unroll
+        for (int k = 0; k < GR_BLOCK; ++k) {
+            uint64_t v = ~0ull;
+            if (r0 + k < n_rows) v = slot[size_t(k) * wx];
+            lo[k] = uint32_t(v);
+            hi[k] = uint32_t(v >> 32);
+        }
+        score_block(lo, hi, n_full);
+    }
+    flush_class(c_ref, w_ref);
+    flush_class(c_alt, w_alt);
+    if (!SKIP_HETS) flush_class(c_het, w_het);
+
+    int32_t vi[32], vn[32];
+    counter_values(c_int, vi);
+    counter_values(c_ninfo, vn);
+    const int64_t o = int64_t(seg) * a.a_pad + int64_t(word) * 32;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+        a.part_score[o + b] = F[b];
+        a.part_int[o + b] = vi[b];
+        a.part_ninfo[o + b] = vn[b];
+    }
+}
+
+// ---- compaction for the grouped order -------------------------------------------------------------
+// as k_scatter_pairs (join.cuh) but the payload of a pair is its weight-triple id
+__global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_grouped(
+        const int32_t *__restrict__ match_row, int64_t n, const int32_t *__restrict__ tile_off, const uint16_t *__restrict__ gid,
+        int32_t *__restrict__ prefix, int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s, uint16_t *__restrict__ pair_gid) {
+    __shared__ int s_warp[33];
+    const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
+    const int32_t row = i < n ? match_row[i] : -1;
+    const int flag = row >= 0;
+    int total;
+    const int ex = block_excl_scan(flag, &total, s_warp);
+    if (i < n) {
+        const int32_t p = tile_off[blockIdx.x] + ex;
+        prefix[i] = p;
+        if (flag) {
+            pair_db[p] = row;
+            pair_s[p] = int32_t(i);
+            pair_gid[p] = gid[i];
+        }
+    }
+}
+
+// chromosome ids travel as one byte (255 = not in the panel)
+__global__ void __launch_bounds__(256) k_expand_chrom(const uint8_t *__restrict__ c8, int64_t n, int32_t *__restrict__ c32) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) c32[i] = c8[i] == 255 ? -1 : int32_t(c8[i]);
+}
+
+// ---- combine: totals of the segment partials of one sample ----------------------------------------------
+// red row layout in grouped mode [3*n_acc + 2]: F[n_acc] | ninfo[n_acc] | matched pairs | y>n violations | I[n_acc]
+// (the first 2*n_acc + 2 entries are laid out as in k_combine; k_grouped_finalize turns F into the score in place)
+__global__ void __launch_bounds__(128) k_combine_grouped(const double *__restrict__ part_score, const int32_t *__restrict__ part_int,
+                                                         const int32_t *__restrict__ part_ninfo, int32_t a_pad, int32_t n_acc,
+                                                         const int32_t *__restrict__ seg_off, const int32_t *__restrict__ mstart,
+                                                         double *__restrict__ red) {
+    const int s = blockIdx.y;
+    const int acc = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j0 = seg_off[s], j1 = seg_off[s + 1];
+    double *row = red + int64_t(s) * (3 * int64_t(n_acc) + 2);
+    if (acc < n_acc) {
+        double f = 0.0;
+        long long ii = 0, ni = 0;
+        constexpr int CB = 8;
+        int j = j0;
+        for (; j + CB <= j1; j += CB) {
+            double v[CB];
+            int32_t ci[CB], cn[CB];
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                v[k] = __ldg(part_score + int64_t(j + k) * a_pad + acc);
+                ci[k] = __ldg(part_int + int64_t(j + k) * a_pad + acc);
+                cn[k] = __ldg(part_ninfo + int64_t(j + k) * a_pad + acc);
+            }
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                f += v[k];
+                ii += ci[k];
+                ni += cn[k];
+            }
+        }
+        for (; j < j1; ++j) {
+            f += part_score[int64_t(j) * a_pad + acc];
+            ii += part_int[int64_t(j) * a_pad + acc];
+            ni += part_ninfo[int64_t(j) * a_pad + acc];
+        }
+        row[acc] = f;
+        row[n_acc + acc] = double(ni);
+        row[2 * n_acc + 2 + acc] = double(ii);
+    }
+    if (acc == 0) {
+        row[2 * n_acc] = double(mstart[s + 1] - mstart[s]);
+        row[2 * n_acc + 1] = 0.0;
+    }
+}
+
+// score = I + F with the reference's truncation made explicit: matches = I + floor(F) (see the header).  The score is
+// stored so that the epilogue's int(score) gives exactly that, and cells whose F lies within the summation-error bound of
+// an integer k >= 1 are counted in guard[s]: for them the reference's own rounding decides, so the caller re-scores the
+// sample in reference order.  Runs after the cross-GPU reduce, on totals.
+__global__ void __launch_bounds__(256) k_grouped_finalize(double *__restrict__ red, int32_t n_acc, int32_t *__restrict__ guard) {
+    const int s = blockIdx.y;
+    const int acc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (acc >= n_acc) return;
+    double *row = red + int64_t(s) * (3 * int64_t(n_acc) + 2);
+    const double f = row[acc], ii = row[2 * n_acc + 2 + acc], m = row[2 * n_acc];
+    // |reference - exact| <= (1000 + 2 + m/1000) u (I+F) for its chunked sequential sums, the same bound holds
+    // for the sums above; u = 2^-53.  Factor 4 covers both plus slack.
+    const double depth = 1010.0 + m * (1.0 / 500.0);
+    const double g = 4.0 * depth * 1.1102230246251565e-16 * (ii + f + 1.0);
+    const double k = rint(f);
+    if (k >= 1.0 && fabs(f - k) <= g) atomicAdd(guard + s, 1);
+    const double want = ii + floor(f);
+    double v = ii + f;
+    if (floor(v) != want) v = __longlong_as_double(__double_as_longlong(want + 1.0) - 1);   // largest double below want + 1
+    row[acc] = v;
+}
+
+}  // namespace snpm

@@ -57,11 +57,12 @@ __global__ void __launch_bounds__(JOIN_TILE) k_join_search(
         const int64_t *__restrict__ off, int64_t S,
         const int32_t *__restrict__ db_pos, const int64_t *__restrict__ chr_regions, int32_t n_chr,
         const int64_t *__restrict__ filter, int64_t n_filter, int64_t row0_global,
-        int32_t *__restrict__ match_row, int32_t *__restrict__ tile_cnt, int *status) {
+        int32_t *__restrict__ match_row, int32_t *__restrict__ tile_cnt, int *status, int check) {
+    // check == 0: markers are in weight-grouped order (snpm_batch_upload_grouped); the search does not need an order
     const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
     int32_t row = -1;
     if (i < n) {
-        check_order(chrom, pos, off, S, i, status);
+        if (check) check_order(chrom, pos, off, S, i, status);
         const int32_t c = chrom[i];
         if (c >= 0 && c < n_chr) {
             const int64_t rs = chr_regions[2 * c], re = chr_regions[2 * c + 1];

@@ -438,13 +438,14 @@ __device__ __forceinline__ double block_nanmin(double v, double *s_red /*[32]*/)
 
 // One CTA per sample row of `red`.  truncate != 0: y = int(score) first (GenotyperOutput.__init__,
 // snpmatch.py:96).  amin_mode 0: TopHit = nanmin(L); 1: TopHit = amin.
-__global__ void __launch_bounds__(1024) k_epilogue(double *__restrict__ red, int32_t n_acc, int truncate, int amin_mode, double amin,
+// `pitch` = doubles per sample row of `red` (2*n_acc + 2, or 3*n_acc + 2 for grouped batches; the first 2*n_acc + 2 are used).
+__global__ void __launch_bounds__(1024) k_epilogue(double *__restrict__ red, int64_t pitch, int32_t n_acc, int truncate, int amin_mode, double amin,
                                                    int64_t *__restrict__ matches, int64_t *__restrict__ ninfo64,
                                                    double *__restrict__ prob, double *__restrict__ L, double *__restrict__ LR) {
     __shared__ double s_red[32];
     __shared__ int s_viol;
     const int s = blockIdx.x;
-    double *row = red + int64_t(s) * (2 * int64_t(n_acc) + 2);
+    double *row = red + int64_t(s) * pitch;
     if (threadIdx.x == 0) s_viol = 0;
     __syncthreads();
     double lmin = nan("");

@@ -19,11 +19,12 @@ SNPM_E_CUDA = -2
 SNPM_E_NOMEM = -3
 SNPM_E_STATE = -4
 SNPM_E_ASSERT = -5
+SNPM_E_RANGE = -6
 
 CHUNK_ROWS = 1000
 
 JOIN_AUTO, JOIN_SEARCH, JOIN_MERGEPATH = 0, 1, 2
-KERNEL_FP64, KERNEL_POPCOUNT = 0, 1
+KERNEL_FP64, KERNEL_POPCOUNT, KERNEL_GROUPED = 0, 1, 2
 
 
 def weights_are_one_hot(wei):
@@ -44,6 +45,44 @@ def index_weights(wei):
     if len(table) > 65536:
         return None
     return inv.astype(np.uint16).reshape(w.shape), table.view(np.float64)
+
+
+class GroupedSamples(object):
+    """Samples prepared for the grouped kernel (snpm_group_markers): every sample's markers ordered by weight triple.
+    offsets int64 [S+1]; chrom uint8 [n] (255 = not in the panel); pos int32 [n]; gid uint16 [n]; table f64 [T,3] in the
+    column order of `wei`; order int64 [n] = index of each marker in the arrays it was built from."""
+
+    def __init__(self, offsets, chrom, pos, gid, table, order):
+        self.offsets, self.chrom, self.pos, self.gid, self.table, self.order = offsets, chrom, pos, gid, table, order
+        self.n_samples = len(offsets) - 1
+
+    @property
+    def h2d_bytes(self):
+        return int(self.offsets.nbytes + self.chrom.nbytes + self.pos.nbytes + self.gid.nbytes + self.table.size // 3 * 32)
+
+
+def group_markers(offsets, s_chrom_id, s_pos, wei, table_cap=65536):
+    """Order the markers of every sample by their weight triple (host code of the library, run once at parse time).
+    Returns a GroupedSamples, or None when the weights do not qualify (more than 65536 distinct triples, a chromosome id
+    above 254, negative / non-finite weights): score such samples in position order."""
+    offsets = as_c(offsets, np.int64)
+    s_chrom_id = as_c(s_chrom_id, np.int32)
+    s_pos = as_c(s_pos, np.int32)
+    wei = as_c(wei, np.float64).reshape(-1, 3)
+    n = int(offsets[-1])
+    assert len(s_chrom_id) == len(s_pos) == len(wei) == n
+    chrom = np.empty(max(n, 1), np.uint8)
+    pos = np.empty(max(n, 1), np.int32)
+    gid = np.empty(max(n, 1), np.uint16)
+    order = np.empty(max(n, 1), np.int64)
+    table = np.empty((int(table_cap), 3), np.float64)
+    nt = C.c_int32(0)
+    rc = load().snpm_group_markers(len(offsets) - 1, ptr(offsets), ptr(s_chrom_id), ptr(s_pos), ptr(wei), ptr(chrom), ptr(pos),
+                                   ptr(gid), ptr(order), ptr(table), int(table_cap), C.byref(nt))
+    if rc in (SNPM_E_RANGE, SNPM_E_ARG):
+        return None
+    check(rc)
+    return GroupedSamples(offsets, chrom[:n], pos[:n], gid[:n], np.ascontiguousarray(table[:max(nt.value, 1)]), order[:n])
 
 
 class SnpmError(RuntimeError):
@@ -85,6 +124,10 @@ SIGNATURES = {
     "snpm_batch_upload": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "snpm_batch_upload_indexed": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
     "snpm_batch_destroy": (C.c_int, [_p]),
+    "snpm_group_markers": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
+    "snpm_batch_upload_grouped": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
+    "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
+    "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
     "snpm_batch_set_row_filter": (C.c_int, [_p, _p, _i64]),
     "snpm_batch_run": (C.c_int, [_p, C.c_int, C.c_int]),
     "snpm_batch_epilogue": (C.c_int, [_p]),
@@ -300,6 +343,24 @@ class Batch(object):
         check(load().snpm_batch_upload_indexed(self._h, self.n_samples, ptr(offsets), ptr(s_chrom_id), ptr(s_pos), ptr(wei_idx),
                                                ptr(table), len(table)))
 
+    def upload_grouped(self, g):
+        """Replace the batch's samples by grouped ones (GroupedSamples); score them with run(kernel_mode=KERNEL_GROUPED)."""
+        self.n_samples = g.n_samples
+        self.offsets = g.offsets
+        self._keep = (g,)
+        check(load().snpm_batch_upload_grouped(self._h, g.n_samples, ptr(g.offsets), ptr(g.chrom), ptr(g.pos), ptr(g.gid),
+                                               ptr(g.table), len(g.table)))
+
+    def set_group_chunk(self, rows):
+        check(load().snpm_batch_set_group_chunk(self._h, int(rows)))
+
+    def guard_counts(self):
+        """Per sample: accessions whose int(score) depends on the reference's summation order (grouped batches; see
+        snpm_batch_guard_counts).  Re-score those samples with the fp64 kernel."""
+        out = np.zeros(self.n_samples, dtype=np.int32)
+        check(load().snpm_batch_guard_counts(self._h, ptr(out)))
+        return out
+
     def close(self):
         if getattr(self, "_scratch", False):
             return                                  # owned by the Database
@@ -416,3 +477,43 @@ def calculate_likelihoods(scores, ninfo, amin="calc", device=0):
     check(load().snpm_calculate_likelihoods(device, ptr(scores), ptr(ninfo), n, int(calc), 0.0 if calc else float(amin),
                                             ptr(prob), ptr(lik), ptr(lr)))
     return prob, lik, lr
+
+
+def score_grouped(db, offsets, s_chrom_id, s_pos, wei, skip_db_hets=False, grouped=None, batch=None):
+    """Throughput scoring of many samples (Genotyper.genotyper per sample, snpmatch.py:207-233) with the grouped kernel:
+    returns the dict of Batch.fetch().  Samples whose truncated score would depend on the reference's summation order
+    (guard_counts > 0, ~1e-7 per accession) are re-scored with the order-exact fp64 kernel, so `matches` is always the
+    reference's.  Falls back to the fp64 kernel for every sample when the weights do not qualify for grouping."""
+    offsets = as_c(offsets, np.int64)
+    s_chrom_id = as_c(s_chrom_id, np.int32)
+    s_pos = as_c(s_pos, np.int32)
+    wei = as_c(wei, np.float64).reshape(-1, 3)
+    g = grouped if grouped is not None else group_markers(offsets, s_chrom_id, s_pos, wei)
+    own = batch is None
+    b = batch if batch is not None else Batch(db, [0, 0], np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)))
+    try:
+        if g is None:
+            b.upload(offsets, s_chrom_id, s_pos, wei)
+            b.run(skip_db_hets)
+            b.epilogue()
+            r = b.fetch()
+            r["rescored"] = np.arange(len(offsets) - 1)
+            return r
+        b.upload_grouped(g)
+        b.run(skip_db_hets, kernel_mode=KERNEL_GROUPED)
+        b.epilogue()
+        r = b.fetch()
+        flagged = np.flatnonzero(b.guard_counts())
+        r["rescored"] = flagged
+        for s in flagged:
+            lo, hi = int(offsets[s]), int(offsets[s + 1])
+            b.upload([0, hi - lo], s_chrom_id[lo:hi], s_pos[lo:hi], wei[lo:hi])
+            b.run(skip_db_hets)
+            b.epilogue()
+            one = b.fetch()
+            for k in ("score", "matches", "ninfo", "prob", "L", "LR", "m"):
+                r[k][s] = one[k][0]
+        return r
+    finally:
+        if own:
+            b.close()

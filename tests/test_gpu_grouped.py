@@ -1,0 +1,214 @@
+"""Parity of the grouped counting kernel (k_score_grouped, kernel mode 2) — the throughput path of likelihood-weighted
+scoring — against the CPU oracle and against the order-exact fp64 kernel.
+
+Bars: matches = int(score), ninfo, matched pairs bit-exact; fp64 scores within rtol 1e-12 of the reference-order sum
+(they are bit-exact when every weight is 0/1); probabilities bit-exact (ratios of exact integers); likelihoods and
+ratios rtol 1e-9 (north star asks 1e-6)."""
+import numpy as np
+import pytest
+
+from oracle import snpmatch_oracle as orc
+from snpmatch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+SCORE_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from snpmatch_b200 import lib as L
+    assert L.device_count() > 0, "GPU tests need a CUDA device"
+    return L
+
+
+def _concat(samples, wei_key="wei"):
+    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])])
+    return (offs, np.concatenate([s["chr_ix"] for s in samples]), np.concatenate([s["pos"] for s in samples]),
+            np.concatenate([s[wei_key] for s in samples]))
+
+
+def _oracle_sample(db_idx, s_idx, wei, n_acc, skip=False):
+    """Genotyper.genotyper's chunk loop (snpmatch.py:218-225) on the panel rows of the matched pairs."""
+    codes = synth.panel_codes(synth.SEED_PANEL, db_idx, n_acc)
+    score, ninfo = np.zeros(n_acc), np.zeros(n_acc, dtype=np.int64)
+    for j in range(0, len(db_idx), 1000):
+        t_s, t_n = orc.match_gts_accs(wei[s_idx[j:j + 1000]], codes[j:j + 1000].copy(), skip)
+        score, ninfo = score + t_s, ninfo + t_n
+    return score, ninfo
+
+
+def _check_against(r, ref, i, exact_scores=False):
+    assert np.array_equal(r["matches"][i], ref["matches"]), "matches differ"
+    assert np.array_equal(r["ninfo"][i], ref["ninfo"]), "ninfo differs"
+    assert int(r["m"][i]) == int(ref["m"])
+    if exact_scores:
+        assert np.array_equal(r["score"][i], ref["score"])
+    else:
+        np.testing.assert_allclose(r["score"][i], ref["score"], rtol=SCORE_RTOL, atol=0)
+    np.testing.assert_array_equal(r["prob"][i], ref["prob"])
+    np.testing.assert_allclose(r["L"][i], ref["L"], rtol=RTOL, equal_nan=True)
+    np.testing.assert_allclose(r["LR"][i], ref["LR"], rtol=RTOL, equal_nan=True)
+
+
+@pytest.mark.parametrize("n_acc", [1135, 33, 2100])
+@pytest.mark.parametrize("skip", [False, True])
+def test_grouped_kernel_vs_oracle_and_exact_kernel(lib, n_acc, skip):
+    n_rows = 70000
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    sizes = [(2500, 200), (0, 50), (999, 0), (1000, 1), (1001, 7), (4321, 300), (1, 0), (17, 3), (20000, 1000)]
+    samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=(3 + 11 * i) % n_acc, n_db=nd, n_extra=ne,
+                                 seed=1900 + i, het=0.05) for i, (nd, ne) in enumerate(sizes)]
+    offs, chrom, p, wei = _concat(samples)
+    # order-exact kernel (bit-exact against the oracle, tests/test_gpu_parity.py)
+    b = lib.Batch(db, offs, chrom, p, wei)
+    b.run(skip_db_hets=skip)
+    b.epilogue()
+    exact = {k: v.copy() for k, v in b.fetch().items()}
+    pairs = [b.fetch_pairs(i) for i in range(len(samples))]
+    # grouped kernel
+    g = lib.group_markers(offs, chrom, p, wei)
+    assert g is not None and len(g.table) < 5000
+    for chunk in (1000, 16, 208, 1008):
+        b.set_group_chunk(chunk)
+        b.upload_grouped(g)
+        b.run(skip_db_hets=skip, kernel_mode=lib.KERNEL_GROUPED)
+        b.epilogue()
+        r = b.fetch()
+        guard = b.guard_counts()
+        for i, s in enumerate(samples):
+            if guard[i]:
+                continue                # int(score) is decided by the reference's rounding: such samples are re-scored (below)
+            _check_against(r, {k: exact[k][i] for k in exact}, i)
+    assert guard.sum() <= 1
+    # oracle, directly, for three samples
+    for i in (0, 5, 8):
+        ref_s, ref_n = _oracle_sample(pairs[i][0], pairs[i][1], samples[i]["wei"], n_acc, skip)
+        lik, lr = orc.calculate_likelihoods(ref_s.astype(np.int64), ref_n)
+        assert np.array_equal(r["matches"][i], ref_s.astype(np.int64)) and np.array_equal(r["ninfo"][i], ref_n)
+        np.testing.assert_allclose(r["score"][i], ref_s, rtol=SCORE_RTOL)
+        np.testing.assert_allclose(r["L"][i], lik, rtol=RTOL, equal_nan=True)
+        np.testing.assert_allclose(r["LR"][i], lr, rtol=RTOL, equal_nan=True)
+    if n_acc > 100:
+        assert int(np.nanargmin(r["L"][8])) == (3 + 11 * 8) % n_acc
+    # the matched pairs of a grouped batch are the same set
+    db_idx, s_idx = b.fetch_pairs(5)
+    assert np.array_equal(np.sort(db_idx), pairs[5][0])
+    assert np.array_equal(pos[db_idx].astype(np.int64), g.pos[int(offs[5]):int(offs[6])][s_idx])
+    b.close()
+    db.close()
+
+
+def test_grouped_called_genotypes_are_exact(lib):
+    """One-hot weights: every score is an integer count, F stays 0 and the result equals the popcount kernel bit for bit."""
+    n_rows, n_acc = 50000, 1135
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=5 + 7 * i, n_db=nd, n_extra=ne, seed=2700 + i, het=0.05)
+               for i, (nd, ne) in enumerate([(3333, 100), (1, 0), (1000, 10), (2049, 5), (0, 3)])]
+    offs, chrom, p, wei = _concat(samples, "wei_hard")
+    b = lib.Batch(db, offs, chrom, p, wei)
+    b.run(kernel_mode=lib.KERNEL_POPCOUNT)
+    b.epilogue()
+    ref = {k: v.copy() for k, v in b.fetch().items()}
+    g = lib.group_markers(offs, chrom, p, wei)
+    assert len(g.table) == 3
+    b.upload_grouped(g)
+    b.run(kernel_mode=lib.KERNEL_GROUPED)
+    b.epilogue()
+    r = b.fetch()
+    assert b.guard_counts().sum() == 0
+    for k in ("score", "matches", "ninfo", "m", "prob", "L", "LR"):
+        assert np.array_equal(r[k], ref[k], equal_nan=True), k
+    # a grouped batch refuses the other kernels, windows and the F1 pass
+    with pytest.raises(lib.SnpmError):
+        b.run(kernel_mode=lib.KERNEL_FP64)
+    b.close()
+    db.close()
+
+
+def test_grouped_unusual_weight_triples(lib):
+    """Triples with two exact ones, no one at all, zeros, values above one, and a group longer than the 255-row counters."""
+    n_rows, n_acc = 30000, 300
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    rng = np.random.default_rng(77)
+    s = synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=9, n_db=6000, n_extra=100, seed=31, het=0.05)
+    n = len(s["pos"])
+    menu = np.array([[1.0, 1.0, 0.25], [0.3, 0.2, 0.7], [0.0, 0.0, 0.0], [2.5, 1.0, 0.0], [1.0, 0.0, 1e-30], [1e-300, 0.125, 1.0],
+                     [0.9999999999999999, 1.0000000000000002, 1.0]])
+    pick = rng.choice(len(menu), size=n, p=[0.05, 0.6, 0.05, 0.05, 0.1, 0.05, 0.1])
+    wei = menu[pick]
+    offs = np.array([0, n])
+    b = lib.Batch(db, offs, s["chr_ix"], s["pos"], wei)
+    b.run()
+    b.epilogue()
+    exact = {k: v.copy() for k, v in b.fetch().items()}
+    r = lib.score_grouped(db, offs, s["chr_ix"], s["pos"], wei, batch=b)
+    _check_against(r, {k: exact[k][0] for k in exact}, 0)
+    b.close()
+    db.close()
+
+
+def test_grouped_guard_band_triggers_rescoring(lib):
+    """Weights of exactly 0.5 make F an exact integer for every accession with an even count: the guard cannot tell that
+    from a rounding accident, flags the sample, and score_grouped re-scores it with the order-exact kernel."""
+    n_rows, n_acc = 20000, 200
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    s0 = synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=4, n_db=3000, n_extra=10, seed=41)
+    s1 = synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=8, n_db=2000, n_extra=10, seed=42)
+    w1 = np.where(s1["wei_hard"] == 1.0, 1.0, 0.5)
+    offs = np.array([0, len(s0["pos"]), len(s0["pos"]) + len(s1["pos"])])
+    chrom = np.concatenate([s0["chr_ix"], s1["chr_ix"]])
+    p = np.concatenate([s0["pos"], s1["pos"]])
+    wei = np.concatenate([s0["wei"], w1])
+    b = lib.Batch(db, offs, chrom, p, wei)
+    b.run()
+    b.epilogue()
+    exact = {k: v.copy() for k, v in b.fetch().items()}
+    g = lib.group_markers(offs, chrom, p, wei)
+    b.upload_grouped(g)
+    b.run(kernel_mode=lib.KERNEL_GROUPED)
+    b.epilogue()
+    raw = b.fetch()
+    guard = b.guard_counts()
+    assert guard[1] > 0
+    # even unre-scored, the grouped integers are right here (0.5 sums are exact in any order)
+    assert np.array_equal(raw["matches"][1], exact["matches"][1])
+    r = lib.score_grouped(db, offs, chrom, p, wei, batch=b)
+    assert 1 in set(r["rescored"].tolist())
+    for i in (0, 1):
+        _check_against(r, {k: exact[k][i] for k in exact}, i, exact_scores=(i in set(r["rescored"].tolist())))
+    b.close()
+    db.close()
+
+
+def test_grouped_full_shape_properties(lib):
+    """BASELINE configs[1] shape (10.7 M x 1135 panel, 50 k-marker PL samples): size-independent properties — the grouped and
+    the order-exact kernels agree on every integer for 4 samples, the true accessions are recovered, ninfo <= matched rows."""
+    n_rows, n_acc = 10_700_000, 1135
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    samples = [synth.make_sample_fast(pos, regions, n_acc, true_acc=7 + 13 * i, n_db=45000, n_extra=5000, seed=5000 + i) for i in range(4)]
+    offs, chrom, p, wei = _concat(samples)
+    r = lib.score_grouped(db, offs, chrom, p, wei)
+    b = lib.Batch(db, offs, chrom, p, wei)
+    b.run()
+    b.epilogue()
+    exact = b.fetch()
+    for i in range(4):
+        _check_against(r, {k: exact[k][i] for k in exact}, i, exact_scores=(i in set(r["rescored"].tolist())))
+        assert int(np.nanargmin(r["L"][i])) == 7 + 13 * i
+        assert r["ninfo"][i].max() <= r["m"][i] == 45000
+    b.close()
+    db.close()

@@ -142,3 +142,35 @@ def test_parsers_on_the_reference_sample_files(tmp_path, golden_outputs):
     assert os.path.isfile(str(bed) + ".snpmatch.npz") and os.path.isfile(str(bed) + ".snpmatch.stats.json")
     again = parsers.ParseInputs(str(bed))                                    # npz cache path
     assert np.array_equal(again.pos, b.pos) and np.array_equal(again.wei, b.wei)
+
+
+def test_group_markers_host_preparation(built_lib):
+    """snpm_group_markers (host code of the library): stable order by weight triple, one-byte chromosome ids, exact table."""
+    lib = built_lib
+    rng = np.random.default_rng(5)
+    n0, n1 = 500, 300
+    offs = np.array([0, n0, n0 + n1])
+    chrom = np.concatenate([np.sort(rng.integers(-1, 5, size=n0)), np.sort(rng.integers(0, 5, size=n1))]).astype(np.int32)
+    pos = np.arange(n0 + n1, dtype=np.int32) * 7 + 3
+    menu = np.exp(-rng.integers(0, 40, size=(12, 3)) / 10.0)
+    menu[:, 0] = 1.0
+    wei = menu[rng.integers(0, 12, size=n0 + n1)]
+    g = lib.group_markers(offs, chrom, pos, wei)
+    assert g is not None and len(g.table) <= 12 and g.table.shape[1] == 3
+    # table[gid] reproduces the weights bit for bit; markers of a sample stay inside it; order is (gid, input order)
+    assert np.array_equal(g.table[g.gid], wei[g.order])
+    assert np.array_equal(g.pos, pos[g.order])
+    assert np.array_equal(g.chrom, np.where(chrom[g.order] < 0, 255, chrom[g.order]).astype(np.uint8))
+    for s in range(2):
+        lo, hi = offs[s], offs[s + 1]
+        assert np.array_equal(np.sort(g.order[lo:hi]), np.arange(lo, hi))
+        key = g.gid[lo:hi].astype(np.int64) * (n0 + n1) + g.order[lo:hi]
+        assert np.all(np.diff(key) > 0)
+    # inputs the grouped kernel cannot take
+    bad = wei.copy()
+    bad[3, 1] = -0.5
+    assert lib.group_markers(offs, chrom, pos, bad) is None
+    bad[3, 1] = np.nan
+    assert lib.group_markers(offs, chrom, pos, bad) is None
+    assert lib.group_markers(offs, chrom, pos, rng.random((n0 + n1, 3)), table_cap=100) is None
+    assert lib.group_markers(offs, np.full(n0 + n1, 300, np.int32), pos, wei) is None
