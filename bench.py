@@ -12,7 +12,8 @@ samples, each scored on its own exactly as separate `snpmatch inbred` runs would
              stream the kernels run on, max over ranks);
   e2e        the same through the host-buffer API: per step the H2D copy of the samples from pinned
              memory and the D2H read of scores / counts / likelihoods are inside the timed region;
-  roofline   the scoring kernel (k_score_segments): algorithmic bytes per launch / its CUDA-event time;
+  roofline   the scoring kernel (k_score_grouped, the grouped counting kernel): algorithmic bytes per launch / its
+             CUDA-event time; the order-exact fp64 kernel (k_score_segments) is reported next to it;
   cpu_baseline  the CPU oracle (a NumPy restatement of the reference path) on one sample, one core.
 
 N > 1 (torchrun): the panel is sharded by SNP-row ranges, samples are replicated, per-GPU partial
@@ -55,6 +56,7 @@ def parse_args():
     ap.add_argument("--accessions", type=int, default=N_ACC)
     ap.add_argument("--markers", type=int, default=N_DB_MARKERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--group-chunk", type=int, default=480, help="rows per segment of the grouped kernel")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     return ap.parse_args()
 
@@ -65,7 +67,7 @@ def workload_config(args, n_gpus, n_samples):
                     "synthetic 1001G-shaped panel %d accessions x %d SNPs" % (
                         n_samples, args.markers + N_EXTRA_MARKERS, args.markers, args.accessions, args.rows),
         "panel_rows": args.rows, "accessions": args.accessions, "samples_per_step": n_samples,
-        "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)",
+        "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)", "kernel": "grouped counting kernel (markers ordered by weight triple at parse time)",
         "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + NCCL all-reduce of per-accession partials" % n_gpus,
         "cache": "inputs larger than L2: each step gathers %.0f MB of distinct panel rows" % (
             n_samples * args.markers * ((args.accessions + 63) // 64 * 16) / 1e6),
@@ -288,13 +290,28 @@ def run_b200_arm(args):
     out_t["m"] = torch.empty(S, dtype=torch.int64).pin_memory()
     out = {k: v.numpy() for k, v in out_t.items()}
 
-    batch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
+    batch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)       # position order: the order-exact fp64 kernel
+    # grouped order (done once, at parse time): markers of every sample ordered by weight triple -> counting kernel
+    t_group = time.perf_counter()
+    gs_raw = lib.group_markers(h_off, h_chr, h_pos, h_wei)
+    t_group = time.perf_counter() - t_group
+    assert gs_raw is not None, "the synthetic PL weights qualify for the grouped kernel"
+    g_arrs = []
+    for a in (gs_raw.chrom, gs_raw.pos, gs_raw.gid, gs_raw.table):
+        t, v = pinned(a)
+        keep.append(t)
+        g_arrs.append(v)
+    gs = lib.GroupedSamples(h_off, g_arrs[0], g_arrs[1], g_arrs[2], g_arrs[3], gs_raw.order)
+    gbatch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
+    gbatch.set_group_chunk(args.group_chunk)
+    gbatch.upload_grouped(gs)
 
-    def device_step():
-        batch.run()
+    def device_step(b=None, mode=None):
+        b = gbatch if b is None else b
+        b.run(kernel_mode=lib.KERNEL_GROUPED if b is gbatch else lib.KERNEL_FP64)
         if world > 1:
-            sharding.allreduce_batch(batch, dist, dev)      # one NCCL all-reduce of [S, 2A+2] f64
-        batch.epilogue()
+            sharding.allreduce_batch(b, dist, dev)          # one NCCL all-reduce of the per-sample totals
+        b.epilogue()
 
     def barrier():
         if world > 1:
@@ -306,7 +323,7 @@ def run_b200_arm(args):
         # ---- resident arm -------------------------------------------------------------------------
         for _ in range(args.warmup):
             device_step()
-        batch.wait()
+        gbatch.wait()
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -316,15 +333,38 @@ def run_b200_arm(args):
         for _ in range(args.steps):
             device_step()
         ev1.record(stream)
-        batch.wait()
+        gbatch.wait()
         barrier()
         dev_ms = ev0.elapsed_time(ev1)
         # per-kernel times of the scoring kernel: one more timed pass that reads the library's own events each step
+        stage_ms = {}
         for _ in range(args.steps):
             device_step()
-            t = batch.timings()
+            t = gbatch.timings()
             score_ms.append(t["score_ms"])
+            for k, v in t.items():
+                stage_ms.setdefault(k, []).append(v)
             total_launches = t["launches"]
+        guard_resident = gbatch.guard_counts()
+        barrier()
+        # ---- the order-exact fp64 kernel on the same samples (position order), for comparison
+        exact_kernel_ms = []
+        for _ in range(args.warmup):
+            device_step(batch)
+        batch.wait()
+        barrier()
+        xv0, xv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xv0.record(stream)
+        for _ in range(args.steps):
+            device_step(batch)
+        xv1.record(stream)
+        batch.wait()
+        barrier()
+        exact_ms = xv0.elapsed_time(xv1)
+        for _ in range(args.steps):
+            device_step(batch)
+            exact_kernel_ms.append(batch.timings()["score_ms"])
+        exact_res = {k: v.copy() for k, v in batch.fetch().items()} if rank == 0 else None
         barrier()
         # ---- called-genotype variant of the same samples (0/1 weights, as BED / GT-only VCF inputs give): popcount kernel
         hard = lib.Batch(db, h_off, h_chr, h_pos, np.concatenate([synth.hard_weights(s["code"][:len(p["pos"])] if world == 1 else
@@ -359,52 +399,51 @@ def run_b200_arm(args):
         # Two batch objects alternate: while one is scored, the next step's samples are copied from pinned host
         # memory on the other's copy stream.  Every step uploads its inputs and reads its results back.
         batch2 = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
-        pair = [batch, batch2]
-        # weights dictionary-coded once at parse time (uint16 index into the table of distinct f64 values: every integer
-        # PL of a VCF gives one exp(-PL/10)); 6 instead of 24 bytes per marker cross PCIe, the device expands them exactly
-        coded = lib.index_weights(h_wei)
-        if coded is not None:
-            idx_t, h_idx = pinned(coded[0])
-            tab_t, h_tab = pinned(coded[1])
-            keep.extend([idx_t, tab_t])
+        batch2.set_group_chunk(args.group_chunk)
+        pair = [gbatch, batch2]
+        rescored = [0]
 
-        def e2e_run(indexed):
-            def up(bt):
-                if indexed:
-                    bt.upload_indexed(h_off, h_chr, h_pos, h_idx, h_tab)
-                else:
-                    bt.upload(h_off, h_chr, h_pos, h_wei)
-
-            def e2e_step(k):
-                cur, nxt = pair[k % 2], pair[(k + 1) % 2]
-                up(nxt)                                          # H2D of step k+1, overlaps the kernels of step k
-                cur.run()
+        def e2e_step(k):
+            cur, nxt = pair[k % 2], pair[(k + 1) % 2]
+            nxt.upload_grouped(gs)                           # H2D of step k+1 (7 bytes per marker), overlaps the kernels of step k
+            cur.run(kernel_mode=lib.KERNEL_GROUPED)
+            if world > 1:
+                sharding.allreduce_batch(cur, dist, dev)
+            cur.epilogue()
+            if rank == 0:
+                cur.fetch(out=out)                           # D2H of step k (waits for it)
+            else:
+                cur.wait()
+            flagged = np.flatnonzero(cur.guard_counts())     # samples whose int(score) needs the reference's summation order
+            for sidx in flagged:                             # (probability ~1e-4 per sample): re-score with the order-exact kernel
+                lo, hi = int(h_off[sidx]), int(h_off[sidx + 1])
+                one = db.scratch_batch([0, hi - lo], h_chr[lo:hi], h_pos[lo:hi], h_wei[lo:hi])
+                one.run()
                 if world > 1:
-                    sharding.allreduce_batch(cur, dist, dev)
-                cur.epilogue()
-                if rank == 0:
-                    cur.fetch(out=out)                           # D2H of step k (waits for it)
-                else:
-                    cur.wait()
-            up(pair[0])
-            for k in range(args.warmup):
-                e2e_step(k)
-            barrier()
-            t0 = time.perf_counter()
-            for k in range(args.warmup, args.warmup + args.steps):
-                e2e_step(k)
-            barrier()
-            return time.perf_counter() - t0
-        e2e_raw_s = e2e_run(False)
-        e2e_s = e2e_run(True) if coded is not None else e2e_raw_s
-        h2d_bytes = h_off.nbytes + h_chr.nbytes + h_pos.nbytes + (h_idx.nbytes + h_tab.nbytes if coded is not None else h_wei.nbytes)
+                    sharding.allreduce_batch(one, dist, dev)
+                one.epilogue()
+                r1 = one.fetch()
+                for key in out:
+                    out[key][sidx] = r1[key][0]
+                rescored[0] += 1
+        pair[0].upload_grouped(gs)
+        for k in range(args.warmup):
+            e2e_step(k)
+        barrier()
+        rescored[0] = 0
+        t0 = time.perf_counter()
+        for k in range(args.warmup, args.warmup + args.steps):
+            e2e_step(k)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        h2d_bytes = h_off.nbytes + gs.chrom.nbytes + gs.pos.nbytes + gs.gid.nbytes + gs.table.size // 3 * 32
         clocks = sampler.stop() if rank == 0 else None
 
     m_per_sample = out["m"].astype(np.int64) if rank == 0 else None
-    tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms, e2e_raw_s * 1e3], dtype=torch.float64, device=dev)
+    tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms, exact_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, hard_ms, e2e_raw_ms = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
+    dev_ms, e2e_ms, hard_ms, exact_ms = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
 
     if rank == 0:
         m_total = int(m_per_sample.sum())
@@ -433,17 +472,20 @@ def run_b200_arm(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, S),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(world * h2d_bytes),
-                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())),
-                    "inputs": "pinned host arrays chrom int32, pos int32, weights as uint16 indices into the table of their distinct "
-                              "f64 values (coded once at parse time; expanded bit-exactly on the device); two batches alternate so "
-                              "that the H2D of step k+1 overlaps the kernels of step k",
-                    "f64_weight_upload": {"value": comps * args.steps / (e2e_raw_ms * 1e-3), "ms_per_step": e2e_raw_ms / args.steps,
-                                          "h2d_bytes_per_step": int(world * (h_off.nbytes + h_chr.nbytes + h_pos.nbytes + h_wei.nbytes))}},
+                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values()) + 4 * S),
+                    "inputs": "pinned host arrays in grouped order (snpm_group_markers, once at parse time: %.0f ms for the batch): "
+                              "chromosome uint8, position int32, weight-triple id uint16 per marker + the table of distinct triples "
+                              "(f64); two batches alternate so that the H2D of step k+1 overlaps the kernels of step k; the D2H holds "
+                              "scores, counts, likelihoods and the per-sample guard counts" % (1e3 * t_group),
+                    "samples_rescored_in_reference_order": int(rescored[0])},
             "gpu_launches": int(total_launches * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "k_score_segments", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_score_grouped", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items() if k.endswith("_ms")},
+            "distinct_weight_triples": int(len(gs.table)), "group_chunk_rows": int(args.group_chunk),
+            "guard_flagged_samples": int((guard_resident > 0).sum()),
             "clocks": clocks,
             "matched_markers_per_step": m_total,
         }
@@ -456,6 +498,18 @@ def run_b200_arm(args):
             "value": int(hard_res["m"].sum()) * n_acc * args.steps / (hard_ms * 1e-3), "unit": UNIT, "ms_per_step": hard_ms / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_score_hard", "achieved": h_ach, "peak": peak, "unit": "GB/s",
                          "frac": h_ach / peak if peak else None, "algorithmic_bytes_per_launch": int(h_bytes), "kernel_ms": hk_ms}}
+        xk_ms = float(np.mean(exact_kernel_ms))
+        x_ach = algo_bytes / (xk_ms * 1e-3) / 1e9 if xk_ms > 0 else 0.0
+        ok = guard_resident == 0
+        line["order_exact_fp64"] = {
+            "workload": "same batch in position order, fp64 kernel k_score_segments (sums in the reference's order: fp64 scores bit-identical)",
+            "value": comps * args.steps / (exact_ms * 1e-3), "unit": UNIT, "ms_per_step": exact_ms / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_score_segments", "achieved": x_ach, "peak": peak, "unit": "GB/s",
+                         "frac": x_ach / peak if peak else None, "kernel_ms": xk_ms},
+            "grouped_vs_exact": {"matches_equal": bool(np.array_equal(out["matches"][ok], exact_res["matches"][ok])),
+                                 "ninfo_equal": bool(np.array_equal(out["ninfo"], exact_res["ninfo"])),
+                                 "score_max_rel_diff": float(np.max(np.abs(out["score"] - exact_res["score"]) / np.maximum(exact_res["score"], 1.0))),
+                                 "LR_max_rel_diff": float(np.nanmax(np.abs(out["LR"][ok] - exact_res["LR"][ok]) / np.abs(exact_res["LR"][ok])))}}
         if not args.no_cpu_baseline and world == 1:
             s0 = samples[0]
             rows, codes = cpu_prepare_sample(s0, n_acc, args.cpu_markers)
@@ -465,8 +519,11 @@ def run_b200_arm(args):
                                               "database labels + chunked matchGTsAccs + likelihoods, NumPy oracle port of "
                                               "snpmatch.py:207-233, database rows held in RAM as int8" % (len(rows), n_acc, n_rows)}
             if not args.cpu_markers:
-                line["cpu_baseline"]["parity"] = bool(np.array_equal(cpu_score, out["score"][0]) and
-                                                      np.array_equal(cpu_ninfo, out["ninfo"][0]))
+                # integers bit-exact (matches = int(score), informative sites); fp64 scores of the grouped kernel to 1e-12
+                line["cpu_baseline"]["parity"] = bool(np.array_equal(cpu_score.astype(np.int64), out["matches"][0]) and
+                                                      np.array_equal(cpu_ninfo, out["ninfo"][0]) and
+                                                      np.allclose(cpu_score, out["score"][0], rtol=1e-12, atol=0.0) and
+                                                      np.array_equal(cpu_score, exact_res["score"][0]))
         if world == 1:
             # batched shared-panel mode (BASELINE configs[3]): 4096 called-genotype samples on 20 000 shared markers as a
             # one-hot int8 GEMM on tcgen05; device time of the GEMM kernel (operand expansion and H2D of the codes excluded)
@@ -486,6 +543,7 @@ def run_b200_arm(args):
         print(json.dumps(line))
     batch.close()
     batch2.close()
+    gbatch.close()
     g.close()
     if world > 1:
         dist.destroy_process_group()
