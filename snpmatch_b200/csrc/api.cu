@@ -121,6 +121,32 @@ int snpm_db_create(int device, int64_t n_rows, int32_t n_acc, const int32_t *pos
     if (e == cudaSuccess && n_chr) e = cudaMemcpyAsync(db->d_chr_regions, chr_regions, size_t(n_chr) * 16, cudaMemcpyHostToDevice, db->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
     if (e != cudaSuccess) { snpm_db_destroy(db); return fail(SNPM_E_CUDA, "snpm_db_create: upload: %s", cudaGetErrorString(e)); }
+    {   // coarse position index for the join: ~16 rows per bucket
+        int64_t span = 0;
+        for (int c = 0; c < n_chr; ++c)
+            if (chr_regions[2 * c + 1] > chr_regions[2 * c]) span += int64_t(positions[chr_regions[2 * c + 1] - 1]) + 1;
+        int shift = 0;
+        while (shift < 30 && (span >> shift) * 16 > std::max<int64_t>(n_rows, 1) * 2) ++shift;     // (span >> shift) buckets ~ n_rows / 16
+        std::vector<int32_t> boff(size_t(n_chr) + 1, 0);
+        int64_t total = 0;
+        for (int c = 0; c < n_chr; ++c) {
+            boff[size_t(c)] = int32_t(total);
+            const int64_t last = chr_regions[2 * c + 1] > chr_regions[2 * c] ? int64_t(positions[chr_regions[2 * c + 1] - 1]) : -1;
+            total += (last < 0 ? 0 : (last >> shift) + 1) + 1;                                  // + the closing entry
+        }
+        boff[size_t(n_chr)] = int32_t(total);
+        if (total >= (int64_t(1) << 31)) { snpm_db_destroy(db); return fail(SNPM_E_ARG, "snpm_db_create: position index too large"); }
+        db->bucket_shift = shift;
+        e = cudaMalloc(&db->d_bucket, std::max<size_t>(size_t(total) * 4, 256));
+        if (e == cudaSuccess) e = cudaMalloc(&db->d_bucket_off, (size_t(n_chr) + 1) * 4);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(db->d_bucket_off, boff.data(), (size_t(n_chr) + 1) * 4, cudaMemcpyHostToDevice, db->stream);
+        if (e == cudaSuccess && total > 0) {
+            k_build_buckets<<<int(ceil_div64(total, 256)), 256, 0, db->stream>>>(db->d_pos, db->d_chr_regions, n_chr, db->d_bucket_off, shift, db->d_bucket);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+        if (e != cudaSuccess) { snpm_db_destroy(db); return fail(SNPM_E_CUDA, "snpm_db_create: position index: %s", cudaGetErrorString(e)); }
+    }
     *out = db;
     return SNPM_OK;
 }
@@ -132,6 +158,8 @@ int snpm_db_destroy(snpm_db *db) {
     if (db->d_packed) cudaFree(db->d_packed);
     if (db->d_pos) cudaFree(db->d_pos);
     if (db->d_chr_regions) cudaFree(db->d_chr_regions);
+    if (db->d_bucket) cudaFree(db->d_bucket);
+    if (db->d_bucket_off) cudaFree(db->d_bucket_off);
     if (db->scratch_batch_) { snpm_batch_destroy(db->scratch_batch_); db->scratch_batch_ = nullptr; }
     db->scratch.release();
     if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
@@ -597,7 +625,8 @@ static int batch_join(snpm_batch *b, int algo) {
                                                          b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>());
         else
             k_join_search<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
-                                                            db->d_pos, db->d_chr_regions, db->n_chr, filter, b->n_filter, db->row0_global,
+                                                            db->d_pos, db->d_chr_regions, db->n_chr, db->d_bucket, db->d_bucket_off, db->bucket_shift,
+                                                            filter, b->n_filter, db->row0_global,
                                                             b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>(), b->grouped ? 0 : 1);
         SNPM_KERNEL_CHECK();
         k_scan_tiles<<<1, 1024, 0, st>>>(b->d_tile_cnt.as<int32_t>(), n_tiles, b->d_tile_off.as<int32_t>(), b->d_prefix.as<int32_t>() + n);

@@ -98,6 +98,9 @@ struct snpm_db {
     uint64_t *d_packed = nullptr;
     int32_t *d_pos = nullptr;
     int64_t *d_chr_regions = nullptr;   // [n_chr,2], local rows
+    int32_t *d_bucket = nullptr;        // coarse position index (k_build_buckets)
+    int32_t *d_bucket_off = nullptr;    // [n_chr + 1]
+    int bucket_shift = 0;
     std::vector<int64_t> h_chr_regions;
     cudaStream_t stream = nullptr;
     bool own_stream = false;

@@ -52,10 +52,28 @@ __device__ __forceinline__ void check_order(const int32_t *__restrict__ chrom, c
     atomicAdd(status, 1);
 }
 
+// Coarse position index of the panel: bucket b of chromosome c covers positions [b << shift, (b + 1) << shift) and stores the
+// first row at or after its start (bucket_off[c] + b; one extra entry per chromosome closes the last bucket).  A marker
+// then needs one table read and a short binary search inside ~16 rows that share a few cache lines, instead of
+// log2(N) dependent probes spread over the whole position array (which made the search L2-bandwidth bound).
+__global__ void __launch_bounds__(256) k_build_buckets(const int32_t *__restrict__ db_pos, const int64_t *__restrict__ chr_regions,
+                                                       int32_t n_chr, const int32_t *__restrict__ bucket_off, int shift,
+                                                       int32_t *__restrict__ bucket) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= bucket_off[n_chr]) return;
+    int c = 0;
+    while (c + 1 < n_chr && bucket_off[c + 1] <= i) ++c;
+    const int64_t b = i - bucket_off[c];
+    const int64_t rs = chr_regions[2 * c], re = chr_regions[2 * c + 1];
+    const int64_t key = b << shift;
+    bucket[i] = key > 0x7fffffffll ? int32_t(re) : int32_t(lower_bound_i32(db_pos, rs, re, int32_t(key)));
+}
+
 __global__ void __launch_bounds__(JOIN_TILE) k_join_search(
         const int32_t *__restrict__ chrom, const int32_t *__restrict__ pos, int64_t n,
         const int64_t *__restrict__ off, int64_t S,
         const int32_t *__restrict__ db_pos, const int64_t *__restrict__ chr_regions, int32_t n_chr,
+        const int32_t *__restrict__ bucket, const int32_t *__restrict__ bucket_off, int shift,
         const int64_t *__restrict__ filter, int64_t n_filter, int64_t row0_global,
         int32_t *__restrict__ match_row, int32_t *__restrict__ tile_cnt, int *status, int check) {
     // check == 0: markers are in weight-grouped order (snpm_batch_upload_grouped); the search does not need an order
@@ -65,12 +83,16 @@ __global__ void __launch_bounds__(JOIN_TILE) k_join_search(
         if (check) check_order(chrom, pos, off, S, i, status);
         const int32_t c = chrom[i];
         if (c >= 0 && c < n_chr) {
-            const int64_t rs = chr_regions[2 * c], re = chr_regions[2 * c + 1];
             const int32_t p = pos[i];
-            const int64_t j = lower_bound_i32(db_pos, rs, re, p);
-            if (j < re && __ldg(db_pos + j) == p) {
-                row = int32_t(j);
-                if (n_filter > 0 && !contains_i64(filter, n_filter, j + row0_global)) row = -1;
+            const int32_t b0 = bucket_off[c], nb = bucket_off[c + 1] - b0 - 1;      // buckets of this chromosome
+            const int32_t b = p >> shift;
+            if (p >= 0 && b < nb) {
+                const int64_t rs = __ldg(bucket + b0 + b), re = __ldg(bucket + b0 + b + 1);
+                const int64_t j = lower_bound_i32(db_pos, rs, re, p);
+                if (j < re && __ldg(db_pos + j) == p) {
+                    row = int32_t(j);
+                    if (n_filter > 0 && !contains_i64(filter, n_filter, j + row0_global)) row = -1;
+                }
             }
         }
         match_row[i] = row;
