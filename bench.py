@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--markers", type=int, default=N_DB_MARKERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group-chunk", type=int, default=480, help="rows per segment of the grouped kernel")
+    ap.add_argument("--force-grouped", action="store_true", help="grouped counting kernel even when row sharding makes the groups small")
+    ap.add_argument("--force-exact", action="store_true", help="order-exact fp64 kernel as the headline path")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     return ap.parse_args()
 
@@ -306,8 +308,14 @@ def run_b200_arm(args):
     gbatch.set_group_chunk(args.group_chunk)
     gbatch.upload_grouped(gs)
 
+    # Row sharding cuts every weight group into `world` pieces; below ~16 rows per group and rank the read-out of the
+    # counters costs more than the order-exact kernel's two fp64 adds per comparison, so the headline path falls back to
+    # that kernel (same decision on every rank: it only looks at the whole samples).
+    rows_per_group = args.markers / float(world) / max(1, len(np.unique(samples[0]["wei"], axis=0)))
+    use_grouped = (rows_per_group >= 16.0 or args.force_grouped) and not args.force_exact
+
     def device_step(b=None, mode=None):
-        b = gbatch if b is None else b
+        b = (gbatch if use_grouped else batch) if b is None else b
         b.run(kernel_mode=lib.KERNEL_GROUPED if b is gbatch else lib.KERNEL_FP64)
         if world > 1:
             sharding.allreduce_batch(b, dist, dev)          # one NCCL all-reduce of the per-sample totals
@@ -321,9 +329,10 @@ def run_b200_arm(args):
     score_ms, total_launches = [], 0
     with torch.cuda.stream(stream):
         # ---- resident arm -------------------------------------------------------------------------
+        head = gbatch if use_grouped else batch
         for _ in range(args.warmup):
             device_step()
-        gbatch.wait()
+        head.wait()
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -333,19 +342,19 @@ def run_b200_arm(args):
         for _ in range(args.steps):
             device_step()
         ev1.record(stream)
-        gbatch.wait()
+        head.wait()
         barrier()
         dev_ms = ev0.elapsed_time(ev1)
         # per-kernel times of the scoring kernel: one more timed pass that reads the library's own events each step
         stage_ms = {}
         for _ in range(args.steps):
             device_step()
-            t = gbatch.timings()
+            t = head.timings()
             score_ms.append(t["score_ms"])
             for k, v in t.items():
                 stage_ms.setdefault(k, []).append(v)
             total_launches = t["launches"]
-        guard_resident = gbatch.guard_counts()
+        guard_resident = head.guard_counts()
         barrier()
         # ---- the order-exact fp64 kernel on the same samples (position order), for comparison
         exact_kernel_ms = []
@@ -403,10 +412,24 @@ def run_b200_arm(args):
         pair = [gbatch, batch2]
         rescored = [0]
 
+        coded = None if use_grouped else lib.index_weights(h_wei)
+        if coded is not None:
+            idx_t, h_idx = pinned(coded[0])
+            tab_t, h_tab = pinned(coded[1])
+            keep.extend([idx_t, tab_t])
+
+        def up(bt):
+            if use_grouped:
+                bt.upload_grouped(gs)                        # 7 bytes per marker
+            elif coded is not None:
+                bt.upload_indexed(h_off, h_chr, h_pos, h_idx, h_tab)      # 14 bytes per marker
+            else:
+                bt.upload(h_off, h_chr, h_pos, h_wei)
+
         def e2e_step(k):
             cur, nxt = pair[k % 2], pair[(k + 1) % 2]
-            nxt.upload_grouped(gs)                           # H2D of step k+1 (7 bytes per marker), overlaps the kernels of step k
-            cur.run(kernel_mode=lib.KERNEL_GROUPED)
+            up(nxt)                                          # H2D of step k+1, overlaps the kernels of step k
+            cur.run(kernel_mode=lib.KERNEL_GROUPED if use_grouped else lib.KERNEL_FP64)
             if world > 1:
                 sharding.allreduce_batch(cur, dist, dev)
             cur.epilogue()
@@ -426,7 +449,7 @@ def run_b200_arm(args):
                 for key in out:
                     out[key][sidx] = r1[key][0]
                 rescored[0] += 1
-        pair[0].upload_grouped(gs)
+        up(pair[0])
         for k in range(args.warmup):
             e2e_step(k)
         barrier()
@@ -436,7 +459,10 @@ def run_b200_arm(args):
             e2e_step(k)
         barrier()
         e2e_s = time.perf_counter() - t0
-        h2d_bytes = h_off.nbytes + gs.chrom.nbytes + gs.pos.nbytes + gs.gid.nbytes + gs.table.size // 3 * 32
+        if use_grouped:
+            h2d_bytes = h_off.nbytes + gs.chrom.nbytes + gs.pos.nbytes + gs.gid.nbytes + gs.table.size // 3 * 32
+        else:
+            h2d_bytes = h_off.nbytes + h_chr.nbytes + h_pos.nbytes + (h_idx.nbytes + h_tab.nbytes if coded is not None else h_wei.nbytes)
         clocks = sampler.stop() if rank == 0 else None
 
     m_per_sample = out["m"].astype(np.int64) if rank == 0 else None
@@ -479,12 +505,13 @@ def run_b200_arm(args):
                               "scores, counts, likelihoods and the per-sample guard counts" % (1e3 * t_group),
                     "samples_rescored_in_reference_order": int(rescored[0])},
             "gpu_launches": int(total_launches * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "k_score_grouped", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_score_grouped" if use_grouped else "k_score_segments", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items() if k.endswith("_ms")},
             "distinct_weight_triples": int(len(gs.table)), "group_chunk_rows": int(args.group_chunk),
+            "headline_kernel": "grouped counting kernel" if use_grouped else "order-exact fp64 kernel (row sharding leaves %.1f rows per weight group and rank)" % rows_per_group,
             "guard_flagged_samples": int((guard_resident > 0).sum()),
             "clocks": clocks,
             "matched_markers_per_step": m_total,

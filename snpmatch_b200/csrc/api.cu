@@ -708,7 +708,7 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
             g.table = b->d_gtable.as<double>(); g.seg_off = a.seg_off; g.mstart = a.mstart; g.S = a.S; g.chunk = b->gchunk;
             g.part_score = a.part_score; g.part_int = b->d_part_int.as<int32_t>(); g.part_ninfo = a.part_ninfo; g.a_pad = a.a_pad;
             const int nsl = (db->stride + GR_MAX_WX - 1) / GR_MAX_WX;
-            g.wx = (db->stride + nsl - 1) / nsl;
+            g.wx = ((db->stride + nsl - 1) / nsl + 1) & ~1;          // even: neighbouring threads copy 16-byte pairs of columns
             g.spc = std::min(GR_THREADS / g.wx, GR_MAX_TEAMS);
             const size_t gsmem = size_t(g.spc) * grouped_team_smem(g.wx, g.chunk);
             static bool gr_attr = false;
@@ -719,7 +719,11 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
                 SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped<false, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 gr_attr = true;
             }
-            dim3 ggrid(unsigned(ceil_div64(b->nseg_cap, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
+            int64_t jmax = 0;
+            for (int64_t smp = 0; smp < b->S; ++smp)
+                jmax = std::max(jmax, ceil_div64(std::min<int64_t>(b->h_off[size_t(smp) + 1] - b->h_off[size_t(smp)], db->n_rows), b->gchunk));
+            g.jmax = int32_t(jmax);
+            dim3 ggrid(unsigned(ceil_div64(b->S * jmax, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
             if (g.wx == GR_MAX_WX) {              // the 1135-accession row: addresses known at compile time
                 if (skip_db_hets) k_score_grouped<true, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
                 else k_score_grouped<false, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);

@@ -54,6 +54,7 @@ struct GroupArgs {
     int32_t a_pad;
     int32_t wx;                   // words per team slice
     int32_t spc;                  // teams (segments) per CTA
+    int32_t jmax;                 // upper bound of the segments of one sample
 };
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void *src_gmem) {
@@ -199,7 +200,7 @@ __host__ __device__ __forceinline__ size_t grouped_team_smem(int wx, int chunk) 
     return size_t(GR_RING) * wx * 8 + size_t(chunk) * 4 + ((size_t(chunk) * 2 + 15) & ~size_t(15)) + ((n_blocks * 8 + 15) & ~size_t(15));
 }
 
-// grid.x = ceil(segments / teams per CTA), grid.y = word slices.  thread -> (team q, word w); a team scores one segment.
+// grid.x = ceil(S * jmax / teams per CTA), grid.y = word slices.  thread -> (team q, word w); a team scores one segment.
 // WX > 0: words per team known at compile time (ring addresses fold into the instructions); WX == 0: a.wx.
 template <bool SKIP_HETS, int WX>
 __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs a) {
@@ -207,18 +208,22 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     const int wx = WX ? WX : a.wx;
     const int spc = a.spc;
     const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
-    const int seg = blockIdx.x * spc + q;
+    // Team slot -> segment, longest first: the tail of every sample's group order holds the rare weight triples (many small
+    // groups, i.e. many counter read-outs), so the LAST segments of the samples are the slow ones.  Slots walk the segments
+    // by position inside the sample, descending, over all samples: the slow segments start first and the cheap ones fill
+    // the end of the grid, instead of one sample's slow tail running alone when everything else has finished.
+    const int slot = blockIdx.x * spc + q;
     const int word = blockIdx.y * wx + w;
-    const bool team_ok = q < spc && seg < a.seg_off[a.S];
-    int begin = 0, end = 0;
-    if (team_ok) {
-        int lo_s = 0, hi_s = a.S;
-        while (lo_s < hi_s) {
-            const int mid = (lo_s + hi_s + 1) >> 1;
-            if (a.seg_off[mid] <= seg) lo_s = mid; else hi_s = mid - 1;
+    int seg = 0, begin = 0, end = 0;
+    bool team_ok = false;
+    if (q < spc) {
+        const int j = a.jmax - 1 - slot / a.S, smp = slot % a.S;
+        if (j >= 0 && j < a.seg_off[smp + 1] - a.seg_off[smp]) {
+            team_ok = true;
+            seg = a.seg_off[smp] + j;
+            begin = a.mstart[smp] + j * a.chunk;
+            end = min(a.mstart[smp + 1], begin + a.chunk);
         }
-        begin = a.mstart[lo_s] + (seg - a.seg_off[lo_s]) * a.chunk;
-        end = min(a.mstart[lo_s + 1], begin + a.chunk);
     }
     const int n_rows = end - begin;
     const int n_blocks = (n_rows + GR_BLOCK - 1) / GR_BLOCK;
@@ -261,21 +266,28 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     const uint32_t ring_pitch = uint32_t(wx) * 8u;
     const int64_t stride = a.stride;
     const int n_full = n_rows / GR_BLOCK;         // blocks without a ragged end
-    // queue the gathers of block b (this thread's 8-byte column of 16 rows); full blocks carry no predicates
+    // Queue the gathers of block b.  Two neighbouring threads (words 2i, 2i+1: always lanes of one warp) share the work: each
+    // copies the 16 bytes that hold BOTH their columns, the even one for rows 0..7 of the block, the odd one for rows 8..15 —
+    // 8 LDGSTS.128 per thread instead of 16 LDGSTS.64, which halves the load on the LSU instruction queue.  Full blocks carry
+    // no predicates.
+    const int odd = w & 1;
+    const uint32_t pair_ring = smem_u32(ring + (w & ~1));
+    const uint64_t *pair_col = a.packed + (word & ~1);
+    const unsigned pair_mask = 3u << (threadIdx.x & 30);
     auto issue = [&](int b) {
-        const int r0 = b * GR_BLOCK;
-        const uint32_t slot0 = my_ring + uint32_t(r0 & (GR_RING - 1)) * ring_pitch;
+        const int r0 = b * GR_BLOCK + 8 * odd;
+        const uint32_t slot0 = pair_ring + uint32_t(r0 & (GR_RING - 1)) * ring_pitch;
         if (b < n_full) {
 #pragma unroll
-            for (int k4 = 0; k4 < GR_BLOCK; k4 += 4) {
+            for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
                 const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
-                cp_async8(slot0 + uint32_t(k4 + 0) * ring_pitch, col + int64_t(rr.x) * stride);
-                cp_async8(slot0 + uint32_t(k4 + 1) * ring_pitch, col + int64_t(rr.y) * stride);
-                cp_async8(slot0 + uint32_t(k4 + 2) * ring_pitch, col + int64_t(rr.z) * stride);
-                cp_async8(slot0 + uint32_t(k4 + 3) * ring_pitch, col + int64_t(rr.w) * stride);
+                cp_async16(slot0 + uint32_t(k4 + 0) * ring_pitch, pair_col + int64_t(rr.x) * stride);
+                cp_async16(slot0 + uint32_t(k4 + 1) * ring_pitch, pair_col + int64_t(rr.y) * stride);
+                cp_async16(slot0 + uint32_t(k4 + 2) * ring_pitch, pair_col + int64_t(rr.z) * stride);
+                cp_async16(slot0 + uint32_t(k4 + 3) * ring_pitch, pair_col + int64_t(rr.w) * stride);
             }
         } else if (b < n_blocks) {
-            for (int k = 0; r0 + k < n_rows; ++k) cp_async8(slot0 + uint32_t(k) * ring_pitch, col + int64_t(s_row[r0 + k]) * stride);
+            for (int k = 0; k < GR_BLOCK / 2 && r0 + k < n_rows; ++k) cp_async16(slot0 + uint32_t(k) * ring_pitch, pair_col + int64_t(s_row[r0 + k]) * stride);
         }
         cp_async_commit();                        // always: the wait below counts groups
     };
@@ -348,7 +360,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     };
 
     for (int b = 0; b < n_full; ++b) {
-        cp_async_wait<GR_INFLIGHT - 1>();         // block b has landed (this thread's own copies)
+        cp_async_wait<GR_INFLIGHT - 1>();         // block b has landed: this thread's copies ...
+        __syncwarp(pair_mask);                    // ... and its neighbour's
         const uint64_t *slot = ring + size_t((b * GR_BLOCK) & (GR_RING - 1)) * wx + w;
         uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
 #pragma unroll
@@ -358,10 +371,12 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
             hi[k] = uint32_t(v >> 32);
         }
         score_block(lo, hi, b);
+        __syncwarp(pair_mask);                    // the neighbour has read its half of the block too
         issue(b + GR_INFLIGHT);                   // refill the slots of this block
     }
     if (n_full < n_blocks) {                      // ragged last block: rows past the end read as missing everywhere
         cp_async_wait<0>();
+        __syncwarp(pair_mask);
         const int r0 = n_full * GR_BLOCK;
         const uint64_t *slot = ring + size_t(r0 & (GR_RING - 1)) * wx + w;
         uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
