@@ -261,7 +261,6 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     __syncthreads();                              // the last CTA-wide barrier: threads may leave from here on
     if (!team_ok || word >= a.stride) return;
 
-    const uint64_t *col = a.packed + word;
     const uint32_t my_ring = smem_u32(ring + w);
     const uint32_t ring_pitch = uint32_t(wx) * 8u;
     const int64_t stride = a.stride;

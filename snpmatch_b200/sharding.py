@@ -100,3 +100,59 @@ def allreduce_batch(batch, dist, device):
     t = torch.as_tensor(holder, device=device)
     dist.all_reduce(t)
     return t
+
+
+# ---- grouped counting kernel (csrc/grouped.cuh): the score travels as an exact integer part I and a fractional part F ----
+def grouped_row_len(n_acc):
+    """f64 per sample in the reduce buffer of a grouped batch: F[n_acc] | ninfo[n_acc] | matched pairs | y>n count | I[n_acc]."""
+    return 3 * n_acc + 2
+
+
+def grouped_partials(wei, codes, skip_db_hets=False):
+    """Host picture of what k_score_grouped + k_combine_grouped leave for one sample on one shard.
+    wei f64 [k,3] in the reference's column order (ref, het, alt; parsers.py:89-94), codes int8 [k,A] (-1/0/1/2).
+    Returns (F f64[A], I int64[A], ninfo int64[A]): matches of weights that are exactly 1.0 are counted in I, every other
+    weight is summed in F (any order: the device sums group by group)."""
+    wei = np.asarray(wei, dtype=np.float64).reshape(-1, 3)
+    codes = np.asarray(codes)
+    if skip_db_hets:
+        codes = np.where(codes == 2, -1, codes)
+    A = codes.shape[1] if codes.ndim == 2 else 0
+    F = np.zeros(A)
+    I = np.zeros(A, dtype=np.int64)
+    for col, code in ((0, 0), (1, 2), (2, 1)):            # weight column -> database code (snpmatch.py:81-87)
+        hit = codes == code
+        w = wei[:, col]
+        one = w == 1.0
+        I += hit[one].sum(axis=0)
+        F += (hit[~one] * w[~one, None]).sum(axis=0)
+    return F, I, (codes >= 0).sum(axis=0).astype(np.int64)
+
+
+def pack_grouped_rows(F, ninfo, m, I):
+    F = np.atleast_2d(np.asarray(F, dtype=np.float64))
+    S, A = F.shape
+    out = np.zeros((S, grouped_row_len(A)), dtype=np.float64)
+    out[:, :A] = F
+    out[:, A:2 * A] = np.atleast_2d(ninfo)
+    out[:, 2 * A] = np.asarray(m).reshape(S)
+    out[:, 2 * A + 2:] = np.atleast_2d(I)
+    return out
+
+
+def finalize_grouped(buf, n_acc):
+    """NumPy restatement of k_grouped_finalize on (all-reduced) totals: returns (score f64[S,A], matches int64[S,A],
+    ninfo int64[S,A], m int64[S], guard bool[S,A]).  matches = I + floor(F): the reference's fp64 sum is >= I (monotone
+    rounding of non-negative terms) and < I + F + eps, so its truncation can only differ where F lies within the summation
+    error bound of an integer k >= 1 — those cells are flagged for re-scoring in reference order."""
+    buf = np.asarray(buf, dtype=np.float64).reshape(-1, grouped_row_len(n_acc))
+    F, ninfo, m, I = buf[:, :n_acc], buf[:, n_acc:2 * n_acc], buf[:, 2 * n_acc], buf[:, 2 * n_acc + 2:]
+    depth = 1010.0 + m[:, None] / 500.0
+    g = 4.0 * depth * 1.1102230246251565e-16 * (I + F + 1.0)
+    k = np.rint(F)
+    guard = (k >= 1.0) & (np.abs(F - k) <= g)
+    want = I + np.floor(F)
+    v = I + F
+    bump = np.floor(v) != want
+    v = np.where(bump, np.nextafter(want + 1.0, 0.0), v)
+    return v, want.astype(np.int64), ninfo.astype(np.int64), m.astype(np.int64), guard

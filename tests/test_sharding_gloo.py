@@ -41,8 +41,15 @@ def _worker(rank, world, port, out_dir):
     dist.all_reduce(t)
     score, ninfo, m = sharding.unpack_reduce_rows(t.numpy(), n_acc)
     # global pair indices of this shard
+    # grouped counting path: the shard's totals travel as (F, ninfo, m, I); finalised after the reduce
+    rows, tar = res.common
+    F, I, ni = sharding.grouped_partials(s["wei"][tar], p["snps"][r0:r1][rows])
+    gt = torch.from_numpy(sharding.pack_grouped_rows(F, ni, len(rows), I))
+    dist.all_reduce(gt)
+    g_score, g_matches, g_ninfo, g_m, g_guard = sharding.finalize_grouped(gt.numpy(), n_acc)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), score=score[0], ninfo=ninfo[0], m=m,
-             db_idx=res.common[0] + r0, s_idx=res.common[1], regions=regions)
+             db_idx=res.common[0] + r0, s_idx=res.common[1], regions=regions, g_score=g_score[0], g_matches=g_matches[0],
+             g_ninfo=g_ninfo[0], g_m=g_m, g_guard=g_guard[0])
     dist.destroy_process_group()
 
 
@@ -70,6 +77,15 @@ def test_row_sharded_allreduce_matches_single_run(tmp_path, world):
     # likelihoods on the reduced totals agree with the single run
     lik, lr = orc.calculate_likelihoods(o["score"].astype(np.int64), o["ninfo"])
     np.testing.assert_allclose(lik, g["likelis"], rtol=1e-12, equal_nan=True)
+    # grouped path: integers exact wherever the guard is silent, scores to 1e-12, identical on every rank
+    for x in outs[1:]:
+        assert np.array_equal(x["g_matches"], o["g_matches"]) and np.array_equal(x["g_score"], o["g_score"])
+    assert int(o["g_m"][0]) == int(g["num_snps"]) and np.array_equal(o["g_ninfo"], g["ninfo"])
+    ok = ~o["g_guard"]
+    assert ok.sum() >= len(ok) - 1
+    assert np.array_equal(o["g_matches"][ok], g["scores"][ok])
+    assert np.array_equal(o["g_score"].astype(np.int64), o["g_matches"])         # the stored score truncates to matches
+    np.testing.assert_allclose(o["g_score"], single.score_f64, rtol=1e-12)
     # the shards' pairs concatenate to the whole join
     db_idx = np.concatenate([x["db_idx"] for x in outs])
     s_idx = np.concatenate([x["s_idx"] for x in outs])
@@ -91,6 +107,18 @@ def test_shard_geometry():
     assert sc.tolist() == [[3.0, 5.0]] and ni.tolist() == [[6, 8]] and m.tolist() == [14]
     g = sharding.truncation_guard(np.array([4719.0, 4718.999999999999, 12.5, 3.0000000000000004, 0.0]))
     assert g.tolist() == [False, True, False, True, False]
+    # grouped totals: I + F; F just below / at / above an integer k >= 1 is flagged, F < 1 never is
+    F = np.array([[0.25, 1e-13, 0.9999999999999999, 2.0000000000000004, 3.5, 0.0]])
+    I = np.array([[10, 4000, 7, 7, 0, 12]])
+    buf = sharding.pack_grouped_rows(F, I + 5, [100], I)
+    sc, ma, ni, m, gd = sharding.finalize_grouped(buf, 6)
+    assert ma.tolist() == [[10, 4000, 7, 9, 3, 12]] and gd.tolist() == [[False, False, True, True, False, False]]
+    assert sc.astype(np.int64).tolist() == ma.tolist() and ni.tolist() == [[15, 4005, 12, 12, 5, 17]] and m.tolist() == [100]
+    w = np.array([[1.0, 0.5, 0.25], [0.125, 1.0, 1.0], [1.0, 0.0, 0.75]])
+    codes = np.array([[0, 1, 2, -1], [2, 1, 0, 1], [1, 1, -1, 0]], dtype=np.int8)
+    Fp, Ip, Np = sharding.grouped_partials(w, codes)
+    assert Ip.tolist() == [2, 1, 0, 2] and Np.tolist() == [3, 3, 2, 2]
+    assert Fp.tolist() == [0.75, 1.0, 0.625, 0.0]
 
 
 def test_marker_slices_cover_the_join_exactly():
