@@ -179,6 +179,12 @@ int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles);
  * prob/L/LR f64[S,A]. */
 int snpm_batch_fetch(snpm_batch *b, double *score, int64_t *matches, int64_t *ninfo, int64_t *m,
                      double *prob, double *L, double *LR);
+/* snpm_batch_fetch in two halves: _async queues the copies (into pinned host buffers) behind the batch's kernels and returns,
+ * _wait blocks until they have landed and reports the errors snpm_batch_fetch would.  guard (optional) receives
+ * snpm_batch_guard_counts.  Between the two calls another batch may be run: its kernels overlap this batch's read-back. */
+int snpm_batch_fetch_async(snpm_batch *b, double *score, int64_t *matches, int64_t *ninfo, int64_t *m,
+                           double *prob, double *L, double *LR, int32_t *guard);
+int snpm_batch_fetch_wait(snpm_batch *b);
 /* matched pairs of sample s (global db rows, marker index inside the sample) — commonSNPs,
  * snpmatch.py:186-187.  capacity in elements; *m receives the pair count. */
 int snpm_batch_fetch_pairs(snpm_batch *b, int64_t s, int64_t *db_idx, int64_t *s_idx, int64_t capacity, int64_t *m);

@@ -576,6 +576,9 @@ int snpm_batch_destroy(snpm_batch *b) {
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->h_status) cudaFreeHost(b->h_status);
+    if (b->h_tail) cudaFreeHost(b->h_tail);
+    if (b->ev_fetched) cudaEventDestroy(b->ev_fetched);
+    if (b->ev_results) cudaEventDestroy(b->ev_results);
     delete b;
     return SNPM_OK;
 }
@@ -898,6 +901,70 @@ int snpm_batch_fetch(snpm_batch *b, double *score, int64_t *matches, int64_t *ni
         viol += (long long)tail[2 * s + 1];
     }
     if (viol > 0 && b->epilogue_done) return fail(SNPM_E_ASSERT, "provided y is greater than n (%lld accessions; likeliTest, snpmatch.py:43)", viol);
+    return SNPM_OK;
+}
+
+
+// Asynchronous variant of snpm_batch_fetch: queues the device-to-host copies behind the batch's kernels and returns; the
+// host buffers (pinned, for the copies to be truly asynchronous) are valid after snpm_batch_fetch_wait.  Lets a caller queue
+// the next batch's kernels before it waits for this one's results.
+int snpm_batch_fetch_async(snpm_batch *b, double *score, int64_t *matches, int64_t *ninfo, int64_t *m, double *prob, double *L, double *LR,
+                           int32_t *guard) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_fetch_async: NULL batch");
+    if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_fetch_async: run the batch first");
+    if (!b->epilogue_done) return fail(SNPM_E_STATE, "snpm_batch_fetch_async: run the epilogue first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    // the copies run on the batch's copy stream, behind an event that marks the end of its kernels: the read-back does not
+    // hold up whatever is queued next on the compute stream
+    cudaStream_t st = b->copy_stream;
+    const size_t A = size_t(db->n_acc), S = size_t(b->S), pitch = size_t(b->red_pitch()) * 8;
+    if (!b->ev_fetched) SNPM_CUDA(cudaEventCreateWithFlags(&b->ev_fetched, cudaEventDisableTiming));
+    if (!b->ev_results) SNPM_CUDA(cudaEventCreateWithFlags(&b->ev_results, cudaEventDisableTiming));
+    SNPM_CUDA(cudaEventRecord(b->ev_results, db->stream));
+    SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_results, 0));
+    if (b->h_tail_cap < int64_t(S)) {
+        if (b->h_tail) cudaFreeHost(b->h_tail);
+        b->h_tail = nullptr;
+        SNPM_CUDA(cudaMallocHost(reinterpret_cast<void **>(&b->h_tail), S * 16));
+        b->h_tail_cap = int64_t(S);
+    }
+    const double *red = b->d_red.as<double>();
+    if (score) SNPM_CUDA(cudaMemcpy2DAsync(score, A * 8, red, pitch, A * 8, S, cudaMemcpyDeviceToHost, st));
+    SNPM_CUDA(cudaMemcpy2DAsync(b->h_tail, 16, red + 2 * A, pitch, 16, S, cudaMemcpyDeviceToHost, st));
+    if (matches) SNPM_CUDA(cudaMemcpyAsync(matches, b->d_matches.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (ninfo) SNPM_CUDA(cudaMemcpyAsync(ninfo, b->d_ninfo64.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, b->d_prob.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (L) SNPM_CUDA(cudaMemcpyAsync(L, b->d_L.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, b->d_LR.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (guard) {
+        if (b->grouped) SNPM_CUDA(cudaMemcpyAsync(guard, b->d_guard.p, S * 4, cudaMemcpyDeviceToHost, st));
+        else memset(guard, 0, S * 4);
+    }
+    if (b->d_status.p) SNPM_CUDA(cudaMemcpyAsync(b->h_status, b->d_status.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    else memset(b->h_status, 0, 8 * sizeof(int));
+    SNPM_CUDA(cudaEventRecord(b->ev_fetched, st));
+    b->pend_m = m;
+    b->fetch_pending = true;
+    return SNPM_OK;
+}
+
+int snpm_batch_fetch_wait(snpm_batch *b) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_fetch_wait: NULL batch");
+    if (!b->fetch_pending) return fail(SNPM_E_STATE, "snpm_batch_fetch_wait: no fetch is pending");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    SNPM_CUDA(cudaEventSynchronize(b->ev_fetched));
+    b->fetch_pending = false;
+    if (b->h_status[0] > 0)
+        return fail(SNPM_E_ARG, "sample markers are not sorted by (database chromosome order, position) or repeat a position (%d places)", b->h_status[0]);
+    if (b->h_status[3] > 0)
+        return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
+    long long viol = 0;
+    for (int64_t s = 0; s < b->S; ++s) {
+        if (b->pend_m) b->pend_m[s] = int64_t(b->h_tail[2 * s]);
+        viol += (long long)b->h_tail[2 * s + 1];
+    }
+    if (viol > 0) return fail(SNPM_E_ASSERT, "provided y is greater than n (%lld accessions; likeliTest, snpmatch.py:43)", viol);
     return SNPM_OK;
 }
 

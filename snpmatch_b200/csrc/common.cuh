@@ -149,4 +149,10 @@ struct snpm_batch {
     cudaEvent_t ev[SNPM_N_EVENTS] = {};
     bool ev_rec[SNPM_N_EVENTS] = {};
     int *h_status = nullptr;  // pinned, 8 ints
+    // asynchronous fetch (snpm_batch_fetch_async / _wait)
+    cudaEvent_t ev_fetched = nullptr, ev_results = nullptr;
+    double *h_tail = nullptr;   // pinned, 2 doubles per sample (matched pairs, y>n count)
+    int64_t h_tail_cap = 0;
+    int64_t *pend_m = nullptr;
+    bool fetch_pending = false;
 };

@@ -134,6 +134,8 @@ SIGNATURES = {
     "snpm_batch_wait": (C.c_int, [_p, _p]),
     "snpm_batch_reduce_buffer": (C.c_int, [_p, _p, _p]),
     "snpm_batch_fetch": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p]),
+    "snpm_batch_fetch_async": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "snpm_batch_fetch_wait": (C.c_int, [_p]),
     "snpm_batch_fetch_pairs": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),
     "snpm_batch_timings": (C.c_int, [_p, _p, C.c_int]),
     "snpm_score": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
@@ -416,6 +418,18 @@ class Batch(object):
         check(load().snpm_batch_fetch(self._h, ptr(r["score"]), ptr(r.get("matches")), ptr(r.get("ninfo")), ptr(r["m"]),
                                       ptr(r.get("prob")), ptr(r.get("L")), ptr(r.get("LR"))))
         return r
+
+    def fetch_async(self, out):
+        """Queue the read-back of the results into `out` (dict of PINNED arrays with the keys of fetch() plus an optional
+        int32 "guard" [S]) behind the batch's kernels; fetch_wait() makes them valid.  Another batch may run in between."""
+        self._pending = out
+        check(load().snpm_batch_fetch_async(self._h, ptr(out.get("score")), ptr(out.get("matches")), ptr(out.get("ninfo")), ptr(out.get("m")),
+                                            ptr(out.get("prob")), ptr(out.get("L")), ptr(out.get("LR")), ptr(out.get("guard"))))
+
+    def fetch_wait(self):
+        check(load().snpm_batch_fetch_wait(self._h))
+        out, self._pending = self._pending, None
+        return out
 
     def fetch_pairs(self, s=0):
         n = int(self.offsets[s + 1] - self.offsets[s])

@@ -212,3 +212,49 @@ def test_grouped_full_shape_properties(lib):
         assert r["ninfo"][i].max() <= r["m"][i] == 45000
     b.close()
     db.close()
+
+
+def test_async_fetch_overlaps_two_batches(lib):
+    """snpm_batch_fetch_async / _wait: the read-back of one batch is queued, another batch runs, both results are right."""
+    n_rows, n_acc = 40000, 500
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    sets = []
+    for j in range(2):
+        samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=2 + 5 * i + j, n_db=1500 + 700 * i, n_extra=50,
+                                     seed=4000 + 10 * j + i) for i in range(3)]
+        sets.append(_concat(samples))
+    ref = []
+    for offs, chrom, p, wei in sets:
+        b = lib.Batch(db, offs, chrom, p, wei)
+        b.run()
+        b.epilogue()
+        ref.append({k: v.copy() for k, v in b.fetch().items()})
+        b.close()
+    batches, outs = [], []
+    for offs, chrom, p, wei in sets:
+        b = lib.Batch(db, offs, chrom, p, wei)
+        b.upload_grouped(lib.group_markers(offs, chrom, p, wei))
+        S = len(offs) - 1
+        out = {k: np.empty((S, n_acc), np.float64) for k in ("score", "prob", "L", "LR")}
+        out.update({k: np.empty((S, n_acc), np.int64) for k in ("matches", "ninfo")})
+        out["m"] = np.empty(S, np.int64)
+        out["guard"] = np.full(S, -1, np.int32)
+        batches.append(b)
+        outs.append(out)
+    with pytest.raises(lib.SnpmError):
+        batches[0].fetch_wait()                      # nothing pending yet
+    for b, out in zip(batches, outs):                # both queued before either is waited for
+        b.run(kernel_mode=lib.KERNEL_GROUPED)
+        b.epilogue()
+        b.fetch_async(out)
+    for j in (1, 0):
+        r = batches[j].fetch_wait()
+        ok = r["guard"] == 0
+        assert ok.all()
+        for i in range(len(r["m"])):
+            _check_against(r, {k: ref[j][k][i] for k in ref[j]}, i)
+    for b in batches:
+        b.close()
+    db.close()
