@@ -17,7 +17,8 @@ samples, each scored on its own exactly as separate `snpmatch inbred` runs would
   cpu_baseline  the CPU oracle (a NumPy restatement of the reference path) on one sample, one core.
 
 N > 1 (torchrun): the panel is sharded by SNP-row ranges, samples are replicated, per-GPU partial
-scores/counts are summed with one NCCL all-reduce, then the epilogue runs on the reduced totals.
+scores/counts are summed with one NCCL reduce-scatter, then every rank runs the epilogue on, and reads back, its
+share of the samples.
 The batch grows with N (samples = N x --samples) so that per-GPU work is fixed: "scaling": "weak".
 
 `--impl reference` times the reference's own CPU path (oracle port; one process per sample on all
@@ -57,7 +58,6 @@ def parse_args():
     ap.add_argument("--markers", type=int, default=N_DB_MARKERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group-chunk", type=int, default=480, help="rows per segment of the grouped kernel")
-    ap.add_argument("--force-grouped", action="store_true", help="grouped counting kernel even when row sharding makes the groups small")
     ap.add_argument("--force-exact", action="store_true", help="order-exact fp64 kernel as the headline path")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     return ap.parse_args()
@@ -70,7 +70,7 @@ def workload_config(args, n_gpus, n_samples):
                         n_samples, args.markers + N_EXTRA_MARKERS, args.markers, args.accessions, args.rows),
         "panel_rows": args.rows, "accessions": args.accessions, "samples_per_step": n_samples,
         "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)", "kernel": "grouped counting kernel (markers ordered by weight triple at parse time)",
-        "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + NCCL all-reduce of per-accession partials" % n_gpus,
+        "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + one NCCL reduce-scatter of the per-accession partials per step (every rank finishes and reads back its share of the samples)" % n_gpus,
         "cache": "inputs larger than L2: each step gathers %.0f MB of distinct panel rows" % (
             n_samples * args.markers * ((args.accessions + 63) // 64 * 16) / 1e6),
     }
@@ -251,6 +251,7 @@ def run_b200_arm(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_pg = dist.new_group(backend="gloo")      # host-side agreement on the (rare) samples to re-score: must not queue behind kernels
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream(device=dev)
 
@@ -287,9 +288,10 @@ def run_b200_arm(args):
         keep.append(t)
         arrs.append(v)
     h_off, h_chr, h_pos, h_wei = arrs
-    out_t = {k: torch.empty((S, n_acc), dtype=torch.float64 if k in ("score", "prob", "L", "LR") else torch.int64).pin_memory()
+    S_loc = S // world                                 # samples whose results this rank finishes and reads back
+    out_t = {k: torch.empty((S_loc, n_acc), dtype=torch.float64 if k in ("score", "prob", "L", "LR") else torch.int64).pin_memory()
              for k in ("score", "matches", "ninfo", "prob", "L", "LR")}
-    out_t["m"] = torch.empty(S, dtype=torch.int64).pin_memory()
+    out_t["m"] = torch.empty(S_loc, dtype=torch.int64).pin_memory()
     out = {k: v.numpy() for k, v in out_t.items()}
 
     batch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)       # position order: the order-exact fp64 kernel
@@ -308,17 +310,29 @@ def run_b200_arm(args):
     gbatch.set_group_chunk(args.group_chunk)
     gbatch.upload_grouped(gs)
 
-    # Row sharding cuts every weight group into `world` pieces; below ~16 rows per group and rank the read-out of the
-    # counters costs more than the order-exact kernel's two fp64 adds per comparison, so the headline path falls back to
-    # that kernel (same decision on every rank: it only looks at the whole samples).
+    # Row sharding cuts every weight group into `world` pieces, which makes the counter read-outs more frequent; measured at
+    # 4 and 8 GPUs the grouped kernel still wins (1.6e13 vs 1.2e13, 2.9e13 vs 2.3e13), so it is the headline path everywhere.
     rows_per_group = args.markers / float(world) / max(1, len(np.unique(samples[0]["wei"], axis=0)))
-    use_grouped = (rows_per_group >= 16.0 or args.force_grouped) and not args.force_exact
+    use_grouped = not args.force_exact
+
+    def reduce_totals(b):
+        # one NCCL reduce-scatter of the per-sample totals: every rank is left with the totals of its S/world samples and
+        # finishes (epilogue) and reads back only those
+        sharding.reduce_scatter_batch(b, dist, dev, rank, world)
+
+    def own_share(b):
+        if world > 1:
+            b.set_result_range(rank * S_loc, S_loc)
+        return b
+
+    own_share(batch)
+    own_share(gbatch)
 
     def device_step(b=None, mode=None):
         b = (gbatch if use_grouped else batch) if b is None else b
         b.run(kernel_mode=lib.KERNEL_GROUPED if b is gbatch else lib.KERNEL_FP64)
         if world > 1:
-            sharding.allreduce_batch(b, dist, dev)          # one NCCL all-reduce of the per-sample totals
+            reduce_totals(b)
         b.epilogue()
 
     def barrier():
@@ -373,18 +387,19 @@ def run_b200_arm(args):
         for _ in range(args.steps):
             device_step(batch)
             exact_kernel_ms.append(batch.timings()["score_ms"])
-        exact_res = {k: v.copy() for k, v in batch.fetch().items()} if rank == 0 else None
+        exact_res = {k: v.copy() for k, v in batch.fetch().items()}
         barrier()
         # ---- called-genotype variant of the same samples (0/1 weights, as BED / GT-only VCF inputs give): popcount kernel
         hard = lib.Batch(db, h_off, h_chr, h_pos, np.concatenate([synth.hard_weights(s["code"][:len(p["pos"])] if world == 1 else
                                                                                      s["code"][sl[0]:sl[1]])
                                                                   for s, p, sl in zip(samples, parts, slices)]))
+        own_share(hard)
         hard_ms, hard_kernel_ms = 0.0, []
 
         def hard_step():
             hard.run(kernel_mode=lib.KERNEL_POPCOUNT)
             if world > 1:
-                sharding.allreduce_batch(hard, dist, dev)
+                reduce_totals(hard)
             hard.epilogue()
         for _ in range(args.warmup):
             hard_step()
@@ -409,6 +424,7 @@ def run_b200_arm(args):
         # memory on the other's copy stream.  Every step uploads its inputs and reads its results back.
         batch2 = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
         batch2.set_group_chunk(args.group_chunk)
+        own_share(batch2)
         pair = [gbatch, batch2]
         rescored = [0]
 
@@ -440,14 +456,28 @@ def run_b200_arm(args):
             b_ = pair[k % 2]
             b_.run(kernel_mode=lib.KERNEL_GROUPED if use_grouped else lib.KERNEL_FP64)
             if world > 1:
-                sharding.allreduce_batch(b_, dist, dev)
+                reduce_totals(b_)
             b_.epilogue()
             b_.fetch_async(outs[k % 2])                      # D2H of step k, queued behind its kernels
 
         def finish(k):
             b_ = pair[k % 2]
-            r = b_.fetch_wait()                              # results of step k are on the host
-            for sidx in np.flatnonzero(r["guard"]):          # int(score) needs the reference's summation order (~1e-4 per sample)
+            r = b_.fetch_wait()                              # results of step k (this rank's share) are on the host
+            flagged = np.flatnonzero(r["guard"])             # int(score) needs the reference's summation order (~1e-4 per sample)
+            if world > 1:
+                # re-scoring a sample is a collective job (every rank holds a row range of the panel): agree on the set
+                n_f = torch.tensor([len(flagged)], dtype=torch.int32)
+                dist.all_reduce(n_f, op=dist.ReduceOp.MAX, group=host_pg)
+                if int(n_f.item()) > 0:
+                    mask = torch.zeros(S, dtype=torch.int32)
+                    mask[rank * S_loc + torch.as_tensor(flagged)] = 1
+                    dist.all_reduce(mask, group=host_pg)
+                    todo = np.flatnonzero(mask.numpy())
+                else:
+                    todo = np.zeros(0, dtype=np.int64)
+            else:
+                todo = flagged
+            for sidx in todo:
                 lo, hi = int(h_off[sidx]), int(h_off[sidx + 1])
                 one = db.scratch_batch([0, hi - lo], h_chr[lo:hi], h_pos[lo:hi], h_wei[lo:hi])
                 one.run()
@@ -455,8 +485,9 @@ def run_b200_arm(args):
                     sharding.allreduce_batch(one, dist, dev)
                 one.epilogue()
                 r1 = one.fetch()
-                for key in r1:
-                    r[key][sidx] = r1[key][0]
+                if sidx // S_loc == rank:
+                    for key in r1:
+                        r[key][sidx - rank * S_loc] = r1[key][0]
                 rescored[0] += 1
             return r
 
@@ -490,14 +521,15 @@ def run_b200_arm(args):
             h2d_bytes = h_off.nbytes + h_chr.nbytes + h_pos.nbytes + (h_idx.nbytes + h_tab.nbytes if coded is not None else h_wei.nbytes)
         clocks = sampler.stop() if rank == 0 else None
 
-    m_per_sample = out["m"].astype(np.int64) if rank == 0 else None
+    m_sum = torch.tensor([float(out["m"].astype(np.int64).sum()), float((guard_resident > 0).sum())], dtype=torch.float64, device=dev)
     tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms, exact_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(m_sum)
     dev_ms, e2e_ms, hard_ms, exact_ms = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
 
     if rank == 0:
-        m_total = int(m_per_sample.sum())
+        m_total = int(m_sum[0])
         comps = m_total * n_acc
         value = comps * args.steps / (dev_ms * 1e-3)
         e2e_value = comps * args.steps / (e2e_ms * 1e-3)
@@ -523,7 +555,7 @@ def run_b200_arm(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, S),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(world * h2d_bytes),
-                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values()) + 4 * S),
+                    "d2h_bytes_per_step": int(world * (sum(v.nbytes for v in out.values()) + 4 * S_loc)),
                     "inputs": "pinned host arrays in grouped order (snpm_group_markers, once at parse time: %.0f ms for the batch): "
                               "chromosome uint8, position int32, weight-triple id uint16 per marker + the table of distinct triples "
                               "(f64); two batches alternate in a software pipeline (H2D of step k+2 and D2H of step k overlap the kernels "
@@ -542,7 +574,7 @@ def run_b200_arm(args):
             "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items() if k.endswith("_ms")},
             "distinct_weight_triples": int(len(gs.table)), "group_chunk_rows": int(args.group_chunk),
             "headline_kernel": "grouped counting kernel" if use_grouped else "order-exact fp64 kernel (row sharding leaves %.1f rows per weight group and rank)" % rows_per_group,
-            "guard_flagged_samples": int((guard_resident > 0).sum()),
+            "guard_flagged_samples": int(m_sum[1]),
             "clocks": clocks,
             "matched_markers_per_step": m_total,
         }
@@ -552,7 +584,7 @@ def run_b200_arm(args):
         h_ach = h_bytes / (hk_ms * 1e-3) / 1e9 if hk_ms > 0 else 0.0
         line["called_genotypes"] = {
             "workload": "same batch with one-hot weights (BED / GT-only VCF inputs), popcount kernel k_score_hard",
-            "value": int(hard_res["m"].sum()) * n_acc * args.steps / (hard_ms * 1e-3), "unit": UNIT, "ms_per_step": hard_ms / args.steps,
+            "value": comps * args.steps / (hard_ms * 1e-3), "unit": UNIT, "ms_per_step": hard_ms / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_score_hard", "achieved": h_ach, "peak": peak, "unit": "GB/s",
                          "frac": h_ach / peak if peak else None, "algorithmic_bytes_per_launch": int(h_bytes), "kernel_ms": hk_ms}}
         xk_ms = float(np.mean(exact_kernel_ms))

@@ -169,6 +169,10 @@ int snpm_batch_epilogue(snpm_batch *b);
 /* wait for the queued work; ms_device = GPU time of the last run+epilogue measured with CUDA
  * events on the db's stream (may be NULL) */
 int snpm_batch_wait(snpm_batch *b, float *ms_device);
+/* restrict snpm_batch_epilogue, the fetches and snpm_batch_guard_counts to samples [first_sample, first_sample + n_samples)
+ * (host arrays then hold n_samples rows); n_samples = -1 restores "all".  For sharded panels: after a reduce-SCATTER of the
+ * reduce buffer every rank finishes and reads back only its share of the samples.  Persists across uploads. */
+int snpm_batch_set_result_range(snpm_batch *b, int64_t first_sample, int64_t n_samples);
 /* device address of the f64 reduce buffer [S, 2*n_acc+2]: per sample score[n_acc],
  * ninfo[n_acc] (as f64, exact), m, y>n violation count — the payload of the cross-GPU sum (8e).
  * Grouped batches: [S, 3*n_acc+2] = fractional part F | ninfo | m | violations | integer part I; the epilogue

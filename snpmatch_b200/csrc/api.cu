@@ -545,11 +545,19 @@ int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *o
 
 int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts) {
     if (!b || !counts) return fail(SNPM_E_ARG, "snpm_batch_guard_counts: NULL argument");
-    if (!b->grouped) { for (int64_t s = 0; s < b->S; ++s) counts[s] = 0; return SNPM_OK; }
+    if (!b->grouped) { for (int64_t s = 0; s < b->rangen(); ++s) counts[s] = 0; return SNPM_OK; }
     if (!b->epilogue_done) return fail(SNPM_E_STATE, "snpm_batch_guard_counts: run the epilogue first");
+    if (b->rangen() == 0) return SNPM_OK;
     SNPM_CUDA(cudaSetDevice(b->db->device));
-    SNPM_CUDA(cudaMemcpyAsync(counts, b->d_guard.p, size_t(b->S) * 4, cudaMemcpyDeviceToHost, b->db->stream));
+    SNPM_CUDA(cudaMemcpyAsync(counts, b->d_guard.as<int32_t>() + b->range0(), size_t(b->rangen()) * 4, cudaMemcpyDeviceToHost, b->db->stream));
     SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
+    return SNPM_OK;
+}
+
+int snpm_batch_set_result_range(snpm_batch *b, int64_t first_sample, int64_t n_samples) {
+    if (!b || first_sample < 0 || n_samples < -1) return fail(SNPM_E_ARG, "snpm_batch_set_result_range: bad range");
+    b->res0 = first_sample;
+    b->resn = n_samples;
     return SNPM_OK;
 }
 
@@ -797,19 +805,24 @@ int snpm_batch_epilogue(snpm_batch *b) {
     if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_epilogue: run the batch first");
     snpm_db *db = b->db;
     SNPM_CUDA(cudaSetDevice(db->device));
+    const int64_t r0 = b->range0(), rn = b->rangen();
+    if (r0 < 0 || rn < 0 || r0 + rn > b->S) return fail(SNPM_E_ARG, "snpm_batch_epilogue: result range [%lld, %lld) outside the %lld samples", (long long)r0, (long long)(r0 + rn), (long long)b->S);
     rec(b, SNPM_EV_EPI_START);
-    if (b->grouped) {
-        // totals (after any cross-GPU reduce) -> score with the reference's truncation, guard counts per sample
-        SNPM_TRY(b->d_guard.ensure(size_t(b->S) * 4));
-        SNPM_CUDA(cudaMemsetAsync(b->d_guard.p, 0, size_t(b->S) * 4, db->stream));
-        dim3 fgrid((db->n_acc + 255) / 256, unsigned(b->S));
-        k_grouped_finalize<<<fgrid, 256, 0, db->stream>>>(b->d_red.as<double>(), db->n_acc, b->d_guard.as<int32_t>());
-        SNPM_KERNEL_CHECK();
-        b->launches += 1;
+    const int64_t pitch = b->red_pitch(), A = db->n_acc;
+    if (rn > 0) {
+        if (b->grouped) {
+            // totals (after any cross-GPU reduce) -> score with the reference's truncation, guard counts per sample
+            SNPM_TRY(b->d_guard.ensure(size_t(b->S) * 4));
+            SNPM_CUDA(cudaMemsetAsync(b->d_guard.as<int32_t>() + r0, 0, size_t(rn) * 4, db->stream));
+            dim3 fgrid((db->n_acc + 255) / 256, unsigned(rn));
+            k_grouped_finalize<<<fgrid, 256, 0, db->stream>>>(b->d_red.as<double>() + r0 * pitch, db->n_acc, b->d_guard.as<int32_t>() + r0);
+            SNPM_KERNEL_CHECK();
+            b->launches += 1;
+        }
+        k_epilogue<<<unsigned(rn), 1024, 0, db->stream>>>(b->d_red.as<double>() + r0 * pitch, pitch, db->n_acc, 1, 0, 0.0,
+                                                        b->d_matches.as<int64_t>() + r0 * A, b->d_ninfo64.as<int64_t>() + r0 * A,
+                                                        b->d_prob.as<double>() + r0 * A, b->d_L.as<double>() + r0 * A, b->d_LR.as<double>() + r0 * A);
     }
-    k_epilogue<<<unsigned(b->S), 1024, 0, db->stream>>>(b->d_red.as<double>(), b->red_pitch(), db->n_acc, 1, 0, 0.0, b->d_matches.as<int64_t>(),
-                                                        b->d_ninfo64.as<int64_t>(), b->d_prob.as<double>(), b->d_L.as<double>(),
-                                                        b->d_LR.as<double>());
     SNPM_KERNEL_CHECK();
     b->launches += 1;
     rec(b, SNPM_EV_EPI_END);
@@ -883,17 +896,20 @@ int snpm_batch_fetch(snpm_batch *b, double *score, int64_t *matches, int64_t *ni
     snpm_db *db = b->db;
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
-    const size_t A = size_t(db->n_acc), S = size_t(b->S), pitch = size_t(b->red_pitch()) * 8;
+    const size_t A = size_t(db->n_acc), S = size_t(b->rangen()), R0 = size_t(b->range0()), pitch = size_t(b->red_pitch()) * 8;
+    if (R0 + S > size_t(b->S)) return fail(SNPM_E_ARG, "snpm_batch_fetch: result range outside the batch");
     if (b->grouped && score && !b->epilogue_done) return fail(SNPM_E_STATE, "snpm_batch_fetch: grouped batches finalise their scores in the epilogue; run it first");
-    const double *red = b->d_red.as<double>();
-    std::vector<double> tail(2 * S);
-    if (score) SNPM_CUDA(cudaMemcpy2DAsync(score, A * 8, red, pitch, A * 8, S, cudaMemcpyDeviceToHost, st));
-    SNPM_CUDA(cudaMemcpy2DAsync(tail.data(), 16, red + 2 * A, pitch, 16, S, cudaMemcpyDeviceToHost, st));
-    if (matches) SNPM_CUDA(cudaMemcpyAsync(matches, b->d_matches.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (ninfo) SNPM_CUDA(cudaMemcpyAsync(ninfo, b->d_ninfo64.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, b->d_prob.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (L) SNPM_CUDA(cudaMemcpyAsync(L, b->d_L.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, b->d_LR.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    const double *red = b->d_red.as<double>() + R0 * size_t(b->red_pitch());
+    std::vector<double> tail(2 * S + 2);
+    if (S > 0) {
+        if (score) SNPM_CUDA(cudaMemcpy2DAsync(score, A * 8, red, pitch, A * 8, S, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpy2DAsync(tail.data(), 16, red + 2 * A, pitch, 16, S, cudaMemcpyDeviceToHost, st));
+        if (matches) SNPM_CUDA(cudaMemcpyAsync(matches, b->d_matches.as<int64_t>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+        if (ninfo) SNPM_CUDA(cudaMemcpyAsync(ninfo, b->d_ninfo64.as<int64_t>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+        if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, b->d_prob.as<double>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+        if (L) SNPM_CUDA(cudaMemcpyAsync(L, b->d_L.as<double>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+        if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, b->d_LR.as<double>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+    }
     SNPM_TRY(snpm_batch_wait(b, nullptr));
     long long viol = 0;
     for (size_t s = 0; s < S; ++s) {
@@ -918,7 +934,8 @@ int snpm_batch_fetch_async(snpm_batch *b, double *score, int64_t *matches, int64
     // the copies run on the batch's copy stream, behind an event that marks the end of its kernels: the read-back does not
     // hold up whatever is queued next on the compute stream
     cudaStream_t st = b->copy_stream;
-    const size_t A = size_t(db->n_acc), S = size_t(b->S), pitch = size_t(b->red_pitch()) * 8;
+    const size_t A = size_t(db->n_acc), S = size_t(b->rangen()), R0 = size_t(b->range0()), pitch = size_t(b->red_pitch()) * 8;
+    if (R0 + S > size_t(b->S) || S == 0) return fail(SNPM_E_ARG, "snpm_batch_fetch_async: empty result range or outside the batch");
     if (!b->ev_fetched) SNPM_CUDA(cudaEventCreateWithFlags(&b->ev_fetched, cudaEventDisableTiming));
     if (!b->ev_results) SNPM_CUDA(cudaEventCreateWithFlags(&b->ev_results, cudaEventDisableTiming));
     SNPM_CUDA(cudaEventRecord(b->ev_results, db->stream));
@@ -929,16 +946,16 @@ int snpm_batch_fetch_async(snpm_batch *b, double *score, int64_t *matches, int64
         SNPM_CUDA(cudaMallocHost(reinterpret_cast<void **>(&b->h_tail), S * 16));
         b->h_tail_cap = int64_t(S);
     }
-    const double *red = b->d_red.as<double>();
+    const double *red = b->d_red.as<double>() + R0 * size_t(b->red_pitch());
     if (score) SNPM_CUDA(cudaMemcpy2DAsync(score, A * 8, red, pitch, A * 8, S, cudaMemcpyDeviceToHost, st));
     SNPM_CUDA(cudaMemcpy2DAsync(b->h_tail, 16, red + 2 * A, pitch, 16, S, cudaMemcpyDeviceToHost, st));
-    if (matches) SNPM_CUDA(cudaMemcpyAsync(matches, b->d_matches.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (ninfo) SNPM_CUDA(cudaMemcpyAsync(ninfo, b->d_ninfo64.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, b->d_prob.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (L) SNPM_CUDA(cudaMemcpyAsync(L, b->d_L.p, S * A * 8, cudaMemcpyDeviceToHost, st));
-    if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, b->d_LR.p, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (matches) SNPM_CUDA(cudaMemcpyAsync(matches, b->d_matches.as<int64_t>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (ninfo) SNPM_CUDA(cudaMemcpyAsync(ninfo, b->d_ninfo64.as<int64_t>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, b->d_prob.as<double>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (L) SNPM_CUDA(cudaMemcpyAsync(L, b->d_L.as<double>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
+    if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, b->d_LR.as<double>() + R0 * A, S * A * 8, cudaMemcpyDeviceToHost, st));
     if (guard) {
-        if (b->grouped) SNPM_CUDA(cudaMemcpyAsync(guard, b->d_guard.p, S * 4, cudaMemcpyDeviceToHost, st));
+        if (b->grouped) SNPM_CUDA(cudaMemcpyAsync(guard, b->d_guard.as<int32_t>() + R0, S * 4, cudaMemcpyDeviceToHost, st));
         else memset(guard, 0, S * 4);
     }
     if (b->d_status.p) SNPM_CUDA(cudaMemcpyAsync(b->h_status, b->d_status.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -960,7 +977,7 @@ int snpm_batch_fetch_wait(snpm_batch *b) {
     if (b->h_status[3] > 0)
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
     long long viol = 0;
-    for (int64_t s = 0; s < b->S; ++s) {
+    for (int64_t s = 0; s < b->rangen(); ++s) {
         if (b->pend_m) b->pend_m[s] = int64_t(b->h_tail[2 * s]);
         viol += (long long)b->h_tail[2 * s + 1];
     }

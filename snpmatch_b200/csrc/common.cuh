@@ -155,4 +155,8 @@ struct snpm_batch {
     int64_t h_tail_cap = 0;
     int64_t *pend_m = nullptr;
     bool fetch_pending = false;
+    // result range (snpm_batch_set_result_range): the epilogue and the fetches work on samples [res0, res0 + resn); resn < 0 = all
+    int64_t res0 = 0, resn = -1;
+    int64_t range0() const { return resn < 0 ? 0 : res0; }
+    int64_t rangen() const { return resn < 0 ? S : resn; }
 };

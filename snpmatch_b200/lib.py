@@ -128,6 +128,7 @@ SIGNATURES = {
     "snpm_batch_upload_grouped": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
     "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
     "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
+    "snpm_batch_set_result_range": (C.c_int, [_p, _i64, _i64]),
     "snpm_batch_set_row_filter": (C.c_int, [_p, _p, _i64]),
     "snpm_batch_run": (C.c_int, [_p, C.c_int, C.c_int]),
     "snpm_batch_epilogue": (C.c_int, [_p]),
@@ -353,13 +354,22 @@ class Batch(object):
         check(load().snpm_batch_upload_grouped(self._h, g.n_samples, ptr(g.offsets), ptr(g.chrom), ptr(g.pos), ptr(g.gid),
                                                ptr(g.table), len(g.table)))
 
+    def set_result_range(self, first_sample=0, n_samples=-1):
+        """Epilogue, fetches and guard counts work on samples [first_sample, first_sample + n_samples) only (-1: all)."""
+        check(load().snpm_batch_set_result_range(self._h, int(first_sample), int(n_samples)))
+        self._res = (int(first_sample), int(n_samples))
+
+    def _n_results(self):
+        r = getattr(self, "_res", (0, -1))
+        return self.n_samples if r[1] < 0 else r[1]
+
     def set_group_chunk(self, rows):
         check(load().snpm_batch_set_group_chunk(self._h, int(rows)))
 
     def guard_counts(self):
         """Per sample: accessions whose int(score) depends on the reference's summation order (grouped batches; see
         snpm_batch_guard_counts).  Re-score those samples with the fp64 kernel."""
-        out = np.zeros(self.n_samples, dtype=np.int32)
+        out = np.zeros(self._n_results(), dtype=np.int32)
         check(load().snpm_batch_guard_counts(self._h, ptr(out)))
         return out
 
@@ -404,7 +414,7 @@ class Batch(object):
         return p.value, n.value
 
     def fetch(self, epilogue=True, out=None):
-        S, A = self.n_samples, self.db.n_acc
+        S, A = self._n_results(), self.db.n_acc
         r = out if out is not None else {}
         if "score" not in r:
             r["score"] = np.empty((S, A), dtype=np.float64)

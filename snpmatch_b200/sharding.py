@@ -156,3 +156,26 @@ def finalize_grouped(buf, n_acc):
     bump = np.floor(v) != want
     v = np.where(bump, np.nextafter(want + 1.0, 0.0), v)
     return v, want.astype(np.int64), ninfo.astype(np.int64), m.astype(np.int64), guard
+
+
+def reduce_scatter_batch(batch, dist, device, rank, world):
+    """Sum the per-sample partial totals of a lib.Batch over all ranks and leave every rank with ITS share of the samples
+    (rows [rank*S/world, (rank+1)*S/world) of the device buffer): half the bytes of an all-reduce on the wire, and the
+    epilogue / read-back of a rank shrink to S/world samples (lib.Batch.set_result_range).  S must be a multiple of world."""
+    import torch
+
+    class _Dev(object):
+        pass
+
+    ptr, n = batch.reduce_buffer()
+    assert n % world == 0 and batch.n_samples % world == 0, "samples must divide evenly over the ranks"
+    holder = _Dev()
+    holder.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    t = torch.as_tensor(holder, device=device)
+    out = getattr(batch, "_rs_out", None)
+    if out is None or out.numel() != n // world:
+        out = torch.empty(n // world, dtype=torch.float64, device=device)
+        batch._rs_out = out
+    dist.reduce_scatter_tensor(out, t)
+    t.view(world, -1)[rank].copy_(out)
+    return out
