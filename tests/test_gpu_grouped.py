@@ -258,3 +258,41 @@ def test_async_fetch_overlaps_two_batches(lib):
     for b in batches:
         b.close()
     db.close()
+
+
+@pytest.mark.parametrize("grouped", [False, True])
+def test_result_range_restricts_epilogue_and_fetch(lib, grouped):
+    """snpm_batch_set_result_range: the share of the samples one rank finishes after a reduce-scatter."""
+    n_rows, n_acc = 30000, 257
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=1 + 3 * i, n_db=900 + 300 * i, n_extra=20, seed=5100 + i)
+               for i in range(4)]
+    offs, chrom, p, wei = _concat(samples)
+    b = lib.Batch(db, offs, chrom, p, wei)
+    mode = lib.KERNEL_GROUPED if grouped else lib.KERNEL_FP64
+    if grouped:
+        b.upload_grouped(lib.group_markers(offs, chrom, p, wei))
+    b.run(kernel_mode=mode)
+    b.epilogue()
+    full = {k: v.copy() for k, v in b.fetch().items()}
+    b.set_result_range(1, 2)
+    b.run(kernel_mode=mode)
+    b.epilogue()
+    part = b.fetch()
+    assert part["score"].shape == (2, n_acc) and len(part["m"]) == 2 and len(b.guard_counts()) == 2
+    for k in full:
+        assert np.array_equal(part[k], full[k][1:3], equal_nan=True), k
+    b.set_result_range(3, 2)                     # past the end
+    b.run(kernel_mode=mode)
+    with pytest.raises(lib.SnpmError):
+        b.epilogue()
+    b.set_result_range()                         # back to all samples
+    b.run(kernel_mode=mode)
+    b.epilogue()
+    again = b.fetch()
+    for k in full:
+        assert np.array_equal(again[k], full[k], equal_nan=True), k
+    b.close()
+    db.close()
