@@ -746,8 +746,8 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
             b->launches += 1;
         }
         rec(b, SNPM_EV_SCORE);
-        dim3 cgrid((db->n_acc + 127) / 128, unsigned(b->S));
-        k_combine_grouped<<<cgrid, 128, 0, st>>>(a.part_score, b->d_part_int.as<int32_t>(), a.part_ninfo, a.a_pad, db->n_acc, a.seg_off, a.mstart,
+        dim3 cgrid((a.a_pad + 127) / 128, unsigned(b->S));
+        k_combine_grouped<<<cgrid, 128, 0, st>>>(a.part_score, b->d_part_int.as<int32_t>(), a.part_ninfo, a.a_pad, db->stride, db->n_acc, a.seg_off, a.mstart,
                                                  b->d_red.as<double>());
         SNPM_KERNEL_CHECK();
         b->launches += 1;

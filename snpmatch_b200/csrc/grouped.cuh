@@ -48,9 +48,9 @@ struct GroupArgs {
     const int32_t *mstart;        // [S+1]
     int32_t S;
     int32_t chunk;
-    double *part_score;           // [nseg, a_pad]  fractional part F of the segment
-    int32_t *part_int;            // [nseg, a_pad]  integer part I (matches of weight-1.0 classes)
-    int32_t *part_ninfo;          // [nseg, a_pad]
+    double *part_score;           // [nseg, 32, stride]  fractional part F of the segment; accession 32 w + b at [b][w]
+    int32_t *part_int;            // [nseg, 32, stride]  integer part I (matches of weight-1.0 classes)
+    int32_t *part_ninfo;          // [nseg, 32, stride]
     int32_t a_pad;
     int32_t wx;                   // words per team slice
     int32_t spc;                  // teams (segments) per CTA
@@ -395,12 +395,14 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     int32_t vi[32], vn[32];
     counter_values(c_int, vi);
     counter_values(c_ninfo, vn);
-    const int64_t o = int64_t(seg) * a.a_pad + int64_t(word) * 32;
+    // segment partials are stored lane-major ([seg][lane 0..31][word]): consecutive threads write consecutive addresses
+    const int64_t o = int64_t(seg) * a.a_pad + word;
+    const int64_t lane_pitch = a.stride;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-        a.part_score[o + b] = F[b];
-        a.part_int[o + b] = vi[b];
-        a.part_ninfo[o + b] = vn[b];
+        a.part_score[o + b * lane_pitch] = F[b];
+        a.part_int[o + b * lane_pitch] = vi[b];
+        a.part_ninfo[o + b * lane_pitch] = vn[b];
     }
 }
 
@@ -436,14 +438,17 @@ __global__ void __launch_bounds__(256) k_expand_chrom(const uint8_t *__restrict_
 // red row layout in grouped mode [3*n_acc + 2]: F[n_acc] | ninfo[n_acc] | matched pairs | y>n violations | I[n_acc]
 // (the first 2*n_acc + 2 entries are laid out as in k_combine; k_grouped_finalize turns F into the score in place)
 __global__ void __launch_bounds__(128) k_combine_grouped(const double *__restrict__ part_score, const int32_t *__restrict__ part_int,
-                                                         const int32_t *__restrict__ part_ninfo, int32_t a_pad, int32_t n_acc,
+                                                         const int32_t *__restrict__ part_ninfo, int32_t a_pad, int32_t stride, int32_t n_acc,
                                                          const int32_t *__restrict__ seg_off, const int32_t *__restrict__ mstart,
                                                          double *__restrict__ red) {
+    // thread -> position p of the lane-major segment partials ([lane b][word w], p = b * stride + w): coalesced reads
     const int s = blockIdx.y;
-    const int acc = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int j0 = seg_off[s], j1 = seg_off[s + 1];
     double *row = red + int64_t(s) * (3 * int64_t(n_acc) + 2);
-    if (acc < n_acc) {
+    const int b = p / stride, w = p - b * stride;
+    const int acc = 32 * w + b;
+    if (p < a_pad && acc < n_acc) {
         double f = 0.0;
         long long ii = 0, ni = 0;
         constexpr int CB = 8;
@@ -453,9 +458,9 @@ __global__ void __launch_bounds__(128) k_combine_grouped(const double *__restric
             int32_t ci[CB], cn[CB];
 #pragma unroll
             for (int k = 0; k < CB; ++k) {
-                v[k] = __ldg(part_score + int64_t(j + k) * a_pad + acc);
-                ci[k] = __ldg(part_int + int64_t(j + k) * a_pad + acc);
-                cn[k] = __ldg(part_ninfo + int64_t(j + k) * a_pad + acc);
+                v[k] = __ldg(part_score + int64_t(j + k) * a_pad + p);
+                ci[k] = __ldg(part_int + int64_t(j + k) * a_pad + p);
+                cn[k] = __ldg(part_ninfo + int64_t(j + k) * a_pad + p);
             }
 #pragma unroll
             for (int k = 0; k < CB; ++k) {
@@ -465,15 +470,15 @@ __global__ void __launch_bounds__(128) k_combine_grouped(const double *__restric
             }
         }
         for (; j < j1; ++j) {
-            f += part_score[int64_t(j) * a_pad + acc];
-            ii += part_int[int64_t(j) * a_pad + acc];
-            ni += part_ninfo[int64_t(j) * a_pad + acc];
+            f += part_score[int64_t(j) * a_pad + p];
+            ii += part_int[int64_t(j) * a_pad + p];
+            ni += part_ninfo[int64_t(j) * a_pad + p];
         }
         row[acc] = f;
         row[n_acc + acc] = double(ni);
         row[2 * n_acc + 2 + acc] = double(ii);
     }
-    if (acc == 0) {
+    if (p == 0) {
         row[2 * n_acc] = double(mstart[s + 1] - mstart[s]);
         row[2 * n_acc + 1] = 0.0;
     }
