@@ -271,7 +271,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     // no predicates.
     const int odd = w & 1;
     const uint32_t pair_ring = smem_u32(ring + (w & ~1));
-    const uint64_t *pair_col = a.packed + (word & ~1);
+    // byte address of a row's pair of columns = base + row * stride_b: one IMAD.WIDE.U32 (32 x 32 -> 64 bit, plus the 64-bit base)
+    const unsigned char *pair_col = reinterpret_cast<const unsigned char *>(a.packed + (word & ~1));
+    const uint32_t stride_b = uint32_t(a.stride) * 8u;
     const unsigned pair_mask = 3u << (threadIdx.x & 30);
     auto issue = [&](int b) {
         const int r0 = b * GR_BLOCK + 8 * odd;
@@ -280,13 +282,13 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
 #pragma unroll
             for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
                 const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
-                cp_async16(slot0 + uint32_t(k4 + 0) * ring_pitch, pair_col + int64_t(rr.x) * stride);
-                cp_async16(slot0 + uint32_t(k4 + 1) * ring_pitch, pair_col + int64_t(rr.y) * stride);
-                cp_async16(slot0 + uint32_t(k4 + 2) * ring_pitch, pair_col + int64_t(rr.z) * stride);
-                cp_async16(slot0 + uint32_t(k4 + 3) * ring_pitch, pair_col + int64_t(rr.w) * stride);
+                cp_async16(slot0 + uint32_t(k4 + 0) * ring_pitch, pair_col + (unsigned long long)(uint32_t(rr.x)) * stride_b);
+                cp_async16(slot0 + uint32_t(k4 + 1) * ring_pitch, pair_col + (unsigned long long)(uint32_t(rr.y)) * stride_b);
+                cp_async16(slot0 + uint32_t(k4 + 2) * ring_pitch, pair_col + (unsigned long long)(uint32_t(rr.z)) * stride_b);
+                cp_async16(slot0 + uint32_t(k4 + 3) * ring_pitch, pair_col + (unsigned long long)(uint32_t(rr.w)) * stride_b);
             }
         } else if (b < n_blocks) {
-            for (int k = 0; k < GR_BLOCK / 2 && r0 + k < n_rows; ++k) cp_async16(slot0 + uint32_t(k) * ring_pitch, pair_col + int64_t(s_row[r0 + k]) * stride);
+            for (int k = 0; k < GR_BLOCK / 2 && r0 + k < n_rows; ++k) cp_async16(slot0 + uint32_t(k) * ring_pitch, pair_col + (unsigned long long)(uint32_t(s_row[r0 + k])) * stride_b);
         }
         cp_async_commit();                        // always: the wait below counts groups
     };
