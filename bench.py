@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--accessions", type=int, default=N_ACC)
     ap.add_argument("--markers", type=int, default=N_DB_MARKERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--group-chunk", type=int, default=480, help="rows per segment of the grouped kernel")
+    ap.add_argument("--group-chunk", type=int, default=320, help="rows per segment of the grouped kernel")
     ap.add_argument("--force-exact", action="store_true", help="order-exact fp64 kernel as the headline path")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     return ap.parse_args()

@@ -29,9 +29,9 @@
 
 namespace snpm {
 
-constexpr int GR_THREADS = 256;                       // 7 teams of 36 threads: one CTA per SM, ~240 registers per thread, no spills
+constexpr int GR_THREADS = 128;                       // 3 teams of 36 threads; two CTAs per SM at ~240 registers per thread, no spills
 constexpr int GR_MAX_WX = 36;                         // words per team (one 1135-accession row)
-constexpr int GR_MAX_TEAMS = 7;
+constexpr int GR_MAX_TEAMS = 3;
 constexpr int GR_BLOCK = 16;                          // rows per step
 constexpr int GR_RING = 64;                           // rows of the per-team ring
 constexpr int GR_INFLIGHT = GR_RING / GR_BLOCK;
@@ -203,7 +203,7 @@ __host__ __device__ __forceinline__ size_t grouped_team_smem(int wx, int chunk) 
 // grid.x = ceil(S * jmax / teams per CTA), grid.y = word slices.  thread -> (team q, word w); a team scores one segment.
 // WX > 0: words per team known at compile time (ring addresses fold into the instructions); WX == 0: a.wx.
 template <bool SKIP_HETS, int WX>
-__global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs a) {
+__global__ void __launch_bounds__(GR_THREADS, 2) k_score_grouped(const GroupArgs a) {
     extern __shared__ __align__(16) unsigned char gr_smem[];
     const int wx = WX ? WX : a.wx;
     const int spc = a.spc;
@@ -274,7 +274,11 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_score_grouped(const GroupArgs
     // byte address of a row's pair of columns = base + row * stride_b: one IMAD.WIDE.U32 (32 x 32 -> 64 bit, plus the 64-bit base)
     const unsigned char *pair_col = reinterpret_cast<const unsigned char *>(a.packed + (word & ~1));
     const uint32_t stride_b = uint32_t(a.stride) * 8u;
-    const unsigned pair_mask = 3u << (threadIdx.x & 30);
+    // The two partners must see each other's copies: a barrier between them.  __syncwarp with a per-pair mask compiles to
+    // MATCH.ANY + REDUX + a divergent branch (11 % of the kernel's stall samples); the whole-warp form is one WARPSYNC.  It is
+    // safe here: every live thread of a warp passes the same barriers per block, threads that have left do not count, and the
+    // extra coupling (a warp may hold lanes of two teams) only makes one team wait for the other's block.
+    constexpr unsigned pair_mask = 0xffffffffu;
     auto issue = [&](int b) {
         const int r0 = b * GR_BLOCK + 8 * odd;
         const uint32_t slot0 = pair_ring + uint32_t(r0 & (GR_RING - 1)) * ring_pitch;

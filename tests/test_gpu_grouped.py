@@ -74,7 +74,7 @@ def test_grouped_kernel_vs_oracle_and_exact_kernel(lib, n_acc, skip):
     # grouped kernel
     g = lib.group_markers(offs, chrom, p, wei)
     assert g is not None and len(g.table) < 5000
-    for chunk in (480, 16, 208, 1008):
+    for chunk in (320, 16, 208, 1008):
         b.set_group_chunk(chunk)
         b.upload_grouped(g)
         b.run(skip_db_hets=skip, kernel_mode=lib.KERNEL_GROUPED)
