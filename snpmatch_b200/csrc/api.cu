@@ -717,7 +717,7 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
             GroupArgs g = {};
             g.packed = db->d_packed; g.stride = db->stride; g.pair_db = a.pair_db; g.pair_gid = b->d_pair_gid.as<uint16_t>();
             g.table = b->d_gtable.as<double>(); g.seg_off = a.seg_off; g.mstart = a.mstart; g.S = a.S; g.chunk = b->gchunk;
-            g.part_score = a.part_score; g.part_int = b->d_part_int.as<int32_t>(); g.part_ninfo = a.part_ninfo; g.a_pad = a.a_pad;
+            g.part_score = a.part_score; g.part_int = b->d_part_int.as<int32_t>(); g.a_pad = a.a_pad;
             const int nsl = (db->stride + GR_MAX_WX - 1) / GR_MAX_WX;
             g.wx = ((db->stride + nsl - 1) / nsl + 1) & ~1;          // even: neighbouring threads copy 16-byte pairs of columns
             g.spc = std::min(GR_THREADS / g.wx, GR_MAX_TEAMS);
@@ -746,8 +746,8 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
             b->launches += 1;
         }
         rec(b, SNPM_EV_SCORE);
-        dim3 cgrid((a.a_pad + 127) / 128, unsigned(b->S));
-        k_combine_grouped<<<cgrid, 128, 0, st>>>(a.part_score, b->d_part_int.as<int32_t>(), a.part_ninfo, a.a_pad, db->stride, db->n_acc, a.seg_off, a.mstart,
+        dim3 cgrid((a.a_pad + 31) / 32, unsigned(b->S));
+        k_combine_grouped<<<cgrid, 32 * CG_PARTS, 0, st>>>(a.part_score, b->d_part_int.as<int32_t>(), a.a_pad, db->stride, db->n_acc, a.seg_off, a.mstart,
                                                  b->d_red.as<double>());
         SNPM_KERNEL_CHECK();
         b->launches += 1;

@@ -49,8 +49,7 @@ struct GroupArgs {
     int32_t S;
     int32_t chunk;
     double *part_score;           // [nseg, 32, stride]  fractional part F of the segment; accession 32 w + b at [b][w]
-    int32_t *part_int;            // [nseg, 32, stride]  integer part I (matches of weight-1.0 classes)
-    int32_t *part_ninfo;          // [nseg, 32, stride]
+    int32_t *part_int;            // [nseg, 32, stride]  low half: integer part I (matches of weight-1.0 classes); high half: ninfo
     int32_t a_pad;
     int32_t wx;                   // words per team slice
     int32_t spc;                  // teams (segments) per CTA
@@ -407,8 +406,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_score_grouped(const GroupArgs
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
         a.part_score[o + b * lane_pitch] = F[b];
-        a.part_int[o + b * lane_pitch] = vi[b];
-        a.part_ninfo[o + b * lane_pitch] = vn[b];
+        a.part_int[o + b * lane_pitch] = vi[b] | (vn[b] << 16);      // both counts are <= 1008 rows: one word carries them
     }
 }
 
@@ -443,50 +441,72 @@ __global__ void __launch_bounds__(256) k_expand_chrom(const uint8_t *__restrict_
 // ---- combine: totals of the segment partials of one sample ----------------------------------------------
 // red row layout in grouped mode [3*n_acc + 2]: F[n_acc] | ninfo[n_acc] | matched pairs | y>n violations | I[n_acc]
 // (the first 2*n_acc + 2 entries are laid out as in k_combine; k_grouped_finalize turns F into the score in place)
-__global__ void __launch_bounds__(128) k_combine_grouped(const double *__restrict__ part_score, const int32_t *__restrict__ part_int,
-                                                         const int32_t *__restrict__ part_ninfo, int32_t a_pad, int32_t stride, int32_t n_acc,
-                                                         const int32_t *__restrict__ seg_off, const int32_t *__restrict__ mstart,
-                                                         double *__restrict__ red) {
-    // thread -> position p of the lane-major segment partials ([lane b][word w], p = b * stride + w): coalesced reads
+constexpr int CG_PARTS = 8;           // warps of a CTA = contiguous parts of a sample's segments, summed in part order at the end
+__global__ void __launch_bounds__(32 * CG_PARTS) k_combine_grouped(const double *__restrict__ part_score, const int32_t *__restrict__ part_int,
+                                                                   int32_t a_pad, int32_t stride, int32_t n_acc,
+                                                                   const int32_t *__restrict__ seg_off, const int32_t *__restrict__ mstart,
+                                                                   double *__restrict__ red) {
+    // thread (x, y) -> position p = 32 * blockIdx.x + x of the lane-major segment partials ([lane b][word w], p = b * stride + w:
+    // coalesced reads), part y of the segments.  The order of the fp64 adds is fixed (segments in order inside a part, parts in
+    // order), so results are reproducible run to run.
+    __shared__ double s_f[CG_PARTS][32];
+    __shared__ long long s_i[CG_PARTS][32], s_n[CG_PARTS][32];
     const int s = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + x;
     const int j0 = seg_off[s], j1 = seg_off[s + 1];
-    double *row = red + int64_t(s) * (3 * int64_t(n_acc) + 2);
-    const int b = p / stride, w = p - b * stride;
-    const int acc = 32 * w + b;
-    if (p < a_pad && acc < n_acc) {
-        double f = 0.0;
-        long long ii = 0, ni = 0;
+    const int per = (j1 - j0 + CG_PARTS - 1) / CG_PARTS;
+    const int ja = min(j1, j0 + y * per), jb = min(j1, ja + per);
+    double f = 0.0;
+    long long ii = 0, ni = 0;
+    if (p < a_pad) {
         constexpr int CB = 8;
-        int j = j0;
-        for (; j + CB <= j1; j += CB) {
+        int j = ja;
+        for (; j + CB <= jb; j += CB) {
             double v[CB];
-            int32_t ci[CB], cn[CB];
+            int32_t ci[CB];
 #pragma unroll
             for (int k = 0; k < CB; ++k) {
                 v[k] = __ldg(part_score + int64_t(j + k) * a_pad + p);
                 ci[k] = __ldg(part_int + int64_t(j + k) * a_pad + p);
-                cn[k] = __ldg(part_ninfo + int64_t(j + k) * a_pad + p);
             }
 #pragma unroll
             for (int k = 0; k < CB; ++k) {
                 f += v[k];
-                ii += ci[k];
-                ni += cn[k];
+                ii += ci[k] & 0xffff;
+                ni += ci[k] >> 16;
             }
         }
-        for (; j < j1; ++j) {
+        for (; j < jb; ++j) {
             f += part_score[int64_t(j) * a_pad + p];
-            ii += part_int[int64_t(j) * a_pad + p];
-            ni += part_ninfo[int64_t(j) * a_pad + p];
+            const int32_t c = part_int[int64_t(j) * a_pad + p];
+            ii += c & 0xffff;
+            ni += c >> 16;
         }
-        row[acc] = f;
-        row[n_acc + acc] = double(ni);
-        row[2 * n_acc + 2 + acc] = double(ii);
     }
-    if (p == 0) {
-        row[2 * n_acc] = double(mstart[s + 1] - mstart[s]);
-        row[2 * n_acc + 1] = 0.0;
+    s_f[y][x] = f;
+    s_i[y][x] = ii;
+    s_n[y][x] = ni;
+    __syncthreads();
+    double *row = red + int64_t(s) * (3 * int64_t(n_acc) + 2);
+    if (y == 0) {
+        const int b = p / stride, w = p - b * stride;
+        const int acc = 32 * w + b;
+        if (p < a_pad && acc < n_acc) {
+#pragma unroll
+            for (int k = 1; k < CG_PARTS; ++k) {
+                f += s_f[k][x];
+                ii += s_i[k][x];
+                ni += s_n[k][x];
+            }
+            row[acc] = f;
+            row[n_acc + acc] = double(ni);
+            row[2 * n_acc + 2 + acc] = double(ii);
+        }
+        if (p == 0) {
+            row[2 * n_acc] = double(mstart[s + 1] - mstart[s]);
+            row[2 * n_acc + 1] = 0.0;
+        }
     }
 }
 
