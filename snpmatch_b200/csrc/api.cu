@@ -121,12 +121,12 @@ int snpm_db_create(int device, int64_t n_rows, int32_t n_acc, const int32_t *pos
     if (e == cudaSuccess && n_chr) e = cudaMemcpyAsync(db->d_chr_regions, chr_regions, size_t(n_chr) * 16, cudaMemcpyHostToDevice, db->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
     if (e != cudaSuccess) { snpm_db_destroy(db); return fail(SNPM_E_CUDA, "snpm_db_create: upload: %s", cudaGetErrorString(e)); }
-    {   // coarse position index for the join: ~16 rows per bucket
+    {   // coarse position index for the join: 2-4 rows per bucket (one table sector + one position sector per marker)
         int64_t span = 0;
         for (int c = 0; c < n_chr; ++c)
             if (chr_regions[2 * c + 1] > chr_regions[2 * c]) span += int64_t(positions[chr_regions[2 * c + 1] - 1]) + 1;
         int shift = 0;
-        while (shift < 30 && (span >> shift) * 16 > std::max<int64_t>(n_rows, 1) * 2) ++shift;     // (span >> shift) buckets ~ n_rows / 16
+        while (shift < 30 && (span >> shift) * 2 > std::max<int64_t>(n_rows, 1)) ++shift;           // (span >> shift) buckets <= n_rows / 2: 2-4 rows per bucket
         std::vector<int32_t> boff(size_t(n_chr) + 1, 0);
         int64_t total = 0;
         for (int c = 0; c < n_chr; ++c) {
