@@ -566,8 +566,8 @@ def run_b200_arm(args):
             "roofline": {"bound": "hbm", "kernel": "k_score_grouped" if use_grouped else "k_score_segments", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this command
-                         # (profiles/r1b_score_grouped_ncu_full.txt); only valid for the default single-GPU workload
-                         "traffic": 1200625000 if (use_grouped and world == 1 and S == 64 and n_rows == N_ROWS and n_acc == N_ACC
+                         # (profiles/r1c_score_grouped_ncu_full.txt); only valid for the default single-GPU workload
+                         "traffic": 1205027000 if (use_grouped and world == 1 and S == 64 and n_rows == N_ROWS and n_acc == N_ACC
                                                    and args.markers == N_DB_MARKERS) else None,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
