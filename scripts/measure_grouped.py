@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--chunks", default="1000")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--hard", action="store_true", help="called genotypes (one-hot weights) instead of PL weights")
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -35,19 +36,19 @@ def main():
     offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in samples])]).astype(np.int64)
     chrom = np.concatenate([s["chr_ix"] for s in samples]).astype(np.int32)
     pos = np.concatenate([s["pos"] for s in samples]).astype(np.int32)
-    wei = np.concatenate([s["wei"] for s in samples])
+    wei = np.concatenate([synth.hard_weights(s["code"]) if args.hard else s["wei"] for s in samples])
     b = lib.Batch(db, offs, chrom, pos, wei)
     out = {"samples": args.samples, "accessions": args.accessions}
     exact = None
     if not args.no_exact:
         ts = []
         for _ in range(args.reps):
-            b.run()
+            b.run(kernel_mode=lib.KERNEL_POPCOUNT if args.hard else lib.KERNEL_FP64)
             b.epilogue()
             b.wait()
             ts.append(b.timings())
         exact = {k: v.copy() for k, v in b.fetch().items()}
-        out["exact"] = {k: float(np.median([t[k] for t in ts])) for k in ts[0]}
+        out["popcount" if args.hard else "exact"] = {k: float(np.median([t[k] for t in ts])) for k in ts[0]}
     import time
     t0 = time.perf_counter()
     gs = lib.group_markers(offs, chrom, pos, wei)

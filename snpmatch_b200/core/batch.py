@@ -46,3 +46,25 @@ def genotype_batch(g, samples, skip_db_hets=False):
         res._attach_fused(r["prob"][i], r["L"][i], r["LR"][i])
         out.append(res)
     return out, {"panel_markers": len(rows), "gemm_ms": r["gemm_ms"]}
+
+
+def genotype_many(g, samples, skip_db_hets=False):
+    """Genotyper.genotyper (snpmatch.py:207-233) for MANY samples with any weights (PL likelihoods or called genotypes) in
+    one device pass: the markers of every sample are ordered by weight triple (host, `lib.group_markers`; what a parser
+    would cache next to <input>.snpmatch.npz) and scored by the counting kernel (csrc/grouped.cuh).  Returns the list of
+    GenotyperOutput, one per sample, with matches / ninfo / overlap identical to Genotyper run sample by sample and
+    likelihoods within 1e-9; samples whose int(score) would depend on the reference's summation order are re-scored by
+    the order-exact kernel inside `lib.score_grouped`."""
+    prepared = [g.prepare_markers(inp.chrs, inp.pos) for inp in samples]
+    offs = np.concatenate([[0], np.cumsum([len(p[2]) for p in prepared])]).astype(np.int64)
+    cid = np.concatenate([p[1] for p in prepared]) if samples else np.zeros(0, np.int32)
+    pos = np.concatenate([p[2] for p in prepared]) if samples else np.zeros(0, np.int32)
+    wei = np.concatenate([np.asarray(inp.wei, dtype=np.float64)[p[0]] for inp, p in zip(samples, prepared)]) if samples else np.zeros((0, 3))
+    r = lib.score_grouped(g.db, offs, cid, pos, wei, skip_db_hets=skip_db_hets)
+    out = []
+    for i, inp in enumerate(samples):
+        m = int(r["m"][i])
+        res = snpmatch.GenotyperOutput(g.g.accessions, r["score"][i], r["ninfo"][i], snpmatch.get_fraction(m, len(inp.pos)), m, inp.dp)
+        res._attach_fused(r["prob"][i], r["L"][i], r["LR"][i])
+        out.append(res)
+    return out

@@ -296,3 +296,28 @@ def test_result_range_restricts_epilogue_and_fetch(lib, grouped):
         assert np.array_equal(again[k], full[k], equal_nan=True), k
     b.close()
     db.close()
+
+
+def test_genotype_many_equals_per_sample_genotyper(lib, tmp_path):
+    """Python mirror: core.batch.genotype_many (grouped kernel, PL and called samples mixed) vs Genotyper sample by sample."""
+    from conftest import load_golden
+    from snpmatch_b200.core import batch, parsers, snp_genotype, snpmatch
+    p = load_golden("small_panel.npz")
+    g = snp_genotype.Genotype.from_arrays(p["snps"], p["positions"], p["chrs"], p["chr_regions"], p["accessions"])
+    inputs = []
+    for i in range(8):
+        s = synth.make_sample(p["positions"], p["chr_regions"], p["chrs"], 40, true_acc=3 + 4 * i, n_db=700 + 90 * i, n_extra=40, seed=600 + i)
+        inp = parsers.ParseInputs("")
+        inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei_hard"] if i % 3 == 2 else s["wei"], s["dp"])
+        inputs.append(inp)
+    for skip in (False, True):
+        results = batch.genotype_many(g, inputs, skip_db_hets=skip)
+        for i, inp in enumerate(inputs):
+            one = snpmatch.Genotyper(inp, g, str(tmp_path / ("m%d" % i)), run_genotyper=False, skip_db_hets=skip).genotyper()
+            got = results[i]
+            assert np.array_equal(got.scores, one.scores) and np.array_equal(got.ninfo, one.ninfo)
+            assert got.num_snps == one.num_snps and got.overlap == one.overlap
+            got.get_likelihoods(); one.get_likelihoods()
+            np.testing.assert_allclose(got.likelis, one.likelis, rtol=RTOL, equal_nan=True)
+            np.testing.assert_allclose(got.lrts, one.lrts, rtol=RTOL, equal_nan=True)
+    g.close()
