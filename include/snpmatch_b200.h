@@ -145,6 +145,12 @@ int snpm_group_markers(int64_t n_samples, const int64_t *offsets, const int32_t 
  * snpm_batch_upload.  Such a batch is scored with snpm_batch_run(mode 2) only; windows and the F1 pass need position order. */
 int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8,
                               const int32_t *s_pos, const uint16_t *gid, const double *table, int32_t n_table);
+/* the same with chromosome id and position of a marker in one word (id << 27 | position; id 31 = not in the panel): 6 bytes per
+ * marker cross the PCIe bus.  snpm_pack_markers (host code) builds the words from snpm_group_markers' output, or answers
+ * SNPM_E_RANGE when a chromosome id exceeds 30 or a position 2^27 - 1 (use snpm_batch_upload_grouped then). */
+int snpm_pack_markers(int64_t n, const uint8_t *chrom_u8, const int32_t *pos, uint32_t *out);
+int snpm_batch_upload_grouped_packed(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
+                                     const uint16_t *gid, const double *table, int32_t n_table);
 /* after snpm_batch_epilogue on a grouped batch: counts[s] = accessions of sample s whose fractional score part lies
  * within the rounding-error bound of an integer, i.e. whose int(score) depends on the reference's own summation order
  * (probability ~1e-7 per accession).  Re-score those samples with mode 0.  All zeros for position-order batches. */

@@ -489,8 +489,8 @@ int snpm_group_markers(int64_t n_samples, const int64_t *offsets, const int32_t 
     return SNPM_OK;
 }
 
-int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8, const int32_t *s_pos,
-                              const uint16_t *gid, const double *table, int32_t n_table) {
+static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8, const int32_t *s_pos,
+                          const uint32_t *packed_cp, const uint16_t *gid, const double *table, int32_t n_table) {
     if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL batch");
     snpm_db *db = b->db;
     if (n_samples < 1 || !offsets || offsets[0] != 0) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: need samples and offsets starting at 0");
@@ -498,7 +498,7 @@ int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *o
         if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: offsets must be non-decreasing");
     const int64_t n = offsets[n_samples];
     if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: %lld markers exceed the 2^31 limit", (long long)n);
-    if (n > 0 && (!chrom_u8 || !s_pos || !gid)) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL marker arrays");
+    if (n > 0 && (!gid || (!packed_cp && (!chrom_u8 || !s_pos)))) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL marker arrays");
     if (!table || n_table < 1 || n_table > 65536) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: weight table must hold 1..65536 triples");
     std::vector<double> t4(size_t(n_table) * 4);
     for (int32_t t = 0; t < n_table; ++t) {
@@ -532,14 +532,41 @@ int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *o
     b->h_gtable.assign(t4.begin(), t4.end());
     SNPM_CUDA(cudaMemcpyAsync(b->d_gtable.p, b->h_gtable.data(), size_t(n_table) * 32, cudaMemcpyHostToDevice, st));
     if (n) {
-        SNPM_CUDA(cudaMemcpyAsync(b->d_chrom8.p, chrom_u8, size_t(n), cudaMemcpyHostToDevice, st));
-        SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, s_pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
         SNPM_CUDA(cudaMemcpyAsync(b->d_gid.p, gid, size_t(n) * 2, cudaMemcpyHostToDevice, st));
-        k_expand_chrom<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_chrom8.as<uint8_t>(), n, b->d_chrom.as<int32_t>());
+        if (packed_cp) {
+            SNPM_TRY(b->d_wei_idx.ensure(size_t(n) * 4));      // staging of the packed words (the buffer is free in grouped mode)
+            SNPM_CUDA(cudaMemcpyAsync(b->d_wei_idx.p, packed_cp, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+            k_expand_packed<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_wei_idx.as<uint32_t>(), n, b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>());
+        } else {
+            SNPM_CUDA(cudaMemcpyAsync(b->d_chrom8.p, chrom_u8, size_t(n), cudaMemcpyHostToDevice, st));
+            SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, s_pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+            k_expand_chrom<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_chrom8.as<uint8_t>(), n, b->d_chrom.as<int32_t>());
+        }
         SNPM_KERNEL_CHECK();
     }
     SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
     b->ran = b->ran_windows = b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8, const int32_t *s_pos,
+                              const uint16_t *gid, const double *table, int32_t n_table) {
+    return upload_grouped(b, n_samples, offsets, chrom_u8, s_pos, nullptr, gid, table, n_table);
+}
+
+int snpm_batch_upload_grouped_packed(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *gid,
+                                     const double *table, int32_t n_table) {
+    return upload_grouped(b, n_samples, offsets, nullptr, nullptr, chrom_pos, gid, table, n_table);
+}
+
+int snpm_pack_markers(int64_t n, const uint8_t *chrom_u8, const int32_t *pos, uint32_t *out) {
+    if (n < 0 || (n > 0 && (!chrom_u8 || !pos || !out))) return fail(SNPM_E_ARG, "snpm_pack_markers: bad arguments");
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t c = chrom_u8[i] == 255 ? 31u : uint32_t(chrom_u8[i]);
+        if ((chrom_u8[i] != 255 && c > 30u) || pos[i] < 0 || pos[i] >= (1 << 27))
+            return fail(SNPM_E_RANGE, "snpm_pack_markers: marker %lld (chromosome id %u, position %d) does not fit 5 + 27 bits", (long long)i, c, pos[i]);
+        out[i] = (c << 27) | uint32_t(pos[i]);
+    }
     return SNPM_OK;
 }
 

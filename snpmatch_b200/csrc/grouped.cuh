@@ -438,6 +438,17 @@ __global__ void __launch_bounds__(256) k_expand_chrom(const uint8_t *__restrict_
     if (i < n) c32[i] = c8[i] == 255 ? -1 : int32_t(c8[i]);
 }
 
+// chromosome id and position in one word: id << 27 | position (ids 0..30, 31 = not in the panel; positions below 2^27)
+__global__ void __launch_bounds__(256) k_expand_packed(const uint32_t *__restrict__ cp, int64_t n, int32_t *__restrict__ c32, int32_t *__restrict__ pos) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t v = cp[i];
+        const uint32_t c = v >> 27;
+        c32[i] = c == 31u ? -1 : int32_t(c);
+        pos[i] = int32_t(v & 0x7ffffffu);
+    }
+}
+
 // ---- combine: totals of the segment partials of one sample ----------------------------------------------
 // red row layout in grouped mode [3*n_acc + 2]: F[n_acc] | ninfo[n_acc] | matched pairs | y>n violations | I[n_acc]
 // (the first 2*n_acc + 2 entries are laid out as in k_combine; k_grouped_finalize turns F into the score in place)

@@ -52,13 +52,23 @@ class GroupedSamples(object):
     offsets int64 [S+1]; chrom uint8 [n] (255 = not in the panel); pos int32 [n]; gid uint16 [n]; table f64 [T,3] in the
     column order of `wei`; order int64 [n] = index of each marker in the arrays it was built from."""
 
-    def __init__(self, offsets, chrom, pos, gid, table, order):
+    def __init__(self, offsets, chrom, pos, gid, table, order, packed=None):
         self.offsets, self.chrom, self.pos, self.gid, self.table, self.order = offsets, chrom, pos, gid, table, order
         self.n_samples = len(offsets) - 1
+        self.packed = packed          # uint32 [n] = chromosome id << 27 | position when everything fits, else None
+
+    def pack(self):
+        """Chromosome id and position of every marker in one word (6 instead of 7 bytes per marker cross PCIe); leaves
+        `packed` None when an id exceeds 30 or a position 2^27 - 1."""
+        out = np.empty(max(len(self.pos), 1), np.uint32)
+        rc = load().snpm_pack_markers(len(self.pos), ptr(self.chrom), ptr(self.pos), ptr(out))
+        self.packed = out[:len(self.pos)] if rc == SNPM_OK else None
+        return self
 
     @property
     def h2d_bytes(self):
-        return int(self.offsets.nbytes + self.chrom.nbytes + self.pos.nbytes + self.gid.nbytes + self.table.size // 3 * 32)
+        marker_bytes = self.packed.nbytes if self.packed is not None else self.chrom.nbytes + self.pos.nbytes
+        return int(self.offsets.nbytes + marker_bytes + self.gid.nbytes + self.table.size // 3 * 32)
 
 
 def group_markers(offsets, s_chrom_id, s_pos, wei, table_cap=65536):
@@ -82,7 +92,7 @@ def group_markers(offsets, s_chrom_id, s_pos, wei, table_cap=65536):
     if rc in (SNPM_E_RANGE, SNPM_E_ARG):
         return None
     check(rc)
-    return GroupedSamples(offsets, chrom[:n], pos[:n], gid[:n], np.ascontiguousarray(table[:max(nt.value, 1)]), order[:n])
+    return GroupedSamples(offsets, chrom[:n], pos[:n], gid[:n], np.ascontiguousarray(table[:max(nt.value, 1)]), order[:n]).pack()
 
 
 class SnpmError(RuntimeError):
@@ -126,6 +136,8 @@ SIGNATURES = {
     "snpm_batch_destroy": (C.c_int, [_p]),
     "snpm_group_markers": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "snpm_batch_upload_grouped": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
+    "snpm_pack_markers": (C.c_int, [_i64, _p, _p, _p]),
+    "snpm_batch_upload_grouped_packed": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32]),
     "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
     "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
     "snpm_batch_set_result_range": (C.c_int, [_p, _i64, _i64]),
@@ -351,8 +363,12 @@ class Batch(object):
         self.n_samples = g.n_samples
         self.offsets = g.offsets
         self._keep = (g,)
-        check(load().snpm_batch_upload_grouped(self._h, g.n_samples, ptr(g.offsets), ptr(g.chrom), ptr(g.pos), ptr(g.gid),
-                                               ptr(g.table), len(g.table)))
+        if g.packed is not None:
+            check(load().snpm_batch_upload_grouped_packed(self._h, g.n_samples, ptr(g.offsets), ptr(g.packed), ptr(g.gid),
+                                                          ptr(g.table), len(g.table)))
+        else:
+            check(load().snpm_batch_upload_grouped(self._h, g.n_samples, ptr(g.offsets), ptr(g.chrom), ptr(g.pos), ptr(g.gid),
+                                                   ptr(g.table), len(g.table)))
 
     def set_result_range(self, first_sample=0, n_samples=-1):
         """Epilogue, fetches and guard counts work on samples [first_sample, first_sample + n_samples) only (-1: all)."""

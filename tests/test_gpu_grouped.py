@@ -126,6 +126,15 @@ def test_grouped_called_genotypes_are_exact(lib):
     assert b.guard_counts().sum() == 0
     for k in ("score", "matches", "ninfo", "m", "prob", "L", "LR"):
         assert np.array_equal(r[k], ref[k], equal_nan=True), k
+    # the unpacked upload (chromosome byte + position word) gives the same
+    assert g.packed is not None
+    g.packed = None
+    b.upload_grouped(g)
+    b.run(kernel_mode=lib.KERNEL_GROUPED)
+    b.epilogue()
+    r2 = b.fetch()
+    for k in ("score", "matches", "ninfo", "m"):
+        assert np.array_equal(r2[k], ref[k]), k
     # a grouped batch refuses the other kernels, windows and the F1 pass
     with pytest.raises(lib.SnpmError):
         b.run(kernel_mode=lib.KERNEL_FP64)

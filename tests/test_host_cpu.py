@@ -166,6 +166,12 @@ def test_group_markers_host_preparation(built_lib):
         assert np.array_equal(np.sort(g.order[lo:hi]), np.arange(lo, hi))
         key = g.gid[lo:hi].astype(np.int64) * (n0 + n1) + g.order[lo:hi]
         assert np.all(np.diff(key) > 0)
+    # chromosome id and position in one word; positions / ids that do not fit leave the unpacked form
+    assert g.packed is not None and np.array_equal(g.packed >> 27, np.where(g.chrom == 255, 31, g.chrom))
+    assert np.array_equal(g.packed & 0x7ffffff, g.pos)
+    big = lib.group_markers(offs, chrom, pos + (1 << 27), wei)
+    assert big is not None and big.packed is None and big.h2d_bytes > g.h2d_bytes
+    assert lib.group_markers(offs, np.where(chrom >= 0, chrom + 40, chrom).astype(np.int32), pos, wei).packed is None
     # inputs the grouped kernel cannot take
     bad = wei.copy()
     bad[3, 1] = -0.5
