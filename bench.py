@@ -498,31 +498,38 @@ def run_b200_arm(args):
             r = b_.fetch_wait()                              # results of step k (this rank's share) are on the host
             flagged = np.flatnonzero(r["guard"])             # int(score) needs the reference's summation order (~1e-4 per sample)
             if world > 1:
-                # re-scoring a sample is a collective job (every rank holds a row range of the panel): agree on the set
-                n_f = torch.tensor([len(flagged)], dtype=torch.int32)
-                dist.all_reduce(n_f, op=dist.ReduceOp.MAX, group=host_pg)
-                if int(n_f.item()) > 0:
-                    mask = torch.zeros(S, dtype=torch.int32)
-                    mask[rank * S_loc + torch.as_tensor(flagged)] = 1
-                    dist.all_reduce(mask, group=host_pg)
-                    todo = np.flatnonzero(mask.numpy())
-                else:
-                    todo = np.zeros(0, dtype=np.int64)
+                # re-scoring a sample is a collective job (every rank holds a row range of the panel): the ranks agree on the
+                # set once, at the end of the run (resolve_flagged), instead of paying a host collective every step
+                pending.extend((k, int(rank * S_loc + sidx)) for sidx in flagged)
             else:
-                todo = flagged
-            for sidx in todo:
-                lo, hi = int(h_off[sidx]), int(h_off[sidx + 1])
-                one = db.scratch_batch([0, hi - lo], h_chr[lo:hi], h_pos[lo:hi], h_wei[lo:hi])
-                one.run()
-                if world > 1:
-                    sharding.allreduce_batch(one, dist, dev)
-                one.epilogue()
-                r1 = one.fetch()
-                if sidx // S_loc == rank:
-                    for key in r1:
-                        r[key][sidx - rank * S_loc] = r1[key][0]
-                rescored[0] += 1
+                for sidx in flagged:
+                    rescore(int(sidx), r)
             return r
+
+        pending = []
+
+        def rescore(sidx, r=None):
+            lo, hi = int(h_off[sidx]), int(h_off[sidx + 1])
+            one = db.scratch_batch([0, hi - lo], h_chr[lo:hi], h_pos[lo:hi], h_wei[lo:hi])
+            one.run()
+            if world > 1:
+                sharding.allreduce_batch(one, dist, dev)
+            one.epilogue()
+            r1 = one.fetch()
+            if r is not None and sidx // S_loc == rank:
+                for key in r1:
+                    r[key][sidx - rank * S_loc] = r1[key][0]
+            rescored[0] += 1
+
+        def resolve_flagged(n, r):
+            """world > 1: one host collective per run; every flagged (step, sample) is re-scored by all ranks together."""
+            mask = torch.zeros((n, S), dtype=torch.int32)
+            for k, sidx in pending:
+                mask[k, sidx] = 1
+            del pending[:]
+            dist.all_reduce(mask, group=host_pg)
+            for k, sidx in zip(*np.nonzero(mask.numpy())):
+                rescore(int(sidx), r if int(k) == n - 1 else None)
 
         def run_pipeline(n):
             """n complete steps, each from the upload of its samples to its results on the host."""
@@ -537,6 +544,8 @@ def run_b200_arm(args):
                 r = finish(k)
                 if k + 2 < n:
                     up(pair[k % 2])                          # H2D of step k+2 into the buffers step k has released
+            if world > 1:
+                resolve_flagged(n, r)
             return r
 
         run_pipeline(max(args.warmup, 1))
