@@ -330,3 +330,30 @@ def test_genotype_many_equals_per_sample_genotyper(lib, tmp_path):
             np.testing.assert_allclose(got.likelis, one.likelis, rtol=RTOL, equal_nan=True)
             np.testing.assert_allclose(got.lrts, one.lrts, rtol=RTOL, equal_nan=True)
     g.close()
+
+
+def test_grouped_edge_cases(lib):
+    """Empty samples, a sample without any panel marker, all-zero weights, a one-accession panel, one marker."""
+    n_rows = 5000
+    pos, regions = synth.panel_positions(n_rows)
+    for n_acc in (1, 40):
+        db = lib.Database(pos, regions, n_acc)
+        db.fill_synthetic(synth.SEED_PANEL)
+        s = synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=0, n_db=300, n_extra=20, seed=77)
+        n = len(s["pos"])
+        miss_pos = np.setdiff1d(np.arange(1, 4000, dtype=np.int64), pos[:regions[0][1]].astype(np.int64))[:50]      # chromosome 0, not in the panel
+        offs = np.array([0, 0, n, n + 50, n + 50 + n, n + 51 + n])
+        chrom = np.concatenate([s["chr_ix"], np.zeros(50, np.int32), s["chr_ix"], s["chr_ix"][:1]])
+        p = np.concatenate([s["pos"], miss_pos, s["pos"], s["pos"][:1]])
+        wei = np.concatenate([s["wei"], np.full((50, 3), 0.5), np.zeros((n, 3)), s["wei"][:1]])
+        b = lib.Batch(db, offs, chrom, p, wei)
+        b.run()
+        b.epilogue()
+        exact = {k: v.copy() for k, v in b.fetch().items()}
+        r = lib.score_grouped(db, offs, chrom, p, wei, batch=b)
+        assert r["m"].tolist() == exact["m"].tolist() and r["m"][0] == 0 and r["m"][2] == 0
+        for i in range(5):
+            _check_against(r, {k: exact[k][i] for k in exact}, i, exact_scores=(i in set(r["rescored"].tolist())))
+        assert np.all(r["matches"][3] == 0) and np.all(np.isnan(r["L"][0])) and np.all(np.isnan(r["L"][3]))
+        b.close()
+        db.close()
