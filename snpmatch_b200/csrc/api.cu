@@ -671,8 +671,8 @@ static int batch_join(snpm_batch *b, int algo) {
         SNPM_KERNEL_CHECK();
         if (b->grouped)
             k_scatter_pairs_grouped<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(),
-                                                                      b->d_gid.as<uint16_t>(), b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(),
-                                                                      b->d_pair_s.as<int32_t>(), b->d_pair_gid.as<uint16_t>());
+                                                                      b->d_gid.as<uint16_t>(), b->n_gtable, b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(),
+                                                                      b->d_pair_s.as<int32_t>(), b->d_pair_gid.as<uint16_t>(), b->d_status.as<int>());
         else
             k_scatter_pairs<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_wei.as<double>(),
                                                               b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(),
@@ -885,6 +885,8 @@ int snpm_batch_wait(snpm_batch *b, float *ms_device) {
         return fail(SNPM_E_ARG, "identity table too short for %d window cells", b->h_status[2]);
     if (b->h_status[3] > 0)
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
+    if (b->h_status[4] > 0)
+        return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table", b->h_status[4]);
     return SNPM_OK;
 }
 
@@ -1003,6 +1005,8 @@ int snpm_batch_fetch_wait(snpm_batch *b) {
         return fail(SNPM_E_ARG, "sample markers are not sorted by (database chromosome order, position) or repeat a position (%d places)", b->h_status[0]);
     if (b->h_status[3] > 0)
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
+    if (b->h_status[4] > 0)
+        return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table", b->h_status[4]);
     long long viol = 0;
     for (int64_t s = 0; s < b->rangen(); ++s) {
         if (b->pend_m) b->pend_m[s] = int64_t(b->h_tail[2 * s]);

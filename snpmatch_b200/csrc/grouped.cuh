@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_score_grouped(const GroupArgs
 // as k_scatter_pairs (join.cuh) but the payload of a pair is its weight-triple id
 __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_grouped(
         const int32_t *__restrict__ match_row, int64_t n, const int32_t *__restrict__ tile_off, const uint16_t *__restrict__ gid,
-        int32_t *__restrict__ prefix, int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s, uint16_t *__restrict__ pair_gid) {
+        int32_t n_table, int32_t *__restrict__ prefix, int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s,
+        uint16_t *__restrict__ pair_gid, int *status) {
     __shared__ int s_warp[33];
     const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
     const int32_t row = i < n ? match_row[i] : -1;
@@ -427,7 +428,12 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_grouped(
         if (flag) {
             pair_db[p] = row;
             pair_s[p] = int32_t(i);
-            pair_gid[p] = gid[i];
+            uint16_t g = gid[i];
+            if (int32_t(g) >= n_table) {            // an id outside the weight table: reported at wait / fetch (status[4])
+                atomicAdd(status + 4, 1);
+                g = 0;
+            }
+            pair_gid[p] = g;
         }
     }
 }

@@ -138,6 +138,13 @@ def test_grouped_called_genotypes_are_exact(lib):
     # a grouped batch refuses the other kernels, windows and the F1 pass
     with pytest.raises(lib.SnpmError):
         b.run(kernel_mode=lib.KERNEL_FP64)
+    # weight-triple ids outside the table are reported, not read
+    bad = lib.GroupedSamples(g.offsets, g.chrom, g.pos, np.full_like(g.gid, 7), g.table, g.order)
+    b.upload_grouped(bad)
+    b.run(kernel_mode=lib.KERNEL_GROUPED)
+    b.epilogue()
+    with pytest.raises(lib.SnpmError):
+        b.fetch()
     b.close()
     db.close()
 
