@@ -225,6 +225,16 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len,
 int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninfo, double *win_L, double *win_LR,
                              uint8_t *win_identical, int32_t *win_num_amb, int32_t *win_nrows,
                              int64_t *matched_s_idx, int64_t capacity, int64_t *n_matched);
+/* The rows of windowscore.txt exactly as the reference keeps them (get_window_data, csmatch.py:57-60), compacted on the
+ * device: for every window with 1 <= num_amb < n_acc its accessions with LR < lr_thres, in accession order.
+ * win_row_off int32 [W+1] cuts the row arrays (accession index, float score, informative sites, likelihood, identity
+ * call) into windows; win_num_amb / win_nrows int32 [W] and matched_s_idx as in snpm_batch_fetch_windows.  capacity in
+ * rows, *n_rows receives the row count (call with NULL row arrays to learn it).  A few KB instead of the 21 bytes x W x A of
+ * the full arrays cross the bus. */
+int snpm_batch_fetch_window_rows(snpm_batch *b, int32_t *win_row_off, int32_t *win_num_amb, int32_t *win_nrows,
+                                 int32_t *row_acc, double *row_score, int32_t *row_ninfo, double *row_L,
+                                 uint8_t *row_identical, int64_t capacity, int64_t *n_rows, int64_t *matched_s_idx,
+                                 int64_t matched_capacity, int64_t *n_matched);
 
 /* ---- A7: simulated F1 pass ----------------------------------------------------------------
  * Replaces the loop body of CrossIdentifier.match_insilico_f1s (csmatch.py:115-126) for sample 0

@@ -111,21 +111,18 @@ class CrossIdentifier(object):
         batch.run_windows(self._skip_db_hets, binLen, win_count, win_off, n_windows, kmax, snpmatch.lr_thres)
         batch.epilogue()
         tot = batch.fetch()
-        w = batch.fetch_windows()
         self.timings = batch.timings()
         accs = g.accessions
         frames = []
         masked = mask_acc_ix is not None
-        for wi in np.flatnonzero(w["nrows"] > 0):
-            sc, ni = w["score"][wi][keep], w["ninfo"][wi][keep]
-            if masked:                                   # likelihoods over the kept accessions only
+        if masked:                                       # likelihoods over the kept accessions only: from the full window arrays
+            w = batch.fetch_windows()
+            for wi in np.flatnonzero(w["nrows"] > 0):
+                sc, ni = w["score"][wi][keep], w["ninfo"][wi][keep]
                 frames.append(self.get_window_data(wi + 1, accs[keep], sc, ni, self.error_rate))
-                continue
-            with np.errstate(invalid="ignore", divide="ignore"):
-                prob = np.where(ni > 0, sc / ni, np.nan)
-                amb = np.flatnonzero(w["LR"][wi] < snpmatch.lr_thres)
-            frames.append(_window_frame(wi + 1, accs, sc, ni, prob, w["L"][wi], w["identical"][wi], int(w["num_amb"][wi]),
-                                        amb, num_lines))
+        else:                                            # the surviving rows of all windows, compacted on the device
+            w = batch.fetch_window_rows()
+            frames.append(_window_rows_frame(w, accs))
         frames = [f for f in frames if len(f)]
         self.windows_data = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=WINDOW_COLUMNS)
         NumMatSNPs = int(tot["m"][0])
@@ -250,6 +247,29 @@ def _window_frame(bin_inds, accs, score, ninfo, prob, lik, identity, num_amb, am
     })
     frame["num_amb"] = int(num_amb)
     frame["window_index"] = int(bin_inds)
+    return frame[WINDOW_COLUMNS]
+
+
+def _window_rows_frame(w, accs):
+    """All rows of windowscore.txt at once from the device-compacted rows (Batch.fetch_window_rows): the same columns and
+    the same text for `score` / `likelihood` as _window_frame builds window by window."""
+    counts = np.diff(w["row_off"]).astype(np.int64)
+    if counts.sum() == 0:
+        return pd.DataFrame(columns=WINDOW_COLUMNS)
+    sc = w["score"]
+    ni = w["ninfo"]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        prob = np.where(ni > 0, sc / ni, np.nan)
+    frame = pd.DataFrame({
+        "acc": np.asarray(accs)[w["acc"]].astype(str),
+        "snps_match": np.array([int(float(x)) for x in _np_str(sc)], dtype=int),
+        "snps_info": ni.astype(int),
+        "score": _np_str(prob),
+        "likelihood": _np_str(w["L"]),
+        "identical": w["identical"].astype(float),
+        "num_amb": np.repeat(w["num_amb"].astype(int), counts),
+        "window_index": np.repeat(np.arange(1, len(counts) + 1, dtype=int), counts),
+    })
     return frame[WINDOW_COLUMNS]
 
 

@@ -605,7 +605,7 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
                       &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
-                      &b->d_win_ident, &b->d_win_amb, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
+                      &b->d_win_ident, &b->d_win_amb, &b->d_win_row_off, &b->d_row_acc, &b->d_row_score, &b->d_row_ninfo, &b->d_row_L, &b->d_row_ident, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
                       &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
@@ -1325,6 +1325,21 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
                                              b->d_win_amb.as<int32_t>(), b->d_status.as<int>());
         SNPM_KERNEL_CHECK();
         b->launches += 1;
+        // the rows the reference keeps, compacted on the device (what snpm_batch_fetch_window_rows reads back)
+        SNPM_TRY(b->d_win_row_off.ensure(size_t(W + 1) * 4));
+        SNPM_TRY(b->d_row_acc.ensure(WA * 4));
+        SNPM_TRY(b->d_row_score.ensure(WA * 8));
+        SNPM_TRY(b->d_row_ninfo.ensure(WA * 4));
+        SNPM_TRY(b->d_row_L.ensure(WA * 8));
+        SNPM_TRY(b->d_row_ident.ensure(WA));
+        k_window_row_offsets<<<1, 1024, 0, st>>>(b->d_win_amb.as<int32_t>(), W, db->n_acc, b->d_win_row_off.as<int32_t>());
+        SNPM_KERNEL_CHECK();
+        k_window_compact<<<W, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, b->d_win_L.as<double>(), b->d_win_LR.as<double>(),
+                                            b->d_win_ident.as<uint8_t>(), b->d_win_row_off.as<int32_t>(), lr_thres, b->d_row_acc.as<int32_t>(),
+                                            b->d_row_score.as<double>(), b->d_row_ninfo.as<int32_t>(), b->d_row_L.as<double>(),
+                                            b->d_row_ident.as<uint8_t>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 2;
     }
     rec(b, SNPM_EV_COMBINE);
     SNPM_CUDA(cudaEventRecord(b->ev_inputs_free, st));
@@ -1370,6 +1385,61 @@ int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninf
         ps.resize(size_t(m_all));
         SNPM_CUDA(cudaMemcpyAsync(ps.data(), b->d_pair_s.p, size_t(m_all) * 4, cudaMemcpyDeviceToHost, st));
         SNPM_CUDA(cudaStreamSynchronize(st));
+        int64_t o = 0;
+        for (size_t w = 0; w < W; ++w)
+            for (int32_t r = wb[w]; r < we[w]; ++r) matched_s_idx[o++] = ps[size_t(r)];
+    }
+    return SNPM_OK;
+}
+
+
+// The rows of windowscore.txt as the reference keeps them (csmatch.py:57-60), compacted on the device: for every window
+// with 1 <= num_amb < n_acc its accessions with LR < lr_thres, in accession order.  win_row_off int32 [W+1] cuts the row
+// arrays into windows; win_num_amb / win_nrows int32 [W] as snpm_batch_fetch_windows.  capacity in rows; *n_rows receives
+// the row count (call with NULL row arrays to learn it).
+int snpm_batch_fetch_window_rows(snpm_batch *b, int32_t *win_row_off, int32_t *win_num_amb, int32_t *win_nrows, int32_t *row_acc,
+                                 double *row_score, int32_t *row_ninfo, double *row_L, uint8_t *row_identical, int64_t capacity,
+                                 int64_t *n_rows, int64_t *matched_s_idx, int64_t matched_capacity, int64_t *n_matched) {
+    if (!b || !n_rows) return fail(SNPM_E_ARG, "snpm_batch_fetch_window_rows: NULL argument");
+    if (!b->ran_windows) return fail(SNPM_E_STATE, "snpm_batch_fetch_window_rows: run the windows first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const size_t W = size_t(b->n_windows);
+    std::vector<int32_t> off(W + 1, 0), wb(W + 1), we(W + 1), ps;
+    if (W) {
+        SNPM_CUDA(cudaMemcpyAsync(off.data(), b->d_win_row_off.p, (W + 1) * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpyAsync(wb.data(), b->d_win_begin.p, W * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpyAsync(we.data(), b->d_win_end.p, W * 4, cudaMemcpyDeviceToHost, st));
+        if (win_num_amb) SNPM_CUDA(cudaMemcpyAsync(win_num_amb, b->d_win_amb.p, W * 4, cudaMemcpyDeviceToHost, st));
+    }
+    int32_t m_all = 0;
+    SNPM_CUDA(cudaMemcpyAsync(&m_all, b->d_prefix.as<int32_t>() + b->n, 4, cudaMemcpyDeviceToHost, st));
+    SNPM_TRY(snpm_batch_wait(b, nullptr));
+    const int64_t R = off[W];
+    *n_rows = R;
+    if (win_row_off) memcpy(win_row_off, off.data(), (W + 1) * 4);
+    int64_t total = 0;
+    for (size_t w = 0; w < W; ++w) {
+        if (win_nrows) win_nrows[w] = we[w] - wb[w];
+        total += we[w] - wb[w];
+    }
+    if (n_matched) *n_matched = total;
+    if (R > 0 && (row_acc || row_score || row_ninfo || row_L || row_identical)) {
+        if (R > capacity) return fail(SNPM_E_ARG, "snpm_batch_fetch_window_rows: capacity %lld < %lld rows", (long long)capacity, (long long)R);
+        if (row_acc) SNPM_CUDA(cudaMemcpyAsync(row_acc, b->d_row_acc.p, size_t(R) * 4, cudaMemcpyDeviceToHost, st));
+        if (row_score) SNPM_CUDA(cudaMemcpyAsync(row_score, b->d_row_score.p, size_t(R) * 8, cudaMemcpyDeviceToHost, st));
+        if (row_ninfo) SNPM_CUDA(cudaMemcpyAsync(row_ninfo, b->d_row_ninfo.p, size_t(R) * 4, cudaMemcpyDeviceToHost, st));
+        if (row_L) SNPM_CUDA(cudaMemcpyAsync(row_L, b->d_row_L.p, size_t(R) * 8, cudaMemcpyDeviceToHost, st));
+        if (row_identical) SNPM_CUDA(cudaMemcpyAsync(row_identical, b->d_row_ident.p, size_t(R), cudaMemcpyDeviceToHost, st));
+    }
+    if (matched_s_idx && total > 0) {
+        if (total > matched_capacity) return fail(SNPM_E_ARG, "snpm_batch_fetch_window_rows: capacity %lld < %lld matched markers", (long long)matched_capacity, (long long)total);
+        ps.resize(size_t(m_all));
+        SNPM_CUDA(cudaMemcpyAsync(ps.data(), b->d_pair_s.p, size_t(m_all) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    SNPM_CUDA(cudaStreamSynchronize(st));
+    if (matched_s_idx && total > 0) {
         int64_t o = 0;
         for (size_t w = 0; w < W; ++w)
             for (int32_t r = wb[w]; r < we[w]; ++r) matched_s_idx[o++] = ps[size_t(r)];

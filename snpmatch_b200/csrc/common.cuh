@@ -129,6 +129,7 @@ struct snpm_batch {
     int64_t bin_len = 0;
     double lr_thres = 3.841;
     snpm::DevBuf d_win_count, d_win_off, d_win_begin, d_win_end, d_kmax, d_win_L, d_win_LR, d_win_ident, d_win_amb;
+    snpm::DevBuf d_win_row_off, d_row_acc, d_row_score, d_row_ninfo, d_row_L, d_row_ident;   // surviving rows, compacted
     // f1
     snpm::DevBuf d_f1_acc, d_f1_part, d_f1_out;
     snpm::DevBuf d_pair_code;

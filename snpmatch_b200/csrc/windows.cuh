@@ -94,4 +94,57 @@ __global__ void __launch_bounds__(256) k_window_epilogue(const double *__restric
     if (threadIdx.x == 0) win_amb[w] = s_cnt;
 }
 
+// ---- compaction of the rows the reference keeps (csmatch.py:57-60) -------------------------------------------------
+// A window contributes its accessions with LR < lr_thres, and only when at least one but not all pass.  win_row_off =
+// exclusive scan of those counts (single CTA); k_window_compact then writes the surviving rows of every window in
+// accession order: accession index, float score, informative sites, likelihood, identity call.
+__global__ void __launch_bounds__(1024) k_window_row_offsets(const int32_t *__restrict__ win_amb, int32_t n_windows, int32_t n_acc,
+                                                             int32_t *__restrict__ win_row_off) {
+    __shared__ int s_warp[33];
+    int carry = 0;
+    for (int base = 0; base < n_windows; base += blockDim.x) {
+        const int w = base + threadIdx.x;
+        int v = 0;
+        if (w < n_windows) {
+            const int amb = win_amb[w];
+            v = (amb >= 1 && amb < n_acc) ? amb : 0;
+        }
+        int total;
+        const int ex = block_excl_scan(v, &total, s_warp);
+        if (w < n_windows) win_row_off[w] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) win_row_off[n_windows] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_window_compact(const double *__restrict__ part_score, const int32_t *__restrict__ part_ninfo,
+                                                        int32_t a_pad, int32_t n_acc, const double *__restrict__ win_L,
+                                                        const double *__restrict__ win_LR, const uint8_t *__restrict__ win_ident,
+                                                        const int32_t *__restrict__ win_row_off, double lr_thres,
+                                                        int32_t *__restrict__ row_acc, double *__restrict__ row_score,
+                                                        int32_t *__restrict__ row_ninfo, double *__restrict__ row_L,
+                                                        uint8_t *__restrict__ row_ident) {
+    __shared__ int s_warp[33];
+    const int w = blockIdx.x;
+    const int out0 = win_row_off[w];
+    if (win_row_off[w + 1] == out0) return;               // nothing survives in this window (whole CTA leaves)
+    const int64_t base = int64_t(w) * n_acc;
+    int carry = 0;
+    for (int a0 = 0; a0 < n_acc; a0 += blockDim.x) {
+        const int acc = a0 + threadIdx.x;
+        const int keep = acc < n_acc && win_LR[base + acc] < lr_thres;
+        int total;
+        const int ex = block_excl_scan(keep, &total, s_warp);
+        if (keep) {
+            const int o = out0 + carry + ex;
+            row_acc[o] = acc;
+            row_score[o] = part_score[int64_t(w) * a_pad + acc];
+            row_ninfo[o] = part_ninfo[int64_t(w) * a_pad + acc];
+            row_L[o] = win_L[base + acc];
+            row_ident[o] = win_ident[base + acc];
+        }
+        carry += total;
+    }
+}
+
 }  // namespace snpm

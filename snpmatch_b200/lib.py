@@ -154,6 +154,7 @@ SIGNATURES = {
     "snpm_score": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "snpm_batch_run_windows": (C.c_int, [_p, C.c_int, _i64, _p, _p, _i32, _p, _i64, _f64]),
     "snpm_batch_fetch_windows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "snpm_batch_fetch_window_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "snpm_batch_f1_pairs": (C.c_int, [_p, _p, _i32, _p, _p]),
     "snpm_score_shared_panel": (C.c_int, [_p, _p, _i64, _p, _i64, C.c_int, _p, _p, _p, _p, _p, _p]),
 }
@@ -483,6 +484,30 @@ class Batch(object):
         m = C.c_int64(0)
         check(load().snpm_batch_fetch_windows(self._h, ptr(r["score"]), ptr(r["ninfo"]), ptr(r["L"]), ptr(r["LR"]),
                                               ptr(r["identical"]), ptr(r["num_amb"]), ptr(r["nrows"]), ptr(tar), n, C.byref(m)))
+        r["matched_s_idx"] = tar[:m.value].copy()
+        return r
+
+    def fetch_window_rows(self):
+        """The surviving rows of every window (csmatch.py:57-60), compacted on the device.  Returns dict(row_off int32 [W+1],
+        num_amb, nrows int32 [W], acc int32 [R], score f64 [R], ninfo int32 [R], L f64 [R], identical uint8 [R],
+        matched_s_idx)."""
+        W = self.n_windows
+        n = int(self.offsets[1])
+        r = {"row_off": np.zeros(W + 1, np.int32), "num_amb": np.zeros(max(W, 1), np.int32), "nrows": np.zeros(max(W, 1), np.int32)}
+        tar = np.empty(max(n, 1), dtype=np.int64)
+        n_rows, m = C.c_int64(0), C.c_int64(0)
+        lib_ = load()
+        check(lib_.snpm_batch_fetch_window_rows(self._h, ptr(r["row_off"]), ptr(r["num_amb"]), ptr(r["nrows"]), None, None, None, None, None,
+                                                0, C.byref(n_rows), ptr(tar), n, C.byref(m)))
+        R = n_rows.value
+        r.update(acc=np.empty(max(R, 1), np.int32), score=np.empty(max(R, 1), np.float64), ninfo=np.empty(max(R, 1), np.int32),
+                 L=np.empty(max(R, 1), np.float64), identical=np.empty(max(R, 1), np.uint8))
+        if R:
+            check(lib_.snpm_batch_fetch_window_rows(self._h, None, None, None, ptr(r["acc"]), ptr(r["score"]), ptr(r["ninfo"]), ptr(r["L"]),
+                                                    ptr(r["identical"]), R, C.byref(n_rows), None, 0, None))
+        for k in ("acc", "score", "ninfo", "L", "identical"):
+            r[k] = r[k][:R]
+        r["num_amb"], r["nrows"] = r["num_amb"][:W], r["nrows"][:W]
         r["matched_s_idx"] = tar[:m.value].copy()
         return r
 

@@ -293,6 +293,24 @@ def test_window_scores_bit_exact_vs_oracle(lib, small_geno, small_panel, sample_
         assert int(win["num_amb"][widx - 1]) == num_amb
         seen[widx - 1] = True
     assert np.array_equal(win["nrows"] > 0, seen)
+    # the surviving rows, compacted on the device (csmatch.py:57-60): exactly the cells the oracle keeps, in accession order
+    rows = b.fetch_window_rows()
+    n_acc = p["snps"].shape[1]
+    assert np.array_equal(rows["num_amb"], win["num_amb"]) and np.array_equal(rows["nrows"], win["nrows"])
+    assert np.array_equal(rows["matched_s_idx"], win["matched_s_idx"])
+    expect_off = [0]
+    for widx in range(1, n_w + 1):
+        amb = int(win["num_amb"][widx - 1])
+        k = np.flatnonzero(win["LR"][widx - 1] < snpmatch.lr_thres) if (win["nrows"][widx - 1] > 0 and 1 <= amb < n_acc) else np.zeros(0, int)
+        lo, hi = rows["row_off"][widx - 1], rows["row_off"][widx]
+        assert hi - lo == len(k), "window %d" % widx
+        assert np.array_equal(rows["acc"][lo:hi], k)
+        assert np.array_equal(rows["score"][lo:hi], win["score"][widx - 1][k])
+        assert np.array_equal(rows["ninfo"][lo:hi], win["ninfo"][widx - 1][k])
+        assert np.array_equal(rows["L"][lo:hi], win["L"][widx - 1][k])
+        assert np.array_equal(rows["identical"][lo:hi], win["identical"][widx - 1][k])
+        expect_off.append(expect_off[-1] + len(k))
+    assert rows["row_off"].tolist() == expect_off and expect_off[-1] > 0
     b.close()
 
 
