@@ -75,6 +75,9 @@ int snpm_db_read_packed(snpm_db *db, int64_t row0, int64_t n, uint64_t *out);
 /* --refine support: flags[r] = 1 when the selected accession columns carry at least two different called genotypes on
  * row r — Genotype.identify_segregating_snps (snp_genotype.py:188-211, segregting_snps :378-383).  flags uint8[n_rows]. */
 int snpm_db_segregating_rows(snpm_db *db, const int32_t *acc_idx, int32_t n_sel, uint8_t *flags);
+/* whole accession columns: out int8 [n_sel, n_rows] (row-contiguous per column) = g_acc.snps[:, acc_idx[c]] of the reference's
+ * column-chunked file (simulate.py:15,36-37; genotype_cross.py:97-98; csmatch.py:116-117), served by the one resident copy. */
+int snpm_db_read_columns(snpm_db *db, const int32_t *acc_idx, int32_t n_sel, int8_t *out);
 int64_t snpm_db_n_rows(const snpm_db *db);
 int32_t snpm_db_n_acc(const snpm_db *db);
 int32_t snpm_db_row_words(const snpm_db *db);
@@ -242,6 +245,14 @@ int snpm_batch_fetch_window_rows(snpm_batch *b, int32_t *win_row_off, int32_t *w
  * given accession columns.  pair_score f64[P], pair_ninfo int64[P]. */
 int snpm_batch_f1_pairs(snpm_batch *b, const int32_t *acc_idx, int32_t n_top,
                         double *pair_score, int64_t *pair_ninfo);
+
+/* ---- 8(f)-3: pairwiseScore ------------------------------------------------------------------
+ * The counting loop of pairwiseScore (snpmatch.py:291-297) over the matched marker pairs (idx1, idx2: outputs of the join,
+ * snpmatch.py:276-284) of two samples: common[c] = pairs on chromosome c, matches[c] = pairs whose genotype strings are
+ * equal.  chrom1 int32[n1] = chromosome id of every marker of sample 1 (0..n_chr-1; others are not counted), gt1 int32[n1]
+ * / gt2 int32[n2] = ids of the genotype strings in a table shared by both samples.  common/matches int64[n_chr]. */
+int snpm_pair_match_counts(int device, const int64_t *idx1, const int64_t *idx2, int64_t m, const int32_t *chrom1, const int32_t *gt1,
+                           int64_t n1, const int32_t *gt2, int64_t n2, int32_t n_chr, int64_t *common, int64_t *matches);
 
 /* ---- A9: batched scoring on a shared marker panel (tensor cores) ------------------------------
  * No reference symbol: the reference scores many samples as one process per sample (README.md:9).  S samples of CALLED

@@ -266,6 +266,116 @@ def gen_workflow_cases(ref):
     print("workflow cases:", sorted(index))
 
 
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {str(k): _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    if isinstance(x, (np.floating, float)):
+        return None if np.isnan(x) else float(x)
+    return x
+
+
+def gen_pairsnp_cases(ref):
+    """pairwiseScore (snpmatch.py:270-309) of the reference on npz inputs, with and without a database."""
+    rng = np.random.default_rng(21)
+    panel = dict(np.load(os.path.join(GOLD, "small_panel.npz")))
+    gts = np.array(["0/0", "1/1", "0/1", "1|1", "0|0", "1/0"])
+    tmp = tempfile.mkdtemp(prefix="snpm_pairsnp_")
+    out, index = {}, {}
+
+    def sample(n_db, n_extra, prefix):
+        rows = np.sort(rng.choice(len(panel["positions"]), n_db, replace=False))
+        starts = panel["chr_regions"][:, 0]
+        chrs = np.char.add(prefix, panel["chrs"].astype("U")[np.searchsorted(starts, rows, side="right") - 1])
+        pos = panel["positions"][rows].astype(np.int64)
+        # extra markers that are not in the panel, on chromosome 1 and on a contig the panel lacks
+        extra_pos = np.setdiff1d(rng.choice(200000, n_extra) + 1, panel["positions"][:int(panel["chr_regions"][0, 1])])
+        chrs = np.concatenate([np.repeat(prefix + "1", len(extra_pos)), chrs, np.repeat(prefix + "M", 5)])
+        pos = np.concatenate([extra_pos, pos, np.arange(1, 6)])
+        order = np.lexsort((pos, chrs))
+        chrs, pos = chrs[order], pos[order]
+        keep = np.ones(len(pos), dtype=bool)
+        keep[1:] = ~((chrs[1:] == chrs[:-1]) & (pos[1:] == pos[:-1]))
+        chrs, pos = chrs[keep], pos[keep]
+        return chrs, pos, gts[rng.integers(0, 4, len(pos))]
+
+    class _G(ref.snp_genotype.Genotype):
+        def __init__(self, hdf5_file, hdf5_acc_file=None):
+            g = rh.make_reference_genotype(ref, panel["snps"], panel["positions"], panel["chrs"], panel["chr_regions"], panel["accessions"])
+            self.__dict__.update(g.__dict__)
+
+    cases = [(1500, 200, "Chr", 1200, 150, ""), (800, 50, "", 2500, 0, "chr"), (30, 5, "", 40, 5, "")]
+    for i, (a, b, pa, c, d, pb) in enumerate(cases):
+        c1, p1, g1 = sample(a, b, pa)
+        c2, p2, g2 = sample(c, d, pb)
+        if i == 2:                                   # disjoint chromosomes on purpose: no common chromosome
+            c2 = np.repeat("7", len(c2))
+            p2 = np.arange(1, len(c2) + 1)
+        f1, f2 = os.path.join(tmp, "s%d_a.npz" % i), os.path.join(tmp, "s%d_b.npz" % i)
+        for f, cc, pp, gg in ((f1, c1, p1, g1), (f2, c2, p2, g2)):
+            np.savez(f, chr=cc, pos=pp, gt=gg, wei=np.ones((len(pp), 3)), dp=np.ones(len(pp)))
+        for k, v in (("c1", c1), ("p1", p1), ("g1", g1), ("c2", c2), ("p2", p2), ("g2", g2)):
+            out["p%d_%s" % (i, k)] = v
+        index["p%d_plain" % i] = _jsonable(ref.snpmatch.pairwiseScore(f1, f2, False, outFile=None, hdf5File=None))
+        orig = ref.snp_genotype.Genotype
+        ref.snp_genotype.Genotype = _G
+        try:
+            r = ref.snpmatch.pairwiseScore(f1, f2, False, outFile=None, hdf5File="panel")
+        finally:
+            ref.snp_genotype.Genotype = orig
+        r.pop("hdf5")
+        index["p%d_db" % i] = _jsonable(r)
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, "pairsnp.npz"), **out)
+    with open(os.path.join(GOLD, "pairsnp.json"), "w") as fh:
+        json.dump(index, fh, indent=1, sort_keys=True)
+    shutil.rmtree(tmp, ignore_errors=True)
+    print("pairsnp: %d cases" % len(cases))
+
+
+def gen_simulate_cases(ref):
+    """simulateSNPs / simulateSNPs_F1 (simulate.py:10-60) of the reference under fixed np.random seeds.  The stand-in
+    database carries its accession ids as text: the reference compares them with `str` arguments (simulate.py:12,34), which
+    cannot match the bytes array of HDF5Genotype under Python 3."""
+    from snpmatch.core import simulate as r_sim
+    import pandas as pd
+    pd.set_option("future.infer_string", False)     # simulate.py:26 writes integers into a column of strings (object dtype)
+    panel = dict(np.load(os.path.join(GOLD, "small_panel.npz")))
+    G = rh.make_reference_genotype(ref, panel["snps"], panel["positions"], panel["chrs"], panel["chr_regions"], panel["accessions"])
+    G.g.accessions = G.g.accessions.astype("U")
+    ids = G.g.accessions
+    out = {}
+    cases = [("inbred", ids[7], 500, 0.01, 1, 11), ("inbred", ids[0], 64, 0.0, 1, 12), ("inbred", ids[3], 1200, 0.1, 1, 13),
+             ("f1", "%sx%s" % (ids[3], ids[21]), 700, 0.01, 1, 14), ("f1", "%sx%s" % (ids[5], ids[6]), 300, 0.05, 0.3, 15)]
+    for i, (kind, acc, n, err, rm, seed) in enumerate(cases):
+        np.random.seed(seed)
+        if kind == "inbred":
+            df = r_sim.simulateSNPs(G, str(acc), n, outFile=None, err_rate=err)
+            gt = np.array([g.decode() if isinstance(g, bytes) else str(g) for g in df.iloc[:, 2]])
+        else:
+            # simulate.py:57 assigns the bytes GT strings into an int64 column, which pandas >= 3 refuses.  The conversion
+            # is routed around that one assignment: the reference's converter is applied to the returned binary column.
+            real = ref.parsers.snp_binary_to_gt
+            ref.parsers.snp_binary_to_gt = lambda b: np.array(b)
+            try:
+                df = r_sim.simulateSNPs_F1(G, str(acc), n, None, err, rm)
+            finally:
+                ref.parsers.snp_binary_to_gt = real
+            gt = np.array([g.decode() for g in real(np.array(df.iloc[:, 2]))])
+        out["s%d_kind" % i] = np.array(kind)
+        out["s%d_acc" % i] = np.array(str(acc))
+        out["s%d_args" % i] = np.array([n, err, rm, seed], dtype=np.float64)
+        out["s%d_chr" % i] = np.array(df.iloc[:, 0]).astype("U")
+        out["s%d_pos" % i] = np.array(df.iloc[:, 1]).astype(np.int64)
+        out["s%d_gt" % i] = gt
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, "simulate.npz"), **out)
+    print("simulate: %d cases" % len(cases))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = rh.load_reference()
@@ -273,6 +383,8 @@ def main():
     gen_join_cases(ref)
     gen_epilogue_cases(ref)
     gen_workflow_cases(ref)
+    gen_pairsnp_cases(ref)
+    gen_simulate_cases(ref)
 
 
 if __name__ == "__main__":

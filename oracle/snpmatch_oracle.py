@@ -379,6 +379,74 @@ def segregating_rows(db_snps, accs_ix):
 
 
 # --------------------------------------------------------------------------
+# 8(f)-3 — pairsnp and simulate
+# --------------------------------------------------------------------------
+def pairwise_score(chrs1, pos1, gt1, chrs2, pos2, gt2, name1="1", name2="2", db=None):
+    """snpmatch.py:270-309 — pairwiseScore on parsed inputs.  db = (db_chromosome_labels, db_positions) restricts sample 1
+    to the database positions first (:276-281).  Returns the stats dict of the reference (without the 'hdf5' path)."""
+    chrs1, chrs2 = np.asarray(chrs1, dtype="str"), np.asarray(chrs2, dtype="str")
+    pos1, pos2 = np.asarray(pos1), np.asarray(pos2)
+    gt1, gt2 = np.asarray(gt1, dtype="str"), np.asarray(gt2, dtype="str")
+    if db is not None:
+        c1 = get_common_positions(db[0], db[1], chrs1, pos1)
+        ci = get_common_positions(chrs1[c1[1]], pos1[c1[1]], chrs2, pos2)
+        ci = (c1[1][ci[0]], ci[1])
+    else:
+        ci = get_common_positions(chrs1, pos1, chrs2, pos2)
+    unique_1 = len(chrs1) - len(ci[0])
+    unique_2 = len(chrs2) - len(ci[0])
+    g1, g2 = normalize_chr_names(chrs1), normalize_chr_names(chrs2)
+    stats = {}
+    common, scores = [], []
+    for i in np.intersect1d(first_appearance_ids(g1), first_appearance_ids(g2)):
+        per = np.flatnonzero(g1[ci[0]] == i)
+        t_common = len(per)
+        t_scores = int(np.sum(gt1[ci[0][per]] == gt2[ci[1][per]]))
+        stats[str(i)] = [get_fraction(t_scores, t_common), t_common]
+        common.append(t_common)
+        scores.append(t_scores)
+    stats["matches"] = [get_fraction(int(np.sum(scores)), int(np.sum(common))), int(np.sum(common))]
+    stats["unique"] = {name1: [get_fraction(unique_1, len(chrs1)), len(chrs1)], name2: [get_fraction(unique_2, len(chrs2)), len(chrs2)]}
+    return stats
+
+
+def simulate_snps(acc_snp, row_chrs, row_pos, num_snps, err_rate, rng=np.random):
+    """simulate.py:10-31 — draws in the reference's order from `rng` (np.random there): marker subset, rows to corrupt,
+    replacement calls.  Returns (chr, pos, binary call) of the simulated sample."""
+    acc_snp = np.asarray(acc_snp)
+    informative = np.flatnonzero(acc_snp >= 0)
+    pick = np.sort(rng.choice(np.arange(informative.shape[0]), num_snps, replace=False))
+    rows = informative[pick]
+    snp = acc_snp[rows].astype(np.int8)
+    n_change = int(err_rate * num_snps)
+    values = rng.choice(3, n_change)            # simulate.py:26 is an assignment: its right-hand side is drawn first
+    change = np.sort(rng.choice(np.arange(num_snps), n_change, replace=False))
+    snp[change] = values
+    return np.asarray(row_chrs)[rows], np.asarray(row_pos)[rows], snp
+
+
+def simulate_snps_f1(snps_p1, snps_p2, row_chrs, row_pos, num_snps, err_rate, rm_hets=1, rng=np.random):
+    """simulate.py:33-60."""
+    p1, p2 = np.asarray(snps_p1), np.asarray(snps_p2)
+    common_ix = np.flatnonzero((p1 >= 0) & (p2 >= 0) & (p1 < 2) & (p2 < 2))
+    seg = np.flatnonzero(p1[common_ix] != p2[common_ix])
+    same = np.setdiff1d(np.arange(len(common_ix)), seg)
+    common_snps = np.zeros(len(common_ix), dtype="int8")
+    common_snps[seg] = 2
+    common_snps[same] = p1[common_ix[same]]
+    pick = np.sort(rng.choice(np.arange(len(common_ix)), num_snps, replace=False))
+    snp = common_snps[pick].astype(int)
+    n_change = int(err_rate * num_snps)
+    values = rng.choice(2, n_change)            # simulate.py:52: right-hand side first
+    change = np.sort(rng.choice(np.flatnonzero(snp != 2), n_change, replace=False))
+    snp[change] = values
+    het_ix = np.flatnonzero(snp == 2)
+    snp[het_ix] = rng.choice(3, het_ix.shape[0], p=[(1 - rm_hets) / 2, (1 - rm_hets) / 2, rm_hets])
+    rows = common_ix[pick]
+    return np.asarray(row_chrs)[rows], np.asarray(row_pos)[rows], snp.astype(np.int8)
+
+
+# --------------------------------------------------------------------------
 # data-format helper shared by the tests (not reference behaviour)
 # --------------------------------------------------------------------------
 def pack_2bit_words(db_snps):

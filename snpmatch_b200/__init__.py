@@ -2,7 +2,8 @@
 snpmatch_b200 — B200-native genotype-matching hot path behind SNPmatch's `inbred` / `cross` interface.
 
 The command line mirrors the reference's `snpmatch/__init__.py` for the two sub-commands on the
-matching path (`inbred`, `cross`: flags of __init__.py:44-63) plus `parser` (:88-92); the other
+matching path (`inbred`, `cross`: flags of __init__.py:44-63), `parser` (:80-84) and the callers next to the
+path that work on the resident panel (`pairsnp` :86-92, `simulate` :101-111); the other
 sub-commands of the reference are outside this package's scope.
 """
 import argparse
@@ -57,6 +58,18 @@ def snpmatch_parser(args):
     parsers.potatoParser(inFile=args['inFile'], logDebug=args['logDebug'], outFile=args['outFile'])
 
 
+def snpmatch_paircomparions(args):
+    check_file(args['inFile_1'])
+    check_file(args['inFile_2'])
+    from .core import snpmatch
+    snpmatch.pairwiseScore(args['inFile_1'], args['inFile_2'], args['logDebug'], args['outFile'], args['hdf5File'])
+
+
+def simulate_snps(args):
+    from .core import simulate
+    simulate.potatoSimulate(args)
+
+
 def get_options(description, version_message):
     p = argparse.ArgumentParser(description=description)
     p.add_argument('-V', '--version', action='version', version=version_message)
@@ -88,6 +101,26 @@ def get_options(description, version_message):
     parser.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
     parser.add_argument("-o", "--output", dest="outFile", help="output + .npz file is generater required for SNPmatch")
     parser.set_defaults(func=snpmatch_parser)
+
+    pair = sub.add_parser('pairsnp', help="pairwise comparison of two snp files")
+    pair.add_argument("-i", "--input_file_1", dest="inFile_1", help="VCF/BED file for the variants in the sample one")
+    pair.add_argument("-j", "--input_file_2", dest="inFile_2", help="VCF/BED file for the variants in the sample two")
+    pair.add_argument("-d", "--hdf5_file", dest="hdf5File", default=None, help=db_help)
+    pair.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    pair.add_argument("-o", "--output", dest="outFile", default="pairsnp", help="output json file")
+    pair.set_defaults(func=snpmatch_paircomparions)
+
+    sim = sub.add_parser('simulate', help="Given SNP database, check the genotyping efficiency randomly selecting 'n' number of SNPs")
+    sim.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
+    sim.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility)")
+    sim.add_argument("-a", "--ecotype_id", dest="AccID", help="Ecotype ID you want draw the SNPs")
+    sim.add_argument("-n", "--number_of_snps", dest="numSNPs", help="number of SNPs to draw in random to genotype the sample", type=int)
+    sim.add_argument("-p", "--error_rate", dest="err_rate", help="error rate while matching the SNPs, error rate of 0 gives perfect match to the accession", default=0.001, type=float)
+    sim.add_argument("--f1", action="store_true", dest="simF1", default=False, help="Simulate SNPs for an F1, give parents as 1061x1062 in argument '-a'")
+    sim.add_argument("--het_frac", default=1, type=float, dest="rm_het", help="For simulated F1s: fraction of segregating sites kept heterozygous; the rest become homozygous ref or alt with equal probability")
+    sim.add_argument("-o", "--output", dest="outFile", help="Output file with scores")
+    sim.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    sim.set_defaults(func=simulate_snps)
     return p
 
 

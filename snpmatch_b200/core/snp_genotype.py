@@ -53,6 +53,14 @@ class _SnpsView(object):
         if not isinstance(key, tuple):
             key = (key, slice(None))
         rows, cols = key
+        if isinstance(rows, slice) and rows == slice(None) and not isinstance(cols, slice):
+            # whole columns (g_acc.snps[:, ix], csmatch.py:116, simulate.py:15): a column kernel on the resident rows,
+            # one sector per row instead of unpacking the panel
+            scalar_col = np.isscalar(cols)
+            ix = np.atleast_1d(np.asarray(cols, dtype=np.int64))
+            ix = np.where(ix < 0, ix + n_acc, ix)
+            out = self._panel.db.read_columns(ix)
+            return out[0] if scalar_col else np.ascontiguousarray(out.T)
         if isinstance(rows, slice):
             rows = np.arange(*rows.indices(n_rows))
             scalar_row = False

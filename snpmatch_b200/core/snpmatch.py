@@ -4,13 +4,14 @@
 Mirrors the public surface of the reference's `snpmatch/core/snpmatch.py`: module constants
 (:17-19), `get_fraction` (:25-28), `likeliTest` (:40-55), `np_test_identity` (:57-72),
 `matchGTsAccs` (:74-89), `GenotyperOutput` (:91-168), `Genotyper` (:170-241), `getHeterozygosity`
-(:244-253), `potatoGenotyper` (:256-268).  All array arithmetic of the path — the join, the
+(:244-253), `potatoGenotyper` (:256-268), `pairwiseScore` (:270-309).  All array arithmetic of the path — the join, the
 per-accession reduction, truncation, probabilities, likelihoods and ratios — runs in
 libsnpmatch_b200 on the GPU (snpmatch_b200/csrc); this file only prepares buffers and writes the
 reference's output files (`scores.txt`, `matches.json`).
 """
 import json
 import logging
+import os
 import sys
 
 import numpy as np
@@ -306,3 +307,51 @@ def potatoGenotyper(args):
         return None
     Genotyper(inputs, g, args['outFile'], run_genotyper=True, skip_db_hets=args['skip_db_hets'])
     log.info("finished!")
+
+
+def pairwiseScore(inFile_1, inFile_2, logDebug, outFile=None, hdf5File=None, device=0):
+    """`snpmatch pairsnp` (snpmatch.py:270-309): fraction of identical genotype strings among the markers two samples
+    share, per chromosome and overall, optionally restricted to the positions of a database.  Both joins and the counting
+    loop (snpmatch.py:291-297) run on the GPU; the returned dict has the reference's keys and values.  Unlike the reference
+    under Python 3 (its json.dumps trips over numpy integers, snpmatch.py:307) the output file is written."""
+    snpmatch_stats = {}
+    log.info("loading input files")
+    inputs_1 = parsers.ParseInputs(inFile=inFile_1, logDebug=logDebug)
+    inputs_2 = parsers.ParseInputs(inFile=inFile_2, logDebug=logDebug)
+    if hdf5File is not None:
+        log.info("loading database file to identify common SNP positions")
+        g = hdf5File if isinstance(hdf5File, snp_genotype.Genotype) else snp_genotype.Genotype(hdf5File, None, device=device)
+        snpmatch_stats['hdf5'] = hdf5File if not isinstance(hdf5File, snp_genotype.Genotype) else "resident"
+        commonSNPs_1 = g.get_positions_idxs(inputs_1.chrs, inputs_1.pos)
+        common_inds = snp_genotype.Genotype.get_common_positions(inputs_1.chrs[commonSNPs_1[1]], inputs_1.pos[commonSNPs_1[1]],
+                                                                 inputs_2.chrs, inputs_2.pos, device=device)
+        common_inds = (commonSNPs_1[1][common_inds[0]], common_inds[1])
+    else:
+        log.info("identify common positions")
+        common_inds = snp_genotype.Genotype.get_common_positions(inputs_1.chrs, inputs_1.pos, inputs_2.chrs, inputs_2.pos, device=device)
+    log.info("done!")
+    n1, n2 = len(inputs_1.chrs), len(inputs_2.chrs)
+    unique_1 = n1 - len(common_inds[0])
+    unique_2 = n2 - len(common_inds[0])
+    inputs_1.filter_chr_names()
+    inputs_2.filter_chr_names()
+    common_chrs = np.intersect1d(inputs_1.g_chrs_ids, inputs_2.g_chrs_ids)
+    # what crosses the C ABI: chromosome id (index into common_chrs, -1 elsewhere) of every marker of sample 1 and the ids
+    # of the genotype strings in one table for both samples
+    pos_in_common = np.searchsorted(common_chrs, inputs_1.g_chrs) if len(common_chrs) else np.zeros(n1, dtype=int)
+    pos_in_common = np.minimum(pos_in_common, max(len(common_chrs) - 1, 0))
+    chrom1 = np.where(common_chrs[pos_in_common] == inputs_1.g_chrs, pos_in_common, -1) if len(common_chrs) else np.full(n1, -1)
+    _, gt_ids = np.unique(np.concatenate([inputs_1.gt.astype("U"), inputs_2.gt.astype("U")]), return_inverse=True)
+    common, scores = lib.pair_match_counts(common_inds[0], common_inds[1], chrom1, gt_ids[:n1], gt_ids[n1:], len(common_chrs), device=device)
+    for k, i in enumerate(common_chrs):
+        log.info("Analysing chromosome %s positions", i)
+        snpmatch_stats[str(i)] = [get_fraction(int(scores[k]), int(common[k])), int(common[k])]
+    snpmatch_stats['matches'] = [get_fraction(int(np.sum(scores)), int(np.sum(common))), int(np.sum(common))]
+    snpmatch_stats['unique'] = {"%s" % os.path.basename(inFile_1): [get_fraction(unique_1, n1), n1],
+                                "%s" % os.path.basename(inFile_2): [get_fraction(unique_2, n2), n2]}
+    if outFile:
+        log.info("writing output in a file: %s" % outFile + ".matches.json")
+        with open(outFile + ".matches.json", "w") as out_stats:
+            out_stats.write(json.dumps(snpmatch_stats, sort_keys=True, indent=4))
+        log.info("finished!")
+    return snpmatch_stats

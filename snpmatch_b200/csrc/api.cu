@@ -8,6 +8,7 @@
 #include "hardcall.cuh"
 #include "gemm_onehot.cuh"
 #include "grouped.cuh"
+#include "pairs.cuh"
 #include <unordered_map>
 
 namespace snpm {
@@ -273,6 +274,81 @@ int snpm_db_segregating_rows(snpm_db *db, const int32_t *acc_idx, int32_t n_sel,
     d_flags.release();
     if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_db_segregating_rows: %s", cudaGetErrorString(e));
     return rc;
+}
+
+int snpm_db_read_columns(snpm_db *db, const int32_t *acc_idx, int32_t n_sel, int8_t *out) {
+    if (!db || n_sel < 0 || (n_sel > 0 && (!acc_idx || (db->n_rows > 0 && !out)))) return fail(SNPM_E_ARG, "snpm_db_read_columns: bad arguments");
+    for (int32_t i = 0; i < n_sel; ++i)
+        if (acc_idx[i] < 0 || acc_idx[i] >= db->n_acc) return fail(SNPM_E_ARG, "snpm_db_read_columns: accession index %d out of range", acc_idx[i]);
+    if (n_sel == 0 || db->n_rows == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    DevBuf d_out;
+    const int32_t per = std::min<int32_t>(n_sel, RC_MAX_COLS);
+    SNPM_TRY(d_out.ensure(size_t(per) * size_t(db->n_rows)));
+    cudaError_t e = cudaSuccess;
+    for (int32_t c0 = 0; c0 < n_sel && e == cudaSuccess; c0 += RC_MAX_COLS) {
+        ColumnSel sel;
+        sel.n = std::min<int32_t>(RC_MAX_COLS, n_sel - c0);
+        for (int32_t c = 0; c < RC_MAX_COLS; ++c) {
+            const int32_t a = c < sel.n ? acc_idx[c0 + c] : 0;
+            sel.word[c] = a >> 5;
+            sel.bit[c] = a & 31;
+        }
+        k_read_columns<<<grid_for(db->n_rows, 256, db->n_sm, 32), 256, 0, db->stream>>>(db->d_packed, db->n_rows, db->stride, sel, d_out.as<int8_t>());
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + size_t(c0) * size_t(db->n_rows), d_out.p, size_t(sel.n) * size_t(db->n_rows), cudaMemcpyDeviceToHost, db->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+    }
+    d_out.release();
+    if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_db_read_columns: %s", cudaGetErrorString(e));
+    return SNPM_OK;
+}
+
+int snpm_pair_match_counts(int device, const int64_t *idx1, const int64_t *idx2, int64_t m, const int32_t *chrom1, const int32_t *gt1, int64_t n1,
+                           const int32_t *gt2, int64_t n2, int32_t n_chr, int64_t *common, int64_t *matches) {
+    if (m < 0 || n1 < 0 || n2 < 0 || n_chr < 0 || (m > 0 && (!idx1 || !idx2 || !chrom1 || !gt1 || !gt2)) || (n_chr > 0 && (!common || !matches)))
+        return fail(SNPM_E_ARG, "snpm_pair_match_counts: bad arguments");
+    for (int64_t k = 0; k < m; ++k)
+        if (idx1[k] < 0 || idx1[k] >= n1 || idx2[k] < 0 || idx2[k] >= n2) return fail(SNPM_E_ARG, "snpm_pair_match_counts: pair %lld points outside the samples", (long long)k);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(SNPM_E_CUDA, "snpm_pair_match_counts: no CUDA device (there is no CPU fallback)");
+    if (n_chr == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(device));
+    DevBuf d_i1, d_i2, d_c1, d_g1, d_g2, d_cnt;
+    int rc = SNPM_OK;
+    cudaError_t e = cudaSuccess;
+    std::vector<unsigned long long> cnt(size_t(2) * n_chr, 0ull);
+    if ((rc = d_cnt.ensure(size_t(2) * n_chr * 8)) == SNPM_OK) e = cudaMemset(d_cnt.p, 0, size_t(2) * n_chr * 8);
+    if (rc == SNPM_OK && e == cudaSuccess && m > 0) {
+        if (rc == SNPM_OK) rc = d_i1.ensure(size_t(m) * 8);
+        if (rc == SNPM_OK) rc = d_i2.ensure(size_t(m) * 8);
+        if (rc == SNPM_OK) rc = d_c1.ensure(size_t(n1) * 4);
+        if (rc == SNPM_OK) rc = d_g1.ensure(size_t(n1) * 4);
+        if (rc == SNPM_OK) rc = d_g2.ensure(size_t(n2) * 4);
+        if (rc == SNPM_OK) {
+            e = cudaMemcpy(d_i1.p, idx1, size_t(m) * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_i2.p, idx2, size_t(m) * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_c1.p, chrom1, size_t(n1) * 4, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_g1.p, gt1, size_t(n1) * 4, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d_g2.p, gt2, size_t(n2) * 4, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                const int grid = int(std::min<int64_t>(ceil_div64(m, 256), 1184));
+                k_pair_counts<<<grid, 256>>>(d_i1.as<int64_t>(), d_i2.as<int64_t>(), m, d_c1.as<int32_t>(), d_g1.as<int32_t>(), d_g2.as<int32_t>(), n_chr,
+                                             d_cnt.as<unsigned long long>());
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+    }
+    if (rc == SNPM_OK && e == cudaSuccess) e = cudaMemcpy(cnt.data(), d_cnt.p, size_t(2) * n_chr * 8, cudaMemcpyDeviceToHost);
+    for (DevBuf *d : {&d_i1, &d_i2, &d_c1, &d_g1, &d_g2, &d_cnt}) d->release();
+    if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_pair_match_counts: %s", cudaGetErrorString(e));
+    if (rc != SNPM_OK) return rc;
+    for (int32_t c = 0; c < n_chr; ++c) {
+        common[c] = int64_t(cnt[size_t(c)]);
+        matches[c] = int64_t(cnt[size_t(n_chr) + c]);
+    }
+    return SNPM_OK;
 }
 
 int64_t snpm_db_n_rows(const snpm_db *db) { return db ? db->n_rows : -1; }

@@ -33,7 +33,10 @@ constexpr int GR_THREADS = 128;                       // 3 teams of 36 threads; 
 constexpr int GR_MAX_WX = 36;                         // words per team (one 1135-accession row)
 constexpr int GR_MAX_TEAMS = 3;
 constexpr int GR_BLOCK = 16;                          // rows per step
-constexpr int GR_RING = 64;                           // rows of the per-team ring
+#ifndef GR_RING_ROWS
+#define GR_RING_ROWS 64
+#endif
+constexpr int GR_RING = GR_RING_ROWS;                           // rows of the per-team ring
 constexpr int GR_INFLIGHT = GR_RING / GR_BLOCK;
 constexpr int GR_LP = 10;                             // planes of a counter (chunk <= 1023 rows)
 constexpr int GR_MAX_CHUNK = 1008;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_score_grouped(const GroupArgs
     constexpr unsigned pair_mask = 0xffffffffu;
     auto issue = [&](int b) {
         const int r0 = b * GR_BLOCK + 8 * odd;
-        const uint32_t slot0 = pair_ring + uint32_t(r0 & (GR_RING - 1)) * ring_pitch;
+        const uint32_t slot0 = pair_ring + uint32_t(r0 % GR_RING) * ring_pitch;
         if (b < n_full) {
 #pragma unroll
             for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_score_grouped(const GroupArgs
     for (int b = 0; b < n_full; ++b) {
         cp_async_wait<GR_INFLIGHT - 1>();         // block b has landed: this thread's copies ...
         __syncwarp(pair_mask);                    // ... and its neighbour's
-        const uint64_t *slot = ring + size_t((b * GR_BLOCK) & (GR_RING - 1)) * wx + w;
+        const uint64_t *slot = ring + size_t((b * GR_BLOCK) % GR_RING) * wx + w;
         uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
 #pragma unroll
         for (int k = 0; k < GR_BLOCK; ++k) {
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_score_grouped(const GroupArgs
         cp_async_wait<0>();
         __syncwarp(pair_mask);
         const int r0 = n_full * GR_BLOCK;
-        const uint64_t *slot = ring + size_t(r0 & (GR_RING - 1)) * wx + w;
+        const uint64_t *slot = ring + size_t(r0 % GR_RING) * wx + w;
         uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
 #pragma unroll
         for (int k = 0; k < GR_BLOCK; ++k) {

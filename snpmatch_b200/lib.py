@@ -122,6 +122,8 @@ SIGNATURES = {
     "snpm_db_read_rows_int8": (C.c_int, [_p, _p, _i64, _p]),
     "snpm_db_read_packed": (C.c_int, [_p, _i64, _i64, _p]),
     "snpm_db_segregating_rows": (C.c_int, [_p, _p, _i32, _p]),
+    "snpm_db_read_columns": (C.c_int, [_p, _p, _i32, _p]),
+    "snpm_pair_match_counts": (C.c_int, [C.c_int, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i32, _p, _p]),
     "snpm_db_n_rows": (_i64, [_p]),
     "snpm_db_n_acc": (_i32, [_p]),
     "snpm_db_row_words": (_i32, [_p]),
@@ -265,6 +267,13 @@ class Database(object):
     def read_packed(self, row0, n):
         out = np.empty((n, self.row_words), dtype=np.uint64)
         check(load().snpm_db_read_packed(self._h, row0, n, ptr(out)))
+        return out
+
+    def read_columns(self, acc_idx):
+        """Whole accession columns, int8 [len(acc_idx), n_rows] = g_acc.snps[:, acc_idx].T (simulate.py:15, genotype_cross.py:97-98)."""
+        acc_idx = as_c(np.atleast_1d(acc_idx), np.int32)
+        out = np.empty((len(acc_idx), self.n_rows), dtype=np.int8)
+        check(load().snpm_db_read_columns(self._h, ptr(acc_idx), len(acc_idx), ptr(out)))
         return out
 
     def segregating_rows(self, acc_idx):
@@ -529,6 +538,18 @@ def match_gts_accs(wei, snps, skip_hets_db=False, device=0):
     ninfo = np.empty(n_acc, dtype=np.int64)
     check(load().snpm_match_gts_accs(device, ptr(wei), ptr(snps), k, n_acc, int(bool(skip_hets_db)), ptr(score), ptr(ninfo)))
     return score, ninfo
+
+
+def pair_match_counts(idx1, idx2, chrom1, gt1, gt2, n_chr, device=0):
+    """Per-chromosome (common, matches) of pairwiseScore's counting loop (snpmatch.py:291-297) on the device."""
+    idx1, idx2 = as_c(idx1, np.int64), as_c(idx2, np.int64)
+    chrom1, gt1, gt2 = as_c(chrom1, np.int32), as_c(gt1, np.int32), as_c(gt2, np.int32)
+    assert len(idx1) == len(idx2) and len(chrom1) == len(gt1)
+    common = np.zeros(n_chr, dtype=np.int64)
+    matches = np.zeros(n_chr, dtype=np.int64)
+    check(load().snpm_pair_match_counts(device, ptr(idx1), ptr(idx2), len(idx1), ptr(chrom1), ptr(gt1), len(gt1), ptr(gt2), len(gt2),
+                                        n_chr, ptr(common), ptr(matches)))
+    return common, matches
 
 
 def calculate_likelihoods(scores, ninfo, amin="calc", device=0):

@@ -121,3 +121,54 @@ def test_cross_workflow(small_panel, sample_inbred, sample_cross, golden_outputs
         assert float(f[5]) == row[5] and int(f[6]) == row[6] and int(f[7]) == row[7]
         np.testing.assert_allclose(float(f[3]), row[3], rtol=1e-12)
         np.testing.assert_allclose(float(f[4]), row[4], rtol=1e-12, equal_nan=True)
+
+
+def _pair_stats_equal(got, want):
+    assert sorted(got) == sorted(want)
+    for k, v in want.items():
+        if k == "unique":
+            assert sorted(got[k]) == sorted(v)
+            for name in v:
+                assert got[k][name][1] == v[name][1]
+                assert got[k][name][0] == v[name][0] or (v[name][0] is None and np.isnan(got[k][name][0]))
+        else:
+            assert got[k][1] == v[1], k
+            assert got[k][0] == v[0] or (v[0] is None and np.isnan(got[k][0])), k
+
+
+def test_pairsnp_cases(small_panel):
+    """pairwiseScore (snpmatch.py:270-309) of the reference, with and without a database."""
+    import json
+    import os
+    from conftest import GOLDEN
+    g = load_golden("pairsnp.npz")
+    with open(os.path.join(GOLDEN, "pairsnp.json")) as fh:
+        want = json.load(fh)
+    db = (orc.db_chromosome_labels(small_panel["chrs"], small_panel["chr_regions"]), small_panel["positions"])
+    for i in range(int(g["n_cases"])):
+        a = [g["p%d_%s" % (i, k)] for k in ("c1", "p1", "g1", "c2", "p2", "g2")]
+        names = ("s%d_a.npz" % i, "s%d_b.npz" % i)
+        _pair_stats_equal(orc.pairwise_score(*a, name1=names[0], name2=names[1]), want["p%d_plain" % i])
+        _pair_stats_equal(orc.pairwise_score(*a, name1=names[0], name2=names[1], db=db), want["p%d_db" % i])
+
+
+def test_simulate_cases(small_panel):
+    """simulateSNPs / simulateSNPs_F1 (simulate.py:10-60) under the reference's np.random call order."""
+    g = load_golden("simulate.npz")
+    p = small_panel
+    ids = p["accessions"].astype("U")
+    row_chrs = np.array(orc.db_chromosome_labels(p["chrs"], p["chr_regions"]))
+    for i in range(int(g["n_cases"])):
+        n, err, rm, seed = g["s%d_args" % i]
+        np.random.seed(int(seed))
+        if str(g["s%d_kind" % i]) == "inbred":
+            col = p["snps"][:, np.flatnonzero(ids == str(g["s%d_acc" % i]))[0]]
+            c, pos, snp = orc.simulate_snps(col, row_chrs, p["positions"], int(n), float(err))
+        else:
+            a, b = str(g["s%d_acc" % i]).split("x")
+            c, pos, snp = orc.simulate_snps_f1(p["snps"][:, np.flatnonzero(ids == a)[0]], p["snps"][:, np.flatnonzero(ids == b)[0]],
+                                               row_chrs, p["positions"], int(n), float(err), float(rm))
+        gt = np.array(["./.", "0/0", "1/1", "0/1"])[snp.astype(int) + 1]
+        assert np.array_equal(c.astype("U"), g["s%d_chr" % i])
+        assert np.array_equal(pos, g["s%d_pos" % i])
+        assert np.array_equal(gt, g["s%d_gt" % i])
