@@ -254,6 +254,18 @@ int snpm_batch_f1_pairs(snpm_batch *b, const int32_t *acc_idx, int32_t n_top,
 int snpm_pair_match_counts(int device, const int64_t *idx1, const int64_t *idx2, int64_t m, const int32_t *chrom1, const int32_t *gt1,
                            int64_t n1, const int32_t *gt2, int64_t n2, int32_t n_chr, int64_t *common, int64_t *matches);
 
+/* ---- 8(f)-4: genotype_cross -----------------------------------------------------------------
+ * The window loop of GenotypeCross.genotype_cross (genotype_cross.py:210-241): for every genome window w and every sample s
+ * of a multi-sample VCF, over the matched pairs k in [win_start[w], win_start[w+1]) (par_idx into the parents' segregating
+ * markers, vcf_idx into the VCF markers; ordered by window): counts int32 [W,S,3] = calls equal to parent 1, heterozygous
+ * calls, calls equal to parent 2 (get_window_genotype_gts :188-199), and geno int8 [W,S] = getWindowGenotype (:21-49) of
+ * those counts with totalMarkers = pairs of the window: 0 parent 1, 1 het, 2 parent 2, -1 NA.  p1/p2 int8[n_par] parental
+ * codes, gt int8 [n_vcf, S] parseGT codes.  borderline (optional) uint8 [W,S]: the call hangs on lr_next >= lr_thres
+ * within 1e-9 relative. */
+int snpm_cross_window_genotypes(int device, const int64_t *par_idx, const int64_t *vcf_idx, int64_t m, const int32_t *win_start, int32_t n_windows,
+                                const int8_t *p1, const int8_t *p2, int64_t n_par, const int8_t *gt, int64_t n_vcf, int32_t n_samples,
+                                double lr_thres, int32_t n_marker_thres, int32_t *counts, int8_t *geno, uint8_t *borderline);
+
 /* ---- A9: batched scoring on a shared marker panel (tensor cores) ------------------------------
  * No reference symbol: the reference scores many samples as one process per sample (README.md:9).  S samples of CALLED
  * genotypes that share K markers (panel_rows int64[K], global rows; codes uint8 [S,K]: 0 ref, 1 alt, 2 het, 3 = sample

@@ -376,6 +376,74 @@ def gen_simulate_cases(ref):
     print("simulate: %d cases" % len(cases))
 
 
+def make_f2_population(panel, parents=(3, 21), n_samples=12, n_db=5200, n_extra=150, seed=31):
+    """A multi-sample VCF worth of arrays: F2-like mosaics (parent 1 / het / parent 2 in 2-4 Mb blocks) of two panel accessions
+    on a subset of the panel's positions plus positions the panel lacks, with call errors and missing calls."""
+    rng = np.random.default_rng(seed)
+    rows = np.sort(rng.choice(len(panel["positions"]), n_db, replace=False))
+    starts = panel["chr_regions"][:, 0]
+    chr_of = np.searchsorted(starts, rows, side="right") - 1
+    chrs = np.char.add("Chr", panel["chrs"].astype("U")[chr_of])
+    pos = panel["positions"][rows].astype(np.int64)
+    p1, p2 = panel["snps"][rows, parents[0]], panel["snps"][rows, parents[1]]
+    gt = np.zeros((n_db, n_samples), dtype=np.int8)
+    for s in range(n_samples):
+        block = (pos // int(rng.integers(2_000_000, 4_000_000))) + 7 * chr_of + s
+        state = (block * 2654435761 % 4)                      # 0: parent 1, 1/2: het, 3: parent 2
+        het_ok = (p1 >= 0) & (p2 >= 0) & (p1 != p2)
+        call = np.where(state == 0, p1, np.where(state == 3, p2, np.where(het_ok, 2, p1)))
+        call = np.where(call < 0, 0, call)
+        err = rng.random(n_db) < 0.01
+        call = np.where(err, rng.integers(0, 3, n_db), call)
+        miss = rng.random(n_db) < (0.05 if s != n_samples - 1 else 0.97)   # the last sample is almost empty
+        gt[:, s] = np.where(miss, -1, call)
+    # positions the panel lacks, chromosome 1, and a contig outside the genome would trip the reference's assert: none added
+    extra = np.setdiff1d(rng.choice(30_000_000, n_extra) + 1, panel["positions"][:int(panel["chr_regions"][0, 1])])
+    chrs = np.concatenate([np.repeat("Chr1", len(extra)), chrs])
+    pos = np.concatenate([extra, pos])
+    gt = np.concatenate([rng.integers(-1, 3, size=(len(extra), n_samples)).astype(np.int8), gt])
+    order = np.lexsort((pos, chrs))
+    names = np.array(["./.", "0/0", "1/1", "0/1"])
+    return {"samples": np.array(["F2_%02d" % s for s in range(n_samples)]), "chr": chrs[order], "pos": pos[order],
+            "gt": names[gt[order].astype(int) + 1]}
+
+
+def gen_genotype_cross_cases(ref):
+    """GenotypeCross.genotype_cross (genotype_cross.py:210-241) of the reference; the VCF parse (scikit-allel, absent here) is
+    replaced by arrays of the shape import_vcf_file returns (parsers.py:176-213)."""
+    from snpmatch.core import genotype_cross as r_gc
+    panel = dict(np.load(os.path.join(GOLD, "small_panel.npz")))
+    G = rh.make_reference_genotype(ref, panel["snps"], panel["positions"], panel["chrs"], panel["chr_regions"], panel["accessions"])
+    ids = G.accessions
+    vcf = make_f2_population(panel)
+    np.savez_compressed(os.path.join(GOLD, "genotype_cross_vcf.npz"), **vcf)
+    r_gc.genome = ref.genomes.Genome("athaliana_tair10")
+    real = ref.parsers.import_vcf_file
+    ref.parsers.import_vcf_file = lambda inFile, logDebug=False, samples_to_load=None, add_fields=None: dict(vcf)
+    index = {}
+    try:
+        for tag, bin_len, lr in (("b300k_lr1.5", 300000, 1.5), ("b1M_lr3", 1000000, 3.0), ("b2M_lr1.5", 2000000, 1.5)):
+            gc = r_gc.GenotypeCross(G, "%sx%s" % (ids[3], ids[21]), bin_len, None, False)
+            lines = gc.genotype_cross("population.vcf", lr)
+            index[tag] = {"bin_len": bin_len, "lr_thres": lr, "parents": "%sx%s" % (ids[3], ids[21]),
+                          "n_segregating": int(len(gc.commonSNPsPOS)), "lines": [str(x) for x in lines]}
+    finally:
+        ref.parsers.import_vcf_file = real
+    # known answers of getWindowGenotype on a grid of counts
+    grid = []
+    for total in (3, 5, 8, 20, 57):
+        for a in range(0, total + 1, max(1, total // 6)):
+            for h in range(0, total + 1 - a, max(1, total // 5)):
+                for b in (0, total - a - h, (total - a - h) // 2):
+                    for lr in (1.5, 3.0):
+                        geno, pval = r_gc.getWindowGenotype([a, h, b], total, lr)
+                        grid.append([total, a, h, b, lr, -1 if geno == "NA" else int(geno)])
+    index["window_genotype_grid"] = grid
+    with open(os.path.join(GOLD, "genotype_cross.json"), "w") as fh:
+        json.dump(index, fh, indent=0, sort_keys=True)
+    print("genotype_cross: %d cases, grid of %d cells" % (len(index) - 1, len(grid)))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = rh.load_reference()
@@ -385,6 +453,7 @@ def main():
     gen_workflow_cases(ref)
     gen_pairsnp_cases(ref)
     gen_simulate_cases(ref)
+    gen_genotype_cross_cases(ref)
 
 
 if __name__ == "__main__":

@@ -447,6 +447,87 @@ def simulate_snps_f1(snps_p1, snps_p2, row_chrs, row_pos, num_snps, err_rate, rm
 
 
 # --------------------------------------------------------------------------
+# 8(f)-4 — genotype_cross: windowed parent matching
+# --------------------------------------------------------------------------
+def parse_gt(gt):
+    """parsers.py:12-35 — GT strings -> 0 / 1 / 2 (het) / -1 (no call); anything else is 0.  Separator from the first element."""
+    gt = np.asarray(gt, dtype="str")
+    out = np.zeros(len(gt), dtype=np.int8)
+    if len(gt) == 0:
+        return out
+    sep = "|" if "|" in gt[0] else "/"
+    out[gt == "1" + sep + "1"] = 1
+    out[(gt == "0" + sep + "1") | (gt == "1" + sep + "0")] = 2
+    out[gt == "." + sep + "."] = -1
+    return out
+
+
+def get_window_genotype(matched, total, lr_thres, n_marker_thres=5):
+    """genotype_cross.py:21-49 — matched = [parent 1, het, parent 2] counts of a window.  Returns 0, 1, 2 or 'NA'."""
+    if total < n_marker_thres:
+        return "NA"
+    assert len(matched) == 3
+    if np.array_equal(np.array(matched), np.repeat(0, 3)):
+        return "NA"
+    lik, lr = calculate_likelihoods(matched, np.repeat(total, 3))
+    if len(np.where(lr == 1)[0]) > 1:
+        return 1
+    high = int(np.nanargmin(lik))
+    rest = lr[np.nonzero(lr - 1)]
+    lr_next = np.nan if (len(rest) == 0 or np.all(np.isnan(rest))) else np.nanmin(rest)
+    if np.isnan(lr_next):
+        lr_next = lr_thres
+    geno = "NA"
+    if high == 0 and lr_next >= lr_thres:
+        geno = 0
+    elif high == 2 and lr_next >= lr_thres:
+        geno = 2
+    if high == 1:
+        geno = 1
+    return geno
+
+
+def segregating_parent_markers(snps_p1, snps_p2):
+    """genotype_cross.py:108 — rows on which both parents are called and differ."""
+    p1, p2 = np.asarray(snps_p1), np.asarray(snps_p2)
+    return np.flatnonzero((p1 != p2) & (p1 >= 0) & (p2 >= 0))
+
+
+def genotype_cross_windows(par_chrs, par_pos, par_p1, par_p2, vcf_chrs, vcf_pos, vcf_gt, genome_chrs, genome_chrlen, bin_len, lr_thres):
+    """genotype_cross.py:210-241 — per genome window (JSON order) the list [geno per sample] or None when the window holds no
+    matched marker, plus the counts.  vcf_gt: GT strings [n, S].  Returns (calls: list over windows, counts: dict w -> int [S,3],
+    n_matched per window)."""
+    ids = genome_chr_ids(genome_chrs)
+    p_ids, v_ids = genome_chr_ids(par_chrs), genome_chr_ids(vcf_chrs)
+    par_pos, vcf_pos = np.asarray(par_pos), np.asarray(vcf_pos)
+    vcf_gt = np.asarray(vcf_gt, dtype="str")
+    calls, counts, n_matched = [], {}, []
+    w = 0
+    for ci, cid in enumerate(ids):
+        p_rows, v_rows = np.flatnonzero(p_ids == cid), np.flatnonzero(v_ids == cid)
+        p_win = window_of(par_pos[p_rows], genome_chrlen[ci], bin_len)
+        v_win = window_of(vcf_pos[v_rows], genome_chrlen[ci], bin_len)
+        for k in range(num_windows(genome_chrlen[ci], bin_len)):
+            e_b, e_s = p_rows[p_win == k], v_rows[v_win == k]
+            acc_ind = e_b[np.isin(par_pos[e_b], vcf_pos[e_s])]
+            tar_ind = e_s[np.isin(vcf_pos[e_s], par_pos[e_b])]
+            n_matched.append(len(tar_ind))
+            if len(tar_ind) == 0:
+                calls.append(None)
+            else:
+                row, cnt = [], []
+                for s_ix in range(vcf_gt.shape[1]):
+                    t = parse_gt(vcf_gt[tar_ind, s_ix])
+                    m = [int(np.sum(t == par_p1[acc_ind])), int(np.sum(t == 2)), int(np.sum(t == par_p2[acc_ind]))]
+                    cnt.append(m)
+                    row.append(get_window_genotype(m, len(tar_ind), lr_thres))
+                calls.append(row)
+                counts[w] = np.array(cnt)
+            w += 1
+    return calls, counts, n_matched
+
+
+# --------------------------------------------------------------------------
 # data-format helper shared by the tests (not reference behaviour)
 # --------------------------------------------------------------------------
 def pack_2bit_words(db_snps):

@@ -3,7 +3,8 @@ snpmatch_b200 — B200-native genotype-matching hot path behind SNPmatch's `inbr
 
 The command line mirrors the reference's `snpmatch/__init__.py` for the two sub-commands on the
 matching path (`inbred`, `cross`: flags of __init__.py:44-63), `parser` (:80-84) and the callers next to the
-path that work on the resident panel (`pairsnp` :86-92, `simulate` :101-111); the other
+path that work on the resident panel (`pairsnp` :86-92, `simulate` :101-111, `genotype_cross`
+:65-78 without its HMM mode); the other
 sub-commands of the reference are outside this package's scope.
 """
 import argparse
@@ -70,6 +71,13 @@ def simulate_snps(args):
     simulate.potatoSimulate(args)
 
 
+def genotype_cross(args):
+    if not args['parents']:
+        die("parents not specified")
+    from .core import genotype_cross as gtm
+    gtm.potatoCrossGenotyper(args)
+
+
 def get_options(description, version_message):
     p = argparse.ArgumentParser(description=description)
     p.add_argument('-V', '--version', action='version', version=version_message)
@@ -101,6 +109,21 @@ def get_options(description, version_message):
     parser.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
     parser.add_argument("-o", "--output", dest="outFile", help="output + .npz file is generater required for SNPmatch")
     parser.set_defaults(func=snpmatch_parser)
+
+    gc = sub.add_parser('genotype_cross', help="Genotype the crosses by windows given parents")
+    gc.add_argument("-i", "--input_file", dest="inFile", help="VCF file for the variants in the sample")
+    gc.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
+    gc.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility)")
+    gc.add_argument("-p", "--parents", dest="parents", help="Parents for the cross, parent1 x parent2")
+    gc.add_argument("-q", "--father", dest="father", help="VCF/BED file of parent 2 when the parents are given as files (then -p is the file of parent 1)")
+    gc.add_argument("-b", "--binLength", dest="binLen", help="bin length", type=int, default=200000)
+    gc.add_argument("--good_samples", dest="good_samples", help="accepted for compatibility (unused by the reference's window genotyper)", default=None)
+    gc.add_argument("--lr_thres", dest="lr_thres", default=1.5, type=float, help="Likelihood ratio threshold for genotype calling.")
+    gc.add_argument("--hmm", dest="hmm", action="store_true", help="HMM Viterbi genotyper of the reference: not part of this package")
+    gc.add_argument("--genome", dest="genome", default="athaliana_tair10", help="Path to Reference JSON file, if you are working with non-thaliana tair10 assembly")
+    gc.add_argument("-o", "--output", dest="outFile", default="genotype_cross", help="output file")
+    gc.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    gc.set_defaults(func=genotype_cross)
 
     pair = sub.add_parser('pairsnp', help="pairwise comparison of two snp files")
     pair.add_argument("-i", "--input_file_1", dest="inFile_1", help="VCF/BED file for the variants in the sample one")

@@ -135,8 +135,45 @@ def read_vcf_minimal(inFile, sample_index=0):
     return out
 
 
+def read_vcf_samples(inFile):
+    """All samples of a VCF: 'samples' str[S], 'chr', 'pos', 'gt' str [n,S] rendered 'a/b' as scikit-allel's
+    GenotypeArray.to_gt does for the reference (parsers.py:191-193).  Used by genotype_cross (genotype_cross.py:212)."""
+    opener = gzip.open if str(inFile).endswith(".gz") else open
+    samples, chrom, pos, rows = [], [], [], []
+    with opener(inFile, "rt") as fh:
+        for line in fh:
+            if line.startswith("##"):
+                continue
+            f = line.rstrip("\n").split("\t")
+            if line.startswith("#"):
+                samples = f[9:]
+                continue
+            if len(f) < 10:
+                continue
+            chrom.append(f[0])
+            pos.append(int(f[1]))
+            gt_at = f[8].split(":").index("GT") if "GT" in f[8].split(":") else -1
+            row = []
+            for cell in f[9:9 + len(samples)]:
+                v = cell.split(":")
+                raw = v[gt_at] if 0 <= gt_at < len(v) else "."
+                alleles = re.split(r"[/|]", raw)
+                if len(alleles) == 1:
+                    alleles = [alleles[0], "."] if alleles[0] != "." else [".", "."]
+                row.append("/".join(a if a != "" else "." for a in alleles[:2]))
+            row += ["./."] * (len(samples) - len(row))
+            rows.append(row)
+    return {"samples": np.array(samples, dtype="str"), "chr": np.array(chrom, dtype="str"), "pos": np.array(pos, dtype=np.int64),
+            "gt": np.array(rows, dtype="str").reshape(len(pos), len(samples))}
+
+
 def import_vcf_file(inFile, logDebug=False, samples_to_load=[0], add_fields=None):
-    """Same role as parsers.py:178-213; returns dict with 'gt' [n,1], 'wei' [n,1,3], 'chr', 'pos', 'dp'."""
+    """Same role as parsers.py:178-213; returns dict with 'gt' [n,1], 'wei' [n,1,3], 'chr', 'pos', 'dp'.
+    samples_to_load=None loads the genotypes of every sample ('samples', 'gt' [n,S]; genotype_cross.py:212)."""
+    if samples_to_load is None:
+        out = read_vcf_samples(inFile)
+        out["dp"] = np.repeat("NA", len(out["pos"]))
+        return out
     raw = read_vcf_minimal(inFile, sample_index=samples_to_load[0])
     snp_inputs = {"chr": raw["chr"], "pos": raw["pos"], "dp": raw["dp"], "gt": raw["gt"][:, None]}
     if "wei" in raw:

@@ -9,6 +9,7 @@
 #include "gemm_onehot.cuh"
 #include "grouped.cuh"
 #include "pairs.cuh"
+#include "cross_geno.cuh"
 #include <unordered_map>
 
 namespace snpm {
@@ -1250,6 +1251,58 @@ int snpm_calculate_likelihoods(int device, const double *scores, const double *n
     d_red.release();
     d_out.release();
     if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_calculate_likelihoods: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+// ---- 8(f)-4: genotype_cross window calls -----------------------------------------------------------------
+int snpm_cross_window_genotypes(int device, const int64_t *par_idx, const int64_t *vcf_idx, int64_t m, const int32_t *win_start, int32_t n_windows,
+                                const int8_t *p1, const int8_t *p2, int64_t n_par, const int8_t *gt, int64_t n_vcf, int32_t n_samples,
+                                double lr_thres, int32_t n_marker_thres, int32_t *counts, int8_t *geno, uint8_t *borderline) {
+    if (m < 0 || n_windows < 0 || n_par < 0 || n_vcf < 0 || n_samples < 0 || !win_start || (m > 0 && (!par_idx || !vcf_idx || !p1 || !p2 || !gt)))
+        return fail(SNPM_E_ARG, "snpm_cross_window_genotypes: bad arguments");
+    if (m >= (int64_t(1) << 31)) return fail(SNPM_E_ARG, "snpm_cross_window_genotypes: at most 2^31 - 1 matched markers");
+    if (win_start[0] != 0 || win_start[n_windows] != m) return fail(SNPM_E_ARG, "snpm_cross_window_genotypes: win_start must run from 0 to m");
+    for (int32_t w = 0; w < n_windows; ++w)
+        if (win_start[w + 1] < win_start[w]) return fail(SNPM_E_ARG, "snpm_cross_window_genotypes: win_start is not ascending");
+    for (int64_t k = 0; k < m; ++k)
+        if (par_idx[k] < 0 || par_idx[k] >= n_par || vcf_idx[k] < 0 || vcf_idx[k] >= n_vcf)
+            return fail(SNPM_E_ARG, "snpm_cross_window_genotypes: pair %lld points outside the marker lists", (long long)k);
+    const size_t cells = size_t(n_windows) * size_t(n_samples);
+    if (cells > 0 && (!counts || !geno)) return fail(SNPM_E_ARG, "snpm_cross_window_genotypes: NULL outputs");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(SNPM_E_CUDA, "snpm_cross_window_genotypes: no CUDA device (there is no CPU fallback)");
+    if (cells == 0) return SNPM_OK;
+    SNPM_CUDA(cudaSetDevice(device));
+    DevBuf d_pi, d_vi, d_ws, d_p1, d_p2, d_gt, d_cnt, d_geno, d_border;
+    int rc = SNPM_OK;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](DevBuf &d, const void *src, size_t bytes) {
+        if (rc != SNPM_OK || e != cudaSuccess) return;
+        rc = d.ensure(bytes);
+        if (rc == SNPM_OK && bytes) e = cudaMemcpy(d.p, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up(d_pi, par_idx, size_t(m) * 8);
+    up(d_vi, vcf_idx, size_t(m) * 8);
+    up(d_ws, win_start, (size_t(n_windows) + 1) * 4);
+    up(d_p1, p1, size_t(n_par));
+    up(d_p2, p2, size_t(n_par));
+    up(d_gt, gt, size_t(n_vcf) * size_t(n_samples));
+    if (rc == SNPM_OK) rc = d_cnt.ensure(cells * 12);
+    if (rc == SNPM_OK) rc = d_geno.ensure(cells);
+    if (rc == SNPM_OK) rc = d_border.ensure(cells);
+    if (rc == SNPM_OK && e == cudaSuccess) {
+        dim3 grid(unsigned(n_windows), unsigned((n_samples + GC_THREADS - 1) / GC_THREADS));
+        k_gc_window_calls<<<grid, GC_THREADS>>>(d_pi.as<int64_t>(), d_vi.as<int64_t>(), d_ws.as<int32_t>(), d_p1.as<int8_t>(), d_p2.as<int8_t>(),
+                                                d_gt.as<int8_t>(), n_samples, lr_thres, n_marker_thres, d_cnt.as<int32_t>(), d_geno.as<int8_t>(),
+                                                d_border.as<uint8_t>());
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(counts, d_cnt.p, cells * 12, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(geno, d_geno.p, cells, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && borderline) e = cudaMemcpy(borderline, d_border.p, cells, cudaMemcpyDeviceToHost);
+    }
+    for (DevBuf *d : {&d_pi, &d_vi, &d_ws, &d_p1, &d_p2, &d_gt, &d_cnt, &d_geno, &d_border}) d->release();
+    if (e != cudaSuccess) return fail(SNPM_E_CUDA, "snpm_cross_window_genotypes: %s", cudaGetErrorString(e));
     return rc;
 }
 

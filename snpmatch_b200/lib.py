@@ -124,6 +124,7 @@ SIGNATURES = {
     "snpm_db_segregating_rows": (C.c_int, [_p, _p, _i32, _p]),
     "snpm_db_read_columns": (C.c_int, [_p, _p, _i32, _p]),
     "snpm_pair_match_counts": (C.c_int, [C.c_int, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i32, _p, _p]),
+    "snpm_cross_window_genotypes": (C.c_int, [C.c_int, _p, _p, _i64, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _f64, _i32, _p, _p, _p]),
     "snpm_db_n_rows": (_i64, [_p]),
     "snpm_db_n_acc": (_i32, [_p]),
     "snpm_db_row_words": (_i32, [_p]),
@@ -550,6 +551,22 @@ def pair_match_counts(idx1, idx2, chrom1, gt1, gt2, n_chr, device=0):
     check(load().snpm_pair_match_counts(device, ptr(idx1), ptr(idx2), len(idx1), ptr(chrom1), ptr(gt1), len(gt1), ptr(gt2), len(gt2),
                                         n_chr, ptr(common), ptr(matches)))
     return common, matches
+
+
+def cross_window_genotypes(par_idx, vcf_idx, win_start, p1, p2, gt, lr_thres, n_marker_thres=5, device=0):
+    """Window calls of genotype_cross (genotype_cross.py:210-241) on the device: returns (counts int32 [W,S,3], geno int8 [W,S]
+    with -1 = NA, borderline uint8 [W,S])."""
+    par_idx, vcf_idx = as_c(par_idx, np.int64), as_c(vcf_idx, np.int64)
+    win_start = as_c(win_start, np.int32)
+    p1, p2, gt = as_c(p1, np.int8), as_c(p2, np.int8), as_c(gt, np.int8)
+    assert gt.ndim == 2 and len(p1) == len(p2) and len(par_idx) == len(vcf_idx)
+    W, S = len(win_start) - 1, gt.shape[1]
+    counts = np.zeros((W, S, 3), dtype=np.int32)
+    geno = np.full((W, S), -1, dtype=np.int8)
+    border = np.zeros((W, S), dtype=np.uint8)
+    check(load().snpm_cross_window_genotypes(device, ptr(par_idx), ptr(vcf_idx), len(par_idx), ptr(win_start), W, ptr(p1), ptr(p2), len(p1),
+                                             ptr(gt), gt.shape[0], S, float(lr_thres), int(n_marker_thres), ptr(counts), ptr(geno), ptr(border)))
+    return counts, geno, border
 
 
 def calculate_likelihoods(scores, ninfo, amin="calc", device=0):

@@ -172,3 +172,45 @@ def test_simulate_cases(small_panel):
         assert np.array_equal(c.astype("U"), g["s%d_chr" % i])
         assert np.array_equal(pos, g["s%d_pos" % i])
         assert np.array_equal(gt, g["s%d_gt" % i])
+
+
+def _gc_lines(calls, samples, genome_chrs, genome_chrlen, rates, bin_len):
+    """Output lines of genotype_cross (genotype_cross.py:217-237) from the oracle's per-window calls."""
+    ids = orc.genome_chr_ids(genome_chrs)
+    lines = ["id,,," + ",".join(samples), "pheno,," + ",0" * len(samples)]
+    w = 0
+    for ci, cid in enumerate(ids):
+        for k in range(orc.num_windows(genome_chrlen[ci], bin_len)):
+            start, end = 1 + k * bin_len, (k + 1) * bin_len
+            cm = rates[ci] * int(round(float(np.mean([start, end])))) / 1000000
+            tail = ",NA" * len(samples) if calls[w] is None else "".join("," + str(g) for g in calls[w])
+            lines.append("%s:%d-%d,%s,%s%s" % (cid, start, end, cid, cm, tail))
+            w += 1
+    return lines
+
+
+TAIR10 = (["1", "2", "3", "4", "5"], [30427671, 19698289, 23459830, 18585056, 26975502], [3.4, 3.6, 3.5, 3.8, 3.6])
+
+
+def test_genotype_cross_cases(small_panel):
+    """GenotypeCross.genotype_cross and getWindowGenotype (genotype_cross.py:21-49,210-241) of the reference."""
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "genotype_cross.json")) as fh:
+        want = json.load(fh)
+    for total, a, h, b, lr, geno in want["window_genotype_grid"]:
+        got = orc.get_window_genotype([a, h, b], total, lr)
+        assert (-1 if got == "NA" else got) == geno, (total, a, h, b, lr)
+    vcf = load_golden("genotype_cross_vcf.npz")
+    p = small_panel
+    ids = p["accessions"].astype("U")
+    row_chrs = np.array(orc.db_chromosome_labels(p["chrs"], p["chr_regions"]))
+    for tag in ("b300k_lr1.5", "b1M_lr3", "b2M_lr1.5"):
+        c = want[tag]
+        i1, i2 = [int(np.flatnonzero(ids == x)[0]) for x in c["parents"].split("x")]
+        seg = orc.segregating_parent_markers(p["snps"][:, i1], p["snps"][:, i2])
+        assert len(seg) == c["n_segregating"]
+        calls, _, _ = orc.genotype_cross_windows(row_chrs[seg], p["positions"][seg], p["snps"][seg, i1], p["snps"][seg, i2],
+                                                 vcf["chr"], vcf["pos"], vcf["gt"], TAIR10[0], TAIR10[1], c["bin_len"], c["lr_thres"])
+        assert _gc_lines(calls, vcf["samples"], TAIR10[0], TAIR10[1], TAIR10[2], c["bin_len"]) == c["lines"]
