@@ -25,7 +25,8 @@ _RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "resources
 
 def genome_style_ids(names):
     """lower-case, then drop 'chr' (genomes.py:28,75,95)."""
-    return np.array([str(c).lower().replace("chr", "") for c in np.asarray(names).ravel()], dtype="str")
+    from . import labels
+    return labels.map_labels(names, lambda c: c.lower().replace("chr", ""))[0]
 
 
 def num_windows(chrlen, bin_len):

@@ -20,6 +20,7 @@ import numpy as np
 
 from .. import lib
 from . import genomes
+from . import labels
 from . import parsers
 from . import snp_genotype
 from . import snpmatch
@@ -72,14 +73,14 @@ def window_calls(par_chrs, par_pos, snps_p1, snps_p2, vcf_chrs, vcf_pos, gt_code
     W = int(off[-1])
 
     def place(chrs, pos, what):
-        gid = genomes.genome_style_ids(chrs)
-        uniq = np.unique(gid)
-        assert len(uniq) <= len(ids), "Please change default --genome option"
-        assert len(np.intersect1d(uniq, ids)) > 0, "Please change default --genome option"
-        if len(np.intersect1d(uniq, ids)) < len(ids):
+        _, codes, uniq = labels.map_labels(chrs, lambda c: c.lower().replace("chr", ""))      # genomes.py:75,95
+        distinct = np.unique(uniq)
+        assert len(distinct) <= len(ids), "Please change default --genome option"
+        assert len(np.intersect1d(distinct, ids)) > 0, "Please change default --genome option"
+        if len(np.intersect1d(distinct, ids)) < len(ids):
             log.warning("Some reference contigs are missing in %s", what)
         lut = {c: i for i, c in enumerate(ids)}
-        cix = np.array([lut.get(c, -1) for c in uniq], dtype=np.int64)[np.searchsorted(uniq, gid)]
+        cix = np.array([lut.get(c, -1) for c in uniq], dtype=np.int64)[codes]
         pos = np.asarray(pos, dtype=np.int64)
         k = (pos - 1) // bin_len
         ok = (cix >= 0) & (pos >= 1) & (k < n_win[np.maximum(cix, 0)])
@@ -88,15 +89,11 @@ def window_calls(par_chrs, par_pos, snps_p1, snps_p2, vcf_chrs, vcf_pos, gt_code
     p_cix, p_win = place(par_chrs, par_pos, "the parental markers")
     v_cix, v_win = place(vcf_chrs, vcf_pos, "given SNPs")
     p_keep, v_keep = np.flatnonzero(p_win >= 0), np.flatnonzero(v_win >= 0)
-    if len(p_keep) and len(v_keep):
-        i_p, i_v = snp_genotype.Genotype.get_common_positions(p_cix[p_keep].astype(str), np.asarray(par_pos)[p_keep],
-                                                              v_cix[v_keep].astype(str), np.asarray(vcf_pos)[v_keep], device=device)
-        # pair the two sides by (window, position): each side comes back in its own order
-        i_p, i_v = p_keep[i_p], v_keep[i_v]
-        i_p = i_p[np.lexsort((np.asarray(par_pos)[i_p], p_win[i_p]))]
-        i_v = i_v[np.lexsort((np.asarray(vcf_pos)[i_v], v_win[i_v]))]
-    else:
-        i_p = i_v = np.zeros(0, dtype=np.int64)
+    par_pos, vcf_pos = np.asarray(par_pos, dtype=np.int64), np.asarray(vcf_pos, dtype=np.int64)
+    # inner join of the markers that lie in a window on (genome chromosome, position); pairs come back ordered by
+    # (chromosome, position) = window order
+    i_p, i_v = snp_genotype.join_coded(p_cix[p_keep], par_pos[p_keep], v_cix[v_keep], vcf_pos[v_keep], len(ids), device=device)
+    i_p, i_v = p_keep[i_p], v_keep[i_v]
     win_start = np.concatenate([[0], np.cumsum(np.bincount(p_win[i_p], minlength=W))]).astype(np.int32)
     counts, geno, border = lib.cross_window_genotypes(i_p, i_v, win_start, snps_p1, snps_p2, gt_codes, lr_thres, device=device)
     return {"chr_ix": np.repeat(np.arange(len(ids)), n_win), "start": np.concatenate([1 + bin_len * np.arange(n) for n in n_win]),

@@ -1,0 +1,32 @@
+"""Vectorised handling of per-marker string labels (chromosome names, GT strings) on the host.
+
+The reference maps names per marker (pandas `str.replace` on every element, parsers.py:161; a Python list of N labels,
+pygwas/genotype.py:156-161).  Here a label column is first reduced to integer codes plus its few distinct values, and every
+string operation runs on the distinct values only."""
+import numpy as np
+import pandas as pd
+
+
+def factorize(labels):
+    """(codes int64[n], uniques str[k]) with uniques in first-appearance order.  Labels that come in long runs (a file sorted
+    by chromosome) are handled by run detection, anything else by pandas' hash-based factorize."""
+    labels = np.asarray(labels).ravel()
+    if labels.dtype.kind not in "US":
+        labels = labels.astype("U")
+    n = len(labels)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64), labels.astype("U")
+    change = np.flatnonzero(labels[1:] != labels[:-1]) + 1
+    if len(change) < max(64, n // 16):
+        starts = np.concatenate([[0], change])
+        run_codes, uniq = pd.factorize(labels[starts])
+        return np.repeat(run_codes.astype(np.int64), np.diff(np.concatenate([starts, [n]]))), np.asarray(uniq).astype("U")
+    codes, uniq = pd.factorize(labels)
+    return codes.astype(np.int64), np.asarray(uniq).astype("U")
+
+
+def map_labels(labels, fn):
+    """fn applied to every label, computed on the distinct labels only: returns (mapped str[n], codes, mapped uniques)."""
+    codes, uniq = factorize(labels)
+    mapped = np.array([fn(str(u)) for u in uniq], dtype="str") if len(uniq) else np.zeros(0, dtype="U1")
+    return (mapped[codes] if len(codes) else np.zeros(0, dtype="U1")), codes, mapped

@@ -276,12 +276,9 @@ class ParseInputs(object):
 
     def filter_chr_names(self):
         """parsers.py:159-163: strip every 'chr' (any case); ids in first-appearance order."""
-        self.g_chrs = np.array([re.sub("chr", "", c, flags=re.IGNORECASE) for c in self.chrs], dtype="str")
-        if len(self.g_chrs):
-            _, idx = np.unique(self.g_chrs, return_index=True)
-            self.g_chrs_ids = self.g_chrs[np.sort(idx)]
-        else:
-            self.g_chrs_ids = self.g_chrs
+        from . import labels
+        self.g_chrs, _, mapped = labels.map_labels(self.chrs, lambda c: re.sub("chr", "", c, flags=re.IGNORECASE))
+        self.g_chrs_ids = labels.factorize(mapped)[1] if len(mapped) else self.g_chrs
 
     def save_to_bed(self, outFile):
         with open(outFile, "w") as fh:

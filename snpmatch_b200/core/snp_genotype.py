@@ -22,6 +22,7 @@ import re
 import numpy as np
 
 from .. import lib
+from . import labels
 from . import parsers
 
 log = logging.getLogger(__name__)
@@ -31,12 +32,64 @@ _CHR_RE = re.compile("chr", re.IGNORECASE)
 
 
 def normalize_chr_names(chrs):
-    """parsers.py:161 — delete every 'chr' (any case)."""
-    return np.array([_CHR_RE.sub("", str(c)) for c in np.asarray(chrs).ravel()], dtype="str")
+    """parsers.py:161 — delete every 'chr' (any case).  Computed on the distinct names only (labels.map_labels)."""
+    return labels.map_labels(chrs, lambda c: _CHR_RE.sub("", c))[0]
 
 
 def load_genotype_files(h5file, hdf5_acc_file=None):
     return Genotype(h5file, hdf5_acc_file)
+
+
+def order_markers(cid, sample_pos):
+    """(order, chrom_id int32, pos int32) for the device join from per-marker database chromosome ids (-1 = not in the
+    database): markers grouped by chromosome id (unknown last), inside a chromosome in the caller's order."""
+    cid = np.asarray(cid)
+    sample_pos = np.asarray(sample_pos)
+    in_range = (sample_pos >= -2**31) & (sample_pos < 2**31 - 1)
+    cid = np.where(in_range, cid, -1).astype(np.int32)
+    sort_key = np.where(cid < 0, np.int64(2**31), cid.astype(np.int64))
+    order = np.argsort(sort_key, kind="stable")
+    cid_o = cid[order]
+    pos_o = np.where(in_range, sample_pos, 0)[order].astype(np.int32)
+    # the join needs strictly ascending positions inside a chromosome (the reference's implicit
+    # precondition, SURVEY A.1); sort a chromosome that is not
+    bad = (cid_o[1:] == cid_o[:-1]) & (cid_o[1:] >= 0) & (pos_o[1:] <= pos_o[:-1])
+    if bad.any():
+        log.warning("sample positions are not sorted inside a chromosome; sorting them for the join")
+        k = np.lexsort((pos_o, np.where(cid_o < 0, np.int64(2**31), cid_o.astype(np.int64))))
+        order, cid_o, pos_o = order[k], cid_o[k], pos_o[k]
+        dup = (cid_o[1:] == cid_o[:-1]) & (cid_o[1:] >= 0) & (pos_o[1:] == pos_o[:-1])
+        if dup.any():                      # a repeated marker cannot be paired one-to-one: keep the first
+            cid_o = cid_o.copy()
+            cid_o[1:][dup] = -1
+            k2 = np.argsort(np.where(cid_o < 0, np.int64(2**31), cid_o.astype(np.int64)), kind="stable")
+            order, cid_o, pos_o = order[k2], cid_o[k2], pos_o[k2]
+    return order, np.ascontiguousarray(cid_o), np.ascontiguousarray(pos_o)
+
+
+def join_coded(c1, p1, c2, p2, n_chr, device=0):
+    """Inner join of two marker lists on (chromosome code, position) on the device: side 1 is indexed as a one-accession
+    panel.  Codes are integers in [0, n_chr) (side 2: anything else = no partner).  Returns (i1, i2), paired, ordered by
+    (code, position)."""
+    c1, p1 = np.asarray(c1, dtype=np.int64), np.asarray(p1, dtype=np.int64)
+    if len(c1) == 0 or len(c2) == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    if np.all((c1[1:] > c1[:-1]) | ((c1[1:] == c1[:-1]) & (p1[1:] > p1[:-1]))):
+        o1 = np.arange(len(p1))                    # already grouped by chromosome with ascending positions
+    else:
+        o1 = np.lexsort((p1, c1))
+    counts = np.bincount(c1, minlength=n_chr)
+    ends = np.cumsum(counts)
+    regions = np.stack([ends - counts, ends], axis=1)
+    c2 = np.asarray(c2, dtype=np.int64)
+    cid2 = np.where((c2 >= 0) & (c2 < n_chr), c2, -1)
+    order2, cid2_o, pos2_o = order_markers(cid2, p2)
+    db = lib.Database(p1[o1].astype(np.int32), regions, 1, device=device)
+    try:
+        db_idx, s_idx = db.intersect(cid2_o, pos2_o, lib.JOIN_AUTO)
+    finally:
+        db.close()
+    return o1[db_idx], order2[s_idx]
 
 
 class _SnpsView(object):
@@ -186,36 +239,16 @@ class Genotype(object):
         from . import genomes
         sample_chrs = np.asarray(sample_chrs)
         sample_pos = np.asarray(sample_pos)
-        if style == "join":
-            db_norm, s_norm = self._db_chr_norm, normalize_chr_names(sample_chrs)
-        else:
-            db_norm, s_norm = genomes.genome_style_ids(self.chrs), genomes.genome_style_ids(sample_chrs)
+        norm = (lambda c: _CHR_RE.sub("", c)) if style == "join" else (lambda c: c.lower().replace("chr", ""))
+        db_norm = self._db_chr_norm if style == "join" else genomes.genome_style_ids(self.chrs)
         first = {}
         for i, name in enumerate(db_norm):
             first.setdefault(name, i)
-        uniq, inv = np.unique(s_norm, return_inverse=True) if len(s_norm) else (s_norm, np.zeros(0, dtype=int))
-        table = np.array([first.get(u, -1) for u in uniq], dtype=np.int32)
-        cid = table[inv] if len(s_norm) else np.zeros(0, dtype=np.int32)
-        in_range = (sample_pos >= -2**31) & (sample_pos < 2**31 - 1)
-        cid = np.where(in_range, cid, -1).astype(np.int32)
-        sort_key = np.where(cid < 0, np.int64(2**31), cid.astype(np.int64))
-        order = np.argsort(sort_key, kind="stable")
-        cid_o = cid[order]
-        pos_o = np.where(in_range, sample_pos, 0)[order].astype(np.int32)
-        # the join needs strictly ascending positions inside a chromosome (the reference's implicit
-        # precondition); sort a chromosome that is not
-        bad = (cid_o[1:] == cid_o[:-1]) & (cid_o[1:] >= 0) & (pos_o[1:] <= pos_o[:-1])
-        if bad.any():
-            log.warning("sample positions are not sorted inside a chromosome; sorting them for the join")
-            k = np.lexsort((pos_o, np.where(cid_o < 0, np.int64(2**31), cid_o.astype(np.int64))))
-            order, cid_o, pos_o = order[k], cid_o[k], pos_o[k]
-            dup = (cid_o[1:] == cid_o[:-1]) & (cid_o[1:] >= 0) & (pos_o[1:] == pos_o[:-1])
-            if dup.any():                      # a repeated marker cannot be paired one-to-one: keep the first
-                cid_o = cid_o.copy()
-                cid_o[1:][dup] = -1
-                k2 = np.argsort(np.where(cid_o < 0, np.int64(2**31), cid_o.astype(np.int64)), kind="stable")
-                order, cid_o, pos_o = order[k2], cid_o[k2], pos_o[k2]
-        return order, np.ascontiguousarray(cid_o), np.ascontiguousarray(pos_o)
+        # per-marker names -> codes + the few distinct names; the database index is looked up per distinct name
+        _, codes, uniq_norm = labels.map_labels(sample_chrs, norm)
+        table = np.array([first.get(u, -1) for u in uniq_norm], dtype=np.int32)
+        cid = table[codes] if len(codes) else np.zeros(0, dtype=np.int32)
+        return order_markers(cid, sample_pos)
 
     # ---- A1 -------------------------------------------------------------------------------------------
     def get_positions_idxs(self, commonSNPsCHR, commonSNPsPOS, algo=lib.JOIN_AUTO):
@@ -232,28 +265,18 @@ class Genotype(object):
         callers' own orders."""
         assert len(input_1_chr) == len(input_1_pos), "Both chromosome and position array provided should be of same length"
         assert len(input_2_chr) == len(input_2_pos), "Both chromosome and position array provided should be of same length"
-        c1 = normalize_chr_names(input_1_chr)
         p1 = np.asarray(input_1_pos).astype(np.int64)
-        if len(c1) == 0 or len(input_2_chr) == 0:
+        if len(input_1_chr) == 0 or len(input_2_chr) == 0:
             return np.zeros(0, dtype=int), np.zeros(0, dtype=int)
-        _, first = np.unique(c1, return_index=True)
-        ids = c1[np.sort(first)]                       # first-appearance order (parsers.py:162-163)
+        # side-1 chromosomes in first-appearance order of their normalised names (parsers.py:161-163)
+        _, codes1, uniq_norm = labels.map_labels(input_1_chr, lambda c: _CHR_RE.sub("", c))
+        rank_of_uniq, ids = labels.factorize(uniq_norm)              # raw names that normalise to the same id share a rank
+        r1 = rank_of_uniq[codes1]
+        # side 2: the rank of its normalised chromosome names among side 1's
+        _, codes2, uniq2 = labels.map_labels(input_2_chr, lambda c: _CHR_RE.sub("", c))
         rank = {name: i for i, name in enumerate(ids)}
-        r1 = np.array([rank[c] for c in c1], dtype=np.int64)
-        o1 = np.lexsort((p1, r1))                      # rows grouped by chromosome, positions ascending
-        counts = np.bincount(r1, minlength=len(ids))
-        ends = np.cumsum(counts)
-        regions = np.stack([ends - counts, ends], axis=1)
-        tmp = object.__new__(Genotype)
-        db = lib.Database(p1[o1].astype(np.int32), regions, 1, device=device)
-        try:
-            tmp._finish(db, p1[o1], ids, regions, np.array([b"0"]))
-            order2, cid2, pos2 = tmp.prepare_markers(input_2_chr, input_2_pos)
-            db_idx, s_idx = db.intersect(cid2, pos2, lib.JOIN_AUTO)
-        finally:
-            db.close()
-        idx1 = o1[db_idx]
-        idx2 = order2[s_idx]
+        r2 = np.array([rank.get(u, -1) for u in uniq2], dtype=np.int64)[codes2]
+        idx1, idx2 = join_coded(r1, p1, r2, input_2_pos, len(ids), device=device)
         # reference order: per chromosome (side-1 order) each side in its own order
         k1 = np.lexsort((idx1, r1[idx1]))
         k2 = np.lexsort((idx2, r1[idx1]))

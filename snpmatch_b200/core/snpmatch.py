@@ -18,6 +18,7 @@ import numpy as np
 import pandas as pd
 
 from .. import lib
+from . import labels
 from . import parsers
 from . import snp_genotype
 
@@ -338,10 +339,10 @@ def pairwiseScore(inFile_1, inFile_2, logDebug, outFile=None, hdf5File=None, dev
     common_chrs = np.intersect1d(inputs_1.g_chrs_ids, inputs_2.g_chrs_ids)
     # what crosses the C ABI: chromosome id (index into common_chrs, -1 elsewhere) of every marker of sample 1 and the ids
     # of the genotype strings in one table for both samples
-    pos_in_common = np.searchsorted(common_chrs, inputs_1.g_chrs) if len(common_chrs) else np.zeros(n1, dtype=int)
-    pos_in_common = np.minimum(pos_in_common, max(len(common_chrs) - 1, 0))
-    chrom1 = np.where(common_chrs[pos_in_common] == inputs_1.g_chrs, pos_in_common, -1) if len(common_chrs) else np.full(n1, -1)
-    _, gt_ids = np.unique(np.concatenate([inputs_1.gt.astype("U"), inputs_2.gt.astype("U")]), return_inverse=True)
+    codes1, uniq1 = labels.factorize(inputs_1.g_chrs)
+    in_common = {c: k for k, c in enumerate(common_chrs)}
+    chrom1 = np.array([in_common.get(u, -1) for u in uniq1], dtype=np.int32)[codes1] if n1 else np.zeros(0, dtype=np.int32)
+    gt_ids = labels.factorize(np.concatenate([inputs_1.gt.astype("U"), inputs_2.gt.astype("U")]))[0]
     common, scores = lib.pair_match_counts(common_inds[0], common_inds[1], chrom1, gt_ids[:n1], gt_ids[n1:], len(common_chrs), device=device)
     for k, i in enumerate(common_chrs):
         log.info("Analysing chromosome %s positions", i)
