@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--hard", action="store_true", help="called genotypes (one-hot weights) instead of PL weights")
+    ap.add_argument("--shard-of", type=int, default=1, help="hold only the first 1/K of the panel rows, as rank 0 of a K-GPU run does "
+                                                            "(use --samples 64*K for the per-rank work of bench.py --gpus K)")
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
@@ -29,7 +31,7 @@ def main():
     from snpmatch_b200.core import snp_genotype
     import bench
     positions, regions = synth.panel_positions(args.rows)
-    g = snp_genotype.Genotype.synthetic(args.rows, args.accessions, device=0)
+    g = snp_genotype.Genotype.synthetic(args.rows, args.accessions, device=0, row_range=(0, args.rows // args.shard_of))
     db = g.db
     bench.N_EXTRA_MARKERS = 5000
     samples = bench.make_samples(positions, regions, args.accessions, args.samples, args.markers)

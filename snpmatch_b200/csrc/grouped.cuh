@@ -33,10 +33,7 @@ constexpr int GR_THREADS = 128;                       // 3 teams of 36 threads; 
 constexpr int GR_MAX_WX = 36;                         // words per team (one 1135-accession row)
 constexpr int GR_MAX_TEAMS = 3;
 constexpr int GR_BLOCK = 16;                          // rows per step
-#ifndef GR_RING_ROWS
-#define GR_RING_ROWS 64
-#endif
-constexpr int GR_RING = GR_RING_ROWS;                           // rows of the per-team ring
+constexpr int GR_RING = 64;                           // rows of the per-team ring
 constexpr int GR_INFLIGHT = GR_RING / GR_BLOCK;
 constexpr int GR_LP = 10;                             // planes of a counter (chunk <= 1023 rows)
 constexpr int GR_MAX_CHUNK = 1008;
