@@ -17,7 +17,7 @@ samples, each scored on its own exactly as separate `snpmatch inbred` runs would
   cpu_baseline  the CPU oracle (a NumPy restatement of the reference path) on one sample, one core.
 
 N > 1 (torchrun): the panel is sharded by SNP-row ranges, samples are replicated, per-GPU partial
-scores/counts are summed with one NCCL reduce-scatter, then every rank runs the epilogue on, and reads back, its
+scores/counts are summed with one reduce-scatter (a one-shot pull over peer memory, or NCCL with --reduce nccl), then every rank runs the epilogue on, and reads back, its
 share of the samples.
 The batch grows with N (samples = N x --samples) so that per-GPU work is fixed: "scaling": "weak".
 
@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group-chunk", type=int, default=320, help="rows per segment of the grouped kernel")
     ap.add_argument("--force-exact", action="store_true", help="order-exact fp64 kernel as the headline path")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl", "none"], help="(none: timing experiment only, totals stay per rank) cross-GPU sum of the per-sample totals: one-shot reduce over peer "
+                    "memory (CUDA IPC over NVLink, barrier + pull in one kernel) or an NCCL reduce-scatter")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     return ap.parse_args()
 
@@ -70,7 +72,8 @@ def workload_config(args, n_gpus, n_samples):
                         n_samples, args.markers + N_EXTRA_MARKERS, args.markers, args.accessions, args.rows),
         "panel_rows": args.rows, "accessions": args.accessions, "samples_per_step": n_samples,
         "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)", "kernel": "grouped counting kernel (markers ordered by weight triple at parse time)",
-        "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + one NCCL reduce-scatter of the per-accession partials per step (every rank finishes and reads back its share of the samples)" % n_gpus,
+        "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + one reduce-scatter of the per-accession partials per step (%s; every rank finishes and reads back its share of the samples)" % (
+            n_gpus, "one kernel over peer memory: flag barrier + 16-byte pulls through NVLink, no collective library on the path" if args.reduce == "p2p" else "NCCL"),
         "cache": "inputs larger than L2: each step gathers %.0f MB of distinct panel rows" % (
             n_samples * args.markers * ((args.accessions + 63) // 64 * 16) / 1e6),
     }
@@ -319,9 +322,19 @@ def run_b200_arm(args):
     use_grouped = not args.force_exact
 
     def reduce_totals(b):
-        # one NCCL reduce-scatter of the per-sample totals: every rank is left with the totals of its S/world samples and
-        # finishes (epilogue) and reads back only those
-        sharding.reduce_scatter_batch(b, dist, dev, rank, world)
+        # reduce-scatter of the per-sample totals: every rank is left with the totals of its S/world samples and finishes
+        # (epilogue) and reads back only those.  p2p: one kernel that is barrier + pull over peer memory (k_reduce_peers)
+        if args.reduce == "p2p":
+            sharding.p2p_reduce_scatter(b)
+        elif args.reduce == "none":
+            pass
+        else:
+            sharding.reduce_scatter_batch(b, dist, dev, rank, world)
+
+    def run_batch(b, **kw):
+        if world > 1 and args.reduce == "p2p":
+            sharding.p2p_before_run(b, dist, rank, world, host_pg)      # maps the peers' buffers on first use (host collective)
+        b.run(**kw)
 
     def own_share(b):
         if world > 1:
@@ -333,7 +346,7 @@ def run_b200_arm(args):
 
     def device_step(b=None, mode=None):
         b = (gbatch if use_grouped else batch) if b is None else b
-        b.run(kernel_mode=lib.KERNEL_GROUPED if b is gbatch else lib.KERNEL_FP64)
+        run_batch(b, kernel_mode=lib.KERNEL_GROUPED if b is gbatch else lib.KERNEL_FP64)
         if world > 1:
             reduce_totals(b)
         b.epilogue()
@@ -350,10 +363,10 @@ def run_b200_arm(args):
         for _ in range(args.warmup):
             device_step()
         head.wait()
-        barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
-            sampler.start()
+            sampler.start()                        # before the barrier: forking nvidia-smi takes ~1 ms, which the other ranks would
+        barrier()                                  # otherwise spend waiting for rank 0 inside the first timed step
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(args.steps):
@@ -400,7 +413,7 @@ def run_b200_arm(args):
         hard_ms, hard_kernel_ms = 0.0, []
 
         def hard_step():
-            hard.run(kernel_mode=lib.KERNEL_POPCOUNT)
+            run_batch(hard, kernel_mode=lib.KERNEL_POPCOUNT)
             if world > 1:
                 reduce_totals(hard)
             hard.epilogue()
@@ -428,7 +441,7 @@ def run_b200_arm(args):
         hard.upload_grouped(hard_gs)
 
         def hardg_step():
-            hard.run(kernel_mode=lib.KERNEL_GROUPED)
+            run_batch(hard, kernel_mode=lib.KERNEL_GROUPED)
             if world > 1:
                 reduce_totals(hard)
             hard.epilogue()
@@ -487,7 +500,7 @@ def run_b200_arm(args):
 
         def launch(k):
             b_ = pair[k % 2]
-            b_.run(kernel_mode=lib.KERNEL_GROUPED if use_grouped else lib.KERNEL_FP64)
+            run_batch(b_, kernel_mode=lib.KERNEL_GROUPED if use_grouped else lib.KERNEL_FP64)
             if world > 1:
                 reduce_totals(b_)
             b_.epilogue()

@@ -187,6 +187,20 @@ int snpm_batch_set_result_range(snpm_batch *b, int64_t first_sample, int64_t n_s
  * Grouped batches: [S, 3*n_acc+2] = fractional part F | ninfo | m | violations | integer part I; the epilogue
  * turns F into the score after the reduce. */
 int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles);
+/* ---- 8(e): the cross-GPU sum as a one-shot reduce over peer memory (NVLink / NVSwitch), one process per GPU -------------
+ * Every rank exports the reduce buffer of its batch (snpm_batch_ipc_export: a 64-byte CUDA IPC handle; the buffer holds
+ * n_doubles values), the handles are exchanged by the host (any transport: torch.distributed.all_gather_object, MPI, a
+ * file), and snpm_batch_ipc_open maps the world's buffers (handles = world x 64 bytes, in rank order; at most 16 ranks).
+ * Per step, AFTER a cross-rank barrier that orders every rank's snpm_batch_run before it on the stream (the host's job:
+ * e.g. a one-element NCCL all-reduce), snpm_batch_reduce_peers queues one kernel that sums, for the samples of this rank's
+ * result range (snpm_batch_set_result_range), the rows of all ranks with 16-byte peer loads in rank order into the own
+ * buffer — the reduce-scatter of sharding.reduce_scatter_batch without a collective library on the data path.  Before the
+ * NEXT snpm_batch_run of any rank a second barrier must have passed (the peers may still be reading).  The batch must keep
+ * its size between export and use (SNPM_E_STATE otherwise). */
+int snpm_batch_ipc_export(snpm_batch *b, void *handle64, int64_t *n_doubles);
+int snpm_batch_ipc_open(snpm_batch *b, const void *handles, int32_t world, int32_t rank);
+int snpm_batch_reduce_peers(snpm_batch *b);
+int snpm_batch_ipc_close(snpm_batch *b);
 /* copy results to the host (any pointer may be NULL).  score f64[S,A] (untruncated),
  * matches int64[S,A] (= int(score), snpmatch.py:96), ninfo int64[S,A], m int64[S],
  * prob/L/LR f64[S,A]. */

@@ -671,6 +671,8 @@ int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows) {
     return SNPM_OK;
 }
 
+static void ipc_close_peers(snpm_batch *b);
+
 int snpm_batch_destroy(snpm_batch *b) {
     if (!b) return SNPM_OK;
     cudaSetDevice(b->db->device);
@@ -691,6 +693,7 @@ int snpm_batch_destroy(snpm_batch *b) {
     if (b->h_tail) cudaFreeHost(b->h_tail);
     if (b->ev_fetched) cudaEventDestroy(b->ev_fetched);
     if (b->ev_results) cudaEventDestroy(b->ev_results);
+    ipc_close_peers(b);
     delete b;
     return SNPM_OK;
 }
@@ -728,6 +731,11 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
     SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_uploaded, 0));       // the samples are on the device
     SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
+    if (!b->peer_red.empty() && b->ipc_step > 0 && b->d_red.p == b->ipc_ptr) {      // the peers have pulled their rows of the last step
+        k_wait_peers_done<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t *>(static_cast<const char *>(b->d_red.p) + b->ipc_flags_off),
+                                            int32_t(b->peer_red.size()), b->ipc_step, b->d_status.as<int>());
+        SNPM_KERNEL_CHECK();
+    }
     // auto: per-marker binary search for low-coverage samples (n << N: a tile of markers spans a long panel slice), merge-path
     // once a sample carries more than an eighth of the panel rows (measured at m = N = 10.7 M: 0.40 ms vs 0.47 ms)
     if (algo == 0) algo = (n / S) * 8 >= db->n_rows ? 2 : 1;
@@ -964,6 +972,8 @@ int snpm_batch_wait(snpm_batch *b, float *ms_device) {
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
     if (b->h_status[4] > 0)
         return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table", b->h_status[4]);
+    if (b->h_status[5] > 0)
+        return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within two seconds (every rank must run and reduce the same batches in the same order)");
     return SNPM_OK;
 }
 
@@ -983,6 +993,12 @@ int snpm_batch_timings(snpm_batch *b, float *ms, int n) {
     ms[3] = el(SNPM_EV_EPI_START, SNPM_EV_EPI_END);
     ms[4] = el(SNPM_EV_START, SNPM_EV_COMBINE) + ms[3];
     ms[5] = float(b->launches);
+    if (n >= 8) {                                  // one-shot peer reduce of the last step: the whole kernel, and its wait for the slowest rank
+        ms[6] = el(SNPM_EV_RED_START, SNPM_EV_RED_END);
+        int wait_ns = 0;
+        if (b->ev_rec[SNPM_EV_RED_END] && b->d_status.p) cudaMemcpy(&wait_ns, b->d_status.as<int>() + 7, sizeof(int), cudaMemcpyDeviceToHost);
+        ms[7] = float(wait_ns) * 1e-6f;
+    }
     return SNPM_OK;
 }
 
@@ -992,6 +1008,93 @@ int snpm_batch_reduce_buffer(snpm_batch *b, void **dev_ptr, int64_t *n_doubles) 
     SNPM_TRY(b->d_red.ensure(size_t(b->S) * size_t(b->red_pitch()) * 8));
     *dev_ptr = b->d_red.p;
     if (n_doubles) *n_doubles = b->S * b->red_pitch();
+    return SNPM_OK;
+}
+
+// ---- one-shot reduce over peer memory ----------------------------------------------------------------------
+static void ipc_close_peers(snpm_batch *b) {
+    for (size_t r = 0; r < b->peer_red.size(); ++r)
+        if (int32_t(r) != b->ipc_rank && b->peer_red[r]) cudaIpcCloseMemHandle(b->peer_red[r]);
+    b->peer_red.clear();
+    b->ipc_rank = -1;
+}
+
+int snpm_batch_ipc_export(snpm_batch *b, void *handle64, int64_t *n_doubles) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!b || !handle64) return fail(SNPM_E_ARG, "snpm_batch_ipc_export: NULL argument");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    // at least 4 MB: large allocations are their own mapping, so the peers' pointer is the buffer itself (small cudaMalloc
+    // blocks may be carved out of a shared 2 MB page, whose IPC handle maps the page).  The last 4 KB hold the flags.
+    const size_t bytes = size_t(b->S) * size_t(b->red_pitch()) * 8;
+    const size_t cap = std::max<size_t>(((bytes + 255) & ~size_t(255)) + PR_FLAG_BYTES, size_t(4) << 20);
+    SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
+    if (b->d_red.cap != cap) {
+        b->d_red.release();
+        SNPM_TRY(b->d_red.ensure(cap));
+    }
+    b->ipc_flags_off = cap - PR_FLAG_BYTES;
+    b->ipc_step = 0;
+    SNPM_CUDA(cudaMemset(static_cast<char *>(b->d_red.p) + b->ipc_flags_off, 0, PR_FLAG_BYTES));
+    SNPM_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), b->d_red.p));
+    b->ipc_ptr = b->d_red.p;
+    if (n_doubles) *n_doubles = b->S * b->red_pitch();
+    return SNPM_OK;
+}
+
+int snpm_batch_ipc_open(snpm_batch *b, const void *handles, int32_t world, int32_t rank) {
+    if (!b || !handles || world < 1 || world > PR_MAX_WORLD || rank < 0 || rank >= world) return fail(SNPM_E_ARG, "snpm_batch_ipc_open: bad arguments (at most %d ranks)", PR_MAX_WORLD);
+    if (!b->ipc_ptr || b->ipc_ptr != b->d_red.p) return fail(SNPM_E_STATE, "snpm_batch_ipc_open: export this batch's buffer first (snpm_batch_ipc_export)");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    ipc_close_peers(b);
+    b->peer_red.assign(size_t(world), nullptr);
+    b->ipc_rank = rank;
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int32_t r = 0; r < world; ++r) {
+        if (r == rank) { b->peer_red[size_t(r)] = b->d_red.p; continue; }
+        cudaError_t e = cudaIpcOpenMemHandle(&b->peer_red[size_t(r)], h[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            b->peer_red[size_t(r)] = nullptr;
+            ipc_close_peers(b);
+            return fail(SNPM_E_CUDA, "snpm_batch_ipc_open: rank %d's buffer: %s", r, cudaGetErrorString(e));
+        }
+    }
+    return SNPM_OK;
+}
+
+int snpm_batch_ipc_close(snpm_batch *b) {
+    if (!b) return SNPM_OK;
+    cudaSetDevice(b->db->device);
+    cudaStreamSynchronize(b->db->stream);
+    ipc_close_peers(b);
+    b->ipc_ptr = nullptr;
+    return SNPM_OK;
+}
+
+int snpm_batch_reduce_peers(snpm_batch *b) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_reduce_peers: NULL batch");
+    if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_reduce_peers: run the batch first");
+    const int32_t world = int32_t(b->peer_red.size());
+    if (world < 1 || b->ipc_rank < 0) return fail(SNPM_E_STATE, "snpm_batch_reduce_peers: open the peers' buffers first (snpm_batch_ipc_open)");
+    if (b->d_red.p != b->ipc_ptr) return fail(SNPM_E_STATE, "snpm_batch_reduce_peers: the reduce buffer moved since it was exported (batch grew): export and open again");
+    const int64_t r0 = b->res0, rn = b->resn < 0 ? b->S - b->res0 : b->resn;
+    if (r0 + rn > b->S) return fail(SNPM_E_ARG, "snpm_batch_reduce_peers: result range outside the batch");
+    const int64_t pitch = b->red_pitch();
+    int64_t first = r0 * pitch, count = rn * pitch;          // an empty share still takes part in the barrier
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    PeerPtrs pp;
+    for (int32_t r = 0; r < PR_MAX_WORLD; ++r) {
+        pp.p[r] = r < world ? static_cast<const double *>(b->peer_red[size_t(r)]) : nullptr;
+        pp.flags[r] = r < world ? reinterpret_cast<uint32_t *>(static_cast<char *>(b->peer_red[size_t(r)]) + b->ipc_flags_off) : nullptr;
+    }
+    b->ipc_step += 1;
+    rec(b, SNPM_EV_RED_START);
+    const bool vec = ((first | count) & 1) == 0;
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(vec ? count / 2 : count, 256), int64_t(b->db->n_sm) * 4)));
+    if (vec) k_reduce_peers<double2><<<grid, 256, 0, b->db->stream>>>(pp, world, b->ipc_rank, b->ipc_step, first, count, b->d_red.as<double>(), b->d_status.as<int>());
+    else k_reduce_peers<double><<<grid, 256, 0, b->db->stream>>>(pp, world, b->ipc_rank, b->ipc_step, first, count, b->d_red.as<double>(), b->d_status.as<int>());
+    rec(b, SNPM_EV_RED_END);
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
     return SNPM_OK;
 }
 
@@ -1084,6 +1187,8 @@ int snpm_batch_fetch_wait(snpm_batch *b) {
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
     if (b->h_status[4] > 0)
         return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table", b->h_status[4]);
+    if (b->h_status[5] > 0)
+        return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within two seconds (every rank must run and reduce the same batches in the same order)");
     long long viol = 0;
     for (int64_t s = 0; s < b->rangen(); ++s) {
         if (b->pend_m) b->pend_m[s] = int64_t(b->h_tail[2 * s]);

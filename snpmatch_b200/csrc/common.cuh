@@ -108,7 +108,7 @@ struct snpm_db {
     struct snpm_batch *scratch_batch_ = nullptr;   // reused by snpm_score
 };
 
-enum { SNPM_EV_START = 0, SNPM_EV_JOIN, SNPM_EV_SCORE, SNPM_EV_COMBINE, SNPM_EV_EPI_START, SNPM_EV_EPI_END, SNPM_N_EVENTS };
+enum { SNPM_EV_START = 0, SNPM_EV_JOIN, SNPM_EV_SCORE, SNPM_EV_COMBINE, SNPM_EV_EPI_START, SNPM_EV_EPI_END, SNPM_EV_RED_START, SNPM_EV_RED_END, SNPM_N_EVENTS };
 
 struct snpm_batch {
     snpm_db *db = nullptr;
@@ -158,6 +158,12 @@ struct snpm_batch {
     bool fetch_pending = false;
     // result range (snpm_batch_set_result_range): the epilogue and the fetches work on samples [res0, res0 + resn); resn < 0 = all
     int64_t res0 = 0, resn = -1;
+    // one-shot reduce over peer memory (snpm_batch_ipc_*): the reduce buffers of the other ranks' batches, opened through CUDA IPC
+    void *ipc_ptr = nullptr;             // d_red.p at export time: the allocation the peers have mapped
+    std::vector<void *> peer_red;        // [world]; [rank] = own buffer
+    int32_t ipc_rank = -1;
+    size_t ipc_flags_off = 0;            // byte offset of the flag block inside the exported allocation (the same on every rank)
+    uint32_t ipc_step = 0;               // reduces done since the export: the value the flags carry
     int64_t range0() const { return resn < 0 ? 0 : res0; }
     int64_t rangen() const { return resn < 0 ? S : resn; }
 };

@@ -527,6 +527,109 @@ __global__ void __launch_bounds__(32 * CG_PARTS) k_combine_grouped(const double 
     }
 }
 
+// ---- one-shot reduce over peer memory --------------------------------------------------------
+// The cross-GPU sum of the per-sample totals with no collective library on the path: every rank's reduce buffer is mapped
+// into every other rank (CUDA IPC over NVLink / NVSwitch).  k_reduce_peers is barrier + reduce-scatter in one kernel:
+//   arrive  block 0 publishes "my totals of step t are complete" into every peer's flag block (st.release.sys; the totals were
+//           written by the kernels before this one on the stream),
+//   wait    every block spins (ld.acquire.sys) until all ranks have arrived at step t,
+//   reduce  the rows of THIS rank's share of the samples are pulled from all ranks with 16-byte loads and summed in rank
+//           order (every rank would compute the same bits) into the own buffer; nothing is pushed, and the rows a rank
+//           writes are never read by a peer,
+//   done    the last block publishes "I have pulled my rows of step t": k_wait_peers_done at the head of the next run keeps
+//           the next totals from overwriting rows a peer is still reading.
+// Flags are step counters (monotonic, compared with wrap-around), so a rank that is one step ahead disturbs nobody.  A spin
+// gives up after two seconds and raises status[5] instead of hanging the GPU.  Works for both row layouts (2A+2, 3A+2).
+constexpr int PR_MAX_WORLD = 16;
+constexpr int PR_FLAG_BYTES = 4096;      // tail of the exported allocation: arrive[16] at u32 0.., done[16] at u32 64..
+constexpr int PR_DONE_OFF = 64;
+struct PeerPtrs {
+    const double *p[PR_MAX_WORLD];
+    uint32_t *flags[PR_MAX_WORLD];
+};
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// true when *f has reached `want` (step counters: signed distance); false after ~2 s
+__device__ __forceinline__ bool spin_until(const uint32_t *f, uint32_t want) {
+    const unsigned long long t0 = global_timer_ns();
+    while (int32_t(ld_acquire_sys_u32(f) - want) < 0) {
+        __nanosleep(40);
+        if (global_timer_ns() - t0 > 2000000000ull) return false;
+    }
+    return true;
+}
+template <typename V>
+__device__ __forceinline__ V ld_peer(const double *p);
+template <>
+__device__ __forceinline__ double ld_peer<double>(const double *p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+template <>
+__device__ __forceinline__ double2 ld_peer<double2>(const double *p) {
+    double2 v;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) k_reduce_peers(const PeerPtrs peers, int32_t world, int32_t rank, uint32_t step, int64_t first, int64_t count,
+                                                      double *__restrict__ own, int *status) {
+    // V = double2 when `first` and `count` (in doubles) are even: 16-byte peer loads; else double
+    constexpr int W = int(sizeof(V) / sizeof(double));
+    __shared__ int s_last;
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys_u32(peers.flags[threadIdx.x] + rank, step);                     // arrive
+    }
+    const unsigned long long t_wait = global_timer_ns();
+    if (threadIdx.x < world && !spin_until(peers.flags[rank] + threadIdx.x, step)) atomicExch(status + 5, 1);   // wait
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[7] = int(global_timer_ns() - t_wait);       // ns spent waiting for the slowest rank
+    const int64_t nv = count / W;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t o = first + W * i;
+        double acc[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k] = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < world; ++r) {
+            const V v = ld_peer<V>(peers.p[r] + o);
+            const double *e = reinterpret_cast<const double *>(&v);
+#pragma unroll
+            for (int k = 0; k < W; ++k) acc[k] += e[k];
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) own[o + k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int prev = atomicAdd(status + 6, 1);                                     // blocks that have pulled their part
+        s_last = prev == int(gridDim.x) - 1;
+        if (s_last) status[6] = 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < world) st_release_sys_u32(peers.flags[threadIdx.x] + PR_DONE_OFF + rank, step);   // done
+}
+
+// head of the next run: every peer has pulled its rows of step `want`
+__global__ void __launch_bounds__(32) k_wait_peers_done(const uint32_t *own_flags, int32_t world, uint32_t want, int *status) {
+    if (threadIdx.x < world && !spin_until(own_flags + PR_DONE_OFF + threadIdx.x, want)) atomicExch(status + 5, 1);
+}
+
 // score = I + F with the reference's truncation made explicit: matches = I + floor(F) (see the header).  The score is
 // stored so that the epilogue's int(score) gives exactly that, and cells whose F lies within the summation-error bound of
 // an integer k >= 1 are counted in guard[s]: for them the reference's own rounding decides, so the caller re-scores the

@@ -149,6 +149,10 @@ SIGNATURES = {
     "snpm_batch_epilogue": (C.c_int, [_p]),
     "snpm_batch_wait": (C.c_int, [_p, _p]),
     "snpm_batch_reduce_buffer": (C.c_int, [_p, _p, _p]),
+    "snpm_batch_ipc_export": (C.c_int, [_p, _p, _p]),
+    "snpm_batch_ipc_open": (C.c_int, [_p, _p, _i32, _i32]),
+    "snpm_batch_reduce_peers": (C.c_int, [_p]),
+    "snpm_batch_ipc_close": (C.c_int, [_p]),
     "snpm_batch_fetch": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p]),
     "snpm_batch_fetch_async": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "snpm_batch_fetch_wait": (C.c_int, [_p]),
@@ -429,16 +433,38 @@ class Batch(object):
         return ms.value
 
     def timings(self):
-        ms = np.zeros(6, dtype=np.float32)
-        check(load().snpm_batch_timings(self._h, ptr(ms), 6))
-        return {"join_ms": float(ms[0]), "score_ms": float(ms[1]), "combine_ms": float(ms[2]), "epilogue_ms": float(ms[3]),
-                "total_ms": float(ms[4]), "launches": int(ms[5])}
+        ms = np.zeros(8, dtype=np.float32)
+        check(load().snpm_batch_timings(self._h, ptr(ms), 8))
+        t = {"join_ms": float(ms[0]), "score_ms": float(ms[1]), "combine_ms": float(ms[2]), "epilogue_ms": float(ms[3]),
+             "total_ms": float(ms[4]), "launches": int(ms[5])}
+        if ms[6] > 0:              # one-shot peer reduce: the kernel, and the part of it spent waiting for the slowest rank
+            t["peer_reduce_ms"], t["peer_wait_ms"] = float(ms[6]), float(ms[7])
+        return t
 
     def reduce_buffer(self):
         """(device pointer, number of f64) of the per-sample totals — the payload of the cross-GPU sum."""
         p, n = C.c_void_p(), C.c_int64(0)
         check(load().snpm_batch_reduce_buffer(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of the reduce buffer (bytes) for the one-shot peer reduce."""
+        h = C.create_string_buffer(64)
+        n = C.c_int64(0)
+        check(load().snpm_batch_ipc_export(self._h, h, C.byref(n)))
+        return h.raw
+
+    def ipc_open(self, handles, rank):
+        """handles: list of every rank's ipc_export() bytes, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        check(load().snpm_batch_ipc_open(self._h, C.c_char_p(blob), len(handles), int(rank)))
+
+    def reduce_peers(self):
+        check(load().snpm_batch_reduce_peers(self._h))
+
+    def ipc_close(self):
+        check(load().snpm_batch_ipc_close(self._h))
 
     def fetch(self, epilogue=True, out=None):
         S, A = self._n_results(), self.db.n_acc

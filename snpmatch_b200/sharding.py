@@ -179,3 +179,34 @@ def reduce_scatter_batch(batch, dist, device, rank, world):
     dist.reduce_scatter_tensor(out, t)
     t.view(world, -1)[rank].copy_(out)
     return out
+
+
+# ---- one-shot reduce over peer memory (csrc/grouped.cuh: k_reduce_peers) ------------------------------------------------
+# The same reduce-scatter as reduce_scatter_batch with no collective library on the path: every rank maps the reduce buffers of
+# all ranks (CUDA IPC over NVLink / NVSwitch) and ONE kernel per step does the cross-rank barrier (step-counter flags in peer
+# memory) and pulls + sums the rows of this rank's samples.  torch.distributed is used once, to exchange the 64-byte handles.
+def p2p_before_run(batch, dist, rank, world, host_group=None):
+    """Call before batch.run() on every rank at the same point: (re)maps the peers' reduce buffers when this batch has not been
+    set up yet or its buffer changed (another sample count or row layout).  The set-up is a host collective."""
+    import torch
+
+    st = getattr(batch, "_p2p", None)
+    if st is None:
+        st = batch._p2p = {"key": None}
+    key = batch.reduce_buffer()                    # (device pointer, doubles): allocates for the current samples and row layout
+    if st["key"] != key:
+        torch.cuda.current_stream().synchronize()
+        seen = [None] * world
+        dist.all_gather_object(seen, key[1], group=host_group)      # nobody is still using the old mapping; sizes agree
+        assert len(set(seen)) == 1, "every rank must hold the same samples (reduce buffers of %s doubles)" % seen
+        handle = batch.ipc_export()                # may move the buffer (IPC wants its own mapping): export before the run
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=host_group)
+        batch.ipc_open(handles, rank)
+        st["key"] = batch.reduce_buffer()
+
+
+def p2p_reduce_scatter(batch):
+    """After batch.run() on every rank: rows [rank*S/world, (rank+1)*S/world) of this rank's reduce buffer become the sums
+    over all ranks (lib.Batch.set_result_range must select that share).  One kernel, stream-ordered; the host does not wait."""
+    batch.reduce_peers()
