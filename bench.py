@@ -310,14 +310,14 @@ def run_b200_arm(args):
     t_group = time.perf_counter() - t_group
     assert gs_raw is not None, "the synthetic PL weights qualify for the grouped kernel"
     g_arrs = []
-    for a in (gs_raw.chrom, gs_raw.pos, gs_raw.gid, gs_raw.table, gs_raw.packed):
+    for a in (gs_raw.chrom, gs_raw.pos, gs_raw.gid, gs_raw.table, gs_raw.packed, gs_raw.run_gid, gs_raw.run_end):
         if a is None:
             g_arrs.append(None)
             continue
         t, v = pinned(a)
         keep.append(t)
         g_arrs.append(v)
-    gs = lib.GroupedSamples(h_off, g_arrs[0], g_arrs[1], g_arrs[2], g_arrs[3], gs_raw.order, packed=g_arrs[4])
+    gs = lib.GroupedSamples(h_off, g_arrs[0], g_arrs[1], g_arrs[2], g_arrs[3], gs_raw.order, packed=g_arrs[4], run_gid=g_arrs[5], run_end=g_arrs[6])
     gbatch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
     gbatch.set_group_chunk(args.group_chunk)
     gbatch.upload_grouped(gs)
@@ -488,7 +488,7 @@ def run_b200_arm(args):
 
         def up(bt):
             if use_grouped:
-                bt.upload_grouped(gs)                        # 6 bytes per marker
+                bt.upload_grouped(gs)                        # ~4.1 bytes per marker
             elif coded is not None:
                 bt.upload_indexed(h_off, h_chr, h_pos, h_idx, h_tab)      # 14 bytes per marker
             else:
@@ -618,7 +618,7 @@ def run_b200_arm(args):
                     "h2d_bytes_per_step": int(world * h2d_bytes),
                     "d2h_bytes_per_step": int(world * (sum(v.nbytes for v in out.values()) + 4 * S_loc)),
                     "inputs": "pinned host arrays in grouped order (snpm_group_markers, once at parse time: %.0f ms for the batch): "
-                              "chromosome id and position in one uint32, weight-triple id uint16 per marker (6 bytes) + the table of distinct triples "
+                              "chromosome id and position in one uint32 per marker, weight-triple ids run-length coded (uint16 id + uint32 end per run; 4.1 bytes per marker) + the table of distinct triples "
                               "(f64); two batches alternate in a software pipeline (H2D of step k+2 and D2H of step k overlap the kernels "
                               "of step k+1; filling the pipeline is inside the timed region); the D2H holds scores, counts, "
                               "likelihoods and the per-sample guard counts" % (1e3 * t_group),

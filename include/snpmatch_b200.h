@@ -154,6 +154,12 @@ int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *o
 int snpm_pack_markers(int64_t n, const uint8_t *chrom_u8, const int32_t *pos, uint32_t *out);
 int snpm_batch_upload_grouped_packed(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
                                      const uint16_t *gid, const double *table, int32_t n_table);
+/* the same with the weight-triple ids run-length coded: markers are ordered by id inside a sample, so run r covers markers
+ * [run_end[r-1], run_end[r]) (global marker indices, strictly ascending, the last one = offsets[n_samples]; a run never
+ * crosses a sample boundary unless both sides carry the same id, which is harmless) and carries run_gid[r].  About
+ * 4 + 6 / (markers per run) bytes per marker cross the PCIe bus (4.1 for PL samples of 50 k markers). */
+int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
+                                   const uint16_t *run_gid, const uint32_t *run_end, int64_t n_runs, const double *table, int32_t n_table);
 /* after snpm_batch_epilogue on a grouped batch: counts[s] = accessions of sample s whose fractional score part lies
  * within the rounding-error bound of an integer, i.e. whose int(score) depends on the reference's own summation order
  * (probability ~1e-7 per accession).  Re-score those samples with mode 0.  All zeros for position-order batches. */

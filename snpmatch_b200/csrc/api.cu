@@ -567,7 +567,8 @@ int snpm_group_markers(int64_t n_samples, const int64_t *offsets, const int32_t 
 }
 
 static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint8_t *chrom_u8, const int32_t *s_pos,
-                          const uint32_t *packed_cp, const uint16_t *gid, const double *table, int32_t n_table) {
+                          const uint32_t *packed_cp, const uint16_t *gid, const double *table, int32_t n_table,
+                          const uint16_t *run_gid = nullptr, const uint32_t *run_end = nullptr, int64_t n_runs = 0) {
     if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL batch");
     snpm_db *db = b->db;
     if (n_samples < 1 || !offsets || offsets[0] != 0) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: need samples and offsets starting at 0");
@@ -575,7 +576,13 @@ static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offse
         if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: offsets must be non-decreasing");
     const int64_t n = offsets[n_samples];
     if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: %lld markers exceed the 2^31 limit", (long long)n);
-    if (n > 0 && (!gid || (!packed_cp && (!chrom_u8 || !s_pos)))) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL marker arrays");
+    if (n > 0 && ((!gid && !run_gid) || (!packed_cp && (!chrom_u8 || !s_pos)))) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL marker arrays");
+    if (run_gid && n > 0) {
+        if (!run_end || n_runs < 1 || n_runs > n) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: need 1..n runs");
+        for (int64_t r = 0; r < n_runs; ++r)
+            if (run_end[r] <= (r ? run_end[r - 1] : 0u)) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: run ends must be strictly ascending (run %lld)", (long long)r);
+        if (int64_t(run_end[n_runs - 1]) != n) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: the last run must end at the last marker");
+    }
     if (!table || n_table < 1 || n_table > 65536) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: weight table must hold 1..65536 triples");
     std::vector<double> t4(size_t(n_table) * 4);
     for (int32_t t = 0; t < n_table; ++t) {
@@ -609,7 +616,17 @@ static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offse
     b->h_gtable.assign(t4.begin(), t4.end());
     SNPM_CUDA(cudaMemcpyAsync(b->d_gtable.p, b->h_gtable.data(), size_t(n_table) * 32, cudaMemcpyHostToDevice, st));
     if (n) {
-        SNPM_CUDA(cudaMemcpyAsync(b->d_gid.p, gid, size_t(n) * 2, cudaMemcpyHostToDevice, st));
+        if (run_gid) {
+            SNPM_TRY(b->d_runs.ensure(size_t(n_runs) * 4 + size_t(n_runs) * 2 + 16));
+            uint32_t *d_end = b->d_runs.as<uint32_t>();
+            uint16_t *d_rg = reinterpret_cast<uint16_t *>(d_end + n_runs);
+            SNPM_CUDA(cudaMemcpyAsync(d_end, run_end, size_t(n_runs) * 4, cudaMemcpyHostToDevice, st));
+            SNPM_CUDA(cudaMemcpyAsync(d_rg, run_gid, size_t(n_runs) * 2, cudaMemcpyHostToDevice, st));
+            k_expand_runs<<<int(ceil_div64(n, 256)), 256, 0, st>>>(d_end, d_rg, int32_t(n_runs), n, b->d_gid.as<uint16_t>());
+            SNPM_KERNEL_CHECK();
+        } else {
+            SNPM_CUDA(cudaMemcpyAsync(b->d_gid.p, gid, size_t(n) * 2, cudaMemcpyHostToDevice, st));
+        }
         if (packed_cp) {
             SNPM_TRY(b->d_wei_idx.ensure(size_t(n) * 4));      // staging of the packed words (the buffer is free in grouped mode)
             SNPM_CUDA(cudaMemcpyAsync(b->d_wei_idx.p, packed_cp, size_t(n) * 4, cudaMemcpyHostToDevice, st));
@@ -634,6 +651,11 @@ int snpm_batch_upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *o
 int snpm_batch_upload_grouped_packed(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *gid,
                                      const double *table, int32_t n_table) {
     return upload_grouped(b, n_samples, offsets, nullptr, nullptr, chrom_pos, gid, table, n_table);
+}
+
+int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *run_gid,
+                                   const uint32_t *run_end, int64_t n_runs, const double *table, int32_t n_table) {
+    return upload_grouped(b, n_samples, offsets, nullptr, nullptr, chrom_pos, nullptr, table, n_table, run_gid, run_end, n_runs);
 }
 
 int snpm_pack_markers(int64_t n, const uint8_t *chrom_u8, const int32_t *pos, uint32_t *out) {
@@ -685,7 +707,7 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
                       &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
                       &b->d_win_ident, &b->d_win_amb, &b->d_win_row_off, &b->d_row_acc, &b->d_row_score, &b->d_row_ninfo, &b->d_row_L, &b->d_row_ident, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
-                      &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard};
+                      &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard, &b->d_runs};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);

@@ -138,7 +138,7 @@ struct snpm_batch {
     bool grouped = false;
     int32_t n_gtable = 0;
     int32_t gchunk = 320;              // rows per segment of the grouped kernel (measured best on the 1135 x 10.7 M workload)
-    snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard;
+    snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard, d_runs;
     std::vector<double> h_gtable;
     int64_t red_pitch() const { return (grouped ? 3 : 2) * int64_t(db->n_acc) + 2; }   // doubles per sample row of d_red
     // state

@@ -455,6 +455,21 @@ __global__ void __launch_bounds__(256) k_expand_packed(const uint32_t *__restric
     }
 }
 
+// weight-triple ids travel run-length coded (markers are ordered by id inside a sample: ~70 markers per run): run r covers
+// markers [run_end[r-1], run_end[r]) and carries run_gid[r].  One thread per marker finds its run by binary search.
+__global__ void __launch_bounds__(256) k_expand_runs(const uint32_t *__restrict__ run_end, const uint16_t *__restrict__ run_gid, int32_t n_runs,
+                                                     int64_t n, uint16_t *__restrict__ gid) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = n_runs - 1;                   // first run whose end lies beyond marker i
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(run_end + mid) > uint32_t(i)) hi = mid;
+        else lo = mid + 1;
+    }
+    gid[i] = __ldg(run_gid + lo);
+}
+
 // ---- combine: totals of the segment partials of one sample ----------------------------------------------
 // red row layout in grouped mode [3*n_acc + 2]: F[n_acc] | ninfo[n_acc] | matched pairs | y>n violations | I[n_acc]
 // (the first 2*n_acc + 2 entries are laid out as in k_combine; k_grouped_finalize turns F into the score in place)

@@ -52,23 +52,33 @@ class GroupedSamples(object):
     offsets int64 [S+1]; chrom uint8 [n] (255 = not in the panel); pos int32 [n]; gid uint16 [n]; table f64 [T,3] in the
     column order of `wei`; order int64 [n] = index of each marker in the arrays it was built from."""
 
-    def __init__(self, offsets, chrom, pos, gid, table, order, packed=None):
+    def __init__(self, offsets, chrom, pos, gid, table, order, packed=None, run_gid=None, run_end=None):
         self.offsets, self.chrom, self.pos, self.gid, self.table, self.order = offsets, chrom, pos, gid, table, order
         self.n_samples = len(offsets) - 1
         self.packed = packed          # uint32 [n] = chromosome id << 27 | position when everything fits, else None
+        self.run_gid, self.run_end = run_gid, run_end     # the ids run-length coded (uint16 [R], uint32 [R] exclusive ends), or None
 
     def pack(self):
-        """Chromosome id and position of every marker in one word (6 instead of 7 bytes per marker cross PCIe); leaves
-        `packed` None when an id exceeds 30 or a position 2^27 - 1."""
-        out = np.empty(max(len(self.pos), 1), np.uint32)
-        rc = load().snpm_pack_markers(len(self.pos), ptr(self.chrom), ptr(self.pos), ptr(out))
-        self.packed = out[:len(self.pos)] if rc == SNPM_OK else None
+        """Chromosome id and position of every marker in one word (6 instead of 7 bytes per marker cross PCIe; leaves `packed`
+        None when an id exceeds 30 or a position 2^27 - 1), and the weight-triple ids run-length coded when that is shorter
+        (markers are ordered by id inside a sample: ~4.1 bytes per marker)."""
+        n = len(self.pos)
+        out = np.empty(max(n, 1), np.uint32)
+        rc = load().snpm_pack_markers(n, ptr(self.chrom), ptr(self.pos), ptr(out))
+        self.packed = out[:n] if rc == SNPM_OK else None
+        self.run_gid = self.run_end = None
+        if self.packed is not None and n > 0:
+            change = np.flatnonzero(self.gid[1:] != self.gid[:-1]) + 1
+            if 6 * (len(change) + 1) < 2 * n:
+                self.run_end = np.ascontiguousarray(np.concatenate([change, [n]]), dtype=np.uint32)
+                self.run_gid = np.ascontiguousarray(self.gid[np.concatenate([[0], change])], dtype=np.uint16)
         return self
 
     @property
     def h2d_bytes(self):
         marker_bytes = self.packed.nbytes if self.packed is not None else self.chrom.nbytes + self.pos.nbytes
-        return int(self.offsets.nbytes + marker_bytes + self.gid.nbytes + self.table.size // 3 * 32)
+        id_bytes = self.run_gid.nbytes + self.run_end.nbytes if self.run_gid is not None else self.gid.nbytes
+        return int(self.offsets.nbytes + marker_bytes + id_bytes + self.table.size // 3 * 32)
 
 
 def group_markers(offsets, s_chrom_id, s_pos, wei, table_cap=65536):
@@ -140,6 +150,7 @@ SIGNATURES = {
     "snpm_group_markers": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "snpm_batch_upload_grouped": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
     "snpm_pack_markers": (C.c_int, [_i64, _p, _p, _p]),
+    "snpm_batch_upload_grouped_runs": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i32]),
     "snpm_batch_upload_grouped_packed": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32]),
     "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
     "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
@@ -378,7 +389,10 @@ class Batch(object):
         self.n_samples = g.n_samples
         self.offsets = g.offsets
         self._keep = (g,)
-        if g.packed is not None:
+        if g.packed is not None and g.run_gid is not None:
+            check(load().snpm_batch_upload_grouped_runs(self._h, g.n_samples, ptr(g.offsets), ptr(g.packed), ptr(g.run_gid), ptr(g.run_end),
+                                                        len(g.run_gid), ptr(g.table), len(g.table)))
+        elif g.packed is not None:
             check(load().snpm_batch_upload_grouped_packed(self._h, g.n_samples, ptr(g.offsets), ptr(g.packed), ptr(g.gid),
                                                           ptr(g.table), len(g.table)))
         else:

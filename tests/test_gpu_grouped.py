@@ -364,3 +364,37 @@ def test_grouped_edge_cases(lib):
         assert np.all(r["matches"][3] == 0) and np.all(np.isnan(r["L"][0])) and np.all(np.isnan(r["L"][3]))
         b.close()
         db.close()
+
+
+def test_grouped_upload_forms_agree(lib):
+    """The three wire forms of a grouped batch (7, 6 and ~4 bytes per marker: separate chromosome/position, packed word,
+    packed word + run-length coded weight-triple ids) give identical results; malformed runs are refused."""
+    n_rows, n_acc = 60000, 257
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    samples = [synth.make_sample(pos, regions, synth.TAIR10_CHRS, n_acc, true_acc=5 + i, n_db=nd, n_extra=ne, seed=2300 + i)
+               for i, (nd, ne) in enumerate([(3000, 100), (0, 10), (1, 0), (777, 33)])]
+    offs, chrom, p, wei = _concat(samples)
+    g = lib.group_markers(offs, chrom, p, wei)
+    assert g.packed is not None and g.run_gid is not None and int(g.run_end[-1]) == len(p)
+    assert g.h2d_bytes < offs.nbytes + 6 * len(p) + len(g.table) * 32
+    b = lib.Batch(db, offs, chrom, p, wei)
+    res = []
+    for form in ("runs", "packed", "plain"):
+        h = lib.GroupedSamples(g.offsets, g.chrom, g.pos, g.gid, g.table, g.order,
+                               packed=None if form == "plain" else g.packed,
+                               run_gid=g.run_gid if form == "runs" else None, run_end=g.run_end if form == "runs" else None)
+        b.upload_grouped(h)
+        b.run(kernel_mode=lib.KERNEL_GROUPED)
+        b.epilogue()
+        res.append({k: v.copy() for k, v in b.fetch().items()})
+    for r in res[1:]:
+        for k in res[0]:
+            assert np.array_equal(r[k], res[0][k], equal_nan=True), k
+    bad_end = g.run_end.copy()
+    bad_end[-1] -= 1
+    with pytest.raises(lib.SnpmError):
+        b.upload_grouped(lib.GroupedSamples(g.offsets, g.chrom, g.pos, g.gid, g.table, g.order, packed=g.packed, run_gid=g.run_gid, run_end=bad_end))
+    b.close()
+    db.close()
