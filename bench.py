@@ -42,6 +42,7 @@ N_ROWS = 10_700_000
 N_ACC = 1135
 N_DB_MARKERS = 45_000
 N_EXTRA_MARKERS = 5_000
+E2E_DEPTH = 3            # batch objects rotating in the end-to-end arm
 METRIC = "snp_accession_comparisons_per_sec"
 UNIT = "comparisons/s"
 
@@ -318,6 +319,8 @@ def run_b200_arm(args):
         keep.append(t)
         g_arrs.append(v)
     gs = lib.GroupedSamples(h_off, g_arrs[0], g_arrs[1], g_arrs[2], g_arrs[3], gs_raw.order, packed=g_arrs[4], run_gid=g_arrs[5], run_end=g_arrs[6])
+    if os.environ.get("SNPM_BENCH_NO_RUNS"):           # experiment: ids as one uint16 per marker (6 bytes per marker) instead of runs
+        gs.run_gid = gs.run_end = None
     gbatch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
     gbatch.set_group_chunk(args.group_chunk)
     gbatch.upload_grouped(gs)
@@ -472,12 +475,17 @@ def run_b200_arm(args):
         hard.close()
         barrier()
         # ---- end-to-end arm: host buffers in, host buffers out -------------------------------------
-        # Two batch objects alternate: while one is scored, the next step's samples are copied from pinned host
-        # memory on the other's copy stream.  Every step uploads its inputs and reads its results back.
-        batch2 = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
-        batch2.set_group_chunk(args.group_chunk)
-        own_share(batch2)
-        pair = [gbatch, batch2]
+        # Every step uploads its inputs from pinned host memory (on the batch's own copy stream) and reads its results back.
+        # E2E_DEPTH batch objects rotate.  One batch's cycle is upload (0.36 ms at 53 GB/s) -> kernels (0.43) -> read-back (0.07) ->
+        # the host sees the results and uploads again; with two batches that cycle (1.1 ms with host latencies) bounds the step at
+        # 0.56 ms, with three the kernels do.
+        extra = []
+        for _ in range(E2E_DEPTH - 1):
+            bx = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
+            bx.set_group_chunk(args.group_chunk)
+            own_share(bx)
+            extra.append(bx)
+        pair = [gbatch] + extra
         rescored = [0]
 
         coded = None if use_grouped else lib.index_weights(h_wei)
@@ -486,7 +494,13 @@ def run_b200_arm(args):
             tab_t, h_tab = pinned(coded[1])
             keep.extend([idx_t, tab_t])
 
+        skip_part = os.environ.get("SNPM_E2E_SKIP", "")    # timing experiments: leave the upload or the read-back out of the steady state
+        primed = set()
+
         def up(bt):
+            if skip_part == "upload" and id(bt) in primed:
+                return
+            primed.add(id(bt))
             if use_grouped:
                 bt.upload_grouped(gs)                        # ~4.1 bytes per marker
             elif coded is not None:
@@ -494,26 +508,32 @@ def run_b200_arm(args):
             else:
                 bt.upload(h_off, h_chr, h_pos, h_wei)
 
-        # software pipeline over the two batches: while step k's results travel to the host and the host looks at them, step
-        # k+1's kernels are already queued and step k+2's samples are being copied in.  Every step still uploads its own
-        # inputs (pinned host arrays) and reads back its own results (pinned host arrays) inside the timed region.
-        out2_t = {k: torch.empty_like(v).pin_memory() for k, v in out_t.items()}
-        outs = [dict(out), {k: v.numpy() for k, v in out2_t.items()}]
+        # software pipeline over the rotating batches: while step k's results travel to the host and the host looks at them, the
+        # kernels of the next steps are already queued and the samples of step k+depth are being copied in.  Every step still
+        # uploads its own inputs (pinned host arrays) and reads back its own results (pinned host arrays) inside the timed region.
+        outs = [dict(out)]
+        for _ in range(E2E_DEPTH - 1):
+            ot = {k: torch.empty_like(v).pin_memory() for k, v in out_t.items()}
+            keep.append(ot)
+            outs.append({k: v.numpy() for k, v in ot.items()})
         for o in outs:
             gt_ = torch.zeros(S, dtype=torch.int32).pin_memory()
             keep.append(gt_)
             o["guard"] = gt_.numpy()
 
         def launch(k):
-            b_ = pair[k % 2]
+            b_ = pair[k % E2E_DEPTH]
             run_batch(b_, kernel_mode=lib.KERNEL_GROUPED if use_grouped else lib.KERNEL_FP64)
             if world > 1:
                 reduce_totals(b_)
             b_.epilogue()
-            b_.fetch_async(outs[k % 2])                      # D2H of step k, queued behind its kernels
+            if skip_part == "fetch":
+                b_.fetch_async({"m": outs[k % E2E_DEPTH]["m"], "guard": outs[k % E2E_DEPTH]["guard"]})      # the counts only (a few hundred bytes)
+            else:
+                b_.fetch_async(outs[k % E2E_DEPTH])                  # D2H of step k, queued behind its kernels
 
         def finish(k):
-            b_ = pair[k % 2]
+            b_ = pair[k % E2E_DEPTH]
             r = b_.fetch_wait()                              # results of step k (this rank's share) are on the host
             flagged = np.flatnonzero(r["guard"])             # int(score) needs the reference's summation order (~1e-4 per sample)
             if world > 1:
@@ -550,19 +570,29 @@ def run_b200_arm(args):
             for k, sidx in zip(*np.nonzero(mask.numpy())):
                 rescore(int(sidx), r if int(k) == n - 1 else None)
 
+        host_s = {"upload": 0.0, "launch": 0.0, "wait": 0.0}
+
+        def timed_call(key, fn, *a):
+            t_ = time.perf_counter()
+            r_ = fn(*a)
+            host_s[key] += time.perf_counter() - t_
+            return r_
+
         def run_pipeline(n):
             """n complete steps, each from the upload of its samples to its results on the host."""
-            up(pair[0])
-            if n > 1:
-                up(pair[1])
-            launch(0)
+            for key in host_s:
+                host_s[key] = 0.0
+            for j in range(min(E2E_DEPTH, n)):
+                timed_call("upload", up, pair[j])            # samples of steps 0 .. depth-1
+            for j in range(min(E2E_DEPTH - 1, n)):
+                timed_call("launch", launch, j)              # depth-1 steps queued on the GPU ahead of the host
             r = None
             for k in range(n):
-                if k + 1 < n:
-                    launch(k + 1)                            # queue step k+1 (its samples were uploaded one step ago)
-                r = finish(k)
-                if k + 2 < n:
-                    up(pair[k % 2])                          # H2D of step k+2 into the buffers step k has released
+                if k + E2E_DEPTH - 1 < n:
+                    timed_call("launch", launch, k + E2E_DEPTH - 1)   # its samples were uploaded when step k-1 was finished
+                r = timed_call("wait", finish, k)
+                if k + E2E_DEPTH < n:
+                    timed_call("upload", up, pair[k % E2E_DEPTH])     # H2D of step k+depth into the buffers step k has released
             if world > 1:
                 resolve_flagged(n, r)
             return r
@@ -575,7 +605,8 @@ def run_b200_arm(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         for key in out:
-            out[key][...] = last[key]
+            if key in last:
+                out[key][...] = last[key]
         if use_grouped:
             h2d_bytes = gs.h2d_bytes
         else:
@@ -615,12 +646,13 @@ def run_b200_arm(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, S),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "host_ms_per_step": {k: 1e3 * v / args.steps for k, v in host_s.items()},
                     "h2d_bytes_per_step": int(world * h2d_bytes),
                     "d2h_bytes_per_step": int(world * (sum(v.nbytes for v in out.values()) + 4 * S_loc)),
                     "inputs": "pinned host arrays in grouped order (snpm_group_markers, once at parse time: %.0f ms for the batch): "
                               "chromosome id and position in one uint32 per marker, weight-triple ids run-length coded (uint16 id + uint32 end per run; 4.1 bytes per marker) + the table of distinct triples "
-                              "(f64); two batches alternate in a software pipeline (H2D of step k+2 and D2H of step k overlap the kernels "
-                              "of step k+1; filling the pipeline is inside the timed region); the D2H holds scores, counts, "
+                              "(f64); three batches rotate in a software pipeline (H2D of step k+3 and D2H of step k overlap the kernels "
+                              "of steps k+1 and k+2; filling the pipeline is inside the timed region); the D2H holds scores, counts, "
                               "likelihoods and the per-sample guard counts" % (1e3 * t_group),
                     "samples_rescored_in_reference_order": int(rescored[0])},
             "gpu_launches": int(total_launches * args.steps),
@@ -697,7 +729,8 @@ def run_b200_arm(args):
                              "peak_source": "2 x measured dense bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 dense is nominally 2x bf16: 4500 vs 2250)"}}
         print(json.dumps(line))
     batch.close()
-    batch2.close()
+    for bx in extra:
+        bx.close()
     gbatch.close()
     g.close()
     if world > 1:

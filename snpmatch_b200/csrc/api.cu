@@ -579,9 +579,7 @@ static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offse
     if (n > 0 && ((!gid && !run_gid) || (!packed_cp && (!chrom_u8 || !s_pos)))) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: NULL marker arrays");
     if (run_gid && n > 0) {
         if (!run_end || n_runs < 1 || n_runs > n) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: need 1..n runs");
-        for (int64_t r = 0; r < n_runs; ++r)
-            if (run_end[r] <= (r ? run_end[r - 1] : 0u)) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: run ends must be strictly ascending (run %lld)", (long long)r);
-        if (int64_t(run_end[n_runs - 1]) != n) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: the last run must end at the last marker");
+        if (int64_t(run_end[n_runs - 1]) != n || run_end[0] == 0) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped_runs: the runs must cover markers 0..n");
     }
     if (!table || n_table < 1 || n_table > 65536) return fail(SNPM_E_ARG, "snpm_batch_upload_grouped: weight table must hold 1..65536 triples");
     std::vector<double> t4(size_t(n_table) * 4);
@@ -598,6 +596,7 @@ static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offse
     b->S = n_samples;
     b->n = n;
     b->grouped = true;
+    b->pending_expand = 0;
     b->n_gtable = n_table;
     b->h_off.assign(offsets, offsets + n_samples + 1);
     int64_t nseg = 0;
@@ -617,26 +616,29 @@ static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offse
     SNPM_CUDA(cudaMemcpyAsync(b->d_gtable.p, b->h_gtable.data(), size_t(n_table) * 32, cudaMemcpyHostToDevice, st));
     if (n) {
         if (run_gid) {
-            SNPM_TRY(b->d_runs.ensure(size_t(n_runs) * 4 + size_t(n_runs) * 2 + 16));
+            const size_t bad_off = (size_t(n_runs) * 6 + 15) & ~size_t(15);
+            SNPM_TRY(b->d_runs.ensure(bad_off + 16));
             uint32_t *d_end = b->d_runs.as<uint32_t>();
             uint16_t *d_rg = reinterpret_cast<uint16_t *>(d_end + n_runs);
+            b->d_runs_bad = reinterpret_cast<int *>(static_cast<char *>(b->d_runs.p) + bad_off);
+            SNPM_CUDA(cudaMemsetAsync(b->d_runs_bad, 0, sizeof(int), st));
             SNPM_CUDA(cudaMemcpyAsync(d_end, run_end, size_t(n_runs) * 4, cudaMemcpyHostToDevice, st));
             SNPM_CUDA(cudaMemcpyAsync(d_rg, run_gid, size_t(n_runs) * 2, cudaMemcpyHostToDevice, st));
-            k_expand_runs<<<int(ceil_div64(n, 256)), 256, 0, st>>>(d_end, d_rg, int32_t(n_runs), n, b->d_gid.as<uint16_t>());
-            SNPM_KERNEL_CHECK();
+            b->pending_expand |= 1;
+            b->pending_runs = n_runs;
         } else {
+            b->d_runs_bad = nullptr;
             SNPM_CUDA(cudaMemcpyAsync(b->d_gid.p, gid, size_t(n) * 2, cudaMemcpyHostToDevice, st));
         }
         if (packed_cp) {
             SNPM_TRY(b->d_wei_idx.ensure(size_t(n) * 4));      // staging of the packed words (the buffer is free in grouped mode)
             SNPM_CUDA(cudaMemcpyAsync(b->d_wei_idx.p, packed_cp, size_t(n) * 4, cudaMemcpyHostToDevice, st));
-            k_expand_packed<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_wei_idx.as<uint32_t>(), n, b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>());
+            b->pending_expand |= 2;
         } else {
             SNPM_CUDA(cudaMemcpyAsync(b->d_chrom8.p, chrom_u8, size_t(n), cudaMemcpyHostToDevice, st));
             SNPM_CUDA(cudaMemcpyAsync(b->d_pos.p, s_pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
-            k_expand_chrom<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_chrom8.as<uint8_t>(), n, b->d_chrom.as<int32_t>());
+            b->pending_expand |= 4;
         }
-        SNPM_KERNEL_CHECK();
     }
     SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
     b->ran = b->ran_windows = b->epilogue_done = false;
@@ -753,6 +755,19 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
     SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_uploaded, 0));       // the samples are on the device
     SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
+    if (b->grouped && b->pending_expand) {                        // compact upload forms -> the arrays the join reads (once per upload)
+        if (b->pending_expand & 1) {
+            const uint32_t *d_end = b->d_runs.as<uint32_t>();
+            k_expand_runs<<<int(ceil_div64(b->pending_runs * 32, 256)), 256, 0, st>>>(d_end, reinterpret_cast<const uint16_t *>(d_end + b->pending_runs),
+                                                                                 int32_t(b->pending_runs), n, b->d_gid.as<uint16_t>(), b->d_runs_bad);
+        }
+        if (b->pending_expand & 2) k_expand_packed<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_wei_idx.as<uint32_t>(), n, b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>());
+        if (b->pending_expand & 4) k_expand_chrom<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_chrom8.as<uint8_t>(), n, b->d_chrom.as<int32_t>());
+        SNPM_KERNEL_CHECK();
+        b->pending_expand = 0;
+    }
+    // run ends that do not ascend were counted by k_expand_runs: reported at wait / fetch (status slot 4, next to ids outside the table)
+    if (b->grouped && b->d_runs_bad) SNPM_CUDA(cudaMemcpyAsync(b->d_status.as<int>() + 4, b->d_runs_bad, sizeof(int), cudaMemcpyDeviceToDevice, st));
     if (!b->peer_red.empty() && b->ipc_step > 0 && b->d_red.p == b->ipc_ptr) {      // the peers have pulled their rows of the last step
         k_wait_peers_done<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t *>(static_cast<const char *>(b->d_red.p) + b->ipc_flags_off),
                                             int32_t(b->peer_red.size()), b->ipc_step, b->d_status.as<int>());
@@ -993,7 +1008,7 @@ int snpm_batch_wait(snpm_batch *b, float *ms_device) {
     if (b->h_status[3] > 0)
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
     if (b->h_status[4] > 0)
-        return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table", b->h_status[4]);
+        return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table (or run-length coded ids do not ascend)", b->h_status[4]);
     if (b->h_status[5] > 0)
         return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within two seconds (every rank must run and reduce the same batches in the same order)");
     return SNPM_OK;
@@ -1208,7 +1223,7 @@ int snpm_batch_fetch_wait(snpm_batch *b) {
     if (b->h_status[3] > 0)
         return fail(SNPM_E_ARG, "kernel mode 1 needs one-hot weights (called genotypes); %d matched markers are not", b->h_status[3]);
     if (b->h_status[4] > 0)
-        return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table", b->h_status[4]);
+        return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table (or run-length coded ids do not ascend)", b->h_status[4]);
     if (b->h_status[5] > 0)
         return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within two seconds (every rank must run and reduce the same batches in the same order)");
     long long viol = 0;

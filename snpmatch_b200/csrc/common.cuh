@@ -140,6 +140,11 @@ struct snpm_batch {
     int32_t gchunk = 320;              // rows per segment of the grouped kernel (measured best on the 1135 x 10.7 M workload)
     snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard, d_runs;
     std::vector<double> h_gtable;
+    // expansion of the compact upload forms, deferred to the head of the next run ON THE COMPUTE STREAM: a kernel on the copy
+    // stream next to the scoring kernel cost 0.15 ms per step end to end (bit 0: run-length ids, 1: packed words, 2: byte chromosomes)
+    int pending_expand = 0;
+    int64_t pending_runs = 0;
+    int *d_runs_bad = nullptr;         // inside d_runs: run-length coded ids whose ends do not ascend (last grouped_runs upload), or null
     int64_t red_pitch() const { return (grouped ? 3 : 2) * int64_t(db->n_acc) + 2; }   // doubles per sample row of d_red
     // state
     bool ran = false, ran_windows = false, epilogue_done = false;

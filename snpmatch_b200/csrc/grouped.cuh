@@ -456,18 +456,20 @@ __global__ void __launch_bounds__(256) k_expand_packed(const uint32_t *__restric
 }
 
 // weight-triple ids travel run-length coded (markers are ordered by id inside a sample: ~70 markers per run): run r covers
-// markers [run_end[r-1], run_end[r]) and carries run_gid[r].  One thread per marker finds its run by binary search.
+// markers [run_end[r-1], run_end[r]) and carries run_gid[r].  One warp per run, lanes stride over its markers (coalesced
+// 2-byte stores).  Ends that do not ascend or leave [0, n] are counted in status_bad (reported by the upload).
 __global__ void __launch_bounds__(256) k_expand_runs(const uint32_t *__restrict__ run_end, const uint16_t *__restrict__ run_gid, int32_t n_runs,
-                                                     int64_t n, uint16_t *__restrict__ gid) {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int lo = 0, hi = n_runs - 1;                   // first run whose end lies beyond marker i
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(run_end + mid) > uint32_t(i)) hi = mid;
-        else lo = mid + 1;
+                                                     int64_t n, uint16_t *__restrict__ gid, int *__restrict__ status_bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_runs) return;
+    const int64_t begin = r ? int64_t(__ldg(run_end + r - 1)) : 0, end = int64_t(__ldg(run_end + r));
+    if (end <= begin || end > n) {
+        if (lane == 0) atomicAdd(status_bad, 1);
+        return;
     }
-    gid[i] = __ldg(run_gid + lo);
+    const uint16_t g = __ldg(run_gid + r);
+    for (int64_t i = begin + lane; i < end; i += 32) gid[i] = g;
 }
 
 // ---- combine: totals of the segment partials of one sample ----------------------------------------------

@@ -396,5 +396,13 @@ def test_grouped_upload_forms_agree(lib):
     bad_end[-1] -= 1
     with pytest.raises(lib.SnpmError):
         b.upload_grouped(lib.GroupedSamples(g.offsets, g.chrom, g.pos, g.gid, g.table, g.order, packed=g.packed, run_gid=g.run_gid, run_end=bad_end))
+    assert len(g.run_end) > 3
+    bad_end = g.run_end.copy()
+    bad_end[2] = bad_end[1]                    # an interior run that does not ascend: counted on the device, reported at fetch
+    b.upload_grouped(lib.GroupedSamples(g.offsets, g.chrom, g.pos, g.gid, g.table, g.order, packed=g.packed, run_gid=g.run_gid, run_end=bad_end))
+    b.run(kernel_mode=lib.KERNEL_GROUPED)
+    b.epilogue()
+    with pytest.raises(lib.SnpmError):
+        b.fetch()
     b.close()
     db.close()
