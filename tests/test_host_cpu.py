@@ -180,3 +180,64 @@ def test_group_markers_host_preparation(built_lib):
     assert lib.group_markers(offs, chrom, pos, bad) is None
     assert lib.group_markers(offs, chrom, pos, rng.random((n0 + n1, 3)), table_cap=100) is None
     assert lib.group_markers(offs, np.full(n0 + n1, 300, np.int32), pos, wei) is None
+
+
+def test_label_factorize_and_chromosome_names():
+    """core/labels.py: per-marker strings reduced to codes + distinct values (run detection and the hash path) reproduce the
+    per-element operations of the reference (parsers.py:161-163, genomes.py:75)."""
+    from snpmatch_b200.core import genomes, labels, snp_genotype
+    rng = np.random.default_rng(4)
+    sorted_chrs = np.char.add("Chr", np.sort(rng.integers(1, 6, 5000)).astype(str))
+    for arr in (sorted_chrs, sorted_chrs[rng.permutation(5000)], np.array(["chrC", "ChrM", "chrC", "1", "CHR1"]),
+                np.array([b"2", b"2", b"10"]), np.array(["x"]), np.array([], dtype="U4")):
+        codes, uniq = labels.factorize(arr)
+        as_text = np.array([a.decode() if isinstance(a, bytes) else str(a) for a in arr], dtype="U8") if len(arr) else arr.astype("U")
+        assert np.array_equal(uniq[codes] if len(arr) else uniq[:0], as_text)
+        if len(arr):
+            _, first = np.unique(as_text, return_index=True)
+            assert uniq.tolist() == as_text[np.sort(first)].tolist()          # first-appearance order
+        want = np.array([re.sub("chr", "", s, flags=re.IGNORECASE) for s in as_text], dtype="U8")
+        assert np.array_equal(snp_genotype.normalize_chr_names(arr), want)
+        assert np.array_equal(orc.normalize_chr_names(as_text), want)
+        assert np.array_equal(genomes.genome_style_ids(arr), np.array([s.lower().replace("chr", "") for s in as_text], dtype="U8"))
+
+
+def test_filter_chr_names_and_multi_sample_vcf(tmp_path):
+    from snpmatch_b200.core import parsers
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(np.array(["Chr2", "Chr2", "chr1", "1", "ChrC"]), np.arange(5), np.repeat("0/0", 5), np.ones((5, 3)), "NA")
+    inp.filter_chr_names()
+    assert inp.g_chrs.tolist() == ["2", "2", "1", "1", "C"] and inp.g_chrs_ids.tolist() == ["2", "1", "C"]
+    vcf = tmp_path / "pop.vcf"
+    vcf.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC\n"
+                   "1\t100\t.\tA\tT\t9\tPASS\t.\tGT:DP\t0/0:3\t0|1:2\t./.:0\n"
+                   "1\t250\t.\tG\tC\t9\tPASS\t.\tDP:GT\t4:1/1\t1:.\t2:1|0\n"
+                   "Chr2\t7\t.\tG\tC\t9\tPASS\t.\tGT\t1/1\t0/0\n")
+    v = parsers.import_vcf_file(str(vcf), samples_to_load=None)
+    assert v["samples"].tolist() == ["A", "B", "C"] and v["chr"].tolist() == ["1", "1", "Chr2"] and v["pos"].tolist() == [100, 250, 7]
+    assert v["gt"].tolist() == [["0/0", "0/1", "./."], ["1/1", "./.", "1/0"], ["1/1", "0/0", "./."]]    # phasing dropped, short rows padded
+    assert parsers.parseGT(v["gt"].ravel()).reshape(3, 3).tolist() == [[0, 2, -1], [1, -1, 2], [1, 0, -1]]
+    assert np.array_equal(parsers.parseGT(v["gt"].ravel()), orc.parse_gt(v["gt"].ravel()))
+
+
+def test_grouped_samples_run_length_ids(built_lib):
+    """GroupedSamples.pack (host code of the library + NumPy): packed chromosome/position words and the run-length form of the ids."""
+    lib = built_lib
+    rng = np.random.default_rng(8)
+    n = [3000, 0, 1, 500]
+    offs = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    chrom = rng.integers(-1, 5, size=offs[-1]).astype(np.int32)
+    pos = rng.integers(1, 30_000_000, size=offs[-1]).astype(np.int32)
+    levels = np.exp(-np.arange(0, 40, 3) / 10.0)
+    many = lib.group_markers(offs, chrom, pos, levels[rng.integers(0, len(levels), size=(offs[-1], 3))])
+    assert many.packed is not None and many.run_gid is None               # ~2000 triples for 3500 markers: runs would be longer than the ids
+    wei = levels[rng.integers(0, 4, size=(offs[-1], 3))]
+    g = lib.group_markers(offs, chrom, pos, wei)
+    assert g.packed is not None and g.run_gid is not None
+    gid = np.repeat(g.run_gid, np.diff(np.concatenate([[0], g.run_end.astype(np.int64)])))
+    assert np.array_equal(gid, g.gid) and int(g.run_end[-1]) == offs[-1] and np.all(np.diff(g.run_end.astype(np.int64)) > 0)
+    assert np.array_equal(g.packed >> 27, np.where(g.chrom == 255, 31, g.chrom)) and np.array_equal(g.packed & 0x7FFFFFF, g.pos)
+    assert np.array_equal(g.table[g.gid], wei[g.order])                     # the table reproduces every marker's weights bit for bit
+    for s in range(len(n)):                                                 # inside a sample the ids ascend (that is what makes runs long)
+        assert np.all(np.diff(g.gid[offs[s]:offs[s + 1]].astype(int)) >= 0)
+    assert g.h2d_bytes < offs.nbytes + 6 * offs[-1] + len(g.table) * 32
