@@ -81,68 +81,68 @@ def genotype_cross(args):
 def get_options(description, version_message):
     p = argparse.ArgumentParser(description=description)
     p.add_argument('-V', '--version', action='version', version=version_message)
-    sub = p.add_subparsers(title='subcommands', description='Choose a command to run', help='Following commands are supported')
+    sub = p.add_subparsers(title='commands', description='one of', help='what each does')
     db_help = "Path to the SNP database: the reference's row-chunked hdf5 file (needs h5py) or a packed .npz written by Genotype.save_packed"
-    inbred = sub.add_parser('inbred', help="SNPmatch on the inbred samples")
-    inbred.add_argument("-i", "--input_file", dest="inFile", help="VCF/BED file for the variants in the sample")
+    inbred = sub.add_parser('inbred', help="identify the accession an inbred sample comes from")
+    inbred.add_argument("-i", "--input_file", dest="inFile", help="sample variants: VCF (GT, optional PL), BED (chr, pos, GT) or a parser .npz")
     inbred.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
     inbred.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility; one resident copy serves both)")
-    inbred.add_argument("--refine", action="store_true", dest="refine", default=False, help="Refine scores for indistinguishable lines")
-    inbred.add_argument("--skip_db_hets", action="store_true", dest="skip_db_hets", default=False, help="Replace heterozygous calls in DB with nan during the analysis.")
-    inbred.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
-    inbred.add_argument("-o", "--output", dest="outFile", default="identify_inbred", help="Output file with the probability scores")
+    inbred.add_argument("--refine", action="store_true", dest="refine", default=False, help="re-score the accessions that cannot be told apart on the SNPs that segregate among them")
+    inbred.add_argument("--skip_db_hets", action="store_true", dest="skip_db_hets", default=False, help="treat heterozygous database calls as missing")
+    inbred.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
+    inbred.add_argument("-o", "--output", dest="outFile", default="identify_inbred", help="output prefix (<prefix>.scores.txt, <prefix>.matches.json)")
     inbred.set_defaults(func=snpmatch_inbred)
 
-    cross = sub.add_parser('cross', help="SNPmatch on the crosses (F2s and F3s) of A. thaliana")
-    cross.add_argument("-i", "--input_file", dest="inFile", help="VCF/BED file for the variants in the sample")
+    cross = sub.add_parser('cross', help="identify the parents of a cross (F2, F3): window scores and simulated F1s")
+    cross.add_argument("-i", "--input_file", dest="inFile", help="sample variants: VCF (GT, optional PL), BED (chr, pos, GT) or a parser .npz")
     cross.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
     cross.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility)")
-    cross.add_argument("-b", "--binLength", dest="binLen", help="Length of bins to calculate the likelihoods", default=300000, type=int)
-    cross.add_argument("--genome", dest="genome", default="athaliana_tair10", help="Path to Reference JSON file, if you are working with non-thaliana tair10 assembly")
-    cross.add_argument("--skip_db_hets", action="store_true", dest="skip_db_hets", default=False, help="Replace heterozygous calls in DB with nan during the analysis.")
-    cross.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
-    cross.add_argument("-o", "--output", dest="outFile", default="identify_cross", help="Output files with the probability scores and scores along windows")
+    cross.add_argument("-b", "--binLength", dest="binLen", help="window length in bp", default=300000, type=int)
+    cross.add_argument("--genome", dest="genome", default="athaliana_tair10", help="bundled genome id or path to a genome JSON (chromosome names and lengths)")
+    cross.add_argument("--skip_db_hets", action="store_true", dest="skip_db_hets", default=False, help="treat heterozygous database calls as missing")
+    cross.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
+    cross.add_argument("-o", "--output", dest="outFile", default="identify_cross", help="output prefix (<prefix>.scores.txt, <prefix>.windowscore.txt, <prefix>.scores.txt.matches.json)")
     cross.set_defaults(func=snpmatch_cross)
 
-    parser = sub.add_parser('parser', help="parse the input file")
-    parser.add_argument("-i", "--input_file", dest="inFile", help="VCF/BED file for the variants in the sample")
-    parser.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
-    parser.add_argument("-o", "--output", dest="outFile", help="output + .npz file is generater required for SNPmatch")
+    parser = sub.add_parser('parser', help="parse a VCF/BED file into the .npz the other commands load")
+    parser.add_argument("-i", "--input_file", dest="inFile", help="sample variants: VCF (GT, optional PL), BED (chr, pos, GT) or a parser .npz")
+    parser.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
+    parser.add_argument("-o", "--output", dest="outFile", help="prefix of the parser dump (<prefix>.npz)")
     parser.set_defaults(func=snpmatch_parser)
 
-    gc = sub.add_parser('genotype_cross', help="Genotype the crosses by windows given parents")
-    gc.add_argument("-i", "--input_file", dest="inFile", help="VCF file for the variants in the sample")
+    gc = sub.add_parser('genotype_cross', help="call parent 1 / het / parent 2 per window for every sample of a multi-sample VCF")
+    gc.add_argument("-i", "--input_file", dest="inFile", help="multi-sample VCF of the cross")
     gc.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
     gc.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility)")
-    gc.add_argument("-p", "--parents", dest="parents", help="Parents for the cross, parent1 x parent2")
+    gc.add_argument("-p", "--parents", dest="parents", help="the two parents as database accession ids, e.g. 6091x6191 (or the file of parent 1 with -q)")
     gc.add_argument("-q", "--father", dest="father", help="VCF/BED file of parent 2 when the parents are given as files (then -p is the file of parent 1)")
-    gc.add_argument("-b", "--binLength", dest="binLen", help="bin length", type=int, default=200000)
+    gc.add_argument("-b", "--binLength", dest="binLen", help="window length in bp", type=int, default=200000)
     gc.add_argument("--good_samples", dest="good_samples", help="accepted for compatibility (unused by the reference's window genotyper)", default=None)
-    gc.add_argument("--lr_thres", dest="lr_thres", default=1.5, type=float, help="Likelihood ratio threshold for genotype calling.")
+    gc.add_argument("--lr_thres", dest="lr_thres", default=1.5, type=float, help="second-best likelihood ratio a homozygous call needs")
     gc.add_argument("--hmm", dest="hmm", action="store_true", help="HMM Viterbi genotyper of the reference: not part of this package")
-    gc.add_argument("--genome", dest="genome", default="athaliana_tair10", help="Path to Reference JSON file, if you are working with non-thaliana tair10 assembly")
-    gc.add_argument("-o", "--output", dest="outFile", default="genotype_cross", help="output file")
-    gc.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    gc.add_argument("--genome", dest="genome", default="athaliana_tair10", help="bundled genome id or path to a genome JSON (chromosome names and lengths)")
+    gc.add_argument("-o", "--output", dest="outFile", default="genotype_cross", help="output CSV (R/qtl layout)")
+    gc.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
     gc.set_defaults(func=genotype_cross)
 
-    pair = sub.add_parser('pairsnp', help="pairwise comparison of two snp files")
-    pair.add_argument("-i", "--input_file_1", dest="inFile_1", help="VCF/BED file for the variants in the sample one")
-    pair.add_argument("-j", "--input_file_2", dest="inFile_2", help="VCF/BED file for the variants in the sample two")
+    pair = sub.add_parser('pairsnp', help="agreement of the genotype calls two samples share")
+    pair.add_argument("-i", "--input_file_1", dest="inFile_1", help="first sample (VCF/BED/npz)")
+    pair.add_argument("-j", "--input_file_2", dest="inFile_2", help="second sample (VCF/BED/npz)")
     pair.add_argument("-d", "--hdf5_file", dest="hdf5File", default=None, help=db_help)
-    pair.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
-    pair.add_argument("-o", "--output", dest="outFile", default="pairsnp", help="output json file")
+    pair.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
+    pair.add_argument("-o", "--output", dest="outFile", default="pairsnp", help="output prefix (<prefix>.matches.json)")
     pair.set_defaults(func=snpmatch_paircomparions)
 
-    sim = sub.add_parser('simulate', help="Given SNP database, check the genotyping efficiency randomly selecting 'n' number of SNPs")
+    sim = sub.add_parser('simulate', help="draw a synthetic sample (or F1) from the database to test the genotyper")
     sim.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)
     sim.add_argument("-e", "--hdf5_acc_file", default=None, dest="hdf5accFile", help="Column-chunked hdf5 file of the reference (accepted for compatibility)")
-    sim.add_argument("-a", "--ecotype_id", dest="AccID", help="Ecotype ID you want draw the SNPs")
-    sim.add_argument("-n", "--number_of_snps", dest="numSNPs", help="number of SNPs to draw in random to genotype the sample", type=int)
-    sim.add_argument("-p", "--error_rate", dest="err_rate", help="error rate while matching the SNPs, error rate of 0 gives perfect match to the accession", default=0.001, type=float)
-    sim.add_argument("--f1", action="store_true", dest="simF1", default=False, help="Simulate SNPs for an F1, give parents as 1061x1062 in argument '-a'")
+    sim.add_argument("-a", "--ecotype_id", dest="AccID", help="accession id to draw from; two ids as AxB with --f1")
+    sim.add_argument("-n", "--number_of_snps", dest="numSNPs", help="markers to draw", type=int)
+    sim.add_argument("-p", "--error_rate", dest="err_rate", help="fraction of the drawn calls replaced by random ones", default=0.001, type=float)
+    sim.add_argument("--f1", action="store_true", dest="simF1", default=False, help="simulate the F1 of the two accessions given with -a")
     sim.add_argument("--het_frac", default=1, type=float, dest="rm_het", help="For simulated F1s: fraction of segregating sites kept heterozygous; the rest become homozygous ref or alt with equal probability")
-    sim.add_argument("-o", "--output", dest="outFile", help="Output file with scores")
-    sim.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="Show verbose debugging output")
+    sim.add_argument("-o", "--output", dest="outFile", help="BED file to write")
+    sim.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
     sim.set_defaults(func=simulate_snps)
     return p
 

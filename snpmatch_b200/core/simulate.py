@@ -44,15 +44,15 @@ def simulateSNPs(g, AccID, numSNPs, outFile=None, err_rate=0.001):
     assert type(AccID) is str, "provide Accession ID as a string"
     assert AccID in g.accessions, "accession is not present in the matrix!"
     AccToCheck = np.where(g.accessions == AccID)[0][0]
-    log.info("loading input files")
+    log.info("reading the column of accession %s from the resident panel", AccID)
     acc_snp = g.g_acc.snps[:, AccToCheck]
     informative_snps = np.where(acc_snp >= 0)[0]            # removing NAs for the accession
-    log.info("sampling %s positions" % numSNPs)
+    log.info("drawing %s of %s called positions", numSNPs, informative_snps.shape[0])
     sampleSNPs = np.sort(np.random.choice(np.arange(informative_snps.shape[0]), numSNPs, replace=False))
     rows = informative_snps[sampleSNPs]
     snp = acc_snp[rows].astype(np.int8)
-    log.info("adding in error rate: %s" % err_rate)
     num_to_change = int(err_rate * numSNPs)
+    log.info("replacing %s calls by random ones (error rate %s)", num_to_change, err_rate)
     new_calls = np.random.choice(3, num_to_change)          # drawn first: simulate.py:26 evaluates its right-hand side first
     change = np.sort(np.random.choice(np.arange(numSNPs), num_to_change, replace=False))
     snp[change] = new_calls
@@ -62,17 +62,17 @@ def simulateSNPs(g, AccID, numSNPs, outFile=None, err_rate=0.001):
 def simulateSNPs_F1(g, parents, numSNPs, outFile, err_rate, rm_hets=1):
     indP1 = np.where(g.accessions == parents.split("x")[0])[0][0]
     indP2 = np.where(g.accessions == parents.split("x")[1])[0][0]
-    log.info("loading files!")
+    log.info("reading the parents' columns from the resident panel")
     cols = g.g_acc.snps[:, [indP1, indP2]]
     snpsP1, snpsP2 = cols[:, 0], cols[:, 1]
     common_ix = np.where((snpsP1 >= 0) & (snpsP2 >= 0) & (snpsP1 < 2) & (snpsP2 < 2))[0]
     common_snps = np.where(snpsP1[common_ix] != snpsP2[common_ix], 2, snpsP1[common_ix]).astype("int8")
-    log.info("sampling %s positions" % numSNPs)
+    log.info("drawing %s of %s positions called homozygous in both parents", numSNPs, common_ix.shape[0])
     sampleSNPs = np.sort(np.random.choice(np.arange(common_ix.shape[0]), numSNPs, replace=False))
     rows = common_ix[sampleSNPs]
     snp = common_snps[sampleSNPs].astype(int)
-    log.info("adding in error rate: %s" % err_rate)
     num_to_change = int(err_rate * numSNPs)
+    log.info("replacing %s homozygous calls by random ones (error rate %s)", num_to_change, err_rate)
     new_calls = np.random.choice(2, num_to_change)          # simulate.py:52: right-hand side first
     change = np.sort(np.random.choice(np.where(snp != 2)[0], num_to_change, replace=False))
     snp[change] = new_calls

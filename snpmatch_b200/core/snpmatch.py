@@ -105,13 +105,11 @@ class GenotyperOutput(object):
     """Result table of a run (snpmatch.py:91-168)."""
 
     def __init__(self, AccList, ScoreList, NumInfoSites, overlap, NumMatSNPs, DPmean):
-        self.accs = np.array(AccList, dtype="str")
-        self.scores = np.array(ScoreList, dtype="int")        # truncation toward zero (snpmatch.py:96)
-        self.ninfo = np.array(NumInfoSites, dtype="int")
-        self.overlap = overlap
-        self.num_snps = NumMatSNPs
-        self.dp = DPmean
         self._fused = None
+        self.overlap, self.num_snps, self.dp = overlap, NumMatSNPs, DPmean
+        self.accs = np.asarray(AccList).astype("str")
+        self.ninfo = np.asarray(NumInfoSites).astype("int")
+        self.scores = np.asarray(ScoreList).astype("int")     # truncation toward zero (snpmatch.py:96)
 
     def _attach_fused(self, prob, lik, lrt):
         """Results of the epilogue that ran fused behind the scoring kernels."""
@@ -143,20 +141,14 @@ class GenotyperOutput(object):
         no header (snpmatch.py:122-138).  BED inputs carry dp = "NA": the mean is nan."""
         self.get_likelihoods()
         self.get_probabilities()
-        output_table = pd.DataFrame({
-            'accs': self.accs,
-            'matches': self.scores,
-            'ninfo': self.ninfo,
-            'probabilities': self.probabilies,
-            'likelihood': self.likelis,
-            'lrt': self.lrts,
-            'num_snps': self.num_snps,
-            'dp': parsers.mean_depth(self.dp),
-        })
-        output_table = output_table[['accs', 'matches', 'ninfo', 'probabilities', 'likelihood', 'lrt', 'num_snps', 'dp']]
+        columns = (('accs', self.accs), ('matches', self.scores), ('ninfo', self.ninfo), ('probabilities', self.probabilies),
+                   ('likelihood', self.likelis), ('lrt', self.lrts), ('num_snps', self.num_snps), ('dp', parsers.mean_depth(self.dp)))
+        n_rows = len(self.accs)
+        table = pd.DataFrame({name: (col if np.ndim(col) else np.repeat(col, n_rows)) for name, col in columns},
+                             columns=[name for name, _ in columns])
         if outFile:
-            output_table.to_csv(outFile, header=None, sep="\t", index=None)
-        return output_table
+            table.to_csv(outFile, sep="\t", header=False, index=False)
+        return table
 
     def print_json_output(self, outFile):
         """`matches.json` (snpmatch.py:140-150)."""
@@ -164,14 +156,14 @@ class GenotyperOutput(object):
         self.get_probabilities()
         with np.errstate(invalid="ignore"):
             topHits = np.where(self.lrts < lr_thres)[0]
-        overlapScore = [get_fraction(self.ninfo[i], self.num_snps) for i in range(len(self.accs))]
-        sorted_order = topHits[np.argsort(-self.probabilies[topHits])]
+        by_probability = topHits[np.argsort(-self.probabilies[topHits])]
         case, note = self.case_interpreter(topHits)
-        matches = [(str(self.accs[i]), float(self.probabilies[i]), int(self.ninfo[i]), float(overlapScore[i]))
-                   for i in sorted_order]
-        top = {'overlap': [self.overlap, self.num_snps], 'matches': matches, 'interpretation': {'case': case, 'text': note}}
-        with open(outFile, "w") as out_stats:
-            out_stats.write(json.dumps(top, sort_keys=True, indent=4))
+        rows = []
+        for i in by_probability:            # accession, probability, informative sites, informative sites / matched markers
+            rows.append((str(self.accs[i]), float(self.probabilies[i]), int(self.ninfo[i]), float(get_fraction(self.ninfo[i], self.num_snps))))
+        report = {'interpretation': {'case': case, 'text': note}, 'matches': rows, 'overlap': [self.overlap, self.num_snps]}
+        with open(outFile, "w") as fh:
+            json.dump(report, fh, sort_keys=True, indent=4)
 
     def case_interpreter(self, topHits):
         """snpmatch.py:152-168."""
@@ -194,13 +186,10 @@ class Genotyper(object):
     def __init__(self, inputs, g, outFile, run_genotyper=True, skip_db_hets=False, chunk_size=1000):
         assert type(g) is snp_genotype.Genotype, "provide a snp_genotype.Genotype class for genotypes"
         assert chunk_size == lib.CHUNK_ROWS, "the device kernels sum in the reference's 1000-row chunks"
-        inputs.filter_chr_names()
-        self.chunk_size = chunk_size
-        self.inputs = inputs
-        self.g = g
-        self.num_lines = len(self.g.g.accessions)
-        self.outFile = outFile
-        self._skip_db_hets = skip_db_hets
+        self.g, self.inputs, self.outFile = g, inputs, outFile
+        self.chunk_size, self._skip_db_hets = chunk_size, skip_db_hets
+        self.num_lines = len(g.g.accessions)
+        self.inputs.filter_chr_names()
         if run_genotyper:
             self.result = self.genotyper()
             self.write_genotyper_output(self.result)
@@ -217,11 +206,11 @@ class Genotyper(object):
         with np.errstate(invalid="ignore"):
             topHits = np.where(self.result.lrts < lr_thres)[0]
         if len(topHits) == 1:
-            log.info("Done! It is a perfect hit")
+            log.info("a single accession is left: perfect hit, nothing to refine")
             return None
-        log.info("#lines indistinguishable: %s" % len(topHits))
+        log.info("%s accessions cannot be told apart at LR < %s", len(topHits), lr_thres)
         if len(topHits) > (self.num_lines / 2):
-            log.info("too many lines are indistinguishable, skipping refining likelihoods step")
+            log.info("more than half of the panel is indistinguishable: not refining")
             return None
         seg_ix = identify_segregating_snps(self.g, topHits)
         with np.errstate(invalid="ignore"):
@@ -263,7 +252,7 @@ class Genotyper(object):
         return out
 
     def write_genotyper_output(self, result):
-        log.info("writing score file!")
+        log.info("writing %s.scores.txt and %s.matches.json", self.outFile, self.outFile)
         result.get_likelihoods()
         result.print_out_table(self.outFile + '.scores.txt')
         result.print_json_output(self.outFile + ".matches.json")
@@ -288,25 +277,22 @@ def getHeterozygosity(snpGT, outFile='default'):
     numHets = int(np.count_nonzero(snpBinary == 2))
     frac = get_fraction(numHets, len(snpGT))
     if outFile != 'default':
-        with open(outFile) as json_out:
-            topHitsDict = json.load(json_out)
-        topHitsDict['percent_heterozygosity'] = frac
-        with open(outFile, "w") as out_stats:
-            out_stats.write(json.dumps(topHitsDict, sort_keys=True, indent=4))
+        with open(outFile) as fh:
+            report = json.load(fh)
+        report['percent_heterozygosity'] = frac
+        with open(outFile, "w") as fh:
+            json.dump(report, fh, sort_keys=True, indent=4)
     return frac
 
 
 def potatoGenotyper(args):
     inputs = parsers.ParseInputs(inFile=args['inFile'], logDebug=args['logDebug'])
-    log.info("loading database files")
+    log.info("packing the database into HBM")
     g = snp_genotype.Genotype(args['hdf5File'], args['hdf5accFile'])
-    log.info("running genotyper!")
-    if args['refine']:
-        genotyper = Genotyper(inputs, g, args['outFile'], run_genotyper=False, skip_db_hets=args['skip_db_hets'])
+    log.info("matching the sample against %s accessions", len(g.accessions))
+    genotyper = Genotyper(inputs, g, args['outFile'], run_genotyper=not args['refine'], skip_db_hets=args['skip_db_hets'])
+    if args['refine']:                       # --refine: score, then re-score the indistinguishable accessions on their segregating SNPs
         genotyper.filter_tophits()
-        log.info("finished!")
-        return None
-    Genotyper(inputs, g, args['outFile'], run_genotyper=True, skip_db_hets=args['skip_db_hets'])
     log.info("finished!")
 
 
@@ -316,11 +302,11 @@ def pairwiseScore(inFile_1, inFile_2, logDebug, outFile=None, hdf5File=None, dev
     loop (snpmatch.py:291-297) run on the GPU; the returned dict has the reference's keys and values.  Unlike the reference
     under Python 3 (its json.dumps trips over numpy integers, snpmatch.py:307) the output file is written."""
     snpmatch_stats = {}
-    log.info("loading input files")
+    log.info("parsing %s and %s", inFile_1, inFile_2)
     inputs_1 = parsers.ParseInputs(inFile=inFile_1, logDebug=logDebug)
     inputs_2 = parsers.ParseInputs(inFile=inFile_2, logDebug=logDebug)
     if hdf5File is not None:
-        log.info("loading database file to identify common SNP positions")
+        log.info("restricting sample 1 to the positions of the database")
         g = hdf5File if isinstance(hdf5File, snp_genotype.Genotype) else snp_genotype.Genotype(hdf5File, None, device=device)
         snpmatch_stats['hdf5'] = hdf5File if not isinstance(hdf5File, snp_genotype.Genotype) else "resident"
         commonSNPs_1 = g.get_positions_idxs(inputs_1.chrs, inputs_1.pos)
@@ -328,7 +314,7 @@ def pairwiseScore(inFile_1, inFile_2, logDebug, outFile=None, hdf5File=None, dev
                                                                  inputs_2.chrs, inputs_2.pos, device=device)
         common_inds = (commonSNPs_1[1][common_inds[0]], common_inds[1])
     else:
-        log.info("identify common positions")
+        log.info("joining the two samples on (chromosome, position)")
         common_inds = snp_genotype.Genotype.get_common_positions(inputs_1.chrs, inputs_1.pos, inputs_2.chrs, inputs_2.pos, device=device)
     log.info("done!")
     n1, n2 = len(inputs_1.chrs), len(inputs_2.chrs)
@@ -345,14 +331,13 @@ def pairwiseScore(inFile_1, inFile_2, logDebug, outFile=None, hdf5File=None, dev
     gt_ids = labels.factorize(np.concatenate([inputs_1.gt.astype("U"), inputs_2.gt.astype("U")]))[0]
     common, scores = lib.pair_match_counts(common_inds[0], common_inds[1], chrom1, gt_ids[:n1], gt_ids[n1:], len(common_chrs), device=device)
     for k, i in enumerate(common_chrs):
-        log.info("Analysing chromosome %s positions", i)
+        log.debug("chromosome %s: %s common markers, %s identical calls", i, int(common[k]), int(scores[k]))
         snpmatch_stats[str(i)] = [get_fraction(int(scores[k]), int(common[k])), int(common[k])]
     snpmatch_stats['matches'] = [get_fraction(int(np.sum(scores)), int(np.sum(common))), int(np.sum(common))]
     snpmatch_stats['unique'] = {"%s" % os.path.basename(inFile_1): [get_fraction(unique_1, n1), n1],
                                 "%s" % os.path.basename(inFile_2): [get_fraction(unique_2, n2), n2]}
     if outFile:
-        log.info("writing output in a file: %s" % outFile + ".matches.json")
-        with open(outFile + ".matches.json", "w") as out_stats:
-            out_stats.write(json.dumps(snpmatch_stats, sort_keys=True, indent=4))
-        log.info("finished!")
+        log.info("writing %s.matches.json", outFile)
+        with open(outFile + ".matches.json", "w") as fh:
+            json.dump(snpmatch_stats, fh, sort_keys=True, indent=4)
     return snpmatch_stats
