@@ -1010,7 +1010,7 @@ int snpm_batch_wait(snpm_batch *b, float *ms_device) {
     if (b->h_status[4] > 0)
         return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table (or run-length coded ids do not ascend)", b->h_status[4]);
     if (b->h_status[5] > 0)
-        return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within two seconds (every rank must run and reduce the same batches in the same order)");
+        return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within thirty seconds (every rank must run and reduce the same batches in the same order)");
     return SNPM_OK;
 }
 
@@ -1225,7 +1225,7 @@ int snpm_batch_fetch_wait(snpm_batch *b) {
     if (b->h_status[4] > 0)
         return fail(SNPM_E_ARG, "%d matched markers carry a weight-triple id outside the table (or run-length coded ids do not ascend)", b->h_status[4]);
     if (b->h_status[5] > 0)
-        return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within two seconds (every rank must run and reduce the same batches in the same order)");
+        return fail(SNPM_E_STATE, "peer reduce: a rank did not arrive within thirty seconds (every rank must run and reduce the same batches in the same order)");
     long long viol = 0;
     for (int64_t s = 0; s < b->rangen(); ++s) {
         if (b->pend_m) b->pend_m[s] = int64_t(b->h_tail[2 * s]);

@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(32 * CG_PARTS) k_combine_grouped(const double 
 //   done    the last block publishes "I have pulled my rows of step t": k_wait_peers_done at the head of the next run keeps
 //           the next totals from overwriting rows a peer is still reading.
 // Flags are step counters (monotonic, compared with wrap-around), so a rank that is one step ahead disturbs nobody.  A spin
-// gives up after two seconds and raises status[5] instead of hanging the GPU.  Works for both row layouts (2A+2, 3A+2).
+// gives up after thirty seconds and raises status[5] instead of hanging the GPU.  Works for both row layouts (2A+2, 3A+2).
 constexpr int PR_MAX_WORLD = 16;
 constexpr int PR_FLAG_BYTES = 4096;      // tail of the exported allocation: arrive[16] at u32 0.., done[16] at u32 64..
 constexpr int PR_DONE_OFF = 64;
@@ -577,12 +577,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// true when *f has reached `want` (step counters: signed distance); false after ~2 s
+// true when *f has reached `want` (step counters: signed distance); false after ~30 s (a rank that died, not one that is late)
 __device__ __forceinline__ bool spin_until(const uint32_t *f, uint32_t want) {
     const unsigned long long t0 = global_timer_ns();
     while (int32_t(ld_acquire_sys_u32(f) - want) < 0) {
         __nanosleep(40);
-        if (global_timer_ns() - t0 > 2000000000ull) return false;
+        if (global_timer_ns() - t0 > 30000000000ull) return false;
     }
     return true;
 }
