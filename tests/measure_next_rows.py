@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Timings of the SURVEY 8(f) rows built next to the matching path, on the full-size synthetic panel (1135 x 10.7 M):
 whole-column reads of the resident panel, `pairsnp`, and the `genotype_cross` window genotyper, each beside the CPU oracle on a
-bounded sample.  One JSON object per line; run on a B200:  python scripts/measure_next_rows.py > out.jsonl"""
+bounded sample.  Lives under tests/ because it runs the CPU oracle next to the GPU path (only tests/, smoke() and bench.py's CPU
+legs may use oracle/); it is a measurement script, not collected by pytest.  One JSON object per line; run on a B200:
+python tests/measure_next_rows.py > out.jsonl"""
 import json
 import os
 import sys
