@@ -184,9 +184,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1, procs),
+        "config": workload_config(args, args.gpus, args.samples * args.gpus),      # the b200 arm's workload; a step here is a bounded sample of it
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": "%d samples per step, one process each (join over the %d database labels + %d-marker "
+                         "sample": "%d samples of that batch per step, one process each (join over the %d database labels + %d-marker "
                                    "chunked matchGTsAccs + likelihoods); NumPy oracle port of snpmatch.py:207-233, database "
                                    "rows held in RAM as int8" % (procs, args.rows, cap or args.markers)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
