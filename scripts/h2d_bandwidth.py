@@ -1,4 +1,5 @@
-import torch, time
+"""Pinned host <-> device copy bandwidth of the box for the byte counts of one bench.py step (H2D 19 MB, D2H 3.5 MB)."""
+import torch
 x = torch.empty(19_070_566, dtype=torch.uint8).pin_memory()
 y = torch.empty_like(x, device="cuda")
 z = torch.empty(3_487_488, dtype=torch.uint8, device="cuda"); zh = torch.empty(3_487_488, dtype=torch.uint8).pin_memory()

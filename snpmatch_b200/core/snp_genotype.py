@@ -23,7 +23,7 @@ import numpy as np
 
 from .. import lib
 from . import labels
-from . import parsers
+from . import parsers  # noqa: F401  (the reference module exposes snp_genotype.parsers)
 
 log = logging.getLogger(__name__)
 
