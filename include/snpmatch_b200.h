@@ -222,7 +222,8 @@ int snpm_batch_fetch_wait(snpm_batch *b);
  * snpmatch.py:186-187.  capacity in elements; *m receives the pair count. */
 int snpm_batch_fetch_pairs(snpm_batch *b, int64_t s, int64_t *db_idx, int64_t *s_idx, int64_t capacity, int64_t *m);
 /* per-stage device times of the last run (ms): [0] join, [1] scoring kernel, [2] combine,
- * [3] epilogue, [4] whole run; plus the number of kernel launches in ms[5] */
+ * [3] epilogue, [4] whole run; plus the number of kernel launches in ms[5]; with n >= 8 also [6] the one-shot peer
+ * reduce kernel of the last step (snpm_batch_reduce_peers) and [7] the part of it spent waiting for the slowest rank */
 int snpm_batch_timings(snpm_batch *b, float *ms, int n);
 
 /* one-call host-buffer form of the above for a single sample (upload, run, epilogue, fetch) */
