@@ -444,6 +444,30 @@ def gen_genotype_cross_cases(ref):
     print("genotype_cross: %d cases, grid of %d cells" % (len(index) - 1, len(grid)))
 
 
+def gen_makedb_cases(ref):
+    """The CSV loader behind `snpmatch makedb` (pygwas/genotype.py:29-105: parse_genotype_csv_file, load_csv_genotype_data) on a
+    small CSV: chromosome entries per run of labels in file order (a label that comes back opens a new entry)."""
+    from snpmatch.pygwas import genotype as r_pg
+    rng = np.random.default_rng(41)
+    labels = ["1"] * 7 + ["2"] * 4 + ["Chr5"] * 5 + ["2"] * 3 + ["M"]
+    pos = np.concatenate([np.sort(rng.choice(5000, n, replace=False)) + 1 for n in (7, 4, 5, 3, 1)])
+    codes = rng.choice(np.array([-1, 0, 1, 2]), size=(len(labels), 6), p=[0.1, 0.5, 0.3, 0.1])
+    accs = ["6909", "8236", " 7000", "9001", "100", "5"]
+    text = "Chromosome,Position," + ",".join(accs) + "\n" + "".join(
+        "%s,%d,%s\n" % (c, p, ",".join(str(v) for v in row)) for c, p, row in zip(labels, pos, codes))
+    tmp = tempfile.mkdtemp(prefix="snpm_makedb_")
+    path = os.path.join(tmp, "db.csv")
+    with open(path, "w") as fh:
+        fh.write(text)
+    g = r_pg.load_csv_genotype_data(path)
+    out = {"csv": np.array(text), "snps": np.array(g.snps, dtype=np.int8), "positions": np.array(g.positions, dtype=np.int64),
+           "chrs": np.array(g.chrs, dtype="U"), "chr_regions": np.array(g.chr_regions, dtype=np.int64),
+           "accessions": np.array(g.accessions, dtype="U")}
+    np.savez_compressed(os.path.join(GOLD, "makedb_csv.npz"), **out)
+    shutil.rmtree(tmp, ignore_errors=True)
+    print("makedb: %d rows, %d chromosome entries" % (len(out["positions"]), len(out["chrs"])))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = rh.load_reference()
@@ -454,6 +478,7 @@ def main():
     gen_pairsnp_cases(ref)
     gen_simulate_cases(ref)
     gen_genotype_cross_cases(ref)
+    gen_makedb_cases(ref)
 
 
 if __name__ == "__main__":

@@ -4,7 +4,7 @@ snpmatch_b200 — B200-native genotype-matching hot path behind SNPmatch's `inbr
 The command line mirrors the reference's `snpmatch/__init__.py` for the two sub-commands on the
 matching path (`inbred`, `cross`: flags of __init__.py:44-63), `parser` (:80-84) and the callers next to the
 path that work on the resident panel (`pairsnp` :86-92, `simulate` :101-111, `genotype_cross`
-:65-78 without its HMM mode); the other
+:65-78 without its HMM mode, `makedb` :94-99 without bcftools / HDF5); the other
 sub-commands of the reference are outside this package's scope.
 """
 import argparse
@@ -64,6 +64,12 @@ def snpmatch_paircomparions(args):
     check_file(args['inFile_2'])
     from .core import snpmatch
     snpmatch.pairwiseScore(args['inFile_1'], args['inFile_2'], args['logDebug'], args['outFile'], args['hdf5File'])
+
+
+def makedb_vcf_to_db(args):
+    check_file(args['inFile'])
+    from .core import makedb
+    makedb.makedb_from_vcf(args)
 
 
 def simulate_snps(args):
@@ -132,6 +138,13 @@ def get_options(description, version_message):
     pair.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
     pair.add_argument("-o", "--output", dest="outFile", default="pairsnp", help="output prefix (<prefix>.matches.json)")
     pair.set_defaults(func=snpmatch_paircomparions)
+
+    mk = sub.add_parser('makedb', help="build the packed database (<id>.npz) and the genome JSON from a multi-sample VCF of the known strains, or from the intermediate CSV of the reference")
+    mk.add_argument("-i", "--input_vcf", dest="inFile", help="VCF of the known strains (biallelic SNPs), or a CSV with the columns Chromosome,Position,<accession>...")
+    mk.add_argument("-p", "--bcftools_path", dest="bcfpath", default='', help="accepted for compatibility: the VCF is read directly, bcftools is not needed")
+    mk.add_argument("-o", "--out_db_id", dest="db_id", help="output id: <id>.npz, <id>.json (and <id>.csv for VCF input)")
+    mk.add_argument("-v", "--verbose", action="store_true", dest="logDebug", default=False, help="log at DEBUG level")
+    mk.set_defaults(func=makedb_vcf_to_db)
 
     sim = sub.add_parser('simulate', help="draw a synthetic sample (or F1) from the database to test the genotyper")
     sim.add_argument("-d", "--hdf5_file", default=None, dest="hdf5File", help=db_help)

@@ -170,3 +170,35 @@ def test_command_line_pairsnp_and_simulate(lib, small_geno, tmp_path):
     assert js["matches"] == st["matches"]
     for c in ("1", "2", "3", "4", "5"):
         assert js[c] == st[c]
+
+
+def test_makedb_builds_a_loadable_database(lib, small_panel, sample_inbred, tmp_path):
+    """CSV (the reference's intermediate makedb format) -> streamed to the GPU in small chunks -> packed .npz -> loaded again:
+    same matrix, same index arrays; `inbred` on it gives the scores of the panel built from arrays; and the command line."""
+    import snpmatch_b200
+    from snpmatch_b200.core import makedb, snp_genotype, parsers, snpmatch
+    p = small_panel
+    labels = np.array(orc.db_chromosome_labels(p["chrs"], p["chr_regions"]))
+    csv = str(tmp_path / "panel.csv")
+    with open(csv, "w") as fh:
+        fh.write("Chromosome,Position," + ",".join(p["accessions"].astype("U")) + "\n")
+        for c, pos, row in zip(labels, p["positions"], p["snps"]):
+            fh.write("%s,%d,%s\n" % (c, pos, ",".join(str(int(v)) for v in row)))
+    g = makedb.makeDB(csv, str(tmp_path / "db"), chunk_rows=1700)          # 6000 rows in four chunks
+    assert np.array_equal(g.g.snps[:, :], p["snps"])
+    g.close()
+    g2 = snp_genotype.Genotype(str(tmp_path / "db.npz"))
+    assert np.array_equal(g2.g.snps[:, :], p["snps"]) and np.array_equal(g2.g.positions, p["positions"])
+    assert g2.chrs.tolist() == p["chrs"].astype("U").tolist() and np.array_equal(g2.g.chr_regions, p["chr_regions"])
+    assert g2.accessions.tolist() == p["accessions"].astype("U").tolist()
+    s = sample_inbred
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei"], s["dp"])
+    r = snpmatch.Genotyper(inp, g2, str(tmp_path / "o"), run_genotyper=True).result
+    want = load_golden("inbred_pl.npz")
+    assert np.array_equal(r.scores, want["scores"]) and np.array_equal(r.ninfo, want["ninfo"])
+    g2.close()
+    assert snpmatch_b200.main(["makedb", "-i", csv, "-o", str(tmp_path / "cli_db")]) == 0
+    g3 = snp_genotype.Genotype(str(tmp_path / "cli_db.npz"))
+    assert np.array_equal(g3.g.snps[[0, 17, 5999], :], p["snps"][[0, 17, 5999], :])
+    g3.close()

@@ -241,3 +241,35 @@ def test_grouped_samples_run_length_ids(built_lib):
     for s in range(len(n)):                                                 # inside a sample the ids ascend (that is what makes runs long)
         assert np.all(np.diff(g.gid[offs[s]:offs[s + 1]].astype(int)) >= 0)
     assert g.h2d_bytes < offs.nbytes + 6 * offs[-1] + len(g.table) * 32
+
+
+def test_makedb_host_side(tmp_path):
+    """`makedb` without bcftools / HDF5: the VCF -> CSV step (getCSV, makedb.py:34-62) and the CSV loader
+    against the arrays the reference's pygwas loader builds (tests/golden/makedb_csv.npz)."""
+    import json
+    from snpmatch_b200.core import makedb
+    g = load_golden("makedb_csv.npz")
+    path = str(tmp_path / "db.csv")
+    with open(path, "w") as fh:
+        fh.write(str(g["csv"]))
+    d = makedb.load_csv(path)
+    assert np.array_equal(d["snps"], g["snps"]) and np.array_equal(d["positions"], g["positions"])
+    assert d["chrs"].tolist() == g["chrs"].tolist() and np.array_equal(d["chr_regions"], g["chr_regions"])
+    assert d["accessions"].astype("U").tolist() == g["accessions"].tolist()
+    with open(str(tmp_path / "tabs.csv"), "w") as fh:
+        fh.write(str(g["csv"]).replace(",", "\t").replace("Position", "Positions"))
+    t = makedb.load_csv(str(tmp_path / "tabs.csv"))
+    assert np.array_equal(t["snps"], g["snps"]) and np.array_equal(t["chr_regions"], g["chr_regions"])
+    with open(str(tmp_path / "bad.csv"), "w") as fh:
+        fh.write("chrom,pos,a\n1,2,0\n")
+    with pytest.raises(Exception, match="First two columns"):
+        makedb.load_csv(str(tmp_path / "bad.csv"))
+    vcf = tmp_path / "strains.vcf"
+    vcf.write_text("##fileformat=VCFv4.2\n##contig=<ID=Chr1,length=30427671>\n##contig=<ID=Chr2,length=19698289,assembly=x>\n"
+                   "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t6909\t8236\t9999\n"
+                   "Chr1\t10\t.\tA\tT\t.\t.\t.\tGT\t0/0\t1/1\t0/1\nChr1\t25\t.\tA\tT\t.\t.\t.\tGT:DP\t1|0:3\t./.:0\t1/2:4\n"
+                   "Chr2\t7\t.\tA\tT\t.\t.\t.\tGT\t1/1\t0|0\t.\n")
+    makedb.vcf_to_csv(str(vcf), str(tmp_path / "db2"))
+    assert open(str(tmp_path / "db2.csv")).read() == "Chromosome,Position,6909,8236,9999\nChr1,10,0,1,2\nChr1,25,2,-1,-1\nChr2,7,1,0,-1\n"
+    assert json.load(open(str(tmp_path / "db2.json"))) == {"ref_chrs": ["Chr1", "Chr2"], "ref_chrlen": [30427671, 19698289]}
+    assert makedb.get_contigs(["##contig=<ID=1,length=5>", "##INFO=<ID=DP>"]) == {"ref_chrs": ["1"], "ref_chrlen": [5]}
