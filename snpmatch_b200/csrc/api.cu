@@ -9,6 +9,7 @@
 #include "gemm_onehot.cuh"
 #include "grouped.cuh"
 #include "pairs.cuh"
+#include "grouped_half.cuh"
 #include "cross_geno.cuh"
 #include <unordered_map>
 
@@ -884,7 +885,20 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
                 jmax = std::max(jmax, ceil_div64(std::min<int64_t>(b->h_off[size_t(smp) + 1] - b->h_off[size_t(smp)], db->n_rows), b->gchunk));
             g.jmax = int32_t(jmax);
             dim3 ggrid(unsigned(ceil_div64(b->S * jmax, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
-            if (g.wx == GR_MAX_WX) {              // the 1135-accession row: addresses known at compile time
+            static const bool use_half = getenv("SNPM_GROUPED_HALF") != nullptr;     // experiment, off by default (grouped_half.cuh)
+            if (use_half && g.wx == GR_MAX_WX) {
+                g.spc = std::min(GH_THREADS / (2 * g.wx), 5);
+                const size_t hsmem = size_t(g.spc) * half_team_smem(g.wx, g.chunk);
+                static bool gh_attr = false;
+                if (!gh_attr) {
+                    SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped_half<true, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped_half<false, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    gh_attr = true;
+                }
+                dim3 hgrid(unsigned(ceil_div64(b->S * jmax, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
+                if (skip_db_hets) k_score_grouped_half<true, GR_MAX_WX><<<hgrid, GH_THREADS, hsmem, st>>>(g);
+                else k_score_grouped_half<false, GR_MAX_WX><<<hgrid, GH_THREADS, hsmem, st>>>(g);
+            } else if (g.wx == GR_MAX_WX) {       // the 1135-accession row: addresses known at compile time
                 if (skip_db_hets) k_score_grouped<true, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
                 else k_score_grouped<false, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
             } else {

@@ -1,17 +1,12 @@
-// EXPERIMENT, NOT PART OF THE LIBRARY, NOT YET RUN ON HARDWARE.
-// The half-word / row-pair variant of k_score_grouped (bit layouts checked by
-// scripts/emulate_halfword_counters.py).  Compiled only to read its register count and SASS:
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xptxas -v -cubin -o /tmp/grouped_half.cubin \
-//        -I snpmatch_b200/csrc scripts/experimental/grouped_half.cu
+// EXPERIMENT — compiled into the library but reached only with SNPM_GROUPED_HALF=1 in the environment; NOT YET RUN ON HARDWARE
+// (written when the round's GPU budget was spent).  The half-word / row-pair variant of k_score_grouped (bit
+// layouts checked by scripts/emulate_halfword_counters.py).  ptxas: 168 registers, no spills at 384 threads per CTA.
 // A thread owns 16 accessions of one 32-accession word column (half h) and packs two rows per register (low 16 bits = row 2j,
 // high 16 bits = row 2j+1 of a 32-row block), so BitCounter::add16 counts 32 rows per call on 32 useful bits.  A team is
 // 2 * wx = 72 threads; five teams per 384-thread CTA, one CTA per SM (12 warps per SM instead of 8, 94 % of the lanes busy
-// instead of 84 %).  The per-class change masks are 32 bits per block.
+// instead of 84 %).  The per-class change masks are 32 bits per block.  Same inputs and outputs as k_score_grouped.
+#pragma once
 #include "common.cuh"
-#include "pack.cuh"
-#include "join.cuh"
-#include "score.cuh"
-#include "hardcall.cuh"
 #include "grouped.cuh"
 
 namespace snpm {
@@ -243,8 +238,5 @@ __global__ void __launch_bounds__(GH_THREADS, 1) k_score_grouped_half(const Grou
         a.part_int[o + b * lane_pitch] = vi[i] | (vn[i] << 16);
     }
 }
-
-template __global__ void k_score_grouped_half<false, 36>(const GroupArgs);
-template __global__ void k_score_grouped_half<true, 36>(const GroupArgs);
 
 }  // namespace snpm
