@@ -160,11 +160,27 @@ int snpm_batch_upload_grouped_packed(snpm_batch *b, int64_t n_samples, const int
  * 4 + 6 / (markers per run) bytes per marker cross the PCIe bus (4.1 for PL samples of 50 k markers). */
 int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
                                    const uint16_t *run_gid, const uint32_t *run_end, int64_t n_runs, const double *table, int32_t n_table);
+/* ---- coded upload: the grouping done on the device (group_sort.cuh) ---------------------------------------------------
+ * What a parser has in hand (parsers.py:141-157) goes up as it is: markers in POSITION order as chrom_pos words (chromosome
+ * id << 27 | position, id 31 = not in the panel: snpm_pack_markers) and, per marker, three dictionary codes in wei's column
+ * order (ref, het, alt) into wtable (n_wtable <= 65536 distinct weight values, finite and >= 0; for a VCF the code is the
+ * integer PL and wtable[k] = exp(-k/10)).  10 bytes per marker cross the PCIe bus and the host does no per-marker work.
+ * snpm_batch_run(mode 2) then joins, builds a sort key per matched pair from its codes (called class | its code | code of the
+ * class with fewer distinct weights | code of the other), sorts every sample's pairs by that key (stable segmented radix
+ * sort), marks where each class weight changes and scores with the persistent counting kernel k_score_grouped2.  Replaces
+ * snpm_group_markers + snpm_batch_upload_grouped*; results are identical (counts do not depend on the order inside a group).
+ * Group chunks (snpm_batch_set_group_chunk) must be multiples of 16 and at most 496 rows for coded batches. */
+int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
+                            const uint16_t *codes, const double *wtable, int32_t n_wtable);
+/* device times (ms) of the last coded run's stages: [0] marker expansion + join + compaction, [1] key sort + change masks,
+ * [2] scoring kernel, [3] combine; n >= 4 */
+int snpm_batch_coded_timings(snpm_batch *b, float *ms, int n);
 /* after snpm_batch_epilogue on a grouped batch: counts[s] = accessions of sample s whose fractional score part lies
  * within the rounding-error bound of an integer, i.e. whose int(score) depends on the reference's own summation order
  * (probability ~1e-7 per accession).  Re-score those samples with mode 0.  All zeros for position-order batches. */
 int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts);
-/* rows per segment of the grouped kernel (16..1008, a multiple of 8, default 1000); takes effect at the next grouped upload */
+/* rows per segment of the grouped kernel (16..1008, a multiple of 8, default 320); takes effect at the next grouped or coded
+ * upload (the value is latched there: buffers are sized from it) */
 int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows);
 int snpm_batch_destroy(snpm_batch *b);
 /* optional Genotyper.genotyper(filter_pos_ix=...) (snpmatch.py:211-216): keep only pairs whose

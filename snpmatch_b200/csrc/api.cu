@@ -8,8 +8,9 @@
 #include "hardcall.cuh"
 #include "gemm_onehot.cuh"
 #include "grouped.cuh"
+#include "group_sort.cuh"
+#include "grouped2.cuh"
 #include "pairs.cuh"
-#include "grouped_half.cuh"
 #include "cross_geno.cuh"
 #include <unordered_map>
 
@@ -373,9 +374,10 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
     b->S = S;
     b->n = n;
     b->grouped = false;
+    b->coded = false;
     b->h_off.assign(offsets, offsets + S + 1);
     int64_t nseg = 0;
-    for (int64_t s = 0; s < S; ++s) nseg += ceil_div64(std::min<int64_t>(offsets[s + 1] - offsets[s], db->n_rows), SNPM_CHUNK_ROWS);
+    for (int64_t s = 0; s < S; ++s) nseg += ceil_div64(offsets[s + 1] - offsets[s], SNPM_CHUNK_ROWS);
     b->nseg_cap = nseg;
     SNPM_TRY(b->d_off.ensure(size_t(S + 1) * 8));
     SNPM_TRY(b->d_chrom.ensure(size_t(n) * 4));
@@ -413,7 +415,8 @@ static int batch_new(snpm_db *db, snpm_batch **out) {
     }
     if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->ev_inputs_free, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&b->ev_inputs_free, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&b->ev_joined) != cudaSuccess) {
         snpm_batch_destroy(b);
         return fail(SNPM_E_CUDA, "snpm_batch_create: copy stream / events");
     }
@@ -597,11 +600,13 @@ static int upload_grouped(snpm_batch *b, int64_t n_samples, const int64_t *offse
     b->S = n_samples;
     b->n = n;
     b->grouped = true;
+    b->coded = false;
     b->pending_expand = 0;
     b->n_gtable = n_table;
+    b->gchunk = b->gchunk_req;                                  // latched: the buffers below and the next runs use this value
     b->h_off.assign(offsets, offsets + n_samples + 1);
-    int64_t nseg = 0;
-    for (int64_t s = 0; s < n_samples; ++s) nseg += ceil_div64(std::min<int64_t>(offsets[s + 1] - offsets[s], db->n_rows), b->gchunk);
+    int64_t nseg = 0;                                           // bound by the markers alone (a repeated marker matches its row twice)
+    for (int64_t s = 0; s < n_samples; ++s) nseg += ceil_div64(offsets[s + 1] - offsets[s], b->gchunk);
     b->nseg_cap = nseg;
     SNPM_TRY(b->d_off.ensure(size_t(n_samples + 1) * 8));
     SNPM_TRY(b->d_chrom8.ensure(size_t(n)));
@@ -661,6 +666,97 @@ int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64
     return upload_grouped(b, n_samples, offsets, nullptr, nullptr, chrom_pos, nullptr, table, n_table, run_gid, run_end, n_runs);
 }
 
+int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *codes,
+                            const double *wtable, int32_t n_wtable) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: NULL batch");
+    snpm_db *db = b->db;
+    if (n_samples < 1 || !offsets || offsets[0] != 0) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: need samples and offsets starting at 0");
+    for (int64_t s = 0; s < n_samples; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: offsets must be non-decreasing");
+    const int64_t n = offsets[n_samples];
+    if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: %lld markers exceed the 2^31 limit", (long long)n);
+    if (n > 0 && (!chrom_pos || !codes)) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: NULL marker arrays");
+    if (!wtable || n_wtable < 1 || n_wtable > 65536) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: the weight table must hold 1..65536 values");
+    for (int32_t t = 0; t < n_wtable; ++t)
+        if (!(wtable[t] >= 0.0) || std::isinf(wtable[t])) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: weights must be finite and non-negative (entry %d)", t);
+    if (b->gchunk_req % GR_BLOCK || b->gchunk_req > G2_MAX_CHUNK)
+        return fail(SNPM_E_ARG, "snpm_batch_upload_coded: the group chunk must be a multiple of %d and at most %d rows (it is %d)", GR_BLOCK, G2_MAX_CHUNK, b->gchunk_req);
+    SNPM_CUDA(cudaSetDevice(db->device));
+    b->S = n_samples;
+    b->n = n;
+    b->grouped = true;
+    b->coded = true;
+    b->pending_expand = 2;                                      // packed words -> chromosome ids + positions at the head of the run
+    b->d_runs_bad = nullptr;
+    b->n_wtable = n_wtable;
+    int bits = 1;
+    while ((1 << bits) < n_wtable) ++bits;
+    b->code_bits = bits;
+    b->key_bits = 3 * bits + 2;
+    b->gchunk = b->gchunk_req;
+    b->h_off.assign(offsets, offsets + n_samples + 1);
+    int64_t nseg = 0;
+    std::vector<int32_t> tile_first(size_t(n_samples) + 1), tile_sample;
+    for (int64_t s = 0; s < n_samples; ++s) {
+        const int64_t ns = offsets[s + 1] - offsets[s];
+        nseg += ceil_div64(ns, b->gchunk);
+        tile_first[size_t(s)] = int32_t(tile_sample.size());
+        for (int64_t t = 0; t < ceil_div64(ns, RS_TILE); ++t) tile_sample.push_back(int32_t(s));
+    }
+    tile_first[size_t(n_samples)] = int32_t(tile_sample.size());
+    b->nseg_cap = nseg;
+    b->n_sort_tiles = int64_t(tile_sample.size());
+    const size_t key_bytes = b->key_bits <= 32 ? 4 : 8;
+    SNPM_TRY(b->d_off.ensure(size_t(n_samples + 1) * 8));
+    SNPM_TRY(b->d_chrom.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pos.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_wei_idx.ensure(size_t(n) * 4));               // staging of the packed words
+    SNPM_TRY(b->d_codes.ensure(size_t(n) * 6));
+    SNPM_TRY(b->d_wtable.ensure(size_t(n_wtable) * 8));
+    SNPM_TRY(b->d_key_a.ensure(size_t(n) * key_bytes));
+    SNPM_TRY(b->d_key_b.ensure(size_t(n) * key_bytes));
+    SNPM_TRY(b->d_idx_a.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_idx_b.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pair_db_tmp.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_pair_s_tmp.ensure(size_t(n) * 4));
+    SNPM_TRY(b->d_tile_sample.ensure(std::max<size_t>(tile_sample.size(), 1) * 4));
+    SNPM_TRY(b->d_tile_first.ensure(size_t(n_samples + 1) * 4));
+    SNPM_TRY(b->d_tile_hist.ensure(std::max<size_t>(tile_sample.size(), 1) * (size_t(1) << RS_MAX_BITS) * 4));
+    SNPM_TRY(b->d_blk_chg.ensure(size_t(std::max<int64_t>(nseg, 1)) * size_t(b->gchunk / GR_BLOCK) * 8));
+    SNPM_TRY(b->d_work_counter.ensure(256));
+    cudaStream_t st = b->copy_stream;
+    SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_inputs_free, 0));
+    // small host-built tables are staged in buffers the batch owns (the copies are asynchronous)
+    b->h_gtable.assign(wtable, wtable + n_wtable);
+    b->h_tiles.assign(tile_first.begin(), tile_first.end());
+    b->h_tiles.insert(b->h_tiles.end(), tile_sample.begin(), tile_sample.end());
+    SNPM_CUDA(cudaMemcpyAsync(b->d_off.p, offsets, size_t(n_samples + 1) * 8, cudaMemcpyHostToDevice, st));
+    SNPM_CUDA(cudaMemcpyAsync(b->d_wtable.p, b->h_gtable.data(), size_t(n_wtable) * 8, cudaMemcpyHostToDevice, st));
+    SNPM_CUDA(cudaMemcpyAsync(b->d_tile_first.p, b->h_tiles.data(), size_t(n_samples + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (!tile_sample.empty())
+        SNPM_CUDA(cudaMemcpyAsync(b->d_tile_sample.p, b->h_tiles.data() + n_samples + 1, tile_sample.size() * 4, cudaMemcpyHostToDevice, st));
+    if (n) {
+        SNPM_CUDA(cudaMemcpyAsync(b->d_wei_idx.p, chrom_pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+        SNPM_CUDA(cudaMemcpyAsync(b->d_codes.p, codes, size_t(n) * 6, cudaMemcpyHostToDevice, st));
+    }
+    SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
+    b->ran = b->ran_windows = b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+int snpm_batch_coded_timings(snpm_batch *b, float *ms, int n) {
+    if (!b || !ms || n < 4) return fail(SNPM_E_ARG, "snpm_batch_coded_timings: need room for 4 floats");
+    if (!b->coded || !b->ran) return fail(SNPM_E_STATE, "snpm_batch_coded_timings: run a coded batch first");
+    SNPM_CUDA(cudaSetDevice(b->db->device));
+    SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    cudaEventElapsedTime(&ms[0], b->ev[SNPM_EV_START], b->ev_joined);
+    cudaEventElapsedTime(&ms[1], b->ev_joined, b->ev[SNPM_EV_JOIN]);
+    cudaEventElapsedTime(&ms[2], b->ev[SNPM_EV_JOIN], b->ev[SNPM_EV_SCORE]);
+    cudaEventElapsedTime(&ms[3], b->ev[SNPM_EV_SCORE], b->ev[SNPM_EV_COMBINE]);
+    return SNPM_OK;
+}
+
 int snpm_pack_markers(int64_t n, const uint8_t *chrom_u8, const int32_t *pos, uint32_t *out) {
     if (n < 0 || (n > 0 && (!chrom_u8 || !pos || !out))) return fail(SNPM_E_ARG, "snpm_pack_markers: bad arguments");
     for (int64_t i = 0; i < n; ++i) {
@@ -692,7 +788,7 @@ int snpm_batch_set_result_range(snpm_batch *b, int64_t first_sample, int64_t n_s
 
 int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows) {
     if (!b || rows < 16 || rows > GR_MAX_CHUNK || rows % 8) return fail(SNPM_E_ARG, "snpm_batch_set_group_chunk: 16..%d rows, a multiple of 8", GR_MAX_CHUNK);
-    b->gchunk = rows;
+    b->gchunk_req = rows;
     return SNPM_OK;
 }
 
@@ -705,12 +801,15 @@ int snpm_batch_destroy(snpm_batch *b) {
     if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
     if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
     if (b->ev_inputs_free) cudaEventDestroy(b->ev_inputs_free);
+    if (b->ev_joined) cudaEventDestroy(b->ev_joined);
     DevBuf *bufs[] = {&b->d_off, &b->d_chrom, &b->d_pos, &b->d_wei, &b->d_filter, &b->d_match_row, &b->d_tile_cnt, &b->d_tile_off,
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
                       &b->d_win_count, &b->d_win_off, &b->d_win_begin, &b->d_win_end, &b->d_kmax, &b->d_win_L, &b->d_win_LR,
                       &b->d_win_ident, &b->d_win_amb, &b->d_win_row_off, &b->d_row_acc, &b->d_row_score, &b->d_row_ninfo, &b->d_row_L, &b->d_row_ident, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
-                      &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard, &b->d_runs};
+                      &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard, &b->d_runs,
+                      &b->d_codes, &b->d_wtable, &b->d_key_a, &b->d_key_b, &b->d_idx_a, &b->d_idx_b, &b->d_pair_db_tmp, &b->d_pair_s_tmp,
+                      &b->d_tile_sample, &b->d_tile_first, &b->d_tile_hist, &b->d_blk_chg, &b->d_work_counter};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
@@ -749,7 +848,8 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_prefix.ensure(size_t(n + 1) * 4));
     SNPM_TRY(b->d_pair_db.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_pair_s.ensure(size_t(n) * 4));
-    if (b->grouped) SNPM_TRY(b->d_pair_gid.ensure(size_t(n) * 2 + 16));
+    if (b->coded) { /* keys and temporaries were sized at upload */ }
+    else if (b->grouped) SNPM_TRY(b->d_pair_gid.ensure(size_t(n) * 2 + 16));
     else SNPM_TRY(b->d_pair_w.ensure(size_t(n) * 32));
     SNPM_TRY(b->d_mstart.ensure(size_t(S + 1) * 4));
     SNPM_TRY(b->d_seg_off.ensure(size_t(S + 1) * 4));
@@ -788,11 +888,20 @@ static int batch_join(snpm_batch *b, int algo) {
             k_join_search<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
                                                             db->d_pos, db->d_chr_regions, db->n_chr, db->d_bucket, db->d_bucket_off, db->bucket_shift,
                                                             filter, b->n_filter, db->row0_global,
-                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>(), b->grouped ? 0 : 1);
+                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>(), (b->grouped && !b->coded) ? 0 : 1);
         SNPM_KERNEL_CHECK();
         k_scan_tiles<<<1, 1024, 0, st>>>(b->d_tile_cnt.as<int32_t>(), n_tiles, b->d_tile_off.as<int32_t>(), b->d_prefix.as<int32_t>() + n);
         SNPM_KERNEL_CHECK();
-        if (b->grouped)
+        if (b->coded) {
+            if (b->key_bits <= 32)
+                k_scatter_pairs_coded<uint32_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
+                        b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
+                        b->d_key_a.as<uint32_t>(), b->d_idx_a.as<uint32_t>(), b->d_status.as<int>());
+            else
+                k_scatter_pairs_coded<uint64_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
+                        b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
+                        b->d_key_a.as<uint64_t>(), b->d_idx_a.as<uint32_t>(), b->d_status.as<int>());
+        } else if (b->grouped)
             k_scatter_pairs_grouped<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(),
                                                                       b->d_gid.as<uint16_t>(), b->n_gtable, b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(),
                                                                       b->d_pair_s.as<int32_t>(), b->d_pair_gid.as<uint16_t>(), b->d_status.as<int>());
@@ -811,6 +920,98 @@ static int batch_join(snpm_batch *b, int algo) {
     b->launches += 1;
     return SNPM_OK;
 }
+
+}  // extern "C" (templates below)
+
+// coded batches: order every sample's pairs by their sort key (stable segmented LSD radix sort), resolve the sorted
+// permutation into the pair arrays the scoring kernels read, and mark the weight changes per 16-row block
+template <typename KeyT>
+static int batch_group_sort_t(snpm_batch *b) {
+    snpm_db *db = b->db;
+    cudaStream_t st = db->stream;
+    const int tiles = int(b->n_sort_tiles);
+    if (tiles == 0 || b->n == 0) return SNPM_OK;
+    const int passes = (b->key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    const int per = (b->key_bits + passes - 1) / passes;
+    KeyT *ka = b->d_key_a.as<KeyT>(), *kb = b->d_key_b.as<KeyT>();
+    uint32_t *ia = b->d_idx_a.as<uint32_t>(), *ib = b->d_idx_b.as<uint32_t>();
+    const int32_t *mstart = b->d_mstart.as<int32_t>(), *tsample = b->d_tile_sample.as<int32_t>(), *tfirst = b->d_tile_first.as<int32_t>();
+    uint32_t *hist = b->d_tile_hist.as<uint32_t>();
+    static bool attr = false;
+    if (!attr) {
+        SNPM_CUDA(cudaFuncSetAttribute(k_radix_scatter<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        SNPM_CUDA(cudaFuncSetAttribute(k_radix_scatter<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * per, bits = std::min(per, b->key_bits - shift), bins = 1 << bits;
+        k_radix_hist<KeyT><<<tiles, RS_THREADS, size_t(bins) * 4, st>>>(ka, mstart, tsample, tfirst, shift, bits, hist);
+        k_radix_scan<<<int(b->S), 1024, 0, st>>>(hist, tfirst, bits);
+        const size_t smem = size_t(RS_THREADS / 32) * bins * 2;
+        if (p == passes - 1)
+            k_radix_scatter<KeyT, true><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
+                                                                         b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(), mstart, tsample, tfirst, hist, shift, bits);
+        else
+            k_radix_scatter<KeyT, false><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, nullptr, nullptr, nullptr, nullptr, mstart, tsample, tfirst, hist, shift, bits);
+        SNPM_KERNEL_CHECK();
+        std::swap(ka, kb);
+        std::swap(ia, ib);
+        b->launches += 3;
+    }
+    b->sorted_key = ka;                                           // after the last swap
+    int64_t max_ns = 0;
+    for (int64_t s = 0; s < b->S; ++s) max_ns = std::max(max_ns, b->h_off[size_t(s) + 1] - b->h_off[size_t(s)]);
+    dim3 mgrid(unsigned(ceil_div64(max_ns, 256)), unsigned(b->S));
+    k_group_masks<KeyT><<<mgrid, 256, 0, st>>>(ka, mstart, b->d_seg_off.as<int32_t>(), b->gchunk, b->code_bits, b->d_blk_chg.as<unsigned long long>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    return SNPM_OK;
+}
+
+template <typename KeyT>
+static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
+    snpm_db *db = b->db;
+    cudaStream_t st = db->stream;
+    Group2Args<KeyT> g = {};
+    g.packed = db->d_packed; g.stride = db->stride; g.pair_db = b->d_pair_db.as<int32_t>();
+    g.pair_key = static_cast<const KeyT *>(b->sorted_key); g.blk_chg = b->d_blk_chg.as<unsigned long long>();
+    g.wtable = b->d_wtable.as<double>(); g.code_bits = b->code_bits;
+    g.seg_off = b->d_seg_off.as<int32_t>(); g.mstart = b->d_mstart.as<int32_t>(); g.S = int32_t(b->S); g.chunk = b->gchunk;
+    g.part_score = b->d_part_score.as<double>(); g.part_int = b->d_part_int.as<int32_t>(); g.a_pad = db->stride * 32;
+    g.n_slices = (db->stride + G2_WX - 1) / G2_WX;
+    g.wx = ((db->stride + g.n_slices - 1) / g.n_slices + 1) & ~1;      // even: neighbouring threads copy 16-byte pairs of columns
+    g.teams = std::min(G2_THREADS / g.wx, G2_MAX_TEAMS);
+    int64_t jmax = 0;
+    for (int64_t s = 0; s < b->S; ++s) jmax = std::max(jmax, ceil_div64(b->h_off[size_t(s) + 1] - b->h_off[size_t(s)], b->gchunk));
+    g.jmax = int32_t(jmax);
+    g.work_counter = b->d_work_counter.as<unsigned int>();
+    const int64_t n_items = b->S * jmax * g.n_slices;
+    if (n_items >= (int64_t(1) << 31) - (int64_t(1) << 20)) return fail(SNPM_E_ARG, "snpm_batch_run: %lld work items exceed the 2^31 limit", (long long)n_items);
+    const size_t smem = size_t(g.teams) * g2_team_smem<KeyT>(g.wx, g.chunk);
+    if (smem > 227 * 1024) return fail(SNPM_E_ARG, "snpm_batch_run: group chunk %d needs %zu bytes of shared memory", g.chunk, smem);
+    static bool attr = false;
+    if (!attr) {
+        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, true, G2_WX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, false, G2_WX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    SNPM_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned int), st));
+    const int grid = int(std::min<int64_t>(db->n_sm, ceil_div64(n_items, g.teams)));
+    if (g.wx == G2_WX) {
+        if (skip_db_hets) k_score_grouped2<KeyT, true, G2_WX, true><<<grid, G2_THREADS, smem, st>>>(g);
+        else k_score_grouped2<KeyT, false, G2_WX, true><<<grid, G2_THREADS, smem, st>>>(g);
+    } else {
+        if (skip_db_hets) k_score_grouped2<KeyT, true, 0, true><<<grid, G2_THREADS, smem, st>>>(g);
+        else k_score_grouped2<KeyT, false, 0, true><<<grid, G2_THREADS, smem, st>>>(g);
+    }
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    return SNPM_OK;
+}
+
+extern "C" {
 
 static int batch_alloc_outputs(snpm_batch *b, int64_t nseg) {
     snpm_db *db = b->db;
@@ -862,6 +1063,26 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     a.part_score = b->d_part_score.as<double>();
     a.part_ninfo = b->d_part_ninfo.as<int32_t>();
     a.a_pad = db->stride * 32;
+    if (kernel_mode == 2 && b->coded) {
+        cudaEventRecord(b->ev_joined, st);
+        if (b->key_bits <= 32) SNPM_TRY(batch_group_sort_t<uint32_t>(b)); else SNPM_TRY(batch_group_sort_t<uint64_t>(b));
+        rec(b, SNPM_EV_JOIN);                      // for coded batches "join" ends after the grouping: score_ms is the scoring kernel alone
+        if (b->nseg_cap > 0 && b->n > 0) {
+            if (b->key_bits <= 32) SNPM_TRY(launch_grouped2<uint32_t>(b, skip_db_hets != 0)); else SNPM_TRY(launch_grouped2<uint64_t>(b, skip_db_hets != 0));
+        }
+        rec(b, SNPM_EV_SCORE);
+        dim3 cgrid((a.a_pad + 31) / 32, unsigned(b->S));
+        k_combine_grouped<<<cgrid, 32 * CG_PARTS, 0, st>>>(a.part_score, b->d_part_int.as<int32_t>(), a.a_pad, db->stride, db->n_acc, a.seg_off, a.mstart,
+                                                 b->d_red.as<double>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 1;
+        rec(b, SNPM_EV_COMBINE);
+        SNPM_CUDA(cudaEventRecord(b->ev_inputs_free, st));
+        b->ran = true;
+        b->ran_windows = false;
+        b->epilogue_done = false;
+        return SNPM_OK;
+    }
     if (kernel_mode == 2) {
         if (b->nseg_cap > 0) {
             GroupArgs g = {};
@@ -882,23 +1103,10 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
             }
             int64_t jmax = 0;
             for (int64_t smp = 0; smp < b->S; ++smp)
-                jmax = std::max(jmax, ceil_div64(std::min<int64_t>(b->h_off[size_t(smp) + 1] - b->h_off[size_t(smp)], db->n_rows), b->gchunk));
+                jmax = std::max(jmax, ceil_div64(b->h_off[size_t(smp) + 1] - b->h_off[size_t(smp)], b->gchunk));
             g.jmax = int32_t(jmax);
             dim3 ggrid(unsigned(ceil_div64(b->S * jmax, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
-            static const bool use_half = getenv("SNPM_GROUPED_HALF") != nullptr;     // experiment, off by default (grouped_half.cuh)
-            if (use_half && g.wx == GR_MAX_WX) {
-                g.spc = std::min(GH_THREADS / (2 * g.wx), 5);
-                const size_t hsmem = size_t(g.spc) * half_team_smem(g.wx, g.chunk);
-                static bool gh_attr = false;
-                if (!gh_attr) {
-                    SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped_half<true, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                    SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped_half<false, GR_MAX_WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                    gh_attr = true;
-                }
-                dim3 hgrid(unsigned(ceil_div64(b->S * jmax, g.spc)), unsigned((db->stride + g.wx - 1) / g.wx));
-                if (skip_db_hets) k_score_grouped_half<true, GR_MAX_WX><<<hgrid, GH_THREADS, hsmem, st>>>(g);
-                else k_score_grouped_half<false, GR_MAX_WX><<<hgrid, GH_THREADS, hsmem, st>>>(g);
-            } else if (g.wx == GR_MAX_WX) {       // the 1135-accession row: addresses known at compile time
+            if (g.wx == GR_MAX_WX) {       // the 1135-accession row: addresses known at compile time
                 if (skip_db_hets) k_score_grouped<true, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
                 else k_score_grouped<false, GR_MAX_WX><<<ggrid, GR_THREADS, gsmem, st>>>(g);
             } else {

@@ -137,9 +137,19 @@ struct snpm_batch {
     // grouped mode (snpm_batch_upload_grouped): markers ordered by weight triple, scored by k_score_grouped
     bool grouped = false;
     int32_t n_gtable = 0;
-    int32_t gchunk = 320;              // rows per segment of the grouped kernel (measured best on the 1135 x 10.7 M workload)
+    int32_t gchunk = 320;              // rows per segment of the grouped kernels for the samples now on the device (latched at upload)
+    int32_t gchunk_req = 320;          // snpm_batch_set_group_chunk: takes effect at the next grouped / coded upload
+    // coded mode (snpm_batch_upload_coded): position-order markers + weight codes; grouped on the device (group_sort.cuh)
+    bool coded = false;
+    int32_t n_wtable = 0, code_bits = 0, key_bits = 0;
+    int64_t n_sort_tiles = 0;
+    snpm::DevBuf d_codes, d_wtable, d_key_a, d_key_b, d_idx_a, d_idx_b, d_pair_db_tmp, d_pair_s_tmp, d_tile_sample, d_tile_first,
+                 d_tile_hist, d_blk_chg, d_work_counter;
+    cudaEvent_t ev_joined = nullptr;   // coded runs: after join + compaction, before the key sort (snpm_batch_coded_timings)
+    const void *sorted_key = nullptr;  // coded runs: the key buffer that holds the sorted keys
     snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard, d_runs;
     std::vector<double> h_gtable;
+    std::vector<int32_t> h_tiles;      // coded mode: tile_first [S+1] | tile_sample [tiles] (staging of the asynchronous copy)
     // expansion of the compact upload forms, deferred to the head of the next run ON THE COMPUTE STREAM: a kernel on the copy
     // stream next to the scoring kernel cost 0.15 ms per step end to end (bit 0: run-length ids, 1: packed words, 2: byte chromosomes)
     int pending_expand = 0;

@@ -1,0 +1,382 @@
+// k_score_grouped2 — the counting kernel (A2/A3 in grouped order) as a persistent grid over device-grouped pairs.
+//
+// Same arithmetic as k_score_grouped (grouped.cuh): a thread owns one 32-accession word column of a segment, adds the class
+// planes of 16 rows at a time into bit-sliced counters, reads a class counter out only where that class's weight changes
+// (per-block change masks, here precomputed by k_group_masks), folds counts into fp64 with one fma per accession, keeps
+// weight-1.0 classes in an exact integer counter: score = I + F (see grouped.cuh for the exactness argument).
+// What is different:
+//   * input is what the device-side grouping produces (group_sort.cuh): sorted panel rows + sort keys that carry the three
+//     weight codes of a pair; weights come from the table of distinct values (L1-resident);
+//   * ONE CTA per SM, 7 teams of 36 threads in 8 warps (252 of 256 lanes work: the 128-thread CTAs of round 1 used 108 of
+//     128) and 7 instead of 6 segments in flight per SM;
+//   * teams are independent: a team claims (segment, word slice) items from a global counter, longest segments first, and
+//     synchronises only with itself (an mbarrier of 36 arrivals), so there is no CTA-wide barrier after start-up and no tail
+//     where an SM waits for its slowest team;
+//   * the row numbers, keys and change masks of the NEXT item are fetched with cp.async while the current one is scored
+//     (double-buffered staging), so a team never waits for a dependent global load between segments;
+//   * class counters have 8 planes (read out at the latest every 240 rows), the totals 9 (segments of at most 496 rows).
+#pragma once
+#include "common.cuh"
+#include "grouped.cuh"
+#include "group_sort.cuh"
+
+namespace snpm {
+
+constexpr int G2_WX = 36;                 // words per team (one 1135-accession row)
+constexpr int G2_MAX_TEAMS = 7;
+constexpr int G2_THREADS = 256;           // 7 teams x 36 = 252 threads: 8 warps, two per scheduler, so a thread may hold 255 registers
+                                          // (9 warps would put three on one scheduler's register file: 168 registers, spills)
+constexpr int G2_MAX_CHUNK = 496;
+constexpr int G2_CP = 8;                  // planes of a class counter
+constexpr int G2_TP = 9;                  // planes of the per-segment totals (I, ninfo)
+
+template <typename KeyT>
+struct Group2Args {
+    const uint64_t *packed;
+    int32_t stride;
+    const int32_t *pair_db;               // [m] matched local rows, grouped order
+    const KeyT *pair_key;                 // [m] sort keys of the pairs (group_sort.cuh)
+    const unsigned long long *blk_chg;    // change masks per 16-row block: [segment][chunk / 16]
+    const double *wtable;                 // distinct weight values
+    int32_t code_bits;
+    const int32_t *seg_off;               // [S+1]
+    const int32_t *mstart;                // [S+1]
+    int32_t S;
+    int32_t chunk;
+    double *part_score;                   // [nseg, 32, stride]  F of the segment; accession 32 w + b at [b][w]
+    int32_t *part_int;                    // [nseg, 32, stride]  low half I, high half ninfo
+    int32_t a_pad;
+    int32_t wx;                           // words per team slice
+    int32_t teams;                        // teams per CTA
+    int32_t n_slices;                     // word slices of a row
+    int32_t jmax;                         // upper bound of the segments of one sample
+    unsigned int *work_counter;           // zeroed before the launch
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+
+// what the leader publishes for an item
+struct G2Item {
+    int32_t seg;        // -1: no more work
+    int32_t begin;      // first pair
+    int32_t n_rows;
+    int32_t slice;
+};
+
+template <typename KeyT>
+__host__ __device__ __forceinline__ size_t g2_stage_bytes(int chunk) {
+    return (size_t(chunk) * 4 + size_t(chunk) * sizeof(KeyT) + size_t(chunk / 16 + 1) * 8 + 15) & ~size_t(15);
+}
+template <typename KeyT>
+__host__ __device__ __forceinline__ size_t g2_team_smem(int wx, int chunk) {
+    return size_t(GR_RING) * wx * 8 + 2 * g2_stage_bytes<KeyT>(chunk) + 64;       // ring | 2 staging buffers | mbarrier + 2 item slots
+}
+
+// fold the counts of an 8-plane counter: F[lane] += w * count[lane]
+__device__ __forceinline__ void fold_counts8(const BitCounter<G2_CP> &c, double w, double (&F)[32]) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = c.p[k];
+    transpose_planes8(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cnt = int((t[i] >> (8 * j)) & 0xffu);
+            F[8 * j + i] = fma(w, double(cnt), F[8 * j + i]);
+        }
+    }
+}
+
+__device__ __forceinline__ void counter_values9(const BitCounter<G2_TP> &c, int32_t (&v)[32]) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = c.p[k];
+    transpose_planes8(t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 8 * j + i;
+            v[b] = int32_t((t[i] >> (8 * j)) & 0xffu) | int32_t(((c.p[8] >> b) & 1u) << 8);
+        }
+    }
+}
+
+// WX > 0: words per team known at compile time; WX == 0: a.wx.  PAIRS: two neighbouring threads share 16-byte copies.
+template <typename KeyT, bool SKIP_HETS, int WX, bool PAIRS>
+__global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Args<KeyT> a) {
+    extern __shared__ __align__(16) unsigned char g2_smem[];
+    const int wx = WX ? WX : a.wx;
+    const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
+    const bool in_team = q < a.teams;
+    const size_t team_bytes = g2_team_smem<KeyT>(wx, a.chunk);
+    const size_t stage_bytes = g2_stage_bytes<KeyT>(a.chunk);
+    unsigned char *team = g2_smem + size_t(in_team ? q : 0) * team_bytes;
+    uint64_t *ring = reinterpret_cast<uint64_t *>(team);
+    unsigned char *stage0 = team + size_t(GR_RING) * wx * 8;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage0 + 2 * stage_bytes);
+    G2Item *slots = reinterpret_cast<G2Item *>(bar + 1);                  // [2]
+    if (in_team && w == 0) {
+        mbar_init(smem_u32(bar), uint32_t(wx));
+        mbar_fence_init();
+    }
+    __syncthreads();                              // the only CTA-wide barrier
+    if (!in_team) return;
+    // lanes of this team inside this warp.  Thread pairs (2i, 2i+1) share 16-byte copies; they read each other's data only while
+    // the team's lanes of the warp execute together (then the neighbour is past its own cp.async.wait_group and past its reads
+    // of the block before).  That is the normal state; if a divergent branch has split them, a sub-warp barrier rejoins them.
+    uint32_t tmask;
+    {
+        const int w0 = int(threadIdx.x) & ~31, t0 = q * wx, t1 = t0 + wx;
+        const int lo_l = max(t0, w0) - w0, hi_l = min(t1, w0 + 32) - w0;
+        tmask = (hi_l >= 32 ? 0xffffffffu : ((1u << hi_l) - 1u)) & ~((1u << lo_l) - 1u);
+    }
+    auto team_converge = [&](uint32_t m) {
+        if ((__activemask() & m) != m) __syncwarp(m);
+    };
+    uint32_t phase = 0u;
+    auto team_sync = [&]() {
+        mbar_arrive(smem_u32(bar));
+        mbar_wait(smem_u32(bar), phase);
+        phase ^= 1u;
+    };
+    const int n_items = a.S * a.jmax * a.n_slices;
+    // leader: claim the next valid item, longest segments first (slot -> segment j = jmax-1 - slot / S of sample slot % S)
+    auto claim = [&](G2Item *out) {
+        G2Item it;
+        it.seg = -1; it.begin = 0; it.n_rows = 0; it.slice = 0;
+        while (true) {
+            const int i = int(atomicAdd(a.work_counter, 1u));
+            if (i >= n_items) break;
+            const int slot = i / a.n_slices, slice = i - slot * a.n_slices;
+            const int j = a.jmax - 1 - slot / a.S, smp = slot % a.S;
+            const int s0 = __ldg(a.seg_off + smp), s1 = __ldg(a.seg_off + smp + 1);
+            if (j < s1 - s0) {
+                const int m0 = __ldg(a.mstart + smp), m1 = __ldg(a.mstart + smp + 1);
+                it.seg = s0 + j;
+                it.begin = m0 + j * a.chunk;
+                it.n_rows = min(m1, it.begin + a.chunk) - it.begin;
+                it.slice = slice;
+                break;
+            }
+        }
+        *out = it;
+    };
+    // queue the copies of an item's row numbers, keys and change masks into staging buffer `buf` (one commit group)
+    auto prefetch = [&](const G2Item &it, int buf) {
+        if (it.seg >= 0) {
+            unsigned char *st = stage0 + size_t(buf) * stage_bytes;
+            const uint32_t s_row = smem_u32(st), s_key = s_row + uint32_t(a.chunk) * 4u, s_chg = s_key + uint32_t(a.chunk) * uint32_t(sizeof(KeyT));
+            for (int r = w; r < it.n_rows; r += wx) {
+                cp_async4(s_row + uint32_t(r) * 4u, a.pair_db + it.begin + r);
+                if (sizeof(KeyT) == 4) cp_async4(s_key + uint32_t(r) * 4u, a.pair_key + it.begin + r);
+                else cp_async8(s_key + uint32_t(r) * 8u, a.pair_key + it.begin + r);
+            }
+            const int nb = (it.n_rows + GR_BLOCK - 1) / GR_BLOCK;
+            const unsigned long long *src = a.blk_chg + size_t(it.seg) * size_t(a.chunk / GR_BLOCK);
+            for (int b = w; b < nb; b += wx) cp_async8(s_chg + uint32_t(b) * 8u, src + b);
+        }
+        cp_async_commit();
+    };
+
+    // start-up: item 0 staged synchronously, item 1 claimed
+    if (w == 0) claim(&slots[0]);
+    team_sync();
+    G2Item cur = slots[0];
+    if (cur.seg < 0) return;
+    prefetch(cur, 0);
+    cp_async_wait<0>();
+    if (w == 0) claim(&slots[1]);
+    team_sync();
+    int buf = 0;
+
+    const int64_t stride = a.stride;
+    const int odd = w & 1;
+    const uint32_t ring_pitch = uint32_t(wx) * 8u;
+    const uint32_t stride_b = uint32_t(a.stride) * 8u;
+    const int cb = a.code_bits;
+
+    while (true) {
+        const G2Item nxt = slots[buf ^ 1];
+        prefetch(nxt, buf ^ 1);                   // lands while this item is scored (oldest commit group)
+        const unsigned char *st = stage0 + size_t(buf) * stage_bytes;
+        const int32_t *s_row = reinterpret_cast<const int32_t *>(st);
+        const KeyT *s_key = reinterpret_cast<const KeyT *>(st + size_t(a.chunk) * 4);
+        const unsigned long long *s_chg = reinterpret_cast<const unsigned long long *>(st + size_t(a.chunk) * 4 + size_t(a.chunk) * sizeof(KeyT));
+        const int n_rows = cur.n_rows;
+        const int n_blocks = (n_rows + GR_BLOCK - 1) / GR_BLOCK;
+        const int n_full = n_rows / GR_BLOCK;
+        const int word = cur.slice * wx + w;
+        const bool live = word < a.stride;        // threads past the row's last word idle through the item (they still stage and sync)
+        const unsigned char *col = reinterpret_cast<const unsigned char *>(a.packed + (PAIRS ? (word & ~1) : word));
+        const uint32_t my_ring = smem_u32(ring + (PAIRS ? (w & ~1) : w));
+        auto issue = [&](int b) {
+            if (live) {
+                if (PAIRS) {
+                    const int r0 = b * GR_BLOCK + 8 * odd;
+                    const uint32_t slot0 = my_ring + uint32_t(r0 % GR_RING) * ring_pitch;
+                    if (b < n_full) {
+#pragma unroll
+                        for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
+                            const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
+                            cp_async16(slot0 + uint32_t(k4 + 0) * ring_pitch, col + (unsigned long long)(uint32_t(rr.x)) * stride_b);
+                            cp_async16(slot0 + uint32_t(k4 + 1) * ring_pitch, col + (unsigned long long)(uint32_t(rr.y)) * stride_b);
+                            cp_async16(slot0 + uint32_t(k4 + 2) * ring_pitch, col + (unsigned long long)(uint32_t(rr.z)) * stride_b);
+                            cp_async16(slot0 + uint32_t(k4 + 3) * ring_pitch, col + (unsigned long long)(uint32_t(rr.w)) * stride_b);
+                        }
+                    } else if (b < n_blocks) {
+                        for (int k = 0; k < GR_BLOCK / 2 && r0 + k < n_rows; ++k)
+                            cp_async16(slot0 + uint32_t(k) * ring_pitch, col + (unsigned long long)(uint32_t(s_row[r0 + k])) * stride_b);
+                    }
+                } else {
+                    const int r0 = b * GR_BLOCK;
+                    const uint32_t slot0 = my_ring + uint32_t(r0 % GR_RING) * ring_pitch;
+                    if (b < n_full) {
+#pragma unroll
+                        for (int k4 = 0; k4 < GR_BLOCK; k4 += 4) {
+                            const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
+                            cp_async8(slot0 + uint32_t(k4 + 0) * ring_pitch, col + (unsigned long long)(uint32_t(rr.x)) * stride_b);
+                            cp_async8(slot0 + uint32_t(k4 + 1) * ring_pitch, col + (unsigned long long)(uint32_t(rr.y)) * stride_b);
+                            cp_async8(slot0 + uint32_t(k4 + 2) * ring_pitch, col + (unsigned long long)(uint32_t(rr.z)) * stride_b);
+                            cp_async8(slot0 + uint32_t(k4 + 3) * ring_pitch, col + (unsigned long long)(uint32_t(rr.w)) * stride_b);
+                        }
+                    } else if (b < n_blocks) {
+                        for (int k = 0; k < GR_BLOCK && r0 + k < n_rows; ++k)
+                            cp_async8(slot0 + uint32_t(k) * ring_pitch, col + (unsigned long long)(uint32_t(s_row[r0 + k])) * stride_b);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int b = 0; b < GR_INFLIGHT; ++b) issue(b);
+
+        double F[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) F[b] = 0.0;
+        BitCounter<G2_TP> c_int, c_ninfo;
+        BitCounter<G2_CP> c_ref, c_alt, c_het;
+        c_int.clear();
+        c_ninfo.clear();
+        c_ref.clear();
+        c_alt.clear();
+        c_het.clear();
+        int age_ref = 0, age_alt = 0, age_het = 0;          // blocks added since the last read-out (an 8-plane counter holds 255)
+        double w_ref, w_alt, w_het;
+        {
+            const KeyT k0 = s_key[0];
+            w_ref = __ldg(a.wtable + gs_code(k0, 0, cb));
+            w_alt = __ldg(a.wtable + gs_code(k0, 1, cb));
+            w_het = __ldg(a.wtable + gs_code(k0, 2, cb));
+        }
+        auto flush_class = [&](BitCounter<G2_CP> &c, double wt, int &age) {
+            age = 0;
+            if (c.any()) {
+                c_ninfo.add_counter(c);
+                if (wt == 1.0) c_int.add_counter(c);
+                else if (wt != 0.0) fold_counts8(c, wt, F);
+                c.clear();
+            }
+        };
+        auto add_class = [&](BitCounter<G2_CP> &c, double &wt, int &age, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, int r0) {
+            if (mask == 0u) {
+                if (age == 15) flush_class(c, wt, age);
+                c.add16(pl);
+                ++age;
+                return;
+            }
+            int k0 = 0;
+            while (true) {
+                const int k1 = mask ? __ffs(mask) - 1 : GR_BLOCK;
+                if (k1 > k0) {
+                    if (age == 15) flush_class(c, wt, age);
+                    const uint32_t rm = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
+                    uint32_t m[GR_BLOCK];
+#pragma unroll
+                    for (int k = 0; k < GR_BLOCK; ++k) m[k] = pl[k] & uint32_t(int32_t(rm << (31 - k)) >> 31);
+                    c.add16(m);
+                    ++age;
+                }
+                if (k1 >= GR_BLOCK) break;
+                flush_class(c, wt, age);
+                wt = __ldg(a.wtable + gs_code(s_key[r0 + k1], which, cb));
+                mask &= mask - 1u;
+                k0 = k1;
+            }
+        };
+        auto score_block = [&](const uint32_t (&lo)[GR_BLOCK], const uint32_t (&hi)[GR_BLOCK], int b) {
+            const unsigned long long chg = s_chg[b];
+            uint32_t pl[GR_BLOCK];
+#pragma unroll
+            for (int k = 0; k < GR_BLOCK; ++k) pl[k] = ~(lo[k] | hi[k]);
+            add_class(c_ref, w_ref, age_ref, pl, uint32_t(chg) & 0xffffu, 0, b * GR_BLOCK);
+#pragma unroll
+            for (int k = 0; k < GR_BLOCK; ++k) pl[k] = lo[k] & ~hi[k];
+            add_class(c_alt, w_alt, age_alt, pl, uint32_t(chg >> 16) & 0xffffu, 1, b * GR_BLOCK);
+            if (!SKIP_HETS) {                     // snpmatch.py:78-79: masked hets match nothing and are not informative
+#pragma unroll
+                for (int k = 0; k < GR_BLOCK; ++k) pl[k] = hi[k] & ~lo[k];
+                add_class(c_het, w_het, age_het, pl, uint32_t(chg >> 32) & 0xffffu, 2, b * GR_BLOCK);
+            }
+        };
+
+        // Every thread of the team runs the loop (threads past the row's last word compute on stale ring contents and store
+        // nothing), so that the lanes a warp holds of one team stay converged.
+        for (int b = 0; b < n_full; ++b) {
+            cp_async_wait<GR_INFLIGHT - 2>();         // block b has landed: this thread's copies ...
+            if (PAIRS) team_converge(tmask);          // ... and its neighbour's; the neighbour has also read block b-1
+            if (b > 0) issue(b + GR_INFLIGHT - 1);    // refill the slots of block b-1
+            const uint64_t *slot = ring + size_t((b * GR_BLOCK) % GR_RING) * wx + w;
+            uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
+#pragma unroll
+            for (int k = 0; k < GR_BLOCK; ++k) {
+                const uint64_t v = slot[size_t(k) * wx];
+                lo[k] = uint32_t(v);
+                hi[k] = uint32_t(v >> 32);
+            }
+            score_block(lo, hi, b);
+        }
+        if (n_full < n_blocks) {                      // ragged last block: rows past the end read as missing everywhere
+            cp_async_wait<0>();
+            if (PAIRS) team_converge(tmask);
+            const int r0 = n_full * GR_BLOCK;
+            const uint64_t *slot = ring + size_t(r0 % GR_RING) * wx + w;
+            uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
+#pragma unroll
+            for (int k = 0; k < GR_BLOCK; ++k) {
+                uint64_t v = ~0ull;
+                if (r0 + k < n_rows) v = slot[size_t(k) * wx];
+                lo[k] = uint32_t(v);
+                hi[k] = uint32_t(v >> 32);
+            }
+            score_block(lo, hi, n_full);
+        }
+        flush_class(c_ref, w_ref, age_ref);
+        flush_class(c_alt, w_alt, age_alt);
+        if (!SKIP_HETS) flush_class(c_het, w_het, age_het);
+        if (live) {
+            int32_t vi[32], vn[32];
+            counter_values9(c_int, vi);
+            counter_values9(c_ninfo, vn);
+            const int64_t o = int64_t(cur.seg) * a.a_pad + word;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                a.part_score[o + b * stride] = F[b];
+                a.part_int[o + b * stride] = vi[b] | (vn[b] << 16);
+            }
+        }
+        if (PAIRS) team_converge(tmask);              // the neighbour has read the last block: the ring may be refilled
+        // switch to the next item: its staging copies are complete (own ones: wait; the team's: barrier), claim the one after
+        cp_async_wait<0>();
+        if (nxt.seg < 0) break;
+        if (w == 0) claim(&slots[buf]);
+        team_sync();
+        cur = nxt;
+        buf ^= 1;
+    }
+}
+
+}  // namespace snpm

@@ -105,6 +105,55 @@ def group_markers(offsets, s_chrom_id, s_pos, wei, table_cap=65536):
     return GroupedSamples(offsets, chrom[:n], pos[:n], gid[:n], np.ascontiguousarray(table[:max(nt.value, 1)]), order[:n]).pack()
 
 
+class CodedSamples(object):
+    """Samples as a parser hands them over (parsers.py:141-157), ready for snpm_batch_upload_coded: markers in POSITION order,
+    chrom_pos uint32 [n] = chromosome id << 27 | position (id 31 = not in the panel), codes uint16 [n,3] = per marker the
+    index of its three weights (columns ref, het, alt as in `wei`) in wtable f64 [V].  The grouping by weight triple
+    happens on the device (csrc/group_sort.cuh)."""
+
+    def __init__(self, offsets, chrom_pos, codes, wtable):
+        self.offsets, self.chrom_pos, self.codes, self.wtable = offsets, chrom_pos, codes, wtable
+        self.n_samples = len(offsets) - 1
+
+    @property
+    def h2d_bytes(self):
+        return int(self.offsets.nbytes + self.chrom_pos.nbytes + self.codes.nbytes + self.wtable.nbytes)
+
+
+def pack_chrom_pos(s_chrom_id, s_pos):
+    """chromosome id << 27 | position (id < 0 -> 31 = not in the panel), or None when an id exceeds 30 or a position 2^27 - 1."""
+    c = np.asarray(s_chrom_id)
+    p = np.asarray(s_pos)
+    if len(c) and (int(c.max()) > 30 or int(p.min()) < 0 or int(p.max()) >= (1 << 27)):
+        return None
+    cc = np.where(c < 0, 31, c).astype(np.uint32)
+    return np.ascontiguousarray((cc << np.uint32(27)) | p.astype(np.uint32))
+
+
+def code_markers(offsets, s_chrom_id, s_pos, wei=None, codes=None, wtable=None):
+    """CodedSamples from position-order markers and either f64 weights [n,3] (dictionary-coded here with index_weights: done
+    once per sample at parse time) or ready-made codes + table (a VCF parser's integer PLs).  None when the samples do not
+    qualify (more than 65536 distinct weight values, negative / non-finite weights, ids or positions that do not fit one
+    word): score such samples in position order with the fp64 kernel."""
+    offsets = as_c(offsets, np.int64)
+    cp = pack_chrom_pos(s_chrom_id, s_pos)
+    if cp is None:
+        return None
+    if codes is None:
+        iw = index_weights(as_c(wei, np.float64).reshape(-1, 3))
+        if iw is None:
+            return None
+        codes, wtable = iw
+    wtable = as_c(wtable, np.float64)
+    if len(wtable) == 0:
+        wtable = np.zeros(1)
+    if not (np.all(np.isfinite(wtable)) and np.all(wtable >= 0.0)):
+        return None
+    codes = as_c(codes, np.uint16).reshape(-1, 3)
+    assert len(codes) == len(cp) == int(offsets[-1])
+    return CodedSamples(offsets, cp, codes, wtable)
+
+
 class SnpmError(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, "libsnpmatch_b200 error %d: %s" % (code, msg))
@@ -152,6 +201,8 @@ SIGNATURES = {
     "snpm_pack_markers": (C.c_int, [_i64, _p, _p, _p]),
     "snpm_batch_upload_grouped_runs": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i32]),
     "snpm_batch_upload_grouped_packed": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32]),
+    "snpm_batch_upload_coded": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32]),
+    "snpm_batch_coded_timings": (C.c_int, [_p, _p, C.c_int]),
     "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
     "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
     "snpm_batch_set_result_range": (C.c_int, [_p, _i64, _i64]),
@@ -398,6 +449,22 @@ class Batch(object):
         else:
             check(load().snpm_batch_upload_grouped(self._h, g.n_samples, ptr(g.offsets), ptr(g.chrom), ptr(g.pos), ptr(g.gid),
                                                    ptr(g.table), len(g.table)))
+
+    def upload_coded(self, cs):
+        """Replace the batch's samples by coded ones (CodedSamples: position order + weight codes; grouped on the device);
+        score them with run(kernel_mode=KERNEL_GROUPED)."""
+        self.n_samples = cs.n_samples
+        self.offsets = cs.offsets
+        self._keep = (cs,)
+        check(load().snpm_batch_upload_coded(self._h, cs.n_samples, ptr(cs.offsets), ptr(cs.chrom_pos), ptr(cs.codes), ptr(cs.wtable),
+                                             len(cs.wtable)))
+
+    def coded_timings(self):
+        """Device times (ms) of the last coded run: join (expansion, search, compaction), group (key sort + change masks),
+        score (k_score_grouped2), combine."""
+        ms = np.zeros(4, dtype=np.float32)
+        check(load().snpm_batch_coded_timings(self._h, ptr(ms), 4))
+        return {"join_ms": float(ms[0]), "group_ms": float(ms[1]), "score_ms": float(ms[2]), "combine_ms": float(ms[3])}
 
     def set_result_range(self, first_sample=0, n_samples=-1):
         """Epilogue, fetches and guard counts work on samples [first_sample, first_sample + n_samples) only (-1: all)."""
@@ -651,6 +718,42 @@ def score_grouped(db, offsets, s_chrom_id, s_pos, wei, skip_db_hets=False, group
         for s in flagged:
             lo, hi = int(offsets[s]), int(offsets[s + 1])
             b.upload([0, hi - lo], s_chrom_id[lo:hi], s_pos[lo:hi], wei[lo:hi])
+            b.run(skip_db_hets)
+            b.epilogue()
+            one = b.fetch()
+            for k in ("score", "matches", "ninfo", "prob", "L", "LR", "m"):
+                r[k][s] = one[k][0]
+        return r
+    finally:
+        if own:
+            b.close()
+
+
+def score_coded(db, cs, s_chrom_id=None, s_pos=None, wei=None, skip_db_hets=False, batch=None):
+    """Throughput scoring of many samples (Genotyper.genotyper per sample, snpmatch.py:207-233) from CodedSamples: join,
+    grouping by weight triple and counting all on the device.  Returns the dict of Batch.fetch() plus "rescored".  Samples
+    whose truncated score would depend on the reference's summation order (guard_counts > 0) are re-scored with the
+    order-exact fp64 kernel when their position-order arrays (s_chrom_id, s_pos, wei of the whole batch) are given."""
+    own = batch is None
+    b = batch if batch is not None else Batch(db, [0, 0], np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)))
+    try:
+        b.upload_coded(cs)
+        b.run(skip_db_hets, kernel_mode=KERNEL_GROUPED)
+        b.epilogue()
+        r = b.fetch()
+        flagged = np.flatnonzero(b.guard_counts())
+        r["rescored"] = flagged
+        offsets = cs.offsets
+        for s in flagged:
+            lo, hi = int(offsets[s]), int(offsets[s + 1])
+            if wei is None:
+                w = cs.wtable[cs.codes[lo:hi].astype(np.int64)]
+                cid = (cs.chrom_pos[lo:hi] >> np.uint32(27)).astype(np.int32)
+                cid[cid == 31] = -1
+                pp = (cs.chrom_pos[lo:hi] & np.uint32((1 << 27) - 1)).astype(np.int32)
+            else:
+                w, cid, pp = np.asarray(wei)[lo:hi], np.asarray(s_chrom_id)[lo:hi], np.asarray(s_pos)[lo:hi]
+            b.upload([0, hi - lo], cid, pp, w)
             b.run(skip_db_hets)
             b.epilogue()
             one = b.fetch()
