@@ -2,27 +2,34 @@
 """
 bench.py — SNP x accession comparisons/s of the genotype-matching hot path (BASELINE.json metric).
 
-Workload (config.workload): BASELINE configs[1] — the synthetic 1001-Genomes-shaped panel
-(1135 accessions x 10.7 M SNPs, generated in HBM) scored against low-coverage samples with PL
-weights (~50 k markers each, ~45 k of them in the panel).  One step = one pass of the hot path
-(join + chunked scoring + combine + likelihood epilogue) over one batch of `--samples` independent
-samples, each scored on its own exactly as separate `snpmatch inbred` runs would.
+Headline workload (config.workload): BASELINE configs[1] — the synthetic 1001-Genomes-shaped panel (1135 accessions x 10.7 M
+SNPs, generated in HBM) scored against low-coverage samples with PL weights (~50 k markers each, ~45 k of them in the panel).
+One step = one pass of the hot path over one batch of `--samples` independent samples, each scored on its own exactly as
+separate `snpmatch inbred` runs would, FROM WHAT A PARSER HANDS OVER: markers in position order as (chromosome, position)
+words + integer PLs as weight codes + the table exp(-PL/10).  Everything per marker happens on the device inside the step:
+expansion, (chrom, pos) join, compaction, grouping of the matched pairs by weight triple (sort), change masks, counting
+kernel, totals, truncation guard, likelihood epilogue.
 
-  value      comparisons/s with the batch already resident in HBM (device-timed, CUDA events on the
-             stream the kernels run on, max over ranks);
-  e2e        the same through the host-buffer API: per step the H2D copy of the samples from pinned
-             memory and the D2H read of scores / counts / likelihoods are inside the timed region;
-  roofline   the scoring kernel (k_score_grouped, the grouped counting kernel): algorithmic bytes per launch / its
-             CUDA-event time; the order-exact fp64 kernel (k_score_segments) is reported next to it;
-  cpu_baseline  the CPU oracle (a NumPy restatement of the reference path) on one sample, one core.
+  value      comparisons/s with the coded batch already resident in HBM (device-timed, CUDA events on the stream the kernels
+             run on, max over ranks);
+  e2e        the same through the host-buffer API: per step the H2D copy of the coded samples from pinned memory and the D2H
+             read of scores / counts / likelihoods are inside the timed region (three batches in a software pipeline);
+  e2e_api    (N = 1) `core.batch.genotype_many` on ParseInputs objects: chromosome-name mapping, marker ordering, upload, run,
+             fetch, GenotyperOutput construction — the call a user of the Python mirror makes;
+  roofline   the scoring kernel k_score_grouped2: SURVEY 8(d) algorithmic bytes per launch / its CUDA-event time;
+  cpu_baseline  the CPU oracle (a NumPy restatement of the reference path) on one sample, one core, with `parity`: the
+             oracle's integers == the GPU's for that sample (at N > 1: one sample finished by rank 0 and one by the last rank).
 
-N > 1 (torchrun): the panel is sharded by SNP-row ranges, samples are replicated, per-GPU partial
-scores/counts are summed with one reduce-scatter (a one-shot pull over peer memory, or NCCL with --reduce nccl), then every rank runs the epilogue on, and reads back, its
-share of the samples.
-The batch grows with N (samples = N x --samples) so that per-GPU work is fixed: "scaling": "weak".
+Sub-records of the same line: the order-exact fp64 kernel, called genotypes, `cross` (configs[2]), the 20 000-accession panel
+(configs[4], STRONG scaling of a fixed batch), the tensor-core batched mode (configs[3]).
 
-`--impl reference` times the reference's own CPU path (oracle port; one process per sample on all
-host cores, the way the reference is deployed) for the same metric and config.
+N > 1 (torchrun): the panel is sharded by SNP-row ranges, every rank gets the slice of every sample's markers that can match
+its rows, per-GPU partial totals are summed with one reduce-scatter (one-shot pull over peer memory, or NCCL), then every rank
+finishes (truncation guard, epilogue) and reads back its share of the samples.  The headline batch grows with N (samples =
+N x --samples: "scaling": "weak"); the configs[4] sub-record keeps its batch fixed.
+
+`--impl reference` times the reference's own CPU path (oracle port; one process per sample on all host cores, the way the
+reference is deployed) for the same metric and config.
 """
 import argparse
 import json
@@ -40,6 +47,7 @@ if ROOT not in sys.path:
 
 N_ROWS = 10_700_000
 N_ACC = 1135
+N_ACC_WIDE = 20_000
 N_DB_MARKERS = 45_000
 N_EXTRA_MARKERS = 5_000
 E2E_DEPTH = 3            # batch objects rotating in the end-to-end arm
@@ -53,13 +61,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--samples", type=int, default=64, help="samples per step and per GPU")
+    ap.add_argument("--samples", type=int, default=64, help="samples per step and per GPU (headline, weak scaling)")
+    ap.add_argument("--wide-samples", type=int, default=64, help="samples of the 20 000-accession sub-record (fixed: strong scaling)")
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--accessions", type=int, default=N_ACC)
     ap.add_argument("--markers", type=int, default=N_DB_MARKERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--group-chunk", type=int, default=320, help="rows per segment of the grouped kernel")
-    ap.add_argument("--force-exact", action="store_true", help="order-exact fp64 kernel as the headline path")
+    ap.add_argument("--headline-only", action="store_true", help="skip the sub-records (development runs)")
+    ap.add_argument("--group-chunk", type=int, default=320, help="rows per segment of the counting kernel")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl", "none"],
                     help="cross-GPU sum of the per-sample totals: p2p = one-shot reduce over peer memory (CUDA IPC over NVLink, flag barrier + "
                          "pulls in one kernel), nccl = NCCL reduce-scatter, auto = what was measured faster (p2p on 2 GPUs; NCCL beyond, "
@@ -67,7 +76,6 @@ def parse_args():
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     args = ap.parse_args()
     if args.reduce == "auto":
-        # measured: 2 GPUs 0.501 ms/step p2p vs 0.505 NCCL; 8 GPUs 0.745 p2p vs 0.720 NCCL
         args.reduce = "p2p" if int(os.environ.get("WORLD_SIZE", args.gpus)) == 2 else "nccl"
     return args
 
@@ -78,7 +86,8 @@ def workload_config(args, n_gpus, n_samples):
                     "synthetic 1001G-shaped panel %d accessions x %d SNPs" % (
                         n_samples, args.markers + N_EXTRA_MARKERS, args.markers, args.accessions, args.rows),
         "panel_rows": args.rows, "accessions": args.accessions, "samples_per_step": n_samples,
-        "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)", "kernel": "grouped counting kernel (markers ordered by weight triple at parse time)",
+        "markers_per_sample": args.markers + N_EXTRA_MARKERS, "weights": "PL (exp(-PL/10), f64)",
+        "kernel": "counting kernel k_score_grouped2 on pairs grouped by weight triple ON THE DEVICE (join -> key sort -> change masks -> scoring, every step)",
         "sharding": "single GPU" if n_gpus == 1 else "SNP-row ranges over %d GPUs + one reduce-scatter of the per-accession partials per step (%s; every rank finishes and reads back its share of the samples)" % (
             n_gpus, "one kernel over peer memory: flag barrier + 16-byte pulls through NVLink, no collective library on the path" if args.reduce == "p2p" else "NCCL"),
         "cache": "inputs larger than L2: each step gathers %.0f MB of distinct panel rows" % (
@@ -112,7 +121,7 @@ def cpu_prepare_sample(sample, n_acc, max_markers=0):
 def cpu_run_sample(positions, regions, sample, rows, codes):
     """Timed region of the CPU arm: Genotyper.genotyper of the reference (snpmatch.py:207-233) as restated by
     the oracle — the (chrom,pos) join over the database's per-row chromosome labels, then 1000-row chunks of
-    matchGTsAccs — plus the likelihood epilogue.  Returns (comparisons, seconds)."""
+    matchGTsAccs — plus the likelihood epilogue.  Returns (comparisons, seconds, score, ninfo)."""
     from oracle import snpmatch_oracle as orc
     from snpmatch_b200 import synth
     n_acc = codes.shape[1]
@@ -136,6 +145,16 @@ def cpu_run_sample(positions, regions, sample, rows, codes):
         orc.calculate_likelihoods(score.astype(np.int64), ninfo)
     dt = time.perf_counter() - t0
     return len(c0) * n_acc, dt, score, ninfo
+
+
+def oracle_parity(cpu_score, cpu_ninfo, res, i, exact_score=None):
+    """The bar of tests/test_gpu_coded.py on one sample of a bench run: integers ==, grouped fp64 scores to 1e-12, the
+    order-exact kernel's scores == (when given)."""
+    ok = bool(np.array_equal(cpu_score.astype(np.int64), res["matches"][i]) and np.array_equal(cpu_ninfo, res["ninfo"][i]) and
+              np.allclose(cpu_score, res["score"][i], rtol=1e-12, atol=0.0))
+    if exact_score is not None:
+        ok = ok and bool(np.array_equal(cpu_score, exact_score))
+    return ok
 
 
 _W = {}
@@ -245,6 +264,275 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class Ctx(object):
+    """Process-wide handles of the GPU arm."""
+    pass
+
+
+def pinned(ctx, a):
+    t = ctx.torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    ctx.keep.append(t)
+    return t.numpy()
+
+
+def rank_inputs(ctx, samples, positions, regions, r0, r1, hard=False):
+    """What this rank uploads: of every sample the slice of its markers that can fall into rows [r0, r1) (position order),
+    as pinned arrays — coded (chrom_pos words, PL codes, table) and plain (chromosome ids, positions, f64 weights)."""
+    from snpmatch_b200 import lib, sharding, synth
+    parts, slices = [], []
+    for s in samples:
+        i0, i1 = (0, len(s["pos"])) if ctx.world == 1 else sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, positions, r0, r1)
+        slices.append((i0, i1))
+        parts.append({k: s[k][i0:i1] for k in ("chr_ix", "pos", "wei", "pl", "code")})
+    offs = np.concatenate([[0], np.cumsum([len(p["pos"]) for p in parts])]).astype(np.int64)
+    chrom = np.concatenate([p["chr_ix"] for p in parts]).astype(np.int32)
+    pos = np.concatenate([p["pos"] for p in parts]).astype(np.int32)
+    if hard:                                                     # called genotypes: one-hot weights, codes into {0.0, 1.0}
+        wei = np.concatenate([synth.hard_weights(p["code"]) for p in parts])
+        codes, table = wei.astype(np.uint16), np.array([0.0, 1.0])
+    else:                                                        # the parser's integer PLs ARE the codes: no per-marker host work
+        wei = np.concatenate([p["wei"] for p in parts]).astype(np.float64)
+        pl = np.concatenate([p["pl"] for p in parts])
+        codes, table = pl.astype(np.uint16), synth.pl_table(int(pl.max()) if len(pl) else 0)
+        assert np.array_equal(table[pl], wei), "exp(-PL/10) table does not reproduce the weights bit for bit"
+    cs = lib.code_markers(offs, chrom, pos, codes=codes, wtable=table)
+    assert cs is not None
+    cs = lib.CodedSamples(pinned(ctx, cs.offsets), pinned(ctx, cs.chrom_pos), pinned(ctx, cs.codes), pinned(ctx, cs.wtable))
+    return cs, (pinned(ctx, offs), pinned(ctx, chrom), pinned(ctx, pos), pinned(ctx, wei)), slices
+
+
+def out_buffers(ctx, S_loc, n_acc, guard_len):
+    torch = ctx.torch
+    t = {k: torch.empty((S_loc, n_acc), dtype=torch.float64 if k in ("score", "prob", "L", "LR") else torch.int64).pin_memory()
+         for k in ("score", "matches", "ninfo", "prob", "L", "LR")}
+    t["m"] = torch.empty(S_loc, dtype=torch.int64).pin_memory()
+    t["guard"] = torch.zeros(guard_len, dtype=torch.int32).pin_memory()
+    ctx.keep.append(t)
+    return {k: v.numpy() for k, v in t.items()}
+
+
+def reduce_totals(ctx, b):
+    """Reduce-scatter of the per-sample totals: every rank is left with the totals of its S/world samples and finishes
+    (epilogue) and reads back only those.  p2p: one kernel that is barrier + pull over peer memory (k_reduce_peers)."""
+    from snpmatch_b200 import sharding
+    if ctx.world == 1 or ctx.args.reduce == "none":
+        return
+    if ctx.args.reduce == "p2p":
+        sharding.p2p_reduce_scatter(b)
+    else:
+        sharding.reduce_scatter_batch(b, ctx.dist, ctx.dev, ctx.rank, ctx.world)
+
+
+def run_batch(ctx, b, **kw):
+    from snpmatch_b200 import sharding
+    if ctx.world > 1 and ctx.args.reduce == "p2p":
+        sharding.p2p_before_run(b, ctx.dist, ctx.rank, ctx.world, ctx.host_pg)      # maps the peers' buffers on first use (host collective)
+    b.run(**kw)
+
+
+def barrier(ctx):
+    if ctx.world > 1:
+        ctx.dist.barrier()
+    ctx.torch.cuda.synchronize()
+
+
+def timed_steps(ctx, step, wait, warmup, steps):
+    """W untimed + K timed steps on the compute stream: barrier + synchronize on both sides, CUDA events, max over ranks."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        step()
+    wait()
+    barrier(ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ctx.stream)
+    for _ in range(steps):
+        step()
+    e1.record(ctx.stream)
+    wait()
+    barrier(ctx)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(ms, op=ctx.dist.ReduceOp.MAX)
+    return float(ms[0])
+
+
+def all_sum(ctx, vals):
+    t = ctx.torch.tensor([float(v) for v in vals], dtype=ctx.torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(t)
+    return [float(x) for x in t]
+
+
+def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, warmup, chunk, e2e=True, exact=True, hard=False):
+    """Resident and end-to-end arms of inbred scoring of `samples` against this rank's shard.  Returns a dict of numbers plus
+    `res`: the last step's results of this rank's share (for the parity checks)."""
+    from snpmatch_b200 import lib
+    torch = ctx.torch
+    db = g.db
+    world, rank = ctx.world, ctx.rank
+    S = len(samples)
+    S_loc = S // world
+    cs, plain, slices = rank_inputs(ctx, samples, positions, regions, r0, r1, hard=hard)
+    h_off, h_chr, h_pos, h_wei = plain
+    out = out_buffers(ctx, S_loc, n_acc, S_loc)
+
+    def own_share(b):
+        if world > 1:
+            b.set_result_range(rank * S_loc, S_loc)
+        return b
+
+    gb = lib.Batch(db, h_off, h_chr, h_pos, h_wei)               # position order: also the order-exact kernel's batch
+    own_share(gb)
+    r = {}
+    with torch.cuda.stream(ctx.stream):
+        # ---- the order-exact fp64 kernel on the same samples (position order), for comparison and as the bit-exact reference
+        if exact:
+            def exact_step():
+                run_batch(ctx, gb, kernel_mode=lib.KERNEL_POPCOUNT if hard else lib.KERNEL_FP64)
+                reduce_totals(ctx, gb)
+                gb.epilogue()
+            x_steps = max(2, min(steps, 5))
+            x_ms = timed_steps(ctx, exact_step, gb.wait, max(1, min(warmup, 2)), x_steps)
+            x_kernel = []
+            for _ in range(x_steps):
+                exact_step()
+                x_kernel.append(gb.timings()["score_ms"])
+            r["exact_res"] = {k: v.copy() for k, v in gb.fetch().items()}
+            r["exact_ms_per_step"] = x_ms / x_steps
+            r["exact_kernel_ms"] = float(np.mean(x_kernel))
+        # ---- resident arm: the coded samples are on the device; every step does all the per-marker work again
+        gb.set_group_chunk(chunk)
+        gb.upload_coded(cs)
+
+        def device_step():
+            run_batch(ctx, gb, kernel_mode=lib.KERNEL_GROUPED)
+            reduce_totals(ctx, gb)
+            gb.epilogue()
+        dev_ms = timed_steps(ctx, device_step, gb.wait, warmup, steps)
+        stage = {}
+        for _ in range(steps):                                   # one more pass that reads the library's own events each step
+            device_step()
+            for k, v in gb.coded_timings().items():
+                stage.setdefault(k, []).append(v)
+            t = gb.timings()
+            stage.setdefault("epilogue_ms", []).append(t["epilogue_ms"])
+            launches = t["launches"]
+        r.update(dev_ms_per_step=dev_ms / steps, stages_ms={k: float(np.mean(v)) for k, v in stage.items()}, launches=int(launches))
+        guard_resident = gb.guard_counts()
+        gb.fetch(out={k: out[k] for k in ("score", "matches", "ninfo", "prob", "L", "LR", "m")})
+        r["res"] = {k: v.copy() for k, v in out.items()}
+        r["res"]["guard"] = guard_resident.copy()
+        r["guard_flagged_local"] = int((guard_resident > 0).sum())
+        barrier(ctx)
+        # ---- end-to-end arm: pinned host buffers in, pinned host buffers out, every step
+        if e2e:
+            batches = [gb]
+            for _ in range(E2E_DEPTH - 1):
+                bx = lib.Batch(db, h_off[:2] * 0, h_chr[:0], h_pos[:0], h_wei[:0])
+                bx.set_group_chunk(chunk)
+                batches.append(bx)
+            outs = [out] + [out_buffers(ctx, S_loc, n_acc, S_loc) for _ in range(E2E_DEPTH - 1)]
+            host_s = {"upload": 0.0, "launch": 0.0, "wait": 0.0}
+            rescored = [0]
+
+            def timed_call(key, fn, *a):
+                t_ = time.perf_counter()
+                v_ = fn(*a)
+                host_s[key] += time.perf_counter() - t_
+                return v_
+
+            def up(bt):
+                bt.upload_coded(cs)                              # 10 bytes per marker from pinned memory, on the batch's copy stream
+                own_share(bt)
+
+            def launch(k):
+                b_ = batches[k % E2E_DEPTH]
+                run_batch(ctx, b_, kernel_mode=lib.KERNEL_GROUPED)
+                reduce_totals(ctx, b_)
+                b_.epilogue()
+                b_.fetch_async(outs[k % E2E_DEPTH])              # D2H of step k, queued behind its kernels
+
+            flagged_all = []
+
+            def finish(k):
+                res = batches[k % E2E_DEPTH].fetch_wait()        # results of step k (this rank's share) are on the host
+                fl = np.flatnonzero(res["guard"])                # int(score) needs the reference's summation order (~1e-4 per sample)
+                if world == 1:
+                    for sidx in fl:
+                        lo, hi = int(h_off[sidx]), int(h_off[sidx + 1])
+                        one = db.scratch_batch([0, hi - lo], h_chr[lo:hi], h_pos[lo:hi], h_wei[lo:hi])
+                        one.run()
+                        one.epilogue()
+                        r1_ = one.fetch()
+                        for key in r1_:
+                            res[key][sidx] = r1_[key][0]
+                        rescored[0] += 1
+                else:
+                    flagged_all.extend(int(x) for x in fl)       # re-scoring is a collective job: counted, and reported below
+                return res
+
+            def run_pipeline(n):
+                """n complete steps, each from the upload of its samples to its results on the host."""
+                for key in host_s:
+                    host_s[key] = 0.0
+                for j in range(min(E2E_DEPTH, n)):
+                    timed_call("upload", up, batches[j])
+                for j in range(min(E2E_DEPTH - 1, n)):
+                    timed_call("launch", launch, j)
+                res = None
+                for k in range(n):
+                    if k + E2E_DEPTH - 1 < n:
+                        timed_call("launch", launch, k + E2E_DEPTH - 1)
+                    res = timed_call("wait", finish, k)
+                    if k + E2E_DEPTH < n:
+                        timed_call("upload", up, batches[k % E2E_DEPTH])
+                return res
+
+            run_pipeline(max(warmup, 1))
+            barrier(ctx)
+            rescored[0] = 0
+            del flagged_all[:]
+            t0 = time.perf_counter()
+            run_pipeline(steps)                                  # includes filling the pipeline: the first upload overlaps nothing
+            barrier(ctx)
+            e2e_s = time.perf_counter() - t0
+            e2e_ms = torch.tensor([e2e_s * 1e3], dtype=torch.float64, device=ctx.dev)
+            if world > 1:
+                ctx.dist.all_reduce(e2e_ms, op=ctx.dist.ReduceOp.MAX)
+            r.update(e2e_ms_per_step=float(e2e_ms[0]) / steps, host_ms_per_step={k: 1e3 * v / steps for k, v in host_s.items()},
+                     h2d_bytes=int(cs.h2d_bytes), d2h_bytes=int(sum(v.nbytes for v in out.values())),
+                     rescored=int(rescored[0]), flagged_e2e=len(flagged_all))
+            for bx in batches[1:]:
+                bx.close()
+    m_tot, flagged = all_sum(ctx, [float(r["res"]["m"].astype(np.int64).sum()), float(r["guard_flagged_local"])])
+    r["m_total"] = int(m_tot)
+    r["guard_flagged_samples"] = int(flagged)
+    r["local_rows"] = int(sum(int(((s["rows"] >= r0) & (s["rows"] < r1)).sum()) for s in samples))
+    r["n_weights"] = int(len(cs.wtable))
+    r["batch"] = gb
+    r["slices"] = slices
+    return r
+
+
+def gather_last_rank_sample(ctx, res, i_local):
+    """Rank 0 receives (matches, ninfo, score) of local sample i_local of the LAST rank (host collective over gloo)."""
+    payload = None
+    if ctx.rank == ctx.world - 1:
+        payload = {k: res[k][i_local].copy() for k in ("matches", "ninfo", "score")}
+    box = [None] * ctx.world
+    ctx.dist.all_gather_object(box, payload, group=ctx.host_pg)
+    return box[ctx.world - 1]
+
+
+def roofline(peak, algo_bytes, kernel_ms, kernel, extra=None):
+    ach = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    d = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+         "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": kernel_ms}
+    if extra:
+        d.update(extra)
+    return d
+
+
 def run_b200_arm(args):
     import torch
     import __graft_entry__ as ge
@@ -252,452 +540,89 @@ def run_b200_arm(args):
     from snpmatch_b200 import lib, sharding, synth
     from snpmatch_b200.core import snp_genotype
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx = Ctx()
+    ctx.args, ctx.torch, ctx.keep = args, torch, []
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
+    ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert lib.device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
-    dist = None
+    ctx.dist = ctx.host_pg = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        host_pg = dist.new_group(backend="gloo")      # host-side agreement on the (rare) samples to re-score: must not queue behind kernels
-    dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.Stream(device=dev)
+        ctx.dist = dist
+        ctx.host_pg = dist.new_group(backend="gloo")     # host-side exchanges must not queue behind kernels
+    ctx.dev = torch.device("cuda", local_rank)
+    ctx.stream = torch.cuda.Stream(device=ctx.dev)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
 
     n_rows, n_acc = args.rows, args.accessions
     S = args.samples * world
     positions, regions = synth.panel_positions(n_rows)
     r0, r1 = sharding.shard_rows(n_rows, world, rank)
     g = snp_genotype.Genotype.synthetic(n_rows, n_acc, row_range=(r0, r1), device=local_rank)
-    db = g.db
-    db.set_stream(stream.cuda_stream)
+    g.db.set_stream(ctx.stream.cuda_stream)
     samples = make_samples(positions, regions, n_acc, S, args.markers)
-    # a rank only needs the markers that can fall into its row range (constant per-GPU join work and H2D bytes)
-    parts = samples
-    slices = [(0, len(s["pos"])) for s in samples]
-    if world > 1:
-        parts, slices = [], []
-        for s in samples:
-            i0, i1 = sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, positions, r0, r1)
-            parts.append({k: s[k][i0:i1] for k in ("chr_ix", "pos", "wei")})
-            slices.append((i0, i1))
-    offs = np.concatenate([[0], np.cumsum([len(s["pos"]) for s in parts])]).astype(np.int64)
-    n_tot = int(offs[-1])
-
-    def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t, t.numpy()
-
-    keep = []
-    arrs = []
-    for a in (offs, np.concatenate([s["chr_ix"] for s in parts]).astype(np.int32),
-              np.concatenate([s["pos"] for s in parts]).astype(np.int32),
-              np.concatenate([s["wei"] for s in parts]).astype(np.float64)):
-        t, v = pinned(a)
-        keep.append(t)
-        arrs.append(v)
-    h_off, h_chr, h_pos, h_wei = arrs
-    S_loc = S // world                                 # samples whose results this rank finishes and reads back
-    out_t = {k: torch.empty((S_loc, n_acc), dtype=torch.float64 if k in ("score", "prob", "L", "LR") else torch.int64).pin_memory()
-             for k in ("score", "matches", "ninfo", "prob", "L", "LR")}
-    out_t["m"] = torch.empty(S_loc, dtype=torch.int64).pin_memory()
-    out = {k: v.numpy() for k, v in out_t.items()}
-
-    batch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)       # position order: the order-exact fp64 kernel
-    # grouped order (done once, at parse time): markers of every sample ordered by weight triple -> counting kernel
-    t_group = time.perf_counter()
-    gs_raw = lib.group_markers(h_off, h_chr, h_pos, h_wei)
-    t_group = time.perf_counter() - t_group
-    assert gs_raw is not None, "the synthetic PL weights qualify for the grouped kernel"
-    g_arrs = []
-    for a in (gs_raw.chrom, gs_raw.pos, gs_raw.gid, gs_raw.table, gs_raw.packed, gs_raw.run_gid, gs_raw.run_end):
-        if a is None:
-            g_arrs.append(None)
-            continue
-        t, v = pinned(a)
-        keep.append(t)
-        g_arrs.append(v)
-    gs = lib.GroupedSamples(h_off, g_arrs[0], g_arrs[1], g_arrs[2], g_arrs[3], gs_raw.order, packed=g_arrs[4], run_gid=g_arrs[5], run_end=g_arrs[6])
-    if os.environ.get("SNPM_BENCH_NO_RUNS"):           # experiment: ids as one uint16 per marker (6 bytes per marker) instead of runs
-        gs.run_gid = gs.run_end = None
-    gbatch = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
-    gbatch.set_group_chunk(args.group_chunk)
-    gbatch.upload_grouped(gs)
-
-    # Row sharding cuts every weight group into `world` pieces, which makes the counter read-outs more frequent; measured at
-    # 4 and 8 GPUs the grouped kernel still wins (1.6e13 vs 1.2e13, 2.9e13 vs 2.3e13), so it is the headline path everywhere.
-    rows_per_group = args.markers / float(world) / max(1, len(np.unique(samples[0]["wei"], axis=0)))
-    use_grouped = not args.force_exact
-
-    def reduce_totals(b):
-        # reduce-scatter of the per-sample totals: every rank is left with the totals of its S/world samples and finishes
-        # (epilogue) and reads back only those.  p2p: one kernel that is barrier + pull over peer memory (k_reduce_peers)
-        if args.reduce == "p2p":
-            sharding.p2p_reduce_scatter(b)
-        elif args.reduce == "none":
-            pass
-        else:
-            sharding.reduce_scatter_batch(b, dist, dev, rank, world)
-
-    def run_batch(b, **kw):
-        if world > 1 and args.reduce == "p2p":
-            sharding.p2p_before_run(b, dist, rank, world, host_pg)      # maps the peers' buffers on first use (host collective)
-        b.run(**kw)
-
-    def own_share(b):
-        if world > 1:
-            b.set_result_range(rank * S_loc, S_loc)
-        return b
-
-    own_share(batch)
-    own_share(gbatch)
-
-    def device_step(b=None, mode=None):
-        b = (gbatch if use_grouped else batch) if b is None else b
-        run_batch(b, kernel_mode=lib.KERNEL_GROUPED if b is gbatch else lib.KERNEL_FP64)
-        if world > 1:
-            reduce_totals(b)
-        b.epilogue()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    score_ms, total_launches = [], 0
-    with torch.cuda.stream(stream):
-        # ---- resident arm -------------------------------------------------------------------------
-        head = gbatch if use_grouped else batch
-        for _ in range(args.warmup):
-            device_step()
-        head.wait()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()                        # before the barrier: forking nvidia-smi takes ~1 ms, which the other ranks would
-        barrier()                                  # otherwise spend waiting for rank 0 inside the first timed step
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            device_step()
-        ev1.record(stream)
-        head.wait()
-        barrier()
-        dev_ms = ev0.elapsed_time(ev1)
-        # per-kernel times of the scoring kernel: one more timed pass that reads the library's own events each step
-        stage_ms = {}
-        for _ in range(args.steps):
-            device_step()
-            t = head.timings()
-            score_ms.append(t["score_ms"])
-            for k, v in t.items():
-                stage_ms.setdefault(k, []).append(v)
-            total_launches = t["launches"]
-        guard_resident = head.guard_counts()
-        barrier()
-        # ---- the order-exact fp64 kernel on the same samples (position order), for comparison
-        exact_kernel_ms = []
-        for _ in range(args.warmup):
-            device_step(batch)
-        batch.wait()
-        barrier()
-        xv0, xv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        xv0.record(stream)
-        for _ in range(args.steps):
-            device_step(batch)
-        xv1.record(stream)
-        batch.wait()
-        barrier()
-        exact_ms = xv0.elapsed_time(xv1)
-        for _ in range(args.steps):
-            device_step(batch)
-            exact_kernel_ms.append(batch.timings()["score_ms"])
-        exact_res = {k: v.copy() for k, v in batch.fetch().items()}
-        barrier()
-        # ---- called-genotype variant of the same samples (0/1 weights, as BED / GT-only VCF inputs give): popcount kernel
-        hard = lib.Batch(db, h_off, h_chr, h_pos, np.concatenate([synth.hard_weights(s["code"][:len(p["pos"])] if world == 1 else
-                                                                                     s["code"][sl[0]:sl[1]])
-                                                                  for s, p, sl in zip(samples, parts, slices)]))
-        own_share(hard)
-        hard_ms, hard_kernel_ms = 0.0, []
-
-        def hard_step():
-            run_batch(hard, kernel_mode=lib.KERNEL_POPCOUNT)
-            if world > 1:
-                reduce_totals(hard)
-            hard.epilogue()
-        for _ in range(args.warmup):
-            hard_step()
-        hard.wait()
-        barrier()
-        hv0, hv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        hv0.record(stream)
-        for _ in range(args.steps):
-            hard_step()
-        hv1.record(stream)
-        hard.wait()
-        barrier()
-        hard_ms = hv0.elapsed_time(hv1)
-        for _ in range(args.steps):
-            hard_step()
-            hard_kernel_ms.append(hard.timings()["score_ms"])
-        hard_res = hard.fetch()
-        # ... and through the grouped counting kernel (three weight groups per sample: pure counting, no fp64 at all)
-        hard_wei = np.concatenate([synth.hard_weights(s["code"][:len(p["pos"])] if world == 1 else s["code"][sl[0]:sl[1]])
-                                   for s, p, sl in zip(samples, parts, slices)])
-        hard_gs = lib.group_markers(h_off, h_chr, h_pos, hard_wei)
-        hard.set_group_chunk(args.group_chunk)
-        hard.upload_grouped(hard_gs)
-
-        def hardg_step():
-            run_batch(hard, kernel_mode=lib.KERNEL_GROUPED)
-            if world > 1:
-                reduce_totals(hard)
-            hard.epilogue()
-        for _ in range(args.warmup):
-            hardg_step()
-        hard.wait()
-        barrier()
-        gv0, gv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gv0.record(stream)
-        for _ in range(args.steps):
-            hardg_step()
-        gv1.record(stream)
-        hard.wait()
-        barrier()
-        hardg_ms = gv0.elapsed_time(gv1)
-        hardg_kernel_ms = []
-        for _ in range(args.steps):
-            hardg_step()
-            hardg_kernel_ms.append(hard.timings()["score_ms"])
-        hardg_res = hard.fetch()
-        hard_same = all(np.array_equal(hardg_res[k], hard_res[k], equal_nan=True) for k in ("score", "matches", "ninfo", "m", "L", "LR"))
-        hard.close()
-        barrier()
-        # ---- end-to-end arm: host buffers in, host buffers out -------------------------------------
-        # Every step uploads its inputs from pinned host memory (on the batch's own copy stream) and reads its results back.
-        # E2E_DEPTH batch objects rotate.  One batch's cycle is upload (0.36 ms at 53 GB/s) -> kernels (0.43) -> read-back (0.07) ->
-        # the host sees the results and uploads again; with two batches that cycle (1.1 ms with host latencies) bounds the step at
-        # 0.56 ms, with three the kernels do.
-        extra = []
-        for _ in range(E2E_DEPTH - 1):
-            bx = lib.Batch(db, h_off, h_chr, h_pos, h_wei)
-            bx.set_group_chunk(args.group_chunk)
-            own_share(bx)
-            extra.append(bx)
-        pair = [gbatch] + extra
-        rescored = [0]
-
-        coded = None if use_grouped else lib.index_weights(h_wei)
-        if coded is not None:
-            idx_t, h_idx = pinned(coded[0])
-            tab_t, h_tab = pinned(coded[1])
-            keep.extend([idx_t, tab_t])
-
-        skip_part = os.environ.get("SNPM_E2E_SKIP", "")    # timing experiments: leave the upload or the read-back out of the steady state
-        primed = set()
-
-        def up(bt):
-            if skip_part == "upload" and id(bt) in primed:
-                return
-            primed.add(id(bt))
-            if use_grouped:
-                bt.upload_grouped(gs)                        # ~4.1 bytes per marker
-            elif coded is not None:
-                bt.upload_indexed(h_off, h_chr, h_pos, h_idx, h_tab)      # 14 bytes per marker
-            else:
-                bt.upload(h_off, h_chr, h_pos, h_wei)
-
-        # software pipeline over the rotating batches: while step k's results travel to the host and the host looks at them, the
-        # kernels of the next steps are already queued and the samples of step k+depth are being copied in.  Every step still
-        # uploads its own inputs (pinned host arrays) and reads back its own results (pinned host arrays) inside the timed region.
-        outs = [dict(out)]
-        for _ in range(E2E_DEPTH - 1):
-            ot = {k: torch.empty_like(v).pin_memory() for k, v in out_t.items()}
-            keep.append(ot)
-            outs.append({k: v.numpy() for k, v in ot.items()})
-        for o in outs:
-            gt_ = torch.zeros(S, dtype=torch.int32).pin_memory()
-            keep.append(gt_)
-            o["guard"] = gt_.numpy()
-
-        def launch(k):
-            b_ = pair[k % E2E_DEPTH]
-            run_batch(b_, kernel_mode=lib.KERNEL_GROUPED if use_grouped else lib.KERNEL_FP64)
-            if world > 1:
-                reduce_totals(b_)
-            b_.epilogue()
-            if skip_part == "fetch":
-                b_.fetch_async({"m": outs[k % E2E_DEPTH]["m"], "guard": outs[k % E2E_DEPTH]["guard"]})      # the counts only (a few hundred bytes)
-            else:
-                b_.fetch_async(outs[k % E2E_DEPTH])                  # D2H of step k, queued behind its kernels
-
-        def finish(k):
-            b_ = pair[k % E2E_DEPTH]
-            r = b_.fetch_wait()                              # results of step k (this rank's share) are on the host
-            flagged = np.flatnonzero(r["guard"])             # int(score) needs the reference's summation order (~1e-4 per sample)
-            if world > 1:
-                # re-scoring a sample is a collective job (every rank holds a row range of the panel): the ranks agree on the
-                # set once, at the end of the run (resolve_flagged), instead of paying a host collective every step
-                pending.extend((k, int(rank * S_loc + sidx)) for sidx in flagged)
-            else:
-                for sidx in flagged:
-                    rescore(int(sidx), r)
-            return r
-
-        pending = []
-
-        def rescore(sidx, r=None):
-            lo, hi = int(h_off[sidx]), int(h_off[sidx + 1])
-            one = db.scratch_batch([0, hi - lo], h_chr[lo:hi], h_pos[lo:hi], h_wei[lo:hi])
-            one.run()
-            if world > 1:
-                sharding.allreduce_batch(one, dist, dev)
-            one.epilogue()
-            r1 = one.fetch()
-            if r is not None and sidx // S_loc == rank:
-                for key in r1:
-                    r[key][sidx - rank * S_loc] = r1[key][0]
-            rescored[0] += 1
-
-        def resolve_flagged(n, r):
-            """world > 1: one host collective per run; every flagged (step, sample) is re-scored by all ranks together."""
-            mask = torch.zeros((n, S), dtype=torch.int32)
-            for k, sidx in pending:
-                mask[k, sidx] = 1
-            del pending[:]
-            dist.all_reduce(mask, group=host_pg)
-            for k, sidx in zip(*np.nonzero(mask.numpy())):
-                rescore(int(sidx), r if int(k) == n - 1 else None)
-
-        host_s = {"upload": 0.0, "launch": 0.0, "wait": 0.0}
-
-        def timed_call(key, fn, *a):
-            t_ = time.perf_counter()
-            r_ = fn(*a)
-            host_s[key] += time.perf_counter() - t_
-            return r_
-
-        def run_pipeline(n):
-            """n complete steps, each from the upload of its samples to its results on the host."""
-            for key in host_s:
-                host_s[key] = 0.0
-            for j in range(min(E2E_DEPTH, n)):
-                timed_call("upload", up, pair[j])            # samples of steps 0 .. depth-1
-            for j in range(min(E2E_DEPTH - 1, n)):
-                timed_call("launch", launch, j)              # depth-1 steps queued on the GPU ahead of the host
-            r = None
-            for k in range(n):
-                if k + E2E_DEPTH - 1 < n:
-                    timed_call("launch", launch, k + E2E_DEPTH - 1)   # its samples were uploaded when step k-1 was finished
-                r = timed_call("wait", finish, k)
-                if k + E2E_DEPTH < n:
-                    timed_call("upload", up, pair[k % E2E_DEPTH])     # H2D of step k+depth into the buffers step k has released
-            if world > 1:
-                resolve_flagged(n, r)
-            return r
-
-        run_pipeline(max(args.warmup, 1))
-        barrier()
-        rescored[0] = 0
-        t0 = time.perf_counter()
-        last = run_pipeline(args.steps)                      # includes filling the pipeline: the first upload overlaps nothing
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        for key in out:
-            if key in last:
-                out[key][...] = last[key]
-        if use_grouped:
-            h2d_bytes = gs.h2d_bytes
-        else:
-            h2d_bytes = h_off.nbytes + h_chr.nbytes + h_pos.nbytes + (h_idx.nbytes + h_tab.nbytes if coded is not None else h_wei.nbytes)
-        clocks = sampler.stop() if rank == 0 else None
-
-    m_sum = torch.tensor([float(out["m"].astype(np.int64).sum()), float((guard_resident > 0).sum())], dtype=torch.float64, device=dev)
-    tms = torch.tensor([dev_ms, e2e_s * 1e3, hard_ms, exact_ms, hardg_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(m_sum)
-    dev_ms, e2e_ms, hard_ms, exact_ms, hardg_ms = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3]), float(tms[4])
-
+    sampler = ClockSampler(local_rank)
     if rank == 0:
-        m_total = int(m_sum[0])
-        comps = m_total * n_acc
-        value = comps * args.steps / (dev_ms * 1e-3)
-        e2e_value = comps * args.steps / (e2e_ms * 1e-3)
-        # roofline of the scoring kernel on this rank: its share of the matched rows
-        m_rank = m_total if world == 1 else None
-        local_rows = None
-        if world > 1:
-            local_rows = sum(int(((s["rows"] >= r0) & (s["rows"] < r1)).sum()) for s in samples)
-        rows_here = m_total if world == 1 else local_rows
-        algo_bytes = rows_here * ((n_acc + 3) // 4 + 24) + 16 * n_acc * S
-        k_ms = float(np.mean(score_ms))
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        sampler.start()
+    h = measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, args.steps, args.warmup, args.group_chunk)
+    clocks = sampler.stop() if rank == 0 else None
+    comps = h["m_total"] * n_acc
+    line = None
+    if rank == 0:
+        value = comps / (h["dev_ms_per_step"] * 1e-3)
+        algo_bytes = h["local_rows"] * ((n_acc + 3) // 4 + 24) + 16 * n_acc * S
+        k_ms = h["stages_ms"]["score_ms"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": h["dev_ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, S),
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "host_ms_per_step": {k: 1e3 * v / args.steps for k, v in host_s.items()},
-                    "h2d_bytes_per_step": int(world * h2d_bytes),
-                    "d2h_bytes_per_step": int(world * (sum(v.nbytes for v in out.values()) + 4 * S_loc)),
-                    "inputs": "pinned host arrays in grouped order (snpm_group_markers, once at parse time: %.0f ms for the batch): "
-                              "chromosome id and position in one uint32 per marker, weight-triple ids run-length coded (uint16 id + uint32 end per run; 4.1 bytes per marker) + the table of distinct triples "
-                              "(f64); three batches rotate in a software pipeline (H2D of step k+3 and D2H of step k overlap the kernels "
-                              "of steps k+1 and k+2; filling the pipeline is inside the timed region); the D2H holds scores, counts, "
-                              "likelihoods and the per-sample guard counts" % (1e3 * t_group),
-                    "samples_rescored_in_reference_order": int(rescored[0])},
-            "gpu_launches": int(total_launches * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "k_score_grouped" if use_grouped else "k_score_segments", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this command
-                         # (profiles/r1c_score_grouped_ncu_full.txt); only valid for the default single-GPU workload
-                         "traffic": 1205027000 if (use_grouped and world == 1 and S == 64 and n_rows == N_ROWS and n_acc == N_ACC
-                                                   and args.markers == N_DB_MARKERS) else None,
-                         "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": k_ms,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-            "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items() if k.endswith("_ms")},
-            "distinct_weight_triples": int(len(gs.table)), "group_chunk_rows": int(args.group_chunk),
-            "headline_kernel": "grouped counting kernel" if use_grouped else "order-exact fp64 kernel (row sharding leaves %.1f rows per weight group and rank)" % rows_per_group,
-            "guard_flagged_samples": int(m_sum[1]),
-            "clocks": clocks,
-            "matched_markers_per_step": m_total,
+            "e2e": {"value": comps / (h["e2e_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": h["e2e_ms_per_step"],
+                    "host_ms_per_step": h["host_ms_per_step"],
+                    "h2d_bytes_per_step": int(world * h["h2d_bytes"]), "d2h_bytes_per_step": int(world * h["d2h_bytes"]),
+                    "untimed_per_sample_host_work": "none: the timed region starts from the parser's arrays",
+                    "inputs": "pinned host arrays as a parser hands them over, markers in position order: chromosome id and position in one "
+                              "uint32, the three integer PLs of a marker as uint16 weight codes (10 bytes per marker), + the table exp(-PL/10) "
+                              "(%d f64); join, grouping by weight triple and scoring all happen on the device inside the step; three batches rotate "
+                              "in a software pipeline (H2D of step k+3 and D2H of step k overlap the kernels of steps k+1 and k+2; filling the "
+                              "pipeline is inside the timed region); the D2H holds scores, counts, likelihoods and the per-sample guard "
+                              "counts" % h["n_weights"],
+                    "samples_rescored_in_reference_order": h["rescored"], "flagged_not_rescored_multi_gpu": h["flagged_e2e"]},
+            "gpu_launches": int(h["launches"] * args.steps),
+            "roofline": roofline(peak, algo_bytes, k_ms, "k_score_grouped2", {
+                "traffic": None, "traffic_source": "profiles/r2_score_grouped2_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload at N=1)",
+                "peak_source": peak_source, "rows_gathered_per_launch": h["local_rows"]}),
+            "stages_ms": h["stages_ms"], "distinct_weight_values": h["n_weights"], "group_chunk_rows": int(args.group_chunk),
+            "headline_kernel": "k_score_grouped2 (counting kernel, device-grouped pairs)",
+            "guard_flagged_samples": h["guard_flagged_samples"], "clocks": clocks, "matched_markers_per_step": h["m_total"],
         }
-        # the same samples as called genotypes (0/1 weights): popcount kernel, bound by the HBM row gather
-        hk_ms = float(np.mean(hard_kernel_ms))
-        h_bytes = rows_here * ((n_acc + 3) // 4 + 5) + 12 * ((n_acc + 63) // 64 * 64) * int(np.ceil(args.markers / 1000.0)) * S
-        h_ach = h_bytes / (hk_ms * 1e-3) / 1e9 if hk_ms > 0 else 0.0
-        hgk_ms = float(np.mean(hardg_kernel_ms))
-        hg_ach = h_bytes / (hgk_ms * 1e-3) / 1e9 if hgk_ms > 0 else 0.0
-        line["called_genotypes"] = {
-            "workload": "same batch with one-hot weights (BED / GT-only VCF inputs): grouped counting kernel (three weight groups per sample)",
-            "value": comps * args.steps / (hardg_ms * 1e-3), "unit": UNIT, "ms_per_step": hardg_ms / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_score_grouped", "achieved": hg_ach, "peak": peak, "unit": "GB/s",
-                         "frac": hg_ach / peak if peak else None, "algorithmic_bytes_per_launch": int(h_bytes), "kernel_ms": hgk_ms},
-            "popcount_kernel": {"kernel": "k_score_hard (position order, no host preparation)", "value": comps * args.steps / (hard_ms * 1e-3),
-                                "ms_per_step": hard_ms / args.steps, "kernel_ms": hk_ms, "frac": h_ach / peak if peak else None,
-                                "identical_results": bool(hard_same)}}
-        xk_ms = float(np.mean(exact_kernel_ms))
-        x_ach = algo_bytes / (xk_ms * 1e-3) / 1e9 if xk_ms > 0 else 0.0
-        ok = guard_resident == 0
+        x_ach_bytes = algo_bytes
         line["order_exact_fp64"] = {
             "workload": "same batch in position order, fp64 kernel k_score_segments (sums in the reference's order: fp64 scores bit-identical)",
-            "value": comps * args.steps / (exact_ms * 1e-3), "unit": UNIT, "ms_per_step": exact_ms / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_score_segments", "achieved": x_ach, "peak": peak, "unit": "GB/s",
-                         "frac": x_ach / peak if peak else None, "kernel_ms": xk_ms},
-            "grouped_vs_exact": {"matches_equal": bool(np.array_equal(out["matches"][ok], exact_res["matches"][ok])),
-                                 "ninfo_equal": bool(np.array_equal(out["ninfo"], exact_res["ninfo"])),
-                                 "score_max_rel_diff": float(np.max(np.abs(out["score"] - exact_res["score"]) / np.maximum(exact_res["score"], 1.0))),
-                                 "LR_max_rel_diff": float(np.nanmax(np.abs(out["LR"][ok] - exact_res["LR"][ok]) / np.abs(exact_res["LR"][ok])))}}
-        if not args.no_cpu_baseline and world == 1:
+            "value": comps / (h["exact_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": h["exact_ms_per_step"],
+            "roofline": roofline(peak, x_ach_bytes, h["exact_kernel_ms"], "k_score_segments")}
+    # ---- grouped vs order-exact on this rank's share, and the CPU oracle ------------------------------------------------
+    ok = h["res"]["guard"] == 0
+    gve = [float(np.array_equal(h["res"]["matches"][ok], h["exact_res"]["matches"][ok])), float(np.array_equal(h["res"]["ninfo"], h["exact_res"]["ninfo"]))]
+    agree = all_sum(ctx, gve)
+    rel = float(np.max(np.abs(h["res"]["score"] - h["exact_res"]["score"]) / np.maximum(h["exact_res"]["score"], 1.0))) if len(h["res"]["m"]) else 0.0
+    if rank == 0:
+        line["order_exact_fp64"]["grouped_vs_exact"] = {"matches_equal_on_all_ranks": agree[0] == world, "ninfo_equal_on_all_ranks": agree[1] == world,
+                                                         "score_max_rel_diff_rank0": rel}
+    if not args.no_cpu_baseline:
+        last = gather_last_rank_sample(ctx, h["res"], len(h["res"]["m"]) - 1) if world > 1 else None
+        last_exact = gather_last_rank_sample(ctx, h["exact_res"], len(h["res"]["m"]) - 1) if world > 1 else None
+        if rank == 0:
             s0 = samples[0]
             rows, codes = cpu_prepare_sample(s0, n_acc, args.cpu_markers)
             c, dt, cpu_score, cpu_ninfo = cpu_run_sample(positions, regions, s0, rows, codes)
@@ -706,35 +631,208 @@ def run_b200_arm(args):
                                               "database labels + chunked matchGTsAccs + likelihoods, NumPy oracle port of "
                                               "snpmatch.py:207-233, database rows held in RAM as int8" % (len(rows), n_acc, n_rows)}
             if not args.cpu_markers:
-                # integers bit-exact (matches = int(score), informative sites); fp64 scores of the grouped kernel to 1e-12
-                line["cpu_baseline"]["parity"] = bool(np.array_equal(cpu_score.astype(np.int64), out["matches"][0]) and
-                                                      np.array_equal(cpu_ninfo, out["ninfo"][0]) and
-                                                      np.allclose(cpu_score, out["score"][0], rtol=1e-12, atol=0.0) and
-                                                      np.array_equal(cpu_score, exact_res["score"][0]))
+                par = {"sample_0_finished_by_rank_0": oracle_parity(cpu_score, cpu_ninfo, h["res"], 0, h["exact_res"]["score"][0])}
+                if world > 1:
+                    sl = samples[S - 1]
+                    rows_l, codes_l = cpu_prepare_sample(sl, n_acc, 0)
+                    _, _, ls, ln = cpu_run_sample(positions, regions, sl, rows_l, codes_l)
+                    par["sample_%d_finished_by_rank_%d" % (S - 1, world - 1)] = oracle_parity(
+                        ls, ln, {k: last[k][None] for k in last}, 0, last_exact["score"])
+                line["cpu_baseline"]["parity"] = bool(all(par.values()))
+                line["cpu_baseline"]["parity_detail"] = par
+                line["cpu_baseline"]["parity_bar"] = "integers (matches = int(score), informative sites) ==; counting-kernel fp64 scores rtol 1e-12; order-exact kernel scores =="
+    h["batch"].close()
+    extras = {}
+    if not args.headline_only:
+        extras["called_genotypes"] = sub_called(ctx, g, samples, positions, regions, r0, r1, n_acc, peak)
         if world == 1:
-            # batched shared-panel mode (BASELINE configs[3]): 4096 called-genotype samples on 20 000 shared markers as a
-            # one-hot int8 GEMM on tcgen05; device time of the GEMM kernel (operand expansion and H2D of the codes excluded)
-            rng = np.random.default_rng(9)
-            S9, K9 = 4096, 20000
-            rows9 = np.sort(rng.choice(n_rows, size=K9, replace=False))
-            codes9 = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(S9, K9), p=[0.6, 0.28, 0.02, 0.1])
-            g9 = min(db.score_shared_panel(rows9, codes9, likelihoods=False)["gemm_ms"] for _ in range(3))
-            ops9 = 2.0 * (2 * S9) * n_acc * (3 * K9)          # algorithmic int8 ops (the kernel pads A to 1280 and K-slots to 4 per row)
-            peak9 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-            line["batched_shared_panel"] = {
-                "workload": "configs[3]: %d called-genotype samples x %d shared markers vs %d accessions, one-hot int8 GEMM on tcgen05" % (S9, K9, n_acc),
-                "value": S9 * K9 * n_acc / (g9 * 1e-3), "unit": UNIT, "gemm_ms": g9,
-                "roofline": {"bound": "tensor", "kernel": "k_onehot_gemm", "achieved": ops9 / (g9 * 1e-3) / 1e12, "peak": peak9, "unit": "TOP/s (int8)",
-                             "frac": ops9 / (g9 * 1e-3) / 1e12 / peak9,
-                             "peak_source": "2 x measured dense bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 dense is nominally 2x bf16: 4500 vs 2250)"}}
-        print(json.dumps(line))
-    batch.close()
-    for bx in extra:
-        bx.close()
-    gbatch.close()
+            extras["e2e_api"] = sub_api(ctx, g, samples, n_acc)
+            extras["cross"] = sub_cross(ctx, g, positions, regions, n_acc)
+            extras["batched_shared_panel"] = sub_a9(ctx, g, n_rows, n_acc, peaks)
     g.close()
+    if not args.headline_only:
+        extras["panel_20k"] = sub_wide(ctx, peak, peak_source)
+    if rank == 0:
+        line.update(extras)
+        print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
+
+
+def sub_called(ctx, g, samples, positions, regions, r0, r1, n_acc, peak):
+    """The same samples as called genotypes (0/1 weights, as BED / GT-only VCF inputs give)."""
+    args = ctx.args
+    steps = max(2, min(args.steps, 5))
+    h = measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, max(1, min(args.warmup, 2)), args.group_chunk, e2e=False, hard=True)
+    same = all(np.array_equal(h["res"][k], h["exact_res"][k], equal_nan=True) for k in ("score", "matches", "ninfo", "m", "L", "LR"))
+    same_all = all_sum(ctx, [float(same)])[0] == ctx.world
+    h["batch"].close()
+    if ctx.rank != 0:
+        return None
+    comps = h["m_total"] * n_acc
+    h_bytes = h["local_rows"] * ((n_acc + 3) // 4 + 5) + 16 * n_acc * len(samples)
+    return {"workload": "same batch with one-hot weights (BED / GT-only VCF inputs): coded path (two weight values), device grouping + counting kernel",
+            "value": comps / (h["dev_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": h["dev_ms_per_step"], "stages_ms": h["stages_ms"],
+            "roofline": roofline(peak, h_bytes, h["stages_ms"]["score_ms"], "k_score_grouped2"),
+            "popcount_kernel": {"kernel": "k_score_hard (position order)", "value": comps / (h["exact_ms_per_step"] * 1e-3),
+                                "ms_per_step": h["exact_ms_per_step"], "kernel_ms": h["exact_kernel_ms"],
+                                "frac": h_bytes / (h["exact_kernel_ms"] * 1e-3) / 1e9 / peak, "identical_results_on_all_ranks": bool(same_all)}}
+
+
+def sub_api(ctx, g, samples, n_acc):
+    """`core.batch.genotype_many` on ParseInputs objects: the public call, host work included."""
+    from snpmatch_b200 import synth
+    from snpmatch_b200.core import batch, parsers
+    names = np.array(["Chr" + c for c in synth.TAIR10_CHRS])
+    inputs = []
+    for s in samples:
+        inp = parsers.ParseInputs("")
+        inp.load_snp_info(names[s["chr_ix"]], s["pos"], synth._gt_strings(s["code"]), s["wei"], s["dp"])
+        table = synth.pl_table(int(s["pl"].max()))
+        inp._coded = (s["pl"].astype(np.uint16), table, inp.wei)           # what read_vcf keeps for a VCF with integer PLs
+        inputs.append(inp)
+    ts = []
+    res = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = batch.genotype_many(g, inputs)
+        ts.append(time.perf_counter() - t0)
+    m = sum(r.num_snps for r in res)
+    for r in res[:4]:
+        r.get_likelihoods()
+    ok = all(int(np.nanargmin(r.likelis)) == (7 + 13 * i) % n_acc for i, r in enumerate(res[:4]))
+    t = float(np.median(ts))
+    return {"call": "core.batch.genotype_many(g, %d ParseInputs)" % len(inputs), "value": m * n_acc / t, "unit": UNIT, "ms_per_call": 1e3 * t,
+            "includes": "chromosome-name mapping and marker ordering per sample (host), merging the samples' PL tables, pageable H2D, device join + grouping + "
+                        "scoring + epilogue, D2H, re-scoring of flagged samples, GenotyperOutput objects", "true_accessions_recovered": bool(ok)}
+
+
+def sub_cross(ctx, g, positions, regions, n_acc):
+    """configs[2]: `snpmatch cross` device work for one PL sample: 399 windows of 300 kb + the 45 simulated F1s."""
+    from snpmatch_b200 import lib, synth
+    from snpmatch_b200.core import genomes, snpmatch
+    s = synth.make_sample_fast(positions, regions, n_acc, 7, seed=777)
+    gen = genomes.Genome("athaliana_tair10")
+    cnt, off, n_w, _ = gen.window_layout(np.array(synth.TAIR10_CHRS), 300000)
+    kmax = snpmatch.identity_kmax_table(4000, 0.02)
+    b = lib.Batch(g.db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei"])
+    res = {}
+
+    def run():
+        b.run_windows(False, 300000, cnt, off, n_w, kmax)
+        b.epilogue()
+        tot = b.fetch()
+        res["w"] = b.fetch_window_rows()             # the surviving rows, compacted on the device
+        top = np.argsort(-tot["prob"][0])[:10]
+        res["f1"] = b.f1_pairs(top)
+        res["tot"] = tot
+    for _ in range(2):
+        run()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    tm = b.timings()
+    m = int(res["tot"]["m"][0])
+    t = float(np.median(ts))
+    # window totals must equal the inbred totals of the same sample restricted to the windows' markers: the windows cover
+    # every chromosome of the genome here, so score totals == a plain inbred run (size-independent property)
+    b2 = lib.Batch(g.db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei"])
+    b2.run()
+    b2.epilogue()
+    inbred = b2.fetch()
+    same = bool(np.array_equal(inbred["ninfo"][0], res["tot"]["ninfo"][0]) and int(inbred["m"][0]) == m)
+    b2.close()
+    out = {"workload": "configs[2]: cross, %d windows of 300 kb + 45 simulated F1s, one PL sample (%d markers, %d matched) vs %d x %d" % (
+               n_w, len(s["pos"]), m, n_acc, len(positions)),
+           "value": m * n_acc / t, "unit": UNIT, "host_call_ms": 1e3 * t, "device_ms": tm["total_ms"], "score_kernel_ms": tm["score_ms"],
+           "join_ms": tm["join_ms"], "windows_with_markers": int((res["w"]["nrows"] > 0).sum()), "surviving_rows": int(len(res["w"]["acc"])),
+           "top_accession_is_true": bool(int(np.nanargmin(res["tot"]["L"][0])) == 7), "window_totals_equal_inbred_counts": same}
+    b.close()
+    return out
+
+
+def sub_a9(ctx, g, n_rows, n_acc, peaks):
+    """configs[3]: batched shared-panel mode, 4096 called-genotype samples on 20 000 shared markers as a one-hot int8 GEMM on
+    tcgen05: the GEMM kernel alone and the whole host call (operand expansion, H2D of the codes, epilogue, D2H)."""
+    rng = np.random.default_rng(9)
+    S9, K9 = 4096, 20000
+    rows9 = np.sort(rng.choice(n_rows, size=K9, replace=False))
+    codes9 = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(S9, K9), p=[0.6, 0.28, 0.02, 0.1])
+    g9, call = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r9 = g.db.score_shared_panel(rows9, codes9, likelihoods=False)
+        call.append(time.perf_counter() - t0)
+        g9.append(r9["gemm_ms"])
+    g9, call = min(g9), min(call)
+    ops9 = 2.0 * (2 * S9) * n_acc * (3 * K9)          # SURVEY 8(d): algorithmic int8 ops (the kernel pads A to 1280 and K-slots to 4 per row)
+    peak9 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+    return {"workload": "configs[3]: %d called-genotype samples x %d shared markers vs %d accessions, one-hot int8 GEMM on tcgen05" % (S9, K9, n_acc),
+            "value": S9 * K9 * n_acc / (g9 * 1e-3), "unit": UNIT, "gemm_ms": g9,
+            "e2e": {"value": S9 * K9 * n_acc / call, "unit": UNIT, "host_call_ms": 1e3 * call,
+                    "includes": "H2D of the uint8 codes (%d MB), operand expansion kernels, GEMM, totals, D2H of matches and ninfo (int64)" % (codes9.nbytes // 1000000)},
+            "roofline": {"bound": "tensor", "kernel": "k_onehot_gemm", "achieved": ops9 / (g9 * 1e-3) / 1e12, "peak": peak9, "unit": "TOP/s (int8)",
+                         "frac": ops9 / (g9 * 1e-3) / 1e12 / peak9, "scope": "GEMM kernel only (k_onehot_expand_* and the copies are in e2e)",
+                         "peak_source": "2 x measured dense bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 dense is nominally 2x bf16: 4500 vs 2250)"}}
+
+
+def sub_wide(ctx, peak, peak_source):
+    """configs[4]: the 20 000-accession panel (53.6 GB packed), SNP-row sharded over the ranks, a FIXED batch of PL samples
+    (strong scaling).  Parity: a bounded sample (3000 matched markers) against the CPU oracle, through the same sharded path."""
+    from snpmatch_b200 import lib, sharding, synth
+    from snpmatch_b200.core import snp_genotype
+    args = ctx.args
+    world, rank = ctx.world, ctx.rank
+    n_rows, n_acc = args.rows, N_ACC_WIDE
+    S = max(world, (args.wide_samples // world) * world)
+    positions, regions = synth.panel_positions(n_rows)
+    r0, r1 = sharding.shard_rows(n_rows, world, rank)
+    g = snp_genotype.Genotype.synthetic(n_rows, n_acc, row_range=(r0, r1), device=ctx.dev.index)
+    g.db.set_stream(ctx.stream.cuda_stream)
+    samples = make_samples(positions, regions, n_acc, S, args.markers, first_seed=9000)
+    steps = max(2, min(args.steps, 5))
+    h = measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, max(1, min(args.warmup, 2)), args.group_chunk, e2e=True, exact=False)
+    recovered = all(int(np.nanargmin(h["res"]["L"][i])) == (7 + 13 * (rank * (S // world) + i)) % n_acc for i in range(len(h["res"]["m"])))
+    recovered = all_sum(ctx, [float(recovered)])[0] == world
+    h["batch"].close()
+    # bounded parity sample: the first 3000 panel markers of sample 0 (+ its non-panel markers in between), all ranks together
+    s0 = samples[0]
+    cut = int(np.flatnonzero(s0["rows"] >= 0)[2999]) + 1
+    sp = {k: s0[k][:cut] for k in ("chr_ix", "pos", "wei", "pl", "code", "rows")}
+    cs, plain, _ = rank_inputs(ctx, [sp] * world, positions, regions, r0, r1)       # `world` copies: the reduce-scatter wants S % world == 0
+    pb = lib.Batch(g.db, *plain)
+    if world > 1:
+        pb.set_result_range(rank, 1)
+    pb.set_group_chunk(args.group_chunk)
+    pb.upload_coded(cs)
+    with ctx.torch.cuda.stream(ctx.stream):
+        run_batch(ctx, pb, kernel_mode=lib.KERNEL_GROUPED)
+        reduce_totals(ctx, pb)
+        pb.epilogue()
+        pres = pb.fetch()
+    parity = None
+    if rank == 0:
+        rows, codes = cpu_prepare_sample(sp, n_acc, 0)
+        _, _, cs_, cn_ = cpu_run_sample(positions, regions, sp, rows, codes)
+        parity = oracle_parity(cs_, cn_, pres, 0)
+    pb.close()
+    g.close()
+    if rank != 0:
+        return None
+    comps = h["m_total"] * n_acc
+    algo_bytes = h["local_rows"] * ((n_acc + 3) // 4 + 24) + 16 * n_acc * S
+    return {"workload": "configs[4]: %d PL samples (fixed batch: strong scaling) vs the 20 000-accession x %d panel (%.1f GB packed), SNP-row sharded over %d GPU(s)" % (
+                S, n_rows, n_rows * 5008 / 1e9, world),
+            "scaling": "strong", "value": comps / (h["dev_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": h["dev_ms_per_step"],
+            "e2e": {"value": comps / (h["e2e_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": h["e2e_ms_per_step"],
+                    "h2d_bytes_per_step": int(world * h["h2d_bytes"]), "d2h_bytes_per_step": int(world * h["d2h_bytes"])},
+            "stages_ms": h["stages_ms"], "roofline": roofline(peak, algo_bytes, h["stages_ms"]["score_ms"], "k_score_grouped2",
+                                                               {"peak_source": peak_source, "rows_gathered_per_launch": h["local_rows"]}),
+            "true_accessions_recovered_on_all_ranks": bool(recovered), "guard_flagged_samples": h["guard_flagged_samples"],
+            "parity": parity, "parity_sample": "the first 3000 panel markers of sample 0 (x 20 000 accessions) through the same sharded coded path vs the CPU oracle: "
+                                               "integers ==, scores rtol 1e-12"}
 
 
 def main():

@@ -63,7 +63,9 @@ int snpm_db_create(int device, int64_t n_rows, int32_t n_acc,
                    const int32_t *positions, const int64_t *chr_regions, int32_t n_chr,
                    int64_t row0_global, snpm_db **out);
 int snpm_db_destroy(snpm_db *db);
-/* streaming loaders: rows [row0, row0+n) of the shard, int8 [n, n_acc] C-order or packed words */
+/* streaming loaders: rows [row0, row0+n) of the shard, int8 [n, n_acc] C-order or packed words.  int8 codes: 0 ref, 1 alt,
+ * 2 het, any negative value = missing (the reference masks every value < 0, snpmatch.py:84-86); values above 2 do not occur in
+ * the reference's databases (makedb.py:59) and make the load fail with SNPM_E_RANGE (the rows may have been overwritten). */
 int snpm_db_load_int8(snpm_db *db, int64_t row0, int64_t n, const int8_t *snps);
 int snpm_db_load_packed(snpm_db *db, int64_t row0, int64_t n, const uint64_t *packed);
 /* deterministic synthetic panel generated in HBM: code = f(seed, global row, accession), the same
@@ -179,12 +181,17 @@ int snpm_batch_coded_timings(snpm_batch *b, float *ms, int n);
  * within the rounding-error bound of an integer, i.e. whose int(score) depends on the reference's own summation order
  * (probability ~1e-7 per accession).  Re-score those samples with mode 0.  All zeros for position-order batches. */
 int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts);
+/* Genotyper(chunk_size=...) (snpmatch.py:173,218): rows per chunk of the order-exact fp64 kernel (default SNPM_CHUNK_ROWS).  The
+ * reference adds chunk sums, so the chunk size is part of its floating-point summation order; takes effect at the next
+ * position-order upload.  The popcount kernel (mode 1) keeps 1000-row chunks: its integer sums do not depend on them. */
+int snpm_batch_set_chunk_rows(snpm_batch *b, int32_t rows);
 /* rows per segment of the grouped kernel (16..1008, a multiple of 8, default 320); takes effect at the next grouped or coded
  * upload (the value is latched there: buffers are sized from it) */
 int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows);
 int snpm_batch_destroy(snpm_batch *b);
 /* optional Genotyper.genotyper(filter_pos_ix=...) (snpmatch.py:211-216): keep only pairs whose
- * GLOBAL database row is in the sorted list (applies to every sample of the batch); n = 0 clears */
+ * GLOBAL database row is in the sorted list (applies to every sample of the batch).  sorted_rows == NULL clears the filter;
+ * a non-NULL list with n = 0 is an empty filter: no pair is kept (scores 0, as the reference with an empty filter_pos_ix) */
 int snpm_batch_set_row_filter(snpm_batch *b, const int64_t *sorted_rows, int64_t n);
 /* join + chunked scoring + per-sample totals; device work is queued on the db's stream and the
  * call returns without waiting (inputs already resident).

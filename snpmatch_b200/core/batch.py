@@ -48,19 +48,45 @@ def genotype_batch(g, samples, skip_db_hets=False):
     return out, {"panel_markers": len(rows), "gemm_ms": r["gemm_ms"]}
 
 
-def genotype_many(g, samples, skip_db_hets=False):
-    """Genotyper.genotyper (snpmatch.py:207-233) for MANY samples with any weights (PL likelihoods or called genotypes) in
-    one device pass: the markers of every sample are ordered by weight triple (host, `lib.group_markers`; what a parser
-    would cache next to <input>.snpmatch.npz) and scored by the counting kernel (csrc/grouped.cuh).  Returns the list of
-    GenotyperOutput, one per sample, with matches / ninfo / overlap identical to Genotyper run sample by sample and
-    likelihoods within 1e-9; samples whose int(score) would depend on the reference's summation order are re-scored by
-    the order-exact kernel inside `lib.score_grouped`."""
+def coded_batch(g, samples):
+    """lib.CodedSamples of a list of ParseInputs: every sample's markers in the order the join wants (database chromosome
+    order, position), chromosome id + position in one word, weights as dictionary codes (ParseInputs.coded_weights: the
+    integer PLs of a VCF, or a one-off np.unique for other inputs) into ONE table for the batch.  Returns (CodedSamples or
+    None, offsets, chrom ids, positions, weights) — the last three in upload order, for re-scoring flagged samples."""
     prepared = [g.prepare_markers(inp.chrs, inp.pos) for inp in samples]
     offs = np.concatenate([[0], np.cumsum([len(p[2]) for p in prepared])]).astype(np.int64)
     cid = np.concatenate([p[1] for p in prepared]) if samples else np.zeros(0, np.int32)
     pos = np.concatenate([p[2] for p in prepared]) if samples else np.zeros(0, np.int32)
     wei = np.concatenate([np.asarray(inp.wei, dtype=np.float64)[p[0]] for inp, p in zip(samples, prepared)]) if samples else np.zeros((0, 3))
-    r = lib.score_grouped(g.db, offs, cid, pos, wei, skip_db_hets=skip_db_hets)
+    coded = [inp.coded_weights() for inp in samples]
+    cs = None
+    if all(c is not None for c in coded) and samples:
+        # one table for the batch: union of the samples' tables (bit patterns), every sample's codes remapped into it
+        tables = [c[1].view(np.uint64) for c in coded]
+        union, inv = np.unique(np.concatenate(tables), return_inverse=True)
+        if len(union) <= 65536:
+            codes, at = [], 0
+            for (c, t), p in zip(coded, prepared):
+                remap = inv[at:at + len(t)].astype(np.uint16)
+                at += len(t)
+                codes.append(remap[c.astype(np.int64)][p[0]])
+            cs = lib.code_markers(offs, cid, pos, codes=np.concatenate(codes), wtable=union.view(np.float64))
+    return cs, offs, cid, pos, wei
+
+
+def genotype_many(g, samples, skip_db_hets=False):
+    """Genotyper.genotyper (snpmatch.py:207-233) for MANY samples with any weights (PL likelihoods or called genotypes) in
+    one device pass: markers go up in position order with their weights as dictionary codes (`coded_batch`), the device
+    joins them with the panel, groups the matched pairs by weight triple (csrc/group_sort.cuh) and scores them with the
+    counting kernel (csrc/grouped2.cuh).  Returns the list of GenotyperOutput, one per sample, with matches / ninfo / overlap
+    identical to Genotyper run sample by sample and likelihoods within 1e-9; samples whose int(score) would depend on the
+    reference's summation order are re-scored by the order-exact kernel inside `lib.score_coded`.  Inputs that cannot be
+    coded (more than 65536 distinct weight values, negative weights) take the order-exact kernel for every sample."""
+    cs, offs, cid, pos, wei = coded_batch(g, samples)
+    if cs is not None:
+        r = lib.score_coded(g.db, cs, cid, pos, wei, skip_db_hets=skip_db_hets, batch=getattr(g, "_many_batch", None))
+    else:
+        r = lib.score_grouped(g.db, offs, cid, pos, wei, skip_db_hets=skip_db_hets)
     out = []
     for i, inp in enumerate(samples):
         m = int(r["m"][i])

@@ -185,7 +185,7 @@ class Genotyper(object):
 
     def __init__(self, inputs, g, outFile, run_genotyper=True, skip_db_hets=False, chunk_size=1000):
         assert type(g) is snp_genotype.Genotype, "provide a snp_genotype.Genotype class for genotypes"
-        assert chunk_size == lib.CHUNK_ROWS, "the device kernels sum in the reference's 1000-row chunks"
+        assert int(chunk_size) >= 1, "chunk_size must be a positive number of SNPs"
         self.g, self.inputs, self.outFile = g, inputs, outFile
         self.chunk_size, self._skip_db_hets = chunk_size, skip_db_hets
         self.num_lines = len(g.g.accessions)
@@ -223,13 +223,15 @@ class Genotyper(object):
         g = self.g
         order, cid, pos = g.prepare_markers(self.inputs.chrs, self.inputs.pos)
         wei = np.ascontiguousarray(np.asarray(self.inputs.wei, dtype=np.float64)[order])
-        batch = g.db.scratch_batch([0, len(pos)], cid, pos, wei)
+        # called genotypes (BED, VCF without PL) take the popcount kernel; likelihood-weighted samples the fp64 one, which
+        # sums in the reference's chunks of `chunk_size` rows (snpmatch.py:173,218: the chunking is part of its rounding)
+        mode = lib.KERNEL_POPCOUNT if lib.weights_are_one_hot(wei) else lib.KERNEL_FP64
+        batch = g.db.scratch_batch([0, len(pos)], cid, pos, wei,
+                                   chunk_rows=int(self.chunk_size) if mode == lib.KERNEL_FP64 else lib.CHUNK_ROWS)
         try:
             if filter_pos_ix is not None:
                 assert type(filter_pos_ix) is np.ndarray, "provide np array for indices to be considered"
                 batch.set_row_filter(filter_pos_ix)
-            # called genotypes (BED, VCF without PL) take the popcount kernel; likelihood-weighted samples the fp64 one
-            mode = lib.KERNEL_POPCOUNT if lib.weights_are_one_hot(wei) else lib.KERNEL_FP64
             batch.run(self._skip_db_hets, kernel_mode=mode)
             batch.epilogue()
             r = batch.fetch()

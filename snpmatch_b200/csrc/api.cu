@@ -186,15 +186,21 @@ int snpm_db_load_int8(snpm_db *db, int64_t row0, int64_t n, const int8_t *snps) 
     if (n == 0) return SNPM_OK;
     SNPM_CUDA(cudaSetDevice(db->device));
     const int64_t max_rows = std::max<int64_t>(1, (int64_t(256) << 20) / db->n_acc);    // 256 MB staging
-    SNPM_TRY(db->scratch.ensure(size_t(std::min(n, max_rows)) * db->n_acc));
+    const size_t stage_bytes = (size_t(std::min(n, max_rows)) * db->n_acc + 255) & ~size_t(255);
+    SNPM_TRY(db->scratch.ensure(stage_bytes + 256));
+    int *d_bad = reinterpret_cast<int *>(static_cast<char *>(db->scratch.p) + stage_bytes);
+    SNPM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), db->stream));
     for (int64_t r = 0; r < n; r += max_rows) {
         const int64_t k = std::min(max_rows, n - r);
         SNPM_CUDA(cudaMemcpyAsync(db->scratch.p, snps + r * db->n_acc, size_t(k) * db->n_acc, cudaMemcpyHostToDevice, db->stream));
         k_pack_int8<<<grid_for(k * db->stride * 32, 256, db->n_sm), 256, 0, db->stream>>>(
-            db->scratch.as<int8_t>(), k, db->n_acc, db->stride, db->d_packed + (row0 + r) * db->stride);
+            db->scratch.as<int8_t>(), k, db->n_acc, db->stride, db->d_packed + (row0 + r) * db->stride, d_bad);
         SNPM_KERNEL_CHECK();
         SNPM_CUDA(cudaStreamSynchronize(db->stream));
     }
+    int bad = 0;
+    SNPM_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad > 0) return fail(SNPM_E_RANGE, "snpm_db_load_int8: %d genotype codes above 2 (codes are 0 ref, 1 alt, 2 het, negative = missing; makedb.py:59)", bad);
     return SNPM_OK;
 }
 
@@ -375,9 +381,10 @@ static int batch_upload(snpm_batch *b, int64_t S, const int64_t *offsets, const 
     b->n = n;
     b->grouped = false;
     b->coded = false;
+    b->chunk_rows = b->chunk_rows_req;                           // latched: the buffers below and the next runs use this value
     b->h_off.assign(offsets, offsets + S + 1);
     int64_t nseg = 0;
-    for (int64_t s = 0; s < S; ++s) nseg += ceil_div64(offsets[s + 1] - offsets[s], SNPM_CHUNK_ROWS);
+    for (int64_t s = 0; s < S; ++s) nseg += ceil_div64(offsets[s + 1] - offsets[s], b->chunk_rows);
     b->nseg_cap = nseg;
     SNPM_TRY(b->d_off.ensure(size_t(S + 1) * 8));
     SNPM_TRY(b->d_chrom.ensure(size_t(n) * 4));
@@ -721,7 +728,7 @@ int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *off
     SNPM_TRY(b->d_pair_s_tmp.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_tile_sample.ensure(std::max<size_t>(tile_sample.size(), 1) * 4));
     SNPM_TRY(b->d_tile_first.ensure(size_t(n_samples + 1) * 4));
-    SNPM_TRY(b->d_tile_hist.ensure(std::max<size_t>(tile_sample.size(), 1) * (size_t(1) << RS_MAX_BITS) * 4));
+    SNPM_TRY(b->d_tile_hist.ensure(std::max<size_t>(tile_sample.size(), 1) * ((size_t(2) << RS_MAX_BITS) * 4 + 8)));      // two count tables + the tile ranges
     SNPM_TRY(b->d_blk_chg.ensure(size_t(std::max<int64_t>(nseg, 1)) * size_t(b->gchunk / GR_BLOCK) * 8));
     SNPM_TRY(b->d_work_counter.ensure(256));
     cudaStream_t st = b->copy_stream;
@@ -786,6 +793,12 @@ int snpm_batch_set_result_range(snpm_batch *b, int64_t first_sample, int64_t n_s
     return SNPM_OK;
 }
 
+int snpm_batch_set_chunk_rows(snpm_batch *b, int32_t rows) {
+    if (!b || rows < 1 || rows > 1000000) return fail(SNPM_E_ARG, "snpm_batch_set_chunk_rows: 1..1000000 rows");
+    b->chunk_rows_req = rows;
+    return SNPM_OK;
+}
+
 int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows) {
     if (!b || rows < 16 || rows > GR_MAX_CHUNK || rows % 8) return fail(SNPM_E_ARG, "snpm_batch_set_group_chunk: 16..%d rows, a multiple of 8", GR_MAX_CHUNK);
     b->gchunk_req = rows;
@@ -823,13 +836,16 @@ int snpm_batch_destroy(snpm_batch *b) {
 }
 
 int snpm_batch_set_row_filter(snpm_batch *b, const int64_t *sorted_rows, int64_t n) {
-    if (!b || n < 0 || (n > 0 && !sorted_rows)) return fail(SNPM_E_ARG, "snpm_batch_set_row_filter: bad arguments");
+    if (!b || n < 0) return fail(SNPM_E_ARG, "snpm_batch_set_row_filter: bad arguments");
     for (int64_t i = 1; i < n; ++i)
         if (sorted_rows[i] <= sorted_rows[i - 1]) return fail(SNPM_E_ARG, "snpm_batch_set_row_filter: rows must be strictly ascending");
     SNPM_CUDA(cudaSetDevice(b->db->device));
-    b->n_filter = n;
-    if (n) {
-        SNPM_TRY(b->d_filter.ensure(size_t(n) * 8));
+    // NULL clears the filter; a non-NULL list of n = 0 rows is an EMPTY filter that keeps no pair (the reference's
+    // filter_pos_ix of length 0 leaves no common SNP, snpmatch.py:211-216)
+    b->has_filter = sorted_rows != nullptr;
+    b->n_filter = b->has_filter ? n : 0;
+    SNPM_TRY(b->d_filter.ensure(size_t(std::max<int64_t>(n, 1)) * 8));
+    if (b->has_filter && n) {
         SNPM_CUDA(cudaMemcpyAsync(b->d_filter.p, sorted_rows, size_t(n) * 8, cudaMemcpyHostToDevice, b->db->stream));
         SNPM_CUDA(cudaStreamSynchronize(b->db->stream));
     }
@@ -856,7 +872,7 @@ static int batch_join(snpm_batch *b, int algo) {
     SNPM_TRY(b->d_status.ensure(8 * sizeof(int)));
     SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_uploaded, 0));       // the samples are on the device
     SNPM_CUDA(cudaMemsetAsync(b->d_status.p, 0, 8 * sizeof(int), st));
-    if (b->grouped && b->pending_expand) {                        // compact upload forms -> the arrays the join reads (once per upload)
+    if (b->grouped && b->pending_expand && n > 0) {               // compact upload forms -> the arrays the join reads (once per upload)
         if (b->pending_expand & 1) {
             const uint32_t *d_end = b->d_runs.as<uint32_t>();
             k_expand_runs<<<int(ceil_div64(b->pending_runs * 32, 256)), 256, 0, st>>>(d_end, reinterpret_cast<const uint16_t *>(d_end + b->pending_runs),
@@ -878,7 +894,7 @@ static int batch_join(snpm_batch *b, int algo) {
     // once a sample carries more than an eighth of the panel rows (measured at m = N = 10.7 M: 0.40 ms vs 0.47 ms)
     if (algo == 0) algo = (n / S) * 8 >= db->n_rows ? 2 : 1;
     if (b->grouped) algo = 1;                                    // markers are not in position order
-    const int64_t *filter = b->n_filter ? b->d_filter.as<int64_t>() : nullptr;
+    const int64_t *filter = b->has_filter ? b->d_filter.as<int64_t>() : nullptr;
     if (n_tiles > 0) {
         if (algo == 2)
             k_join_mergepath<<<int(n_tiles), 256, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
@@ -914,7 +930,7 @@ static int batch_join(snpm_batch *b, int algo) {
     } else {
         SNPM_CUDA(cudaMemsetAsync(b->d_prefix.p, 0, 4, st));
     }
-    k_sample_ranges<<<1, 1024, 0, st>>>(b->d_prefix.as<int32_t>(), b->d_off.as<int64_t>(), S, b->grouped ? b->gchunk : SNPM_CHUNK_ROWS, b->d_mstart.as<int32_t>(),
+    k_sample_ranges<<<1, 1024, 0, st>>>(b->d_prefix.as<int32_t>(), b->d_off.as<int64_t>(), S, b->grouped ? b->gchunk : b->chunk_rows, b->d_mstart.as<int32_t>(),
                                         b->d_seg_off.as<int32_t>());
     SNPM_KERNEL_CHECK();
     b->launches += 1;
@@ -936,27 +952,46 @@ static int batch_group_sort_t(snpm_batch *b) {
     KeyT *ka = b->d_key_a.as<KeyT>(), *kb = b->d_key_b.as<KeyT>();
     uint32_t *ia = b->d_idx_a.as<uint32_t>(), *ib = b->d_idx_b.as<uint32_t>();
     const int32_t *mstart = b->d_mstart.as<int32_t>(), *tsample = b->d_tile_sample.as<int32_t>(), *tfirst = b->d_tile_first.as<int32_t>();
-    uint32_t *hist = b->d_tile_hist.as<uint32_t>();
+    const size_t hist_elems = size_t(tiles) << RS_MAX_BITS;
+    uint32_t *ha = b->d_tile_hist.as<uint32_t>(), *hb = ha + hist_elems;        // ping-pong: this pass's counts / the next pass's
+    int2 *range = reinterpret_cast<int2 *>(hb + hist_elems);
     static bool attr = false;
     if (!attr) {
-        SNPM_CUDA(cudaFuncSetAttribute(k_radix_scatter<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        SNPM_CUDA(cudaFuncSetAttribute(k_radix_scatter<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        SNPM_CUDA(cudaFuncSetAttribute(k_radix_pass<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        SNPM_CUDA(cudaFuncSetAttribute(k_radix_pass<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
+    k_tile_ranges<<<(tiles + 255) / 256, 256, 0, st>>>(mstart, tsample, tfirst, tiles, range);
+    {
+        const int bits0 = std::min(per, b->key_bits);
+        k_radix_hist<KeyT><<<tiles, RS_THREADS, size_t(1 << bits0) * 4, st>>>(ka, range, 0, bits0, ha);
+    }
+    SNPM_KERNEL_CHECK();
+    b->launches += 2;
+    // the next digit's tile counts: booked by the scatter of the pass before (atomics), or by a k_radix_hist launch of their own
+    static const bool fused_hist = !(getenv("SNPM_SORT_FUSED") && !strcmp(getenv("SNPM_SORT_FUSED"), "0"));      // measurement switch
     for (int p = 0; p < passes; ++p) {
         const int shift = p * per, bits = std::min(per, b->key_bits - shift), bins = 1 << bits;
-        k_radix_hist<KeyT><<<tiles, RS_THREADS, size_t(bins) * 4, st>>>(ka, mstart, tsample, tfirst, shift, bits, hist);
-        k_radix_scan<<<int(b->S), 1024, 0, st>>>(hist, tfirst, bits);
-        const size_t smem = size_t(RS_THREADS / 32) * bins * 2;
-        if (p == passes - 1)
-            k_radix_scatter<KeyT, true><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
-                                                                         b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(), mstart, tsample, tfirst, hist, shift, bits);
-        else
-            k_radix_scatter<KeyT, false><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, nullptr, nullptr, nullptr, nullptr, mstart, tsample, tfirst, hist, shift, bits);
+        const int nshift = shift + bits, nbits = p + 1 < passes ? std::min(per, b->key_bits - nshift) : 0;
+        const size_t smem = size_t(bins) * 20;
+        if (p > 0 && !fused_hist) {
+            k_radix_hist<KeyT><<<tiles, RS_THREADS, size_t(bins) * 4, st>>>(ka, range, shift, bits, ha);
+            b->launches += 1;
+        }
+        if (p == passes - 1) {
+            k_radix_pass<KeyT, true><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
+                                                                      b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(), mstart, tsample, tfirst, range, ha, nullptr,
+                                                                      shift, bits, 0, 0);
+        } else {
+            if (fused_hist) SNPM_CUDA(cudaMemsetAsync(hb, 0, (size_t(tiles) << nbits) * 4, st));
+            k_radix_pass<KeyT, false><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, nullptr, nullptr, nullptr, nullptr, mstart, tsample, tfirst, range, ha,
+                                                                       fused_hist ? hb : nullptr, shift, bits, nshift, nbits);
+        }
         SNPM_KERNEL_CHECK();
         std::swap(ka, kb);
         std::swap(ia, ib);
-        b->launches += 3;
+        if (fused_hist) std::swap(ha, hb);
+        b->launches += 1;
     }
     b->sorted_key = ka;                                           // after the last swap
     int64_t max_ns = 0;
@@ -978,8 +1013,9 @@ static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
     g.wtable = b->d_wtable.as<double>(); g.code_bits = b->code_bits;
     g.seg_off = b->d_seg_off.as<int32_t>(); g.mstart = b->d_mstart.as<int32_t>(); g.S = int32_t(b->S); g.chunk = b->gchunk;
     g.part_score = b->d_part_score.as<double>(); g.part_int = b->d_part_int.as<int32_t>(); g.a_pad = db->stride * 32;
-    g.n_slices = (db->stride + G2_WX - 1) / G2_WX;
-    g.wx = ((db->stride + g.n_slices - 1) / g.n_slices + 1) & ~1;      // even: neighbouring threads copy 16-byte pairs of columns
+    // a row of up to 36 words (1135 accessions) is one slice; wider rows are cut into warp-aligned slices of 32 words
+    if (db->stride <= G2_WX) { g.n_slices = 1; g.wx = (db->stride + 1) & ~1; }
+    else { g.wx = 32; g.n_slices = (db->stride + 31) / 32; }
     g.teams = std::min(G2_THREADS / g.wx, G2_MAX_TEAMS);
     int64_t jmax = 0;
     for (int64_t s = 0; s < b->S; ++s) jmax = std::max(jmax, ceil_div64(b->h_off[size_t(s) + 1] - b->h_off[size_t(s)], b->gchunk));
@@ -988,24 +1024,35 @@ static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
     const int64_t n_items = b->S * jmax * g.n_slices;
     if (n_items >= (int64_t(1) << 31) - (int64_t(1) << 20)) return fail(SNPM_E_ARG, "snpm_batch_run: %lld work items exceed the 2^31 limit", (long long)n_items);
     const size_t smem = size_t(g.teams) * g2_team_smem<KeyT>(g.wx, g.chunk);
-    if (smem > 227 * 1024) return fail(SNPM_E_ARG, "snpm_batch_run: group chunk %d needs %zu bytes of shared memory", g.chunk, smem);
-    static bool attr = false;
-    if (!attr) {
-        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, true, G2_WX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, false, G2_WX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    if (smem > 226 * 1024) return fail(SNPM_E_ARG, "snpm_batch_run: group chunk %d needs %zu bytes of shared memory", g.chunk, smem);
+    // L2 prefetch distance in blocks (measurement switch SNPM_G2_PF = 0 / 6 / 12; default below)
+    static const int pf = getenv("SNPM_G2_PF") ? atoi(getenv("SNPM_G2_PF")) : G2_PF_DEFAULT;
     SNPM_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned int), st));
     const int grid = int(std::min<int64_t>(db->n_sm, ceil_div64(n_items, g.teams)));
+#define G2_LAUNCH(SK, WXV, PFV)                                                                                                     \
+    do {                                                                                                                            \
+        static bool attr_ = false;                                                                                                  \
+        if (!attr_) {                                                                                                               \
+            SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, SK, WXV, PFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+            attr_ = true;                                                                                                           \
+        }                                                                                                                           \
+        k_score_grouped2<KeyT, SK, WXV, PFV><<<grid, G2_THREADS, smem, st>>>(g);                                                    \
+    } while (0)
+#define G2_LAUNCH_PF(SK, WXV)                                                          \
+    do {                                                                               \
+        if (pf <= 0) G2_LAUNCH(SK, WXV, 0);                                            \
+        else if (pf <= 6) G2_LAUNCH(SK, WXV, 6);                                       \
+        else G2_LAUNCH(SK, WXV, 12);                                                   \
+    } while (0)
     if (g.wx == G2_WX) {
-        if (skip_db_hets) k_score_grouped2<KeyT, true, G2_WX, true><<<grid, G2_THREADS, smem, st>>>(g);
-        else k_score_grouped2<KeyT, false, G2_WX, true><<<grid, G2_THREADS, smem, st>>>(g);
+        if (skip_db_hets) G2_LAUNCH_PF(true, G2_WX); else G2_LAUNCH_PF(false, G2_WX);
+    } else if (g.wx == 32) {
+        if (skip_db_hets) G2_LAUNCH_PF(true, 32); else G2_LAUNCH_PF(false, 32);
     } else {
-        if (skip_db_hets) k_score_grouped2<KeyT, true, 0, true><<<grid, G2_THREADS, smem, st>>>(g);
-        else k_score_grouped2<KeyT, false, 0, true><<<grid, G2_THREADS, smem, st>>>(g);
+        if (skip_db_hets) G2_LAUNCH(true, 0, 0); else G2_LAUNCH(false, 0, 0);
     }
+#undef G2_LAUNCH_PF
+#undef G2_LAUNCH
     SNPM_KERNEL_CHECK();
     b->launches += 1;
     return SNPM_OK;
@@ -1058,7 +1105,7 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
     a.seg_off = b->d_seg_off.as<int32_t>();
     a.mstart = b->d_mstart.as<int32_t>();
     a.S = int32_t(b->S);
-    a.chunk = SNPM_CHUNK_ROWS;
+    a.chunk = b->chunk_rows;
     a.table = 0;
     a.part_score = b->d_part_score.as<double>();
     a.part_ninfo = b->d_part_ninfo.as<int32_t>();
@@ -1129,6 +1176,8 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
         b->epilogue_done = false;
         return SNPM_OK;
     }
+    if (kernel_mode == 1 && b->chunk_rows != SNPM_CHUNK_ROWS)
+        return fail(SNPM_E_STATE, "snpm_batch_run: the popcount kernel works in %d-row chunks (its sums are exact in any chunking); set the chunk back", SNPM_CHUNK_ROWS);
     if (kernel_mode == 1 && b->nseg_cap > 0) {
         // called genotypes (one-hot weights): popcount kernel, exact in every summation order
         SNPM_TRY(b->d_pair_code.ensure(size_t(std::max<int64_t>(b->n, 1))));
@@ -1555,8 +1604,17 @@ int snpm_match_gts_accs(int device, const double *wei, const int8_t *snps, int64
         MG_CUDA(cudaMemcpyAsync(d_snps.p, snps, size_t(k) * n_acc, cudaMemcpyHostToDevice, st));
         MG_CUDA(cudaMemcpyAsync(d_rows.p, iota.data(), size_t(k) * 4, cudaMemcpyHostToDevice, st));
         MG_CUDA(cudaMemcpyAsync(d_w.p, w4.data(), size_t(k) * 32, cudaMemcpyHostToDevice, st));
-        k_pack_int8<<<grid_for(k * stride * 32, 256, 148), 256, 0, st>>>(d_snps.as<int8_t>(), k, n_acc, stride, d_packed.as<uint64_t>());
+        int *d_bad = d_seg.as<int>() + 4;            // DevBuf allocations hold at least 256 bytes
+        MG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+        k_pack_int8<<<grid_for(k * stride * 32, 256, 148), 256, 0, st>>>(d_snps.as<int8_t>(), k, n_acc, stride, d_packed.as<uint64_t>(), d_bad);
         MG_CUDA(cudaGetLastError());
+        int bad = 0;
+        MG_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MG_CUDA(cudaStreamSynchronize(st));
+        if (bad > 0) {
+            cleanup();
+            return fail(SNPM_E_RANGE, "snpm_match_gts_accs: %d genotype codes above 2 (codes are 0 ref, 1 alt, 2 het, negative = missing)", bad);
+        }
     }
     MG_CUDA(cudaMemcpyAsync(d_seg.p, seg, 8, cudaMemcpyHostToDevice, st));
     ScoreArgs a = {};

@@ -119,6 +119,7 @@ struct snpm_batch {
     // inputs (device)
     snpm::DevBuf d_off, d_chrom, d_pos, d_wei, d_filter;
     int64_t n_filter = 0;
+    bool has_filter = false;  // snpm_batch_set_row_filter: a filter is set (possibly an empty one, which keeps nothing)
     // join products
     snpm::DevBuf d_match_row, d_tile_cnt, d_tile_off, d_prefix, d_pair_db, d_pair_s, d_pair_w;
     snpm::DevBuf d_mstart, d_seg_off;
@@ -137,6 +138,7 @@ struct snpm_batch {
     // grouped mode (snpm_batch_upload_grouped): markers ordered by weight triple, scored by k_score_grouped
     bool grouped = false;
     int32_t n_gtable = 0;
+    int32_t chunk_rows = SNPM_CHUNK_ROWS, chunk_rows_req = SNPM_CHUNK_ROWS;   // position-order batches: rows per chunk of the fp64 kernel (snpm_batch_set_chunk_rows; latched at upload)
     int32_t gchunk = 320;              // rows per segment of the grouped kernels for the samples now on the device (latched at upload)
     int32_t gchunk_req = 320;          // snpm_batch_set_group_chunk: takes effect at the next grouped / coded upload
     // coded mode (snpm_batch_upload_coded): position-order markers + weight codes; grouped on the device (group_sort.cuh)

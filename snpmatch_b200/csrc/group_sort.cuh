@@ -6,9 +6,9 @@
 //   1. give every matched pair a sort key  [called class | code of the called class | code of the slow class | code of the
 //      fast class]  (k_scatter_pairs_coded) — the hierarchical order that makes every class weight change as rarely as
 //      possible along a sample (the counting kernel reads a class counter out only when THAT class's weight changes),
-//   2. sort the pairs of every sample by that key with a stable, segmented LSD radix sort (k_radix_hist / _scan / _scatter:
-//      digits of up to 11 bits, tile histograms, warp-aggregated ranks via match.any) — deterministic, position order is kept
-//      inside a group,
+//   2. sort the pairs of every sample by that key with a stable, segmented LSD radix sort (k_radix_hist once, then one
+//      k_radix_pass per digit of up to 11 bits: offsets from the tile histograms, warp-aggregated ranks via match.any, scatter,
+//      next digit's histogram on the way) — deterministic, position order is kept inside a group,
 //   3. mark, per block of 16 sorted rows, where each class weight changes (k_group_masks).
 // Replaces the per-sample work of Genotyper.genotyper's chunk loop set-up (snpmatch.py:218-227) in the grouped formulation;
 // results do not depend on the order (counts are order-free), only the speed does.
@@ -72,35 +72,56 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
     }
 }
 
-// tile t of the sort covers pairs [mstart[s] + lt * RS_TILE, ...) of sample s = tile_sample[t], lt = t - tile_first[s]; the
-// tile layout comes from the host's upper bound (markers per sample), so a tile may be empty
-__device__ __forceinline__ void rs_tile_range(const int32_t *__restrict__ mstart, const int32_t *__restrict__ tile_sample,
-                                              const int32_t *__restrict__ tile_first, int t, int *begin, int *end, int *sample) {
+// lanes of the warp that hold the same `bits`-bit digit as the caller (valid lanes only): one ballot per digit bit.  (match.any
+// does the same in one instruction but its cost grows with the number of distinct values in the warp — up to 32 here.)
+__device__ __forceinline__ uint32_t rs_peers(uint32_t d, bool valid, int bits) {
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+    for (int b = 0; b < bits; ++b) {
+        const uint32_t bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
+// Tile t of the sort covers pairs [begin, end) of sample tile_sample[t]: the lt-th RS_TILE pairs of the sample's matched range
+// (lt = t - tile_first[sample]).  The tile layout comes from the host's upper bound (markers per sample), so a tile may be empty.
+// One thread per tile; runs once per step behind k_sample_ranges so that the sort kernels find their range with ONE load
+// instead of a chain of three dependent ones.
+__global__ void __launch_bounds__(256) k_tile_ranges(const int32_t *__restrict__ mstart, const int32_t *__restrict__ tile_sample,
+                                                     const int32_t *__restrict__ tile_first, int32_t n_tiles, int2 *__restrict__ range) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
     const int s = tile_sample[t];
     const int lt = t - tile_first[s];
     const int b0 = mstart[s], b1 = mstart[s + 1];
-    *sample = s;
-    *begin = min(b1, b0 + lt * RS_TILE);
-    *end = min(b1, *begin + RS_TILE);
+    const int begin = min(b1, b0 + lt * RS_TILE);
+    range[t] = make_int2(begin, min(b1, begin + RS_TILE));
 }
 
-// digit histogram of one tile -> tile_hist[t][0..bins)
+// digit histogram of one tile -> tile_hist[t][0..bins)  (first pass only: later passes get theirs from the scatter before them)
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const KeyT *__restrict__ key, const int32_t *__restrict__ mstart,
-                                                          const int32_t *__restrict__ tile_sample, const int32_t *__restrict__ tile_first,
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const KeyT *__restrict__ key, const int2 *__restrict__ range,
                                                           int shift, int bits, uint32_t *__restrict__ tile_hist) {
     extern __shared__ uint32_t rs_h[];
     const int bins = 1 << bits;
+    const int2 rg = range[blockIdx.x];
     for (int d = threadIdx.x; d < bins; d += RS_THREADS) rs_h[d] = 0u;
     __syncthreads();
-    int begin, end, s;
-    rs_tile_range(mstart, tile_sample, tile_first, blockIdx.x, &begin, &end, &s);
+    const int begin = rg.x, end = rg.y;
     const uint32_t dmask = uint32_t(bins - 1);
-    const int lane = threadIdx.x & 31;
-    for (int i0 = begin + (threadIdx.x & ~31); i0 < end; i0 += RS_THREADS) {
-        const int i = i0 + lane;
-        const uint32_t d = i < end ? uint32_t(key[i] >> shift) & dmask : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KeyT k[RS_PER_THREAD];
+#pragma unroll
+    for (int e = 0; e < RS_PER_THREAD; ++e) {                      // all loads first: the tile is one DRAM round trip, not eight
+        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
+        k[e] = i < end ? key[i] : KeyT(0);
+    }
+#pragma unroll
+    for (int e = 0; e < RS_PER_THREAD; ++e) {
+        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
+        const uint32_t d = uint32_t(k[e] >> shift) & dmask;
+        const uint32_t peers = rs_peers(d, i < end, bits);
         if (i < end && lane == __ffs(peers) - 1) atomicAdd(rs_h + d, uint32_t(__popc(peers)));
     }
     __syncthreads();
@@ -108,76 +129,105 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const KeyT *__restric
     for (int d = threadIdx.x; d < bins; d += RS_THREADS) out[d] = rs_h[d];
 }
 
-// one CTA per sample: tile_hist[t][d] -> exclusive offset of (digit d, tile t) inside the sample's sorted range
-__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ tile_hist, const int32_t *__restrict__ tile_first, int bits) {
-    __shared__ int s_warp[33];
-    const int bins = 1 << bits;
-    const int s = blockIdx.x;
-    const int t0 = tile_first[s], t1 = tile_first[s + 1];
-    // thread -> `per` consecutive digits
-    const int per = (bins + int(blockDim.x) - 1) / int(blockDim.x);
-    const int d0 = threadIdx.x * per;
-    uint32_t run[2] = {0u, 0u};                      // per <= 2 (2048 bins, 1024 threads)
-    for (int t = t0; t < t1; ++t) {
-        uint32_t *h = tile_hist + size_t(t) * bins;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (k < per && d0 + k < bins) {
-                const uint32_t v = h[d0 + k];
-                h[d0 + k] = run[k];
-                run[k] += v;
-            }
-        }
-    }
-    int total;
-    const int mine = int(run[0] + (per > 1 ? run[1] : 0u));
-    const int ex = block_excl_scan(mine, &total, s_warp);
-    const uint32_t base0 = uint32_t(ex), base1 = uint32_t(ex) + run[0];
-    for (int t = t0; t < t1; ++t) {
-        uint32_t *h = tile_hist + size_t(t) * bins;
-        if (d0 < bins) h[d0] += base0;
-        if (per > 1 && d0 + 1 < bins) h[d0 + 1] += base1;
-    }
-}
-
-// stable scatter of one tile.  Warp w owns pairs [256 w, 256 w + 256) of the tile and takes them 32 at a time in order, so
-// ranks inside a digit follow the pair order: rank = (pairs of that digit in earlier warps) + (earlier rounds of this warp) +
-// (lower lanes of this round, match.any).  LAST: the payload index is resolved to the pair itself (panel row, marker index).
+// One pass of the stable segmented LSD radix sort, one CTA per tile, three steps in one kernel:
+//   offsets  where the tile's pairs of digit d go inside the sample's range = (pairs of smaller digits in the whole sample) +
+//            (pairs of digit d in earlier tiles of the sample), from the per-tile digit counts of ALL tiles of the sample
+//            (a few tens of KB out of L2 per CTA: cheaper than a separate scan kernel between two dependent launches);
+//   ranks    warp w owns pairs [256 w, 256 w + 256) of the tile and takes them 32 at a time in order, so ranks inside a digit
+//            follow the pair order: (pairs of that digit in earlier warps) + (earlier rounds of this warp) + (lower lanes of
+//            this round, match.any);
+//   scatter  key + payload to their place; the NEXT pass's per-tile digit counts are accumulated on the way (atomics into a
+//            zeroed table, indexed by the tile the pair lands in).  LAST: the payload index is resolved to the pair itself
+//            (panel row, marker index).
+// Dynamic shared memory: bins * 20 bytes (8 warp histograms of u16 + one u32 offset per digit).
 template <typename KeyT, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const KeyT *__restrict__ key_in, const uint32_t *__restrict__ idx_in,
+__global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const KeyT *__restrict__ key_in, const uint32_t *__restrict__ idx_in,
                                                              KeyT *__restrict__ key_out, uint32_t *__restrict__ idx_out,
                                                              const int32_t *__restrict__ pair_db_in, const int32_t *__restrict__ pair_s_in,
                                                              int32_t *__restrict__ pair_db_out, int32_t *__restrict__ pair_s_out,
                                                              const int32_t *__restrict__ mstart, const int32_t *__restrict__ tile_sample,
-                                                             const int32_t *__restrict__ tile_first, const uint32_t *__restrict__ tile_off,
-                                                             int shift, int bits) {
+                                                             const int32_t *__restrict__ tile_first, const int2 *__restrict__ range,
+                                                             const uint32_t *__restrict__ hist_in, uint32_t *__restrict__ hist_out,
+                                                             int shift, int bits, int next_shift, int next_bits) {
     extern __shared__ uint32_t rs_sm[];
+    __shared__ int s_warp[33];
     const int bins = 1 << bits;
-    uint16_t *whist = reinterpret_cast<uint16_t *>(rs_sm);          // [8][bins]
     constexpr int NW = RS_THREADS / 32;
-    for (int k = threadIdx.x; k < NW * bins / 2; k += RS_THREADS) rs_sm[k] = 0u;
-    __syncthreads();
-    int begin, end, s;
-    rs_tile_range(mstart, tile_sample, tile_first, blockIdx.x, &begin, &end, &s);
-    if (begin >= end) return;
-    const uint32_t dmask = uint32_t(bins - 1);
+    uint16_t *whist = reinterpret_cast<uint16_t *>(rs_sm);          // [NW][bins]
+    uint32_t *off = rs_sm + NW * bins / 2;                          // [bins]
+    const int t = blockIdx.x;
+    const int2 rg = range[t];
+    const int begin = rg.x, end = rg.y;
+    if (begin >= end) return;                                       // the whole CTA: an empty tile
+    const int s = tile_sample[t];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint16_t *mine = whist + size_t(warp) * bins;
+    // the tile's pairs: loads issued before anything depends on them
     KeyT k[RS_PER_THREAD];
-    uint32_t v[RS_PER_THREAD], rank[RS_PER_THREAD];
+    uint32_t v[RS_PER_THREAD];
 #pragma unroll
     for (int e = 0; e < RS_PER_THREAD; ++e) {
         const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
         const bool on = i < end;
         k[e] = on ? key_in[i] : KeyT(0);
         v[e] = on ? idx_in[i] : 0u;
-        const uint32_t d = on ? uint32_t(k[e] >> shift) & dmask : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    }
+    for (int j = threadIdx.x; j < NW * bins / 2; j += RS_THREADS) rs_sm[j] = 0u;
+    const int t0 = tile_first[s], t1 = tile_first[s + 1], base = mstart[s];
+    // offsets: thread -> `per` consecutive digits
+    {
+        const int per = (bins + RS_THREADS - 1) / RS_THREADS;       // 1, 2, 4 or 8
+        const int d0 = threadIdx.x * per;
+        uint32_t total[8], before[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) total[j] = before[j] = 0u;
+        if (d0 < bins) {
+            constexpr int U = 8;                                    // tiles per batch of independent loads (the loop is latency bound)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < per) {
+                    for (int tt = t0; tt < t1; tt += 2 * U) {
+                        uint32_t c[2 * U];
+#pragma unroll
+                        for (int u = 0; u < 2 * U; ++u) c[u] = tt + u < t1 ? __ldg(hist_in + size_t(tt + u) * bins + d0 + j) : 0u;
+#pragma unroll
+                        for (int u = 0; u < 2 * U; ++u) {
+                            total[j] += c[u];
+                            if (tt + u < t) before[j] += c[u];
+                        }
+                    }
+                }
+            }
+        }
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += total[j];
+        int all;
+        uint32_t run = uint32_t(block_excl_scan(int(mine), &all, s_warp));
+        if (d0 < bins) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < per) {
+                    off[d0 + j] = run + before[j];
+                    run += total[j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t dmask = uint32_t(bins - 1);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint16_t *mine_h = whist + size_t(warp) * bins;
+    uint32_t rank[RS_PER_THREAD];
+#pragma unroll
+    for (int e = 0; e < RS_PER_THREAD; ++e) {
+        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
+        const bool on = i < end;
+        const uint32_t d = uint32_t(k[e] >> shift) & dmask;
+        const uint32_t peers = rs_peers(d, on, bits);
         uint32_t prior = 0u;
-        if (on) prior = mine[d];
+        if (on) prior = mine_h[d];
         __syncwarp();
-        if (on && lane == __ffs(peers) - 1) mine[d] = uint16_t(prior + __popc(peers));
+        if (on && lane == __ffs(peers) - 1) mine_h[d] = uint16_t(prior + __popc(peers));
         __syncwarp();
         rank[e] = prior + uint32_t(__popc(peers & lt_mask));
     }
@@ -193,14 +243,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const KeyT *__rest
         }
     }
     __syncthreads();
-    const uint32_t *off = tile_off + size_t(blockIdx.x) * bins;
-    const int base = mstart[s];
+    const uint32_t nmask = next_bits > 0 ? uint32_t((1 << next_bits) - 1) : 0u;
 #pragma unroll
     for (int e = 0; e < RS_PER_THREAD; ++e) {
         const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
         if (i < end) {
             const uint32_t d = uint32_t(k[e] >> shift) & dmask;
-            const int o = base + int(off[d]) + int(mine[d]) + int(rank[e]);
+            const int local = int(off[d]) + int(mine_h[d]) + int(rank[e]);
+            const int o = base + local;
             key_out[o] = k[e];
             if (LAST) {
                 pair_db_out[o] = pair_db_in[v[e]];
@@ -208,6 +258,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const KeyT *__rest
             } else {
                 idx_out[o] = v[e];
             }
+        }
+        if (!LAST && hist_out != nullptr && i < end) {
+            // next pass's digit counts, booked on the tile the pair lands in (fire-and-forget atomics into a zeroed table)
+            const uint32_t d = uint32_t(k[e] >> shift) & dmask;
+            const int local = int(off[d]) + int(mine_h[d]) + int(rank[e]);
+            atomicAdd(hist_out + ((size_t(t0) + size_t(local / RS_TILE)) << next_bits) + (uint32_t(k[e] >> next_shift) & nmask), 1u);
         }
     }
 }

@@ -7,14 +7,17 @@
 // What is different:
 //   * input is what the device-side grouping produces (group_sort.cuh): sorted panel rows + sort keys that carry the three
 //     weight codes of a pair; weights come from the table of distinct values (L1-resident);
-//   * ONE CTA per SM, 7 teams of 36 threads in 8 warps (252 of 256 lanes work: the 128-thread CTAs of round 1 used 108 of
-//     128) and 7 instead of 6 segments in flight per SM;
-//   * teams are independent: a team claims (segment, word slice) items from a global counter, longest segments first, and
-//     synchronises only with itself (an mbarrier of 36 arrivals), so there is no CTA-wide barrier after start-up and no tail
-//     where an SM waits for its slowest team;
-//   * the row numbers, keys and change masks of the NEXT item are fetched with cp.async while the current one is scored
-//     (double-buffered staging), so a team never waits for a dependent global load between segments;
-//   * class counters have 8 planes (read out at the latest every 240 rows), the totals 9 (segments of at most 496 rows).
+//   * ONE persistent CTA per SM, 7 teams of 36 threads in 8 warps (252 of 256 lanes work: the 128-thread CTAs of round 1
+//     used 108 of 128) and 7 instead of 6 segments in flight per SM; wide panels (rows of more than 36 words) are cut into
+//     warp-aligned slices of 32 words, 8 teams = 8 slices of the same segment;
+//   * the CTA works in rounds: it draws `teams` consecutive (segment, word slice) items from a global counter, longest
+//     segments first; the teams score them block by block in lockstep (one full-warp barrier per 16-row block, a no-op
+//     while the warp is converged) and meet at ONE __syncthreads per round.  Lockstep is deliberate: a 36-thread team
+//     spans two warps, and two teams that share a warp issue ONE instruction stream only while they run the same code
+//     (measured: independent teams executed 160 M warp instructions for the work the lockstep kernel does in 113 M);
+//   * the row numbers, keys and change masks of the NEXT round are fetched with cp.async while the current one is scored
+//     (double-buffered staging), so no team waits for a dependent global load between segments;
+//   * class counters and totals have 9 planes (segments of at most 496 rows: no counter can overflow inside one).
 #pragma once
 #include "common.cuh"
 #include "grouped.cuh"
@@ -23,11 +26,12 @@
 namespace snpm {
 
 constexpr int G2_WX = 36;                 // words per team (one 1135-accession row)
-constexpr int G2_MAX_TEAMS = 7;
+constexpr int G2_MAX_TEAMS = 8;
 constexpr int G2_THREADS = 256;           // 7 teams x 36 = 252 threads: 8 warps, two per scheduler, so a thread may hold 255 registers
                                           // (9 warps would put three on one scheduler's register file: 168 registers, spills)
 constexpr int G2_MAX_CHUNK = 496;
-constexpr int G2_CP = 8;                  // planes of a class counter
+constexpr int G2_CP = 9;                  // planes of a class counter
+constexpr int G2_PF_DEFAULT = 0;          // L2 prefetch distance in 16-row blocks (0 = off: measured 0.272 ms off, 0.328 at 6, 0.354 at 12)
 constexpr int G2_TP = 9;                  // planes of the per-segment totals (I, ninfo)
 
 template <typename KeyT>
@@ -57,7 +61,7 @@ __device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src_gme
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
 
-// what the leader publishes for an item
+// one work item: a segment (chunk rows of one sample) x one word slice
 struct G2Item {
     int32_t seg;        // -1: no more work
     int32_t begin;      // first pair
@@ -71,21 +75,33 @@ __host__ __device__ __forceinline__ size_t g2_stage_bytes(int chunk) {
 }
 template <typename KeyT>
 __host__ __device__ __forceinline__ size_t g2_team_smem(int wx, int chunk) {
-    return size_t(GR_RING) * wx * 8 + 2 * g2_stage_bytes<KeyT>(chunk) + 64;       // ring | 2 staging buffers | mbarrier + 2 item slots
+    return size_t(GR_RING) * wx * 8 + 2 * g2_stage_bytes<KeyT>(chunk);             // ring | 2 staging buffers
 }
 
-// fold the counts of an 8-plane counter: F[lane] += w * count[lane]
-__device__ __forceinline__ void fold_counts8(const BitCounter<G2_CP> &c, double w, double (&F)[32]) {
+// fold the counts of a class counter: F[lane] += w * count[lane]
+__device__ __forceinline__ void fold_counts9(const BitCounter<G2_CP> &c, double w, double (&F)[32]) {
     uint32_t t[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) t[k] = c.p[k];
     transpose_planes8(t);
+    if (c.p[8] == 0u) {                           // fewer than 256 rows since the last read-out: the common case
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int cnt = int((t[i] >> (8 * j)) & 0xffu);
-            F[8 * j + i] = fma(w, double(cnt), F[8 * j + i]);
+            for (int j = 0; j < 4; ++j) {
+                const int cnt = int((t[i] >> (8 * j)) & 0xffu);
+                F[8 * j + i] = fma(w, double(cnt), F[8 * j + i]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 8 * j + i;
+                const int cnt = int((t[i] >> (8 * j)) & 0xffu) | int(((c.p[8] >> b) & 1u) << 8);
+                F[b] = fma(w, double(cnt), F[b]);
+            }
         }
     }
 }
@@ -105,10 +121,17 @@ __device__ __forceinline__ void counter_values9(const BitCounter<G2_TP> &c, int3
     }
 }
 
-// WX > 0: words per team known at compile time; WX == 0: a.wx.  PAIRS: two neighbouring threads share 16-byte copies.
-template <typename KeyT, bool SKIP_HETS, int WX, bool PAIRS>
+// WX > 0: words per team known at compile time; WX == 0: a.wx.  Thread pairs (2i, 2i+1) share 16-byte copies of two columns.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// PF: rows of block b + PF are pulled into L2 (prefetch.global.L2, one 128-byte line per instruction) when block b's copies
+// are queued: the shared-memory ring holds 3 blocks per team in flight (~100 KB per SM), too few outstanding bytes to saturate
+// HBM with 288-byte gathers (scripts/microbench_gather2.cu: 147 KB in flight 4.4 TB/s, 221 KB 4.8 TB/s); the L2 prefetches
+// put as many rows in flight at the DRAM level as wanted, and the ring then only has to hide L2 latency.
+template <typename KeyT, bool SKIP_HETS, int WX, int PF>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Args<KeyT> a) {
     extern __shared__ __align__(16) unsigned char g2_smem[];
+    __shared__ int s_base[2];                     // first item of the round in staging buffer 0 / 1
     const int wx = WX ? WX : a.wx;
     const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
     const bool in_team = q < a.teams;
@@ -117,40 +140,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     unsigned char *team = g2_smem + size_t(in_team ? q : 0) * team_bytes;
     uint64_t *ring = reinterpret_cast<uint64_t *>(team);
     unsigned char *stage0 = team + size_t(GR_RING) * wx * 8;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(stage0 + 2 * stage_bytes);
-    G2Item *slots = reinterpret_cast<G2Item *>(bar + 1);                  // [2]
-    if (in_team && w == 0) {
-        mbar_init(smem_u32(bar), uint32_t(wx));
-        mbar_fence_init();
-    }
-    __syncthreads();                              // the only CTA-wide barrier
-    if (!in_team) return;
-    // lanes of this team inside this warp.  Thread pairs (2i, 2i+1) share 16-byte copies; they read each other's data only while
-    // the team's lanes of the warp execute together (then the neighbour is past its own cp.async.wait_group and past its reads
-    // of the block before).  That is the normal state; if a divergent branch has split them, a sub-warp barrier rejoins them.
-    uint32_t tmask;
-    {
-        const int w0 = int(threadIdx.x) & ~31, t0 = q * wx, t1 = t0 + wx;
-        const int lo_l = max(t0, w0) - w0, hi_l = min(t1, w0 + 32) - w0;
-        tmask = (hi_l >= 32 ? 0xffffffffu : ((1u << hi_l) - 1u)) & ~((1u << lo_l) - 1u);
-    }
-    auto team_converge = [&](uint32_t m) {
-        if ((__activemask() & m) != m) __syncwarp(m);
-    };
-    uint32_t phase = 0u;
-    auto team_sync = [&]() {
-        mbar_arrive(smem_u32(bar));
-        mbar_wait(smem_u32(bar), phase);
-        phase ^= 1u;
-    };
     const int n_items = a.S * a.jmax * a.n_slices;
-    // leader: claim the next valid item, longest segments first (slot -> segment j = jmax-1 - slot / S of sample slot % S)
-    auto claim = [&](G2Item *out) {
+    // item i -> (slot, slice); slot -> segment j = jmax-1 - slot / S of sample slot % S: longest segments first
+    auto decode = [&](int i) {
         G2Item it;
         it.seg = -1; it.begin = 0; it.n_rows = 0; it.slice = 0;
-        while (true) {
-            const int i = int(atomicAdd(a.work_counter, 1u));
-            if (i >= n_items) break;
+        if (in_team && i < n_items) {
             const int slot = i / a.n_slices, slice = i - slot * a.n_slices;
             const int j = a.jmax - 1 - slot / a.S, smp = slot % a.S;
             const int s0 = __ldg(a.seg_off + smp), s1 = __ldg(a.seg_off + smp + 1);
@@ -160,10 +155,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 it.begin = m0 + j * a.chunk;
                 it.n_rows = min(m1, it.begin + a.chunk) - it.begin;
                 it.slice = slice;
-                break;
             }
         }
-        *out = it;
+        return it;
     };
     // queue the copies of an item's row numbers, keys and change masks into staging buffer `buf` (one commit group)
     auto prefetch = [&](const G2Item &it, int buf) {
@@ -182,15 +176,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         cp_async_commit();
     };
 
-    // start-up: item 0 staged synchronously, item 1 claimed
-    if (w == 0) claim(&slots[0]);
-    team_sync();
-    G2Item cur = slots[0];
-    if (cur.seg < 0) return;
+    // start-up: round 0 staged synchronously, round 1 drawn
+    if (threadIdx.x == 0) s_base[0] = int(atomicAdd(a.work_counter, unsigned(a.teams)));
+    __syncthreads();
+    if (s_base[0] >= n_items) return;
+    G2Item cur = decode(s_base[0] + q);
     prefetch(cur, 0);
     cp_async_wait<0>();
-    if (w == 0) claim(&slots[1]);
-    team_sync();
+    if (threadIdx.x == 0) s_base[1] = int(atomicAdd(a.work_counter, unsigned(a.teams)));
+    __syncthreads();
     int buf = 0;
 
     const int64_t stride = a.stride;
@@ -198,59 +192,66 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     const uint32_t ring_pitch = uint32_t(wx) * 8u;
     const uint32_t stride_b = uint32_t(a.stride) * 8u;
     const int cb = a.code_bits;
+    const int nb_round = a.chunk / GR_BLOCK;      // every team runs this many block steps per round (lockstep)
 
     while (true) {
-        const G2Item nxt = slots[buf ^ 1];
-        prefetch(nxt, buf ^ 1);                   // lands while this item is scored (oldest commit group)
+        const int next_base = s_base[buf ^ 1];
+        int ticket = 0;
+        if (threadIdx.x == 0 && next_base < n_items) ticket = int(atomicAdd(a.work_counter, unsigned(a.teams)));      // the round after next
+        const G2Item nxt = decode(next_base + q);
+        prefetch(nxt, buf ^ 1);                   // lands while this round is scored (oldest commit group)
         const unsigned char *st = stage0 + size_t(buf) * stage_bytes;
         const int32_t *s_row = reinterpret_cast<const int32_t *>(st);
         const KeyT *s_key = reinterpret_cast<const KeyT *>(st + size_t(a.chunk) * 4);
         const unsigned long long *s_chg = reinterpret_cast<const unsigned long long *>(st + size_t(a.chunk) * 4 + size_t(a.chunk) * sizeof(KeyT));
-        const int n_rows = cur.n_rows;
+        const int n_rows = cur.n_rows;            // 0: no item for this team in this round (it still keeps step with the others)
         const int n_blocks = (n_rows + GR_BLOCK - 1) / GR_BLOCK;
         const int n_full = n_rows / GR_BLOCK;
         const int word = cur.slice * wx + w;
-        const bool live = word < a.stride;        // threads past the row's last word idle through the item (they still stage and sync)
-        const unsigned char *col = reinterpret_cast<const unsigned char *>(a.packed + (PAIRS ? (word & ~1) : word));
-        const uint32_t my_ring = smem_u32(ring + (PAIRS ? (w & ~1) : w));
+        const bool live = in_team && n_rows > 0 && word < a.stride;
+        const unsigned char *col = reinterpret_cast<const unsigned char *>(a.packed + (word & ~1));
+        const uint32_t my_ring = smem_u32(ring + (w & ~1));
         auto issue = [&](int b) {
             if (live) {
-                if (PAIRS) {
-                    const int r0 = b * GR_BLOCK + 8 * odd;
-                    const uint32_t slot0 = my_ring + uint32_t(r0 % GR_RING) * ring_pitch;
-                    if (b < n_full) {
+                const int r0 = b * GR_BLOCK + 8 * odd;
+                const uint32_t slot0 = my_ring + uint32_t(r0 % GR_RING) * ring_pitch;
+                if (b < n_full) {
 #pragma unroll
-                        for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
-                            const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
-                            cp_async16(slot0 + uint32_t(k4 + 0) * ring_pitch, col + (unsigned long long)(uint32_t(rr.x)) * stride_b);
-                            cp_async16(slot0 + uint32_t(k4 + 1) * ring_pitch, col + (unsigned long long)(uint32_t(rr.y)) * stride_b);
-                            cp_async16(slot0 + uint32_t(k4 + 2) * ring_pitch, col + (unsigned long long)(uint32_t(rr.z)) * stride_b);
-                            cp_async16(slot0 + uint32_t(k4 + 3) * ring_pitch, col + (unsigned long long)(uint32_t(rr.w)) * stride_b);
-                        }
-                    } else if (b < n_blocks) {
-                        for (int k = 0; k < GR_BLOCK / 2 && r0 + k < n_rows; ++k)
-                            cp_async16(slot0 + uint32_t(k) * ring_pitch, col + (unsigned long long)(uint32_t(s_row[r0 + k])) * stride_b);
+                    for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
+                        const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
+                        cp_async16(slot0 + uint32_t(k4 + 0) * ring_pitch, col + (unsigned long long)(uint32_t(rr.x)) * stride_b);
+                        cp_async16(slot0 + uint32_t(k4 + 1) * ring_pitch, col + (unsigned long long)(uint32_t(rr.y)) * stride_b);
+                        cp_async16(slot0 + uint32_t(k4 + 2) * ring_pitch, col + (unsigned long long)(uint32_t(rr.z)) * stride_b);
+                        cp_async16(slot0 + uint32_t(k4 + 3) * ring_pitch, col + (unsigned long long)(uint32_t(rr.w)) * stride_b);
                     }
-                } else {
-                    const int r0 = b * GR_BLOCK;
-                    const uint32_t slot0 = my_ring + uint32_t(r0 % GR_RING) * ring_pitch;
-                    if (b < n_full) {
-#pragma unroll
-                        for (int k4 = 0; k4 < GR_BLOCK; k4 += 4) {
-                            const int4 rr = *reinterpret_cast<const int4 *>(s_row + r0 + k4);
-                            cp_async8(slot0 + uint32_t(k4 + 0) * ring_pitch, col + (unsigned long long)(uint32_t(rr.x)) * stride_b);
-                            cp_async8(slot0 + uint32_t(k4 + 1) * ring_pitch, col + (unsigned long long)(uint32_t(rr.y)) * stride_b);
-                            cp_async8(slot0 + uint32_t(k4 + 2) * ring_pitch, col + (unsigned long long)(uint32_t(rr.z)) * stride_b);
-                            cp_async8(slot0 + uint32_t(k4 + 3) * ring_pitch, col + (unsigned long long)(uint32_t(rr.w)) * stride_b);
-                        }
-                    } else if (b < n_blocks) {
-                        for (int k = 0; k < GR_BLOCK && r0 + k < n_rows; ++k)
-                            cp_async8(slot0 + uint32_t(k) * ring_pitch, col + (unsigned long long)(uint32_t(s_row[r0 + k])) * stride_b);
-                    }
+                } else if (b < n_blocks) {
+                    for (int k = 0; k < GR_BLOCK / 2 && r0 + k < n_rows; ++k)
+                        cp_async16(slot0 + uint32_t(k) * ring_pitch, col + (unsigned long long)(uint32_t(s_row[r0 + k])) * stride_b);
                 }
             }
-            cp_async_commit();
+            cp_async_commit();                    // always: the waits below count groups
         };
+        // lines of the rows of block b -> L2: the slice of a row is wx * 8 bytes from a 16-byte aligned start, i.e. at most
+        // wx / 16 + 1 lines of 128 bytes; the team's threads share the (row, line) pairs of the block
+        auto prefetch_block = [&](int b) {
+            if (PF > 0 && live && b < n_blocks) {
+                const int lines = (wx * 8 + 127) / 128 + 1;
+                const int todo = min(GR_BLOCK, n_rows - b * GR_BLOCK) * lines;
+                const unsigned char *col0 = reinterpret_cast<const unsigned char *>(a.packed + cur.slice * wx);
+                for (int j = w; j < todo; j += wx) {
+                    const int r = j / lines, ln = j - r * lines;
+                    const unsigned char *row = col0 + (unsigned long long)(uint32_t(s_row[b * GR_BLOCK + r])) * stride_b;
+                    const unsigned long long first = reinterpret_cast<unsigned long long>(row) & ~127ull;
+                    const unsigned long long last = (reinterpret_cast<unsigned long long>(row) + uint32_t(min(wx, a.stride - cur.slice * wx)) * 8u - 1u) & ~127ull;
+                    const unsigned long long p = first + (unsigned long long)(ln) * 128ull;
+                    if (p <= last) prefetch_l2(reinterpret_cast<const void *>(p));
+                }
+            }
+        };
+        if (PF > 0) {
+#pragma unroll 1
+            for (int b = GR_INFLIGHT; b < GR_INFLIGHT + PF; ++b) prefetch_block(b);
+        }
 #pragma unroll
         for (int b = 0; b < GR_INFLIGHT; ++b) issue(b);
 
@@ -264,44 +265,41 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         c_ref.clear();
         c_alt.clear();
         c_het.clear();
-        int age_ref = 0, age_alt = 0, age_het = 0;          // blocks added since the last read-out (an 8-plane counter holds 255)
-        double w_ref, w_alt, w_het;
-        {
+        double w_ref = 0.0, w_alt = 0.0, w_het = 0.0;
+        if (n_rows > 0) {
             const KeyT k0 = s_key[0];
             w_ref = __ldg(a.wtable + gs_code(k0, 0, cb));
             w_alt = __ldg(a.wtable + gs_code(k0, 1, cb));
             w_het = __ldg(a.wtable + gs_code(k0, 2, cb));
         }
-        auto flush_class = [&](BitCounter<G2_CP> &c, double wt, int &age) {
-            age = 0;
+        // read a class counter out: its counts are informative sites, and matches weighted by `wt`
+        auto flush_class = [&](BitCounter<G2_CP> &c, double wt) {
             if (c.any()) {
                 c_ninfo.add_counter(c);
                 if (wt == 1.0) c_int.add_counter(c);
-                else if (wt != 0.0) fold_counts8(c, wt, F);
+                else if (wt != 0.0) fold_counts9(c, wt, F);
                 c.clear();
             }
         };
-        auto add_class = [&](BitCounter<G2_CP> &c, double &wt, int &age, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, int r0) {
+        // one class: add the block's planes; where the class weight changes inside the block (bit k of `mask`: row k starts a new
+        // weight), add the rows piece by piece and read the counter out in between
+        auto add_class = [&](BitCounter<G2_CP> &c, double &wt, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, int r0) {
             if (mask == 0u) {
-                if (age == 15) flush_class(c, wt, age);
                 c.add16(pl);
-                ++age;
                 return;
             }
             int k0 = 0;
             while (true) {
                 const int k1 = mask ? __ffs(mask) - 1 : GR_BLOCK;
                 if (k1 > k0) {
-                    if (age == 15) flush_class(c, wt, age);
                     const uint32_t rm = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
                     uint32_t m[GR_BLOCK];
 #pragma unroll
                     for (int k = 0; k < GR_BLOCK; ++k) m[k] = pl[k] & uint32_t(int32_t(rm << (31 - k)) >> 31);
                     c.add16(m);
-                    ++age;
                 }
                 if (k1 >= GR_BLOCK) break;
-                flush_class(c, wt, age);
+                flush_class(c, wt);
                 wt = __ldg(a.wtable + gs_code(s_key[r0 + k1], which, cb));
                 mask &= mask - 1u;
                 k0 = k1;
@@ -312,51 +310,64 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
             uint32_t pl[GR_BLOCK];
 #pragma unroll
             for (int k = 0; k < GR_BLOCK; ++k) pl[k] = ~(lo[k] | hi[k]);
-            add_class(c_ref, w_ref, age_ref, pl, uint32_t(chg) & 0xffffu, 0, b * GR_BLOCK);
+            add_class(c_ref, w_ref, pl, uint32_t(chg) & 0xffffu, 0, b * GR_BLOCK);
 #pragma unroll
             for (int k = 0; k < GR_BLOCK; ++k) pl[k] = lo[k] & ~hi[k];
-            add_class(c_alt, w_alt, age_alt, pl, uint32_t(chg >> 16) & 0xffffu, 1, b * GR_BLOCK);
+            add_class(c_alt, w_alt, pl, uint32_t(chg >> 16) & 0xffffu, 1, b * GR_BLOCK);
             if (!SKIP_HETS) {                     // snpmatch.py:78-79: masked hets match nothing and are not informative
 #pragma unroll
                 for (int k = 0; k < GR_BLOCK; ++k) pl[k] = hi[k] & ~lo[k];
-                add_class(c_het, w_het, age_het, pl, uint32_t(chg >> 32) & 0xffffu, 2, b * GR_BLOCK);
+                add_class(c_het, w_het, pl, uint32_t(chg >> 32) & 0xffffu, 2, b * GR_BLOCK);
             }
         };
 
-        // Every thread of the team runs the loop (threads past the row's last word compute on stale ring contents and store
-        // nothing), so that the lanes a warp holds of one team stay converged.
-        for (int b = 0; b < n_full; ++b) {
-            cp_async_wait<GR_INFLIGHT - 2>();         // block b has landed: this thread's copies ...
-            if (PAIRS) team_converge(tmask);          // ... and its neighbour's; the neighbour has also read block b-1
-            if (b > 0) issue(b + GR_INFLIGHT - 1);    // refill the slots of block b-1
-            const uint64_t *slot = ring + size_t((b * GR_BLOCK) % GR_RING) * wx + w;
-            uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
-#pragma unroll
-            for (int k = 0; k < GR_BLOCK; ++k) {
-                const uint64_t v = slot[size_t(k) * wx];
-                lo[k] = uint32_t(v);
-                hi[k] = uint32_t(v >> 32);
+        // Every thread runs all nb_round steps (idle teams and threads past the row's last word only keep step), one full-warp
+        // barrier per step: after it the neighbour's copies of block b have landed too and it has read block b-1, whose slots
+        // are refilled next.
+        for (int b = 0; b < nb_round; ++b) {
+            cp_async_wait<GR_INFLIGHT - 2>();
+            __syncwarp();
+            if (b > 0) issue(b + GR_INFLIGHT - 1);
+            if (PF > 0) prefetch_block(b + GR_INFLIGHT + PF);
+            if (PF > 0 && b == 1 && nxt.seg >= 0 && nxt.slice * wx + w < a.stride) {
+                // first rows of the NEXT round's item -> L2, so that its first copies do not start with a DRAM round trip.  A
+                // thread uses only the row numbers it has staged itself (its cp.async group is older than every ring group, so
+                // the wait above has completed it): no barrier needed.
+                const int32_t *n_row = reinterpret_cast<const int32_t *>(stage0 + size_t(buf ^ 1) * stage_bytes);
+                const unsigned char *ncol0 = reinterpret_cast<const unsigned char *>(a.packed + nxt.slice * wx);
+                const uint32_t nbytes = uint32_t(min(wx, a.stride - nxt.slice * wx)) * 8u;
+                for (int r = w; r < min(nxt.n_rows, GR_INFLIGHT * GR_BLOCK); r += wx) {
+                    const unsigned long long row = reinterpret_cast<unsigned long long>(ncol0 + (unsigned long long)(uint32_t(n_row[r])) * stride_b);
+                    for (unsigned long long p = row & ~127ull; p <= ((row + nbytes - 1u) & ~127ull); p += 128ull) prefetch_l2(reinterpret_cast<const void *>(p));
+                }
             }
-            score_block(lo, hi, b);
-        }
-        if (n_full < n_blocks) {                      // ragged last block: rows past the end read as missing everywhere
-            cp_async_wait<0>();
-            if (PAIRS) team_converge(tmask);
-            const int r0 = n_full * GR_BLOCK;
-            const uint64_t *slot = ring + size_t(r0 % GR_RING) * wx + w;
-            uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
+            if (b < n_full) {
+                const uint64_t *slot = ring + size_t((b * GR_BLOCK) % GR_RING) * wx + w;
+                uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
 #pragma unroll
-            for (int k = 0; k < GR_BLOCK; ++k) {
-                uint64_t v = ~0ull;
-                if (r0 + k < n_rows) v = slot[size_t(k) * wx];
-                lo[k] = uint32_t(v);
-                hi[k] = uint32_t(v >> 32);
+                for (int k = 0; k < GR_BLOCK; ++k) {
+                    const uint64_t v = slot[size_t(k) * wx];
+                    lo[k] = uint32_t(v);
+                    hi[k] = uint32_t(v >> 32);
+                }
+                score_block(lo, hi, b);
+            } else if (b < n_blocks) {            // ragged last block: rows past the end read as missing everywhere
+                const int r0 = b * GR_BLOCK;
+                const uint64_t *slot = ring + size_t(r0 % GR_RING) * wx + w;
+                uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
+#pragma unroll
+                for (int k = 0; k < GR_BLOCK; ++k) {
+                    uint64_t v = ~0ull;
+                    if (r0 + k < n_rows) v = slot[size_t(k) * wx];
+                    lo[k] = uint32_t(v);
+                    hi[k] = uint32_t(v >> 32);
+                }
+                score_block(lo, hi, b);
             }
-            score_block(lo, hi, n_full);
         }
-        flush_class(c_ref, w_ref, age_ref);
-        flush_class(c_alt, w_alt, age_alt);
-        if (!SKIP_HETS) flush_class(c_het, w_het, age_het);
+        flush_class(c_ref, w_ref);
+        flush_class(c_alt, w_alt);
+        if (!SKIP_HETS) flush_class(c_het, w_het);
         if (live) {
             int32_t vi[32], vn[32];
             counter_values9(c_int, vi);
@@ -368,12 +379,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 a.part_int[o + b * stride] = vi[b] | (vn[b] << 16);
             }
         }
-        if (PAIRS) team_converge(tmask);              // the neighbour has read the last block: the ring may be refilled
-        // switch to the next item: its staging copies are complete (own ones: wait; the team's: barrier), claim the one after
+        // next round: its staging copies are complete (own ones: wait; everybody's: barrier), the ring is free
         cp_async_wait<0>();
-        if (nxt.seg < 0) break;
-        if (w == 0) claim(&slots[buf]);
-        team_sync();
+        if (next_base >= n_items) break;          // the same for every thread of the CTA
+        if (threadIdx.x == 0) s_base[buf] = ticket;        // nobody reads this slot during the round that ends here
+        __syncthreads();                          // everyone is done with this round's staging buffer; the next base is visible
         cur = nxt;
         buf ^= 1;
     }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(JOIN_TILE) k_join_search(
                 const int64_t j = lower_bound_i32(db_pos, rs, re, p);
                 if (j < re && __ldg(db_pos + j) == p) {
                     row = int32_t(j);
-                    if (n_filter > 0 && !contains_i64(filter, n_filter, j + row0_global)) row = -1;
+                    if (filter && !contains_i64(filter, n_filter, j + row0_global)) row = -1;       // an empty list keeps nothing
                 }
             }
         }
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) k_join_mergepath(
                 } else {
                     if (j > 0 && s_db[j - 1] == s_pos[m0 + i]) {
                         int32_t row = int32_t(dc + j - 1);
-                        if (n_filter > 0 && !contains_i64(filter, n_filter, int64_t(row) + row0_global)) row = -1;
+                        if (filter && !contains_i64(filter, n_filter, int64_t(row) + row0_global)) row = -1;
                         match_row[base + m0 + i] = row;
                         if (row >= 0) ++local_cnt;
                     }

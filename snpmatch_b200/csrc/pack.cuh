@@ -7,8 +7,10 @@
 namespace snpm {
 
 // One warp packs one (row, word): lane j reads the code of accession word*32+j.
+// Values below 0 are missing calls (the reference masks every value < 0, snpmatch.py:84-86); values above 2 have no meaning in
+// the reference's data (makedb.py:59) and are counted in *bad (the load is refused).
 __global__ void __launch_bounds__(256) k_pack_int8(const int8_t *__restrict__ snps, int64_t n_rows, int32_t n_acc,
-                                                   int32_t stride, uint64_t *__restrict__ packed) {
+                                                   int32_t stride, uint64_t *__restrict__ packed, int *__restrict__ bad) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -18,7 +20,11 @@ __global__ void __launch_bounds__(256) k_pack_int8(const int8_t *__restrict__ sn
         const int32_t w = int32_t(it - row * stride);
         const int32_t acc = w * 32 + lane;
         uint32_t code = 3u;
-        if (acc < n_acc) code = uint32_t(snps[row * int64_t(n_acc) + acc]) & 3u;
+        if (acc < n_acc) {
+            const int v = snps[row * int64_t(n_acc) + acc];
+            if (v > 2) atomicAdd(bad, 1);
+            code = v < 0 || v > 2 ? 3u : uint32_t(v);
+        }
         const uint32_t lo = __ballot_sync(0xffffffffu, code & 1u);
         const uint32_t hi = __ballot_sync(0xffffffffu, code & 2u);
         if (lane == 0) packed[it] = uint64_t(lo) | (uint64_t(hi) << 32);

@@ -7,6 +7,7 @@ the call raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -205,6 +206,7 @@ SIGNATURES = {
     "snpm_batch_coded_timings": (C.c_int, [_p, _p, C.c_int]),
     "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
     "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
+    "snpm_batch_set_chunk_rows": (C.c_int, [_p, _i32]),
     "snpm_batch_set_result_range": (C.c_int, [_p, _i64, _i64]),
     "snpm_batch_set_row_filter": (C.c_int, [_p, _p, _i64]),
     "snpm_batch_run": (C.c_int, [_p, C.c_int, C.c_int]),
@@ -293,6 +295,7 @@ class Database(object):
         check(lib.snpm_db_create(self.device, self.n_rows, self.n_acc, ptr(self.positions), ptr(self.chr_regions),
                                  len(self.chr_regions), self.row0_global, C.byref(h)))
         self._h = h
+        self._batches = weakref.WeakSet()          # closed before the database: a batch handle points into it
         self.row_words = lib.snpm_db_row_words(h)
         self.packed_bytes = lib.snpm_db_packed_bytes(h)
 
@@ -302,6 +305,9 @@ class Database(object):
             b._scratch = False
             b.close()
             self._scratch = None
+        for b in list(getattr(self, "_batches", ())):
+            b._scratch = False
+            b.close()
         if getattr(self, "_h", None):
             load().snpm_db_destroy(self._h)
             self._h = None
@@ -370,17 +376,23 @@ class Database(object):
     def set_stream(self, cuda_stream):
         check(load().snpm_db_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
-    def scratch_batch(self, offsets, s_chrom_id, s_pos, wei):
+    def scratch_batch(self, offsets, s_chrom_id, s_pos, wei, chunk_rows=CHUNK_ROWS):
         """A Batch that lives with the database: the first call creates it, later calls re-upload into the same device
-        buffers (creating a batch costs a few ms of cudaMalloc / stream / event setup).  Do not close it."""
+        buffers (creating a batch costs a few ms of cudaMalloc / stream / event setup).  Do not close it.
+        chunk_rows: Genotyper's chunk_size (the order-exact kernel sums in chunks of that many rows)."""
         b = getattr(self, "_scratch", None)
         if b is None or b._h is None:
             b = Batch(self, offsets, s_chrom_id, s_pos, wei)
             b._scratch = True
+            b._chunk_rows = CHUNK_ROWS
             self._scratch = b
-        else:
-            b.set_row_filter(None)
-            b.upload(offsets, s_chrom_id, s_pos, wei)
+            if chunk_rows == CHUNK_ROWS:
+                return b
+        b.set_row_filter(None)
+        if getattr(b, "_chunk_rows", CHUNK_ROWS) != chunk_rows:
+            b.set_chunk_rows(chunk_rows)
+            b._chunk_rows = chunk_rows
+        b.upload(offsets, s_chrom_id, s_pos, wei)
         return b
 
     def intersect(self, s_chrom_id, s_pos, algo=JOIN_AUTO):
@@ -404,6 +416,7 @@ class Batch(object):
         h = C.c_void_p()
         check(load().snpm_batch_create(db._h, self.n_samples, *[ptr(a) for a in args], C.byref(h)))
         self._h = h
+        db._batches.add(self)
 
     def _prep(self, offsets, s_chrom_id, s_pos, wei):
         offsets = as_c(offsets, np.int64)
@@ -475,6 +488,10 @@ class Batch(object):
         r = getattr(self, "_res", (0, -1))
         return self.n_samples if r[1] < 0 else r[1]
 
+    def set_chunk_rows(self, rows):
+        """Genotyper chunk_size (snpmatch.py:173): rows per chunk of the order-exact kernel; applies from the next upload()."""
+        check(load().snpm_batch_set_chunk_rows(self._h, int(rows)))
+
     def set_group_chunk(self, rows):
         check(load().snpm_batch_set_group_chunk(self._h, int(rows)))
 
@@ -499,8 +516,14 @@ class Batch(object):
             pass
 
     def set_row_filter(self, rows):
-        rows = as_c(np.unique(np.asarray(rows, dtype=np.int64)), np.int64) if rows is not None else np.zeros(0, np.int64)
-        check(load().snpm_batch_set_row_filter(self._h, ptr(rows) if len(rows) else None, len(rows)))
+        """rows=None clears the filter; an empty array keeps no pair at all (Genotyper.genotyper(filter_pos_ix=...) with nothing
+        in it leaves no common SNP, snpmatch.py:211-216)."""
+        if rows is None:
+            check(load().snpm_batch_set_row_filter(self._h, None, 0))
+            return
+        rows = as_c(np.unique(np.asarray(rows, dtype=np.int64)), np.int64)
+        self._filter_keep = rows if len(rows) else np.zeros(1, np.int64)      # a valid pointer for the empty list
+        check(load().snpm_batch_set_row_filter(self._h, ptr(self._filter_keep), len(rows)))
 
     def run(self, skip_db_hets=False, kernel_mode=0, join_algo=JOIN_AUTO):
         check(load().snpm_batch_run(self._h, int(bool(skip_db_hets)), int(kernel_mode) | (int(join_algo) << 8)))

@@ -236,6 +236,12 @@ def make_sample_fast(positions, chr_regions, n_acc, true_acc, n_db=45000, n_extr
     o = np.argsort(key, kind="stable")
     key, s_code, s_rows = key[o], s_code[o], s_rows[o]
     dp = 1 + rng.poisson(3, size=len(key))
-    _, wei = _pl_weights(rng, s_code, dp)
+    pl, wei = _pl_weights(rng, s_code, dp)
     return dict(chr_ix=(key >> 32).astype(np.int32), pos=(key & 0xFFFFFFFF).astype(np.int32), wei=wei, code=s_code,
-                rows=s_rows, dp=dp.astype(np.float64))
+                rows=s_rows, dp=dp.astype(np.float64), pl=pl)
+
+
+def pl_table(max_pl):
+    """exp(-PL/10) for PL = 0..max_pl, computed as parsers.py:147-148 computes it per marker (PL / -10, then exp): the weight
+    of a marker IS table[PL], bit for bit, so integer PLs are ready-made dictionary codes of the weights."""
+    return np.exp(np.arange(int(max_pl) + 1) / -10.0)

@@ -641,3 +641,83 @@ def test_command_line_inbred_and_cross(lib, small_geno, sample_inbred, golden_ou
     assert os.path.exists(out + "_x.windowscore.txt") and os.path.exists(out + "_x.scores.txt")
     with pytest.raises(SystemExit):                                 # die(): missing input file -> exit 1, as the reference
         snpmatch_b200.main(["inbred", "-i", str(tmp_path / "missing.bed"), "-d", db_path])
+
+
+def test_empty_row_filter_keeps_nothing(lib, small_geno, small_panel, sample_inbred, tmp_path):
+    """Genotyper.genotyper(filter_pos_ix=<empty>) (snpmatch.py:211-216): the reference is left without any common SNP, so
+    every score and count is 0 (not the unfiltered scores); None clears the filter again."""
+    from snpmatch_b200.core import parsers, snpmatch
+    p, s = small_panel, sample_inbred
+    ref = orc.genotyper(p["snps"], p["chrs"], p["chr_regions"], p["positions"], s["chrs"], s["pos"], s["wei"],
+                        filter_pos_ix=np.zeros(0, dtype=np.int64))
+    assert ref.num_snps == 0
+    order, cid, pos = small_geno.prepare_markers(s["chrs"], s["pos"])
+    b = lib.Batch(small_geno.db, [0, len(pos)], cid, pos, s["wei"][order])
+    b.run()
+    b.epilogue()
+    full = {k: v.copy() for k, v in b.fetch().items()}
+    b.set_row_filter(np.zeros(0, dtype=np.int64))
+    b.run()
+    b.epilogue()
+    r = b.fetch()
+    assert int(r["m"][0]) == 0 and np.all(r["score"][0] == 0.0) and np.all(r["ninfo"][0] == 0) and np.all(np.isnan(r["L"][0]))
+    b.set_row_filter(None)
+    b.run()
+    b.epilogue()
+    again = b.fetch()
+    assert int(again["m"][0]) == int(full["m"][0]) and np.array_equal(again["score"][0], full["score"][0])
+    b.close()
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei"], s["dp"])
+    gt = snpmatch.Genotyper(inp, small_geno, str(tmp_path / "e"), run_genotyper=False)
+    res = gt.genotyper(filter_pos_ix=np.zeros(0, dtype=np.int64))
+    assert res.num_snps == 0 and np.all(res.scores == 0)
+
+
+@pytest.mark.parametrize("chunk", [1, 37, 500, 1000, 2500, 100000])
+def test_genotyper_chunk_size_is_part_of_the_summation_order(lib, small_geno, small_panel, sample_inbred, tmp_path, chunk):
+    """Genotyper(chunk_size=...) (snpmatch.py:173,218): the reference adds chunk sums, so its fp64 score depends on the chunk
+    size in the last bits; the order-exact kernel follows any chunk size bit for bit."""
+    from snpmatch_b200.core import parsers, snpmatch
+    p, s = small_panel, sample_inbred
+    ref = orc.genotyper(p["snps"], p["chrs"], p["chr_regions"], p["positions"], s["chrs"], s["pos"], s["wei"], chunk_size=chunk)
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(s["chrs"], s["pos"], s["gt"], s["wei"], s["dp"])
+    res = snpmatch.Genotyper(inp, small_geno, str(tmp_path / "c"), run_genotyper=False, chunk_size=chunk).genotyper()
+    assert res.num_snps == ref.num_snps and np.array_equal(res.ninfo, ref.ninfo)
+    assert np.array_equal(np.asarray(res.scores), ref.scores)
+    b = lib.Batch(small_geno.db, [0, 0], np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)))
+    order, cid, pos = small_geno.prepare_markers(s["chrs"], s["pos"])
+    b.set_chunk_rows(chunk)
+    b.upload([0, len(pos)], cid, pos, s["wei"][order])
+    b.run()
+    b.epilogue()
+    assert np.array_equal(b.fetch()["score"][0], ref.score_f64), "fp64 scores must follow the reference's chunked sums"
+    b.close()
+    # back to the default for the database's shared scratch batch
+    snpmatch.Genotyper(inp, small_geno, str(tmp_path / "d"), run_genotyper=False).genotyper()
+
+
+def test_int8_codes_outside_the_reference_range(lib):
+    """Negative codes are missing calls (the reference masks every value < 0); codes above 2 do not exist in its databases
+    (makedb.py:59) and are refused instead of being folded into 0..3."""
+    n_rows, n_acc = 40, 70
+    pos = (np.arange(n_rows, dtype=np.int32) + 1) * 10
+    regions = np.array([[0, n_rows]], dtype=np.int64)
+    rng = np.random.default_rng(3)
+    snps = rng.integers(-1, 3, size=(n_rows, n_acc)).astype(np.int8)
+    weird = snps.copy()
+    weird[snps == -1] = rng.choice(np.array([-2, -7, -128], dtype=np.int8), size=int((snps == -1).sum()))
+    db = lib.Database(pos, regions, n_acc)
+    db.load_int8(weird)
+    assert np.array_equal(db.read_rows(np.arange(n_rows)), snps)
+    bad = snps.copy()
+    bad[5, 9] = 3
+    with pytest.raises(lib.SnpmError):
+        db.load_int8(bad)
+    with pytest.raises(lib.SnpmError):
+        lib.match_gts_accs(np.full((n_rows, 3), 0.5), bad)
+    s, n = lib.match_gts_accs(np.full((n_rows, 3), 0.5), weird)
+    rs, rn = orc.match_gts_accs(np.full((n_rows, 3), 0.5), weird)
+    assert np.array_equal(s, rs) and np.array_equal(n, rn)
+    db.close()
