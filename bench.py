@@ -147,13 +147,14 @@ def cpu_run_sample(positions, regions, sample, rows, codes):
     return len(c0) * n_acc, dt, score, ninfo
 
 
-def oracle_parity(cpu_score, cpu_ninfo, res, i, exact_score=None):
-    """The bar of tests/test_gpu_coded.py on one sample of a bench run: integers ==, grouped fp64 scores to 1e-12, the
-    order-exact kernel's scores == (when given)."""
+def oracle_parity(cpu_score, cpu_ninfo, res, i, exact_score=None, bitwise=True):
+    """The bar of tests/test_gpu_coded.py on one sample of a bench run: integers ==, grouped fp64 scores to 1e-12, and the
+    order-exact kernel's scores (when given) == on one GPU / to 1e-12 on a sharded panel (per-rank sums added by the reduce:
+    the last bits of an fp64 sum depend on that split; the integers do not)."""
     ok = bool(np.array_equal(cpu_score.astype(np.int64), res["matches"][i]) and np.array_equal(cpu_ninfo, res["ninfo"][i]) and
               np.allclose(cpu_score, res["score"][i], rtol=1e-12, atol=0.0))
     if exact_score is not None:
-        ok = ok and bool(np.array_equal(cpu_score, exact_score))
+        ok = ok and bool(np.array_equal(cpu_score, exact_score) if bitwise else np.allclose(cpu_score, exact_score, rtol=1e-12, atol=0.0))
     return ok
 
 
@@ -402,6 +403,7 @@ def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, wa
             r["exact_kernel_ms"] = float(np.mean(x_kernel))
         # ---- resident arm: the coded samples are on the device; every step does all the per-marker work again
         gb.set_group_chunk(chunk)
+        gb.set_track_pairs(False)                                # scores only: the marker indices of the pairs are not read back
         gb.upload_coded(cs)
 
         def device_step():
@@ -430,6 +432,7 @@ def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, wa
             for _ in range(E2E_DEPTH - 1):
                 bx = lib.Batch(db, h_off[:2] * 0, h_chr[:0], h_pos[:0], h_wei[:0])
                 bx.set_group_chunk(chunk)
+                bx.set_track_pairs(False)
                 batches.append(bx)
             outs = [out] + [out_buffers(ctx, S_loc, n_acc, S_loc) for _ in range(E2E_DEPTH - 1)]
             host_s = {"upload": 0.0, "launch": 0.0, "wait": 0.0}
@@ -488,7 +491,7 @@ def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, wa
                         timed_call("upload", up, batches[k % E2E_DEPTH])
                 return res
 
-            run_pipeline(max(warmup, 1))
+            run_pipeline(max(warmup, E2E_DEPTH))                   # every rotating batch has run once (peer mappings, allocations)
             barrier(ctx)
             rescored[0] = 0
             del flagged_all[:]
@@ -631,16 +634,17 @@ def run_b200_arm(args):
                                               "database labels + chunked matchGTsAccs + likelihoods, NumPy oracle port of "
                                               "snpmatch.py:207-233, database rows held in RAM as int8" % (len(rows), n_acc, n_rows)}
             if not args.cpu_markers:
-                par = {"sample_0_finished_by_rank_0": oracle_parity(cpu_score, cpu_ninfo, h["res"], 0, h["exact_res"]["score"][0])}
+                par = {"sample_0_finished_by_rank_0": oracle_parity(cpu_score, cpu_ninfo, h["res"], 0, h["exact_res"]["score"][0], bitwise=world == 1)}
                 if world > 1:
                     sl = samples[S - 1]
                     rows_l, codes_l = cpu_prepare_sample(sl, n_acc, 0)
                     _, _, ls, ln = cpu_run_sample(positions, regions, sl, rows_l, codes_l)
                     par["sample_%d_finished_by_rank_%d" % (S - 1, world - 1)] = oracle_parity(
-                        ls, ln, {k: last[k][None] for k in last}, 0, last_exact["score"])
+                        ls, ln, {k: last[k][None] for k in last}, 0, last_exact["score"], bitwise=False)
                 line["cpu_baseline"]["parity"] = bool(all(par.values()))
                 line["cpu_baseline"]["parity_detail"] = par
-                line["cpu_baseline"]["parity_bar"] = "integers (matches = int(score), informative sites) ==; counting-kernel fp64 scores rtol 1e-12; order-exact kernel scores =="
+                line["cpu_baseline"]["parity_bar"] = "integers (matches = int(score), informative sites) ==; counting-kernel fp64 scores rtol 1e-12; order-exact kernel scores %s" % (
+                    "==" if world == 1 else "rtol 1e-12 (sums of per-rank partial sums)")
     h["batch"].close()
     extras = {}
     if not args.headline_only:

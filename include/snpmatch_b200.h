@@ -168,12 +168,17 @@ int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64
  * order (ref, het, alt) into wtable (n_wtable <= 65536 distinct weight values, finite and >= 0; for a VCF the code is the
  * integer PL and wtable[k] = exp(-k/10)).  10 bytes per marker cross the PCIe bus and the host does no per-marker work.
  * snpm_batch_run(mode 2) then joins, builds a sort key per matched pair from its codes (called class | its code | code of the
- * class with fewer distinct weights | code of the other), sorts every sample's pairs by that key (stable segmented radix
- * sort), marks where each class weight changes and scores with the persistent counting kernel k_score_grouped2.  Replaces
+ * class with fewer distinct weights | code of the other), orders every sample's pairs by that key (dense ids of the distinct keys
+ * of a sample + one stable partition pass), marks where each class weight changes and scores with the persistent counting kernel
+ * k_score_grouped2.  A sample with more than 2048 distinct weight triples is reported through snpm_batch_guard_counts (re-score it).  Replaces
  * snpm_group_markers + snpm_batch_upload_grouped*; results are identical (counts do not depend on the order inside a group).
  * Group chunks (snpm_batch_set_group_chunk) must be multiples of 16 and at most 496 rows for coded batches. */
 int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
                             const uint16_t *codes, const double *wtable, int32_t n_wtable);
+/* coded batches: keep (1, default) or drop (0) the marker index of every matched pair in grouped order.  The scoring path only
+ * needs the panel rows; with 0 snpm_batch_fetch_pairs answers SNPM_E_STATE for coded batches and the grouping moves one array
+ * instead of two. */
+int snpm_batch_set_track_pairs(snpm_batch *b, int on);
 /* device times (ms) of the last coded run's stages: [0] marker expansion + join + compaction, [1] key sort + change masks,
  * [2] scoring kernel, [3] combine; n >= 4 */
 int snpm_batch_coded_timings(snpm_batch *b, float *ms, int n);

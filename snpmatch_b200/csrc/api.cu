@@ -151,6 +151,38 @@ int snpm_db_create(int device, int64_t n_rows, int32_t n_acc, const int32_t *pos
         if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
         if (e != cudaSuccess) { snpm_db_destroy(db); return fail(SNPM_E_CUDA, "snpm_db_create: position index: %s", cudaGetErrorString(e)); }
     }
+    {   // exact position index (bitmap + first row per word) when the genome fits 2^31 bits
+        std::vector<int64_t> bm(size_t(n_chr) + 1, 0);
+        int64_t bits = 0;
+        for (int c = 0; c < n_chr; ++c) {
+            bm[size_t(c)] = bits;
+            const int64_t last = chr_regions[2 * c + 1] > chr_regions[2 * c] ? int64_t(positions[chr_regions[2 * c + 1] - 1]) : -1;
+            bits += ((last + 1) + 63) / 64 * 64;
+        }
+        bm[size_t(n_chr)] = bits;
+        static const bool no_bitmap = getenv("SNPM_JOIN_BITMAP") && !strcmp(getenv("SNPM_JOIN_BITMAP"), "0");      // measurement switch
+        if (bits > 0 && bits <= (int64_t(1) << 31) && n_rows > 0 && !no_bitmap) {
+            const int64_t n_words = bits / 64;
+            e = cudaMalloc(&db->d_bitmap, size_t(n_words) * 8);
+            if (e == cudaSuccess) e = cudaMalloc(&db->d_bm_first_row, size_t(n_words) * 4);
+            if (e == cudaSuccess) e = cudaMalloc(&db->d_bm_off, (size_t(n_chr) + 1) * 8);
+            if (e == cudaSuccess) e = cudaMemsetAsync(db->d_bitmap, 0, size_t(n_words) * 8, db->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(db->d_bm_off, bm.data(), (size_t(n_chr) + 1) * 8, cudaMemcpyHostToDevice, db->stream);
+            if (e == cudaSuccess) {
+                k_bitmap_set<<<int(ceil_div64(n_rows, 256)), 256, 0, db->stream>>>(db->d_pos, db->d_chr_regions, n_chr, db->d_bm_off, n_rows, db->d_bitmap);
+                k_bitmap_rows<<<int(ceil_div64(n_words, 256)), 256, 0, db->stream>>>(db->d_pos, db->d_chr_regions, n_chr, db->d_bm_off, n_words, db->d_bm_first_row);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+            if (e != cudaSuccess) {                            // the bitmap is an optimisation: fall back to the bucket search
+                cudaGetLastError();
+                if (db->d_bitmap) cudaFree(db->d_bitmap);
+                if (db->d_bm_first_row) cudaFree(db->d_bm_first_row);
+                if (db->d_bm_off) cudaFree(db->d_bm_off);
+                db->d_bitmap = nullptr; db->d_bm_first_row = nullptr; db->d_bm_off = nullptr;
+            }
+        }
+    }
     *out = db;
     return SNPM_OK;
 }
@@ -164,6 +196,9 @@ int snpm_db_destroy(snpm_db *db) {
     if (db->d_chr_regions) cudaFree(db->d_chr_regions);
     if (db->d_bucket) cudaFree(db->d_bucket);
     if (db->d_bucket_off) cudaFree(db->d_bucket_off);
+    if (db->d_bitmap) cudaFree(db->d_bitmap);
+    if (db->d_bm_first_row) cudaFree(db->d_bm_first_row);
+    if (db->d_bm_off) cudaFree(db->d_bm_off);
     if (db->scratch_batch_) { snpm_batch_destroy(db->scratch_batch_); db->scratch_batch_ = nullptr; }
     db->scratch.release();
     if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
@@ -721,16 +756,21 @@ int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *off
     SNPM_TRY(b->d_codes.ensure(size_t(n) * 6));
     SNPM_TRY(b->d_wtable.ensure(size_t(n_wtable) * 8));
     SNPM_TRY(b->d_key_a.ensure(size_t(n) * key_bytes));
-    SNPM_TRY(b->d_key_b.ensure(size_t(n) * key_bytes));
-    SNPM_TRY(b->d_idx_a.ensure(size_t(n) * 4));
-    SNPM_TRY(b->d_idx_b.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_pair_db_tmp.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_pair_s_tmp.ensure(size_t(n) * 4));
     SNPM_TRY(b->d_tile_sample.ensure(std::max<size_t>(tile_sample.size(), 1) * 4));
     SNPM_TRY(b->d_tile_first.ensure(size_t(n_samples + 1) * 4));
-    SNPM_TRY(b->d_tile_hist.ensure(std::max<size_t>(tile_sample.size(), 1) * ((size_t(2) << RS_MAX_BITS) * 4 + 8)));      // two count tables + the tile ranges
+    SNPM_TRY(b->d_tile_hist.ensure(std::max<size_t>(tile_sample.size(), 1) * (size_t(GH_MAX_GROUPS) * 4 + 8)));      // id counts per tile + the tile ranges
     SNPM_TRY(b->d_blk_chg.ensure(size_t(std::max<int64_t>(nseg, 1)) * size_t(b->gchunk / GR_BLOCK) * 8));
     SNPM_TRY(b->d_work_counter.ensure(256));
+    SNPM_TRY(b->d_hash.ensure(size_t(n_samples) * GH_SLOTS * 8));
+    SNPM_TRY(b->d_slot_gid.ensure(size_t(n_samples) * GH_SLOTS * 2));
+    SNPM_TRY(b->d_ngroups.ensure(size_t(n_samples) * 4));
+    SNPM_TRY(b->d_group_overflow.ensure(size_t(n_samples) * 4));
+    SNPM_TRY(b->d_gkeys.ensure(size_t(n_samples) * GH_MAX_GROUPS * key_bytes));
+    SNPM_TRY(b->d_gw.ensure(size_t(n_samples) * GH_MAX_GROUPS * 32));
+    SNPM_TRY(b->d_goff.ensure(size_t(n_samples) * (GH_MAX_GROUPS + 1) * 4));
+    SNPM_TRY(b->d_gid.ensure(size_t(n) * 2));
     cudaStream_t st = b->copy_stream;
     SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_inputs_free, 0));
     // small host-built tables are staged in buffers the batch owns (the copies are asynchronous)
@@ -793,6 +833,12 @@ int snpm_batch_set_result_range(snpm_batch *b, int64_t first_sample, int64_t n_s
     return SNPM_OK;
 }
 
+int snpm_batch_set_track_pairs(snpm_batch *b, int on) {
+    if (!b) return fail(SNPM_E_ARG, "snpm_batch_set_track_pairs: NULL batch");
+    b->track_pairs = on != 0;
+    return SNPM_OK;
+}
+
 int snpm_batch_set_chunk_rows(snpm_batch *b, int32_t rows) {
     if (!b || rows < 1 || rows > 1000000) return fail(SNPM_E_ARG, "snpm_batch_set_chunk_rows: 1..1000000 rows");
     b->chunk_rows_req = rows;
@@ -822,7 +868,8 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_win_ident, &b->d_win_amb, &b->d_win_row_off, &b->d_row_acc, &b->d_row_score, &b->d_row_ninfo, &b->d_row_L, &b->d_row_ident, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
                       &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard, &b->d_runs,
                       &b->d_codes, &b->d_wtable, &b->d_key_a, &b->d_key_b, &b->d_idx_a, &b->d_idx_b, &b->d_pair_db_tmp, &b->d_pair_s_tmp,
-                      &b->d_tile_sample, &b->d_tile_first, &b->d_tile_hist, &b->d_blk_chg, &b->d_work_counter};
+                      &b->d_tile_sample, &b->d_tile_first, &b->d_tile_hist, &b->d_blk_chg, &b->d_work_counter, &b->d_hash, &b->d_slot_gid, &b->d_ngroups,
+                      &b->d_group_overflow, &b->d_gkeys, &b->d_gw, &b->d_goff};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
@@ -878,10 +925,10 @@ static int batch_join(snpm_batch *b, int algo) {
             k_expand_runs<<<int(ceil_div64(b->pending_runs * 32, 256)), 256, 0, st>>>(d_end, reinterpret_cast<const uint16_t *>(d_end + b->pending_runs),
                                                                                  int32_t(b->pending_runs), n, b->d_gid.as<uint16_t>(), b->d_runs_bad);
         }
-        if (b->pending_expand & 2) k_expand_packed<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_wei_idx.as<uint32_t>(), n, b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>());
+        // packed chromosome/position words (bit 1) are unpacked by the join itself (grouped batches always take k_join_search)
         if (b->pending_expand & 4) k_expand_chrom<<<int(ceil_div64(n, 256)), 256, 0, st>>>(b->d_chrom8.as<uint8_t>(), n, b->d_chrom.as<int32_t>());
         SNPM_KERNEL_CHECK();
-        b->pending_expand = 0;
+        b->pending_expand &= 2;                               // the packed words stay where they are
     }
     // run ends that do not ascend were counted by k_expand_runs: reported at wait / fetch (status slot 4, next to ids outside the table)
     if (b->grouped && b->d_runs_bad) SNPM_CUDA(cudaMemcpyAsync(b->d_status.as<int>() + 4, b->d_runs_bad, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -904,19 +951,24 @@ static int batch_join(snpm_batch *b, int algo) {
             k_join_search<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), n, b->d_off.as<int64_t>(), S,
                                                             db->d_pos, db->d_chr_regions, db->n_chr, db->d_bucket, db->d_bucket_off, db->bucket_shift,
                                                             filter, b->n_filter, db->row0_global,
-                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>(), (b->grouped && !b->coded) ? 0 : 1);
+                                                            b->d_match_row.as<int32_t>(), b->d_tile_cnt.as<int32_t>(), b->d_status.as<int>(), (b->grouped && !b->coded) ? 0 : 1,
+                                                            db->d_bitmap, db->d_bm_first_row, db->d_bm_off,
+                                                            (b->grouped && (b->pending_expand & 2)) ? b->d_wei_idx.as<uint32_t>() : nullptr);
         SNPM_KERNEL_CHECK();
         k_scan_tiles<<<1, 1024, 0, st>>>(b->d_tile_cnt.as<int32_t>(), n_tiles, b->d_tile_off.as<int32_t>(), b->d_prefix.as<int32_t>() + n);
         SNPM_KERNEL_CHECK();
         if (b->coded) {
+            unsigned long long *hash = b->d_hash.as<unsigned long long>();
+            SNPM_CUDA(cudaMemsetAsync(b->d_group_overflow.p, 0, size_t(S) * 4, st));
+            SNPM_CUDA(cudaMemsetAsync(hash, 0, size_t(S) * GH_SLOTS * 8, st));
             if (b->key_bits <= 32)
                 k_scatter_pairs_coded<uint32_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
                         b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
-                        b->d_key_a.as<uint32_t>(), b->d_idx_a.as<uint32_t>(), b->d_status.as<int>());
+                        b->d_key_a.as<uint32_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>());
             else
                 k_scatter_pairs_coded<uint64_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
                         b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
-                        b->d_key_a.as<uint64_t>(), b->d_idx_a.as<uint32_t>(), b->d_status.as<int>());
+                        b->d_key_a.as<uint64_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>());
         } else if (b->grouped)
             k_scatter_pairs_grouped<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(),
                                                                       b->d_gid.as<uint16_t>(), b->n_gtable, b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(),
@@ -939,78 +991,45 @@ static int batch_join(snpm_batch *b, int algo) {
 
 }  // extern "C" (templates below)
 
-// coded batches: order every sample's pairs by their sort key (stable segmented LSD radix sort), resolve the sorted
-// permutation into the pair arrays the scoring kernels read, and mark the weight changes per 16-row block
+// coded batches: dense group ids from the per-sample key tables, ONE stable partition pass that moves the panel rows into
+// (group, position) order, block words (change masks + first group) from the group table
 template <typename KeyT>
 static int batch_group_sort_t(snpm_batch *b) {
     snpm_db *db = b->db;
     cudaStream_t st = db->stream;
     const int tiles = int(b->n_sort_tiles);
     if (tiles == 0 || b->n == 0) return SNPM_OK;
-    const int passes = (b->key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
-    const int per = (b->key_bits + passes - 1) / passes;
-    KeyT *ka = b->d_key_a.as<KeyT>(), *kb = b->d_key_b.as<KeyT>();
-    uint32_t *ia = b->d_idx_a.as<uint32_t>(), *ib = b->d_idx_b.as<uint32_t>();
     const int32_t *mstart = b->d_mstart.as<int32_t>(), *tsample = b->d_tile_sample.as<int32_t>(), *tfirst = b->d_tile_first.as<int32_t>();
-    const size_t hist_elems = size_t(tiles) << RS_MAX_BITS;
-    uint32_t *ha = b->d_tile_hist.as<uint32_t>(), *hb = ha + hist_elems;        // ping-pong: this pass's counts / the next pass's
-    int2 *range = reinterpret_cast<int2 *>(hb + hist_elems);
-    static bool attr = false;
-    if (!attr) {
-        SNPM_CUDA(cudaFuncSetAttribute(k_radix_pass<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        SNPM_CUDA(cudaFuncSetAttribute(k_radix_pass<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
+    uint32_t *hist = b->d_tile_hist.as<uint32_t>();
+    int2 *range = reinterpret_cast<int2 *>(hist + (size_t(tiles) << 11));
+    static bool gattr = false;
+    if (!gattr) {
+        SNPM_CUDA(cudaFuncSetAttribute(k_group_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        gattr = true;
     }
+    KeyT *gkeys = b->d_gkeys.as<KeyT>();
+    k_group_rank<KeyT><<<int(b->S), 1024, 0, st>>>(b->d_hash.as<unsigned long long>(), b->d_wtable.as<double>(), b->code_bits, b->d_slot_gid.as<uint16_t>(),
+                                                   b->d_ngroups.as<int32_t>(), gkeys, b->d_gw.as<double4>(), b->d_group_overflow.as<int>());
     k_tile_ranges<<<(tiles + 255) / 256, 256, 0, st>>>(mstart, tsample, tfirst, tiles, range);
-    {
-        const int bits0 = std::min(per, b->key_bits);
-        k_radix_hist<KeyT><<<tiles, RS_THREADS, size_t(1 << bits0) * 4, st>>>(ka, range, 0, bits0, ha);
-    }
+    k_group_ids<KeyT><<<tiles, RS_THREADS, 0, st>>>(b->d_key_a.as<KeyT>(), range, tsample, b->d_hash.as<unsigned long long>(), b->d_slot_gid.as<uint16_t>(),
+                                                    b->d_ngroups.as<int32_t>(), b->d_gid.as<uint16_t>(), hist);
+    SNPM_CUDA(cudaMemsetAsync(b->d_blk_chg.p, 0, size_t(std::max<int64_t>(b->nseg_cap, 1)) * size_t(b->gchunk / GR_BLOCK) * 8, st));
+    k_group_place<<<tiles, RS_THREADS, size_t(GH_MAX_GROUPS) * 20, st>>>(b->d_gid.as<uint16_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
+                                                                        b->d_pair_db.as<int32_t>(), b->track_pairs ? b->d_pair_s.as<int32_t>() : nullptr, mstart, tsample,
+                                                                        tfirst, range, hist, b->d_ngroups.as<int32_t>(), b->d_goff.as<int32_t>());
+    k_group_marks<KeyT><<<int(b->S), 1024, 0, st>>>(b->d_goff.as<int32_t>(), gkeys, b->d_ngroups.as<int32_t>(), mstart, b->d_seg_off.as<int32_t>(), b->gchunk,
+                                                    b->code_bits, b->d_blk_chg.as<unsigned long long>());
     SNPM_KERNEL_CHECK();
-    b->launches += 2;
-    // the next digit's tile counts: booked by the scatter of the pass before (atomics), or by a k_radix_hist launch of their own
-    static const bool fused_hist = !(getenv("SNPM_SORT_FUSED") && !strcmp(getenv("SNPM_SORT_FUSED"), "0"));      // measurement switch
-    for (int p = 0; p < passes; ++p) {
-        const int shift = p * per, bits = std::min(per, b->key_bits - shift), bins = 1 << bits;
-        const int nshift = shift + bits, nbits = p + 1 < passes ? std::min(per, b->key_bits - nshift) : 0;
-        const size_t smem = size_t(bins) * 20;
-        if (p > 0 && !fused_hist) {
-            k_radix_hist<KeyT><<<tiles, RS_THREADS, size_t(bins) * 4, st>>>(ka, range, shift, bits, ha);
-            b->launches += 1;
-        }
-        if (p == passes - 1) {
-            k_radix_pass<KeyT, true><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
-                                                                      b->d_pair_db.as<int32_t>(), b->d_pair_s.as<int32_t>(), mstart, tsample, tfirst, range, ha, nullptr,
-                                                                      shift, bits, 0, 0);
-        } else {
-            if (fused_hist) SNPM_CUDA(cudaMemsetAsync(hb, 0, (size_t(tiles) << nbits) * 4, st));
-            k_radix_pass<KeyT, false><<<tiles, RS_THREADS, smem, st>>>(ka, ia, kb, ib, nullptr, nullptr, nullptr, nullptr, mstart, tsample, tfirst, range, ha,
-                                                                       fused_hist ? hb : nullptr, shift, bits, nshift, nbits);
-        }
-        SNPM_KERNEL_CHECK();
-        std::swap(ka, kb);
-        std::swap(ia, ib);
-        if (fused_hist) std::swap(ha, hb);
-        b->launches += 1;
-    }
-    b->sorted_key = ka;                                           // after the last swap
-    int64_t max_ns = 0;
-    for (int64_t s = 0; s < b->S; ++s) max_ns = std::max(max_ns, b->h_off[size_t(s) + 1] - b->h_off[size_t(s)]);
-    dim3 mgrid(unsigned(ceil_div64(max_ns, 256)), unsigned(b->S));
-    k_group_masks<KeyT><<<mgrid, 256, 0, st>>>(ka, mstart, b->d_seg_off.as<int32_t>(), b->gchunk, b->code_bits, b->d_blk_chg.as<unsigned long long>());
-    SNPM_KERNEL_CHECK();
-    b->launches += 1;
+    b->launches += 5;
     return SNPM_OK;
 }
 
-template <typename KeyT>
 static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
     snpm_db *db = b->db;
     cudaStream_t st = db->stream;
-    Group2Args<KeyT> g = {};
+    Group2Args g = {};
     g.packed = db->d_packed; g.stride = db->stride; g.pair_db = b->d_pair_db.as<int32_t>();
-    g.pair_key = static_cast<const KeyT *>(b->sorted_key); g.blk_chg = b->d_blk_chg.as<unsigned long long>();
-    g.wtable = b->d_wtable.as<double>(); g.code_bits = b->code_bits;
+    g.blk_chg = b->d_blk_chg.as<unsigned long long>(); g.gw = b->d_gw.as<double>();
     g.seg_off = b->d_seg_off.as<int32_t>(); g.mstart = b->d_mstart.as<int32_t>(); g.S = int32_t(b->S); g.chunk = b->gchunk;
     g.part_score = b->d_part_score.as<double>(); g.part_int = b->d_part_int.as<int32_t>(); g.a_pad = db->stride * 32;
     // a row of up to 36 words (1135 accessions) is one slice; wider rows are cut into warp-aligned slices of 32 words
@@ -1023,35 +1042,26 @@ static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
     g.work_counter = b->d_work_counter.as<unsigned int>();
     const int64_t n_items = b->S * jmax * g.n_slices;
     if (n_items >= (int64_t(1) << 31) - (int64_t(1) << 20)) return fail(SNPM_E_ARG, "snpm_batch_run: %lld work items exceed the 2^31 limit", (long long)n_items);
-    const size_t smem = size_t(g.teams) * g2_team_smem<KeyT>(g.wx, g.chunk);
+    const size_t smem = size_t(g.teams) * g2_team_smem(g.wx, g.chunk);
     if (smem > 226 * 1024) return fail(SNPM_E_ARG, "snpm_batch_run: group chunk %d needs %zu bytes of shared memory", g.chunk, smem);
-    // L2 prefetch distance in blocks (measurement switch SNPM_G2_PF = 0 / 6 / 12; default below)
-    static const int pf = getenv("SNPM_G2_PF") ? atoi(getenv("SNPM_G2_PF")) : G2_PF_DEFAULT;
     SNPM_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned int), st));
     const int grid = int(std::min<int64_t>(db->n_sm, ceil_div64(n_items, g.teams)));
-#define G2_LAUNCH(SK, WXV, PFV)                                                                                                     \
-    do {                                                                                                                            \
-        static bool attr_ = false;                                                                                                  \
-        if (!attr_) {                                                                                                               \
-            SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<KeyT, SK, WXV, PFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
-            attr_ = true;                                                                                                           \
-        }                                                                                                                           \
-        k_score_grouped2<KeyT, SK, WXV, PFV><<<grid, G2_THREADS, smem, st>>>(g);                                                    \
-    } while (0)
-#define G2_LAUNCH_PF(SK, WXV)                                                          \
-    do {                                                                               \
-        if (pf <= 0) G2_LAUNCH(SK, WXV, 0);                                            \
-        else if (pf <= 6) G2_LAUNCH(SK, WXV, 6);                                       \
-        else G2_LAUNCH(SK, WXV, 12);                                                   \
+#define G2_LAUNCH(SK, WXV)                                                                                                      \
+    do {                                                                                                                        \
+        static bool attr_ = false;                                                                                              \
+        if (!attr_) {                                                                                                           \
+            SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<SK, WXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+            attr_ = true;                                                                                                       \
+        }                                                                                                                       \
+        k_score_grouped2<SK, WXV><<<grid, G2_THREADS, smem, st>>>(g);                                                           \
     } while (0)
     if (g.wx == G2_WX) {
-        if (skip_db_hets) G2_LAUNCH_PF(true, G2_WX); else G2_LAUNCH_PF(false, G2_WX);
+        if (skip_db_hets) G2_LAUNCH(true, G2_WX); else G2_LAUNCH(false, G2_WX);
     } else if (g.wx == 32) {
-        if (skip_db_hets) G2_LAUNCH_PF(true, 32); else G2_LAUNCH_PF(false, 32);
+        if (skip_db_hets) G2_LAUNCH(true, 32); else G2_LAUNCH(false, 32);
     } else {
-        if (skip_db_hets) G2_LAUNCH(true, 0, 0); else G2_LAUNCH(false, 0, 0);
+        if (skip_db_hets) G2_LAUNCH(true, 0); else G2_LAUNCH(false, 0);
     }
-#undef G2_LAUNCH_PF
 #undef G2_LAUNCH
     SNPM_KERNEL_CHECK();
     b->launches += 1;
@@ -1115,7 +1125,7 @@ int snpm_batch_run(snpm_batch *b, int skip_db_hets, int mode) {
         if (b->key_bits <= 32) SNPM_TRY(batch_group_sort_t<uint32_t>(b)); else SNPM_TRY(batch_group_sort_t<uint64_t>(b));
         rec(b, SNPM_EV_JOIN);                      // for coded batches "join" ends after the grouping: score_ms is the scoring kernel alone
         if (b->nseg_cap > 0 && b->n > 0) {
-            if (b->key_bits <= 32) SNPM_TRY(launch_grouped2<uint32_t>(b, skip_db_hets != 0)); else SNPM_TRY(launch_grouped2<uint64_t>(b, skip_db_hets != 0));
+            SNPM_TRY(launch_grouped2(b, skip_db_hets != 0));
         }
         rec(b, SNPM_EV_SCORE);
         dim3 cgrid((a.a_pad + 31) / 32, unsigned(b->S));
@@ -1235,7 +1245,8 @@ int snpm_batch_epilogue(snpm_batch *b) {
             SNPM_TRY(b->d_guard.ensure(size_t(b->S) * 4));
             SNPM_CUDA(cudaMemsetAsync(b->d_guard.as<int32_t>() + r0, 0, size_t(rn) * 4, db->stream));
             dim3 fgrid((db->n_acc + 255) / 256, unsigned(rn));
-            k_grouped_finalize<<<fgrid, 256, 0, db->stream>>>(b->d_red.as<double>() + r0 * pitch, db->n_acc, b->d_guard.as<int32_t>() + r0);
+            k_grouped_finalize<<<fgrid, 256, 0, db->stream>>>(b->d_red.as<double>() + r0 * pitch, db->n_acc, b->d_guard.as<int32_t>() + r0,
+                                                              b->coded ? b->d_group_overflow.as<int>() + r0 : nullptr);
             SNPM_KERNEL_CHECK();
             b->launches += 1;
         }
@@ -1509,6 +1520,7 @@ int snpm_batch_fetch_wait(snpm_batch *b) {
 int snpm_batch_fetch_pairs(snpm_batch *b, int64_t s, int64_t *db_idx, int64_t *s_idx, int64_t capacity, int64_t *m) {
     if (!b || s < 0 || s >= b->S || !m) return fail(SNPM_E_ARG, "snpm_batch_fetch_pairs: bad arguments");
     if (!b->ran) return fail(SNPM_E_STATE, "snpm_batch_fetch_pairs: run the batch first");
+    if (b->coded && !b->track_pairs) return fail(SNPM_E_STATE, "snpm_batch_fetch_pairs: the pairs of this coded batch are not tracked (snpm_batch_set_track_pairs)");
     snpm_db *db = b->db;
     SNPM_CUDA(cudaSetDevice(db->device));
     int32_t range[2];

@@ -101,6 +101,9 @@ struct snpm_db {
     int32_t *d_bucket = nullptr;        // coarse position index (k_build_buckets)
     int32_t *d_bucket_off = nullptr;    // [n_chr + 1]
     int bucket_shift = 0;
+    unsigned long long *d_bitmap = nullptr;   // exact position index (k_bitmap_set / k_bitmap_rows), or null: bucket search
+    int32_t *d_bm_first_row = nullptr;
+    int64_t *d_bm_off = nullptr;         // [n_chr + 1] first bit of every chromosome
     std::vector<int64_t> h_chr_regions;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -146,9 +149,9 @@ struct snpm_batch {
     int32_t n_wtable = 0, code_bits = 0, key_bits = 0;
     int64_t n_sort_tiles = 0;
     snpm::DevBuf d_codes, d_wtable, d_key_a, d_key_b, d_idx_a, d_idx_b, d_pair_db_tmp, d_pair_s_tmp, d_tile_sample, d_tile_first,
-                 d_tile_hist, d_blk_chg, d_work_counter;
+                 d_tile_hist, d_blk_chg, d_work_counter, d_hash, d_slot_gid, d_ngroups, d_group_overflow, d_gkeys, d_gw, d_goff;
+    bool track_pairs = true;           // coded runs: also move the marker index of every pair into grouped order (snpm_batch_fetch_pairs)
     cudaEvent_t ev_joined = nullptr;   // coded runs: after join + compaction, before the key sort (snpm_batch_coded_timings)
-    const void *sorted_key = nullptr;  // coded runs: the key buffer that holds the sorted keys
     snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard, d_runs;
     std::vector<double> h_gtable;
     std::vector<int32_t> h_tiles;      // coded mode: tile_first [S+1] | tile_sample [tiles] (staging of the asynchronous copy)

@@ -3,15 +3,21 @@
 // The host uploads what a parser has in hand (parsers.py:141-157): markers in position order as (chromosome id, position)
 // words plus, per marker, three dictionary codes (ref, het, alt) into a table of distinct weight values (for a VCF the code
 // IS the integer PL and the table is exp(-PL/10)).  After the (chrom, pos) join the kernels here
-//   1. give every matched pair a sort key  [called class | code of the called class | code of the slow class | code of the
-//      fast class]  (k_scatter_pairs_coded) — the hierarchical order that makes every class weight change as rarely as
-//      possible along a sample (the counting kernel reads a class counter out only when THAT class's weight changes),
-//   2. sort the pairs of every sample by that key with a stable, segmented LSD radix sort (k_radix_hist once, then one
-//      k_radix_pass per digit of up to 11 bits: offsets from the tile histograms, warp-aggregated ranks via match.any, scatter,
-//      next digit's histogram on the way) — deterministic, position order is kept inside a group,
-//   3. mark, per block of 16 sorted rows, where each class weight changes (k_group_masks).
-// Replaces the per-sample work of Genotyper.genotyper's chunk loop set-up (snpmatch.py:218-227) in the grouped formulation;
-// results do not depend on the order (counts are order-free), only the speed does.
+//   1. give every matched pair a key  [called class | code of the called class | code of the slow class | code of the fast
+//      class]  — ordering by it is the hierarchical order that makes every class weight change as rarely as possible along a
+//      sample (the counting kernel reads a class counter out only when THAT class's weight changes) — and collect the
+//      distinct keys of every sample in a small hash table (k_scatter_pairs_coded),
+//   2. sort each sample's keys (a few hundred): the rank of a key is the dense id of its group; the group's three weights go
+//      into a table (k_group_rank),
+//   3. look the id of every pair up and count ids per tile of 2048 pairs (k_group_ids),
+//   4. move the panel rows of the pairs, ONCE, from position order to (id, position) order with a stable partition
+//      (k_group_place: offsets from the tile counts, ranks in pair order, scatter) — deterministic,
+//   5. mark, per block of 16 grouped rows, where each class weight changes and which group the block starts in
+//      (k_group_marks), from the group table alone.
+// A radix sort over the ~30-bit key did the same in three scatter passes of key + permutation (0.20 ms for 2.9 M pairs against
+// a 0.27 ms scoring kernel: scattered 4-byte stores are the cost, one LSU transaction each); the dense ids need one pass over
+// one array.  Replaces the per-sample work of Genotyper.genotyper's chunk loop set-up (snpmatch.py:218-227) in the grouped
+// formulation; results do not depend on the order (counts are order-free), only the speed does.
 #pragma once
 #include "common.cuh"
 #include "join.cuh"
@@ -20,8 +26,7 @@ namespace snpm {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_PER_THREAD = 8;
-constexpr int RS_TILE = RS_THREADS * RS_PER_THREAD;       // pairs per sort tile
-constexpr int RS_MAX_BITS = 11;                            // digit width (2048 bins: 8 warps x 2048 x u16 = 32 KB of shared memory)
+constexpr int RS_TILE = RS_THREADS * RS_PER_THREAD;       // pairs per tile of the partition pass
 
 // class indices of the scoring kernels: 0 ref, 1 alt, 2 het.  Called class c -> (slow, fast) = the remaining classes, the one
 // whose weight takes fewer distinct values first (het for homozygous calls: 3*DP-like PLs; ref for het calls).
@@ -37,18 +42,56 @@ __host__ __device__ __forceinline__ uint32_t gs_code(KeyT key, int which, int b)
     return uint32_t(key >> gs_field_shift(c, which, b)) & ((1u << b) - 1u);
 }
 
-// as k_scatter_pairs (join.cuh), the payload of a pair being its sort key and its own index (the sort's initial permutation)
+// ---- dense group ids: one open-addressing hash table of sort keys per sample -------------------------------------------
+// A sample carries a few hundred distinct weight triples (740 among the 50 000 markers of a synthetic PL sample, 796 among
+// the 7545 of 701_501.filter.vcf), so its pairs can be ordered with ONE stable partition pass over dense ids instead of a
+// radix sort over the ~30-bit key: the keys of a sample are collected in its table while the pairs are compacted
+// (gh_insert), sorted (k_group_rank: the id of a key is its rank, so ordering by id is ordering by key), looked up per pair
+// (k_group_ids) and the pairs placed (k_group_place).  A sample with more than GH_MAX_GROUPS distinct triples is flagged
+// (its groups would be a handful of rows each: the order-exact kernel is the right tool) and re-scored by the caller.
+constexpr int GH_SLOTS = 4096;            // slots per sample
+constexpr int GH_MAX_GROUPS = 2048;       // dense ids per sample: one 11-bit digit
+
+__device__ __forceinline__ uint32_t gh_hash(unsigned long long key) { return uint32_t((key * 0x9E3779B97F4A7C15ull) >> 52); }
+// a slot holds key + 1 (0 = empty); slots only ever change from empty to taken
+__device__ __forceinline__ void gh_insert(unsigned long long *__restrict__ table, unsigned long long key, int *overflow) {
+    const unsigned long long want = key + 1ull;
+    uint32_t h = gh_hash(key);
+    for (int probe = 0; probe < GH_SLOTS; ++probe) {
+        unsigned long long cur = __ldcg(table + h);
+        if (cur == 0ull) cur = atomicCAS(table + h, 0ull, want);
+        if (cur == 0ull || cur == want) return;
+        h = (h + 1u) & uint32_t(GH_SLOTS - 1);
+    }
+    atomicExch(overflow, 1);
+}
+__device__ __forceinline__ uint32_t gh_find(const unsigned long long *__restrict__ table, unsigned long long key) {
+    const unsigned long long want = key + 1ull;
+    uint32_t h = gh_hash(key);
+    for (int probe = 0; probe < GH_SLOTS; ++probe) {
+        const unsigned long long cur = __ldg(table + h);
+        if (cur == want || cur == 0ull) break;
+        h = (h + 1u) & uint32_t(GH_SLOTS - 1);
+    }
+    return h;
+}
+
+// as k_scatter_pairs (join.cuh), the payload of a pair being its key, which also goes into its sample's key table (lanes of
+// a warp that hold the same key of the same sample insert once)
 template <typename KeyT>
 __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
         const int32_t *__restrict__ match_row, int64_t n, const int32_t *__restrict__ tile_off, const uint16_t *__restrict__ codes,
         const double *__restrict__ wtable, int32_t n_table, int32_t code_bits, int32_t *__restrict__ prefix,
-        int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s, KeyT *__restrict__ key, uint32_t *__restrict__ idx, int *status) {
+        int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s, KeyT *__restrict__ key, int *status,
+        const int64_t *__restrict__ off, int64_t S, unsigned long long *__restrict__ hash, int *__restrict__ overflow) {
     __shared__ int s_warp[33];
     const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
     const int32_t row = i < n ? match_row[i] : -1;
     const int flag = row >= 0;
     int total;
     const int ex = block_excl_scan(flag, &total, s_warp);
+    unsigned long long ins = ~0ull;                 // the key to insert, or nothing
+    int64_t smp = 0;
     if (i < n) {
         const int32_t p = tile_off[blockIdx.x] + ex;
         prefix[i] = p;
@@ -66,22 +109,20 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
             if (w0 == 1.0) c = 0; else if (w1 == 1.0) c = 1; else if (w2 == 1.0) c = 2;
             else { c = 0; if (w1 > w0) c = 1; if (w2 > (c ? w1 : w0)) c = 2; }
             const int b = code_bits;
-            key[p] = (KeyT(c) << (3 * b)) | (KeyT(cd[c]) << (2 * b)) | (KeyT(cd[gs_slow_class(c)]) << b) | KeyT(cd[gs_fast_class(c)]);
-            idx[p] = uint32_t(p);
+            const KeyT kk = (KeyT(c) << (3 * b)) | (KeyT(cd[c]) << (2 * b)) | (KeyT(cd[gs_slow_class(c)]) << b) | KeyT(cd[gs_fast_class(c)]);
+            key[p] = kk;
+            int64_t lo = 0, hi = S;                         // sample of marker i: the last offset <= i
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (off[mid] <= i) lo = mid; else hi = mid;
+            }
+            smp = lo;
+            ins = (unsigned long long)(kk);
         }
     }
-}
-
-// lanes of the warp that hold the same `bits`-bit digit as the caller (valid lanes only): one ballot per digit bit.  (match.any
-// does the same in one instruction but its cost grows with the number of distinct values in the warp — up to 32 here.)
-__device__ __forceinline__ uint32_t rs_peers(uint32_t d, bool valid, int bits) {
-    uint32_t peers = __ballot_sync(0xffffffffu, valid);
-    for (int b = 0; b < bits; ++b) {
-        const uint32_t bit = (d >> b) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
-    }
-    return peers;
+    // one insert per distinct (sample, key) of the warp: a sample's common triples would otherwise hammer one slot
+    const uint32_t peers = __match_any_sync(0xffffffffu, ins) & __match_any_sync(0xffffffffu, smp);
+    if (ins != ~0ull && (threadIdx.x & 31) == __ffs(peers) - 1) gh_insert(hash + size_t(smp) * GH_SLOTS, ins, overflow + smp);
 }
 
 // Tile t of the sort covers pairs [begin, end) of sample tile_sample[t]: the lt-th RS_TILE pairs of the sample's matched range
@@ -99,101 +140,172 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const int32_t *__restrict__
     range[t] = make_int2(begin, min(b1, begin + RS_TILE));
 }
 
-// digit histogram of one tile -> tile_hist[t][0..bins)  (first pass only: later passes get theirs from the scatter before them)
+
+// One CTA per sample: the sample's distinct keys (its hash table, compacted) are sorted in shared memory (bitonic over the
+// next power of two); the rank of a key is the dense id of its group: slot_gid[s][slot] = rank, ngroups[s] = their number
+// (capped at GH_MAX_GROUPS, overflow flagged), gkeys[s][rank] = key, gw[s][rank] = (w_ref, w_alt, w_het, 0) of the group.
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const KeyT *__restrict__ key, const int2 *__restrict__ range,
-                                                          int shift, int bits, uint32_t *__restrict__ tile_hist) {
-    extern __shared__ uint32_t rs_h[];
-    const int bins = 1 << bits;
-    const int2 rg = range[blockIdx.x];
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) rs_h[d] = 0u;
-    __syncthreads();
-    const int begin = rg.x, end = rg.y;
-    const uint32_t dmask = uint32_t(bins - 1);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KeyT k[RS_PER_THREAD];
+__global__ void __launch_bounds__(1024) k_group_rank(const unsigned long long *__restrict__ hash, const double *__restrict__ wtable, int32_t code_bits,
+                                                     uint16_t *__restrict__ slot_gid, int32_t *__restrict__ ngroups, KeyT *__restrict__ gkeys,
+                                                     double4 *__restrict__ gw, int *__restrict__ overflow) {
+    __shared__ unsigned long long sm[GH_SLOTS];
+    __shared__ int s_warp[33];
+    const int s = blockIdx.x;
+    const unsigned long long *tab = hash + size_t(s) * GH_SLOTS;
+    // compaction: thread -> 4 consecutive slots
+    unsigned long long v[4];
+    int cnt = 0;
 #pragma unroll
-    for (int e = 0; e < RS_PER_THREAD; ++e) {                      // all loads first: the tile is one DRAM round trip, not eight
-        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
-        k[e] = i < end ? key[i] : KeyT(0);
+    for (int j = 0; j < 4; ++j) {
+        v[j] = tab[4 * threadIdx.x + j];
+        cnt += v[j] != 0ull;
     }
-#pragma unroll
-    for (int e = 0; e < RS_PER_THREAD; ++e) {
-        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
-        const uint32_t d = uint32_t(k[e] >> shift) & dmask;
-        const uint32_t peers = rs_peers(d, i < end, bits);
-        if (i < end && lane == __ffs(peers) - 1) atomicAdd(rs_h + d, uint32_t(__popc(peers)));
-    }
+    int n;
+    int at = block_excl_scan(cnt, &n, s_warp);
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) sm[j] = ~0ull;
     __syncthreads();
-    uint32_t *out = tile_hist + size_t(blockIdx.x) * bins;
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) out[d] = rs_h[d];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (v[j] != 0ull) sm[at++] = ((v[j] - 1ull) << 12) | (unsigned long long)(4 * threadIdx.x + j);      // keys have at most 50 bits
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const unsigned long long a = sm[i], c = sm[x];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) { sm[i] = c; sm[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int ng = min(n, GH_MAX_GROUPS);
+    uint16_t *out = slot_gid + size_t(s) * GH_SLOTS;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        const unsigned long long e = sm[p];
+        out[e & 4095ull] = uint16_t(min(p, GH_MAX_GROUPS - 1));
+        if (p < ng) {
+            const KeyT key = KeyT(e >> 12);
+            gkeys[size_t(s) * GH_MAX_GROUPS + p] = key;
+            double4 w;
+            w.x = __ldg(wtable + gs_code(key, 0, code_bits));
+            w.y = __ldg(wtable + gs_code(key, 1, code_bits));
+            w.z = __ldg(wtable + gs_code(key, 2, code_bits));
+            w.w = 0.0;
+            gw[size_t(s) * GH_MAX_GROUPS + p] = w;
+        }
+    }
+    if (threadIdx.x == 0) {
+        ngroups[s] = ng;
+        if (n > GH_MAX_GROUPS) overflow[s] = 1;
+    }
 }
 
-// One pass of the stable segmented LSD radix sort, one CTA per tile, three steps in one kernel:
-//   offsets  where the tile's pairs of digit d go inside the sample's range = (pairs of smaller digits in the whole sample) +
-//            (pairs of digit d in earlier tiles of the sample), from the per-tile digit counts of ALL tiles of the sample
-//            (a few tens of KB out of L2 per CTA: cheaper than a separate scan kernel between two dependent launches);
-//   ranks    warp w owns pairs [256 w, 256 w + 256) of the tile and takes them 32 at a time in order, so ranks inside a digit
-//            follow the pair order: (pairs of that digit in earlier warps) + (earlier rounds of this warp) + (lower lanes of
-//            this round, match.any);
-//   scatter  key + payload to their place; the NEXT pass's per-tile digit counts are accumulated on the way (atomics into a
-//            zeroed table, indexed by the tile the pair lands in).  LAST: the payload index is resolved to the pair itself
-//            (panel row, marker index).
-// Dynamic shared memory: bins * 20 bytes (8 warp histograms of u16 + one u32 offset per digit).
-template <typename KeyT, bool LAST>
-__global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const KeyT *__restrict__ key_in, const uint32_t *__restrict__ idx_in,
-                                                             KeyT *__restrict__ key_out, uint32_t *__restrict__ idx_out,
-                                                             const int32_t *__restrict__ pair_db_in, const int32_t *__restrict__ pair_s_in,
-                                                             int32_t *__restrict__ pair_db_out, int32_t *__restrict__ pair_s_out,
-                                                             const int32_t *__restrict__ mstart, const int32_t *__restrict__ tile_sample,
-                                                             const int32_t *__restrict__ tile_first, const int2 *__restrict__ range,
-                                                             const uint32_t *__restrict__ hist_in, uint32_t *__restrict__ hist_out,
-                                                             int shift, int bits, int next_shift, int next_bits) {
-    extern __shared__ uint32_t rs_sm[];
-    __shared__ int s_warp[33];
-    const int bins = 1 << bits;
-    constexpr int NW = RS_THREADS / 32;
-    uint16_t *whist = reinterpret_cast<uint16_t *>(rs_sm);          // [NW][bins]
-    uint32_t *off = rs_sm + NW * bins / 2;                          // [bins]
+// One CTA per tile: dense id of every pair (lookup in its sample's table) -> gid[], and the tile's id counts -> tile_hist[t][0..ngroups)
+// (rows of GH_MAX_GROUPS counters; only the first ngroups[s] are written and read).
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) k_group_ids(const KeyT *__restrict__ key, const int2 *__restrict__ range,
+                                                         const int32_t *__restrict__ tile_sample, const unsigned long long *__restrict__ hash,
+                                                         const uint16_t *__restrict__ slot_gid, const int32_t *__restrict__ ngroups,
+                                                         uint16_t *__restrict__ gid, uint32_t *__restrict__ tile_hist) {
+    __shared__ uint32_t h[GH_MAX_GROUPS];
     const int t = blockIdx.x;
     const int2 rg = range[t];
     const int begin = rg.x, end = rg.y;
-    if (begin >= end) return;                                       // the whole CTA: an empty tile
+    if (begin >= end) return;
     const int s = tile_sample[t];
+    const int ng = ngroups[s];
+    for (int d = threadIdx.x; d < ng; d += RS_THREADS) h[d] = 0u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // the tile's pairs: loads issued before anything depends on them
+    const unsigned long long *tab = hash + size_t(s) * GH_SLOTS;
+    const uint16_t *sg = slot_gid + size_t(s) * GH_SLOTS;
     KeyT k[RS_PER_THREAD];
-    uint32_t v[RS_PER_THREAD];
+#pragma unroll
+    for (int e = 0; e < RS_PER_THREAD; ++e) {
+        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
+        k[e] = i < end ? key[i] : KeyT(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < RS_PER_THREAD; ++e) {
+        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
+        if (i < end) {
+            const uint32_t g = min(uint32_t(__ldg(sg + gh_find(tab, (unsigned long long)(k[e])))), uint32_t(max(ng, 1) - 1));
+            gid[i] = uint16_t(g);
+            atomicAdd(h + g, 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t *out = tile_hist + size_t(t) * GH_MAX_GROUPS;
+    for (int d = threadIdx.x; d < ng; d += RS_THREADS) out[d] = h[d];
+}
+
+// One CTA per tile: the stable partition of the tile's pairs by dense id, three steps in one kernel:
+//   offsets  where the tile's pairs of id g go inside the sample's range = (pairs of smaller ids in the whole sample) + (pairs
+//            of id g in earlier tiles of the sample), from the id counts of ALL tiles of the sample (a few tens of KB out of
+//            L2 per CTA: cheaper than a scan kernel between two dependent launches); the sample's first tile also publishes
+//            the group starts goff[s][0..ngroups];
+//   ranks    warp w owns pairs [256 w, 256 w + 256) of the tile and takes them 32 at a time in order, so ranks inside an id
+//            follow the pair order: (pairs of that id in earlier warps) + (earlier rounds of this warp) + (lower lanes of this
+//            round, match.any);
+//   scatter  the panel row of the pair (and, when the caller wants the pairs back, its marker index) to its place.  Nothing
+//            else moves: keys and weights live in the per-sample group table.
+// Dynamic shared memory: GH_MAX_GROUPS * 20 bytes.
+__global__ void __launch_bounds__(RS_THREADS, 3) k_group_place(const uint16_t *__restrict__ gid_in,
+                                                              const int32_t *__restrict__ pair_db_in, const int32_t *__restrict__ pair_s_in,
+                                                              int32_t *__restrict__ pair_db_out, int32_t *__restrict__ pair_s_out,
+                                                              const int32_t *__restrict__ mstart, const int32_t *__restrict__ tile_sample,
+                                                              const int32_t *__restrict__ tile_first, const int2 *__restrict__ range,
+                                                              const uint32_t *__restrict__ tile_hist, const int32_t *__restrict__ ngroups,
+                                                              int32_t *__restrict__ goff) {
+    extern __shared__ uint32_t rs_sm[];
+    __shared__ int s_warp[33];
+    constexpr int NW = RS_THREADS / 32;
+    constexpr int PITCH = GH_MAX_GROUPS;
+    uint16_t *whist = reinterpret_cast<uint16_t *>(rs_sm);          // [NW][PITCH]
+    uint32_t *off = rs_sm + NW * PITCH / 2;                         // [PITCH]
+    const int t = blockIdx.x;
+    const int2 rg = range[t];
+    const int begin = rg.x, end = rg.y;
+    const int s = tile_sample[t];
+    const int t0 = tile_first[s], t1 = tile_first[s + 1];
+    if (begin >= end && t != t0) return;                            // an empty tile (the first tile of a sample still writes goff)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t d[RS_PER_THREAD];
+    int32_t pdb[RS_PER_THREAD], ps[RS_PER_THREAD];
 #pragma unroll
     for (int e = 0; e < RS_PER_THREAD; ++e) {
         const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
         const bool on = i < end;
-        k[e] = on ? key_in[i] : KeyT(0);
-        v[e] = on ? idx_in[i] : 0u;
+        d[e] = on ? uint32_t(gid_in[i]) : 0xffffffffu;
+        pdb[e] = on ? pair_db_in[i] : 0;
+        ps[e] = on && pair_s_out ? pair_s_in[i] : 0;
     }
-    for (int j = threadIdx.x; j < NW * bins / 2; j += RS_THREADS) rs_sm[j] = 0u;
-    const int t0 = tile_first[s], t1 = tile_first[s + 1], base = mstart[s];
-    // offsets: thread -> `per` consecutive digits
+    const int ng = ngroups[s];
+    const int base = mstart[s];
+    for (int j = threadIdx.x; j < NW * PITCH / 2; j += RS_THREADS) rs_sm[j] = 0u;
     {
-        const int per = (bins + RS_THREADS - 1) / RS_THREADS;       // 1, 2, 4 or 8
+        const int per = (ng + RS_THREADS - 1) / RS_THREADS;         // 1..8 consecutive ids per thread
         const int d0 = threadIdx.x * per;
         uint32_t total[8], before[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) total[j] = before[j] = 0u;
-        if (d0 < bins) {
-            constexpr int U = 8;                                    // tiles per batch of independent loads (the loop is latency bound)
+        constexpr int U = 16;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < per) {
-                    for (int tt = t0; tt < t1; tt += 2 * U) {
-                        uint32_t c[2 * U];
+        for (int j = 0; j < 8; ++j) {
+            if (j < per && d0 + j < ng) {
+                for (int tt = t0; tt < t1; tt += U) {
+                    uint32_t c[U];
 #pragma unroll
-                        for (int u = 0; u < 2 * U; ++u) c[u] = tt + u < t1 ? __ldg(hist_in + size_t(tt + u) * bins + d0 + j) : 0u;
+                    for (int u = 0; u < U; ++u) c[u] = tt + u < t1 ? __ldg(tile_hist + size_t(tt + u) * PITCH + d0 + j) : 0u;
 #pragma unroll
-                        for (int u = 0; u < 2 * U; ++u) {
-                            total[j] += c[u];
-                            if (tt + u < t) before[j] += c[u];
-                        }
+                    for (int u = 0; u < U; ++u) {
+                        total[j] += c[u];
+                        if (tt + u < t) before[j] += c[u];
                     }
                 }
             }
@@ -203,104 +315,97 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const KeyT *__rest
         for (int j = 0; j < 8; ++j) mine += total[j];
         int all;
         uint32_t run = uint32_t(block_excl_scan(int(mine), &all, s_warp));
-        if (d0 < bins) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < per) {
-                    off[d0 + j] = run + before[j];
-                    run += total[j];
-                }
+        for (int j = 0; j < 8; ++j) {
+            if (j < per && d0 + j < ng) {
+                off[d0 + j] = run + before[j];
+                if (t == t0) goff[size_t(s) * (GH_MAX_GROUPS + 1) + d0 + j] = int32_t(run);
+                run += total[j];
             }
         }
+        if (t == t0 && threadIdx.x == 0) goff[size_t(s) * (GH_MAX_GROUPS + 1) + ng] = all;
     }
     __syncthreads();
-    const uint32_t dmask = uint32_t(bins - 1);
+    if (begin >= end) return;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint16_t *mine_h = whist + size_t(warp) * bins;
+    uint16_t *mine_h = whist + size_t(warp) * PITCH;
     uint32_t rank[RS_PER_THREAD];
 #pragma unroll
     for (int e = 0; e < RS_PER_THREAD; ++e) {
-        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
-        const bool on = i < end;
-        const uint32_t d = uint32_t(k[e] >> shift) & dmask;
-        const uint32_t peers = rs_peers(d, on, bits);
+        const bool on = d[e] != 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d[e]);
         uint32_t prior = 0u;
-        if (on) prior = mine_h[d];
+        if (on) prior = mine_h[d[e]];
         __syncwarp();
-        if (on && lane == __ffs(peers) - 1) mine_h[d] = uint16_t(prior + __popc(peers));
+        if (on && lane == __ffs(peers) - 1) mine_h[d[e]] = uint16_t(prior + __popc(peers));
         __syncwarp();
         rank[e] = prior + uint32_t(__popc(peers & lt_mask));
     }
     __syncthreads();
-    // per digit: exclusive prefix over the warps (in place)
-    for (int d = threadIdx.x; d < bins; d += RS_THREADS) {
+    for (int g = threadIdx.x; g < ng; g += RS_THREADS) {
         uint32_t run = 0u;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            const uint32_t c = whist[size_t(w) * bins + d];
-            whist[size_t(w) * bins + d] = uint16_t(run);
+            const uint32_t c = whist[size_t(w) * PITCH + g];
+            whist[size_t(w) * PITCH + g] = uint16_t(run);
             run += c;
         }
     }
     __syncthreads();
-    const uint32_t nmask = next_bits > 0 ? uint32_t((1 << next_bits) - 1) : 0u;
 #pragma unroll
     for (int e = 0; e < RS_PER_THREAD; ++e) {
-        const int i = begin + warp * (32 * RS_PER_THREAD) + e * 32 + lane;
-        if (i < end) {
-            const uint32_t d = uint32_t(k[e] >> shift) & dmask;
-            const int local = int(off[d]) + int(mine_h[d]) + int(rank[e]);
-            const int o = base + local;
-            key_out[o] = k[e];
-            if (LAST) {
-                pair_db_out[o] = pair_db_in[v[e]];
-                pair_s_out[o] = pair_s_in[v[e]];
-            } else {
-                idx_out[o] = v[e];
-            }
-        }
-        if (!LAST && hist_out != nullptr && i < end) {
-            // next pass's digit counts, booked on the tile the pair lands in (fire-and-forget atomics into a zeroed table)
-            const uint32_t d = uint32_t(k[e] >> shift) & dmask;
-            const int local = int(off[d]) + int(mine_h[d]) + int(rank[e]);
-            atomicAdd(hist_out + ((size_t(t0) + size_t(local / RS_TILE)) << next_bits) + (uint32_t(k[e] >> next_shift) & nmask), 1u);
+        if (d[e] != 0xffffffffu) {
+            const int o = base + int(off[d[e]]) + int(mine_h[d[e]]) + int(rank[e]);
+            pair_db_out[o] = pdb[e];
+            if (pair_s_out) pair_s_out[o] = ps[e];
         }
     }
 }
 
-// Per block of 16 sorted rows of a sample (blocks counted from the sample's first pair; a segment of `chunk` rows is chunk/16
-// blocks): three 16-bit masks (ref | alt << 16 | het << 32), bit k set <=> the weight code of that class at row 16 b + k
-// differs from the row before it.  The first row of a segment is never marked (the kernel loads its weights afresh).
-// grid (ceil(max pairs of a sample / 256), S).
+// One CTA per sample, from the group table alone: per block of 16 grouped rows of the sample (blocks counted from its first
+// pair; a segment of `chunk` rows is chunk/16 blocks) one word
+//     ref mask | alt mask << 16 | het mask << 32 | (group of the block's first row) << 48
+// mask bit k set <=> the weight of that class at row 16 b + k differs from the row before it.  blk_chg must be zeroed before.
 template <typename KeyT>
-__global__ void __launch_bounds__(256) k_group_masks(const KeyT *__restrict__ key, const int32_t *__restrict__ mstart,
-                                                     const int32_t *__restrict__ seg_off, int32_t chunk, int32_t code_bits,
-                                                     unsigned long long *__restrict__ blk_chg) {
-    const int s = blockIdx.y;
-    const int b0 = mstart[s], m = mstart[s + 1] - b0;
-    const int r = blockIdx.x * 256 + threadIdx.x;
-    if ((r & ~31) >= m) return;                       // whole warp past the end
-    uint32_t f[3] = {0u, 0u, 0u};
-    if (r < m && r % chunk != 0) {
-        const KeyT k1 = key[b0 + r], k0 = key[b0 + r - 1];
-        const int b = code_bits;
+__global__ void __launch_bounds__(1024) k_group_marks(const int32_t *__restrict__ goff, const KeyT *__restrict__ gkeys, const int32_t *__restrict__ ngroups,
+                                                      const int32_t *__restrict__ mstart, const int32_t *__restrict__ seg_off, int32_t chunk,
+                                                      int32_t code_bits, unsigned long long *__restrict__ blk_chg) {
+    __shared__ int32_t s_off[GH_MAX_GROUPS + 1];
+    const int s = blockIdx.x;
+    const int ng = ngroups[s];
+    const int m = mstart[s + 1] - mstart[s];
+    if (m <= 0 || ng <= 0) return;
+    for (int g = threadIdx.x; g <= ng; g += blockDim.x) s_off[g] = goff[size_t(s) * (GH_MAX_GROUPS + 1) + g];
+    __syncthreads();
+    unsigned long long *out = blk_chg + size_t(seg_off[s]) * size_t(chunk / 16);
+    const KeyT *gk = gkeys + size_t(s) * GH_MAX_GROUPS;
+    const int b = code_bits;
+    for (int g = 1 + threadIdx.x; g < ng; g += blockDim.x) {       // the start of group g: which classes change there
+        const int r = s_off[g];
+        if (r >= m || s_off[g + 1] == r) continue;                 // (an id without pairs cannot occur; be safe)
+        const KeyT k1 = gk[g], k0 = gk[g - 1];
         const int c1 = int(k1 >> (3 * b)) & 3, c0 = int(k0 >> (3 * b)) & 3;
+        unsigned long long bits = 0ull;
         if (c1 != c0) {
-            f[0] = f[1] = f[2] = 1u;
+            bits = 1ull | (1ull << 16) | (1ull << 32);
         } else {
-            const KeyT d = k1 ^ k0;
+            const KeyT dd = k1 ^ k0;
             const uint32_t fm = (1u << b) - 1u;
 #pragma unroll
-            for (int w = 0; w < 3; ++w) f[w] = (uint32_t(d >> gs_field_shift(c1, w, b)) & fm) != 0u;
+            for (int w = 0; w < 3; ++w)
+                if ((uint32_t(dd >> gs_field_shift(c1, w, b)) & fm) != 0u) bits |= 1ull << (16 * w);
         }
+        atomicOr(out + (r >> 4), bits << (r & 15));
     }
-    const uint32_t b_ref = __ballot_sync(0xffffffffu, f[0]), b_alt = __ballot_sync(0xffffffffu, f[1]), b_het = __ballot_sync(0xffffffffu, f[2]);
-    const int lane = threadIdx.x & 31;
-    if ((lane & 15) == 0 && r < m) {
-        const int sh = lane;                          // 0 or 16
-        const unsigned long long v = (unsigned long long)((b_ref >> sh) & 0xffffu) | ((unsigned long long)((b_alt >> sh) & 0xffffu) << 16) |
-                                     ((unsigned long long)((b_het >> sh) & 0xffffu) << 32);
-        blk_chg[size_t(seg_off[s]) * size_t(chunk / 16) + size_t(r >> 4)] = v;
+    const int nb = (m + 15) / 16;
+    for (int blk = threadIdx.x; blk < nb; blk += blockDim.x) {     // group of the block's first row: the last start <= 16 blk
+        int lo = 0, hi = ng;
+        const int r = 16 * blk;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= r) lo = mid; else hi = mid;
+        }
+        atomicOr(out + blk, (unsigned long long)(lo) << 48);
     }
 }
 

@@ -651,10 +651,14 @@ __global__ void __launch_bounds__(32) k_wait_peers_done(const uint32_t *own_flag
 // stored so that the epilogue's int(score) gives exactly that, and cells whose F lies within the summation-error bound of
 // an integer k >= 1 are counted in guard[s]: for them the reference's own rounding decides, so the caller re-scores the
 // sample in reference order.  Runs after the cross-GPU reduce, on totals.
-__global__ void __launch_bounds__(256) k_grouped_finalize(double *__restrict__ red, int32_t n_acc, int32_t *__restrict__ guard) {
+__global__ void __launch_bounds__(256) k_grouped_finalize(double *__restrict__ red, int32_t n_acc, int32_t *__restrict__ guard,
+                                                          const int *__restrict__ overflow = nullptr) {
     const int s = blockIdx.y;
     const int acc = blockIdx.x * blockDim.x + threadIdx.x;
     if (acc >= n_acc) return;
+    // a sample whose weight triples did not fit the dense ids of the device grouping (group_sort.cuh) was scored with ids
+    // folded together: flag it like a guard hit, the caller re-scores it in reference order
+    if (acc == 0 && overflow != nullptr && overflow[s]) atomicAdd(guard + s, 1);
     double *row = red + int64_t(s) * (3 * int64_t(n_acc) + 2);
     const double f = row[acc], ii = row[2 * n_acc + 2 + acc], m = row[2 * n_acc];
     // |reference - exact| <= (1000 + 2 + m/1000) u (I+F) for its chunked sequential sums, the same bound holds

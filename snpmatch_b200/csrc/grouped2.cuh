@@ -5,8 +5,8 @@
 // (per-block change masks, here precomputed by k_group_masks), folds counts into fp64 with one fma per accession, keeps
 // weight-1.0 classes in an exact integer counter: score = I + F (see grouped.cuh for the exactness argument).
 // What is different:
-//   * input is what the device-side grouping produces (group_sort.cuh): sorted panel rows + sort keys that carry the three
-//     weight codes of a pair; weights come from the table of distinct values (L1-resident);
+//   * input is what the device-side grouping produces (group_sort.cuh): panel rows in grouped order, one word per 16-row
+//     block (change masks + the group its first row belongs to) and the weights of every group (a few KB per sample);
 //   * ONE persistent CTA per SM, 7 teams of 36 threads in 8 warps (252 of 256 lanes work: the 128-thread CTAs of round 1
 //     used 108 of 128) and 7 instead of 6 segments in flight per SM; wide panels (rows of more than 36 words) are cut into
 //     warp-aligned slices of 32 words, 8 teams = 8 slices of the same segment;
@@ -31,18 +31,14 @@ constexpr int G2_THREADS = 256;           // 7 teams x 36 = 252 threads: 8 warps
                                           // (9 warps would put three on one scheduler's register file: 168 registers, spills)
 constexpr int G2_MAX_CHUNK = 496;
 constexpr int G2_CP = 9;                  // planes of a class counter
-constexpr int G2_PF_DEFAULT = 0;          // L2 prefetch distance in 16-row blocks (0 = off: measured 0.272 ms off, 0.328 at 6, 0.354 at 12)
 constexpr int G2_TP = 9;                  // planes of the per-segment totals (I, ninfo)
 
-template <typename KeyT>
 struct Group2Args {
     const uint64_t *packed;
     int32_t stride;
     const int32_t *pair_db;               // [m] matched local rows, grouped order
-    const KeyT *pair_key;                 // [m] sort keys of the pairs (group_sort.cuh)
-    const unsigned long long *blk_chg;    // change masks per 16-row block: [segment][chunk / 16]
-    const double *wtable;                 // distinct weight values
-    int32_t code_bits;
+    const unsigned long long *blk_chg;    // per 16-row block: change masks + group of its first row (k_group_marks): [segment][chunk / 16]
+    const double *gw;                     // [S][GH_MAX_GROUPS][4] weights (ref, alt, het, 0) of every group of every sample
     const int32_t *seg_off;               // [S+1]
     const int32_t *mstart;                // [S+1]
     int32_t S;
@@ -67,15 +63,14 @@ struct G2Item {
     int32_t begin;      // first pair
     int32_t n_rows;
     int32_t slice;
+    int32_t smp;
 };
 
-template <typename KeyT>
 __host__ __device__ __forceinline__ size_t g2_stage_bytes(int chunk) {
-    return (size_t(chunk) * 4 + size_t(chunk) * sizeof(KeyT) + size_t(chunk / 16 + 1) * 8 + 15) & ~size_t(15);
+    return (size_t(chunk) * 4 + size_t(chunk / 16 + 1) * 8 + 15) & ~size_t(15);      // row numbers | block words
 }
-template <typename KeyT>
 __host__ __device__ __forceinline__ size_t g2_team_smem(int wx, int chunk) {
-    return size_t(GR_RING) * wx * 8 + 2 * g2_stage_bytes<KeyT>(chunk);             // ring | 2 staging buffers
+    return size_t(GR_RING) * wx * 8 + 2 * g2_stage_bytes(chunk);             // ring | 2 staging buffers
 }
 
 // fold the counts of a class counter: F[lane] += w * count[lane]
@@ -122,21 +117,18 @@ __device__ __forceinline__ void counter_values9(const BitCounter<G2_TP> &c, int3
 }
 
 // WX > 0: words per team known at compile time; WX == 0: a.wx.  Thread pairs (2i, 2i+1) share 16-byte copies of two columns.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// PF: rows of block b + PF are pulled into L2 (prefetch.global.L2, one 128-byte line per instruction) when block b's copies
-// are queued: the shared-memory ring holds 3 blocks per team in flight (~100 KB per SM), too few outstanding bytes to saturate
-// HBM with 288-byte gathers (scripts/microbench_gather2.cu: 147 KB in flight 4.4 TB/s, 221 KB 4.8 TB/s); the L2 prefetches
-// put as many rows in flight at the DRAM level as wanted, and the ring then only has to hide L2 latency.
-template <typename KeyT, bool SKIP_HETS, int WX, int PF>
-__global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Args<KeyT> a) {
+// (Measured and dropped: pulling the rows of block b + 6 / b + 12 into L2 with prefetch.global.L2 while block b's copies are
+// queued — to have more bytes in flight at the DRAM level than the shared-memory ring holds — made the kernel slower: 0.272 ms
+// without, 0.328 ms at distance 6, 0.354 ms at 12.)
+template <bool SKIP_HETS, int WX>
+__global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Args a) {
     extern __shared__ __align__(16) unsigned char g2_smem[];
     __shared__ int s_base[2];                     // first item of the round in staging buffer 0 / 1
     const int wx = WX ? WX : a.wx;
     const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
     const bool in_team = q < a.teams;
-    const size_t team_bytes = g2_team_smem<KeyT>(wx, a.chunk);
-    const size_t stage_bytes = g2_stage_bytes<KeyT>(a.chunk);
+    const size_t team_bytes = g2_team_smem(wx, a.chunk);
+    const size_t stage_bytes = g2_stage_bytes(a.chunk);
     unsigned char *team = g2_smem + size_t(in_team ? q : 0) * team_bytes;
     uint64_t *ring = reinterpret_cast<uint64_t *>(team);
     unsigned char *stage0 = team + size_t(GR_RING) * wx * 8;
@@ -144,7 +136,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     // item i -> (slot, slice); slot -> segment j = jmax-1 - slot / S of sample slot % S: longest segments first
     auto decode = [&](int i) {
         G2Item it;
-        it.seg = -1; it.begin = 0; it.n_rows = 0; it.slice = 0;
+        it.seg = -1; it.begin = 0; it.n_rows = 0; it.slice = 0; it.smp = 0;
         if (in_team && i < n_items) {
             const int slot = i / a.n_slices, slice = i - slot * a.n_slices;
             const int j = a.jmax - 1 - slot / a.S, smp = slot % a.S;
@@ -155,6 +147,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 it.begin = m0 + j * a.chunk;
                 it.n_rows = min(m1, it.begin + a.chunk) - it.begin;
                 it.slice = slice;
+                it.smp = smp;
             }
         }
         return it;
@@ -163,12 +156,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     auto prefetch = [&](const G2Item &it, int buf) {
         if (it.seg >= 0) {
             unsigned char *st = stage0 + size_t(buf) * stage_bytes;
-            const uint32_t s_row = smem_u32(st), s_key = s_row + uint32_t(a.chunk) * 4u, s_chg = s_key + uint32_t(a.chunk) * uint32_t(sizeof(KeyT));
-            for (int r = w; r < it.n_rows; r += wx) {
-                cp_async4(s_row + uint32_t(r) * 4u, a.pair_db + it.begin + r);
-                if (sizeof(KeyT) == 4) cp_async4(s_key + uint32_t(r) * 4u, a.pair_key + it.begin + r);
-                else cp_async8(s_key + uint32_t(r) * 8u, a.pair_key + it.begin + r);
-            }
+            const uint32_t s_row = smem_u32(st), s_chg = s_row + uint32_t(a.chunk) * 4u;
+            for (int r = w; r < it.n_rows; r += wx) cp_async4(s_row + uint32_t(r) * 4u, a.pair_db + it.begin + r);
             const int nb = (it.n_rows + GR_BLOCK - 1) / GR_BLOCK;
             const unsigned long long *src = a.blk_chg + size_t(it.seg) * size_t(a.chunk / GR_BLOCK);
             for (int b = w; b < nb; b += wx) cp_async8(s_chg + uint32_t(b) * 8u, src + b);
@@ -191,7 +180,6 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     const int odd = w & 1;
     const uint32_t ring_pitch = uint32_t(wx) * 8u;
     const uint32_t stride_b = uint32_t(a.stride) * 8u;
-    const int cb = a.code_bits;
     const int nb_round = a.chunk / GR_BLOCK;      // every team runs this many block steps per round (lockstep)
 
     while (true) {
@@ -202,8 +190,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         prefetch(nxt, buf ^ 1);                   // lands while this round is scored (oldest commit group)
         const unsigned char *st = stage0 + size_t(buf) * stage_bytes;
         const int32_t *s_row = reinterpret_cast<const int32_t *>(st);
-        const KeyT *s_key = reinterpret_cast<const KeyT *>(st + size_t(a.chunk) * 4);
-        const unsigned long long *s_chg = reinterpret_cast<const unsigned long long *>(st + size_t(a.chunk) * 4 + size_t(a.chunk) * sizeof(KeyT));
+        const unsigned long long *s_chg = reinterpret_cast<const unsigned long long *>(st + size_t(a.chunk) * 4);
+        const double *gwp = a.gw + size_t(cur.smp) * (4 * GH_MAX_GROUPS);
         const int n_rows = cur.n_rows;            // 0: no item for this team in this round (it still keeps step with the others)
         const int n_blocks = (n_rows + GR_BLOCK - 1) / GR_BLOCK;
         const int n_full = n_rows / GR_BLOCK;
@@ -231,27 +219,6 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
             }
             cp_async_commit();                    // always: the waits below count groups
         };
-        // lines of the rows of block b -> L2: the slice of a row is wx * 8 bytes from a 16-byte aligned start, i.e. at most
-        // wx / 16 + 1 lines of 128 bytes; the team's threads share the (row, line) pairs of the block
-        auto prefetch_block = [&](int b) {
-            if (PF > 0 && live && b < n_blocks) {
-                const int lines = (wx * 8 + 127) / 128 + 1;
-                const int todo = min(GR_BLOCK, n_rows - b * GR_BLOCK) * lines;
-                const unsigned char *col0 = reinterpret_cast<const unsigned char *>(a.packed + cur.slice * wx);
-                for (int j = w; j < todo; j += wx) {
-                    const int r = j / lines, ln = j - r * lines;
-                    const unsigned char *row = col0 + (unsigned long long)(uint32_t(s_row[b * GR_BLOCK + r])) * stride_b;
-                    const unsigned long long first = reinterpret_cast<unsigned long long>(row) & ~127ull;
-                    const unsigned long long last = (reinterpret_cast<unsigned long long>(row) + uint32_t(min(wx, a.stride - cur.slice * wx)) * 8u - 1u) & ~127ull;
-                    const unsigned long long p = first + (unsigned long long)(ln) * 128ull;
-                    if (p <= last) prefetch_l2(reinterpret_cast<const void *>(p));
-                }
-            }
-        };
-        if (PF > 0) {
-#pragma unroll 1
-            for (int b = GR_INFLIGHT; b < GR_INFLIGHT + PF; ++b) prefetch_block(b);
-        }
 #pragma unroll
         for (int b = 0; b < GR_INFLIGHT; ++b) issue(b);
 
@@ -267,10 +234,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         c_het.clear();
         double w_ref = 0.0, w_alt = 0.0, w_het = 0.0;
         if (n_rows > 0) {
-            const KeyT k0 = s_key[0];
-            w_ref = __ldg(a.wtable + gs_code(k0, 0, cb));
-            w_alt = __ldg(a.wtable + gs_code(k0, 1, cb));
-            w_het = __ldg(a.wtable + gs_code(k0, 2, cb));
+            const double *w0 = gwp + 4 * int(s_chg[0] >> 48);
+            w_ref = __ldg(w0);
+            w_alt = __ldg(w0 + 1);
+            w_het = __ldg(w0 + 2);
         }
         // read a class counter out: its counts are informative sites, and matches weighted by `wt`
         auto flush_class = [&](BitCounter<G2_CP> &c, double wt) {
@@ -283,7 +250,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         };
         // one class: add the block's planes; where the class weight changes inside the block (bit k of `mask`: row k starts a new
         // weight), add the rows piece by piece and read the counter out in between
-        auto add_class = [&](BitCounter<G2_CP> &c, double &wt, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, int r0) {
+        auto add_class = [&](BitCounter<G2_CP> &c, double &wt, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, unsigned long long chg) {
             if (mask == 0u) {
                 c.add16(pl);
                 return;
@@ -300,7 +267,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 }
                 if (k1 >= GR_BLOCK) break;
                 flush_class(c, wt);
-                wt = __ldg(a.wtable + gs_code(s_key[r0 + k1], which, cb));
+                // the group row k1 starts in: the block's first group + the group starts up to k1 (a start at row 0 is already counted)
+                const uint32_t starts = uint32_t(chg | (chg >> 16) | (chg >> 32)) & 0xffffu;
+                const int g = int(chg >> 48) + __popc(starts & ((2u << k1) - 2u));
+                wt = __ldg(gwp + 4 * g + which);
                 mask &= mask - 1u;
                 k0 = k1;
             }
@@ -310,14 +280,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
             uint32_t pl[GR_BLOCK];
 #pragma unroll
             for (int k = 0; k < GR_BLOCK; ++k) pl[k] = ~(lo[k] | hi[k]);
-            add_class(c_ref, w_ref, pl, uint32_t(chg) & 0xffffu, 0, b * GR_BLOCK);
+            add_class(c_ref, w_ref, pl, uint32_t(chg) & 0xffffu, 0, chg);
 #pragma unroll
             for (int k = 0; k < GR_BLOCK; ++k) pl[k] = lo[k] & ~hi[k];
-            add_class(c_alt, w_alt, pl, uint32_t(chg >> 16) & 0xffffu, 1, b * GR_BLOCK);
+            add_class(c_alt, w_alt, pl, uint32_t(chg >> 16) & 0xffffu, 1, chg);
             if (!SKIP_HETS) {                     // snpmatch.py:78-79: masked hets match nothing and are not informative
 #pragma unroll
                 for (int k = 0; k < GR_BLOCK; ++k) pl[k] = hi[k] & ~lo[k];
-                add_class(c_het, w_het, pl, uint32_t(chg >> 32) & 0xffffu, 2, b * GR_BLOCK);
+                add_class(c_het, w_het, pl, uint32_t(chg >> 32) & 0xffffu, 2, chg);
             }
         };
 
@@ -328,19 +298,6 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
             cp_async_wait<GR_INFLIGHT - 2>();
             __syncwarp();
             if (b > 0) issue(b + GR_INFLIGHT - 1);
-            if (PF > 0) prefetch_block(b + GR_INFLIGHT + PF);
-            if (PF > 0 && b == 1 && nxt.seg >= 0 && nxt.slice * wx + w < a.stride) {
-                // first rows of the NEXT round's item -> L2, so that its first copies do not start with a DRAM round trip.  A
-                // thread uses only the row numbers it has staged itself (its cp.async group is older than every ring group, so
-                // the wait above has completed it): no barrier needed.
-                const int32_t *n_row = reinterpret_cast<const int32_t *>(stage0 + size_t(buf ^ 1) * stage_bytes);
-                const unsigned char *ncol0 = reinterpret_cast<const unsigned char *>(a.packed + nxt.slice * wx);
-                const uint32_t nbytes = uint32_t(min(wx, a.stride - nxt.slice * wx)) * 8u;
-                for (int r = w; r < min(nxt.n_rows, GR_INFLIGHT * GR_BLOCK); r += wx) {
-                    const unsigned long long row = reinterpret_cast<unsigned long long>(ncol0 + (unsigned long long)(uint32_t(n_row[r])) * stride_b);
-                    for (unsigned long long p = row & ~127ull; p <= ((row + nbytes - 1u) & ~127ull); p += 128ull) prefetch_l2(reinterpret_cast<const void *>(p));
-                }
-            }
             if (b < n_full) {
                 const uint64_t *slot = ring + size_t((b * GR_BLOCK) % GR_RING) * wx + w;
                 uint32_t lo[GR_BLOCK], hi[GR_BLOCK];

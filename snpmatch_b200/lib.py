@@ -207,6 +207,7 @@ SIGNATURES = {
     "snpm_batch_guard_counts": (C.c_int, [_p, _p]),
     "snpm_batch_set_group_chunk": (C.c_int, [_p, _i32]),
     "snpm_batch_set_chunk_rows": (C.c_int, [_p, _i32]),
+    "snpm_batch_set_track_pairs": (C.c_int, [_p, C.c_int]),
     "snpm_batch_set_result_range": (C.c_int, [_p, _i64, _i64]),
     "snpm_batch_set_row_filter": (C.c_int, [_p, _p, _i64]),
     "snpm_batch_run": (C.c_int, [_p, C.c_int, C.c_int]),
@@ -491,6 +492,10 @@ class Batch(object):
     def set_chunk_rows(self, rows):
         """Genotyper chunk_size (snpmatch.py:173): rows per chunk of the order-exact kernel; applies from the next upload()."""
         check(load().snpm_batch_set_chunk_rows(self._h, int(rows)))
+
+    def set_track_pairs(self, on):
+        """Coded batches: keep the marker index of every matched pair (fetch_pairs) or not (one array less to move)."""
+        check(load().snpm_batch_set_track_pairs(self._h, int(bool(on))))
 
     def set_group_chunk(self, rows):
         check(load().snpm_batch_set_group_chunk(self._h, int(rows)))
