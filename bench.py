@@ -357,6 +357,13 @@ def timed_steps(ctx, step, wait, warmup, steps):
     return float(ms[0])
 
 
+def all_max(ctx, vals):
+    t = ctx.torch.tensor([float(v) for v in vals], dtype=ctx.torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
 def all_sum(ctx, vals):
     t = ctx.torch.tensor([float(v) for v in vals], dtype=ctx.torch.float64, device=ctx.dev)
     if ctx.world > 1:
@@ -649,9 +656,9 @@ def run_b200_arm(args):
     extras = {}
     if not args.headline_only:
         extras["called_genotypes"] = sub_called(ctx, g, samples, positions, regions, r0, r1, n_acc, peak)
+        extras["cross"] = sub_cross(ctx, g, positions, regions, r0, r1, n_acc)
         if world == 1:
             extras["e2e_api"] = sub_api(ctx, g, samples, n_acc)
-            extras["cross"] = sub_cross(ctx, g, positions, regions, n_acc)
             extras["batched_shared_panel"] = sub_a9(ctx, g, n_rows, n_acc, peaks)
     g.close()
     if not args.headline_only:
@@ -711,48 +718,73 @@ def sub_api(ctx, g, samples, n_acc):
                         "scoring + epilogue, D2H, re-scoring of flagged samples, GenotyperOutput objects", "true_accessions_recovered": bool(ok)}
 
 
-def sub_cross(ctx, g, positions, regions, n_acc):
-    """configs[2]: `snpmatch cross` device work for one PL sample: 399 windows of 300 kb + the 45 simulated F1s."""
-    from snpmatch_b200 import lib, synth
+def sub_cross(ctx, g, positions, regions, r0, r1, n_acc):
+    """configs[2]: `snpmatch cross` device work for one PL sample: 399 windows of 300 kb + the 45 simulated F1s.  On a sharded
+    panel every rank scores the windows' rows it holds and ONE all-reduce sums the per-window partials (sharding.py).  Parity:
+    every window's informative sites and scores, totals and a sample of the per-window calls against the CPU oracle."""
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import lib, sharding, synth
     from snpmatch_b200.core import genomes, snpmatch
+    world, rank = ctx.world, ctx.rank
     s = synth.make_sample_fast(positions, regions, n_acc, 7, seed=777)
     gen = genomes.Genome("athaliana_tair10")
     cnt, off, n_w, _ = gen.window_layout(np.array(synth.TAIR10_CHRS), 300000)
     kmax = snpmatch.identity_kmax_table(4000, 0.02)
-    b = lib.Batch(g.db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei"])
+    i0, i1 = (0, len(s["pos"])) if world == 1 else sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, positions, r0, r1)
+    b = lib.Batch(g.db, [0, i1 - i0], s["chr_ix"][i0:i1], s["pos"][i0:i1], s["wei"][i0:i1])
     res = {}
 
     def run():
-        b.run_windows(False, 300000, cnt, off, n_w, kmax)
+        sharding.run_windows_sharded(b, ctx.dist, ctx.dev, False, 300000, cnt, off, n_w, kmax)
         b.epilogue()
         tot = b.fetch()
         res["w"] = b.fetch_window_rows()             # the surviving rows, compacted on the device
         top = np.argsort(-tot["prob"][0])[:10]
-        res["f1"] = b.f1_pairs(top)
+        res["f1"] = sharding.f1_pairs_sharded(b, ctx.dist, ctx.dev, top)
         res["tot"] = tot
-    for _ in range(2):
-        run()
-    ts = []
-    for _ in range(5):
-        t0 = time.perf_counter()
-        run()
-        ts.append(time.perf_counter() - t0)
-    tm = b.timings()
-    m = int(res["tot"]["m"][0])
+    with ctx.torch.cuda.stream(ctx.stream):
+        for _ in range(2):
+            run()
+        barrier(ctx)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+        tm = b.timings()
+        full = b.fetch_windows() if rank == 0 else None
     t = float(np.median(ts))
-    # window totals must equal the inbred totals of the same sample restricted to the windows' markers: the windows cover
-    # every chromosome of the genome here, so score totals == a plain inbred run (size-independent property)
-    b2 = lib.Batch(g.db, [0, len(s["pos"])], s["chr_ix"], s["pos"], s["wei"])
-    b2.run()
-    b2.epilogue()
-    inbred = b2.fetch()
-    same = bool(np.array_equal(inbred["ninfo"][0], res["tot"]["ninfo"][0]) and int(inbred["m"][0]) == m)
-    b2.close()
-    out = {"workload": "configs[2]: cross, %d windows of 300 kb + 45 simulated F1s, one PL sample (%d markers, %d matched) vs %d x %d" % (
-               n_w, len(s["pos"]), m, n_acc, len(positions)),
-           "value": m * n_acc / t, "unit": UNIT, "host_call_ms": 1e3 * t, "device_ms": tm["total_ms"], "score_kernel_ms": tm["score_ms"],
-           "join_ms": tm["join_ms"], "windows_with_markers": int((res["w"]["nrows"] > 0).sum()), "surviving_rows": int(len(res["w"]["acc"])),
-           "top_accession_is_true": bool(int(np.nanargmin(res["tot"]["L"][0])) == 7), "window_totals_equal_inbred_counts": same}
+    t = max(all_max(ctx, [t]))
+    m = int(res["w"]["nrows"].sum())
+    out = None
+    if rank == 0:
+        # oracle on the compact panel of the rows the sample touches (same windows, same arithmetic: snpmatch.py / csmatch.py)
+        rows = s["rows"][s["rows"] >= 0]
+        codes = synth.panel_codes(synth.SEED_PANEL, rows, n_acc)
+        row_chr = np.searchsorted(regions[:, 1], rows, side="right")
+        creg = np.array([[int((row_chr < c).sum()), int((row_chr <= c).sum())] for c in range(len(regions))], dtype=np.int64)
+        names = np.array(synth.TAIR10_CHRS)
+        t0 = time.perf_counter()
+        o = orc.window_genotyper(codes, names, creg, positions[rows], np.char.add("Chr", names[s["chr_ix"]]), s["pos"].astype(np.int64), s["wei"],
+                                 gen.chrs, gen.chrlen, 300000)
+        cpu_s = time.perf_counter() - t0
+        ok = o.num_snps == m and len(o.windows) == int((full["nrows"] > 0).sum())
+        calls_ok = True
+        for k, (widx, sc, ni) in enumerate(o.windows):
+            ok = ok and np.array_equal(full["ninfo"][widx - 1], ni)
+            ok = ok and (np.array_equal(full["score"][widx - 1], sc) if world == 1 else np.allclose(full["score"][widx - 1], sc, rtol=1e-12, atol=0))
+            if k % 20 == 0:                          # per-window epilogue on a sample of the windows
+                lik, lr, ident, num_amb, keep = orc.window_epilogue(sc, ni)
+                calls_ok = calls_ok and np.array_equal(full["identical"][widx - 1], ident.astype(np.uint8)) and int(full["num_amb"][widx - 1]) == num_amb
+        ok = ok and np.array_equal(res["tot"]["ninfo"][0], o.tot_ninfo) and np.array_equal(res["tot"]["matches"][0], o.tot_score.astype(np.int64))
+        out = {"workload": "configs[2]: cross, %d windows of 300 kb + 45 simulated F1s, one PL sample (%d markers, %d matched) vs %d x %d, %s" % (
+                   n_w, len(s["pos"]), m, n_acc, len(positions), "one GPU" if world == 1 else "panel sharded over %d GPUs, one all-reduce of the per-window partials" % world),
+               "value": m * n_acc / t, "unit": UNIT, "host_call_ms": 1e3 * t, "device_ms_rank0": tm["total_ms"], "score_kernel_ms_rank0": tm["score_ms"],
+               "join_ms_rank0": tm["join_ms"], "windows_with_markers": int((res["w"]["nrows"] > 0).sum()), "surviving_rows": int(len(res["w"]["acc"])),
+               "top_accession_is_true": bool(int(np.nanargmin(res["tot"]["L"][0])) == 7),
+               "parity": bool(ok and calls_ok), "parity_bar": "every window: informative sites ==, float scores %s; totals ==; identity calls and num_amb of every 20th window ==" % (
+                   "==" if world == 1 else "rtol 1e-12 (boundary windows are sums of two ranks)"),
+               "cpu_oracle_s": cpu_s}
     b.close()
     return out
 

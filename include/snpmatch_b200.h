@@ -270,6 +270,18 @@ int snpm_score(snpm_db *db, const int32_t *s_chrom_id, const int32_t *s_pos, con
 int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len,
                            const int32_t *win_count, const int32_t *win_off, int32_t n_windows,
                            const int32_t *kmax, int64_t kmax_len, double lr_thres);
+/* The same in two halves for a panel sharded by SNP-row ranges over several GPUs: _begin joins the sample with this
+ * device's rows, finds the windows' bounds and scores every window's local rows (windows without rows here give zeros), then
+ * packs score | ninfo | rows of all windows into ONE device buffer of *n_doubles f64 (integers are exact in f64): the caller
+ * sums it over the ranks in place (one all-reduce: a window's rows lie in one shard except at the <= G-1 shard boundaries, where
+ * two ranks contribute); _finish unpacks the sums and runs totals, per-window likelihoods, identity calls and the compaction on
+ * them.  Fetches then return the window rows of ALL ranks' markers; matched_s_idx stays this rank's (the caller concatenates).
+ * fp64 window scores of the boundary windows are sums of two in-order partial sums (last bits may differ from the reference's
+ * single in-order sum; integers do not). */
+int snpm_batch_run_windows_begin(snpm_batch *b, int skip_db_hets, int64_t bin_len, const int32_t *win_count, const int32_t *win_off,
+                                 int32_t n_windows, const int32_t *kmax, int64_t kmax_len, double lr_thres, void **dev_ptr,
+                                 int64_t *n_doubles);
+int snpm_batch_run_windows_finish(snpm_batch *b);
 /* win_score f64[W,A], win_ninfo int32[W,A], win_L f64[W,A], win_LR f64[W,A],
  * win_identical uint8[W,A], win_num_amb int32[W], win_nrows int32[W] (matched markers per window),
  * matched_s_idx int64[capacity] in window order (matchedTarInd, csmatch.py:90) with *n_matched;

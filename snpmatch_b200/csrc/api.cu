@@ -1013,6 +1013,7 @@ static int batch_group_sort_t(snpm_batch *b) {
     k_tile_ranges<<<(tiles + 255) / 256, 256, 0, st>>>(mstart, tsample, tfirst, tiles, range);
     k_group_ids<KeyT><<<tiles, RS_THREADS, 0, st>>>(b->d_key_a.as<KeyT>(), range, tsample, b->d_hash.as<unsigned long long>(), b->d_slot_gid.as<uint16_t>(),
                                                     b->d_ngroups.as<int32_t>(), b->d_gid.as<uint16_t>(), hist);
+    k_group_scan<<<int(b->S), 1024, 0, st>>>(hist, tfirst, b->d_ngroups.as<int32_t>(), b->d_goff.as<int32_t>());
     SNPM_CUDA(cudaMemsetAsync(b->d_blk_chg.p, 0, size_t(std::max<int64_t>(b->nseg_cap, 1)) * size_t(b->gchunk / GR_BLOCK) * 8, st));
     k_group_place<<<tiles, RS_THREADS, size_t(GH_MAX_GROUPS) * 20, st>>>(b->d_gid.as<uint16_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
                                                                         b->d_pair_db.as<int32_t>(), b->track_pairs ? b->d_pair_s.as<int32_t>() : nullptr, mstart, tsample,
@@ -1020,7 +1021,7 @@ static int batch_group_sort_t(snpm_batch *b) {
     k_group_marks<KeyT><<<int(b->S), 1024, 0, st>>>(b->d_goff.as<int32_t>(), gkeys, b->d_ngroups.as<int32_t>(), mstart, b->d_seg_off.as<int32_t>(), b->gchunk,
                                                     b->code_bits, b->d_blk_chg.as<unsigned long long>());
     SNPM_KERNEL_CHECK();
-    b->launches += 5;
+    b->launches += 6;
     return SNPM_OK;
 }
 
@@ -1822,8 +1823,9 @@ int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, c
 }
 
 // ---- A5 + A6 ----------------------------------------------------------------------------------------
-int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, const int32_t *win_count, const int32_t *win_off,
-                           int32_t n_windows, const int32_t *kmax, int64_t kmax_len, double lr_thres) {
+// phase 1 of `cross` on this device's rows: join, window bounds, one order-exact segment per window
+static int windows_begin(snpm_batch *b, int skip_db_hets, int64_t bin_len, const int32_t *win_count, const int32_t *win_off,
+                         int32_t n_windows, const int32_t *kmax, int64_t kmax_len, double lr_thres) {
     if (!b || bin_len <= 0 || n_windows < 0 || !win_count || !win_off || !kmax || kmax_len < 1)
         return fail(SNPM_E_ARG, "snpm_batch_run_windows: bad arguments");
     if (b->S != 1) return fail(SNPM_E_ARG, "snpm_batch_run_windows: windows are scored for a single-sample batch");
@@ -1840,6 +1842,8 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
     SNPM_TRY(b->d_win_off.ensure(size_t(std::max(db->n_chr, 1)) * 4));
     SNPM_TRY(b->d_win_begin.ensure(size_t(std::max(W, 1)) * 4));
     SNPM_TRY(b->d_win_end.ensure(size_t(std::max(W, 1)) * 4));
+    SNPM_TRY(b->d_win_nrows.ensure(size_t(std::max(W, 1)) * 4));
+    SNPM_TRY(b->d_win_zero.ensure(size_t(std::max(W, 1)) * 4));
     SNPM_TRY(b->d_kmax.ensure(size_t(kmax_len) * 4));
     SNPM_TRY(b->d_win_L.ensure(WA * 8));
     SNPM_TRY(b->d_win_LR.ensure(WA * 8));
@@ -1850,17 +1854,21 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
         SNPM_CUDA(cudaMemcpyAsync(b->d_win_off.p, win_off, size_t(db->n_chr) * 4, cudaMemcpyHostToDevice, st));
     }
     SNPM_CUDA(cudaMemcpyAsync(b->d_kmax.p, kmax, size_t(kmax_len) * 4, cudaMemcpyHostToDevice, st));
+    b->kmax_len = kmax_len;
     rec(b, SNPM_EV_START);
     SNPM_TRY(batch_join(b, 0));
     SNPM_CUDA(cudaMemsetAsync(b->d_win_begin.p, 0, size_t(std::max(W, 1)) * 4, st));
     SNPM_CUDA(cudaMemsetAsync(b->d_win_end.p, 0, size_t(std::max(W, 1)) * 4, st));
+    SNPM_CUDA(cudaMemsetAsync(b->d_win_zero.p, 0, size_t(std::max(W, 1)) * 4, st));
+    SNPM_CUDA(cudaMemsetAsync(b->d_win_nrows.p, 0, size_t(std::max(W, 1)) * 4, st));
     if (b->n > 0 && W > 0) {
         k_window_bounds<<<int(ceil_div64(b->n, 256)), 256, 0, st>>>(b->d_pair_s.as<int32_t>(), b->d_prefix.as<int32_t>() + b->n,
                                                                  b->d_chrom.as<int32_t>(), b->d_pos.as<int32_t>(), b->d_win_count.as<int32_t>(),
                                                                  b->d_win_off.as<int32_t>(), bin_len, b->d_win_begin.as<int32_t>(),
                                                                  b->d_win_end.as<int32_t>());
+        k_window_nrows<<<(W + 255) / 256, 256, 0, st>>>(b->d_win_begin.as<int32_t>(), b->d_win_end.as<int32_t>(), W, b->d_win_nrows.as<int32_t>());
         SNPM_KERNEL_CHECK();
-        b->launches += 1;
+        b->launches += 2;
     }
     rec(b, SNPM_EV_JOIN);
     ScoreArgs a = {};
@@ -1878,13 +1886,32 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
     SNPM_TRY(launch_score(st, a, W, skip_db_hets != 0));
     if (W > 0) b->launches += 1;
     rec(b, SNPM_EV_SCORE);
+    b->n_windows = W;
+    b->bin_len = bin_len;
+    b->lr_thres = lr_thres;
+    b->win_pending = true;
+    b->ran = b->ran_windows = b->epilogue_done = false;
+    return SNPM_OK;
+}
+
+// phase 2: totals over the windows in order, per-window likelihoods / identity calls, compaction of the rows the reference keeps —
+// on this device's partials, or on the sums over all ranks
+static int windows_finish(snpm_batch *b) {
+    snpm_db *db = b->db;
+    cudaStream_t st = db->stream;
+    const int32_t W = b->n_windows;
+    const size_t WA = size_t(std::max(W, 1)) * db->n_acc;
+    const int32_t a_pad = db->stride * 32;
+    const double *part_score = b->d_part_score.as<double>();
+    const int32_t *part_ninfo = b->d_part_ninfo.as<int32_t>();
+    const int32_t *zero = b->d_win_zero.as<int32_t>(), *nrows = b->d_win_nrows.as<int32_t>();
     dim3 cgrid((db->n_acc + 31) / 32, 1);
-    k_combine<<<cgrid, 32, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, nullptr, nullptr, W, a.seg_begin, a.seg_end, b->d_red.as<double>());
+    k_combine<<<cgrid, 32, 0, st>>>(part_score, part_ninfo, a_pad, db->n_acc, nullptr, nullptr, W, zero, nrows, b->d_red.as<double>());
     SNPM_KERNEL_CHECK();
     b->launches += 1;
     if (W > 0) {
-        k_window_epilogue<<<W, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, a.seg_begin, a.seg_end, b->d_kmax.as<int32_t>(), kmax_len,
-                                             lr_thres, b->d_win_L.as<double>(), b->d_win_LR.as<double>(), b->d_win_ident.as<uint8_t>(),
+        k_window_epilogue<<<W, 256, 0, st>>>(part_score, part_ninfo, a_pad, db->n_acc, zero, nrows, b->d_kmax.as<int32_t>(), b->kmax_len,
+                                             b->lr_thres, b->d_win_L.as<double>(), b->d_win_LR.as<double>(), b->d_win_ident.as<uint8_t>(),
                                              b->d_win_amb.as<int32_t>(), b->d_status.as<int>());
         SNPM_KERNEL_CHECK();
         b->launches += 1;
@@ -1897,8 +1924,8 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
         SNPM_TRY(b->d_row_ident.ensure(WA));
         k_window_row_offsets<<<1, 1024, 0, st>>>(b->d_win_amb.as<int32_t>(), W, db->n_acc, b->d_win_row_off.as<int32_t>());
         SNPM_KERNEL_CHECK();
-        k_window_compact<<<W, 256, 0, st>>>(a.part_score, a.part_ninfo, a.a_pad, db->n_acc, b->d_win_L.as<double>(), b->d_win_LR.as<double>(),
-                                            b->d_win_ident.as<uint8_t>(), b->d_win_row_off.as<int32_t>(), lr_thres, b->d_row_acc.as<int32_t>(),
+        k_window_compact<<<W, 256, 0, st>>>(part_score, part_ninfo, a_pad, db->n_acc, b->d_win_L.as<double>(), b->d_win_LR.as<double>(),
+                                            b->d_win_ident.as<uint8_t>(), b->d_win_row_off.as<int32_t>(), b->lr_thres, b->d_row_acc.as<int32_t>(),
                                             b->d_row_score.as<double>(), b->d_row_ninfo.as<int32_t>(), b->d_row_L.as<double>(),
                                             b->d_row_ident.as<uint8_t>());
         SNPM_KERNEL_CHECK();
@@ -1906,13 +1933,47 @@ int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, con
     }
     rec(b, SNPM_EV_COMBINE);
     SNPM_CUDA(cudaEventRecord(b->ev_inputs_free, st));
-    b->n_windows = W;
-    b->bin_len = bin_len;
-    b->lr_thres = lr_thres;
+    b->win_pending = false;
     b->ran = true;
     b->ran_windows = true;
     b->epilogue_done = false;
     return SNPM_OK;
+}
+
+int snpm_batch_run_windows(snpm_batch *b, int skip_db_hets, int64_t bin_len, const int32_t *win_count, const int32_t *win_off,
+                           int32_t n_windows, const int32_t *kmax, int64_t kmax_len, double lr_thres) {
+    SNPM_TRY(windows_begin(b, skip_db_hets, bin_len, win_count, win_off, n_windows, kmax, kmax_len, lr_thres));
+    b->win_reduced = false;
+    return windows_finish(b);
+}
+
+int snpm_batch_run_windows_begin(snpm_batch *b, int skip_db_hets, int64_t bin_len, const int32_t *win_count, const int32_t *win_off,
+                                 int32_t n_windows, const int32_t *kmax, int64_t kmax_len, double lr_thres, void **dev_ptr, int64_t *n_doubles) {
+    if (!dev_ptr || !n_doubles) return fail(SNPM_E_ARG, "snpm_batch_run_windows_begin: NULL output");
+    SNPM_TRY(windows_begin(b, skip_db_hets, bin_len, win_count, win_off, n_windows, kmax, kmax_len, lr_thres));
+    snpm_db *db = b->db;
+    const int64_t cells = int64_t(std::max(n_windows, 1)) * db->stride * 32;
+    SNPM_TRY(b->d_win_red.ensure(size_t(2 * cells + std::max(n_windows, 1)) * 8));
+    k_window_pack<<<int(ceil_div64(cells, 256)), 256, 0, db->stream>>>(b->d_part_score.as<double>(), b->d_part_ninfo.as<int32_t>(), b->d_win_nrows.as<int32_t>(),
+                                                                      cells, n_windows, b->d_win_red.as<double>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    *dev_ptr = b->d_win_red.p;
+    *n_doubles = 2 * cells + n_windows;
+    return SNPM_OK;
+}
+
+int snpm_batch_run_windows_finish(snpm_batch *b) {
+    if (!b || !b->win_pending) return fail(SNPM_E_STATE, "snpm_batch_run_windows_finish: call snpm_batch_run_windows_begin first");
+    snpm_db *db = b->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    const int64_t cells = int64_t(std::max(b->n_windows, 1)) * db->stride * 32;
+    k_window_unpack<<<int(ceil_div64(cells, 256)), 256, 0, db->stream>>>(b->d_win_red.as<double>(), cells, b->n_windows, b->d_part_score.as<double>(),
+                                                                        b->d_part_ninfo.as<int32_t>(), b->d_win_nrows.as<int32_t>());
+    SNPM_KERNEL_CHECK();
+    b->launches += 1;
+    b->win_reduced = true;
+    return windows_finish(b);
 }
 
 int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninfo, double *win_L, double *win_LR, uint8_t *win_identical,
@@ -1923,7 +1984,7 @@ int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninf
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
     const size_t W = size_t(b->n_windows), A = size_t(db->n_acc), a_pad = size_t(db->stride) * 32;
-    std::vector<int32_t> wb(W + 1), we(W + 1), ps;
+    std::vector<int32_t> wb(W + 1), we(W + 1), nr(W + 1), ps;
     if (W) {
         if (win_score) SNPM_CUDA(cudaMemcpy2DAsync(win_score, A * 8, b->d_part_score.p, a_pad * 8, A * 8, W, cudaMemcpyDeviceToHost, st));
         if (win_ninfo) SNPM_CUDA(cudaMemcpy2DAsync(win_ninfo, A * 4, b->d_part_ninfo.p, a_pad * 4, A * 4, W, cudaMemcpyDeviceToHost, st));
@@ -1933,13 +1994,14 @@ int snpm_batch_fetch_windows(snpm_batch *b, double *win_score, int32_t *win_ninf
         if (win_num_amb) SNPM_CUDA(cudaMemcpyAsync(win_num_amb, b->d_win_amb.p, W * 4, cudaMemcpyDeviceToHost, st));
         SNPM_CUDA(cudaMemcpyAsync(wb.data(), b->d_win_begin.p, W * 4, cudaMemcpyDeviceToHost, st));
         SNPM_CUDA(cudaMemcpyAsync(we.data(), b->d_win_end.p, W * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpyAsync(nr.data(), b->d_win_nrows.p, W * 4, cudaMemcpyDeviceToHost, st));     // rows of the window on ALL ranks after a sharded run
     }
     int32_t m_all = 0;
     SNPM_CUDA(cudaMemcpyAsync(&m_all, b->d_prefix.as<int32_t>() + b->n, 4, cudaMemcpyDeviceToHost, st));
     SNPM_TRY(snpm_batch_wait(b, nullptr));
     int64_t total = 0;
     for (size_t w = 0; w < W; ++w) {
-        if (win_nrows) win_nrows[w] = we[w] - wb[w];
+        if (win_nrows) win_nrows[w] = nr[w];
         total += we[w] - wb[w];
     }
     if (n_matched) *n_matched = total;
@@ -1969,11 +2031,12 @@ int snpm_batch_fetch_window_rows(snpm_batch *b, int32_t *win_row_off, int32_t *w
     SNPM_CUDA(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
     const size_t W = size_t(b->n_windows);
-    std::vector<int32_t> off(W + 1, 0), wb(W + 1), we(W + 1), ps;
+    std::vector<int32_t> off(W + 1, 0), wb(W + 1), we(W + 1), nr(W + 1), ps;
     if (W) {
         SNPM_CUDA(cudaMemcpyAsync(off.data(), b->d_win_row_off.p, (W + 1) * 4, cudaMemcpyDeviceToHost, st));
         SNPM_CUDA(cudaMemcpyAsync(wb.data(), b->d_win_begin.p, W * 4, cudaMemcpyDeviceToHost, st));
         SNPM_CUDA(cudaMemcpyAsync(we.data(), b->d_win_end.p, W * 4, cudaMemcpyDeviceToHost, st));
+        SNPM_CUDA(cudaMemcpyAsync(nr.data(), b->d_win_nrows.p, W * 4, cudaMemcpyDeviceToHost, st));     // rows of the window on ALL ranks after a sharded run
         if (win_num_amb) SNPM_CUDA(cudaMemcpyAsync(win_num_amb, b->d_win_amb.p, W * 4, cudaMemcpyDeviceToHost, st));
     }
     int32_t m_all = 0;
@@ -1984,7 +2047,7 @@ int snpm_batch_fetch_window_rows(snpm_batch *b, int32_t *win_row_off, int32_t *w
     if (win_row_off) memcpy(win_row_off, off.data(), (W + 1) * 4);
     int64_t total = 0;
     for (size_t w = 0; w < W; ++w) {
-        if (win_nrows) win_nrows[w] = we[w] - wb[w];
+        if (win_nrows) win_nrows[w] = nr[w];
         total += we[w] - wb[w];
     }
     if (n_matched) *n_matched = total;

@@ -133,6 +133,10 @@ struct snpm_batch {
     int64_t bin_len = 0;
     double lr_thres = 3.841;
     snpm::DevBuf d_win_count, d_win_off, d_win_begin, d_win_end, d_kmax, d_win_L, d_win_LR, d_win_ident, d_win_amb;
+    snpm::DevBuf d_win_nrows, d_win_zero, d_win_red;     // rows per window (summed over the ranks of a sharded run), zeros, the packed partials
+    int64_t kmax_len = 0;
+    bool win_pending = false;                            // snpm_batch_run_windows_begin done, _finish not yet
+    bool win_reduced = false;                            // the last windows run went through the packed buffer (sharded run)
     snpm::DevBuf d_win_row_off, d_row_acc, d_row_score, d_row_ninfo, d_row_L, d_row_ident;   // surviving rows, compacted
     // f1
     snpm::DevBuf d_f1_acc, d_f1_part, d_f1_out;

@@ -90,7 +90,20 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
     const int flag = row >= 0;
     int total;
     const int ex = block_excl_scan(flag, &total, s_warp);
-    unsigned long long ins = ~0ull;                 // the key to insert, or nothing
+    __shared__ int64_t s_first_sm;
+    if (threadIdx.x == 0) {                         // sample of the tile's first marker
+        const int64_t i0 = int64_t(blockIdx.x) * JOIN_TILE;
+        int64_t lo = 0, hi = S;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (off[mid] <= i0) lo = mid; else hi = mid;
+        }
+        s_first_sm = lo;
+    }
+    __syncthreads();
+    const int64_t s_first = s_first_sm;
+    unsigned long long ins = ~0ull, fold = 0ull;    // the key to insert, or nothing
+    bool solo = false;
     int64_t smp = 0;
     if (i < n) {
         const int32_t p = tile_off[blockIdx.x] + ex;
@@ -111,18 +124,18 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
             const int b = code_bits;
             const KeyT kk = (KeyT(c) << (3 * b)) | (KeyT(cd[c]) << (2 * b)) | (KeyT(cd[gs_slow_class(c)]) << b) | KeyT(cd[gs_fast_class(c)]);
             key[p] = kk;
-            int64_t lo = 0, hi = S;                         // sample of marker i: the last offset <= i
-            while (hi - lo > 1) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (off[mid] <= i) lo = mid; else hi = mid;
-            }
+            int64_t lo = s_first;                           // sample of marker i: the last offset <= i (a tile spans few samples)
+            while (lo + 1 < S && off[lo + 1] <= i) ++lo;
             smp = lo;
+            // one insert per distinct (sample, key) of the warp: a sample's common triples would otherwise hammer one slot.  The
+            // sample is folded into the word that is matched (keys have at most 50 bits) when it is close enough to the tile's first
             ins = (unsigned long long)(kk);
+            if (lo - s_first < 8192) fold = (unsigned long long)(lo - s_first) << 50;
+            else solo = true;
         }
     }
-    // one insert per distinct (sample, key) of the warp: a sample's common triples would otherwise hammer one slot
-    const uint32_t peers = __match_any_sync(0xffffffffu, ins) & __match_any_sync(0xffffffffu, smp);
-    if (ins != ~0ull && (threadIdx.x & 31) == __ffs(peers) - 1) gh_insert(hash + size_t(smp) * GH_SLOTS, ins, overflow + smp);
+    const uint32_t peers = __match_any_sync(0xffffffffu, solo ? (0xffffull << 48 | (unsigned long long)(threadIdx.x)) : (ins | fold));
+    if (ins != ~0ull && (solo || (threadIdx.x & 31) == __ffs(peers) - 1)) gh_insert(hash + size_t(smp) * GH_SLOTS, ins, overflow + smp);
 }
 
 // Tile t of the sort covers pairs [begin, end) of sample tile_sample[t]: the lt-th RS_TILE pairs of the sample's matched range
@@ -216,9 +229,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_group_ids(const KeyT *__restrict
     const int t = blockIdx.x;
     const int2 rg = range[t];
     const int begin = rg.x, end = rg.y;
-    if (begin >= end) return;
     const int s = tile_sample[t];
     const int ng = ngroups[s];
+    if (begin >= end) {                                             // an empty tile (the layout is an upper bound): its counts are zero
+        for (int d = threadIdx.x; d < ng; d += RS_THREADS) tile_hist[size_t(t) * GH_MAX_GROUPS + d] = 0u;
+        return;
+    }
     for (int d = threadIdx.x; d < ng; d += RS_THREADS) h[d] = 0u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long *tab = hash + size_t(s) * GH_SLOTS;
@@ -244,11 +260,45 @@ __global__ void __launch_bounds__(RS_THREADS) k_group_ids(const KeyT *__restrict
     for (int d = threadIdx.x; d < ng; d += RS_THREADS) out[d] = h[d];
 }
 
-// One CTA per tile: the stable partition of the tile's pairs by dense id, three steps in one kernel:
-//   offsets  where the tile's pairs of id g go inside the sample's range = (pairs of smaller ids in the whole sample) + (pairs
-//            of id g in earlier tiles of the sample), from the id counts of ALL tiles of the sample (a few tens of KB out of
-//            L2 per CTA: cheaper than a scan kernel between two dependent launches); the sample's first tile also publishes
-//            the group starts goff[s][0..ngroups];
+// One CTA per sample: tile_hist[t][g] (pairs of id g in tile t) -> pairs of id g in EARLIER tiles of the sample, and
+// goff[s][g] = first position of group g inside the sample's grouped range (goff[s][ngroups] = its pairs).
+__global__ void __launch_bounds__(1024) k_group_scan(uint32_t *__restrict__ tile_hist, const int32_t *__restrict__ tile_first,
+                                                     const int32_t *__restrict__ ngroups, int32_t *__restrict__ goff) {
+    __shared__ int s_warp[33];
+    const int s = blockIdx.x;
+    const int ng = ngroups[s];
+    const int t0 = tile_first[s], t1 = tile_first[s + 1];
+    constexpr int PITCH = GH_MAX_GROUPS, U = 8;
+    uint32_t tot[2] = {0u, 0u};                                   // thread -> ids 2 tid, 2 tid + 1
+    const int d0 = 2 * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (d0 + j < ng) {
+            uint32_t run = 0u;
+            for (int t = t0; t < t1; t += U) {
+                uint32_t c[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) c[u] = t + u < t1 ? tile_hist[size_t(t + u) * PITCH + d0 + j] : 0u;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (t + u < t1) tile_hist[size_t(t + u) * PITCH + d0 + j] = run;
+                    run += c[u];
+                }
+            }
+            tot[j] = run;
+        }
+    }
+    int all;
+    const int ex = block_excl_scan(int(tot[0] + tot[1]), &all, s_warp);
+    int32_t *out = goff + size_t(s) * (GH_MAX_GROUPS + 1);
+    if (d0 < ng) out[d0] = ex;
+    if (d0 + 1 < ng) out[d0 + 1] = ex + int(tot[0]);
+    if (threadIdx.x == 0) out[ng] = all;
+}
+
+// One CTA per tile: the stable partition of the tile's pairs by dense id:
+//   offsets  where the tile's pairs of id g go inside the sample's range = goff[s][g] + (pairs of id g in earlier tiles), both
+//            from k_group_scan;
 //   ranks    warp w owns pairs [256 w, 256 w + 256) of the tile and takes them 32 at a time in order, so ranks inside an id
 //            follow the pair order: (pairs of that id in earlier warps) + (earlier rounds of this warp) + (lower lanes of this
 //            round, match.any);
@@ -261,9 +311,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_group_place(const uint16_t *_
                                                               const int32_t *__restrict__ mstart, const int32_t *__restrict__ tile_sample,
                                                               const int32_t *__restrict__ tile_first, const int2 *__restrict__ range,
                                                               const uint32_t *__restrict__ tile_hist, const int32_t *__restrict__ ngroups,
-                                                              int32_t *__restrict__ goff) {
+                                                              const int32_t *__restrict__ goff) {
     extern __shared__ uint32_t rs_sm[];
-    __shared__ int s_warp[33];
     constexpr int NW = RS_THREADS / 32;
     constexpr int PITCH = GH_MAX_GROUPS;
     uint16_t *whist = reinterpret_cast<uint16_t *>(rs_sm);          // [NW][PITCH]
@@ -272,8 +321,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_group_place(const uint16_t *_
     const int2 rg = range[t];
     const int begin = rg.x, end = rg.y;
     const int s = tile_sample[t];
-    const int t0 = tile_first[s], t1 = tile_first[s + 1];
-    if (begin >= end && t != t0) return;                            // an empty tile (the first tile of a sample still writes goff)
+    if (begin >= end) return;                                       // an empty tile (the whole CTA)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t d[RS_PER_THREAD];
     int32_t pdb[RS_PER_THREAD], ps[RS_PER_THREAD];
@@ -288,45 +336,9 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_group_place(const uint16_t *_
     const int ng = ngroups[s];
     const int base = mstart[s];
     for (int j = threadIdx.x; j < NW * PITCH / 2; j += RS_THREADS) rs_sm[j] = 0u;
-    {
-        const int per = (ng + RS_THREADS - 1) / RS_THREADS;         // 1..8 consecutive ids per thread
-        const int d0 = threadIdx.x * per;
-        uint32_t total[8], before[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) total[j] = before[j] = 0u;
-        constexpr int U = 16;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < per && d0 + j < ng) {
-                for (int tt = t0; tt < t1; tt += U) {
-                    uint32_t c[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) c[u] = tt + u < t1 ? __ldg(tile_hist + size_t(tt + u) * PITCH + d0 + j) : 0u;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        total[j] += c[u];
-                        if (tt + u < t) before[j] += c[u];
-                    }
-                }
-            }
-        }
-        uint32_t mine = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mine += total[j];
-        int all;
-        uint32_t run = uint32_t(block_excl_scan(int(mine), &all, s_warp));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < per && d0 + j < ng) {
-                off[d0 + j] = run + before[j];
-                if (t == t0) goff[size_t(s) * (GH_MAX_GROUPS + 1) + d0 + j] = int32_t(run);
-                run += total[j];
-            }
-        }
-        if (t == t0 && threadIdx.x == 0) goff[size_t(s) * (GH_MAX_GROUPS + 1) + ng] = all;
-    }
+    for (int g = threadIdx.x; g < ng; g += RS_THREADS)
+        off[g] = uint32_t(__ldg(goff + size_t(s) * (GH_MAX_GROUPS + 1) + g)) + __ldg(tile_hist + size_t(t) * PITCH + g);
     __syncthreads();
-    if (begin >= end) return;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint16_t *mine_h = whist + size_t(warp) * PITCH;
     uint32_t rank[RS_PER_THREAD];

@@ -39,6 +39,33 @@ __global__ void __launch_bounds__(256) k_window_bounds(const int32_t *__restrict
     if (r == m - 1 && w >= 0) win_end[w] = int32_t(m);
 }
 
+// rows of every window on this device, and the packing of the per-window partials into ONE f64 buffer for a cross-GPU sum
+// (a window's rows lie in one SNP-row shard except at the <= G-1 shard boundaries; summing the [W, A] partials of all
+// ranks handles both): red = score [W * a_pad] | ninfo as f64 [W * a_pad] | rows as f64 [W]  (integers are exact in f64)
+__global__ void __launch_bounds__(256) k_window_nrows(const int32_t *__restrict__ win_begin, const int32_t *__restrict__ win_end, int32_t W,
+                                                      int32_t *__restrict__ nrows) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < W) nrows[w] = win_end[w] - win_begin[w];
+}
+__global__ void __launch_bounds__(256) k_window_pack(const double *__restrict__ part_score, const int32_t *__restrict__ part_ninfo,
+                                                     const int32_t *__restrict__ nrows, int64_t cells, int32_t W, double *__restrict__ red) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < cells) {
+        red[i] = part_score[i];
+        red[cells + i] = double(part_ninfo[i]);
+    }
+    if (i < W) red[2 * cells + i] = double(nrows[i]);
+}
+__global__ void __launch_bounds__(256) k_window_unpack(const double *__restrict__ red, int64_t cells, int32_t W, double *__restrict__ part_score,
+                                                       int32_t *__restrict__ part_ninfo, int32_t *__restrict__ nrows) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < cells) {
+        part_score[i] = red[i];
+        part_ninfo[i] = int32_t(red[cells + i]);
+    }
+    if (i < W) nrows[i] = int32_t(red[2 * cells + i]);
+}
+
 // One CTA per window: likelihoods from the FLOAT window scores, per-window nanmin, LR, the number of
 // accessions with LR < lr_thres, and the identity call identical <=> floor(n - x - 1) + 1 <= kmax[n]
 // (np_test_identity = binom.sf(n-x-1, n, e) >= 0.05, snpmatch.py:57-72; the table is built by the host

@@ -225,6 +225,8 @@ SIGNATURES = {
     "snpm_batch_timings": (C.c_int, [_p, _p, C.c_int]),
     "snpm_score": (C.c_int, [_p, _p, _p, _p, _i64, C.c_int, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "snpm_batch_run_windows": (C.c_int, [_p, C.c_int, _i64, _p, _p, _i32, _p, _i64, _f64]),
+    "snpm_batch_run_windows_begin": (C.c_int, [_p, C.c_int, _i64, _p, _p, _i32, _p, _i64, _f64, _p, _p]),
+    "snpm_batch_run_windows_finish": (C.c_int, [_p]),
     "snpm_batch_fetch_windows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "snpm_batch_fetch_window_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "snpm_batch_f1_pairs": (C.c_int, [_p, _p, _i32, _p, _p]),
@@ -618,6 +620,21 @@ class Batch(object):
         self.n_windows = int(n_windows)
         check(load().snpm_batch_run_windows(self._h, int(bool(skip_db_hets)), int(bin_len), ptr(win_count), ptr(win_off),
                                             self.n_windows, ptr(kmax), len(kmax), float(lr_thres)))
+
+    def run_windows_begin(self, skip_db_hets, bin_len, win_count, win_off, n_windows, kmax, lr_thres=3.841):
+        """First half of run_windows on a SNP-row shard: returns (device pointer, number of f64) of the packed per-window
+        partials (score | ninfo | rows) to be summed over the ranks in place; run_windows_finish() then completes the run."""
+        win_count = as_c(win_count, np.int32)
+        win_off = as_c(win_off, np.int32)
+        kmax = as_c(kmax, np.int32)
+        self.n_windows = int(n_windows)
+        p, n = C.c_void_p(), C.c_int64(0)
+        check(load().snpm_batch_run_windows_begin(self._h, int(bool(skip_db_hets)), int(bin_len), ptr(win_count), ptr(win_off),
+                                                  self.n_windows, ptr(kmax), len(kmax), float(lr_thres), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def run_windows_finish(self):
+        check(load().snpm_batch_run_windows_finish(self._h))
 
     def fetch_windows(self):
         W, A = self.n_windows, self.db.n_acc

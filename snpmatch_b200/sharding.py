@@ -210,3 +210,53 @@ def p2p_reduce_scatter(batch):
     """After batch.run() on every rank: rows [rank*S/world, (rank+1)*S/world) of this rank's reduce buffer become the sums
     over all ranks (lib.Batch.set_result_range must select that share).  One kernel, stream-ordered; the host does not wait."""
     batch.reduce_peers()
+
+
+# ---- `cross` on a sharded panel (SURVEY 8e; csmatch.py:64-129) --------------------------------------------------------------
+def device_view(ptr, n, device):
+    """Zero-copy torch view of n f64 at a device pointer of the library."""
+    import torch
+
+    class _Dev(object):
+        pass
+
+    holder = _Dev()
+    holder.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(holder, device=device)
+
+
+def run_windows_sharded(batch, dist, device, skip_db_hets, bin_len, win_count, win_off, n_windows, kmax, lr_thres=3.841):
+    """CrossIdentifier.window_genotyper (csmatch.py:64-104) over a panel sharded by SNP-row ranges: every rank scores the
+    windows' rows it holds, ONE all-reduce sums the per-window partials (score, informative sites, rows: a window lies in one
+    shard except at the shard boundaries), then every rank runs totals, per-window likelihoods, identity calls and the
+    compaction on identical sums.  `batch` holds this rank's slice of the sample's markers (position order)."""
+    ptr, n = batch.run_windows_begin(skip_db_hets, bin_len, win_count, win_off, n_windows, kmax, lr_thres)
+    if dist is not None and dist.get_world_size() > 1:
+        dist.all_reduce(device_view(ptr, n, device))
+    batch.run_windows_finish()
+
+
+def f1_pairs_sharded(batch, dist, device, acc_idx):
+    """match_insilico_f1s (csmatch.py:106-129) over a sharded panel: partial (score, numinfo) of the 45 pairs per rank, summed."""
+    import torch
+    score, ninfo = batch.f1_pairs(acc_idx)
+    if dist is not None and dist.get_world_size() > 1:
+        t = torch.tensor(np.concatenate([score, ninfo.astype(np.float64)]), dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        v = t.cpu().numpy()
+        score, ninfo = v[:len(score)], v[len(score):].astype(np.int64)
+    return score, ninfo
+
+
+def window_partials_host(win_score, win_ninfo, win_nrows):
+    """Host picture of the packed buffer of snpm_batch_run_windows_begin (csrc/windows.cuh k_window_pack) for a_pad == n_acc:
+    score [W*A] | ninfo as f64 [W*A] | rows as f64 [W] — used by the gloo test of the layout."""
+    s = np.asarray(win_score, dtype=np.float64)
+    return np.concatenate([s.ravel(), np.asarray(win_ninfo, dtype=np.float64).ravel(), np.asarray(win_nrows, dtype=np.float64).ravel()])
+
+
+def unpack_window_partials(buf, n_windows, n_acc):
+    buf = np.asarray(buf, dtype=np.float64)
+    cells = n_windows * n_acc
+    return (buf[:cells].reshape(n_windows, n_acc), buf[cells:2 * cells].astype(np.int64).reshape(n_windows, n_acc),
+            buf[2 * cells:2 * cells + n_windows].astype(np.int64))

@@ -721,3 +721,82 @@ def test_int8_codes_outside_the_reference_range(lib):
     rs, rn = orc.match_gts_accs(np.full((n_rows, 3), 0.5), weird)
     assert np.array_equal(s, rs) and np.array_equal(n, rn)
     db.close()
+
+
+def test_cross_on_two_row_shards_equals_one_database(lib, small_panel, sample_cross):
+    """SURVEY 8(e) for `cross`: the panel cut into two SNP-row shards (both held on this one GPU, the exchange step done by
+    hand), per-window partials summed through the packed buffer of snpm_batch_run_windows_begin, then the second half on
+    both — against the unsharded run: integers and identity calls ==, float window scores == except in the window that
+    straddles the shard boundary (two in-order partial sums instead of one: rtol 1e-12), and against the oracle."""
+    import torch
+    from snpmatch_b200 import sharding
+    from snpmatch_b200.core import genomes, snpmatch
+    p, s = small_panel, sample_cross
+    n_rows, n_acc = len(p["positions"]), p["snps"].shape[1]
+    gen = genomes.Genome("athaliana_tair10")
+    cnt, off, n_w, _ = gen.window_layout(p["chrs"], 300000)
+    kmax = snpmatch.identity_kmax_table(4000, 0.02)
+    first = {str(c): i for i, c in enumerate(p["chrs"])}
+    cid = np.array([first[str(c).replace("Chr", "").replace("chr", "")] for c in s["chrs"]], dtype=np.int32)
+    pos = s["pos"].astype(np.int32)
+    # reference: one database
+    db = lib.Database(p["positions"], p["chr_regions"], n_acc)
+    db.load_int8(p["snps"])
+    b = lib.Batch(db, [0, len(pos)], cid, pos, s["wei"])
+    b.run_windows(False, 300000, cnt, off, n_w, kmax)
+    b.epilogue()
+    tot = {k: v.copy() for k, v in b.fetch().items()}
+    ref = b.fetch_windows()
+    ref_rows = b.fetch_window_rows()
+    f1_ref = b.f1_pairs(np.argsort(-tot["prob"][0])[:10])
+    b.close()
+    db.close()
+    # two shards with a boundary in the middle of a chromosome (and of a window)
+    cut = int(p["chr_regions"][1][0] + (p["chr_regions"][1][1] - p["chr_regions"][1][0]) // 3)
+    shards = []
+    for r0, r1 in ((0, cut), (cut, n_rows)):
+        d = lib.Database(p["positions"][r0:r1], sharding.local_regions(p["chr_regions"], r0, r1), n_acc, row0_global=r0)
+        d.load_int8(p["snps"][r0:r1])
+        i0, i1 = sharding.shard_marker_range(cid, pos, p["chr_regions"], p["positions"], r0, r1)
+        bb = lib.Batch(d, [0, i1 - i0], cid[i0:i1], pos[i0:i1], s["wei"][i0:i1])
+        shards.append((d, bb, i0))
+    views = []
+    for d, bb, _ in shards:
+        ptr, n = bb.run_windows_begin(False, 300000, cnt, off, n_w, kmax)
+        views.append(sharding.device_view(ptr, n, torch.device("cuda", 0)))
+    torch.cuda.synchronize()
+    total = views[0].clone() + views[1]                      # the all-reduce, by hand
+    for v in views:
+        v.copy_(total)
+    torch.cuda.synchronize()
+    matched = []
+    for d, bb, i0 in shards:
+        bb.run_windows_finish()
+        bb.epilogue()
+        t2 = bb.fetch()
+        w2 = bb.fetch_windows()
+        r2 = bb.fetch_window_rows()
+        matched.append(w2["matched_s_idx"] + i0)
+        assert np.array_equal(w2["ninfo"], ref["ninfo"]) and np.array_equal(w2["nrows"], ref["nrows"])
+        assert np.array_equal(w2["identical"], ref["identical"]) and np.array_equal(w2["num_amb"], ref["num_amb"])
+        differs = np.flatnonzero((w2["score"] != ref["score"]).any(axis=1))
+        assert len(differs) <= 1, "only the window on the shard boundary may differ in the last bits"
+        np.testing.assert_allclose(w2["score"], ref["score"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(w2["L"], ref["L"], rtol=RTOL, equal_nan=True)
+        assert np.array_equal(t2["ninfo"][0], tot["ninfo"][0]) and np.array_equal(t2["matches"][0], tot["matches"][0])
+        assert np.array_equal(r2["row_off"], ref_rows["row_off"]) and np.array_equal(r2["acc"], ref_rows["acc"])
+        assert np.array_equal(r2["ninfo"], ref_rows["ninfo"]) and np.array_equal(r2["identical"], ref_rows["identical"])
+    assert np.array_equal(np.concatenate(matched), ref["matched_s_idx"])
+    # simulated F1s: partial sums of the two shards
+    top = np.argsort(-tot["prob"][0])[:10]
+    parts = [bb.f1_pairs(top) for _, bb, _ in shards]
+    np.testing.assert_allclose(parts[0][0] + parts[1][0], f1_ref[0], rtol=1e-12)
+    assert np.array_equal(parts[0][1] + parts[1][1], f1_ref[1])
+    # oracle
+    o = orc.window_genotyper(p["snps"], p["chrs"], p["chr_regions"], p["positions"], s["chrs"], s["pos"], s["wei"], gen.chrs, gen.chrlen, 300000)
+    assert o.num_snps == int(ref["nrows"].sum())
+    for widx, sc, ni in o.windows:
+        assert np.array_equal(ref["ninfo"][widx - 1], ni) and np.array_equal(ref["score"][widx - 1], sc)
+    for d, bb, _ in shards:
+        bb.close()
+        d.close()

@@ -138,3 +138,59 @@ def test_marker_slices_cover_the_join_exactly():
         assert np.all(seen[rows >= 0] >= 1)
         assert seen.sum() <= len(rows) + 2 * world                             # slices overlap by boundary markers at most
     assert sharding.shard_marker_range(s["chr_ix"], s["pos"], regions, pos, 10, 10) == (0, 0)
+
+
+def _cross_worker(rank, world, port, out_dir):
+    """`cross` on a sharded panel (the exchange step of sharding.run_windows_sharded) with the oracle as the compute stand-in."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import sharding, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_acc, bin_len = 20, 3000000
+    panel = synth.small_panel(n_rows=3000, n_acc=n_acc)
+    s = synth.make_sample(panel["positions"], panel["chr_regions"], panel["chrs"], n_acc, true_acc=3, n_db=900, n_extra=40, seed=77)
+    chrlen = synth.TAIR10_CHRLEN
+    per_chr = [orc.num_windows(l, bin_len) for l in chrlen]
+    base = np.concatenate([[0], np.cumsum(per_chr)])
+    W = int(base[-1])
+    r0, r1 = sharding.shard_rows(len(panel["positions"]), world, rank)
+    reg = sharding.local_regions(panel["chr_regions"], r0, r1)
+    i0, i1 = sharding.shard_marker_range(s["chr_ix"], s["pos"], panel["chr_regions"], panel["positions"], r0, r1)
+    part = orc.window_genotyper(panel["snps"][r0:r1], panel["chrs"], reg, panel["positions"][r0:r1], s["chrs"][i0:i1], s["pos"][i0:i1],
+                                s["wei"][i0:i1], panel["chrs"], chrlen, bin_len)
+    score, ninfo, nrows = np.zeros((W, n_acc)), np.zeros((W, n_acc), dtype=np.int64), np.zeros(W, dtype=np.int64)
+    for widx, sc, ni in part.windows:
+        score[widx - 1], ninfo[widx - 1] = sc, ni
+    tar = part.matched_tar                                   # rows per window of this shard, from its matched markers
+    win = base[s["chr_ix"][i0:i1][tar]] + (s["pos"][i0:i1][tar] - 1) // bin_len
+    np.add.at(nrows, win.astype(np.int64), 1)
+    buf = torch.from_numpy(sharding.window_partials_host(score, ninfo, nrows))
+    dist.all_reduce(buf)
+    sc, ni, nr = sharding.unpack_window_partials(buf.numpy(), W, n_acc)
+    np.savez(os.path.join(out_dir, "cross%d.npz" % rank), score=sc, ninfo=ni, nrows=nr)
+    dist.destroy_process_group()
+
+
+def test_cross_window_partials_sum_over_two_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import snpmatch_oracle as orc
+    from snpmatch_b200 import synth
+    world = 2
+    mp.spawn(_cross_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(str(tmp_path / ("cross%d.npz" % r))) for r in range(world)]
+    for k in ("score", "ninfo", "nrows"):
+        assert np.array_equal(outs[0][k], outs[1][k])       # every rank holds the same sums
+    panel = synth.small_panel(n_rows=3000, n_acc=20)
+    s = synth.make_sample(panel["positions"], panel["chr_regions"], panel["chrs"], 20, true_acc=3, n_db=900, n_extra=40, seed=77)
+    full = orc.window_genotyper(panel["snps"], panel["chrs"], panel["chr_regions"], panel["positions"], s["chrs"], s["pos"], s["wei"],
+                                panel["chrs"], synth.TAIR10_CHRLEN, 3000000)
+    o = outs[0]
+    assert int(o["nrows"].sum()) == full.num_snps and int((o["nrows"] > 0).sum()) == len(full.windows)
+    for widx, fs, fn in full.windows:
+        assert np.array_equal(o["ninfo"][widx - 1], fn)
+        np.testing.assert_allclose(o["score"][widx - 1], fs, rtol=1e-12, atol=0)
