@@ -298,7 +298,8 @@ def rank_inputs(ctx, samples, positions, regions, r0, r1, hard=False):
         assert np.array_equal(table[pl], wei), "exp(-PL/10) table does not reproduce the weights bit for bit"
     cs = lib.code_markers(offs, chrom, pos, codes=codes, wtable=table)
     assert cs is not None
-    cs = lib.CodedSamples(pinned(ctx, cs.offsets), pinned(ctx, cs.chrom_pos), pinned(ctx, cs.codes), pinned(ctx, cs.wtable))
+    cs = lib.CodedSamples(pinned(ctx, cs.offsets), pinned(ctx, cs.chrom_pos), pinned(ctx, cs.codes), pinned(ctx, cs.wtable),
+                          codes32=pinned(ctx, cs.codes32) if cs.codes32 is not None else None)
     return cs, (pinned(ctx, offs), pinned(ctx, chrom), pinned(ctx, pos), pinned(ctx, wei)), slices
 
 
@@ -452,7 +453,7 @@ def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, wa
                 return v_
 
             def up(bt):
-                bt.upload_coded(cs)                              # 10 bytes per marker from pinned memory, on the batch's copy stream
+                bt.upload_coded(cs)                              # 8 bytes per marker from pinned memory, on the batch's copy stream
                 own_share(bt)
 
             def launch(k):
@@ -602,7 +603,7 @@ def run_b200_arm(args):
                     "h2d_bytes_per_step": int(world * h["h2d_bytes"]), "d2h_bytes_per_step": int(world * h["d2h_bytes"]),
                     "untimed_per_sample_host_work": "none: the timed region starts from the parser's arrays",
                     "inputs": "pinned host arrays as a parser hands them over, markers in position order: chromosome id and position in one "
-                              "uint32, the three integer PLs of a marker as uint16 weight codes (10 bytes per marker), + the table exp(-PL/10) "
+                              "uint32, the three integer PLs of a marker as weight codes in a second uint32 (10 bits each; 8 bytes per marker), + the table exp(-PL/10) "
                               "(%d f64); join, grouping by weight triple and scoring all happen on the device inside the step; three batches rotate "
                               "in a software pipeline (H2D of step k+3 and D2H of step k overlap the kernels of steps k+1 and k+2; filling the "
                               "pipeline is inside the timed region); the D2H holds scores, counts, likelihoods and the per-sample guard "

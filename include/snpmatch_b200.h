@@ -175,6 +175,10 @@ int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64
  * Group chunks (snpm_batch_set_group_chunk) must be multiples of 16 and at most 496 rows for coded batches. */
 int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
                             const uint16_t *codes, const double *wtable, int32_t n_wtable);
+/* the same with the three codes of a marker in one word, ref | het << 10 | alt << 20 (n_wtable <= 1024: e.g. integer PLs up to
+ * 1023): 8 bytes per marker cross the PCIe bus */
+int snpm_batch_upload_coded32(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
+                              const uint32_t *codes32, const double *wtable, int32_t n_wtable);
 /* coded batches: keep (1, default) or drop (0) the marker index of every matched pair in grouped order.  The scoring path only
  * needs the panel rows; with 0 snpm_batch_fetch_pairs answers SNPM_E_STATE for coded batches and the grouping moves one array
  * instead of two. */

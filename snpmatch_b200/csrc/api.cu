@@ -708,16 +708,17 @@ int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64
     return upload_grouped(b, n_samples, offsets, nullptr, nullptr, chrom_pos, nullptr, table, n_table, run_gid, run_end, n_runs);
 }
 
-int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *codes,
-                            const double *wtable, int32_t n_wtable) {
+static int upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *codes,
+                        const uint32_t *codes32, const double *wtable, int32_t n_wtable) {
     if (!b) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: NULL batch");
+    if (codes32 && n_wtable > 1024) return fail(SNPM_E_ARG, "snpm_batch_upload_coded32: three codes share one word only up to 1024 weight values (%d given)", n_wtable);
     snpm_db *db = b->db;
     if (n_samples < 1 || !offsets || offsets[0] != 0) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: need samples and offsets starting at 0");
     for (int64_t s = 0; s < n_samples; ++s)
         if (offsets[s + 1] < offsets[s]) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: offsets must be non-decreasing");
     const int64_t n = offsets[n_samples];
     if (n >= (int64_t(1) << 31) - 2048) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: %lld markers exceed the 2^31 limit", (long long)n);
-    if (n > 0 && (!chrom_pos || !codes)) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: NULL marker arrays");
+    if (n > 0 && (!chrom_pos || (!codes && !codes32))) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: NULL marker arrays");
     if (!wtable || n_wtable < 1 || n_wtable > 65536) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: the weight table must hold 1..65536 values");
     for (int32_t t = 0; t < n_wtable; ++t)
         if (!(wtable[t] >= 0.0) || std::isinf(wtable[t])) return fail(SNPM_E_ARG, "snpm_batch_upload_coded: weights must be finite and non-negative (entry %d)", t);
@@ -728,6 +729,7 @@ int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *off
     b->n = n;
     b->grouped = true;
     b->coded = true;
+    b->codes_packed = codes32 != nullptr;
     b->pending_expand = 2;                                      // packed words -> chromosome ids + positions at the head of the run
     b->d_runs_bad = nullptr;
     b->n_wtable = n_wtable;
@@ -784,11 +786,22 @@ int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *off
         SNPM_CUDA(cudaMemcpyAsync(b->d_tile_sample.p, b->h_tiles.data() + n_samples + 1, tile_sample.size() * 4, cudaMemcpyHostToDevice, st));
     if (n) {
         SNPM_CUDA(cudaMemcpyAsync(b->d_wei_idx.p, chrom_pos, size_t(n) * 4, cudaMemcpyHostToDevice, st));
-        SNPM_CUDA(cudaMemcpyAsync(b->d_codes.p, codes, size_t(n) * 6, cudaMemcpyHostToDevice, st));
+        if (codes32) SNPM_CUDA(cudaMemcpyAsync(b->d_codes.p, codes32, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+        else SNPM_CUDA(cudaMemcpyAsync(b->d_codes.p, codes, size_t(n) * 6, cudaMemcpyHostToDevice, st));
     }
     SNPM_CUDA(cudaEventRecord(b->ev_uploaded, st));
     b->ran = b->ran_windows = b->epilogue_done = false;
     return SNPM_OK;
+}
+
+int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint16_t *codes,
+                            const double *wtable, int32_t n_wtable) {
+    return upload_coded(b, n_samples, offsets, chrom_pos, codes, nullptr, wtable, n_wtable);
+}
+
+int snpm_batch_upload_coded32(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos, const uint32_t *codes32,
+                              const double *wtable, int32_t n_wtable) {
+    return upload_coded(b, n_samples, offsets, chrom_pos, nullptr, codes32, wtable, n_wtable);
 }
 
 int snpm_batch_coded_timings(snpm_batch *b, float *ms, int n) {
@@ -964,11 +977,13 @@ static int batch_join(snpm_batch *b, int algo) {
             if (b->key_bits <= 32)
                 k_scatter_pairs_coded<uint32_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
                         b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
-                        b->d_key_a.as<uint32_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>());
+                        b->d_key_a.as<uint32_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>(),
+                        b->codes_packed ? b->d_codes.as<uint32_t>() : nullptr);
             else
                 k_scatter_pairs_coded<uint64_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
                         b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
-                        b->d_key_a.as<uint64_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>());
+                        b->d_key_a.as<uint64_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>(),
+                        b->codes_packed ? b->d_codes.as<uint32_t>() : nullptr);
         } else if (b->grouped)
             k_scatter_pairs_grouped<<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(),
                                                                       b->d_gid.as<uint16_t>(), b->n_gtable, b->d_prefix.as<int32_t>(), b->d_pair_db.as<int32_t>(),
@@ -1043,18 +1058,19 @@ static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
     g.work_counter = b->d_work_counter.as<unsigned int>();
     const int64_t n_items = b->S * jmax * g.n_slices;
     if (n_items >= (int64_t(1) << 31) - (int64_t(1) << 20)) return fail(SNPM_E_ARG, "snpm_batch_run: %lld work items exceed the 2^31 limit", (long long)n_items);
-    const size_t smem = size_t(g.teams) * g2_team_smem(g.wx, g.chunk);
+    constexpr int ring = 64;                 // rows of a team's gather ring: 3 blocks in flight while one is scored
+    const size_t smem = size_t(g.teams) * g2_team_smem(g.wx, g.chunk, ring);
     if (smem > 226 * 1024) return fail(SNPM_E_ARG, "snpm_batch_run: group chunk %d needs %zu bytes of shared memory", g.chunk, smem);
     SNPM_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned int), st));
     const int grid = int(std::min<int64_t>(db->n_sm, ceil_div64(n_items, g.teams)));
-#define G2_LAUNCH(SK, WXV)                                                                                                      \
-    do {                                                                                                                        \
-        static bool attr_ = false;                                                                                              \
-        if (!attr_) {                                                                                                           \
-            SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<SK, WXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
-            attr_ = true;                                                                                                       \
-        }                                                                                                                       \
-        k_score_grouped2<SK, WXV><<<grid, G2_THREADS, smem, st>>>(g);                                                           \
+#define G2_LAUNCH(SK, WXV)                                                                                                        \
+    do {                                                                                                                          \
+        static bool attr_ = false;                                                                                                \
+        if (!attr_) {                                                                                                             \
+            SNPM_CUDA(cudaFuncSetAttribute(k_score_grouped2<SK, WXV, ring>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+            attr_ = true;                                                                                                         \
+        }                                                                                                                         \
+        k_score_grouped2<SK, WXV, ring><<<grid, G2_THREADS, smem, st>>>(g);                                                       \
     } while (0)
     if (g.wx == G2_WX) {
         if (skip_db_hets) G2_LAUNCH(true, G2_WX); else G2_LAUNCH(false, G2_WX);

@@ -150,6 +150,7 @@ struct snpm_batch {
     int32_t gchunk_req = 320;          // snpm_batch_set_group_chunk: takes effect at the next grouped / coded upload
     // coded mode (snpm_batch_upload_coded): position-order markers + weight codes; grouped on the device (group_sort.cuh)
     bool coded = false;
+    bool codes_packed = false;         // the three codes of a marker in one uint32 (snpm_batch_upload_coded32)
     int32_t n_wtable = 0, code_bits = 0, key_bits = 0;
     int64_t n_sort_tiles = 0;
     snpm::DevBuf d_codes, d_wtable, d_key_a, d_key_b, d_idx_a, d_idx_b, d_pair_db_tmp, d_pair_s_tmp, d_tile_sample, d_tile_first,

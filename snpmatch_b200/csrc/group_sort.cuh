@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
         const int32_t *__restrict__ match_row, int64_t n, const int32_t *__restrict__ tile_off, const uint16_t *__restrict__ codes,
         const double *__restrict__ wtable, int32_t n_table, int32_t code_bits, int32_t *__restrict__ prefix,
         int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s, KeyT *__restrict__ key, int *status,
-        const int64_t *__restrict__ off, int64_t S, unsigned long long *__restrict__ hash, int *__restrict__ overflow) {
+        const int64_t *__restrict__ off, int64_t S, unsigned long long *__restrict__ hash, int *__restrict__ overflow,
+        const uint32_t *__restrict__ codes32) {
     __shared__ int s_warp[33];
     const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
     const int32_t row = i < n ? match_row[i] : -1;
@@ -111,7 +112,13 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
         if (flag) {
             pair_db[p] = row;
             pair_s[p] = int32_t(i);
-            uint32_t cd[3] = {codes[3 * i], codes[3 * i + 2], codes[3 * i + 1]};      // wei columns are (ref, het, alt); classes (ref, alt, het)
+            uint32_t cd[3];                             // wei columns are (ref, het, alt); classes (ref, alt, het)
+            if (codes32 != nullptr) {                   // three 10-bit codes in one word: ref | het << 10 | alt << 20
+                const uint32_t v = codes32[i];
+                cd[0] = v & 1023u; cd[2] = (v >> 10) & 1023u; cd[1] = (v >> 20) & 1023u;
+            } else {
+                cd[0] = codes[3 * i]; cd[2] = codes[3 * i + 1]; cd[1] = codes[3 * i + 2];
+            }
             bool bad = false;
 #pragma unroll
             for (int k = 0; k < 3; ++k)

@@ -69,8 +69,8 @@ struct G2Item {
 __host__ __device__ __forceinline__ size_t g2_stage_bytes(int chunk) {
     return (size_t(chunk) * 4 + size_t(chunk / 16 + 1) * 8 + 15) & ~size_t(15);      // row numbers | block words
 }
-__host__ __device__ __forceinline__ size_t g2_team_smem(int wx, int chunk) {
-    return size_t(GR_RING) * wx * 8 + 2 * g2_stage_bytes(chunk);             // ring | 2 staging buffers
+__host__ __device__ __forceinline__ size_t g2_team_smem(int wx, int chunk, int ring) {
+    return size_t(ring) * wx * 8 + 2 * g2_stage_bytes(chunk);                // ring | 2 staging buffers
 }
 
 // fold the counts of a class counter: F[lane] += w * count[lane]
@@ -120,18 +120,23 @@ __device__ __forceinline__ void counter_values9(const BitCounter<G2_TP> &c, int3
 // (Measured and dropped: pulling the rows of block b + 6 / b + 12 into L2 with prefetch.global.L2 while block b's copies are
 // queued — to have more bytes in flight at the DRAM level than the shared-memory ring holds — made the kernel slower: 0.272 ms
 // without, 0.328 ms at distance 6, 0.354 ms at 12.)
-template <bool SKIP_HETS, int WX>
+// RING: rows of a team's gather ring (a multiple of 16): RING / 16 - 1 blocks are in flight while one is scored.  (Measured:
+// 96 rows instead of 64 changed nothing for called genotypes (0.205 ms) and cost 4-6 % with PL weights and on the 20 000-accession
+// panel; 10 teams in a 384-thread CTA at 168 registers — three warps per scheduler, 224 bytes of spills — ran at 0.350 ms against
+// 0.307 in the same session.)
+template <bool SKIP_HETS, int WX, int RING>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Args a) {
+    constexpr int INFLIGHT = RING / GR_BLOCK;
     extern __shared__ __align__(16) unsigned char g2_smem[];
     __shared__ int s_base[2];                     // first item of the round in staging buffer 0 / 1
     const int wx = WX ? WX : a.wx;
     const int q = threadIdx.x / wx, w = threadIdx.x - q * wx;
     const bool in_team = q < a.teams;
-    const size_t team_bytes = g2_team_smem(wx, a.chunk);
+    const size_t team_bytes = g2_team_smem(wx, a.chunk, RING);
     const size_t stage_bytes = g2_stage_bytes(a.chunk);
     unsigned char *team = g2_smem + size_t(in_team ? q : 0) * team_bytes;
     uint64_t *ring = reinterpret_cast<uint64_t *>(team);
-    unsigned char *stage0 = team + size_t(GR_RING) * wx * 8;
+    unsigned char *stage0 = team + size_t(RING) * wx * 8;
     const int n_items = a.S * a.jmax * a.n_slices;
     // item i -> (slot, slice); slot -> segment j = jmax-1 - slot / S of sample slot % S: longest segments first
     auto decode = [&](int i) {
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         auto issue = [&](int b) {
             if (live) {
                 const int r0 = b * GR_BLOCK + 8 * odd;
-                const uint32_t slot0 = my_ring + uint32_t(r0 % GR_RING) * ring_pitch;
+                const uint32_t slot0 = my_ring + uint32_t(r0 % RING) * ring_pitch;
                 if (b < n_full) {
 #pragma unroll
                     for (int k4 = 0; k4 < GR_BLOCK / 2; k4 += 4) {
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
             cp_async_commit();                    // always: the waits below count groups
         };
 #pragma unroll
-        for (int b = 0; b < GR_INFLIGHT; ++b) issue(b);
+        for (int b = 0; b < INFLIGHT; ++b) issue(b);
 
         double F[32];
 #pragma unroll
@@ -295,11 +300,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         // barrier per step: after it the neighbour's copies of block b have landed too and it has read block b-1, whose slots
         // are refilled next.
         for (int b = 0; b < nb_round; ++b) {
-            cp_async_wait<GR_INFLIGHT - 2>();
+            cp_async_wait<INFLIGHT - 2>();
             __syncwarp();
-            if (b > 0) issue(b + GR_INFLIGHT - 1);
+            if (b > 0) issue(b + INFLIGHT - 1);
             if (b < n_full) {
-                const uint64_t *slot = ring + size_t((b * GR_BLOCK) % GR_RING) * wx + w;
+                const uint64_t *slot = ring + size_t((b * GR_BLOCK) % RING) * wx + w;
                 uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
 #pragma unroll
                 for (int k = 0; k < GR_BLOCK; ++k) {
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 score_block(lo, hi, b);
             } else if (b < n_blocks) {            // ragged last block: rows past the end read as missing everywhere
                 const int r0 = b * GR_BLOCK;
-                const uint64_t *slot = ring + size_t(r0 % GR_RING) * wx + w;
+                const uint64_t *slot = ring + size_t(r0 % RING) * wx + w;
                 uint32_t lo[GR_BLOCK], hi[GR_BLOCK];
 #pragma unroll
                 for (int k = 0; k < GR_BLOCK; ++k) {

@@ -273,3 +273,36 @@ def test_makedb_host_side(tmp_path):
     assert open(str(tmp_path / "db2.csv")).read() == "Chromosome,Position,6909,8236,9999\nChr1,10,0,1,2\nChr1,25,2,-1,-1\nChr2,7,1,0,-1\n"
     assert json.load(open(str(tmp_path / "db2.json"))) == {"ref_chrs": ["Chr1", "Chr2"], "ref_chrlen": [30427671, 19698289]}
     assert makedb.get_contigs(["##contig=<ID=1,length=5>", "##INFO=<ID=DP>"]) == {"ref_chrs": ["1"], "ref_chrlen": [5]}
+
+
+def test_coded_samples_host_side():
+    """lib.code_markers / CodedSamples.pack / ParseInputs.coded_weights: what crosses the bus reproduces the inputs bit for bit."""
+    from snpmatch_b200 import lib, synth
+    from snpmatch_b200.core import parsers
+    pos, regions = synth.panel_positions(20000)
+    s = synth.make_sample_fast(pos, regions, 50, 3, n_db=2000, n_extra=200, seed=5)
+    n = len(s["pos"])
+    cs = lib.code_markers(np.array([0, n]), s["chr_ix"], s["pos"], s["wei"])
+    assert cs is not None and cs.codes.shape == (n, 3) and cs.codes.dtype == np.uint16
+    assert np.array_equal(cs.wtable[cs.codes.astype(np.int64)].view(np.uint64), s["wei"].view(np.uint64))
+    assert np.array_equal(cs.chrom_pos >> np.uint32(27), s["chr_ix"].astype(np.uint32))
+    assert np.array_equal(cs.chrom_pos & np.uint32((1 << 27) - 1), s["pos"].astype(np.uint32))
+    assert cs.codes32 is not None and cs.h2d_bytes < 8 * n + 8 * len(cs.wtable) + 64
+    c32 = cs.codes32
+    assert np.array_equal(c32 & 1023, cs.codes[:, 0]) and np.array_equal((c32 >> 10) & 1023, cs.codes[:, 1]) and np.array_equal(c32 >> 20, cs.codes[:, 2])
+    # integer PLs as ready-made codes
+    table = synth.pl_table(int(s["pl"].max()))
+    assert np.array_equal(table[s["pl"]].view(np.uint64), s["wei"].view(np.uint64))
+    cs2 = lib.code_markers(np.array([0, n]), s["chr_ix"], s["pos"], codes=s["pl"].astype(np.uint16), wtable=table)
+    assert np.array_equal(cs2.wtable[cs2.codes.astype(np.int64)], s["wei"])
+    # markers outside the panel's chromosomes, ids / positions that do not fit one word, weights that cannot be coded
+    assert int(lib.pack_chrom_pos(np.array([-1, 2]), np.array([5, 6]))[0] >> 27) == 31
+    assert lib.pack_chrom_pos(np.array([31]), np.array([5])) is None and lib.pack_chrom_pos(np.array([0]), np.array([1 << 27])) is None
+    assert lib.code_markers(np.array([0, 1]), np.array([0]), np.array([1]), np.array([[-0.5, 0.0, 1.0]])) is None
+    big = lib.CodedSamples(np.array([0, 1]), np.zeros(1, np.uint32), np.zeros((1, 3), np.uint16), np.arange(2000.0)).pack()
+    assert big.codes32 is None                                   # more than 1024 weight values: three uint16 per marker
+    inp = parsers.ParseInputs("")
+    inp.load_snp_info(np.array(["Chr1"] * n), s["pos"], synth._gt_strings(s["code"]), s["wei"], s["dp"])
+    codes, tab = inp.coded_weights()
+    assert np.array_equal(tab[codes.astype(np.int64)].view(np.uint64), s["wei"].view(np.uint64))
+    assert inp.coded_weights()[0] is codes                       # cached
