@@ -544,6 +544,21 @@ def roofline(peak, algo_bytes, kernel_ms, kernel, extra=None):
     return d
 
 
+def measured_traffic(args, world, n_samples):
+    """dram bytes of one launch of the dominant kernel from the committed ncu capture; null for any other workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+            t = json.load(fh)
+    except Exception:
+        return {"traffic": None, "traffic_source": "no capture under profiles/"}
+    here = {"n_gpus": world, "panel_rows": args.rows, "accessions": args.accessions, "samples_per_step": n_samples,
+            "markers": args.markers, "group_chunk": args.group_chunk}
+    if here != t["workload"]:
+        return {"traffic": None, "traffic_source": "%s was captured on another workload (%s)" % (t["source"], json.dumps(t["workload"]))}
+    return {"traffic": int(t["dram_bytes_read"] + t["dram_bytes_write"]), "traffic_unit": "bytes per launch",
+            "traffic_source": t["source"], "traffic_note": t["note"]}
+
+
 def run_b200_arm(args):
     import torch
     import __graft_entry__ as ge
@@ -611,7 +626,7 @@ def run_b200_arm(args):
                     "samples_rescored_in_reference_order": h["rescored"], "flagged_not_rescored_multi_gpu": h["flagged_e2e"]},
             "gpu_launches": int(h["launches"] * args.steps),
             "roofline": roofline(peak, algo_bytes, k_ms, "k_score_grouped2", {
-                "traffic": None, "traffic_source": "profiles/r2_score_grouped2_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload at N=1)",
+                **measured_traffic(args, world, S),
                 "peak_source": peak_source, "rows_gathered_per_launch": h["local_rows"]}),
             "stages_ms": h["stages_ms"], "distinct_weight_values": h["n_weights"], "group_chunk_rows": int(args.group_chunk),
             "headline_kernel": "k_score_grouped2 (counting kernel, device-grouped pairs)",

@@ -26,10 +26,13 @@ def main():
     ap.add_argument("--no-old", action="store_true")
     ap.add_argument("--hard", action="store_true")
     ap.add_argument("--shard-of", type=int, default=1)
+    ap.add_argument("--lib", default="", help="another build of the library (A/B runs in one session)")
     args = ap.parse_args()
     import __graft_entry__ as ge
     ge.build()
     from snpmatch_b200 import lib, synth
+    if args.lib:
+        lib.LIB_PATH = os.path.abspath(args.lib)
     from snpmatch_b200.core import snp_genotype
     import bench
     positions, regions = synth.panel_positions(args.rows)

@@ -73,6 +73,36 @@ __host__ __device__ __forceinline__ size_t g2_team_smem(int wx, int chunk, int r
     return size_t(ring) * wx * 8 + 2 * g2_stage_bytes(chunk);                // ring | 2 staging buffers
 }
 
+// the four bytes of a word as doubles (I2F.F64.U8 takes a byte of a register; written as PTX because the compiler's own
+// lowering of (t >> 8j) & 0xff spends a shift and a mask per byte before the conversion)
+__device__ __forceinline__ void bytes_to_f64(uint32_t t, double &d0, double &d1, double &d2, double &d3) {
+    asm("{\n\t.reg .b8 b0, b1, b2, b3;\n\tmov.b32 {b0, b1, b2, b3}, %4;\n\tcvt.rn.f64.u8 %0, b0;\n\tcvt.rn.f64.u8 %1, b1;\n\t"
+        "cvt.rn.f64.u8 %2, b2;\n\tcvt.rn.f64.u8 %3, b3;\n\t}"
+        : "=d"(d0), "=d"(d1), "=d"(d2), "=d"(d3)
+        : "r"(t));
+}
+
+// row k of a block if bit k of `rm` is set, else 0: one predicate per row (R2P) and a select, instead of shift, shift, and
+template <int K>
+__device__ __forceinline__ uint32_t row_if_bit(uint32_t pl, uint32_t rm) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\tselp.b32 %0, %1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(pl), "r"(rm), "n"(1u << K));
+    return r;
+}
+template <int K>
+struct MaskRows {
+    static __device__ __forceinline__ void go(uint32_t (&m)[GR_BLOCK], const uint32_t (&pl)[GR_BLOCK], uint32_t rm) {
+        m[K] = row_if_bit<K>(pl[K], rm);
+        MaskRows<K - 1>::go(m, pl, rm);
+    }
+};
+template <>
+struct MaskRows<-1> {
+    static __device__ __forceinline__ void go(uint32_t (&)[GR_BLOCK], const uint32_t (&)[GR_BLOCK], uint32_t) {}
+};
+
 // fold the counts of a class counter: F[lane] += w * count[lane]
 __device__ __forceinline__ void fold_counts9(const BitCounter<G2_CP> &c, double w, double (&F)[32]) {
     uint32_t t[8];
@@ -82,11 +112,12 @@ __device__ __forceinline__ void fold_counts9(const BitCounter<G2_CP> &c, double 
     if (c.p[8] == 0u) {                           // fewer than 256 rows since the last read-out: the common case
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int cnt = int((t[i] >> (8 * j)) & 0xffu);
-                F[8 * j + i] = fma(w, double(cnt), F[8 * j + i]);
-            }
+            double d0, d1, d2, d3;
+            bytes_to_f64(t[i], d0, d1, d2, d3);
+            F[i] = fma(w, d0, F[i]);
+            F[8 + i] = fma(w, d1, F[8 + i]);
+            F[16 + i] = fma(w, d2, F[16 + i]);
+            F[24 + i] = fma(w, d3, F[24 + i]);
         }
     } else {
 #pragma unroll
@@ -256,7 +287,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         // one class: add the block's planes; where the class weight changes inside the block (bit k of `mask`: row k starts a new
         // weight), add the rows piece by piece and read the counter out in between
         auto add_class = [&](BitCounter<G2_CP> &c, double &wt, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, unsigned long long chg) {
-            if (mask == 0u) {
+            // The two teams of a warp take the same path: a team without a change in this block joins the other team's first
+            // piece (its own piece is the whole block) instead of running the plain add first while the other team waits.
+            if (__all_sync(__activemask(), mask == 0u)) {
                 c.add16(pl);
                 return;
             }
@@ -266,8 +299,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 if (k1 > k0) {
                     const uint32_t rm = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
                     uint32_t m[GR_BLOCK];
-#pragma unroll
-                    for (int k = 0; k < GR_BLOCK; ++k) m[k] = pl[k] & uint32_t(int32_t(rm << (31 - k)) >> 31);
+                    MaskRows<GR_BLOCK - 1>::go(m, pl, rm);
                     c.add16(m);
                 }
                 if (k1 >= GR_BLOCK) break;
