@@ -340,6 +340,21 @@ int snpm_cross_window_genotypes(int device, const int64_t *par_idx, const int64_
 int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, const uint8_t *codes, int64_t S, int skip_db_hets,
                             int64_t *score, int64_t *ninfo, double *prob, double *L, double *LR, float *ms_gemm);
 
+/* The same as an object, for callers that score batch after batch on one marker panel: snpm_panel_create expands the panel-side
+ * GEMM operand once (K markers x A accessions one-hot, 4 bytes per cell, resident), snpm_panel_score re-uses it and the
+ * panel's scratch buffers (nothing is allocated after the first call of a given S).  codes: packed = 0 -> uint8 [S,K] as
+ * above; packed = 1 -> 2 bits per marker, four markers per byte (marker k in bits 2(k&3), 2(k&3)+1 of byte k >> 2 of the
+ * sample's row; rows are ceil(K/4) bytes; spare bits of the last byte are ignored), a quarter of the bytes over PCIe.
+ * score / ninfo int32 [S,A]: with called genotypes the score is the number of matches (snpmatch.py:96 truncates nothing), so
+ * the int32 accumulators are returned as they are; prob/L/LR f64 [S,A] optional (all three NULL skips the likelihood
+ * epilogue).  Pass page-locked host buffers for full PCIe speed.  ms (optional) float[3]: device time of H2D + sample
+ * operand expansion, of the GEMM, and of the whole call including the copies back. */
+typedef struct snpm_panel snpm_panel;
+int snpm_panel_create(snpm_db *db, const int64_t *panel_rows, int64_t K, int skip_db_hets, snpm_panel **out);
+int snpm_panel_score(snpm_panel *p, const uint8_t *codes, int packed, int64_t S, int32_t *score, int32_t *ninfo, double *prob, double *L,
+                     double *LR, float *ms);
+void snpm_panel_destroy(snpm_panel *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,7 @@
 // C ABI of libsnpmatch_b200 (include/snpmatch_b200.h): handle lifecycle, uploads, kernel launches.
 #include "common.cuh"
+#include <memory>
+#include <new>
 #include "pack.cuh"
 #include "join.cuh"
 #include "score.cuh"
@@ -1758,83 +1760,156 @@ int snpm_cross_window_genotypes(int device, const int64_t *par_idx, const int64_
 }
 
 // ---- A9 ------------------------------------------------------------------------------------------------
+// A shared marker panel: the panel-side GEMM operand is expanded once (snpm_panel_create) and every snpm_panel_score call
+// re-uses it and the panel's scratch buffers (no allocation after the first call of a given batch size).
+struct snpm_panel {
+    snpm_db *db = nullptr;
+    int64_t K = 0, Kpad = 0;
+    int32_t n_kb = 0, n_blocks = 0, ld_out = 0;
+    DevBuf d_rows, d_bt, d_codes, d_at, d_os, d_on, d_red, d_m, d_n64, d_p, d_l, d_lr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    void release() {
+        for (DevBuf *d : {&d_rows, &d_bt, &d_codes, &d_at, &d_os, &d_on, &d_red, &d_m, &d_n64, &d_p, &d_l, &d_lr}) d->release();
+        for (cudaEvent_t &e : ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+    }
+};
+
+int snpm_panel_create(snpm_db *db, const int64_t *panel_rows, int64_t K, int skip_db_hets, snpm_panel **out) {
+    if (!db || !out || K < 0 || (K > 0 && !panel_rows)) return fail(SNPM_E_ARG, "snpm_panel_create: bad arguments");
+    if (K >= (int64_t(1) << 29)) return fail(SNPM_E_ARG, "snpm_panel_create: int32 accumulators hold at most 2^29 markers");
+    *out = nullptr;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    std::unique_ptr<snpm_panel, void (*)(snpm_panel *)> p(new (std::nothrow) snpm_panel, [](snpm_panel *q) { q->release(); delete q; });
+    if (!p) return fail(SNPM_E_NOMEM, "snpm_panel_create: out of host memory");
+    p->db = db;
+    p->K = K;
+    p->Kpad = std::max<int64_t>(OG_ROWS, ceil_div64(K, OG_ROWS) * OG_ROWS);
+    p->n_kb = int32_t(p->Kpad / OG_ROWS);
+    p->ld_out = int32_t(ceil_div64(db->n_acc, OG_BN) * OG_BN);
+    p->n_blocks = p->ld_out / OG_BN;
+    std::vector<int32_t> rows(size_t(p->Kpad), -1);
+    for (int64_t k = 0; k < K; ++k) {
+        const int64_t r = panel_rows[k] - db->row0_global;
+        if (r < 0 || r >= db->n_rows) return fail(SNPM_E_ARG, "snpm_panel_create: panel row %lld is not on this device", (long long)panel_rows[k]);
+        rows[size_t(k)] = int32_t(r);
+    }
+    SNPM_TRY(p->d_rows.ensure(size_t(p->Kpad) * 4));
+    SNPM_TRY(p->d_bt.ensure(size_t(p->n_blocks) * p->n_kb * OG_B_TILE));
+    for (cudaEvent_t &e : p->ev) SNPM_CUDA(cudaEventCreate(&e));
+    SNPM_CUDA(cudaMemcpyAsync(p->d_rows.p, rows.data(), size_t(p->Kpad) * 4, cudaMemcpyHostToDevice, st));
+    k_onehot_expand_panel<<<dim3(p->n_kb, p->n_blocks), 256, 0, st>>>(db->d_packed, db->stride, p->d_rows.as<int32_t>(), int32_t(p->Kpad),
+                                                                      skip_db_hets ? 1 : 0, p->d_bt.as<unsigned char>());
+    SNPM_KERNEL_CHECK();
+    SNPM_CUDA(cudaStreamSynchronize(st));                        // `rows` leaves scope
+    *out = p.release();
+    return SNPM_OK;
+}
+
+void snpm_panel_destroy(snpm_panel *p) {
+    if (!p) return;
+    cudaSetDevice(p->db->device);
+    p->release();
+    delete p;
+}
+
+int snpm_panel_score(snpm_panel *p, const uint8_t *codes, int packed, int64_t S, int32_t *score, int32_t *ninfo, double *prob, double *L,
+                     double *LR, float *ms) {
+    if (!p || S < 1 || S > (1 << 22) || (p->K > 0 && !codes) || !score || !ninfo) return fail(SNPM_E_ARG, "snpm_panel_score: bad arguments");
+    snpm_db *db = p->db;
+    SNPM_CUDA(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const int64_t K = p->K, Kpad = p->Kpad;
+    const int32_t A = db->n_acc, ld_out = p->ld_out;
+    const int m_blocks = int(ceil_div64(S, 64));
+    const bool like = prob || L || LR;
+    const int64_t dev_pitch = packed ? Kpad / 4 : Kpad, host_pitch = packed ? ceil_div64(K, 4) : K;
+    SNPM_TRY(p->d_codes.ensure(size_t(S) * dev_pitch));
+    SNPM_TRY(p->d_at.ensure(size_t(m_blocks) * p->n_kb * OG_A_TILE));
+    SNPM_TRY(p->d_os.ensure(size_t(S) * ld_out * 4));
+    SNPM_TRY(p->d_on.ensure(size_t(S) * ld_out * 4));
+    if (like) {
+        SNPM_TRY(p->d_red.ensure(size_t(S) * (2 * size_t(A) + 2) * 8));
+        SNPM_TRY(p->d_m.ensure(size_t(S) * A * 8));
+        SNPM_TRY(p->d_n64.ensure(size_t(S) * A * 8));
+        SNPM_TRY(p->d_p.ensure(size_t(S) * A * 8));
+        SNPM_TRY(p->d_l.ensure(size_t(S) * A * 8));
+        SNPM_TRY(p->d_lr.ensure(size_t(S) * A * 8));
+    }
+    SNPM_CUDA(cudaEventRecord(p->ev[0], st));
+    // markers past K (up to the k-block boundary) are absent: code 3 everywhere, then the caller's codes on top
+    if (host_pitch != dev_pitch || K == 0) SNPM_CUDA(cudaMemsetAsync(p->d_codes.p, packed ? 0xFF : 3, size_t(S) * dev_pitch, st));
+    if (K > 0) SNPM_CUDA(cudaMemcpy2DAsync(p->d_codes.p, size_t(dev_pitch), codes, size_t(host_pitch), size_t(host_pitch), size_t(S), cudaMemcpyHostToDevice, st));
+    if (packed && (K & 3) && K > 0) {
+        // the last byte of a row holds 1-3 markers: whatever the caller left in its spare bits must read as absent
+        k_onehot_mask_tail<<<int(ceil_div64(S, 256)), 256, 0, st>>>(p->d_codes.as<uint8_t>(), S, dev_pitch, K);
+    }
+    if (packed) k_onehot_expand_samples<true><<<dim3(p->n_kb, m_blocks), 128, 0, st>>>(p->d_codes.as<uint8_t>(), int32_t(S), int32_t(Kpad), dev_pitch, p->d_at.as<unsigned char>());
+    else k_onehot_expand_samples<false><<<dim3(p->n_kb, m_blocks), 128, 0, st>>>(p->d_codes.as<uint8_t>(), int32_t(S), int32_t(Kpad), dev_pitch, p->d_at.as<unsigned char>());
+    SNPM_KERNEL_CHECK();
+    OneHotGemmArgs g = {};
+    g.a_tiled = p->d_at.as<unsigned char>(); g.b_tiled = p->d_bt.as<unsigned char>(); g.n_kb = p->n_kb; g.m_blocks = m_blocks; g.n_blocks = p->n_blocks;
+    g.S = int32_t(S); g.out_score = p->d_os.as<int32_t>(); g.out_ninfo = p->d_on.as<int32_t>(); g.ld_out = ld_out;
+    const size_t smem = size_t(OG_STAGES) * (OG_A_TILE + OG_B_TILE) + 1024;
+    static bool og_attr = false;
+    if (!og_attr) { SNPM_CUDA(cudaFuncSetAttribute(k_onehot_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); og_attr = true; }
+    dim3 grid((unsigned)std::min(m_blocks * p->n_blocks, db->n_sm));      // persistent: one CTA per SM walks the tiles
+    SNPM_CUDA(cudaEventRecord(p->ev[1], st));
+    k_onehot_gemm<<<grid, OG_THREADS, smem, st>>>(g);
+    SNPM_KERNEL_CHECK();
+    SNPM_CUDA(cudaEventRecord(p->ev[2], st));
+    if (like) {
+        dim3 tgrid((A + 255) / 256, unsigned(S));
+        k_onehot_totals<<<tgrid, 256, 0, st>>>(g.out_score, g.out_ninfo, ld_out, A, int32_t(K), p->d_red.as<double>());
+        k_epilogue<<<unsigned(S), 1024, 0, st>>>(p->d_red.as<double>(), 2 * int64_t(A) + 2, A, 1, 0, 0.0, p->d_m.as<int64_t>(), p->d_n64.as<int64_t>(),
+                                                 p->d_p.as<double>(), p->d_l.as<double>(), p->d_lr.as<double>());
+        SNPM_KERNEL_CHECK();
+    }
+    // with one-hot weights the score IS the number of matches: the int32 accumulators go back as they are (pitched copy)
+    SNPM_CUDA(cudaMemcpy2DAsync(score, size_t(A) * 4, p->d_os.p, size_t(ld_out) * 4, size_t(A) * 4, size_t(S), cudaMemcpyDeviceToHost, st));
+    SNPM_CUDA(cudaMemcpy2DAsync(ninfo, size_t(A) * 4, p->d_on.p, size_t(ld_out) * 4, size_t(A) * 4, size_t(S), cudaMemcpyDeviceToHost, st));
+    if (prob) SNPM_CUDA(cudaMemcpyAsync(prob, p->d_p.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    if (L) SNPM_CUDA(cudaMemcpyAsync(L, p->d_l.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    if (LR) SNPM_CUDA(cudaMemcpyAsync(LR, p->d_lr.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
+    SNPM_CUDA(cudaEventRecord(p->ev[3], st));
+    SNPM_CUDA(cudaStreamSynchronize(st));
+    if (ms) {
+        ms[0] = ms[1] = ms[2] = 0.f;
+        cudaEventElapsedTime(&ms[0], p->ev[0], p->ev[1]);      // H2D + operand expansion
+        cudaEventElapsedTime(&ms[1], p->ev[1], p->ev[2]);      // GEMM
+        cudaEventElapsedTime(&ms[2], p->ev[0], p->ev[3]);      // everything on the device, copies included
+    }
+    return SNPM_OK;
+}
+
+// one-shot form: panel operand, scoring, int64 results
 int snpm_score_shared_panel(snpm_db *db, const int64_t *panel_rows, int64_t K, const uint8_t *codes, int64_t S, int skip_db_hets,
                             int64_t *score, int64_t *ninfo, double *prob, double *L, double *LR, float *ms_gemm) {
     if (!db || K < 0 || S < 1 || S > (1 << 22) || (K > 0 && (!panel_rows || !codes)) || !score || !ninfo)
         return fail(SNPM_E_ARG, "snpm_score_shared_panel: bad arguments");
-    if (K >= (int64_t(1) << 29)) return fail(SNPM_E_ARG, "snpm_score_shared_panel: int32 accumulators hold at most 2^29 markers");
-    SNPM_CUDA(cudaSetDevice(db->device));
-    cudaStream_t st = db->stream;
-    const int64_t Kpad = std::max<int64_t>(OG_ROWS, ceil_div64(K, OG_ROWS) * OG_ROWS);
-    const int32_t A = db->n_acc, ld_out = int32_t(ceil_div64(A, OG_BN) * OG_BN);
-    std::vector<int32_t> rows(size_t(Kpad), -1);
-    for (int64_t k = 0; k < K; ++k) {
-        const int64_t r = panel_rows[k] - db->row0_global;
-        if (r < 0 || r >= db->n_rows) return fail(SNPM_E_ARG, "snpm_score_shared_panel: panel row %lld is not on this device", (long long)panel_rows[k]);
-        rows[size_t(k)] = int32_t(r);
+    snpm_panel *p = nullptr;
+    SNPM_TRY(snpm_panel_create(db, panel_rows, K, skip_db_hets, &p));
+    const size_t SA = size_t(S) * size_t(db->n_acc);
+    std::vector<int32_t> s32, n32;
+    try {
+        s32.resize(SA);
+        n32.resize(SA);
+    } catch (const std::bad_alloc &) {
+        snpm_panel_destroy(p);
+        return fail(SNPM_E_NOMEM, "snpm_score_shared_panel: out of host memory");
     }
-    DevBuf d_rows, d_codes, d_os, d_on, d_red, d_m, d_n64, d_p, d_l, d_lr, d_at, d_bt;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    int rc = SNPM_OK;
-    auto cleanup = [&]() {
-        for (DevBuf *d : {&d_rows, &d_codes, &d_os, &d_on, &d_red, &d_m, &d_n64, &d_p, &d_l, &d_lr, &d_at, &d_bt}) d->release();
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-    };
-#define SP_TRY(x) do { rc = (x); if (rc != SNPM_OK) { cleanup(); return rc; } } while (0)
-#define SP_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(SNPM_E_CUDA, "snpm_score_shared_panel: %s -> %s", #x, cudaGetErrorString(e_)); } } while (0)
-    const int n_kb = int(Kpad / OG_ROWS);
-    const int m_blocks = int(ceil_div64(S, 64)), n_blocks = ld_out / OG_BN;
-    SP_TRY(d_rows.ensure(size_t(Kpad) * 4));
-    SP_TRY(d_codes.ensure(size_t(S) * Kpad));
-    SP_TRY(d_at.ensure(size_t(m_blocks) * n_kb * OG_A_TILE));
-    SP_TRY(d_bt.ensure(size_t(n_blocks) * n_kb * OG_B_TILE));
-    SP_TRY(d_os.ensure(size_t(S) * ld_out * 4));
-    SP_TRY(d_on.ensure(size_t(S) * ld_out * 4));
-    SP_TRY(d_red.ensure(size_t(S) * (2 * size_t(A) + 2) * 8));
-    SP_TRY(d_m.ensure(size_t(S) * A * 8));
-    SP_TRY(d_n64.ensure(size_t(S) * A * 8));
-    SP_TRY(d_p.ensure(size_t(S) * A * 8));
-    SP_TRY(d_l.ensure(size_t(S) * A * 8));
-    SP_TRY(d_lr.ensure(size_t(S) * A * 8));
-    SP_CUDA(cudaEventCreate(&e0));
-    SP_CUDA(cudaEventCreate(&e1));
-    SP_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), size_t(Kpad) * 4, cudaMemcpyHostToDevice, st));
-    SP_CUDA(cudaMemsetAsync(d_codes.p, 3, size_t(S) * Kpad, st));                 // padding markers are absent
-    if (K > 0) SP_CUDA(cudaMemcpy2DAsync(d_codes.p, size_t(Kpad), codes, size_t(K), size_t(K), size_t(S), cudaMemcpyHostToDevice, st));
-    // one-hot operands, tile by tile in their shared-memory image
-    k_onehot_expand_samples<<<dim3(n_kb, m_blocks), 128, 0, st>>>(d_codes.as<uint8_t>(), int32_t(S), int32_t(Kpad), d_at.as<unsigned char>());
-    SP_CUDA(cudaGetLastError());
-    k_onehot_expand_panel<<<dim3(n_kb, n_blocks), 256, 0, st>>>(db->d_packed, db->stride, d_rows.as<int32_t>(), int32_t(Kpad), skip_db_hets ? 1 : 0,
-                                                                d_bt.as<unsigned char>());
-    SP_CUDA(cudaGetLastError());
-    OneHotGemmArgs g = {};
-    g.a_tiled = d_at.as<unsigned char>(); g.b_tiled = d_bt.as<unsigned char>(); g.n_kb = n_kb; g.m_blocks = m_blocks; g.n_blocks = n_blocks; g.S = int32_t(S);
-    g.out_score = d_os.as<int32_t>(); g.out_ninfo = d_on.as<int32_t>(); g.ld_out = ld_out;
-    const size_t smem = size_t(OG_STAGES) * (OG_A_TILE + OG_B_TILE) + 1024;
-    static bool og_attr = false;
-    if (!og_attr) { SP_CUDA(cudaFuncSetAttribute(k_onehot_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); og_attr = true; }
-    dim3 grid((unsigned)std::min(m_blocks * n_blocks, db->n_sm));      // persistent: one CTA per SM walks the tiles
-    SP_CUDA(cudaEventRecord(e0, st));
-    k_onehot_gemm<<<grid, OG_THREADS, smem, st>>>(g);
-    SP_CUDA(cudaGetLastError());
-    SP_CUDA(cudaEventRecord(e1, st));
-    dim3 tgrid((A + 255) / 256, unsigned(S));
-    k_onehot_totals<<<tgrid, 256, 0, st>>>(g.out_score, g.out_ninfo, ld_out, A, int32_t(K), d_red.as<double>());
-    SP_CUDA(cudaGetLastError());
-    k_epilogue<<<unsigned(S), 1024, 0, st>>>(d_red.as<double>(), 2 * int64_t(A) + 2, A, 1, 0, 0.0, d_m.as<int64_t>(), d_n64.as<int64_t>(), d_p.as<double>(),
-                                             d_l.as<double>(), d_lr.as<double>());
-    SP_CUDA(cudaGetLastError());
-    SP_CUDA(cudaMemcpyAsync(score, d_m.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
-    SP_CUDA(cudaMemcpyAsync(ninfo, d_n64.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
-    if (prob) SP_CUDA(cudaMemcpyAsync(prob, d_p.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
-    if (L) SP_CUDA(cudaMemcpyAsync(L, d_l.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
-    if (LR) SP_CUDA(cudaMemcpyAsync(LR, d_lr.p, size_t(S) * A * 8, cudaMemcpyDeviceToHost, st));
-    SP_CUDA(cudaStreamSynchronize(st));
-    if (ms_gemm) { *ms_gemm = 0.f; cudaEventElapsedTime(ms_gemm, e0, e1); }
-    cleanup();
-#undef SP_TRY
-#undef SP_CUDA
+    float ms[3] = {0.f, 0.f, 0.f};
+    const int rc = snpm_panel_score(p, codes, 0, S, s32.data(), n32.data(), prob, L, LR, ms);
+    snpm_panel_destroy(p);
+    if (rc != SNPM_OK) return rc;
+    for (size_t i = 0; i < SA; ++i) {
+        score[i] = s32[i];
+        ninfo[i] = n32[i];
+    }
+    if (ms_gemm) *ms_gemm = ms[1];
     return SNPM_OK;
 }
 

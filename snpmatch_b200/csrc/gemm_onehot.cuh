@@ -37,16 +37,31 @@ __host__ __device__ __forceinline__ uint32_t og_tile_offset(int row, int chunk, 
 
 // A operand: tile (m_blk, kb) = 64 samples x 32 markers; rows 0-63 one-hot of the sample's call (score), rows 64-127 ones in
 // every class slot when the sample has the marker (ninfo).  K slot = 4 * marker + class; slot 3 stays zero.
-__global__ void __launch_bounds__(128) k_onehot_expand_samples(const uint8_t *__restrict__ codes, int32_t S, int32_t Kpad,
+// PACKED: codes are 2 bits per marker, four markers per byte (marker k in bits 2(k&3)..2(k&3)+1 of byte k >> 2), `pitch` bytes
+// per sample; else one byte per marker.
+template <bool PACKED>
+__global__ void __launch_bounds__(128) k_onehot_expand_samples(const uint8_t *__restrict__ codes, int32_t S, int32_t Kpad, int64_t pitch,
                                                                unsigned char *__restrict__ a_tiled) {
     const int n_kb = Kpad / OG_ROWS;
     const int kb = blockIdx.x, m_blk = blockIdx.y, t = threadIdx.x;
     const int sample = m_blk * 64 + (t & 63);
     const bool ninfo_row = t >= 64;
     unsigned char *tile = a_tiled + (size_t(m_blk) * n_kb + kb) * OG_A_TILE;
+    uint32_t pk[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};              // PACKED: the 32 markers of this k-block (8 bytes)
+    if (PACKED && sample < S) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(codes + size_t(sample) * pitch + size_t(kb) * (OG_ROWS / 4));
+        pk[0] = v.x;
+        pk[1] = v.y;
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const uint32_t cw = sample < S ? *reinterpret_cast<const uint32_t *>(codes + size_t(sample) * Kpad + kb * OG_ROWS + 4 * c) : 0x03030303u;
+        uint32_t cw;
+        if (PACKED) {
+            const uint32_t b = (pk[c >> 2] >> (8 * (c & 3))) & 0xFFu;
+            cw = (b & 3u) | ((b >> 2 & 3u) << 8) | ((b >> 4 & 3u) << 16) | ((b >> 6) << 24);
+        } else {
+            cw = sample < S ? *reinterpret_cast<const uint32_t *>(codes + size_t(sample) * pitch + kb * OG_ROWS + 4 * c) : 0x03030303u;
+        }
         uint4 v;
         uint32_t *pv = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
@@ -230,6 +245,12 @@ __global__ void __launch_bounds__(OG_THREADS, 1) k_onehot_gemm(const OneHotGemmA
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// packed codes, K not a multiple of 4: the spare bit pairs of a row's last byte read as absent (code 3)
+__global__ void k_onehot_mask_tail(uint8_t *__restrict__ codes, int64_t S, int64_t pitch, int64_t K) {
+    const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s < S) codes[s * pitch + (K >> 2)] |= uint8_t(0xFFu << (2 * (K & 3)));
 }
 
 // int32 GEMM outputs -> the f64 reduce rows the likelihood epilogue reads (score | ninfo | markers | 0)

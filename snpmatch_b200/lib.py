@@ -241,6 +241,9 @@ SIGNATURES = {
     "snpm_batch_fetch_window_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "snpm_batch_f1_pairs": (C.c_int, [_p, _p, _i32, _p, _p]),
     "snpm_score_shared_panel": (C.c_int, [_p, _p, _i64, _p, _i64, C.c_int, _p, _p, _p, _p, _p, _p]),
+    "snpm_panel_create": (C.c_int, [_p, _p, _i64, C.c_int, _p]),
+    "snpm_panel_score": (C.c_int, [_p, _p, C.c_int, _i64, _p, _p, _p, _p, _p, _p]),
+    "snpm_panel_destroy": (None, [_p]),
 }
 
 
@@ -386,6 +389,10 @@ class Database(object):
         r["gemm_ms"] = ms.value
         return r
 
+    def shared_panel(self, panel_rows, skip_db_hets=False):
+        """SharedPanel on the markers `panel_rows` (global rows): score batch after batch against it."""
+        return SharedPanel(self, panel_rows, skip_db_hets)
+
     def set_stream(self, cuda_stream):
         check(load().snpm_db_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
@@ -417,6 +424,70 @@ class Database(object):
         m = C.c_int64(0)
         check(load().snpm_intersect(self._h, ptr(s_chrom_id), ptr(s_pos), n, algo, ptr(db_idx), ptr(s_idx), C.byref(m)))
         return db_idx[:m.value].copy(), s_idx[:m.value].copy()
+
+
+def pack_codes2(codes):
+    """uint8 codes [S,K] (0 ref, 1 alt, 2 het, 3 absent) -> 2-bit packed rows uint8 [S, ceil(K/4)] (marker k in bits 2(k&3) of
+    byte k >> 2; the spare bits of the last byte read as absent)."""
+    codes = np.asarray(codes, dtype=np.uint8)
+    S, K = codes.shape
+    pad = (-K) % 4
+    if pad:
+        codes = np.concatenate([codes, np.full((S, pad), 3, np.uint8)], axis=1)
+    c = (codes & 3).reshape(S, -1, 4)
+    return np.ascontiguousarray(c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6))
+
+
+class SharedPanel(object):
+    """A9 as an object: the panel-side tensor-core operand of K shared markers is expanded once, every score() call re-uses it
+    and the panel's device scratch (snpm_panel_*)."""
+
+    def __init__(self, db, panel_rows, skip_db_hets=False):
+        self.db = db
+        self.panel_rows = as_c(panel_rows, np.int64)
+        self.K = int(len(self.panel_rows))
+        h = C.c_void_p()
+        check(load().snpm_panel_create(db._h, ptr(self.panel_rows), self.K, int(bool(skip_db_hets)), C.byref(h)))
+        self._h = h
+        db._batches.add(self)                      # closed before the database
+
+    def score(self, codes, packed=False, likelihoods=False, out=None):
+        """codes: uint8 [S,K], or with packed=True the 2-bit rows of pack_codes2 ([S, ceil(K/4)]).  out: optional dict of
+        preallocated (page-locked) arrays matches/ninfo int32 [S,A] (and prob/L/LR f64 when likelihoods).
+        Returns dict(matches, ninfo[, prob, L, LR], expand_ms, gemm_ms, device_ms)."""
+        codes = as_c(codes, np.uint8)
+        S = int(codes.shape[0])
+        assert codes.ndim == 2 and codes.shape[1] == ((self.K + 3) // 4 if packed else self.K)
+        A = self.db.n_acc
+        r = dict(out) if out is not None else {}
+        for k in ("matches", "ninfo"):
+            if k not in r:
+                r[k] = np.empty((S, A), np.int32)
+            assert r[k].dtype == np.int32 and r[k].shape == (S, A) and r[k].flags.c_contiguous
+        if likelihoods:
+            for k in ("prob", "L", "LR"):
+                if k not in r:
+                    r[k] = np.empty((S, A), np.float64)
+                assert r[k].dtype == np.float64 and r[k].shape == (S, A) and r[k].flags.c_contiguous
+        ms = (C.c_float * 3)()
+        check(load().snpm_panel_score(self._h, ptr(codes), int(bool(packed)), S, ptr(r["matches"]), ptr(r["ninfo"]),
+                                      ptr(r.get("prob")) if likelihoods else None, ptr(r.get("L")) if likelihoods else None,
+                                      ptr(r.get("LR")) if likelihoods else None, ms))
+        r["expand_ms"], r["gemm_ms"], r["device_ms"] = ms[0], ms[1], ms[2]
+        return r
+
+    _scratch = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().snpm_panel_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch(object):

@@ -591,6 +591,47 @@ def test_shared_panel_tensor_core_batch(lib, n_acc, S, K, skip):
     db.close()
 
 
+@pytest.mark.parametrize("n_acc,K,skip", [(1135, 1001, False), (300, 34, True), (129, 3, False), (257, 64, False)])
+def test_shared_panel_object_packed_and_plain(lib, n_acc, K, skip):
+    """A9 as an object (snpm_panel_*): the panel operand is expanded once and re-used by batches of different sizes; 2-bit
+    packed codes (K not a multiple of 4 included, garbage in the spare bits) and uint8 codes give the oracle's integers."""
+    n_rows = 20000
+    pos, regions = synth.panel_positions(n_rows)
+    db = lib.Database(pos, regions, n_acc)
+    db.fill_synthetic(synth.SEED_PANEL)
+    rng = np.random.default_rng(7000 + K)
+    rows = np.sort(rng.choice(n_rows, size=K, replace=False))
+    panel = synth.panel_codes(synth.SEED_PANEL, rows, n_acc)
+    sp = db.shared_panel(rows, skip_db_hets=skip)
+    for S in (70, 5, 130):                                          # grows, shrinks, grows: scratch is re-used
+        codes = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(S, K), p=[0.55, 0.3, 0.05, 0.1])
+        packed = lib.pack_codes2(codes)
+        assert packed.shape == (S, (K + 3) // 4)
+        if K % 4:
+            packed[:, -1] &= np.uint8((1 << (2 * (K % 4))) - 1)     # spare bits 0 = would read as ref calls if not masked
+        r_plain = sp.score(codes, likelihoods=True)
+        r_packed = sp.score(packed, packed=True, likelihoods=True)
+        for s in range(S):
+            have = np.flatnonzero(codes[s] < 3)
+            sc, ni = orc.match_gts_accs(synth.hard_weights(codes[s][have].astype(np.int8)), panel[have], skip)
+            for r in (r_plain, r_packed):
+                assert r["matches"].dtype == np.int32
+                assert np.array_equal(r["matches"][s], sc.astype(np.int64)) and np.array_equal(r["ninfo"][s], ni), "sample %d" % s
+            lik, lr = orc.calculate_likelihoods(sc.astype(np.int64), ni)
+            np.testing.assert_allclose(r_packed["L"][s], lik, rtol=RTOL, equal_nan=True)
+            np.testing.assert_allclose(r_packed["LR"][s], lr, rtol=RTOL, equal_nan=True)
+        assert np.array_equal(r_plain["L"], r_packed["L"], equal_nan=True)
+        r_int = sp.score(packed, packed=True)                       # no likelihoods: integers only
+        assert np.array_equal(r_int["matches"], r_packed["matches"]) and "L" not in r_int
+        assert r_int["gemm_ms"] > 0 and r_int["device_ms"] >= r_int["gemm_ms"]
+    one = db.score_shared_panel(rows, codes, skip_db_hets=skip)      # the one-shot form (int64) agrees
+    assert np.array_equal(one["matches"], r_packed["matches"]) and np.array_equal(one["ninfo"], r_packed["ninfo"])
+    with pytest.raises(Exception):
+        lib.SharedPanel(db, np.array([n_rows + 5], dtype=np.int64))
+    sp.close()
+    db.close()
+
+
 def test_genotype_batch_equals_per_sample_genotyper(lib, small_geno, small_panel, tmp_path):
     """Batched tensor-core mode through the Python mirror vs Genotyper run sample by sample (called genotypes)."""
     from snpmatch_b200.core import batch, parsers, snpmatch
