@@ -28,11 +28,12 @@ def main():
     ap.add_argument("--shard-of", type=int, default=1)
     ap.add_argument("--lib", default="", help="another build of the library (A/B runs in one session)")
     args = ap.parse_args()
+    if args.lib:
+        os.environ["SNPM_LIB_PATH"] = os.path.abspath(args.lib)
     import __graft_entry__ as ge
     ge.build()
     from snpmatch_b200 import lib, synth
-    if args.lib:
-        lib.LIB_PATH = os.path.abspath(args.lib)
+    out_lib = lib.LIB_PATH
     from snpmatch_b200.core import snp_genotype
     import bench
     positions, regions = synth.panel_positions(args.rows)
@@ -45,7 +46,7 @@ def main():
     pos = np.concatenate([s["pos"] for s in samples]).astype(np.int32)
     wei = np.concatenate([synth.hard_weights(s["code"]) if args.hard else s["wei"] for s in samples])
     b = lib.Batch(db, offs, chrom, pos, wei)
-    out = {"samples": args.samples, "accessions": args.accessions, "shard_of": args.shard_of}
+    out = {"samples": args.samples, "accessions": args.accessions, "shard_of": args.shard_of, "lib": out_lib}
     exact = None
     if not args.no_exact:
         b.run(kernel_mode=lib.KERNEL_POPCOUNT if args.hard else lib.KERNEL_FP64)

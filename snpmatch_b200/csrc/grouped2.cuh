@@ -154,7 +154,9 @@ __device__ __forceinline__ void counter_values9(const BitCounter<G2_TP> &c, int3
 // RING: rows of a team's gather ring (a multiple of 16): RING / 16 - 1 blocks are in flight while one is scored.  (Measured:
 // 96 rows instead of 64 changed nothing for called genotypes (0.205 ms) and cost 4-6 % with PL weights and on the 20 000-accession
 // panel; 10 teams in a 384-thread CTA at 168 registers — three warps per scheduler, 224 bytes of spills — ran at 0.350 ms against
-// 0.307 in the same session.)
+// 0.307 in the same session.  Drawing the next round's ticket one round ahead instead of two — published by thread 0 through
+// shared memory and picked up mid-round, to shorten the tail (the slowest SM is active 26 % longer than the average one) —
+// was slower everywhere: 0.2764 vs 0.2702 ms, 0.981 vs 0.924 ms on the 20 000-accession panel.)
 template <bool SKIP_HETS, int WX, int RING>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Args a) {
     constexpr int INFLIGHT = RING / GR_BLOCK;
@@ -287,9 +289,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         // one class: add the block's planes; where the class weight changes inside the block (bit k of `mask`: row k starts a new
         // weight), add the rows piece by piece and read the counter out in between
         auto add_class = [&](BitCounter<G2_CP> &c, double &wt, const uint32_t (&pl)[GR_BLOCK], uint32_t mask, int which, unsigned long long chg) {
-            // The two teams of a warp take the same path: a team without a change in this block joins the other team's first
-            // piece (its own piece is the whole block) instead of running the plain add first while the other team waits.
-            if (__all_sync(__activemask(), mask == 0u)) {
+            // (measured and dropped: a warp vote so that both teams of a warp take the same path — 0.2683-0.2703 ms against 0.2664)
+            if (mask == 0u) {
                 c.add16(pl);
                 return;
             }
@@ -299,7 +300,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
                 if (k1 > k0) {
                     const uint32_t rm = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
                     uint32_t m[GR_BLOCK];
-                    MaskRows<GR_BLOCK - 1>::go(m, pl, rm);
+                    // measured (PL samples / 20 000-accession panel / called genotypes, kernel ms): shift-shift-and masks 0.2744 /
+                    // 0.8827 / 0.1987, predicate selects 0.2664 / 0.9053 / 0.2007: the selects pay where teams share warps
+                    if (WX != 32) {
+                        MaskRows<GR_BLOCK - 1>::go(m, pl, rm);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < GR_BLOCK; ++k) m[k] = pl[k] & uint32_t(int32_t(rm << (31 - k)) >> 31);
+                    }
                     c.add16(m);
                 }
                 if (k1 >= GR_BLOCK) break;

@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnpmatch_b200.so")
+LIB_PATH = os.environ.get("SNPM_LIB_PATH") or os.path.join(_HERE, "libsnpmatch_b200.so")      # the override is for A/B runs of two builds
 
 SNPM_OK = 0
 SNPM_E_ARG = -1
