@@ -765,7 +765,9 @@ static int upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets
     SNPM_TRY(b->d_tile_sample.ensure(std::max<size_t>(tile_sample.size(), 1) * 4));
     SNPM_TRY(b->d_tile_first.ensure(size_t(n_samples + 1) * 4));
     SNPM_TRY(b->d_tile_hist.ensure(std::max<size_t>(tile_sample.size(), 1) * (size_t(GH_MAX_GROUPS) * 4 + 8)));      // id counts per tile + the tile ranges
-    SNPM_TRY(b->d_blk_chg.ensure(size_t(std::max<int64_t>(nseg, 1)) * size_t(b->gchunk / GR_BLOCK) * 8));
+    // block words of every segment, their cost estimates, the bucket counts of the work order (zeroed together), then (bucket, rank)
+    SNPM_TRY(b->d_blk_chg.ensure(size_t(std::max<int64_t>(nseg, 1)) * (size_t(b->gchunk / GR_BLOCK) * 8 + 12) + size_t(SO_BUCKETS) * 4 + 16));
+    SNPM_TRY(b->d_seg_order.ensure(size_t(std::max<int64_t>(nseg, 1)) * 16));
     SNPM_TRY(b->d_work_counter.ensure(256));
     SNPM_TRY(b->d_hash.ensure(size_t(n_samples) * GH_SLOTS * 8));
     SNPM_TRY(b->d_slot_gid.ensure(size_t(n_samples) * GH_SLOTS * 2));
@@ -876,6 +878,8 @@ int snpm_batch_destroy(snpm_batch *b) {
     if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
     if (b->ev_inputs_free) cudaEventDestroy(b->ev_inputs_free);
     if (b->ev_joined) cudaEventDestroy(b->ev_joined);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     DevBuf *bufs[] = {&b->d_off, &b->d_chrom, &b->d_pos, &b->d_wei, &b->d_filter, &b->d_match_row, &b->d_tile_cnt, &b->d_tile_off,
                       &b->d_prefix, &b->d_pair_db, &b->d_pair_s, &b->d_pair_w, &b->d_mstart, &b->d_seg_off, &b->d_part_score,
                       &b->d_part_ninfo, &b->d_red, &b->d_matches, &b->d_ninfo64, &b->d_prob, &b->d_L, &b->d_LR, &b->d_status,
@@ -883,7 +887,7 @@ int snpm_batch_destroy(snpm_batch *b) {
                       &b->d_win_ident, &b->d_win_amb, &b->d_win_row_off, &b->d_row_acc, &b->d_row_score, &b->d_row_ninfo, &b->d_row_L, &b->d_row_ident, &b->d_f1_acc, &b->d_f1_part, &b->d_f1_out, &b->d_pair_code, &b->d_wei_idx, &b->d_wei_table,
                       &b->d_chrom8, &b->d_gid, &b->d_gtable, &b->d_pair_gid, &b->d_part_int, &b->d_guard, &b->d_runs,
                       &b->d_codes, &b->d_wtable, &b->d_key_a, &b->d_key_b, &b->d_idx_a, &b->d_idx_b, &b->d_pair_db_tmp, &b->d_pair_s_tmp,
-                      &b->d_tile_sample, &b->d_tile_first, &b->d_tile_hist, &b->d_blk_chg, &b->d_work_counter, &b->d_hash, &b->d_slot_gid, &b->d_ngroups,
+                      &b->d_tile_sample, &b->d_tile_first, &b->d_tile_hist, &b->d_blk_chg, &b->d_seg_order, &b->d_work_counter, &b->d_hash, &b->d_slot_gid, &b->d_ngroups,
                       &b->d_group_overflow, &b->d_gkeys, &b->d_gw, &b->d_goff};
     for (DevBuf *d : bufs) d->release();
     for (int i = 0; i < SNPM_N_EVENTS; ++i)
@@ -1031,14 +1035,31 @@ static int batch_group_sort_t(snpm_batch *b) {
     k_group_ids<KeyT><<<tiles, RS_THREADS, 0, st>>>(b->d_key_a.as<KeyT>(), range, tsample, b->d_hash.as<unsigned long long>(), b->d_slot_gid.as<uint16_t>(),
                                                     b->d_ngroups.as<int32_t>(), b->d_gid.as<uint16_t>(), hist);
     k_group_scan<<<int(b->S), 1024, 0, st>>>(hist, tfirst, b->d_ngroups.as<int32_t>(), b->d_goff.as<int32_t>());
-    SNPM_CUDA(cudaMemsetAsync(b->d_blk_chg.p, 0, size_t(std::max<int64_t>(b->nseg_cap, 1)) * size_t(b->gchunk / GR_BLOCK) * 8, st));
+    const size_t nseg_cap = size_t(std::max<int64_t>(b->nseg_cap, 1));
+    int32_t *seg_cost = reinterpret_cast<int32_t *>(b->d_blk_chg.as<unsigned long long>() + nseg_cap * size_t(b->gchunk / GR_BLOCK));
+    int32_t *bucket_cnt = seg_cost + nseg_cap;
+    const size_t zero_bytes = nseg_cap * (size_t(b->gchunk / GR_BLOCK) * 8 + 4) + size_t(SO_BUCKETS) * 4;
+    int2 *seg_br = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(b->d_blk_chg.p) + ((zero_bytes + 7) & ~size_t(7)));
+    int64_t jcap = 1;
+    for (int64_t s = 0; s < b->S; ++s) jcap = std::max(jcap, ceil_div64(b->h_off[size_t(s) + 1] - b->h_off[size_t(s)], b->gchunk));
+    // The block words and the work order need the group table only, not the placed rows: they run on the batch's second stream
+    // (idle between its upload and its read-back) next to the partition pass.
+    cudaStream_t aux = b->copy_stream;
+    if (!b->ev_fork) SNPM_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    if (!b->ev_join) SNPM_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    SNPM_CUDA(cudaEventRecord(b->ev_fork, st));
+    SNPM_CUDA(cudaStreamWaitEvent(aux, b->ev_fork, 0));
+    SNPM_CUDA(cudaMemsetAsync(b->d_blk_chg.p, 0, zero_bytes, aux));
+    k_group_marks<KeyT><<<int(b->S), 1024, 0, aux>>>(b->d_goff.as<int32_t>(), gkeys, b->d_ngroups.as<int32_t>(), mstart, b->d_seg_off.as<int32_t>(), b->gchunk,
+                                                     b->code_bits, b->d_blk_chg.as<unsigned long long>(), seg_cost, int32_t(jcap), bucket_cnt, seg_br);
+    k_order_place<<<int(b->S), 256, 0, aux>>>(bucket_cnt, seg_br, b->d_seg_off.as<int32_t>(), mstart, b->gchunk, b->d_seg_order.as<int4>());
+    SNPM_CUDA(cudaEventRecord(b->ev_join, aux));
     k_group_place<<<tiles, RS_THREADS, size_t(GH_MAX_GROUPS) * 20, st>>>(b->d_gid.as<uint16_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
                                                                         b->d_pair_db.as<int32_t>(), b->track_pairs ? b->d_pair_s.as<int32_t>() : nullptr, mstart, tsample,
-                                                                        tfirst, range, hist, b->d_ngroups.as<int32_t>(), b->d_goff.as<int32_t>());
-    k_group_marks<KeyT><<<int(b->S), 1024, 0, st>>>(b->d_goff.as<int32_t>(), gkeys, b->d_ngroups.as<int32_t>(), mstart, b->d_seg_off.as<int32_t>(), b->gchunk,
-                                                    b->code_bits, b->d_blk_chg.as<unsigned long long>());
+                                                                        tfirst, range, hist, b->d_ngroups.as<int32_t>(), b->d_goff.as<int32_t>(), b->d_work_counter.as<unsigned int>());
+    SNPM_CUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
     SNPM_KERNEL_CHECK();
-    b->launches += 6;
+    b->launches += 7;
     return SNPM_OK;
 }
 
@@ -1054,16 +1075,13 @@ static int launch_grouped2(snpm_batch *b, bool skip_db_hets) {
     if (db->stride <= G2_WX) { g.n_slices = 1; g.wx = (db->stride + 1) & ~1; }
     else { g.wx = 32; g.n_slices = (db->stride + 31) / 32; }
     g.teams = std::min(G2_THREADS / g.wx, G2_MAX_TEAMS);
-    int64_t jmax = 0;
-    for (int64_t s = 0; s < b->S; ++s) jmax = std::max(jmax, ceil_div64(b->h_off[size_t(s) + 1] - b->h_off[size_t(s)], b->gchunk));
-    g.jmax = int32_t(jmax);
+    g.order = b->d_seg_order.as<int4>();
     g.work_counter = b->d_work_counter.as<unsigned int>();
-    const int64_t n_items = b->S * jmax * g.n_slices;
+    const int64_t n_items = std::max<int64_t>(b->nseg_cap, 1) * g.n_slices;      // upper bound (segments by markers; the kernel counts matched ones)
     if (n_items >= (int64_t(1) << 31) - (int64_t(1) << 20)) return fail(SNPM_E_ARG, "snpm_batch_run: %lld work items exceed the 2^31 limit", (long long)n_items);
     constexpr int ring = 64;                 // rows of a team's gather ring: 3 blocks in flight while one is scored
     const size_t smem = size_t(g.teams) * g2_team_smem(g.wx, g.chunk, ring);
     if (smem > 226 * 1024) return fail(SNPM_E_ARG, "snpm_batch_run: group chunk %d needs %zu bytes of shared memory", g.chunk, smem);
-    SNPM_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned int), st));
     const int grid = int(std::min<int64_t>(db->n_sm, ceil_div64(n_items, g.teams)));
 #define G2_LAUNCH(SK, WXV)                                                                                                        \
     do {                                                                                                                          \

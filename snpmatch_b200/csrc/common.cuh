@@ -154,8 +154,9 @@ struct snpm_batch {
     int32_t n_wtable = 0, code_bits = 0, key_bits = 0;
     int64_t n_sort_tiles = 0;
     snpm::DevBuf d_codes, d_wtable, d_key_a, d_key_b, d_idx_a, d_idx_b, d_pair_db_tmp, d_pair_s_tmp, d_tile_sample, d_tile_first,
-                 d_tile_hist, d_blk_chg, d_work_counter, d_hash, d_slot_gid, d_ngroups, d_group_overflow, d_gkeys, d_gw, d_goff;
+                 d_tile_hist, d_blk_chg, d_seg_order, d_work_counter, d_hash, d_slot_gid, d_ngroups, d_group_overflow, d_gkeys, d_gw, d_goff;
     bool track_pairs = true;           // coded runs: also move the marker index of every pair into grouped order (snpm_batch_fetch_pairs)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // coded runs: block words + work order on the copy stream next to the partition pass
     cudaEvent_t ev_joined = nullptr;   // coded runs: after join + compaction, before the key sort (snpm_batch_coded_timings)
     snpm::DevBuf d_chrom8, d_gid, d_gtable, d_pair_gid, d_part_int, d_guard, d_runs;
     std::vector<double> h_gtable;

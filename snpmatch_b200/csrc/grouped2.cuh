@@ -49,7 +49,7 @@ struct Group2Args {
     int32_t wx;                           // words per team slice
     int32_t teams;                        // teams per CTA
     int32_t n_slices;                     // word slices of a row
-    int32_t jmax;                         // upper bound of the segments of one sample
+    const int4 *order;                    // work order: (segment, first pair, rows, sample), most expensive first (k_order_place)
     unsigned int *work_counter;           // zeroed before the launch
 };
 
@@ -170,23 +170,19 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     unsigned char *team = g2_smem + size_t(in_team ? q : 0) * team_bytes;
     uint64_t *ring = reinterpret_cast<uint64_t *>(team);
     unsigned char *stage0 = team + size_t(RING) * wx * 8;
-    const int n_items = a.S * a.jmax * a.n_slices;
-    // item i -> (slot, slice); slot -> segment j = jmax-1 - slot / S of sample slot % S: longest segments first
+    const int n_items = __ldg(a.seg_off + a.S) * a.n_slices;      // segments of the batch x word slices
+    // item i -> (entry i / n_slices of the work order, slice i % n_slices)
     auto decode = [&](int i) {
         G2Item it;
         it.seg = -1; it.begin = 0; it.n_rows = 0; it.slice = 0; it.smp = 0;
         if (in_team && i < n_items) {
-            const int slot = i / a.n_slices, slice = i - slot * a.n_slices;
-            const int j = a.jmax - 1 - slot / a.S, smp = slot % a.S;
-            const int s0 = __ldg(a.seg_off + smp), s1 = __ldg(a.seg_off + smp + 1);
-            if (j < s1 - s0) {
-                const int m0 = __ldg(a.mstart + smp), m1 = __ldg(a.mstart + smp + 1);
-                it.seg = s0 + j;
-                it.begin = m0 + j * a.chunk;
-                it.n_rows = min(m1, it.begin + a.chunk) - it.begin;
-                it.slice = slice;
-                it.smp = smp;
-            }
+            const int rank = i / a.n_slices;
+            const int4 o = __ldg(a.order + rank);
+            it.seg = o.x;
+            it.begin = o.y;
+            it.n_rows = o.z;
+            it.slice = i - rank * a.n_slices;
+            it.smp = o.w;
         }
         return it;
     };
@@ -204,13 +200,20 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     };
 
     // start-up: round 0 staged synchronously, round 1 drawn
-    if (threadIdx.x == 0) s_base[0] = int(atomicAdd(a.work_counter, unsigned(a.teams)));
+    // The first two rounds of a CTA are fixed: round blockIdx.x and round 2 G - 1 - blockIdx.x of the work order (most expensive
+    // first), so that whoever starts on the most expensive segments gets the cheapest second helping; tickets are drawn from
+    // round 2 G on.  (With three rounds per CTA drawn at once when the kernel starts, the CTAs that drew the most expensive first
+    // AND second rounds finished last: 251 us against 218 us of average busy time.)
+    const int static_items = 2 * int(gridDim.x) * a.teams;
+    if (threadIdx.x == 0) {
+        s_base[0] = int(blockIdx.x) * a.teams;
+        s_base[1] = (2 * int(gridDim.x) - 1 - int(blockIdx.x)) * a.teams;
+    }
     __syncthreads();
     if (s_base[0] >= n_items) return;
     G2Item cur = decode(s_base[0] + q);
     prefetch(cur, 0);
     cp_async_wait<0>();
-    if (threadIdx.x == 0) s_base[1] = int(atomicAdd(a.work_counter, unsigned(a.teams)));
     __syncthreads();
     int buf = 0;
 
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     while (true) {
         const int next_base = s_base[buf ^ 1];
         int ticket = 0;
-        if (threadIdx.x == 0 && next_base < n_items) ticket = int(atomicAdd(a.work_counter, unsigned(a.teams)));      // the round after next
+        if (threadIdx.x == 0 && next_base < n_items) ticket = static_items + int(atomicAdd(a.work_counter, unsigned(a.teams)));      // the round after next
         const G2Item nxt = decode(next_base + q);
         prefetch(nxt, buf ^ 1);                   // lands while this round is scored (oldest commit group)
         const unsigned char *st = stage0 + size_t(buf) * stage_bytes;
