@@ -199,15 +199,20 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
         cp_async_commit();
     };
 
-    // start-up: round 0 staged synchronously, round 1 drawn
-    // The first two rounds of a CTA are fixed: round blockIdx.x and round 2 G - 1 - blockIdx.x of the work order (most expensive
-    // first), so that whoever starts on the most expensive segments gets the cheapest second helping; tickets are drawn from
-    // round 2 G on.  (With three rounds per CTA drawn at once when the kernel starts, the CTAs that drew the most expensive first
-    // AND second rounds finished last: 251 us against 218 us of average busy time.)
-    const int static_items = 2 * int(gridDim.x) * a.teams;
+    // start-up: round 0 staged synchronously.  The first three rounds of a CTA are fixed — a ticket is drawn two rounds before
+    // it is used, so three rounds are committed when the kernel starts whatever the scheme: round blockIdx.x of the work order
+    // (most expensive first) and two of the 2 G cheapest rounds at its end (R - 1 - blockIdx.x, R - 1 - G - blockIdx.x), so
+    // that whoever starts on the most expensive segments (184 us for one round against 215 us of average busy time) is committed
+    // to ~30 us more, not to whatever its first two tickets bring.  Tickets cover rounds [G, R - 2 G) in order; the kernel ends on
+    // ordinary cheap rounds.  (Three tickets per CTA at the start: the slowest CTA finished at 251 us; rounds b and 2 G - 1 - b
+    // fixed: 239 us, because the cost estimate cannot see how sparse the class planes are.)
+    const int G = int(gridDim.x), T = a.teams;
+    const int R = (n_items + T - 1) / T;          // rounds of the launch
+    const int dyn_end = max(G, R - 2 * G);        // tickets: rounds [G, dyn_end)
+    const int second = R - 1 - int(blockIdx.x), third = R - 1 - G - int(blockIdx.x);
     if (threadIdx.x == 0) {
-        s_base[0] = int(blockIdx.x) * a.teams;
-        s_base[1] = (2 * int(gridDim.x) - 1 - int(blockIdx.x)) * a.teams;
+        s_base[0] = int(blockIdx.x) * T;
+        s_base[1] = second >= max(G, R - G) ? second * T : n_items;
     }
     __syncthreads();
     if (s_base[0] >= n_items) return;
@@ -216,6 +221,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     cp_async_wait<0>();
     __syncthreads();
     int buf = 0;
+    bool first_round = true;
 
     const int64_t stride = a.stride;
     const int odd = w & 1;
@@ -226,7 +232,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_score_grouped2(const Group2Ar
     while (true) {
         const int next_base = s_base[buf ^ 1];
         int ticket = 0;
-        if (threadIdx.x == 0 && next_base < n_items) ticket = static_items + int(atomicAdd(a.work_counter, unsigned(a.teams)));      // the round after next
+        if (threadIdx.x == 0 && next_base < n_items) {      // the round after next
+            if (first_round) {
+                ticket = third >= dyn_end && third < R - G ? third * T : n_items;
+            } else {
+                const int r = G + int(atomicAdd(a.work_counter, 1u));
+                ticket = r < dyn_end ? r * T : n_items;
+            }
+        }
+        first_round = false;
         const G2Item nxt = decode(next_base + q);
         prefetch(nxt, buf ^ 1);                   // lands while this round is scored (oldest commit group)
         const unsigned char *st = stage0 + size_t(buf) * stage_bytes;
