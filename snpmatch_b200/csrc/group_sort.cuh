@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
     const int flag = row >= 0;
     int total;
     const int ex = block_excl_scan(flag, &total, s_warp);
-    __shared__ int64_t s_first_sm;
-    if (threadIdx.x == 0) {                         // sample of the tile's first marker
+    __shared__ int64_t s_first_sm, s_first_end;
+    if (threadIdx.x == 0) {                         // sample of the tile's first marker, and where that sample ends
         const int64_t i0 = int64_t(blockIdx.x) * JOIN_TILE;
         int64_t lo = 0, hi = S;
         while (hi - lo > 1) {
@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
             if (off[mid] <= i0) lo = mid; else hi = mid;
         }
         s_first_sm = lo;
+        s_first_end = off[lo + 1];
     }
     __syncthreads();
-    const int64_t s_first = s_first_sm;
+    const int64_t s_first = s_first_sm, first_end = s_first_end;
     unsigned long long ins = ~0ull, fold = 0ull;    // the key to insert, or nothing
     bool solo = false;
     int64_t smp = 0;
@@ -131,8 +132,11 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
             const int b = code_bits;
             const KeyT kk = (KeyT(c) << (3 * b)) | (KeyT(cd[c]) << (2 * b)) | (KeyT(cd[gs_slow_class(c)]) << b) | KeyT(cd[gs_fast_class(c)]);
             key[p] = kk;
-            int64_t lo = s_first;                           // sample of marker i: the last offset <= i (a tile spans few samples)
-            while (lo + 1 < S && off[lo + 1] <= i) ++lo;
+            int64_t lo = s_first;                           // sample of marker i: the last offset <= i (a tile lies inside one sample
+            if (i >= first_end) {                           // almost always: no load then; else it spans few samples)
+                ++lo;
+                while (lo + 1 < S && off[lo + 1] <= i) ++lo;
+            }
             smp = lo;
             // one insert per distinct (sample, key) of the warp: a sample's common triples would otherwise hammer one slot.  The
             // sample is folded into the word that is matched (keys have at most 50 bits) when it is close enough to the tile's first
