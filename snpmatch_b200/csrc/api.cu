@@ -981,12 +981,12 @@ static int batch_join(snpm_batch *b, int algo) {
             SNPM_CUDA(cudaMemsetAsync(b->d_group_overflow.p, 0, size_t(S) * 4, st));
             SNPM_CUDA(cudaMemsetAsync(hash, 0, size_t(S) * GH_SLOTS * 8, st));
             if (b->key_bits <= 32)
-                k_scatter_pairs_coded<uint32_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
+                k_scatter_pairs_coded<uint32_t><<<int(n_tiles), SC_THREADS, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
                         b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
                         b->d_key_a.as<uint32_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>(),
                         b->codes_packed ? b->d_codes.as<uint32_t>() : nullptr);
             else
-                k_scatter_pairs_coded<uint64_t><<<int(n_tiles), JOIN_TILE, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
+                k_scatter_pairs_coded<uint64_t><<<int(n_tiles), SC_THREADS, 0, st>>>(b->d_match_row.as<int32_t>(), n, b->d_tile_off.as<int32_t>(), b->d_codes.as<uint16_t>(),
                         b->d_wtable.as<double>(), b->n_wtable, b->code_bits, b->d_prefix.as<int32_t>(), b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(),
                         b->d_key_a.as<uint64_t>(), b->d_status.as<int>(), b->d_off.as<int64_t>(), S, hash, b->d_group_overflow.as<int>(),
                         b->codes_packed ? b->d_codes.as<uint32_t>() : nullptr);

@@ -76,24 +76,51 @@ __device__ __forceinline__ uint32_t gh_find(const unsigned long long *__restrict
     return h;
 }
 
-// as k_scatter_pairs (join.cuh), the payload of a pair being its key, which also goes into its sample's key table (lanes of
-// a warp that hold the same key of the same sample insert once)
+// as k_scatter_pairs (join.cuh), the payload of a pair being its key, which also goes into its sample's key table.  A CTA of
+// SC_THREADS threads takes one tile of JOIN_TILE markers, four per thread (marker j * SC_THREADS + thread of the tile: all
+// loads of a thread are issued before the first is used), ranks the matched ones with warp ballots and ONE block barrier, and
+// inserts every distinct (sample, key) of the tile once: lanes of a warp that hold the same combination elect one
+// (match.any), which asks a shared-memory table of the CTA before it probes the sample's table in global memory (an L2 round
+// trip behind an atomicCAS: 40 % of the stall samples of the first version, a 1024-thread CTA with one marker per thread and
+// three barriers: 82 us per 3.2 M markers).
+constexpr int SC_THREADS = 256;
+constexpr int SC_PER = JOIN_TILE / SC_THREADS;
+constexpr int SC_SLOTS = 1024;
 template <typename KeyT>
-__global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
+__global__ void __launch_bounds__(SC_THREADS) k_scatter_pairs_coded(
         const int32_t *__restrict__ match_row, int64_t n, const int32_t *__restrict__ tile_off, const uint16_t *__restrict__ codes,
         const double *__restrict__ wtable, int32_t n_table, int32_t code_bits, int32_t *__restrict__ prefix,
         int32_t *__restrict__ pair_db, int32_t *__restrict__ pair_s, KeyT *__restrict__ key, int *status,
         const int64_t *__restrict__ off, int64_t S, unsigned long long *__restrict__ hash, int *__restrict__ overflow,
         const uint32_t *__restrict__ codes32) {
-    __shared__ int s_warp[33];
-    const int64_t i = int64_t(blockIdx.x) * JOIN_TILE + threadIdx.x;
-    const int32_t row = i < n ? match_row[i] : -1;
-    const int flag = row >= 0;
-    int total;
-    const int ex = block_excl_scan(flag, &total, s_warp);
+    constexpr int NW = SC_THREADS / 32;
+    __shared__ int s_cnt[SC_PER][NW];
     __shared__ int64_t s_first_sm, s_first_end;
+    __shared__ unsigned long long s_seen[SC_SLOTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = int64_t(blockIdx.x) * JOIN_TILE;
+    int32_t row[SC_PER];
+    uint32_t cw[SC_PER];
+#pragma unroll
+    for (int j = 0; j < SC_PER; ++j) {
+        const int64_t i = i0 + j * SC_THREADS + threadIdx.x;
+        row[j] = i < n ? match_row[i] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SC_PER; ++j) {
+        const int64_t i = i0 + j * SC_THREADS + threadIdx.x;
+        cw[j] = (codes32 != nullptr && i < n) ? codes32[i] : 0u;
+    }
+    const int32_t base0 = tile_off[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SC_SLOTS / SC_THREADS; ++j) s_seen[j * SC_THREADS + threadIdx.x] = 0ull;
+    uint32_t bal[SC_PER];
+#pragma unroll
+    for (int j = 0; j < SC_PER; ++j) {
+        bal[j] = __ballot_sync(0xffffffffu, row[j] >= 0);
+        if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
+    }
     if (threadIdx.x == 0) {                         // sample of the tile's first marker, and where that sample ends
-        const int64_t i0 = int64_t(blockIdx.x) * JOIN_TILE;
         int64_t lo = 0, hi = S;
         while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
@@ -104,49 +131,74 @@ __global__ void __launch_bounds__(JOIN_TILE) k_scatter_pairs_coded(
     }
     __syncthreads();
     const int64_t s_first = s_first_sm, first_end = s_first_end;
-    unsigned long long ins = ~0ull, fold = 0ull;    // the key to insert, or nothing
-    bool solo = false;
-    int64_t smp = 0;
-    if (i < n) {
-        const int32_t p = tile_off[blockIdx.x] + ex;
-        prefix[i] = p;
-        if (flag) {
-            pair_db[p] = row;
-            pair_s[p] = int32_t(i);
-            uint32_t cd[3];                             // wei columns are (ref, het, alt); classes (ref, alt, het)
-            if (codes32 != nullptr) {                   // three 10-bit codes in one word: ref | het << 10 | alt << 20
-                const uint32_t v = codes32[i];
-                cd[0] = v & 1023u; cd[2] = (v >> 10) & 1023u; cd[1] = (v >> 20) & 1023u;
-            } else {
-                cd[0] = codes[3 * i]; cd[2] = codes[3 * i + 1]; cd[1] = codes[3 * i + 2];
-            }
-            bool bad = false;
+    int32_t base = base0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (int32_t(cd[k]) >= n_table) { bad = true; cd[k] = 0; }
-            if (bad) atomicAdd(status + 4, 1);             // a code outside the table: reported at wait / fetch
-            const double w0 = __ldg(wtable + cd[0]), w1 = __ldg(wtable + cd[1]), w2 = __ldg(wtable + cd[2]);
-            int c;                                          // called class: the weight that is 1.0, else the largest
-            if (w0 == 1.0) c = 0; else if (w1 == 1.0) c = 1; else if (w2 == 1.0) c = 2;
-            else { c = 0; if (w1 > w0) c = 1; if (w2 > (c ? w1 : w0)) c = 2; }
-            const int b = code_bits;
-            const KeyT kk = (KeyT(c) << (3 * b)) | (KeyT(cd[c]) << (2 * b)) | (KeyT(cd[gs_slow_class(c)]) << b) | KeyT(cd[gs_fast_class(c)]);
-            key[p] = kk;
-            int64_t lo = s_first;                           // sample of marker i: the last offset <= i (a tile lies inside one sample
-            if (i >= first_end) {                           // almost always: no load then; else it spans few samples)
-                ++lo;
-                while (lo + 1 < S && off[lo + 1] <= i) ++lo;
+    for (int j = 0; j < SC_PER; ++j) {
+        const int64_t i = i0 + j * SC_THREADS + threadIdx.x;
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int c = s_cnt[j][w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        const int32_t p = base + before + __popc(bal[j] & ((1u << lane) - 1u));
+        base += total;
+        unsigned long long ins = ~0ull, fold = 0ull;    // the key to insert, or nothing
+        bool solo = false;
+        int64_t smp = 0;
+        if (i < n) {
+            prefix[i] = p;
+            if (row[j] >= 0) {
+                pair_db[p] = row[j];
+                pair_s[p] = int32_t(i);
+                uint32_t cd[3];                             // wei columns are (ref, het, alt); classes (ref, alt, het)
+                if (codes32 != nullptr) {                   // three 10-bit codes in one word: ref | het << 10 | alt << 20
+                    const uint32_t v = cw[j];
+                    cd[0] = v & 1023u; cd[2] = (v >> 10) & 1023u; cd[1] = (v >> 20) & 1023u;
+                } else {
+                    cd[0] = codes[3 * i]; cd[2] = codes[3 * i + 1]; cd[1] = codes[3 * i + 2];
+                }
+                bool bad = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (int32_t(cd[k]) >= n_table) { bad = true; cd[k] = 0; }
+                if (bad) atomicAdd(status + 4, 1);             // a code outside the table: reported at wait / fetch
+                const double w0 = __ldg(wtable + cd[0]), w1 = __ldg(wtable + cd[1]), w2 = __ldg(wtable + cd[2]);
+                int c;                                          // called class: the weight that is 1.0, else the largest
+                if (w0 == 1.0) c = 0; else if (w1 == 1.0) c = 1; else if (w2 == 1.0) c = 2;
+                else { c = 0; if (w1 > w0) c = 1; if (w2 > (c ? w1 : w0)) c = 2; }
+                const int b = code_bits;
+                const KeyT kk = (KeyT(c) << (3 * b)) | (KeyT(cd[c]) << (2 * b)) | (KeyT(cd[gs_slow_class(c)]) << b) | KeyT(cd[gs_fast_class(c)]);
+                key[p] = kk;
+                int64_t lo = s_first;                           // sample of marker i: the last offset <= i (a tile lies inside one sample
+                if (i >= first_end) {                           // almost always: no load then; else it spans few samples)
+                    ++lo;
+                    while (lo + 1 < S && off[lo + 1] <= i) ++lo;
+                }
+                smp = lo;
+                // the sample is folded into the word that is matched (keys have at most 50 bits) when it is close enough to the tile's first
+                ins = (unsigned long long)(kk);
+                if (lo - s_first < 8192) fold = (unsigned long long)(lo - s_first) << 50;
+                else solo = true;
             }
-            smp = lo;
-            // one insert per distinct (sample, key) of the warp: a sample's common triples would otherwise hammer one slot.  The
-            // sample is folded into the word that is matched (keys have at most 50 bits) when it is close enough to the tile's first
-            ins = (unsigned long long)(kk);
-            if (lo - s_first < 8192) fold = (unsigned long long)(lo - s_first) << 50;
-            else solo = true;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, solo ? (0xffffull << 48 | (unsigned long long)(threadIdx.x)) : (ins | fold));
+        if (ins != ~0ull && (solo || lane == __ffs(peers) - 1)) {
+            bool fresh = true;                              // not inserted by this CTA yet (or its table cannot tell)
+            if (!solo) {
+                const unsigned long long want = (ins | fold) + 1ull;
+                uint32_t h = uint32_t((want * 0x9E3779B97F4A7C15ull) >> 54);
+                for (int probe = 0; probe < 16; ++probe) {
+                    const unsigned long long cur = atomicCAS(s_seen + h, 0ull, want);
+                    if (cur == 0ull) break;
+                    if (cur == want) { fresh = false; break; }
+                    h = (h + 1u) & uint32_t(SC_SLOTS - 1);
+                }
+            }
+            if (fresh) gh_insert(hash + size_t(smp) * GH_SLOTS, ins, overflow + smp);
         }
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, solo ? (0xffffull << 48 | (unsigned long long)(threadIdx.x)) : (ins | fold));
-    if (ins != ~0ull && (solo || (threadIdx.x & 31) == __ffs(peers) - 1)) gh_insert(hash + size_t(smp) * GH_SLOTS, ins, overflow + smp);
 }
 
 // Tile t of the sort covers pairs [begin, end) of sample tile_sample[t]: the lt-th RS_TILE pairs of the sample's matched range
