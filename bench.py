@@ -74,6 +74,7 @@ def parse_args():
                          "pulls in one kernel), nccl = NCCL reduce-scatter, auto = what was measured faster (p2p on 2 GPUs; NCCL beyond, "
                          "where it reduces inside the NVSwitch), none = timing experiment only (totals stay per rank)")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on whatever cores it was started on (default: the cores next to its GPU)")
     args = ap.parse_args()
     if args.reduce == "auto":
         args.reduce = "p2p" if int(os.environ.get("WORLD_SIZE", args.gpus)) == 2 else "nccl"
@@ -563,7 +564,43 @@ def measured_traffic(args, world, n_samples):
             "traffic_source": t["source"], "traffic_note": t["note"]}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the host cores next to its GPU (one process per GPU): pinned buffers allocated afterwards land in that
+    NUMA node's memory, so that eight ranks uploading at once do not pull half of their bytes across the socket link.  Returns
+    a description for the JSON line; does nothing when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(vis.split(",")[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local_rank
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(hdl).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s" % (dom[-4:].lower(), rest.lower())
+        with open(path + "/local_cpulist") as fh:
+            spec = fh.read().strip()
+        with open(path + "/numa_node") as fh:
+            node = int(fh.read().strip())
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": "no local cores in this process's affinity mask"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "numa_node": node, "cores": len(cpus)}
+    except Exception as e:  # noqa: BLE001 - the binding is an optimisation
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_b200_arm(args):
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     import torch
     import __graft_entry__ as ge
     ge.build()
@@ -574,7 +611,6 @@ def run_b200_arm(args):
     ctx.args, ctx.torch, ctx.keep = args, torch, []
     ctx.rank = rank = int(os.environ.get("RANK", "0"))
     ctx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert lib.device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     ctx.dist = ctx.host_pg = None
@@ -641,6 +677,7 @@ def run_b200_arm(args):
             "stages_ms": h["stages_ms"], "distinct_weight_values": h["n_weights"], "group_chunk_rows": int(args.group_chunk),
             "headline_kernel": "k_score_grouped2 (counting kernel, device-grouped pairs)",
             "guard_flagged_samples": h["guard_flagged_samples"], "clocks": clocks, "matched_markers_per_step": h["m_total"],
+            "host_numa_binding_rank0": numa,
         }
         x_ach_bytes = algo_bytes
         line["order_exact_fp64"] = {

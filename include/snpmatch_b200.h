@@ -175,6 +175,12 @@ int snpm_batch_upload_grouped_runs(snpm_batch *b, int64_t n_samples, const int64
  * Group chunks (snpm_batch_set_group_chunk) must be multiples of 16 and at most 496 rows for coded batches. */
 int snpm_batch_upload_coded(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,
                             const uint16_t *codes, const double *wtable, int32_t n_wtable);
+/* host code, one pass over the markers: the chrom_pos words (chromosome id << 27 | position; id < 0 -> 31) from int32 ids and
+ * positions and, when codes32 is not NULL, the three codes of a marker in one word (ref | het << 10 | alt << 20).  What
+ * ParseInputs holds after parsers.py:141-157 -> what snpm_batch_upload_coded / _coded32 take.  SNPM_E_RANGE when an id exceeds
+ * 30, a position 2^27 - 1 or (codes32 wanted) a code 1023. */
+int snpm_pack_coded(int64_t n, const int32_t *chrom_id, const int32_t *pos, const uint16_t *codes, uint32_t *chrom_pos,
+                    uint32_t *codes32);
 /* the same with the three codes of a marker in one word, ref | het << 10 | alt << 20 (n_wtable <= 1024: e.g. integer PLs up to
  * 1023): 8 bytes per marker cross the PCIe bus */
 int snpm_batch_upload_coded32(snpm_batch *b, int64_t n_samples, const int64_t *offsets, const uint32_t *chrom_pos,

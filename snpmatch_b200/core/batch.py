@@ -48,30 +48,55 @@ def genotype_batch(g, samples, skip_db_hets=False):
     return out, {"panel_markers": len(rows), "gemm_ms": r["gemm_ms"]}
 
 
-def coded_batch(g, samples):
+def _is_identity(order):
+    n = len(order)
+    return n == 0 or (order[0] == 0 and order[-1] == n - 1 and bool(np.all(order[1:] > order[:-1])))
+
+
+def coded_batch(g, samples, with_weights=True):
     """lib.CodedSamples of a list of ParseInputs: every sample's markers in the order the join wants (database chromosome
     order, position), chromosome id + position in one word, weights as dictionary codes (ParseInputs.coded_weights: the
     integer PLs of a VCF, or a one-off np.unique for other inputs) into ONE table for the batch.  Returns (CodedSamples or
-    None, offsets, chrom ids, positions, weights) — the last three in upload order, for re-scoring flagged samples."""
+    None, offsets, chrom ids, positions, weights) — the last three in upload order, for re-scoring flagged samples (weights:
+    None unless `with_weights` or the samples cannot be coded; table[codes] gives them back bit for bit).
+    Per-marker work is skipped wherever the input allows it: a file that is already in the join's order is not permuted, and
+    samples whose tables are prefixes of one table (VCFs: code = PL, table = exp(-PL/10)) keep their codes as they are."""
     prepared = [g.prepare_markers(inp.chrs, inp.pos) for inp in samples]
+    ident = [_is_identity(p[0]) for p in prepared]
     offs = np.concatenate([[0], np.cumsum([len(p[2]) for p in prepared])]).astype(np.int64)
     cid = np.concatenate([p[1] for p in prepared]) if samples else np.zeros(0, np.int32)
     pos = np.concatenate([p[2] for p in prepared]) if samples else np.zeros(0, np.int32)
-    wei = np.concatenate([np.asarray(inp.wei, dtype=np.float64)[p[0]] for inp, p in zip(samples, prepared)]) if samples else np.zeros((0, 3))
+
+    def weights():
+        if not samples:
+            return np.zeros((0, 3))
+        return np.concatenate([np.asarray(inp.wei, dtype=np.float64) if same else np.asarray(inp.wei, dtype=np.float64)[p[0]]
+                               for inp, p, same in zip(samples, prepared, ident)])
+
     coded = [inp.coded_weights() for inp in samples]
     cs = None
     if all(c is not None for c in coded) and samples:
-        # one table for the batch: union of the samples' tables (bit patterns), every sample's codes remapped into it
-        tables = [c[1].view(np.uint64) for c in coded]
-        union, inv = np.unique(np.concatenate(tables), return_inverse=True)
-        if len(union) <= 65536:
-            codes, at = [], 0
-            for (c, t), p in zip(coded, prepared):
-                remap = inv[at:at + len(t)].astype(np.uint16)
+        # one table for the batch: the longest table when every other one is a prefix of it (bit patterns), else the union of
+        # the tables with every sample's codes remapped into it
+        tables = [np.ascontiguousarray(c[1], dtype=np.float64).view(np.uint64) for c in coded]
+        longest = max(tables, key=len)
+        if all(np.array_equal(t, longest[:len(t)]) for t in tables):
+            union, remaps = longest, [None] * len(tables)
+        else:
+            union, inv = np.unique(np.concatenate(tables), return_inverse=True)
+            remaps, at = [], 0
+            for t in tables:
+                remaps.append(inv[at:at + len(t)].astype(np.uint16))
                 at += len(t)
-                codes.append(remap[c.astype(np.int64)][p[0]])
+        if len(union) <= 65536:
+            codes = []
+            for (c, _), p, same, remap in zip(coded, prepared, ident, remaps):
+                c = np.asarray(c, dtype=np.uint16)
+                if not same:
+                    c = c[p[0]]
+                codes.append(c if remap is None else remap[c])
             cs = lib.code_markers(offs, cid, pos, codes=np.concatenate(codes), wtable=union.view(np.float64))
-    return cs, offs, cid, pos, wei
+    return cs, offs, cid, pos, (weights() if with_weights or cs is None else None)
 
 
 def genotype_many(g, samples, skip_db_hets=False):
@@ -82,7 +107,7 @@ def genotype_many(g, samples, skip_db_hets=False):
     identical to Genotyper run sample by sample and likelihoods within 1e-9; samples whose int(score) would depend on the
     reference's summation order are re-scored by the order-exact kernel inside `lib.score_coded`.  Inputs that cannot be
     coded (more than 65536 distinct weight values, negative weights) take the order-exact kernel for every sample."""
-    cs, offs, cid, pos, wei = coded_batch(g, samples)
+    cs, offs, cid, pos, wei = coded_batch(g, samples, with_weights=False)     # flagged samples get their weights back from the codes
     if cs is not None:
         r = lib.score_coded(g.db, cs, cid, pos, wei, skip_db_hets=skip_db_hets, batch=getattr(g, "_many_batch", None))
     else:

@@ -16,7 +16,16 @@ def factorize(labels):
     n = len(labels)
     if n == 0:
         return np.zeros(0, dtype=np.int64), labels.astype("U")
-    change = np.flatnonzero(labels[1:] != labels[:-1]) + 1
+    # neighbours compared as integer words (a fixed-width unicode array is 4 bytes per character): several times faster than
+    # NumPy's string comparison
+    if labels.dtype.kind == "U" and labels.dtype.itemsize >= 4:
+        words = np.ascontiguousarray(labels).view(np.uint32).reshape(n, -1)
+        differ = words[1:, 0] != words[:-1, 0]
+        for k in range(1, words.shape[1]):
+            differ |= words[1:, k] != words[:-1, k]
+        change = np.flatnonzero(differ) + 1
+    else:
+        change = np.flatnonzero(labels[1:] != labels[:-1]) + 1
     if len(change) < max(64, n // 16):
         starts = np.concatenate([[0], change])
         run_codes, uniq = pd.factorize(labels[starts])
@@ -25,8 +34,11 @@ def factorize(labels):
     return codes.astype(np.int64), np.asarray(uniq).astype("U")
 
 
-def map_labels(labels, fn):
-    """fn applied to every label, computed on the distinct labels only: returns (mapped str[n], codes, mapped uniques)."""
+def map_labels(labels, fn, per_label=True):
+    """fn applied to every label, computed on the distinct labels only: returns (mapped str[n], codes, mapped uniques); the
+    per-marker strings are left out (None) with per_label=False."""
     codes, uniq = factorize(labels)
     mapped = np.array([fn(str(u)) for u in uniq], dtype="str") if len(uniq) else np.zeros(0, dtype="U1")
+    if not per_label:
+        return None, codes, mapped
     return (mapped[codes] if len(codes) else np.zeros(0, dtype="U1")), codes, mapped

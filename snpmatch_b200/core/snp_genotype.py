@@ -45,12 +45,24 @@ def order_markers(cid, sample_pos):
     database): markers grouped by chromosome id (unknown last), inside a chromosome in the caller's order."""
     cid = np.asarray(cid)
     sample_pos = np.asarray(sample_pos)
-    in_range = (sample_pos >= -2**31) & (sample_pos < 2**31 - 1)
-    cid = np.where(in_range, cid, -1).astype(np.int32)
-    sort_key = np.where(cid < 0, np.int64(2**31), cid.astype(np.int64))
-    order = np.argsort(sort_key, kind="stable")
-    cid_o = cid[order]
-    pos_o = np.where(in_range, sample_pos, 0)[order].astype(np.int32)
+    n = len(cid)
+    if n and int(sample_pos.min()) >= -2**31 and int(sample_pos.max()) < 2**31 - 1 and int(cid.min()) >= 0:
+        # the common case in two cheap passes: every position fits, every chromosome is known
+        in_range = np.ones(n, dtype=bool)
+        cid = cid.astype(np.int32, copy=False)
+        sort_key = cid
+    else:
+        in_range = (sample_pos >= -2**31) & (sample_pos < 2**31 - 1)
+        cid = np.where(in_range, cid, -1).astype(np.int32)
+        sort_key = np.where(cid < 0, np.int64(2**31), cid.astype(np.int64))
+    if len(sort_key) < 2 or bool(np.all(sort_key[1:] >= sort_key[:-1])):      # already grouped by chromosome in database order: nothing moves
+        order = np.arange(len(cid), dtype=np.int64)
+        cid_o = cid
+        pos_o = sample_pos.astype(np.int32) if sort_key is cid else np.where(in_range, sample_pos, 0).astype(np.int32)
+    else:
+        order = np.argsort(sort_key, kind="stable")
+        cid_o = cid[order]
+        pos_o = np.where(in_range, sample_pos, 0)[order].astype(np.int32)
     # the join needs strictly ascending positions inside a chromosome (the reference's implicit
     # precondition, SURVEY A.1); sort a chromosome that is not
     bad = (cid_o[1:] == cid_o[:-1]) & (cid_o[1:] >= 0) & (pos_o[1:] <= pos_o[:-1])
@@ -245,7 +257,7 @@ class Genotype(object):
         for i, name in enumerate(db_norm):
             first.setdefault(name, i)
         # per-marker names -> codes + the few distinct names; the database index is looked up per distinct name
-        _, codes, uniq_norm = labels.map_labels(sample_chrs, norm)
+        _, codes, uniq_norm = labels.map_labels(sample_chrs, norm, per_label=False)
         table = np.array([first.get(u, -1) for u in uniq_norm], dtype=np.int32)
         cid = table[codes] if len(codes) else np.zeros(0, dtype=np.int32)
         return order_markers(cid, sample_pos)

@@ -832,6 +832,24 @@ int snpm_pack_markers(int64_t n, const uint8_t *chrom_u8, const int32_t *pos, ui
     return SNPM_OK;
 }
 
+int snpm_pack_coded(int64_t n, const int32_t *chrom_id, const int32_t *pos, const uint16_t *codes, uint32_t *chrom_pos, uint32_t *codes32) {
+    if (n < 0 || (n > 0 && (!chrom_id || !pos || !chrom_pos || (codes32 && !codes)))) return fail(SNPM_E_ARG, "snpm_pack_coded: bad arguments");
+    uint32_t bad = 0u;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t c = chrom_id[i], p = pos[i];
+        bad |= uint32_t(c > 30) | uint32_t(p < 0) | uint32_t(p >= (1 << 27));
+        chrom_pos[i] = ((c < 0 ? 31u : uint32_t(c)) << 27) | (uint32_t(p) & ((1u << 27) - 1u));
+    }
+    if (codes32)
+        for (int64_t i = 0; i < n; ++i) {
+            const uint32_t a = codes[3 * i], h = codes[3 * i + 1], t = codes[3 * i + 2];
+            bad |= uint32_t((a | h | t) > 1023u);
+            codes32[i] = a | (h << 10) | (t << 20);
+        }
+    if (bad) return fail(SNPM_E_RANGE, "snpm_pack_coded: a chromosome id above 30, a position outside 27 bits or a code above 1023");
+    return SNPM_OK;
+}
+
 int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts) {
     if (!b || !counts) return fail(SNPM_E_ARG, "snpm_batch_guard_counts: NULL argument");
     if (!b->grouped) { for (int64_t s = 0; s < b->rangen(); ++s) counts[s] = 0; return SNPM_OK; }

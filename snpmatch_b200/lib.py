@@ -146,6 +146,25 @@ def code_markers(offsets, s_chrom_id, s_pos, wei=None, codes=None, wtable=None):
     qualify (more than 65536 distinct weight values, negative / non-finite weights, ids or positions that do not fit one
     word): score such samples in position order with the fp64 kernel."""
     offsets = as_c(offsets, np.int64)
+    if codes is not None and wtable is not None and len(wtable) <= 1024:
+        # ready-made codes of a small table (a VCF's integer PLs): both upload words in one native pass over the markers
+        wtable = as_c(wtable, np.float64)
+        if len(wtable) == 0:
+            wtable = np.zeros(1)
+        if not (np.all(np.isfinite(wtable)) and np.all(wtable >= 0.0)):
+            return None
+        cid, pp = as_c(s_chrom_id, np.int32), as_c(s_pos, np.int32)
+        codes = as_c(codes, np.uint16).reshape(-1, 3)
+        n = int(offsets[-1])
+        assert len(codes) == len(cid) == len(pp) == n
+        if n and int(codes.max()) >= len(wtable):
+            return None
+        cp, c32 = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        rc = load().snpm_pack_coded(n, ptr(cid), ptr(pp), ptr(codes), ptr(cp), ptr(c32))
+        if rc == SNPM_E_RANGE:
+            return None
+        check(rc)
+        return CodedSamples(offsets, cp, codes, wtable, codes32=c32)
     cp = pack_chrom_pos(s_chrom_id, s_pos)
     if cp is None:
         return None
@@ -209,6 +228,7 @@ SIGNATURES = {
     "snpm_group_markers": (C.c_int, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "snpm_batch_upload_grouped": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i32]),
     "snpm_pack_markers": (C.c_int, [_i64, _p, _p, _p]),
+    "snpm_pack_coded": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "snpm_batch_upload_grouped_runs": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i32]),
     "snpm_batch_upload_grouped_packed": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32]),
     "snpm_batch_upload_coded": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i32]),

@@ -306,3 +306,54 @@ def test_coded_samples_host_side():
     codes, tab = inp.coded_weights()
     assert np.array_equal(tab[codes.astype(np.int64)].view(np.uint64), s["wei"].view(np.uint64))
     assert inp.coded_weights()[0] is codes                       # cached
+
+
+def test_coded_batch_host_side(built_lib):
+    """core.batch.coded_batch: what goes up for a list of ParseInputs reproduces every sample's markers and weights bit for bit
+    whichever shortcut was taken (files already in the join's order, tables that are prefixes of one table) or not."""
+    from snpmatch_b200 import lib, synth
+    from snpmatch_b200.core import batch, parsers, snp_genotype
+    pos, regions = synth.panel_positions(20000)
+    g = object.__new__(snp_genotype.Genotype)
+    g.chrs = np.array(synth.TAIR10_CHRS)
+    g._db_chr_norm = snp_genotype.normalize_chr_names(g.chrs)
+    names = np.array(["Chr" + c for c in synth.TAIR10_CHRS])
+
+    def make(seed, shuffle_chromosomes, own_table):
+        s = synth.make_sample_fast(pos, regions, 50, 3, n_db=1500, n_extra=150, seed=seed)
+        chrs, p, wei, pl = names[s["chr_ix"]], s["pos"], s["wei"], s["pl"]
+        if shuffle_chromosomes:                                  # chromosome blocks in another order than the database's
+            blocks = [np.flatnonzero(s["chr_ix"] == c) for c in (3, 0, 4, 1, 2)]
+            k = np.concatenate(blocks)
+            chrs, p, wei, pl = chrs[k], p[k], wei[k], pl[k]
+        inp = parsers.ParseInputs("")
+        inp.load_snp_info(chrs, p, synth._gt_strings(s["code"]), wei, s["dp"])
+        if not own_table:
+            inp._coded = (pl.astype(np.uint16), synth.pl_table(int(pl.max())), inp.wei)
+        return inp
+
+    for case in ([(11, False, False), (12, False, False)],       # in order, prefix tables: no permutation, no remap
+                 [(13, True, False), (14, False, False)],        # one sample permuted
+                 [(15, False, True), (16, True, False)]):        # one sample with its own dictionary (np.unique order): union + remap
+        inputs = [make(*c) for c in case]
+        cs, offs, cid, p, wei = batch.coded_batch(g, inputs)
+        assert cs is not None and cs.codes32 is not None
+        cs_lazy = batch.coded_batch(g, inputs, with_weights=False)
+        assert cs_lazy[4] is None and np.array_equal(cs_lazy[0].codes32, cs.codes32) and np.array_equal(cs_lazy[0].chrom_pos, cs.chrom_pos)
+        for i, inp in enumerate(inputs):
+            order, c_i, p_i = g.prepare_markers(inp.chrs, inp.pos)
+            lo, hi = int(offs[i]), int(offs[i + 1])
+            assert np.array_equal(cid[lo:hi], c_i) and np.array_equal(p[lo:hi], p_i)
+            want = np.asarray(inp.wei)[order]
+            assert np.array_equal(wei[lo:hi].view(np.uint64), want.view(np.uint64))
+            assert np.array_equal(cs.wtable[cs.codes[lo:hi].astype(np.int64)].view(np.uint64), want.view(np.uint64))
+            assert np.array_equal(cs.chrom_pos[lo:hi] >> np.uint32(27), np.where(c_i < 0, 31, c_i).astype(np.uint32))
+            assert np.array_equal(cs.chrom_pos[lo:hi] & np.uint32((1 << 27) - 1), p_i.astype(np.uint32))
+        c32 = cs.codes32
+        assert np.array_equal(c32 & 1023, cs.codes[:, 0]) and np.array_equal((c32 >> 10) & 1023, cs.codes[:, 1]) and np.array_equal(c32 >> 20, cs.codes[:, 2])
+    # the native packer refuses what does not fit the words
+    assert lib.code_markers(np.array([0, 1]), np.array([31]), np.array([5]), codes=np.zeros((1, 3), np.uint16), wtable=np.ones(4)) is None
+    assert lib.code_markers(np.array([0, 1]), np.array([0]), np.array([1 << 27]), codes=np.zeros((1, 3), np.uint16), wtable=np.ones(4)) is None
+    assert lib.code_markers(np.array([0, 1]), np.array([0]), np.array([7]), codes=np.full((1, 3), 9, np.uint16), wtable=np.ones(4)) is None
+    one = lib.code_markers(np.array([0, 2]), np.array([-1, 2]), np.array([5, 6]), codes=np.array([[0, 1, 2], [3, 2, 1]], np.uint16), wtable=np.arange(4.0))
+    assert int(one.chrom_pos[0] >> 27) == 31 and int(one.chrom_pos[1]) == (2 << 27 | 6) and one.codes32.tolist() == [0 | 1 << 10 | 2 << 20, 3 | 2 << 10 | 1 << 20]
