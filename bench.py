@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the sub-records (development runs)")
     ap.add_argument("--group-chunk", type=int, default=320, help="rows per segment of the counting kernel")
+    ap.add_argument("--wide-group-chunk", type=int, default=496, help="the same for the 20 000-accession sub-record (the library's choice for wide panels)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl", "none"],
                     help="cross-GPU sum of the per-sample totals: p2p = one-shot reduce over peer memory (CUDA IPC over NVLink, flag barrier + "
                          "pulls in one kernel), nccl = NCCL reduce-scatter, auto = what was measured faster (p2p on 2 GPUs; NCCL beyond, "
@@ -916,7 +917,7 @@ def sub_wide(ctx, peak, peak_source):
     g.db.set_stream(ctx.stream.cuda_stream)
     samples = make_samples(positions, regions, n_acc, S, args.markers, first_seed=9000)
     steps = max(2, min(args.steps, 5))
-    h = measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, max(1, min(args.warmup, 2)), args.group_chunk, e2e=True, exact=False)
+    h = measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, max(1, min(args.warmup, 2)), args.wide_group_chunk, e2e=True, exact=False)
     recovered = all(int(np.nanargmin(h["res"]["L"][i])) == (7 + 13 * (rank * (S // world) + i)) % n_acc for i in range(len(h["res"]["m"])))
     recovered = all_sum(ctx, [float(recovered)])[0] == world
     h["batch"].close()
@@ -928,7 +929,7 @@ def sub_wide(ctx, peak, peak_source):
     pb = lib.Batch(g.db, *plain)
     if world > 1:
         pb.set_result_range(rank, 1)
-    pb.set_group_chunk(args.group_chunk)
+    pb.set_group_chunk(args.wide_group_chunk)
     pb.upload_coded(cs)
     with ctx.torch.cuda.stream(ctx.stream):
         run_batch(ctx, pb, kernel_mode=lib.KERNEL_GROUPED)
@@ -954,7 +955,7 @@ def sub_wide(ctx, peak, peak_source):
             "stages_ms": h["stages_ms"], "roofline": roofline(peak, algo_bytes, h["stages_ms"]["score_ms"], "k_score_grouped2",
                                                                {"peak_source": peak_source, "rows_gathered_per_launch": h["local_rows"]}),
             "true_accessions_recovered_on_all_ranks": bool(recovered), "guard_flagged_samples": h["guard_flagged_samples"],
-            "parity": parity, "parity_sample": "the first 3000 panel markers of sample 0 (x 20 000 accessions) through the same sharded coded path vs the CPU oracle: "
+            "group_chunk_rows": int(args.wide_group_chunk), "parity": parity, "parity_sample": "the first 3000 panel markers of sample 0 (x 20 000 accessions) through the same sharded coded path vs the CPU oracle: "
                                                "integers ==, scores rtol 1e-12"}
 
 

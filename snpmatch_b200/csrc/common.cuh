@@ -148,6 +148,7 @@ struct snpm_batch {
     int32_t chunk_rows = SNPM_CHUNK_ROWS, chunk_rows_req = SNPM_CHUNK_ROWS;   // position-order batches: rows per chunk of the fp64 kernel (snpm_batch_set_chunk_rows; latched at upload)
     int32_t gchunk = 320;              // rows per segment of the grouped kernels for the samples now on the device (latched at upload)
     int32_t gchunk_req = 320;          // snpm_batch_set_group_chunk: takes effect at the next grouped / coded upload
+    bool gchunk_set = false;           // false: coded uploads pick 320 rows, or 496 on panels wider than one 36-word slice (measured)
     // coded mode (snpm_batch_upload_coded): position-order markers + weight codes; grouped on the device (group_sort.cuh)
     bool coded = false;
     bool codes_packed = false;         // the three codes of a marker in one uint32 (snpm_batch_upload_coded32)
