@@ -1311,9 +1311,9 @@ int snpm_batch_epilogue(snpm_batch *b) {
             SNPM_KERNEL_CHECK();
             b->launches += 1;
         }
-        k_epilogue<<<unsigned(rn), 1024, 0, db->stream>>>(b->d_red.as<double>() + r0 * pitch, pitch, db->n_acc, 1, 0, 0.0,
-                                                        b->d_matches.as<int64_t>() + r0 * A, b->d_ninfo64.as<int64_t>() + r0 * A,
-                                                        b->d_prob.as<double>() + r0 * A, b->d_L.as<double>() + r0 * A, b->d_LR.as<double>() + r0 * A);
+        SNPM_CUDA(launch_epilogue(db->stream, rn, b->d_red.as<double>() + r0 * pitch, pitch, db->n_acc, 1, 0, 0.0,
+                                  b->d_matches.as<int64_t>() + r0 * A, b->d_ninfo64.as<int64_t>() + r0 * A,
+                                  b->d_prob.as<double>() + r0 * A, b->d_L.as<double>() + r0 * A, b->d_LR.as<double>() + r0 * A));
     }
     SNPM_KERNEL_CHECK();
     b->launches += 1;
@@ -1732,8 +1732,8 @@ int snpm_calculate_likelihoods(int device, const double *scores, const double *n
         e = cudaMemcpy(d_red.p, red.data(), (2 * A + 2) * 8, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) {
             double *o = d_out.as<double>();
-            k_epilogue<<<1, 1024>>>(d_red.as<double>(), 2 * int64_t(n_acc) + 2, int32_t(n_acc), 0, amin_is_calc ? 0 : 1, amin, nullptr, nullptr, o, o + A, o + 2 * A);
-            e = cudaGetLastError();
+            e = launch_epilogue(nullptr, 1, d_red.as<double>(), 2 * int64_t(n_acc) + 2, int32_t(n_acc), 0, amin_is_calc ? 0 : 1, amin, nullptr, nullptr, o, o + A, o + 2 * A);
+            if (e == cudaSuccess) e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         double viol = 0.0;
@@ -1906,8 +1906,8 @@ int snpm_panel_score(snpm_panel *p, const uint8_t *codes, int packed, int64_t S,
     if (like) {
         dim3 tgrid((A + 255) / 256, unsigned(S));
         k_onehot_totals<<<tgrid, 256, 0, st>>>(g.out_score, g.out_ninfo, ld_out, A, int32_t(K), p->d_red.as<double>());
-        k_epilogue<<<unsigned(S), 1024, 0, st>>>(p->d_red.as<double>(), 2 * int64_t(A) + 2, A, 1, 0, 0.0, p->d_m.as<int64_t>(), p->d_n64.as<int64_t>(),
-                                                 p->d_p.as<double>(), p->d_l.as<double>(), p->d_lr.as<double>());
+        SNPM_CUDA(launch_epilogue(st, S, p->d_red.as<double>(), 2 * int64_t(A) + 2, A, 1, 0, 0.0, p->d_m.as<int64_t>(), p->d_n64.as<int64_t>(),
+                                  p->d_p.as<double>(), p->d_l.as<double>(), p->d_lr.as<double>()));
         SNPM_KERNEL_CHECK();
     }
     // with one-hot weights the score IS the number of matches: the int32 accumulators go back as they are (pitched copy)
