@@ -295,6 +295,9 @@ class Genotype(object):
         return idx1[k1], idx2[k2]
 
     def close(self):
+        if getattr(self, "_many_batch", None) is not None:      # the batch of core.batch.genotype_many
+            self._many_batch.close()
+            self._many_batch = None
         if getattr(self, "db", None) is not None:
             self.db.close()
             self.db = None

@@ -887,6 +887,7 @@ def score_coded(db, cs, s_chrom_id=None, s_pos=None, wei=None, skip_db_hets=Fals
     own = batch is None
     b = batch if batch is not None else Batch(db, [0, 0], np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)))
     try:
+        b.set_track_pairs(False)                    # scores only: the marker indices of the pairs are not read back
         b.upload_coded(cs)
         b.run(skip_db_hets, kernel_mode=KERNEL_GROUPED)
         b.epilogue()
