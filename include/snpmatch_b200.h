@@ -200,8 +200,10 @@ int snpm_batch_guard_counts(snpm_batch *b, int32_t *counts);
  * reference adds chunk sums, so the chunk size is part of its floating-point summation order; takes effect at the next
  * position-order upload.  The popcount kernel (mode 1) keeps 1000-row chunks: its integer sums do not depend on them. */
 int snpm_batch_set_chunk_rows(snpm_batch *b, int32_t rows);
-/* rows per segment of the grouped kernel (16..1008, a multiple of 8, default 320); takes effect at the next grouped or coded
- * upload (the value is latched there: buffers are sized from it) */
+/* rows per segment of the grouped kernel (16..1008, a multiple of 8; coded uploads: a multiple of 16, at most 496); takes
+ * effect at the next grouped or coded upload (the value is latched there: buffers are sized from it).  Unless this is called,
+ * host-grouped uploads use 320 rows and coded uploads 320 rows on panels of up to 36 words per row (1152 accessions), 496 on
+ * wider ones (measured: DESIGN 4.2b) */
 int snpm_batch_set_group_chunk(snpm_batch *b, int32_t rows);
 int snpm_batch_destroy(snpm_batch *b);
 /* optional Genotyper.genotyper(filter_pos_ix=...) (snpmatch.py:211-216): keep only pairs whose
