@@ -1055,6 +1055,41 @@ static int batch_group_sort_t(snpm_batch *b) {
     KeyT *gkeys = b->d_gkeys.as<KeyT>();
     k_group_rank<KeyT><<<int(b->S), 1024, 0, st>>>(b->d_hash.as<unsigned long long>(), b->d_wtable.as<double>(), b->code_bits, b->d_slot_gid.as<uint16_t>(),
                                                    b->d_ngroups.as<int32_t>(), gkeys, b->d_gw.as<double4>(), b->d_group_overflow.as<int>());
+    int64_t n_max = 0, jcap1 = 1;
+    for (int64_t s = 0; s < b->S; ++s) {
+        n_max = std::max(n_max, b->h_off[size_t(s) + 1] - b->h_off[size_t(s)]);
+        jcap1 = std::max(jcap1, ceil_div64(b->h_off[size_t(s) + 1] - b->h_off[size_t(s)], b->gchunk));
+    }
+    // One kernel per sample (a CTA walks its sample's pairs twice, ~2.4 us per 1000 pairs) or five kernels over tiles of 2048 pairs
+    // (~0.07 ms of latency whatever the batch)?  Measured, group stage in ms, one kernel / tiles: 64 samples x 45 000 pairs 0.151 /
+    // 0.112; 128 x 22 500 (a 2-GPU rank) 0.108 / 0.114; 256 x 11 250: 0.110 / 0.129; 512 x 5 600: 0.136 / 0.164; 64 x 5 600: 0.048 / 0.062.
+    const char *force = getenv("SNPM_GROUP_KERNEL");                        // measurement / test switch: "tiled" or "sample"
+    const bool fits = n_max <= GP_MAX_PAIRS;
+    const bool want = force ? !strcmp(force, "sample") : (n_max <= 32768 || b->S >= 128);
+    if (fits && want) {
+        // every sample's counters fit shared memory: ids, offsets, placement, block words and segment costs in one kernel per sample
+        static bool sattr = false;
+        if (!sattr) {
+            SNPM_CUDA(cudaFuncSetAttribute(k_group_sample<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GP_SMEM)));
+            SNPM_CUDA(cudaFuncSetAttribute(k_group_sample<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GP_SMEM)));
+            sattr = true;
+        }
+        const size_t ncap = size_t(std::max<int64_t>(b->nseg_cap, 1));
+        int32_t *cost = reinterpret_cast<int32_t *>(b->d_blk_chg.as<unsigned long long>() + ncap * size_t(b->gchunk / GR_BLOCK));
+        int32_t *buckets = cost + ncap;
+        const size_t zbytes = ncap * (size_t(b->gchunk / GR_BLOCK) * 8 + 4) + size_t(SO_BUCKETS) * 4;
+        int2 *br = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(b->d_blk_chg.p) + ((zbytes + 7) & ~size_t(7)));
+        SNPM_CUDA(cudaMemsetAsync(b->d_blk_chg.p, 0, zbytes, st));
+        k_group_sample<KeyT><<<int(b->S), 32 * GP_WARPS, GP_SMEM, st>>>(
+            b->d_key_a.as<KeyT>(), b->d_hash.as<unsigned long long>(), b->d_slot_gid.as<uint16_t>(), b->d_ngroups.as<int32_t>(), b->d_gid.as<uint16_t>(),
+            b->d_pair_db_tmp.as<int32_t>(), b->d_pair_s_tmp.as<int32_t>(), b->d_pair_db.as<int32_t>(), b->track_pairs ? b->d_pair_s.as<int32_t>() : nullptr,
+            b->d_goff.as<int32_t>(), gkeys, mstart, b->d_seg_off.as<int32_t>(), b->gchunk, b->code_bits, b->d_blk_chg.as<unsigned long long>(), cost,
+            int32_t(jcap1), buckets, br, b->d_work_counter.as<unsigned int>());
+        k_order_place<<<int(b->S), 256, 0, st>>>(buckets, br, b->d_seg_off.as<int32_t>(), mstart, b->gchunk, b->d_seg_order.as<int4>());
+        SNPM_KERNEL_CHECK();
+        b->launches += 3;
+        return SNPM_OK;
+    }
     k_tile_ranges<<<(tiles + 255) / 256, 256, 0, st>>>(mstart, tsample, tfirst, tiles, range);
     k_group_ids<KeyT><<<tiles, RS_THREADS, 0, st>>>(b->d_key_a.as<KeyT>(), range, tsample, b->d_hash.as<unsigned long long>(), b->d_slot_gid.as<uint16_t>(),
                                                     b->d_ngroups.as<int32_t>(), b->d_gid.as<uint16_t>(), hist);

@@ -468,6 +468,63 @@ __device__ __forceinline__ int seg_cost_class(int cost, int base) {       // 0 =
 // units of SEG_COST_*, and from it the segment's bucket and its rank inside the bucket (seg_cost and bucket_cnt zeroed before).
 constexpr int SEG_COST_BLOCK = 8;         // one block of 16 rows without a weight change (~0.85 us of a team)
 constexpr int SEG_COST_CHANGE = 8;        // one class weight change: a piece of a block re-added under a mask + a counter read-out
+// the body of k_group_marks for sample s; s_off[0..ng] (shared memory, complete and synchronised): the group starts of the sample
+template <typename KeyT>
+__device__ __forceinline__ void group_marks_body(int s, const int32_t *s_off, int ng, const KeyT *__restrict__ gkeys,
+                                                 const int32_t *__restrict__ mstart, const int32_t *__restrict__ seg_off, int32_t chunk,
+                                                 int32_t code_bits, unsigned long long *__restrict__ blk_chg, int32_t *__restrict__ seg_cost,
+                                                 int32_t jcap, int32_t *__restrict__ bucket_cnt, int2 *__restrict__ seg_br) {
+    const int m = mstart[s + 1] - mstart[s];
+    const int seg0 = seg_off[s];
+    const int nseg_s = seg_off[s + 1] - seg0;
+    for (int j = threadIdx.x; j < nseg_s; j += blockDim.x) {
+        const int rows = min(chunk, m - j * chunk);
+        atomicAdd(seg_cost + seg0 + j, SEG_COST_BLOCK * ((rows + 15) / 16));
+    }
+    if (m > 0 && ng > 0) {
+        unsigned long long *out = blk_chg + size_t(seg0) * size_t(chunk / 16);
+        const KeyT *gk = gkeys + size_t(s) * GH_MAX_GROUPS;
+        const int b = code_bits;
+        for (int g = 1 + threadIdx.x; g < ng; g += blockDim.x) {       // the start of group g: which classes change there
+            const int r = s_off[g];
+            if (r >= m || s_off[g + 1] == r) continue;                 // (an id without pairs cannot occur; be safe)
+            const KeyT k1 = gk[g], k0 = gk[g - 1];
+            const int c1 = int(k1 >> (3 * b)) & 3, c0 = int(k0 >> (3 * b)) & 3;
+            unsigned long long bits = 0ull;
+            if (c1 != c0) {
+                bits = 1ull | (1ull << 16) | (1ull << 32);
+            } else {
+                const KeyT dd = k1 ^ k0;
+                const uint32_t fm = (1u << b) - 1u;
+#pragma unroll
+                for (int w = 0; w < 3; ++w)
+                    if ((uint32_t(dd >> gs_field_shift(c1, w, b)) & fm) != 0u) bits |= 1ull << (16 * w);
+            }
+            atomicOr(out + (r >> 4), bits << (r & 15));
+            atomicAdd(seg_cost + seg0 + r / chunk, SEG_COST_CHANGE * __popcll(bits));
+        }
+        const int nb = (m + 15) / 16;
+        for (int blk = threadIdx.x; blk < nb; blk += blockDim.x) {     // group of the block's first row: the last start <= 16 blk
+            int lo = 0, hi = ng;
+            const int r = 16 * blk;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= r) lo = mid; else hi = mid;
+            }
+            atomicOr(out + blk, (unsigned long long)(lo) << 48);
+        }
+    }
+    // once the costs are complete: every segment's bucket of the work order and its rank inside the bucket
+    __threadfence();
+    __syncthreads();
+    const int base = SEG_COST_BLOCK * (chunk / 16);
+    const int jdiv = (jcap + SO_LEVELS - 1) / SO_LEVELS;
+    for (int j = threadIdx.x; j < nseg_s; j += blockDim.x) {
+        const int bkt = seg_cost_class(__ldcg(seg_cost + seg0 + j), base) * SO_LEVELS + min(SO_LEVELS - 1, j / jdiv);
+        seg_br[seg0 + j] = make_int2(bkt, atomicAdd(bucket_cnt + bkt, 1));
+    }
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(1024) k_group_marks(const int32_t *__restrict__ goff, const KeyT *__restrict__ gkeys, const int32_t *__restrict__ ngroups,
                                                       const int32_t *__restrict__ mstart, const int32_t *__restrict__ seg_off, int32_t chunk,
@@ -476,62 +533,141 @@ __global__ void __launch_bounds__(1024) k_group_marks(const int32_t *__restrict_
     __shared__ int32_t s_off[GH_MAX_GROUPS + 1];
     const int s = blockIdx.x;
     const int ng = ngroups[s];
-    const int m = mstart[s + 1] - mstart[s];
-    const int seg0 = seg_off[s];
-    const int nseg_s = seg_off[s + 1] - seg0;
-    for (int j = threadIdx.x; j < nseg_s; j += blockDim.x) {
-        const int rows = min(chunk, m - j * chunk);
-        atomicAdd(seg_cost + seg0 + j, SEG_COST_BLOCK * ((rows + 15) / 16));
-    }
-    // once the costs are complete: every segment's bucket of the work order and its rank inside the bucket
-    auto rank_segments = [&]() {
-        __threadfence();
-        __syncthreads();
-        const int base = SEG_COST_BLOCK * (chunk / 16);
-        const int jdiv = (jcap + SO_LEVELS - 1) / SO_LEVELS;
-        for (int j = threadIdx.x; j < nseg_s; j += blockDim.x) {
-            const int bkt = seg_cost_class(__ldcg(seg_cost + seg0 + j), base) * SO_LEVELS + min(SO_LEVELS - 1, j / jdiv);
-            seg_br[seg0 + j] = make_int2(bkt, atomicAdd(bucket_cnt + bkt, 1));
-        }
-    };
-    if (m <= 0 || ng <= 0) {
-        rank_segments();
-        return;
-    }
     for (int g = threadIdx.x; g <= ng; g += blockDim.x) s_off[g] = goff[size_t(s) * (GH_MAX_GROUPS + 1) + g];
     __syncthreads();
-    unsigned long long *out = blk_chg + size_t(seg_off[s]) * size_t(chunk / 16);
-    const KeyT *gk = gkeys + size_t(s) * GH_MAX_GROUPS;
-    const int b = code_bits;
-    for (int g = 1 + threadIdx.x; g < ng; g += blockDim.x) {       // the start of group g: which classes change there
-        const int r = s_off[g];
-        if (r >= m || s_off[g + 1] == r) continue;                 // (an id without pairs cannot occur; be safe)
-        const KeyT k1 = gk[g], k0 = gk[g - 1];
-        const int c1 = int(k1 >> (3 * b)) & 3, c0 = int(k0 >> (3 * b)) & 3;
-        unsigned long long bits = 0ull;
-        if (c1 != c0) {
-            bits = 1ull | (1ull << 16) | (1ull << 32);
-        } else {
-            const KeyT dd = k1 ^ k0;
-            const uint32_t fm = (1u << b) - 1u;
+    group_marks_body<KeyT>(s, s_off, ng, gkeys, mstart, seg_off, chunk, code_bits, blk_chg, seg_cost, jcap, bucket_cnt, seg_br);
+}
+
+// ---- samples of up to GP_MAX_PAIRS matched pairs: ids, offsets, placement and block words in ONE kernel, one CTA per sample ----
+// What k_tile_ranges + k_group_ids + k_group_scan + k_group_place + k_group_marks do over tiles of 2048 pairs (five launches,
+// 0.07 ms of mostly latency per 2.9 M pairs) for a sample whose counters fit shared memory: warp w owns the w-th 32nd of the
+// sample's pairs (in pair order);
+//   pass 1   dense id of every pair (lookup in the sample's key table, four independent probes in flight per lane) -> gid[],
+//            counts per (warp, id) in shared memory (u16 [32][2048]; lanes with equal ids elect one: match.any);
+//   scan     per id: exclusive prefix of the counts over the warps (in place) and the id's total; block scan of the totals ->
+//            s_off[id] = first position of the group inside the sample (also written to goff);
+//   pass 2   every warp walks its pairs again in order: position = s_off[id] + (pairs of that id in earlier warps) + (earlier
+//            rounds of this warp) + (lower lanes of this round): a stable partition, deterministic; the panel row (and marker
+//            index) of the pair goes to its place;
+//   marks    group_marks_body: block words, segment costs, buckets of the work order, from s_off in shared memory.
+// Dynamic shared memory: GP_SMEM bytes.  Counts and prefixes are 16-bit: a sample must not hold more than GP_MAX_PAIRS pairs
+// (the caller falls back to the tiled kernels for batches with larger samples).
+constexpr int GP_WARPS = 32;
+constexpr int GP_MAX_PAIRS = 65535;
+constexpr size_t GP_SMEM = size_t(GP_WARPS) * GH_MAX_GROUPS * 2 + size_t(GH_MAX_GROUPS + 4) * 4;
+template <typename KeyT>
+__global__ void __launch_bounds__(32 * GP_WARPS) k_group_sample(
+        const KeyT *__restrict__ key, const unsigned long long *__restrict__ hash, const uint16_t *__restrict__ slot_gid,
+        const int32_t *__restrict__ ngroups, uint16_t *__restrict__ gid, const int32_t *__restrict__ pair_db_in,
+        const int32_t *__restrict__ pair_s_in, int32_t *__restrict__ pair_db_out, int32_t *__restrict__ pair_s_out,
+        int32_t *__restrict__ goff, const KeyT *__restrict__ gkeys, const int32_t *__restrict__ mstart,
+        const int32_t *__restrict__ seg_off, int32_t chunk, int32_t code_bits, unsigned long long *__restrict__ blk_chg,
+        int32_t *__restrict__ seg_cost, int32_t jcap, int32_t *__restrict__ bucket_cnt, int2 *__restrict__ seg_br,
+        unsigned int *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char gp_smem[];
+    __shared__ int s_warp[33];
+    uint16_t *whist = reinterpret_cast<uint16_t *>(gp_smem);                                  // [GP_WARPS][GH_MAX_GROUPS]
+    uint32_t *whist32 = reinterpret_cast<uint32_t *>(gp_smem);                                // the same, two ids per word
+    int32_t *s_off = reinterpret_cast<int32_t *>(gp_smem + size_t(GP_WARPS) * GH_MAX_GROUPS * 2);   // [GH_MAX_GROUPS + 1]
+    if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0u;      // the scoring kernel's ticket counter (it runs next on this stream)
+    const int s = blockIdx.x;
+    const int ng = ngroups[s];
+    const int b0 = mstart[s], m = min(mstart[s + 1] - b0, GP_MAX_PAIRS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int used_words = (ng + 1) / 2;                              // words of a warp's row that hold ids of this sample
+    for (int j = threadIdx.x; j < GP_WARPS * used_words; j += blockDim.x) whist32[size_t(j / used_words) * (GH_MAX_GROUPS / 2) + j % used_words] = 0u;
+    __syncthreads();
+    const int per = ((m + GP_WARPS - 1) / GP_WARPS + 31) & ~31;       // pairs per warp, whole rounds of 32
+    const int r0 = min(m, warp * per), r1 = min(m, r0 + per);
+    uint16_t *mine = whist + size_t(warp) * GH_MAX_GROUPS;
+    const unsigned long long *tab = hash + size_t(s) * GH_SLOTS;
+    const uint16_t *sg = slot_gid + size_t(s) * GH_SLOTS;
+    const uint32_t last_id = uint32_t(max(ng, 1) - 1);
+    constexpr int U = 8;
+    for (int base = r0; base < r1; base += 32 * U) {
+        unsigned long long want[U], cur[U];
+        uint32_t h[U];
 #pragma unroll
-            for (int w = 0; w < 3; ++w)
-                if ((uint32_t(dd >> gs_field_shift(c1, w, b)) & fm) != 0u) bits |= 1ull << (16 * w);
+        for (int u = 0; u < U; ++u) {
+            const int i = base + 32 * u + lane;
+            want[u] = i < r1 ? (unsigned long long)(key[b0 + i]) + 1ull : 0ull;
+            h[u] = gh_hash(want[u] - 1ull);
         }
-        atomicOr(out + (r >> 4), bits << (r & 15));
-        atomicAdd(seg_cost + seg0 + r / chunk, SEG_COST_CHANGE * __popcll(bits));
-    }
-    const int nb = (m + 15) / 16;
-    for (int blk = threadIdx.x; blk < nb; blk += blockDim.x) {     // group of the block's first row: the last start <= 16 blk
-        int lo = 0, hi = ng;
-        const int r = 16 * blk;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= r) lo = mid; else hi = mid;
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = want[u] ? __ldg(tab + h[u]) : 0ull;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            for (int probe = 1; probe < GH_SLOTS && cur[u] != want[u] && cur[u] != 0ull; ++probe) {
+                h[u] = (h[u] + 1u) & uint32_t(GH_SLOTS - 1);
+                cur[u] = __ldg(tab + h[u]);
+            }
         }
-        atomicOr(out + blk, (unsigned long long)(lo) << 48);
+        uint32_t g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) g[u] = want[u] ? min(uint32_t(__ldg(sg + h[u])), last_id) : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (base + 32 * u >= r1) break;                          // uniform: the whole round is past the warp's range
+            const int i = base + 32 * u + lane;
+            const bool on = i < r1;
+            if (on) gid[b0 + i] = uint16_t(g[u]);
+            const uint32_t peers = __match_any_sync(0xffffffffu, g[u]);
+            if (on && lane == __ffs(peers) - 1) mine[g[u]] = uint16_t(mine[g[u]] + __popc(peers));
+            __syncwarp();
+        }
     }
-    rank_segments();
+    __syncthreads();
+    // per id: prefix of the counts over the warps, total; thread -> ids 2 tid, 2 tid + 1 (one 32-bit word of every warp's row)
+    uint32_t tot0 = 0u, tot1 = 0u;
+    if (2 * int(threadIdx.x) < ng) {
+#pragma unroll 8
+        for (int w = 0; w < GP_WARPS; ++w) {
+            const uint32_t c = whist32[size_t(w) * (GH_MAX_GROUPS / 2) + threadIdx.x];
+            whist32[size_t(w) * (GH_MAX_GROUPS / 2) + threadIdx.x] = tot0 | (tot1 << 16);
+            tot0 += c & 0xffffu;
+            tot1 += c >> 16;
+        }
+    }
+    int all;
+    const int ex = block_excl_scan(int(tot0 + tot1), &all, s_warp);
+    int32_t *out = goff + size_t(s) * (GH_MAX_GROUPS + 1);
+    const int d0 = 2 * int(threadIdx.x);
+    if (d0 < ng) { s_off[d0] = ex; out[d0] = ex; }
+    if (d0 + 1 < ng) { s_off[d0 + 1] = ex + int(tot0); out[d0 + 1] = ex + int(tot0); }
+    if (threadIdx.x == 0) { s_off[ng] = all; out[ng] = all; }
+    __syncthreads();
+    // placement (the loads of U rounds are issued before the first round is ranked: a warp has nothing else to hide them behind)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int base = r0; base < r1; base += 32 * U) {
+        uint32_t g[U];
+        int32_t pdb[U], ps[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + 32 * u + lane;
+            const bool on = i < r1;
+            g[u] = on ? uint32_t(gid[b0 + i]) : 0xffffffffu;
+            pdb[u] = on ? pair_db_in[b0 + i] : 0;
+            ps[u] = on && pair_s_out ? pair_s_in[b0 + i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (base + 32 * u >= r1) break;                          // uniform
+            const bool on = g[u] != 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, g[u]);
+            uint32_t prior = 0u;
+            if (on) prior = mine[g[u]];
+            __syncwarp();
+            if (on && lane == __ffs(peers) - 1) mine[g[u]] = uint16_t(prior + __popc(peers));
+            __syncwarp();
+            if (on) {
+                const int o = b0 + s_off[g[u]] + int(prior) + __popc(peers & lt_mask);
+                pair_db_out[o] = pdb[u];
+                if (pair_s_out) pair_s_out[o] = ps[u];
+            }
+        }
+    }
+    __syncthreads();
+    group_marks_body<KeyT>(s, s_off, ng, gkeys, mstart, seg_off, chunk, code_bits, blk_chg, seg_cost, jcap, bucket_cnt, seg_br);
 }
 
 // One CTA per sample: exclusive scan of the bucket counts (every CTA for itself: 8 KB), then the entries of the sample's segments.

@@ -72,7 +72,10 @@ def _host_keys(cs):
 
 @pytest.mark.parametrize("n_acc", [1135, 33, 2100])
 @pytest.mark.parametrize("skip", [False, True])
-def test_coded_path_vs_oracle_and_exact_kernel(lib, n_acc, skip):
+@pytest.mark.parametrize("group_kernel", ["sample", "tiled"])
+def test_coded_path_vs_oracle_and_exact_kernel(lib, n_acc, skip, group_kernel, monkeypatch):
+    # both forms of the device grouping: one kernel per sample (counters in shared memory) and the kernels over tiles of pairs
+    monkeypatch.setenv("SNPM_GROUP_KERNEL", group_kernel)
     n_rows = 70000
     pos, regions = synth.panel_positions(n_rows)
     db = lib.Database(pos, regions, n_acc)
