@@ -72,13 +72,14 @@ def parse_args():
     ap.add_argument("--wide-group-chunk", type=int, default=496, help="the same for the 20 000-accession sub-record (the library's choice for wide panels)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl", "none"],
                     help="cross-GPU sum of the per-sample totals: p2p = one-shot reduce over peer memory (CUDA IPC over NVLink, flag barrier + "
-                         "pulls in one kernel), nccl = NCCL reduce-scatter, auto = what was measured faster (p2p on 2 GPUs; NCCL beyond, "
-                         "where it reduces inside the NVSwitch), none = timing experiment only (totals stay per rank)")
+                         "pulls in one kernel), nccl = NCCL reduce-scatter on its own stream, overlapped with the next step's join and "
+                         "grouping kernels, auto = what was measured faster (nccl: 0.558 against 0.589 ms per step with the peer kernel on "
+                         "2 GPUs, and NCCL reduces inside the NVSwitch beyond), none = timing experiment only (totals stay per rank)")
     ap.add_argument("--cpu-markers", type=int, default=0, help="bound the CPU sample (0 = one whole sample)")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on whatever cores it was started on (default: the cores next to its GPU)")
     args = ap.parse_args()
     if args.reduce == "auto":
-        args.reduce = "p2p" if int(os.environ.get("WORLD_SIZE", args.gpus)) == 2 else "nccl"
+        args.reduce = "nccl"
     return args
 
 
@@ -327,6 +328,22 @@ def reduce_totals(ctx, b):
         sharding.reduce_scatter_batch(b, ctx.dist, ctx.dev, ctx.rank, ctx.world)
 
 
+def reduce_begin(ctx, b):
+    """First half of reduce_totals: with NCCL the exchange is queued and nothing waits for it yet (sharding.reduce_scatter_begin);
+    the peer kernel (one kernel on the compute stream) and the single-GPU case complete here."""
+    from snpmatch_b200 import sharding
+    if ctx.world > 1 and ctx.args.reduce == "nccl":
+        return sharding.reduce_scatter_begin(b, ctx.dist, ctx.dev, ctx.rank, ctx.world)
+    reduce_totals(ctx, b)
+    return None
+
+
+def reduce_end(ctx, handle):
+    from snpmatch_b200 import sharding
+    if handle is not None:
+        sharding.reduce_scatter_end(handle)
+
+
 def run_batch(ctx, b, **kw):
     from snpmatch_b200 import sharding
     if ctx.world > 1 and ctx.args.reduce == "p2p":
@@ -340,17 +357,22 @@ def barrier(ctx):
     ctx.torch.cuda.synchronize()
 
 
-def timed_steps(ctx, step, wait, warmup, steps):
-    """W untimed + K timed steps on the compute stream: barrier + synchronize on both sides, CUDA events, max over ranks."""
+def timed_steps(ctx, step, wait, warmup, steps, flush=None):
+    """W untimed + K timed steps on the compute stream: barrier + synchronize on both sides, CUDA events, max over ranks.
+    flush: queues whatever a pipelined step leaves for the next one (inside the timed region)."""
     torch = ctx.torch
     for _ in range(warmup):
         step()
+    if flush:
+        flush()
     wait()
     barrier(ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ctx.stream)
     for _ in range(steps):
         step()
+    if flush:
+        flush()
     e1.record(ctx.stream)
     wait()
     barrier(ctx)
@@ -420,7 +442,39 @@ def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, wa
             run_batch(ctx, gb, kernel_mode=lib.KERNEL_GROUPED)
             reduce_totals(ctx, gb)
             gb.epilogue()
-        dev_ms = timed_steps(ctx, device_step, gb.wait, warmup, steps)
+        if world > 1 and ctx.args.reduce == "nccl":
+            # two resident batches alternate: the exchange of step k runs next to the join and grouping kernels of step k + 1,
+            # its epilogue follows them.  Every step's work, the last epilogue included, is inside the timed region.
+            gb2 = lib.Batch(db, h_off[:2] * 0, h_chr[:0], h_pos[:0], h_wei[:0])
+            own_share(gb2)
+            gb2.set_group_chunk(chunk)
+            gb2.set_track_pairs(False)
+            gb2.upload_coded(cs)
+            pair, pend, count = [gb, gb2], [None], [0]
+
+            def flush_step():
+                if pend[0] is not None:
+                    pb, ph = pend[0]
+                    reduce_end(ctx, ph)
+                    pb.epilogue()
+                    pend[0] = None
+
+            def piped_step():
+                b_ = pair[count[0] % 2]
+                count[0] += 1
+                run_batch(ctx, b_, kernel_mode=lib.KERNEL_GROUPED)
+                h_ = reduce_begin(ctx, b_)
+                flush_step()
+                pend[0] = (b_, h_)
+
+            def wait_both():
+                gb.wait()
+                gb2.wait()
+            dev_ms = timed_steps(ctx, piped_step, wait_both, warmup, steps, flush=flush_step)
+            gb2.close()
+            r["resident_loop"] = "two batches alternate; the NCCL reduce-scatter of a step overlaps the join and grouping kernels of the next"
+        else:
+            dev_ms = timed_steps(ctx, device_step, gb.wait, warmup, steps)
         stage = {}
         for _ in range(steps):                                   # one more pass that reads the library's own events each step
             device_step()
@@ -458,16 +512,30 @@ def measure_inbred(ctx, g, samples, positions, regions, r0, r1, n_acc, steps, wa
                 bt.upload_coded(cs)                              # 8 bytes per marker from pinned memory, on the batch's copy stream
                 own_share(bt)
 
+            pending = [None]
+
+            def complete_pending():
+                if pending[0] is not None:
+                    k_, b_, h_ = pending[0]
+                    reduce_end(ctx, h_)
+                    b_.epilogue()
+                    b_.fetch_async(outs[k_ % E2E_DEPTH])         # D2H of step k, queued behind its kernels
+                    pending[0] = None
+
             def launch(k):
                 b_ = batches[k % E2E_DEPTH]
                 run_batch(ctx, b_, kernel_mode=lib.KERNEL_GROUPED)
-                reduce_totals(ctx, b_)
-                b_.epilogue()
-                b_.fetch_async(outs[k % E2E_DEPTH])              # D2H of step k, queued behind its kernels
+                h_ = reduce_begin(ctx, b_)                       # NCCL: runs next to the join / grouping kernels of the step launched next
+                complete_pending()                               # the step before this one: its exchange is over by now
+                pending[0] = (k, b_, h_)
+                if h_ is None:
+                    complete_pending()                           # nothing to overlap (one GPU, peer kernel): finish at once
 
             flagged_all = []
 
             def finish(k):
+                if pending[0] is not None and pending[0][0] == k:
+                    complete_pending()
                 res = batches[k % E2E_DEPTH].fetch_wait()        # results of step k (this rank's share) are on the host
                 fl = np.flatnonzero(res["guard"])                # int(score) needs the reference's summation order (~1e-4 per sample)
                 if world == 1:
@@ -679,6 +747,7 @@ def run_b200_arm(args):
             "headline_kernel": "k_score_grouped2 (counting kernel, device-grouped pairs)",
             "guard_flagged_samples": h["guard_flagged_samples"], "clocks": clocks, "matched_markers_per_step": h["m_total"],
             "host_numa_binding_rank0": numa,
+            "resident_loop": h.get("resident_loop", "one batch; the steps run one after the other"),
         }
         x_ach_bytes = algo_bytes
         line["order_exact_fp64"] = {

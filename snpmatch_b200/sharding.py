@@ -181,6 +181,37 @@ def reduce_scatter_batch(batch, dist, device, rank, world):
     return out
 
 
+def reduce_scatter_begin(batch, dist, device, rank, world):
+    """reduce_scatter_batch in two halves, so that the exchange of step k runs next to the join and grouping kernels of step
+    k + 1 (they are latency bound and leave most SMs idle): this queues the NCCL reduce-scatter behind the kernels already on
+    the current stream and returns at once; nothing later on the current stream waits for it until reduce_scatter_end.  The
+    batch's reduce buffer must not be written (no run of the same batch) in between."""
+    import torch
+
+    class _Dev(object):
+        pass
+
+    ptr, n = batch.reduce_buffer()
+    assert n % world == 0 and batch.n_samples % world == 0, "samples must divide evenly over the ranks"
+    holder = _Dev()
+    holder.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    t = torch.as_tensor(holder, device=device)
+    out = getattr(batch, "_rs_out", None)
+    if out is None or out.numel() != n // world:
+        out = torch.empty(n // world, dtype=torch.float64, device=device)
+        batch._rs_out = out
+    work = dist.reduce_scatter_tensor(out, t, async_op=True)
+    return work, out, t.view(world, -1)[rank]
+
+
+def reduce_scatter_end(handle):
+    """The current stream waits for the exchange begun by reduce_scatter_begin and copies this rank's share of the sums into
+    the batch's buffer (the epilogue may follow)."""
+    work, out, mine = handle
+    work.wait()
+    mine.copy_(out)
+
+
 # ---- one-shot reduce over peer memory (csrc/grouped.cuh: k_reduce_peers) ------------------------------------------------
 # The same reduce-scatter as reduce_scatter_batch with no collective library on the path: every rank maps the reduce buffers of
 # all ranks (CUDA IPC over NVLink / NVSwitch) and ONE kernel per step does the cross-rank barrier (step-counter flags in peer
