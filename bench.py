@@ -24,9 +24,12 @@ Sub-records of the same line: the order-exact fp64 kernel, called genotypes, `cr
 (configs[4], STRONG scaling of a fixed batch), the tensor-core batched mode (configs[3]).
 
 N > 1 (torchrun): the panel is sharded by SNP-row ranges, every rank gets the slice of every sample's markers that can match
-its rows, per-GPU partial totals are summed with one reduce-scatter (one-shot pull over peer memory, or NCCL), then every rank
-finishes (truncation guard, epilogue) and reads back its share of the samples.  The headline batch grows with N (samples =
-N x --samples: "scaling": "weak"); the configs[4] sub-record keeps its batch fixed.
+its rows, per-GPU partial totals are summed with one reduce-scatter, then every rank finishes (truncation guard, epilogue) and
+reads back its share of the samples.  The exchange is NCCL's on its own stream, begun after a step's combine and waited for by
+that step's epilogue only: two resident batches alternate, so it runs next to the join and grouping kernels of the next step
+(every step's work, the last epilogue included, is inside the timed region; `--reduce p2p` is the hand-written one-kernel pull
+over peer memory, on the compute stream).  The headline batch grows with N (samples = N x --samples: "scaling": "weak"); the
+configs[4] sub-record keeps its batch fixed.  Every rank runs on the host cores next to its GPU.
 
 `--impl reference` times the reference's own CPU path (oracle port; one process per sample on all host cores, the way the
 reference is deployed) for the same metric and config.
