@@ -357,3 +357,16 @@ def test_coded_batch_host_side(built_lib):
     assert lib.code_markers(np.array([0, 1]), np.array([0]), np.array([7]), codes=np.full((1, 3), 9, np.uint16), wtable=np.ones(4)) is None
     one = lib.code_markers(np.array([0, 2]), np.array([-1, 2]), np.array([5, 6]), codes=np.array([[0, 1, 2], [3, 2, 1]], np.uint16), wtable=np.arange(4.0))
     assert int(one.chrom_pos[0] >> 27) == 31 and int(one.chrom_pos[1]) == (2 << 27 | 6) and one.codes32.tolist() == [0 | 1 << 10 | 2 << 20, 3 | 2 << 10 | 1 << 20]
+
+
+def test_bench_numa_binding_is_optional():
+    """bench.py binds a rank to the cores next to its GPU when the topology can be read, and says why not otherwise
+    (no NVML in the build container): never an exception, never an empty affinity mask."""
+    import os
+    import bench
+    before = os.sched_getaffinity(0)
+    info = bench.bind_to_gpu_numa_node(0)
+    assert isinstance(info, dict) and "bound" in info
+    assert info["bound"] or "why" in info
+    assert len(os.sched_getaffinity(0)) >= 1
+    os.sched_setaffinity(0, before)
