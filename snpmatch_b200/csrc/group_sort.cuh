@@ -14,6 +14,9 @@
 //      (k_group_place: offsets from the tile counts, ranks in pair order, scatter) — deterministic,
 //   5. mark, per block of 16 grouped rows, where each class weight changes and which group the block starts in
 //      (k_group_marks), from the group table alone.
+// Steps 3-5 run either as kernels over tiles of 2048 pairs (k_group_ids, k_group_scan, k_group_place, k_group_marks: any sample
+// size) or, for samples of up to 65 535 pairs, as ONE kernel with a CTA per sample that keeps the sample's counters in shared
+// memory (k_group_sample); api.cu picks by batch shape.  Both produce the same order.
 // A radix sort over the ~30-bit key did the same in three scatter passes of key + permutation (0.20 ms for 2.9 M pairs against
 // a 0.27 ms scoring kernel: scattered 4-byte stores are the cost, one LSU transaction each); the dense ids need one pass over
 // one array.  Replaces the per-sample work of Genotyper.genotyper's chunk loop set-up (snpmatch.py:218-227) in the grouped
