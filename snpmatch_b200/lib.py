@@ -883,7 +883,9 @@ def score_coded(db, cs, s_chrom_id=None, s_pos=None, wei=None, skip_db_hets=Fals
     """Throughput scoring of many samples (Genotyper.genotyper per sample, snpmatch.py:207-233) from CodedSamples: join,
     grouping by weight triple and counting all on the device.  Returns the dict of Batch.fetch() plus "rescored".  Samples
     whose truncated score would depend on the reference's summation order (guard_counts > 0) are re-scored with the
-    order-exact fp64 kernel when their position-order arrays (s_chrom_id, s_pos, wei of the whole batch) are given."""
+    order-exact fp64 kernel when their position-order arrays (s_chrom_id, s_pos, wei of the whole batch) are given (else from
+    the codes: table[codes] gives the weights back bit for bit).  Pass a `batch` to keep its device buffers between calls: a
+    fresh batch costs 0.3 - 1 s of cudaMalloc / cudaFree per call on a loaded device (core.batch.genotype_many keeps one)."""
     own = batch is None
     b = batch if batch is not None else Batch(db, [0, 0], np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)))
     try:
