@@ -19,7 +19,8 @@ def factorize(labels):
     # neighbours compared as integer words (a fixed-width unicode array is 4 bytes per character): several times faster than
     # NumPy's string comparison
     if labels.dtype.kind == "U" and labels.dtype.itemsize >= 4:
-        words = np.ascontiguousarray(labels).view(np.uint32).reshape(n, -1)
+        wide = labels.dtype.itemsize % 8 == 0                      # an even number of characters: compare two at a time
+        words = np.ascontiguousarray(labels).view(np.uint64 if wide else np.uint32).reshape(n, -1)
         differ = words[1:, 0] != words[:-1, 0]
         for k in range(1, words.shape[1]):
             differ |= words[1:, k] != words[:-1, k]
